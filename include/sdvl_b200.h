@@ -1,0 +1,236 @@
+/*
+ * sdvl_b200.h — C-ABI of the B200-native SDVL tracking front-end.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * The reference (JdeRobot/slam-SDVL) has no FFI; its boundary for this path is
+ * four C++ classes.  Each entry point below names the reference interface it
+ * replaces (file:line relative to the reference tree):
+ *
+ *   sdvlb_frame_create / _detect / _level / _corners
+ *        -> Frame::Frame, Frame::CreatePyramid, Frame::CreateCorners,
+ *           Frame::GetPyramid, Frame::GetCorners
+ *           (frame.h:45,58-60,139; frame.cc:34-56,114-131;
+ *            extra/fast_detector.cc:58-175)
+ *   sdvlb_image_align
+ *        -> ImageAlign::ComputePose / GetError
+ *           (image_align.h:41,43; image_align.cc:46-267)
+ *   sdvlb_search_points
+ *        -> Matcher::SearchPoint (matcher.h:45-46; matcher.cc:45-121) as it is
+ *           driven by FeatureAlign::SelectPoints/ProjectPoint
+ *           (feature_align.cc:88-150,323-339)
+ *   sdvlb_track_batch
+ *        -> one SDVL::ProcessFrame front half (sdvl.cc:59,185-193) for many
+ *           independent sequences in one submission (no reference equivalent;
+ *           it is how one GPU is kept busy).
+ *
+ * All functions return 0 on success or a negative sdvlb_status.  Nothing
+ * throws across this boundary.  There is NO CPU fallback: if no CUDA device is
+ * usable sdvlb_ctx_create fails with SDVLB_ERR_CUDA.
+ *
+ * Poses are world->camera (frame.h:90) packed as double[7] =
+ * {q0(w), q1(x), q2(y), q3(z), tx, ty, tz} (extra/se3.h:76-77).
+ */
+#ifndef SDVL_B200_H_
+#define SDVL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sdvlb_status {
+  SDVLB_OK = 0,
+  SDVLB_ERR_CUDA = -1,        /* CUDA runtime error (see sdvlb_last_error) */
+  SDVLB_ERR_ARG = -2,         /* invalid argument / unsupported parameter */
+  SDVLB_ERR_NOMEM = -3,
+  SDVLB_ERR_OVERFLOW = -4,    /* a fixed device-side capacity was exceeded */
+  SDVLB_ERR_STATE = -5        /* call order violated (e.g. corners not detected) */
+} sdvlb_status;
+
+/* Tunables of the path; defaults are config.cc:55-85 of the reference. */
+typedef struct sdvlb_params {
+  int32_t pyramid_levels;      /* kPyramidLevels_   5  */
+  int32_t cell_size;           /* kCellSize_        32 (only 32 supported) */
+  int32_t max_matches;         /* kMaxMatches_      150 */
+  int32_t max_align_level;     /* kMaxAlignLevel_   4  */
+  int32_t min_align_level;     /* kMinAlignLevel_   2  */
+  int32_t max_img_align_its;   /* kMaxImgAlignIts_  30 */
+  int32_t align_patch_size;    /* kAlignPatchSize_  4  (only 4 supported) */
+  int32_t patch_size;          /* kPatchSize_       8  (only 8 supported) */
+  int32_t max_align_its;       /* kMaxAlignIts_     10 */
+  int32_t search_size;         /* kSearchSize_      6  */
+  int32_t max_fast_levels;     /* kMaxFastLevels_   3  */
+  int32_t fast_threshold;      /* kFastThreshold_   10 */
+  int32_t num_features;        /* kNumFeatures_     1000 */
+  int32_t max_failed;          /* kMaxFailed_       15 */
+  int32_t max_optim_pose_its;  /* kMaxOptimPoseIts_ 10 */
+  int32_t max_ransac_points;   /* kMaxRansacPoints_ 5  */
+  int32_t max_ransac_its;      /* kMaxRansacIts_    100 */
+  int32_t min_matches;         /* kMinMatches_      20 */
+  double inlier_error_threshold; /* kInlierErrorThreshold_ 2.0 */
+} sdvlb_params;
+
+/* Pinhole intrinsics without distortion (camera.h:119-126). */
+typedef struct sdvlb_camera {
+  double width, height, fx, fy, u0, v0;
+} sdvlb_camera;
+
+/* Fills *p with the reference defaults (config.cc:55-85). */
+void sdvlb_params_default(sdvlb_params* p);
+
+typedef struct sdvlb_ctx sdvlb_ctx;     /* device, stream, scratch; one per host thread */
+typedef struct sdvlb_frame sdvlb_frame; /* device pyramid + corners, pinned host mirror */
+
+/* ---- context ------------------------------------------------------------ */
+int sdvlb_ctx_create(int device, const sdvlb_params* params, const sdvlb_camera* cam,
+                     sdvlb_ctx** out);
+int sdvlb_ctx_destroy(sdvlb_ctx* ctx);
+/* Blocks until everything submitted on this context has finished. */
+int sdvlb_ctx_sync(sdvlb_ctx* ctx);
+/* The cudaStream_t every kernel of this context is launched on (for external
+ * CUDA-event timing). */
+void* sdvlb_ctx_stream(sdvlb_ctx* ctx);
+const char* sdvlb_last_error(void);
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
+int sdvlb_host_alloc(void** p, uint64_t bytes);
+int sdvlb_host_free(void* p);
+/* Device buffers for callers that keep inputs resident in HBM. */
+int sdvlb_dev_alloc(sdvlb_ctx* ctx, void** p, uint64_t bytes);
+int sdvlb_dev_free(sdvlb_ctx* ctx, void* p);
+int sdvlb_dev_upload(sdvlb_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+
+/* ---- per-kernel timing (CUDA events on the context stream) -------------- */
+enum {
+  SDVLB_K_PYRAMID = 0, SDVLB_K_FAST = 1, SDVLB_K_SELECT = 2, SDVLB_K_ALIGN = 3,
+  SDVLB_K_SEARCH = 4, SDVLB_K_COUNT = 5
+};
+int sdvlb_timing_enable(sdvlb_ctx* ctx, int on);
+/* Accumulated milliseconds and launch counts per kernel since the last reset.
+ * Synchronises the context. */
+int sdvlb_timing_read(sdvlb_ctx* ctx, double ms[SDVLB_K_COUNT], int64_t launches[SDVLB_K_COUNT],
+                      int reset);
+
+/* ---- Frame -------------------------------------------------------------- */
+/* Frame::Frame(camera, detector, img, corners): uploads `img` (u8, `stride`
+ * bytes per row), builds the pyramid on the device, optionally runs FAST with
+ * budget `nfeatures` (Config::NumFeatures()), mirrors levels and corners into
+ * pinned host memory, and synchronises.  `img` may be pageable. */
+int sdvlb_frame_create(sdvlb_ctx* ctx, const uint8_t* img, int w, int h, int stride,
+                       int want_corners, int nfeatures, sdvlb_frame** out);
+/* Frame::CreateCorners(levels, nfeatures) (frame.cc:122-131). Replaces corners. */
+int sdvlb_frame_detect(sdvlb_ctx* ctx, sdvlb_frame* f, int nfeatures);
+/* Frame::GetPyramid()[l]: continuous u8 host mirror (stride == *w). */
+int sdvlb_frame_level(const sdvlb_frame* f, int level, const uint8_t** data, int* w, int* h);
+/* Frame::GetCorners(): n triplets (x, y, level) in level coordinates, in the
+ * reference's order; `score` holds cv::KeyPoint::response (not kept by the
+ * reference, exposed for parity checks). */
+int sdvlb_frame_corners(const sdvlb_frame* f, const int32_t** xyl, const int32_t** score, int* n);
+int sdvlb_frame_destroy(sdvlb_ctx* ctx, sdvlb_frame* f);
+
+/* ---- ImageAlign --------------------------------------------------------- */
+/* One feature of frame1 (frame1->GetFeatures() order). */
+typedef struct sdvlb_align_feat {
+  double px[2];    /* Feature::GetPosition(), level-0 pixels */
+  double v[3];     /* Feature::GetVector(), unit bearing */
+  double depth;    /* |Point::GetPosition() - frame1 world position| (image_align.cc:159,234) */
+  int32_t valid;   /* GetPoint() != nullptr && !GetPoint()->ToDelete() (image_align.cc:154,229) */
+  int32_t pad_;
+} sdvlb_align_feat;
+
+/* One Gauss-Newton iteration as seen by ImageAlign::Optimize (image_align.cc:91-124). */
+typedef struct sdvlb_gn_iter {
+  int32_t level;
+  int32_t iter;
+  int32_t n_meas;     /* n_meas_ after ComputeResiduals */
+  int32_t flags;      /* bit0: iteration rejected (rollback), bit1: NaN solve, bit2: n_meas==0 */
+  double T_in[7];     /* relative pose T (frame2 <- frame1) the residuals were evaluated at */
+  double H[36];       /* row-major, full symmetric */
+  double b[6];        /* Jres_ */
+  double x[6];        /* H.ldlt().solve(Jres_) */
+  double chi2;        /* chi2 / n_meas */
+} sdvlb_gn_iter;
+
+/* Optional teacher forcing, used by parity tests: iteration k is evaluated at
+ * T[k] and level l runs exactly iters[l] iterations; the kernel's own
+ * accept/rollback decisions are bypassed. */
+typedef struct sdvlb_gn_forced {
+  const double* T;        /* n_total x 7 */
+  const int32_t* iters;   /* indexed by pyramid level, pyramid_levels entries */
+  int32_t n_total;
+  int32_t pad_;
+} sdvlb_gn_forced;
+
+/* ImageAlign::ComputePose(frame1=ref, frame2=cur, fast).
+ * T_ref: pose of ref; T_cur: in = prior pose of cur, out = aligned pose
+ * (frame2->SetPose).  *n_tracked = return value (n_meas_/patch_area),
+ * *error = GetError().  n == 0 returns 0 tracked and leaves T_cur untouched
+ * (image_align.cc:55-58).  trace (optional) receives up to trace_cap
+ * iterations; *trace_n = number that ran. */
+int sdvlb_image_align(sdvlb_ctx* ctx, const sdvlb_frame* ref, sdvlb_frame* cur,
+                      const sdvlb_align_feat* feats, int n, const double T_ref[7],
+                      double T_cur[7], int fast, int* n_tracked, double* error,
+                      sdvlb_gn_iter* trace, int trace_cap, int* trace_n,
+                      const sdvlb_gn_forced* forced);
+
+/* ---- Matcher::SearchPoint batch ---------------------------------------- */
+enum { SDVLB_CAND_FIXED = 1, SDVLB_CAND_PROJECT = 2 };
+typedef struct sdvlb_candidate {
+  const sdvlb_frame* ref_frame; /* feature->GetFrame(): frame of the point's init feature */
+  double ref_T[7];     /* ref_frame->GetPose() */
+  double ref_px[2];    /* feature->GetPosition() */
+  double ref_v[3];     /* feature->GetVector() */
+  double idepth;       /* point->GetInverseDepth() */
+  double idepth_std;   /* point->GetStd() */
+  double px[2];        /* in: *px (predicted position) unless SDVLB_CAND_PROJECT */
+  double pos[3];       /* point->GetPosition(), used with SDVLB_CAND_PROJECT */
+  int32_t ref_level;   /* feature->GetLevel() */
+  int32_t flags;       /* SDVLB_CAND_FIXED = point->IsFixed();
+                          SDVLB_CAND_PROJECT = run FeatureAlign::ProjectPoint first */
+} sdvlb_candidate;
+
+enum { SDVLB_MATCH_UNSEEN = 0, SDVLB_MATCH_NOT_FOUND = 1, SDVLB_MATCH_FOUND = 2 };
+typedef struct sdvlb_match {
+  double px[2];        /* refined position, level-0 pixels (valid when FOUND) */
+  double proj[2];      /* projected position (SDVLB_CAND_PROJECT), else copy of input px */
+  int32_t level;       /* search level (valid when FOUND) */
+  int32_t status;      /* SDVLB_MATCH_* ; UNSEEN only with SDVLB_CAND_PROJECT */
+  int32_t zmssd;       /* best ZMSSD score, -1 if no corner in range */
+  int32_t n_in_range;  /* corners that passed GetCornersInRange */
+} sdvlb_match;
+
+/* Evaluates Matcher::SearchPoint for n candidates against `cur` (which must
+ * have corners).  T_cur == NULL uses the pose the last sdvlb_image_align left
+ * on `cur` in device memory. */
+int sdvlb_search_points(sdvlb_ctx* ctx, const sdvlb_frame* cur, const sdvlb_candidate* cands,
+                        int n, const double T_cur[7], sdvlb_match* out);
+
+/* ---- batched front half of ProcessFrame -------------------------------- */
+typedef struct sdvlb_track_job {
+  const uint8_t* image;     /* w*h u8, continuous; host (pinned preferred) or device */
+  int32_t image_on_device;
+  int32_t want_corners;
+  int32_t nfeatures;
+  int32_t n_feats;
+  int32_t n_cands;
+  int32_t n_tracked;        /* out */
+  const sdvlb_frame* ref;   /* last frame (NULL: only build the frame) */
+  sdvlb_frame* cur;         /* out: new frame handle (created by the call) */
+  const sdvlb_align_feat* feats;
+  const sdvlb_candidate* cands;
+  sdvlb_match* matches;     /* out, n_cands entries */
+  double T_ref[7];
+  double T_cur[7];          /* in: prior, out: ImageAlign result */
+  double error;             /* out */
+} sdvlb_track_job;
+
+/* For every job: upload image, pyramid, FAST, ImageAlign(ref,cur), then
+ * SearchPoint for all candidates at the aligned pose — submitted as batched
+ * launches with a single synchronisation at the end.  `mirror` != 0 also
+ * copies pyramids and corners to the pinned host mirrors of the new frames. */
+int sdvlb_track_batch(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, int mirror);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SDVL_B200_H_ */

@@ -1,0 +1,141 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE: import only from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs)."""
+import ctypes as C
+import importlib.util
+import os
+import subprocess
+import sys
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+
+
+def _pkg():
+    name = "slam_sdvl_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(_ROOT, "slam-sdvl_b200", "__init__.py"),
+                                                  submodule_search_locations=[os.path.join(_ROOT, "slam-sdvl_b200")])
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+abi = importlib.import_module(_pkg().__name__ + ".abi")
+ptr = abi.ptr
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "-j8"])
+    return os.path.join(_HERE, "liboracle.so")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_pyramid.restype = C.c_int64
+        _LIB.orc_tracker_create.restype = C.c_void_p
+        _LIB.orc_tracker_run.restype = C.c_double
+    return _LIB
+
+
+def pyramid(img, levels):
+    h, w = img.shape
+    img = np.ascontiguousarray(img)
+    n = lib().orc_pyramid(ptr(img), w, h, levels, None)
+    out = np.zeros(n, np.uint8)
+    lib().orc_pyramid(ptr(img), w, h, levels, ptr(out))
+    res, off = [], 0
+    for _ in range(levels):
+        res.append(out[off:off + w * h].reshape(h, w))
+        off += w * h
+        w //= 2
+        h //= 2
+    return res
+
+
+def fast_roi(img, x0, y0, cols, rows, thr=10):
+    img = np.ascontiguousarray(img)
+    cap = cols * rows
+    xy = np.zeros((cap, 2), np.int32)
+    sc = np.zeros(cap, np.int32)
+    base = img.ctypes.data + y0 * img.shape[1] + x0
+    n = lib().orc_fast_roi(C.c_void_p(base), img.shape[1], cols, rows, thr, ptr(xy), ptr(sc), cap)
+    return xy[:n].copy(), sc[:n].copy()
+
+
+def retain_best(xyr, keep):
+    a = np.ascontiguousarray(xyr, np.float32).copy()
+    n = lib().orc_retain_best(ptr(a), a.shape[0], keep)
+    return a[:n]
+
+
+def detect(params, img, nfeatures):
+    img = np.ascontiguousarray(img)
+    h, w = img.shape
+    cap = 16 * max(nfeatures, 64) + 4096
+    xyl = np.zeros((cap, 3), np.int32)
+    sc = np.zeros(cap, np.int32)
+    n = lib().orc_detect(C.byref(params), ptr(img), w, h, nfeatures, ptr(xyl), ptr(sc), cap)
+    assert n <= cap
+    return xyl[:n].copy(), sc[:n].copy()
+
+
+def image_align(params, cam, ref_img, cur_img, feats, pos3, T_ref, T_cur, fast=False, trace_cap=256):
+    ref_img = np.ascontiguousarray(ref_img)
+    cur_img = np.ascontiguousarray(cur_img)
+    h, w = ref_img.shape
+    feats = np.ascontiguousarray(feats)
+    pos3 = np.ascontiguousarray(pos3, np.float64)
+    T_ref = np.ascontiguousarray(T_ref, np.float64)
+    T_out = np.array(T_cur, np.float64)
+    trace = np.zeros(trace_cap, abi.GN_ITER_DT)
+    nt, tn, err = C.c_int(0), C.c_int(0), C.c_double(0)
+    lib().orc_image_align(C.byref(params), C.byref(cam), ptr(ref_img), ptr(cur_img), w, h, ptr(feats), ptr(pos3),
+                          feats.shape[0], ptr(T_ref), ptr(T_out), int(fast), C.byref(nt), C.byref(err), ptr(trace),
+                          trace_cap, C.byref(tn))
+    return T_out, nt.value, err.value, trace[:min(tn.value, trace_cap)].copy()
+
+
+def search_points(params, cam, cur_img, T_cur, ref_imgs, cands):
+    cur_img = np.ascontiguousarray(cur_img)
+    h, w = cur_img.shape
+    refs = [np.ascontiguousarray(r) for r in ref_imgs]
+    arr = (C.c_void_p * len(refs))(*[r.ctypes.data for r in refs])
+    cands = np.ascontiguousarray(cands)
+    out = np.zeros(cands.shape[0], abi.MATCH_DT)
+    T_cur = np.ascontiguousarray(T_cur, np.float64)
+    rc = lib().orc_search_points(C.byref(params), C.byref(cam), ptr(cur_img), w, h, ptr(T_cur), arr, len(refs),
+                                 ptr(cands), cands.shape[0], ptr(out))
+    assert rc == 0
+    return out
+
+
+class Tracker:
+    def __init__(self, params, cam, plane, max_points, kf_every):
+        plane = np.ascontiguousarray(plane, np.float64)
+        self.h = lib().orc_tracker_create(C.byref(params), C.byref(cam), ptr(plane), max_points, kf_every)
+
+    def run(self, imgs, gt_poses):
+        imgs = np.ascontiguousarray(imgs)
+        n, h, w = imgs.shape
+        gt = np.ascontiguousarray(gt_poses, np.float64)
+        est = np.zeros((n, 7))
+        stats = np.zeros((n, 8), np.int32)
+        sec = lib().orc_tracker_run(C.c_void_p(self.h), ptr(imgs), n, w, h, ptr(gt), ptr(est), ptr(stats))
+        return est, stats, sec
+
+    def close(self):
+        if self.h:
+            lib().orc_tracker_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        self.close()

@@ -1,0 +1,75 @@
+"""ctypes mirrors of the POD structs in include/sdvl_b200.h (shared by the product binding, the synthetic world
+and the oracle's test binding)."""
+import ctypes as C
+import numpy as np
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "pyramid_levels", "cell_size", "max_matches", "max_align_level", "min_align_level", "max_img_align_its",
+        "align_patch_size", "patch_size", "max_align_its", "search_size", "max_fast_levels", "fast_threshold",
+        "num_features", "max_failed", "max_optim_pose_its", "max_ransac_points", "max_ransac_its", "min_matches")] + \
+        [("inlier_error_threshold", C.c_double)]
+
+
+class Camera(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("width", "height", "fx", "fy", "u0", "v0")]
+
+
+class AlignFeat(C.Structure):
+    _fields_ = [("px", C.c_double * 2), ("v", C.c_double * 3), ("depth", C.c_double), ("valid", C.c_int32),
+                ("pad_", C.c_int32)]
+
+
+class GnIter(C.Structure):
+    _fields_ = [("level", C.c_int32), ("iter", C.c_int32), ("n_meas", C.c_int32), ("flags", C.c_int32),
+                ("T_in", C.c_double * 7), ("H", C.c_double * 36), ("b", C.c_double * 6), ("x", C.c_double * 6),
+                ("chi2", C.c_double)]
+
+
+class GnForced(C.Structure):
+    _fields_ = [("T", C.c_void_p), ("iters", C.c_void_p), ("n_total", C.c_int32), ("pad_", C.c_int32)]
+
+
+class Candidate(C.Structure):
+    _fields_ = [("ref_frame", C.c_void_p), ("ref_T", C.c_double * 7), ("ref_px", C.c_double * 2),
+                ("ref_v", C.c_double * 3), ("idepth", C.c_double), ("idepth_std", C.c_double),
+                ("px", C.c_double * 2), ("pos", C.c_double * 3), ("ref_level", C.c_int32), ("flags", C.c_int32)]
+
+
+class Match(C.Structure):
+    _fields_ = [("px", C.c_double * 2), ("proj", C.c_double * 2), ("level", C.c_int32), ("status", C.c_int32),
+                ("zmssd", C.c_int32), ("n_in_range", C.c_int32)]
+
+
+CAND_FIXED, CAND_PROJECT = 1, 2
+MATCH_UNSEEN, MATCH_NOT_FOUND, MATCH_FOUND = 0, 1, 2
+
+# numpy views of the same layouts (for bulk construction)
+ALIGN_FEAT_DT = np.dtype([("px", "f8", 2), ("v", "f8", 3), ("depth", "f8"), ("valid", "i4"), ("pad_", "i4")])
+GN_ITER_DT = np.dtype([("level", "i4"), ("iter", "i4"), ("n_meas", "i4"), ("flags", "i4"), ("T_in", "f8", 7),
+                       ("H", "f8", 36), ("b", "f8", 6), ("x", "f8", 6), ("chi2", "f8")])
+CANDIDATE_DT = np.dtype([("ref_frame", "u8"), ("ref_T", "f8", 7), ("ref_px", "f8", 2), ("ref_v", "f8", 3),
+                         ("idepth", "f8"), ("idepth_std", "f8"), ("px", "f8", 2), ("pos", "f8", 3),
+                         ("ref_level", "i4"), ("flags", "i4")])
+MATCH_DT = np.dtype([("px", "f8", 2), ("proj", "f8", 2), ("level", "i4"), ("status", "i4"), ("zmssd", "i4"),
+                     ("n_in_range", "i4")])
+assert ALIGN_FEAT_DT.itemsize == C.sizeof(AlignFeat)
+assert GN_ITER_DT.itemsize == C.sizeof(GnIter)
+assert CANDIDATE_DT.itemsize == C.sizeof(Candidate)
+assert MATCH_DT.itemsize == C.sizeof(Match)
+
+
+def default_params():
+    """config.cc:55-85 of the reference."""
+    p = Params()
+    (p.pyramid_levels, p.cell_size, p.max_matches, p.max_align_level, p.min_align_level, p.max_img_align_its,
+     p.align_patch_size, p.patch_size, p.max_align_its, p.search_size, p.max_fast_levels, p.fast_threshold,
+     p.num_features, p.max_failed, p.max_optim_pose_its, p.max_ransac_points, p.max_ransac_its, p.min_matches) = \
+        (5, 32, 150, 4, 2, 30, 4, 8, 10, 6, 3, 10, 1000, 15, 10, 5, 100, 20)
+    p.inlier_error_threshold = 2.0
+    return p
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
