@@ -1,0 +1,164 @@
+"""ctypes binding of libsdvl_b200.so (the C-ABI in include/sdvl_b200.h).
+
+There is no CPU fallback: importing works anywhere, but `load()` raises if the CUDA library has not been built, and
+`Context()` raises if no CUDA device is usable."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+from . import abi
+from .abi import ptr
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdvl_b200.so")
+_LIB = None
+
+K_NAMES = ("pyramid", "fast", "select", "align", "search")
+
+
+class SdvlbError(RuntimeError):
+    pass
+
+
+class TrackJob(C.Structure):
+    _fields_ = [("image", C.c_void_p), ("image_on_device", C.c_int32), ("want_corners", C.c_int32),
+                ("nfeatures", C.c_int32), ("n_feats", C.c_int32), ("n_cands", C.c_int32), ("n_tracked", C.c_int32),
+                ("ref", C.c_void_p), ("cur", C.c_void_p), ("feats", C.c_void_p), ("cands", C.c_void_p),
+                ("matches", C.c_void_p), ("T_ref", C.c_double * 7), ("T_cur", C.c_double * 7), ("error", C.c_double)]
+
+
+def build(verbose=False):
+    """Compiles the sm_100a kernels + C-ABI in-tree (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise SdvlbError(f"{LIB_PATH} is missing: build it with slam_sdvl_b200.binding.build() "
+                             "(there is no CPU fallback for this path)")
+        L = C.CDLL(LIB_PATH)
+        L.sdvlb_last_error.restype = C.c_char_p
+        L.sdvlb_ctx_stream.restype = C.c_void_p
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise SdvlbError(f"sdvlb status {rc}: {load().sdvlb_last_error().decode()}")
+
+
+EXPORTS = [
+    "sdvlb_params_default", "sdvlb_ctx_create", "sdvlb_ctx_destroy", "sdvlb_ctx_sync", "sdvlb_ctx_stream",
+    "sdvlb_last_error", "sdvlb_host_alloc", "sdvlb_host_free", "sdvlb_dev_alloc", "sdvlb_dev_free",
+    "sdvlb_dev_upload", "sdvlb_timing_enable", "sdvlb_timing_read", "sdvlb_frame_create", "sdvlb_frame_detect",
+    "sdvlb_frame_level", "sdvlb_frame_corners", "sdvlb_frame_destroy", "sdvlb_image_align", "sdvlb_search_points",
+    "sdvlb_track_batch",
+]
+
+
+class Frame:
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    def level(self, l):
+        data, w, h = C.c_void_p(), C.c_int(), C.c_int()
+        _check(load().sdvlb_frame_level(C.c_void_p(self.h), l, C.byref(data), C.byref(w), C.byref(h)))
+        buf = (C.c_uint8 * (w.value * h.value)).from_address(data.value)
+        return np.frombuffer(buf, np.uint8).reshape(h.value, w.value).copy()
+
+    def corners(self):
+        xyl, sc, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        _check(load().sdvlb_frame_corners(C.c_void_p(self.h), C.byref(xyl), C.byref(sc), C.byref(n)))
+        if n.value == 0:
+            return np.zeros((0, 3), np.int32), np.zeros(0, np.int32)
+        a = np.frombuffer((C.c_int32 * (3 * n.value)).from_address(xyl.value), np.int32).reshape(-1, 3).copy()
+        s = np.frombuffer((C.c_int32 * n.value).from_address(sc.value), np.int32).copy()
+        return a, s
+
+    def detect(self, nfeatures):
+        _check(load().sdvlb_frame_detect(C.c_void_p(self.ctx.h), C.c_void_p(self.h), nfeatures))
+
+    def destroy(self):
+        if self.h:
+            load().sdvlb_frame_destroy(C.c_void_p(self.ctx.h), C.c_void_p(self.h))
+            self.h = None
+
+
+class Context:
+    def __init__(self, params, cam, device=0):
+        self.params, self.cam = params, cam
+        h = C.c_void_p()
+        _check(load().sdvlb_ctx_create(device, C.byref(params), C.byref(cam), C.byref(h)))
+        self.h = h.value
+        self.w, self.hh = int(cam.width), int(cam.height)
+
+    def close(self):
+        if self.h:
+            load().sdvlb_ctx_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def stream(self):
+        return load().sdvlb_ctx_stream(C.c_void_p(self.h))
+
+    def sync(self):
+        _check(load().sdvlb_ctx_sync(C.c_void_p(self.h)))
+
+    def timing(self, on):
+        load().sdvlb_timing_enable(C.c_void_p(self.h), int(on))
+
+    def timing_read(self, reset=True):
+        ms = (C.c_double * 5)()
+        n = (C.c_int64 * 5)()
+        _check(load().sdvlb_timing_read(C.c_void_p(self.h), ms, n, int(reset)))
+        return {k: (ms[i], n[i]) for i, k in enumerate(K_NAMES)}
+
+    def frame(self, img, corners=True, nfeatures=None):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        out = C.c_void_p()
+        nf = self.params.num_features if nfeatures is None else nfeatures
+        _check(load().sdvlb_frame_create(C.c_void_p(self.h), ptr(img), w, h, w, int(corners), nf, C.byref(out)))
+        return Frame(self, out.value)
+
+    def image_align(self, ref, cur, feats, T_ref, T_cur, fast=False, trace_cap=256, forced=None):
+        feats = np.ascontiguousarray(feats)
+        assert feats.dtype == abi.ALIGN_FEAT_DT
+        T_ref = np.ascontiguousarray(T_ref, np.float64)
+        T_out = np.array(T_cur, np.float64)
+        trace = np.zeros(max(trace_cap, 1), abi.GN_ITER_DT)
+        nt, tn, err = C.c_int(0), C.c_int(0), C.c_double(0)
+        fptr = None
+        keep = None
+        if forced is not None:
+            fT = np.ascontiguousarray(forced[0], np.float64)
+            fi = np.ascontiguousarray(forced[1], np.int32)
+            keep = (fT, fi)
+            fs = abi.GnForced(fT.ctypes.data, fi.ctypes.data, fT.shape[0], 0)
+            fptr = C.byref(fs)
+        _check(load().sdvlb_image_align(C.c_void_p(self.h), C.c_void_p(ref.h), C.c_void_p(cur.h), ptr(feats),
+                                        feats.shape[0], ptr(T_ref), ptr(T_out), int(fast), C.byref(nt),
+                                        C.byref(err), ptr(trace) if trace_cap else None, trace_cap, C.byref(tn), fptr))
+        return T_out, nt.value, err.value, trace[:min(tn.value, trace_cap)].copy()
+
+    def search_points(self, cur, cands, T_cur):
+        cands = np.ascontiguousarray(cands)
+        assert cands.dtype == abi.CANDIDATE_DT
+        out = np.zeros(cands.shape[0], abi.MATCH_DT)
+        Tp = None
+        if T_cur is not None:
+            T_cur = np.ascontiguousarray(T_cur, np.float64)
+            Tp = ptr(T_cur)
+        _check(load().sdvlb_search_points(C.c_void_p(self.h), C.c_void_p(cur.h), ptr(cands), cands.shape[0], Tp,
+                                          ptr(out)))
+        return out
+
+    def track_batch(self, jobs, mirror=1):
+        """jobs: ctypes array of TrackJob."""
+        _check(load().sdvlb_track_batch(C.c_void_p(self.h), jobs, len(jobs), self.w, self.hh, mirror))

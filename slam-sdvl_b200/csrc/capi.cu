@@ -1,0 +1,758 @@
+// capi.cu — implementation of the C-ABI in include/sdvl_b200.h: contexts, frame storage pool, pinned staging,
+// batched submission of the K1..K4 kernels and per-kernel CUDA-event timing.  No CPU fallback: every entry point
+// either runs the sm_100a kernels or fails with a negative status.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+// ---- kernel launchers (other translation units)
+cudaError_t sdvlb_launch_pyramid(const FrameDev* d_frames, int n_frames, const PyrGeom& g, cudaStream_t stream);
+void sdvlb_fast_plan(const PyrGeom& g, const sdvlb_params& p, int nfeatures, int corner_cap, FastPlan* plan);
+cudaError_t sdvlb_launch_fast_cells(const FrameDev* d_frames, int n_frames, const FastPlan& plan, uint32_t* cell_kp,
+                                    int32_t* cell_cnt, cudaStream_t stream);
+cudaError_t sdvlb_launch_fast_select(const FrameDev* d_frames, int n_frames, const FastPlan& plan, uint32_t* cell_kp,
+                                     int32_t* cell_cnt, uint32_t* level_kp, int32_t* level_cnt, int32_t* frame_ticket,
+                                     int32_t* overflow_flag, cudaStream_t stream);
+cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, const PyrGeom& g, const DevParams& dp,
+                               cudaStream_t stream);
+cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const FrameDev* d_frames, sdvlb_match* d_out,
+                                const PyrGeom& g, const DevParams& dp, cudaStream_t stream);
+
+// ---- error reporting
+static thread_local std::string g_last_error;
+int sdvlb_set_cuda_error(cudaError_t e, const char* expr, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", int(e), cudaGetErrorString(e), file, line, expr);
+  g_last_error = buf;
+  return SDVLB_ERR_CUDA;
+}
+int sdvlb_set_error(int code, const char* msg) {
+  g_last_error = msg;
+  return code;
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Arena {   // bump allocator over a (pinned host, device) buffer pair with identical layout
+  uint8_t* h = nullptr;
+  uint8_t* d = nullptr;
+  size_t cap = 0, used = 0;
+  size_t take(size_t bytes) {
+    const size_t off = align_up(used, 256);
+    used = off + bytes;
+    return off;
+  }
+};
+
+struct TimerSlot { cudaEvent_t a, b; int kind; };
+
+}  // namespace
+
+struct sdvlb_frame {
+  sdvlb_ctx* ctx = nullptr;
+  FrameDev dev{};
+  uint8_t* d_block = nullptr;
+  uint8_t* h_block = nullptr;    // pinned mirror with the same layout
+  size_t off_xyl = 0, off_score = 0, off_cnt = 0, off_pose = 0, block_bytes = 0;
+  bool has_corners = false;
+  bool pyr_mirrored = false;
+  int corners_mirrored = -1;     // number of corners valid in the host mirror, -1 = unknown
+  int n_corners = 0;
+};
+
+struct sdvlb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  sdvlb_params params{};
+  sdvlb_camera cam{};
+  PyrGeom geom{};
+  DevParams dp{};
+  int w = 0, h = 0;
+  int corner_cap = 0;
+  int corner_copy = 0;           // corners copied eagerly to the host mirror
+  std::vector<sdvlb_frame*> pool;
+  std::vector<FastPlan> plans;   // one per nfeatures budget seen
+  // FAST scratch (sized for `fast_frames` frames)
+  int fast_frames = 0;
+  uint32_t* cell_kp = nullptr;
+  int32_t* cell_cnt = nullptr;
+  uint32_t* level_kp = nullptr;
+  int32_t* level_cnt = nullptr;
+  int32_t* frame_ticket = nullptr;
+  int32_t* overflow_flag = nullptr;   // device
+  size_t level_kp_total = 0;
+  // staging
+  Arena in, out;                 // host->device descriptors, device->host results
+  uint8_t* scratch = nullptr;    // device-only scratch for ImageAlign caches
+  size_t scratch_cap = 0;
+  // timing
+  bool timing = false;
+  std::vector<TimerSlot> timers;
+  size_t timers_used = 0;
+  double t_ms[SDVLB_K_COUNT] = {0, 0, 0, 0, 0};
+  int64_t t_launches[SDVLB_K_COUNT] = {0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int ensure_arena(Arena* a, size_t bytes, bool need_device) {
+  if (bytes <= a->cap) return 0;
+  const size_t ncap = align_up(std::max(bytes, a->cap * 2), 1 << 20);
+  if (a->h) cudaFreeHost(a->h);
+  if (a->d) cudaFree(a->d);
+  a->h = nullptr; a->d = nullptr; a->cap = 0;
+  SDVLB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&a->h), ncap, cudaHostAllocDefault));
+  if (need_device) SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&a->d), ncap));
+  a->cap = ncap;
+  return 0;
+}
+
+int ensure_scratch(sdvlb_ctx* c, size_t bytes) {
+  if (bytes <= c->scratch_cap) return 0;
+  const size_t ncap = align_up(std::max(bytes, c->scratch_cap * 2), 1 << 20);
+  if (c->scratch) cudaFree(c->scratch);
+  c->scratch = nullptr; c->scratch_cap = 0;
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->scratch), ncap));
+  c->scratch_cap = ncap;
+  return 0;
+}
+
+int ensure_fast_scratch(sdvlb_ctx* c, int n_frames) {
+  if (n_frames <= c->fast_frames) return 0;
+  const int nf = std::max(n_frames, c->fast_frames * 2);
+  cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt); cudaFree(c->frame_ticket);
+  c->cell_kp = nullptr; c->cell_cnt = nullptr; c->level_kp = nullptr; c->level_cnt = nullptr; c->frame_ticket = nullptr;
+  c->fast_frames = 0;
+  const size_t cells = size_t(c->geom.total_cells) * nf;
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->cell_kp), cells * SDVLB_CELL_CAP * sizeof(uint32_t)));
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->cell_cnt), cells * sizeof(int32_t)));
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->level_kp), c->level_kp_total * nf * sizeof(uint32_t)));
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->level_cnt), size_t(nf) * SDVLB_MAX_LEVELS * sizeof(int32_t)));
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->frame_ticket), size_t(nf) * sizeof(int32_t)));
+  SDVLB_CUDA_TRY(cudaMemsetAsync(c->frame_ticket, 0, size_t(nf) * sizeof(int32_t), c->stream));
+  c->fast_frames = nf;
+  return 0;
+}
+
+int frame_alloc(sdvlb_ctx* c, sdvlb_frame** out) {
+  if (!c->pool.empty()) {
+    sdvlb_frame* f = c->pool.back();
+    c->pool.pop_back();
+    f->has_corners = false; f->pyr_mirrored = false; f->corners_mirrored = -1; f->n_corners = 0;
+    *out = f;
+    return 0;
+  }
+  sdvlb_frame* f = new sdvlb_frame;
+  f->ctx = c;
+  size_t off = align_up(size_t(c->geom.total) + 256, 256);
+  f->off_xyl = off;   off = align_up(off + size_t(c->corner_cap) * 3 * sizeof(int32_t), 256);
+  f->off_score = off; off = align_up(off + size_t(c->corner_cap) * sizeof(int32_t), 256);
+  f->off_cnt = off;   off = align_up(off + 64, 256);
+  f->off_pose = off;  off = align_up(off + 7 * sizeof(double), 256);
+  f->block_bytes = off;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&f->d_block), f->block_bytes);
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&f->h_block), f->block_bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    if (f->d_block) cudaFree(f->d_block);
+    delete f;
+    return sdvlb_set_cuda_error(e, "frame_alloc", __FILE__, __LINE__);
+  }
+  f->dev.pyr = f->d_block;
+  f->dev.xyl = reinterpret_cast<int32_t*>(f->d_block + f->off_xyl);
+  f->dev.score = reinterpret_cast<int32_t*>(f->d_block + f->off_score);
+  f->dev.n_corners = reinterpret_cast<int32_t*>(f->d_block + f->off_cnt);
+  f->dev.pose = reinterpret_cast<double*>(f->d_block + f->off_pose);
+  *out = f;
+  return 0;
+}
+
+void frame_release(sdvlb_ctx* c, sdvlb_frame* f) { c->pool.push_back(f); }
+
+// ---- timing helpers
+void timer_begin(sdvlb_ctx* c, int kind) {
+  if (!c->timing) return;
+  if (c->timers_used == c->timers.size()) {
+    TimerSlot s;
+    cudaEventCreate(&s.a);
+    cudaEventCreate(&s.b);
+    c->timers.push_back(s);
+  }
+  TimerSlot& s = c->timers[c->timers_used];
+  s.kind = kind;
+  cudaEventRecord(s.a, c->stream);
+}
+void timer_end(sdvlb_ctx* c) {
+  if (!c->timing) return;
+  cudaEventRecord(c->timers[c->timers_used].b, c->stream);
+  c->timers_used++;
+}
+void timer_collect(sdvlb_ctx* c) {   // stream must be idle
+  for (size_t i = 0; i < c->timers_used; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->timers[i].a, c->timers[i].b) == cudaSuccess) {
+      c->t_ms[c->timers[i].kind] += ms;
+      c->t_launches[c->timers[i].kind] += 1;
+    }
+  }
+  c->timers_used = 0;
+}
+
+void build_geom(const sdvlb_params& p, int w, int h, PyrGeom* g) {
+  memset(g, 0, sizeof(*g));
+  g->levels = p.pyramid_levels;
+  int cw = w, ch = h;
+  size_t off = 0;
+  for (int l = 0; l < p.pyramid_levels; l++) {
+    g->w[l] = cw; g->h[l] = ch;
+    g->off[l] = int(off);
+    off = align_up(off + size_t(cw) * ch, 256);
+    cw /= 2; ch /= 2;   // frame.cc:119
+  }
+  g->total = int(off);
+  int cells = 0;
+  for (int l = 0; l < p.max_fast_levels; l++) {
+    g->wcells[l] = int(std::ceil(double(g->w[l]) / double(p.cell_size)));   // fast_detector.cc:72-73
+    g->hcells[l] = int(std::ceil(double(g->h[l]) / double(p.cell_size)));
+    g->cell_off[l] = cells;
+    cells += g->wcells[l] * g->hcells[l];
+  }
+  g->total_cells = cells;
+}
+
+const FastPlan* get_plan(sdvlb_ctx* c, int nfeatures) {
+  for (const FastPlan& p : c->plans)
+    if (p.nfeatures == nfeatures) return &p;
+  c->plans.reserve(16);
+  FastPlan p;
+  sdvlb_fast_plan(c->geom, c->params, nfeatures, c->corner_cap, &p);
+  c->plans.push_back(p);
+  return &c->plans.back();
+}
+
+}  // namespace
+
+extern "C" {
+
+void sdvlb_params_default(sdvlb_params* p) {   // config.cc:55-85
+  p->pyramid_levels = 5; p->cell_size = 32; p->max_matches = 150; p->max_align_level = 4; p->min_align_level = 2;
+  p->max_img_align_its = 30; p->align_patch_size = 4; p->patch_size = 8; p->max_align_its = 10; p->search_size = 6;
+  p->max_fast_levels = 3; p->fast_threshold = 10; p->num_features = 1000; p->max_failed = 15;
+  p->max_optim_pose_its = 10; p->max_ransac_points = 5; p->max_ransac_its = 100; p->min_matches = 20;
+  p->inlier_error_threshold = 2.0;
+}
+
+const char* sdvlb_last_error(void) { return g_last_error.c_str(); }
+
+int sdvlb_ctx_create(int device, const sdvlb_params* params, const sdvlb_camera* cam, sdvlb_ctx** out) {
+  if (!params || !cam || !out) return sdvlb_set_error(SDVLB_ERR_ARG, "null argument");
+  const sdvlb_params& p = *params;
+  const int w = int(cam->width), h = int(cam->height);
+  if (p.cell_size != SDVLB_CELL || p.align_patch_size != 4 || p.patch_size != 8)
+    return sdvlb_set_error(SDVLB_ERR_ARG, "only cell_size 32, align_patch_size 4, patch_size 8 are supported");
+  if (p.pyramid_levels < 1 || p.pyramid_levels > SDVLB_MAX_LEVELS || p.max_fast_levels < 1 ||
+      p.max_fast_levels > p.pyramid_levels || p.max_align_level >= p.pyramid_levels || p.min_align_level < 0 ||
+      p.min_align_level > p.max_align_level)
+    return sdvlb_set_error(SDVLB_ERR_ARG, "inconsistent pyramid / level parameters");
+  if (w < 16 || h < 16 || w > SDVLB_MAX_DIM || h > SDVLB_MAX_DIM)
+    return sdvlb_set_error(SDVLB_ERR_ARG, "image size must be within [16, 2048]");
+  int ndev = 0;
+  SDVLB_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return sdvlb_set_error(SDVLB_ERR_CUDA, "no such CUDA device");
+  SDVLB_CUDA_TRY(cudaSetDevice(device));
+  sdvlb_ctx* c = new sdvlb_ctx;
+  c->device = device;
+  c->params = p;
+  c->cam = *cam;
+  c->dp.p = p;
+  c->dp.cam = *cam;
+  c->w = w; c->h = h;
+  build_geom(p, w, h, &c->geom);
+  c->corner_cap = std::max(8192, 8 * p.num_features);
+  c->corner_copy = std::min(c->corner_cap, std::max(2048, 2 * p.num_features));
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return sdvlb_set_cuda_error(e, "cudaStreamCreate", __FILE__, __LINE__); }
+  e = cudaMalloc(reinterpret_cast<void**>(&c->overflow_flag), 64);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->overflow_flag, 0, 64, c->stream);
+  if (e != cudaSuccess) { delete c; return sdvlb_set_cuda_error(e, "overflow flag", __FILE__, __LINE__); }
+  const FastPlan* plan = get_plan(c, p.num_features);
+  c->level_kp_total = size_t(plan->args.level_kp_total);
+  *out = c;
+  return 0;
+}
+
+int sdvlb_ctx_destroy(sdvlb_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (sdvlb_frame* f : c->pool) { cudaFree(f->d_block); cudaFreeHost(f->h_block); delete f; }
+  cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
+  cudaFree(c->frame_ticket); cudaFree(c->overflow_flag); cudaFree(c->scratch);
+  if (c->in.h) cudaFreeHost(c->in.h);
+  if (c->in.d) cudaFree(c->in.d);
+  if (c->out.h) cudaFreeHost(c->out.h);
+  if (c->out.d) cudaFree(c->out.d);
+  for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int sdvlb_ctx_sync(sdvlb_ctx* c) {
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+void* sdvlb_ctx_stream(sdvlb_ctx* c) { return c->stream; }
+
+int sdvlb_host_alloc(void** p, uint64_t bytes) { SDVLB_CUDA_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault)); return 0; }
+int sdvlb_host_free(void* p) { SDVLB_CUDA_TRY(cudaFreeHost(p)); return 0; }
+int sdvlb_dev_alloc(sdvlb_ctx* c, void** p, uint64_t bytes) {
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  SDVLB_CUDA_TRY(cudaMalloc(p, bytes));
+  return 0;
+}
+int sdvlb_dev_free(sdvlb_ctx* c, void* p) {
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  SDVLB_CUDA_TRY(cudaFree(p));
+  return 0;
+}
+int sdvlb_dev_upload(sdvlb_ctx* c, void* dst, const void* src, uint64_t bytes) {
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int sdvlb_timing_enable(sdvlb_ctx* c, int on) { c->timing = on != 0; return 0; }
+int sdvlb_timing_read(sdvlb_ctx* c, double ms[SDVLB_K_COUNT], int64_t launches[SDVLB_K_COUNT], int reset) {
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  timer_collect(c);
+  for (int i = 0; i < SDVLB_K_COUNT; i++) {
+    if (ms) ms[i] = c->t_ms[i];
+    if (launches) launches[i] = c->t_launches[i];
+    if (reset) { c->t_ms[i] = 0; c->t_launches[i] = 0; }
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+// ================================================================================================ batched core
+namespace {
+
+struct BatchOut {   // per-job results in the `out` arena
+  double pose[7];
+  double error;
+  int32_t info[2];
+  int32_t pad[2];
+};
+
+// Submits pyramid (+FAST) (+align) (+search) for n jobs and synchronises once.
+int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_iter* trace, int trace_cap,
+              int* trace_n, const sdvlb_gn_forced* forced, bool build_frames, int fast = 0) {
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  const PyrGeom& g = c->geom;
+  const size_t img_bytes = size_t(c->w) * c->h;
+
+  // ---- frames
+  if (build_frames) {
+    for (int i = 0; i < n; i++) {
+      sdvlb_frame* f = nullptr;
+      const int rc = frame_alloc(c, &f);
+      if (rc) { for (int k = 0; k < i; k++) { frame_release(c, jobs[k].cur); jobs[k].cur = nullptr; } return rc; }
+      jobs[i].cur = f;
+    }
+  }
+  int n_detect = 0, n_align = 0, n_cands = 0, n_feats = 0, nfeatures = -1;
+  for (int i = 0; i < n; i++) {
+    if (build_frames && jobs[i].want_corners) {
+      n_detect++;
+      if (nfeatures < 0) nfeatures = jobs[i].nfeatures;
+      else if (nfeatures != jobs[i].nfeatures) return sdvlb_set_error(SDVLB_ERR_ARG, "mixed nfeatures in one batch");
+    }
+    if (jobs[i].ref) { n_align++; n_feats += jobs[i].n_feats; }
+    if (jobs[i].n_cands < 0 || jobs[i].n_feats < 0) return sdvlb_set_error(SDVLB_ERR_ARG, "negative count");
+    n_cands += jobs[i].n_cands;
+  }
+
+  // ---- stage inputs
+  Arena& in = c->in;
+  Arena& out = c->out;
+  in.used = 0; out.used = 0;
+  const size_t need_in = 4096 + size_t(n) * (2 * sizeof(FrameDev) + sizeof(AlignJobDev) + 512) +
+                         size_t(n_feats) * sizeof(sdvlb_align_feat) + size_t(n_cands) * sizeof(SearchCandDev) +
+                         (forced ? size_t(forced->n_total) * 56 + 512 : 0) + 32 * 256;
+  const size_t need_out = 4096 + size_t(n) * sizeof(BatchOut) + size_t(n_cands) * sizeof(sdvlb_match) +
+                          size_t(trace ? trace_cap : 0) * sizeof(sdvlb_gn_iter) + 8 * 256;
+  int rc = ensure_arena(&in, need_in, true);
+  if (rc) return rc;
+  rc = ensure_arena(&out, need_out, true);
+  if (rc) return rc;
+  size_t scratch_need = 0;
+  for (int i = 0; i < n; i++)
+    if (jobs[i].ref) scratch_need += align_up(size_t(jobs[i].n_feats) * (48 * 4 + 18 * 8 + 4) + 1024, 256);
+  rc = ensure_scratch(c, scratch_need);
+  if (rc) return rc;
+
+  const size_t o_frames = in.take(size_t(n) * sizeof(FrameDev));
+  const size_t o_detect = in.take(size_t(std::max(n_detect, 1)) * sizeof(FrameDev));
+  const size_t o_align = in.take(size_t(std::max(n_align, 1)) * sizeof(AlignJobDev));
+  const size_t o_feats = in.take(size_t(std::max(n_feats, 1)) * sizeof(sdvlb_align_feat));
+  const size_t o_cands = in.take(size_t(std::max(n_cands, 1)) * sizeof(SearchCandDev));
+  size_t o_forced_T = 0, o_forced_it = 0;
+  if (forced) {
+    o_forced_T = in.take(size_t(forced->n_total) * 7 * sizeof(double));
+    o_forced_it = in.take(SDVLB_MAX_LEVELS * sizeof(int32_t));
+    memcpy(in.h + o_forced_T, forced->T, size_t(forced->n_total) * 7 * sizeof(double));
+    memset(in.h + o_forced_it, 0, SDVLB_MAX_LEVELS * sizeof(int32_t));
+    memcpy(in.h + o_forced_it, forced->iters, size_t(c->params.pyramid_levels) * sizeof(int32_t));
+  }
+  const size_t o_prior = in.take(size_t(n) * 7 * sizeof(double));
+  for (int i = 0; i < n; i++) memcpy(in.h + o_prior + size_t(i) * 56, jobs[i].T_cur, 56);
+  const size_t o_res = out.take(size_t(n) * sizeof(BatchOut));
+  const size_t o_match = out.take(size_t(std::max(n_cands, 1)) * sizeof(sdvlb_match));
+  const size_t o_trace = trace ? out.take(size_t(trace_cap) * sizeof(sdvlb_gn_iter)) : 0;
+  const size_t o_flag = out.take(64);
+
+  FrameDev* hf = reinterpret_cast<FrameDev*>(in.h + o_frames);
+  FrameDev* hd = reinterpret_cast<FrameDev*>(in.h + o_detect);
+  AlignJobDev* ha = reinterpret_cast<AlignJobDev*>(in.h + o_align);
+  sdvlb_align_feat* hfe = reinterpret_cast<sdvlb_align_feat*>(in.h + o_feats);
+  SearchCandDev* hc = reinterpret_cast<SearchCandDev*>(in.h + o_cands);
+  int di = 0, ai = 0, fi = 0, cidx = 0;
+  size_t sc_off = 0;
+  for (int i = 0; i < n; i++) {
+    sdvlb_track_job& j = jobs[i];
+    if (!j.cur) return sdvlb_set_error(SDVLB_ERR_ARG, "job without current frame");
+    hf[i] = j.cur->dev;
+    if (build_frames && j.want_corners) hd[di++] = j.cur->dev;
+    if (j.ref) {
+      AlignJobDev& a = ha[ai];
+      memset(&a, 0, sizeof(a));
+      a.ref = j.ref->dev;
+      a.cur = j.cur->dev;
+      a.feats = reinterpret_cast<const sdvlb_align_feat*>(in.d + o_feats) + fi;
+      a.n = j.n_feats;
+      a.fast = fast;
+      memcpy(a.T_ref, j.T_ref, sizeof(a.T_ref));
+      memcpy(a.T_cur, j.T_cur, sizeof(a.T_cur));
+      BatchOut* dres = reinterpret_cast<BatchOut*>(out.d + o_res) + i;
+      a.out_pose = dres->pose;
+      a.out_info = dres->info;
+      a.out_error = &dres->error;
+      a.trace = (trace && ai == 0) ? reinterpret_cast<sdvlb_gn_iter*>(out.d + o_trace) : nullptr;
+      a.trace_cap = trace ? trace_cap : 0;
+      if (forced && ai == 0) {
+        a.forced_T = reinterpret_cast<const double*>(in.d + o_forced_T);
+        a.forced_iters = reinterpret_cast<const int32_t*>(in.d + o_forced_it);
+        a.forced_n = forced->n_total;
+      }
+      uint8_t* sc = c->scratch + sc_off;
+      a.sc_d = reinterpret_cast<double*>(sc);
+      a.sc_f = reinterpret_cast<float*>(sc + align_up(size_t(j.n_feats) * 18 * 8, 256));
+      a.sc_flags = reinterpret_cast<int32_t*>(sc + align_up(size_t(j.n_feats) * 18 * 8, 256) +
+                                              align_up(size_t(j.n_feats) * 48 * 4, 256));
+      sc_off += align_up(size_t(j.n_feats) * (48 * 4 + 18 * 8 + 4) + 1024, 256);
+      if (j.n_feats > 0) memcpy(hfe + fi, j.feats, size_t(j.n_feats) * sizeof(sdvlb_align_feat));
+      fi += j.n_feats;
+      ai++;
+    }
+    for (int k = 0; k < j.n_cands; k++) {
+      const sdvlb_candidate& s = j.cands[k];
+      SearchCandDev& d = hc[cidx++];
+      if (!s.ref_frame) return sdvlb_set_error(SDVLB_ERR_ARG, "candidate without reference frame");
+      d.ref_pyr = s.ref_frame->dev.pyr;
+      memcpy(d.ref_T, s.ref_T, sizeof(d.ref_T));
+      d.ref_px[0] = s.ref_px[0]; d.ref_px[1] = s.ref_px[1];
+      d.ref_v[0] = s.ref_v[0]; d.ref_v[1] = s.ref_v[1]; d.ref_v[2] = s.ref_v[2];
+      d.idepth = s.idepth; d.idepth_std = s.idepth_std;
+      d.px[0] = s.px[0]; d.px[1] = s.px[1];
+      d.pos[0] = s.pos[0]; d.pos[1] = s.pos[1]; d.pos[2] = s.pos[2];
+      d.ref_level = s.ref_level;
+      d.flags = s.flags;
+      d.cur_index = i;
+      d.pad_ = 0;
+      if (s.ref_level < 0 || s.ref_level >= c->params.pyramid_levels)
+        return sdvlb_set_error(SDVLB_ERR_ARG, "candidate level out of range");
+    }
+  }
+
+  // ---- H2D
+  if (build_frames)
+    for (int i = 0; i < n; i++)
+      SDVLB_CUDA_TRY(cudaMemcpyAsync(jobs[i].cur->dev.pyr, jobs[i].image, img_bytes,
+                                     jobs[i].image_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                     c->stream));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, in.used, cudaMemcpyHostToDevice, c->stream));
+  // prior poses for frames that are not aligned (search may still read cur.pose)
+  for (int i = 0; i < n; i++)
+    if (!jobs[i].ref && jobs[i].n_cands > 0)
+      SDVLB_CUDA_TRY(cudaMemcpyAsync(jobs[i].cur->dev.pose, in.d + o_prior + size_t(i) * 56, 56,
+                                     cudaMemcpyDeviceToDevice, c->stream));
+
+  // ---- kernels
+  if (build_frames) {
+    timer_begin(c, SDVLB_K_PYRAMID);
+    SDVLB_CUDA_TRY(sdvlb_launch_pyramid(reinterpret_cast<const FrameDev*>(in.d + o_frames), n, g, c->stream));
+    timer_end(c);
+    if (n_detect > 0) {
+      rc = ensure_fast_scratch(c, n_detect);
+      if (rc) return rc;
+      const FastPlan* plan = get_plan(c, nfeatures);
+      const FrameDev* dfr = reinterpret_cast<const FrameDev*>(in.d + o_detect);
+      timer_begin(c, SDVLB_K_FAST);
+      SDVLB_CUDA_TRY(sdvlb_launch_fast_cells(dfr, n_detect, *plan, c->cell_kp, c->cell_cnt, c->stream));
+      timer_end(c);
+      timer_begin(c, SDVLB_K_SELECT);
+      SDVLB_CUDA_TRY(sdvlb_launch_fast_select(dfr, n_detect, *plan, c->cell_kp, c->cell_cnt, c->level_kp, c->level_cnt,
+                                              c->frame_ticket, c->overflow_flag, c->stream));
+      timer_end(c);
+    }
+  }
+  if (n_align > 0) {
+    timer_begin(c, SDVLB_K_ALIGN);
+    SDVLB_CUDA_TRY(sdvlb_launch_align(in.d + o_align, n_align, g, c->dp, c->stream));
+    timer_end(c);
+  }
+  if (n_cands > 0) {
+    timer_begin(c, SDVLB_K_SEARCH);
+    SDVLB_CUDA_TRY(sdvlb_launch_search(reinterpret_cast<const SearchCandDev*>(in.d + o_cands), n_cands,
+                                       reinterpret_cast<const FrameDev*>(in.d + o_frames),
+                                       reinterpret_cast<sdvlb_match*>(out.d + o_match), g, c->dp, c->stream));
+    timer_end(c);
+  }
+
+  // ---- D2H
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(out.d + o_flag, c->overflow_flag, 4, cudaMemcpyDeviceToDevice, c->stream));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(out.h, out.d, out.used, cudaMemcpyDeviceToHost, c->stream));
+  if (build_frames && mirror) {
+    for (int i = 0; i < n; i++) {
+      sdvlb_frame* f = jobs[i].cur;
+      if (mirror >= 2)
+        SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block, f->d_block, size_t(g.total), cudaMemcpyDeviceToHost, c->stream));
+      if (jobs[i].want_corners) {
+        SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_xyl, f->d_block + f->off_xyl,
+                                       size_t(c->corner_copy) * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_score, f->d_block + f->off_score,
+                                       size_t(c->corner_copy) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_cnt, f->d_block + f->off_cnt, sizeof(int32_t),
+                                       cudaMemcpyDeviceToHost, c->stream));
+      }
+    }
+  }
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+
+  // ---- results
+  int32_t flag;
+  memcpy(&flag, out.h + o_flag, 4);
+  if (flag) {
+    cudaMemsetAsync(c->overflow_flag, 0, 4, c->stream);
+    return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in FAST selection");
+  }
+  const BatchOut* res = reinterpret_cast<const BatchOut*>(out.h + o_res);
+  const sdvlb_match* hm = reinterpret_cast<const sdvlb_match*>(out.h + o_match);
+  int mo = 0;
+  bool first_align = true;
+  for (int i = 0; i < n; i++) {
+    sdvlb_track_job& j = jobs[i];
+    if (build_frames) {
+      j.cur->has_corners = j.want_corners != 0;
+      j.cur->pyr_mirrored = mirror >= 2;
+      if (j.want_corners && mirror) {
+        memcpy(&j.cur->n_corners, j.cur->h_block + j.cur->off_cnt, sizeof(int32_t));
+        j.cur->corners_mirrored = std::min(j.cur->n_corners, c->corner_copy);
+      }
+    }
+    if (j.ref) {
+      memcpy(j.T_cur, res[i].pose, sizeof(j.T_cur));
+      j.n_tracked = res[i].info[0] / (c->params.align_patch_size * c->params.align_patch_size);
+      j.error = res[i].error;
+      if (first_align) {
+        if (trace_n) *trace_n = res[i].info[1];
+        if (trace) memcpy(trace, out.h + o_trace, size_t(std::min(res[i].info[1], trace_cap)) * sizeof(sdvlb_gn_iter));
+        first_align = false;
+      }
+    }
+    if (j.n_cands > 0) memcpy(j.matches, hm + mo, size_t(j.n_cands) * sizeof(sdvlb_match));
+    mo += j.n_cands;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdvlb_track_batch(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, int mirror) {
+  if (!ctx || !jobs || n_jobs <= 0) return sdvlb_set_error(SDVLB_ERR_ARG, "bad batch");
+  if (w != ctx->w || h != ctx->h) return sdvlb_set_error(SDVLB_ERR_ARG, "image size differs from the context camera");
+  for (int i = 0; i < n_jobs; i++)
+    if (!jobs[i].image) return sdvlb_set_error(SDVLB_ERR_ARG, "job without image");
+  return run_batch(ctx, jobs, n_jobs, mirror, nullptr, 0, nullptr, nullptr, true);
+}
+
+int sdvlb_frame_create(sdvlb_ctx* ctx, const uint8_t* img, int w, int h, int stride, int want_corners, int nfeatures,
+                       sdvlb_frame** out) {
+  if (!ctx || !img || !out) return sdvlb_set_error(SDVLB_ERR_ARG, "null argument");
+  if (w != ctx->w || h != ctx->h) return sdvlb_set_error(SDVLB_ERR_ARG, "image size differs from the context camera");
+  std::vector<uint8_t> packed;
+  const uint8_t* src = img;
+  if (stride != w) {   // the device layout is continuous (image_align.cc:139 assumes stride == cols too)
+    packed.resize(size_t(w) * h);
+    for (int y = 0; y < h; y++) memcpy(packed.data() + size_t(y) * w, img + size_t(y) * stride, w);
+    src = packed.data();
+  }
+  sdvlb_track_job j;
+  memset(&j, 0, sizeof(j));
+  j.image = src;
+  j.want_corners = want_corners;
+  j.nfeatures = nfeatures;
+  const int rc = run_batch(ctx, &j, 1, 2, nullptr, 0, nullptr, nullptr, true);
+  if (rc) return rc;
+  *out = j.cur;
+  return 0;
+}
+
+int sdvlb_frame_detect(sdvlb_ctx* ctx, sdvlb_frame* f, int nfeatures) {
+  if (!ctx || !f) return sdvlb_set_error(SDVLB_ERR_ARG, "null argument");
+  SDVLB_CUDA_TRY(cudaSetDevice(ctx->device));
+  int rc = ensure_fast_scratch(ctx, 1);
+  if (rc) return rc;
+  rc = ensure_arena(&ctx->in, 4096, true);
+  if (rc) return rc;
+  memcpy(ctx->in.h, &f->dev, sizeof(FrameDev));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(ctx->in.d, ctx->in.h, sizeof(FrameDev), cudaMemcpyHostToDevice, ctx->stream));
+  const FastPlan* plan = get_plan(ctx, nfeatures);
+  const FrameDev* dfr = reinterpret_cast<const FrameDev*>(ctx->in.d);
+  timer_begin(ctx, SDVLB_K_FAST);
+  SDVLB_CUDA_TRY(sdvlb_launch_fast_cells(dfr, 1, *plan, ctx->cell_kp, ctx->cell_cnt, ctx->stream));
+  timer_end(ctx);
+  timer_begin(ctx, SDVLB_K_SELECT);
+  SDVLB_CUDA_TRY(sdvlb_launch_fast_select(dfr, 1, *plan, ctx->cell_kp, ctx->cell_cnt, ctx->level_kp, ctx->level_cnt,
+                                          ctx->frame_ticket, ctx->overflow_flag, ctx->stream));
+  timer_end(ctx);
+  int32_t flag = 0;
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_cnt, f->d_block + f->off_cnt, sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(&flag, ctx->overflow_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (flag) {
+    cudaMemsetAsync(ctx->overflow_flag, 0, 4, ctx->stream);
+    return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in FAST selection");
+  }
+  memcpy(&f->n_corners, f->h_block + f->off_cnt, sizeof(int32_t));
+  f->has_corners = true;
+  f->corners_mirrored = 0;
+  return 0;
+}
+
+int sdvlb_frame_level(const sdvlb_frame* f, int level, const uint8_t** data, int* w, int* h) {
+  if (!f || level < 0 || level >= f->ctx->geom.levels) return sdvlb_set_error(SDVLB_ERR_ARG, "bad level");
+  sdvlb_frame* mf = const_cast<sdvlb_frame*>(f);
+  if (!mf->pyr_mirrored) {   // lazy mirror
+    sdvlb_ctx* c = f->ctx;
+    SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_block, mf->d_block, size_t(c->geom.total), cudaMemcpyDeviceToHost, c->stream));
+    SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    mf->pyr_mirrored = true;
+  }
+  if (data) *data = f->h_block + f->ctx->geom.off[level];
+  if (w) *w = f->ctx->geom.w[level];
+  if (h) *h = f->ctx->geom.h[level];
+  return 0;
+}
+
+int sdvlb_frame_corners(const sdvlb_frame* f, const int32_t** xyl, const int32_t** score, int* n) {
+  if (!f) return sdvlb_set_error(SDVLB_ERR_ARG, "null frame");
+  if (!f->has_corners) return sdvlb_set_error(SDVLB_ERR_STATE, "corners were not detected on this frame");
+  sdvlb_frame* mf = const_cast<sdvlb_frame*>(f);
+  sdvlb_ctx* c = f->ctx;
+  if (mf->corners_mirrored < 0) {
+    SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_block + mf->off_cnt, mf->d_block + mf->off_cnt, sizeof(int32_t),
+                                   cudaMemcpyDeviceToHost, c->stream));
+    SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(&mf->n_corners, mf->h_block + mf->off_cnt, sizeof(int32_t));
+    mf->corners_mirrored = 0;
+  }
+  if (mf->corners_mirrored < mf->n_corners) {
+    SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_block + mf->off_xyl, mf->d_block + mf->off_xyl,
+                                   size_t(mf->n_corners) * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_block + mf->off_score, mf->d_block + mf->off_score,
+                                   size_t(mf->n_corners) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    mf->corners_mirrored = mf->n_corners;
+  }
+  if (xyl) *xyl = reinterpret_cast<const int32_t*>(f->h_block + f->off_xyl);
+  if (score) *score = reinterpret_cast<const int32_t*>(f->h_block + f->off_score);
+  if (n) *n = f->n_corners;
+  return 0;
+}
+
+int sdvlb_frame_destroy(sdvlb_ctx* ctx, sdvlb_frame* f) {
+  if (!f) return 0;
+  if (!ctx) ctx = f->ctx;
+  frame_release(ctx, f);
+  return 0;
+}
+
+int sdvlb_image_align(sdvlb_ctx* ctx, const sdvlb_frame* ref, sdvlb_frame* cur, const sdvlb_align_feat* feats, int n,
+                      const double T_ref[7], double T_cur[7], int fast, int* n_tracked, double* error,
+                      sdvlb_gn_iter* trace, int trace_cap, int* trace_n, const sdvlb_gn_forced* forced) {
+  if (!ctx || !ref || !cur || !T_ref || !T_cur || n < 0 || (n > 0 && !feats))
+    return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  if (trace_n) *trace_n = 0;
+  if (n == 0) {   // image_align.cc:55-58
+    if (n_tracked) *n_tracked = 0;
+    if (error) *error = 1e10;
+    return 0;
+  }
+  sdvlb_track_job j;
+  memset(&j, 0, sizeof(j));
+  j.ref = ref;
+  j.cur = cur;
+  j.feats = feats;
+  j.n_feats = n;
+  memcpy(j.T_ref, T_ref, sizeof(j.T_ref));
+  memcpy(j.T_cur, T_cur, sizeof(j.T_cur));
+  const int rc = run_batch(ctx, &j, 1, 0, trace, trace ? trace_cap : 0, trace_n, forced, false, fast);
+  if (rc) return rc;
+  memcpy(T_cur, j.T_cur, sizeof(j.T_cur));
+  if (n_tracked) *n_tracked = j.n_tracked;
+  if (error) *error = j.error;
+  return 0;
+}
+
+int sdvlb_search_points(sdvlb_ctx* ctx, const sdvlb_frame* cur, const sdvlb_candidate* cands, int n,
+                        const double T_cur[7], sdvlb_match* out) {
+  if (!ctx || !cur || n < 0 || (n > 0 && (!cands || !out))) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  if (!cur->has_corners) return sdvlb_set_error(SDVLB_ERR_STATE, "current frame has no corners");
+  if (n == 0) return 0;
+  sdvlb_track_job j;
+  memset(&j, 0, sizeof(j));
+  j.cur = const_cast<sdvlb_frame*>(cur);
+  j.cands = cands;
+  j.n_cands = n;
+  j.matches = out;
+  if (T_cur) {
+    memcpy(j.T_cur, T_cur, sizeof(j.T_cur));
+  } else {   // keep the device-side pose: read it back so the upload below is a no-op in value
+    SDVLB_CUDA_TRY(cudaSetDevice(ctx->device));
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(j.T_cur, cur->dev.pose, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SDVLB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  return run_batch(ctx, &j, 1, 0, nullptr, 0, nullptr, nullptr, false);
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+// common.cuh — device-side data model and SE3/camera math shared by the sm_100a kernels.
+// Math follows extra/se3.cc, camera.cc, extra/utils.cc of the reference (file:line cited per function).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sdvl_b200.h"
+
+#define SDVLB_MAX_LEVELS 8
+#define SDVLB_CELL 32
+#define SDVLB_CELL_CAP 176          // > 13*13: upper bound of NMS survivors in a 26x26 tested area
+#define SDVLB_MAX_DIM 2048          // x,y packed in 11 bits each by the corner selector
+
+// Geometry of one pyramid (all frames of a context share it).
+struct PyrGeom {
+  int levels;
+  int w[SDVLB_MAX_LEVELS], h[SDVLB_MAX_LEVELS];
+  int off[SDVLB_MAX_LEVELS];        // byte offset of each level inside a frame's pyramid allocation (256-B aligned)
+  int total;                        // bytes per frame
+  // FAST cell grid per level
+  int wcells[SDVLB_MAX_LEVELS], hcells[SDVLB_MAX_LEVELS], cell_off[SDVLB_MAX_LEVELS];
+  int total_cells;                  // over levels 0..max_fast_levels-1
+};
+
+// Device view of one frame.
+struct FrameDev {
+  uint8_t* pyr;        // levels at PyrGeom::off
+  int32_t* xyl;        // corners: (x, y, level) triplets in level coordinates, reference order
+  int32_t* score;      // FAST score per corner
+  int32_t* n_corners;  // device counter
+  double* pose;        // 7 doubles, world->camera, written by the ImageAlign kernel / uploaded by the host
+};
+
+struct DevParams {
+  sdvlb_params p;
+  sdvlb_camera cam;
+};
+
+// One ImageAlign::ComputePose call (device descriptor).
+struct AlignJobDev {
+  FrameDev ref, cur;
+  const sdvlb_align_feat* feats;
+  int n;
+  int fast;
+  double T_ref[7];
+  double T_cur[7];
+  // outputs
+  double* out_pose;        // 7 doubles (also written to cur.pose)
+  int32_t* out_info;       // [0] = n_meas of the last ComputeResiduals, [1] = iterations run
+  double* out_error;       // GetError()
+  sdvlb_gn_iter* trace;    // optional
+  int trace_cap;
+  int forced_n;
+  // teacher forcing (parity tests)
+  const double* forced_T;
+  const int32_t* forced_iters;
+  // scratch
+  float* sc_f;             // patch[n*16], dx[n*16], dy[n*16]
+  double* sc_d;            // xyz[n*3], j0[n*6], j1[n*6], abc[n*3]
+  int32_t* sc_flags;       // bit0 visible (sticky), bit1 has a Jacobian at this level
+};
+
+// One Matcher::SearchPoint call (device descriptor; frame handles resolved to device pointers).
+struct SearchCandDev {
+  const uint8_t* ref_pyr;
+  double ref_T[7];
+  double ref_px[2];
+  double ref_v[3];
+  double idepth, idepth_std;
+  double px[2];
+  double pos[3];
+  int32_t ref_level;
+  int32_t flags;
+  int32_t cur_index;       // index into the FrameDev array passed to the kernel
+  int32_t pad_;
+};
+
+// FAST detection + selection launch parameters (fast.cu).
+struct FastArgs {
+  PyrGeom g;
+  int n_fast_levels;
+  int margin;            // 1 + patch_size/2 (fast_detector.cc:66, use_orb == 0)
+  int threshold;
+  int nfeat[SDVLB_MAX_LEVELS];   // per-level budgets (fast_detector.cc:160-173)
+  int corner_cap;
+  int level_cap[SDVLB_MAX_LEVELS];   // capacity of the per-level scratch list
+  int level_kp_off[SDVLB_MAX_LEVELS];
+  int level_kp_total;
+};
+struct FastPlan {
+  FastArgs args;
+  int max_cells_level;
+  int nfeatures;
+};
+
+// ----------------------------------------------------------------------------- fp64 SE3
+struct DSE3 {
+  double q0, q1, q2, q3, tx, ty, tz;
+};
+
+__host__ __device__ inline DSE3 se3_load(const double* a) {
+  DSE3 s;
+  s.q0 = a[0]; s.q1 = a[1]; s.q2 = a[2]; s.q3 = a[3]; s.tx = a[4]; s.ty = a[5]; s.tz = a[6];
+  return s;
+}
+__host__ __device__ inline void se3_store(const DSE3& s, double* a) {
+  a[0] = s.q0; a[1] = s.q1; a[2] = s.q2; a[3] = s.q3; a[4] = s.tx; a[5] = s.ty; a[6] = s.tz;
+}
+
+// Eigen::Quaterniond::toRotationMatrix (used by SE3::GetRotation, extra/se3.h:41)
+__host__ __device__ inline void se3_rot(const DSE3& s, double R[9]) {
+  const double tx = 2.0 * s.q1, ty = 2.0 * s.q2, tz = 2.0 * s.q3;
+  const double twx = tx * s.q0, twy = ty * s.q0, twz = tz * s.q0;
+  const double txx = tx * s.q1, txy = ty * s.q1, txz = tz * s.q1;
+  const double tyy = ty * s.q2, tyz = tz * s.q2, tzz = tz * s.q3;
+  R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz;         R[2] = txz + twy;
+  R[3] = txy + twz;         R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;         R[7] = tyz + twx;         R[8] = 1.0 - (txx + tyy);
+}
+
+__host__ __device__ inline void mat3_mul_vec(const double R[9], double x, double y, double z, double& ox, double& oy,
+                                             double& oz) {
+  ox = R[0] * x + R[1] * y + R[2] * z;
+  oy = R[3] * x + R[4] * y + R[5] * z;
+  oz = R[6] * x + R[7] * y + R[8] * z;
+}
+
+// SE3::operator*(Vector3d) (extra/se3.h:68)
+__host__ __device__ inline void se3_apply(const DSE3& s, double x, double y, double z, double& ox, double& oy,
+                                          double& oz) {
+  double R[9];
+  se3_rot(s, R);
+  mat3_mul_vec(R, x, y, z, ox, oy, oz);
+  ox += s.tx; oy += s.ty; oz += s.tz;
+}
+
+// SE3::Inverse (extra/se3.cc:59-70)
+__host__ __device__ inline DSE3 se3_inverse(const DSE3& s) {
+  DSE3 r;
+  const double n2 = s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3;
+  if (n2 > 0.0) {
+    r.q0 = s.q0 / n2; r.q1 = -s.q1 / n2; r.q2 = -s.q2 / n2; r.q3 = -s.q3 / n2;
+  } else {
+    r.q0 = r.q1 = r.q2 = r.q3 = 0.0;
+  }
+  double R[9], x, y, z;
+  se3_rot(r, R);
+  mat3_mul_vec(R, s.tx, s.ty, s.tz, x, y, z);
+  r.tx = -x; r.ty = -y; r.tz = -z;
+  return r;
+}
+
+// SE3::operator*(SE3) (extra/se3.cc:166-177): quaternion product, normalise, t = t_a + R_a t_b
+__host__ __device__ inline DSE3 se3_mul(const DSE3& a, const DSE3& b) {
+  DSE3 r;
+  const double w = a.q0 * b.q0 - a.q1 * b.q1 - a.q2 * b.q2 - a.q3 * b.q3;
+  const double x = a.q0 * b.q1 + a.q1 * b.q0 + a.q2 * b.q3 - a.q3 * b.q2;
+  const double y = a.q0 * b.q2 + a.q2 * b.q0 + a.q3 * b.q1 - a.q1 * b.q3;
+  const double z = a.q0 * b.q3 + a.q3 * b.q0 + a.q1 * b.q2 - a.q2 * b.q1;
+  const double n = sqrt(w * w + x * x + y * y + z * z);
+  r.q0 = w / n; r.q1 = x / n; r.q2 = y / n; r.q3 = z / n;
+  double R[9], ox, oy, oz;
+  se3_rot(a, R);
+  mat3_mul_vec(R, b.tx, b.ty, b.tz, ox, oy, oz);
+  r.tx = a.tx + ox; r.ty = a.ty + oy; r.tz = a.tz + oz;
+  return r;
+}
+
+// SE3::Exp (extra/se3.cc:72-94,114-130); u = [upsilon; omega]
+__host__ __device__ inline DSE3 se3_exp(const double u[6]) {
+  const double SMALL_EPS = 1e-10;
+  const double ox = u[3], oy = u[4], oz = u[5];
+  const double theta = sqrt(ox * ox + oy * oy + oz * oz);
+  const double half_theta = 0.5 * theta;
+  double imag_factor;
+  const double real_factor = cos(half_theta);
+  if (theta < SMALL_EPS) {
+    const double theta_sq = theta * theta;
+    const double theta_po4 = theta_sq * theta_sq;
+    imag_factor = 0.5 - 0.0208333 * theta_sq + 0.000260417 * theta_po4;
+  } else {
+    imag_factor = sin(half_theta) / theta;
+  }
+  DSE3 r;
+  r.q0 = real_factor; r.q1 = imag_factor * ox; r.q2 = imag_factor * oy; r.q3 = imag_factor * oz;
+  double V[9];
+  if (theta < SMALL_EPS) {
+    se3_rot(r, V);
+  } else {
+    const double Om[9] = {0, -oz, oy, oz, 0, -ox, -oy, ox, 0};
+    double Om2[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += Om[i * 3 + k] * Om[k * 3 + j];
+        Om2[i * 3 + j] = s;
+      }
+    const double theta_sq = theta * theta;
+    const double a = (1 - cos(theta)) / theta_sq;
+    const double b = (theta - sin(theta)) / (theta_sq * theta);
+    for (int i = 0; i < 9; i++) V[i] = ((i == 0 || i == 4 || i == 8) ? 1.0 : 0.0) + a * Om[i] + b * Om2[i];
+  }
+  mat3_mul_vec(V, u[0], u[1], u[2], r.tx, r.ty, r.tz);
+  return r;
+}
+
+// Eigen LDLT<Matrix6d>::solve (image_align.cc:102): diagonal-pivoted LDL^T, pseudo-inverse of D.
+__host__ __device__ inline void ldlt_solve6(const double Hin[36], const double b[6], double x[6]) {
+  const int n = 6;
+  double m[36];
+  int tr[6];
+  for (int i = 0; i < 36; i++) m[i] = Hin[i];
+  bool zero_matrix = false;
+  for (int k = 0; k < n; ++k) {
+    int big = k;
+    double best = fabs(m[k * 6 + k]);
+    for (int i = k + 1; i < n; ++i)
+      if (fabs(m[i * 6 + i]) > best) { best = fabs(m[i * 6 + i]); big = i; }
+    tr[k] = big;
+    if (k != big) {
+      for (int j = 0; j < k; ++j) { double t = m[k * 6 + j]; m[k * 6 + j] = m[big * 6 + j]; m[big * 6 + j] = t; }
+      for (int i = big + 1; i < n; ++i) { double t = m[i * 6 + k]; m[i * 6 + k] = m[i * 6 + big]; m[i * 6 + big] = t; }
+      { double t = m[k * 6 + k]; m[k * 6 + k] = m[big * 6 + big]; m[big * 6 + big] = t; }
+      for (int i = k + 1; i < big; ++i) { double t = m[i * 6 + k]; m[i * 6 + k] = m[big * 6 + i]; m[big * 6 + i] = t; }
+    }
+    const int rs = n - k - 1;
+    if (k > 0) {
+      double temp[6];
+      for (int j = 0; j < k; ++j) temp[j] = m[j * 6 + j] * m[k * 6 + j];
+      double s = 0;
+      for (int j = 0; j < k; ++j) s += m[k * 6 + j] * temp[j];
+      m[k * 6 + k] -= s;
+      for (int i = 0; i < rs; ++i) {
+        double a = 0;
+        for (int j = 0; j < k; ++j) a += m[(k + 1 + i) * 6 + j] * temp[j];
+        m[(k + 1 + i) * 6 + k] -= a;
+      }
+    }
+    const double akk = m[k * 6 + k];
+    const bool pivot_is_valid = fabs(akk) > 0.0;
+    if (k == 0 && !pivot_is_valid) {
+      for (int j = 0; j < n; ++j) tr[j] = j;
+      zero_matrix = true;
+      break;
+    }
+    if (rs > 0 && pivot_is_valid)
+      for (int i = 0; i < rs; ++i) m[(k + 1 + i) * 6 + k] /= akk;
+  }
+  double d[6];
+  for (int i = 0; i < n; i++) d[i] = b[i];
+  for (int k = 0; k < n; ++k)
+    if (tr[k] != k) { double t = d[k]; d[k] = d[tr[k]]; d[tr[k]] = t; }
+  if (!zero_matrix)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < i; ++j) d[i] -= m[i * 6 + j] * d[j];
+  const double tol = 2.2250738585072014e-308;  // std::numeric_limits<double>::min()
+  for (int i = 0; i < n; ++i) {
+    if (fabs(m[i * 6 + i]) > tol) d[i] /= m[i * 6 + i];
+    else d[i] = 0.0;
+  }
+  if (!zero_matrix)
+    for (int i = n - 1; i >= 0; --i)
+      for (int j = i + 1; j < n; ++j) d[i] -= m[j * 6 + i] * d[j];
+  for (int k = n - 1; k >= 0; --k)
+    if (tr[k] != k) { double t = d[k]; d[k] = d[tr[k]]; d[tr[k]] = t; }
+  for (int i = 0; i < n; i++) x[i] = d[i];
+}
+
+// Jacobian3DToPlane, 2x6 (extra/utils.cc:99-118)
+__host__ __device__ inline void jacobian3d_to_plane(double x, double y, double z, double J0[6], double J1[6]) {
+  const double z_inv = 1. / z;
+  const double z_inv_2 = z_inv * z_inv;
+  J0[0] = -z_inv;
+  J0[1] = 0.0;
+  J0[2] = x * z_inv_2;
+  J0[3] = y * J0[2];
+  J0[4] = -(1.0 + x * J0[2]);
+  J0[5] = y * z_inv;
+  J1[0] = 0.0;
+  J1[1] = -z_inv;
+  J1[2] = y * z_inv_2;
+  J1[3] = 1.0 + y * J1[2];
+  J1[4] = -J0[3];
+  J1[5] = -x * z_inv;
+}
+
+// error handling shared by the host side
+#define SDVLB_CUDA_TRY(expr)                                                   \
+  do {                                                                         \
+    cudaError_t e_ = (expr);                                                   \
+    if (e_ != cudaSuccess) return sdvlb_set_cuda_error(e_, #expr, __FILE__, __LINE__); \
+  } while (0)
+int sdvlb_set_cuda_error(cudaError_t e, const char* expr, const char* file, int line);
+int sdvlb_set_error(int code, const char* msg);

@@ -1,0 +1,342 @@
+// search.cu — K4: Matcher::SearchPoint (matcher.cc:45-121, non-ORB) for a batch of map points, one warp per
+// candidate: optional FeatureAlign::ProjectPoint (feature_align.cc:323-339), depth-range projection test, affine warp
+// (WarpMatrixAffine :293-312), search level (:314-323), warped 10x10 reference patch (CreatePatch :325-357), corner
+// gating (GetCornersInRange :123-230), integer ZMSSD (:447-476, bit-exact) and the 3-parameter inverse-compositional
+// Lucas-Kanade refinement (AlignPatch :359-445, fp32 as in the reference).
+// Geometry is evaluated redundantly by all 32 lanes in fp64 (uniform control flow); patch pixels, corner scan and LK
+// pixels are spread over the lanes; the LK normal equations are reduced with xor-butterfly shuffles (every lane ends
+// with the same bits).  Ties in ZMSSD resolve to the lowest corner index, as the reference's in-order scan does.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SE_WARPS = 4;
+constexpr int SE_THREADS = SE_WARPS * 32;
+
+struct SearchArgs {
+  PyrGeom g;
+  DevParams dp;
+  int n;
+};
+
+__device__ __forceinline__ void cam_project(const sdvlb_camera& c, double x, double y, double z, double& u, double& v) {
+  u = c.u0 + c.fx * x / z;   // camera.cc:69-72
+  v = c.v0 + c.fy * y / z;
+}
+__device__ __forceinline__ void cam_unproject(const sdvlb_camera& c, double u, double v, double& x, double& y,
+                                              double& z) {  // camera.cc:74-79
+  x = (u - c.u0) / c.fx;
+  y = (v - c.v0) / c.fy;
+  z = 1.0;
+  const double n = sqrt(x * x + y * y + z * z);
+  x /= n; y /= n; z /= n;
+}
+__device__ __forceinline__ bool finite2(double a, double b) { return isfinite(a) && isfinite(b); }
+
+// Interpolate8U (extra/utils.cc:44-59), then (uint8_t) truncation (matcher.cc:348)
+__device__ __forceinline__ uint8_t interp8u(const uint8_t* __restrict__ img, int stride, float u, float v) {
+  const int x = int(floorf(u)), y = int(floorf(v));
+  const float sx = u - float(x), sy = v - float(y);
+  const float w00 = (1.0f - sx) * (1.0f - sy);
+  const float w01 = (1.0f - sx) * sy;
+  const float w10 = sx * (1.0f - sy);
+  const float w11 = 1.0f - w00 - w01 - w10;
+  const uint8_t* p = img + size_t(y) * stride + x;
+  const float r = w00 * float(__ldg(p)) + w01 * float(__ldg(p + stride)) + w10 * float(__ldg(p + 1)) +
+                  w11 * float(__ldg(p + stride + 1));
+  return uint8_t(int(r));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchCandDev* __restrict__ cands,
+                                                                   const FrameDev* __restrict__ frames,
+                                                                   sdvlb_match* __restrict__ out,
+                                                                   const __grid_constant__ SearchArgs A) {
+  __shared__ uint8_t s_bp[SE_WARPS][104];
+  __shared__ uint8_t s_patch[SE_WARPS][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ci = blockIdx.x * SE_WARPS + warp;
+  if (ci >= A.n) return;
+  const SearchCandDev& C = cands[ci];
+  const sdvlb_params& P = A.dp.p;
+  const sdvlb_camera& cam = A.dp.cam;
+  const FrameDev cur = frames[C.cur_index];
+  const int ps = 8, half = 4;
+
+  sdvlb_match m;
+  m.px[0] = m.px[1] = 0.0;
+  m.proj[0] = C.px[0]; m.proj[1] = C.px[1];
+  m.level = 0; m.status = SDVLB_MATCH_NOT_FOUND; m.zmssd = -1; m.n_in_range = 0;
+
+  const DSE3 T_cur = se3_load(cur.pose);
+  const DSE3 T_ref = se3_load(C.ref_T);
+  const DSE3 T_ref_w = se3_inverse(T_ref);              // ref_frame->GetWorldPose()
+  const DSE3 pose = se3_mul(T_cur, T_ref_w);            // matcher.cc:55
+  const bool fixed = (C.flags & SDVLB_CAND_FIXED) != 0;
+  double px0 = C.px[0], px1 = C.px[1];
+  bool alive = true;
+
+  if (C.flags & SDVLB_CAND_PROJECT) {                   // feature_align.cc:323-339
+    double x, y, z, u, v;
+    se3_apply(T_cur, C.pos[0], C.pos[1], C.pos[2], x, y, z);
+    bool ok = !(z < 0.0);
+    if (ok) {
+      cam_project(cam, x, y, z, u, v);
+      ok = finite2(u, v) && fabs(u) < 1e9 && fabs(v) < 1e9;
+      if (ok) {
+        const int iu = int(u), iv = int(v);             // Vector2d::cast<int>() truncates
+        const int mrg = P.patch_size;
+        ok = iu >= mrg && iu < cam.width - mrg && iv >= mrg && iv < cam.height - mrg;   // camera.h:93-95
+      }
+    }
+    if (!ok) { m.status = SDVLB_MATCH_UNSEEN; alive = false; }
+    else { px0 = u; px1 = v; m.proj[0] = u; m.proj[1] = v; }
+  }
+
+  double pxa0 = 0, pxa1 = 0, pxb0 = 0, pxb1 = 0;
+  if (alive) {                                          // matcher.cc:57-77
+    const double zmin = 1.0 / (C.idepth + 2.0 * C.idepth_std);
+    double wx, wy, wz, x, y, z;
+    se3_apply(T_ref_w, C.ref_v[0] * zmin, C.ref_v[1] * zmin, C.ref_v[2] * zmin, wx, wy, wz);
+    se3_apply(T_cur, wx, wy, wz, x, y, z);
+    if (z < 0.0) alive = false;
+    else cam_project(cam, x, y, z, pxa0, pxa1);
+    if (alive && !fixed) {
+      const double zmax = 1.0 / fmax(C.idepth - 2.0 * C.idepth_std, 0.00000001);
+      se3_apply(T_ref_w, C.ref_v[0] * zmax, C.ref_v[1] * zmax, C.ref_v[2] * zmax, wx, wy, wz);
+      se3_apply(T_cur, wx, wy, wz, x, y, z);
+      if (z < 0.0) alive = false;
+      else cam_project(cam, x, y, z, pxb0, pxb1);
+    }
+  }
+  const int level = C.ref_level;
+  if (alive) {                                          // matcher.cc:83, camera.h:96-98, feature.h:93-95
+    const int lx = int(C.ref_px[0] / double(1 << level)), ly = int(C.ref_px[1] / double(1 << level));
+    const int mrg = ps / 2 + 2;
+    if (!(lx >= mrg && lx < cam.width / double(1 << level) - mrg && ly >= mrg &&
+          ly < cam.height / double(1 << level) - mrg))
+      alive = false;
+  }
+
+  int slevel = 0;
+  double Ai00 = 0, Ai01 = 0, Ai10 = 0, Ai11 = 0;
+  if (alive) {                                          // WarpMatrixAffine (matcher.cc:293-312)
+    const double depth = 1.0 / C.idepth;
+    const double p0 = C.ref_v[0] * depth, p1 = C.ref_v[1] * depth, p2 = C.ref_v[2] * depth;
+    double dux, duy, duz, dvx, dvy, dvz;
+    cam_unproject(cam, C.ref_px[0] + 5.0 * double(1 << level), C.ref_px[1] + 0.0 * double(1 << level), dux, duy, duz);
+    cam_unproject(cam, C.ref_px[0] + 0.0 * double(1 << level), C.ref_px[1] + 5.0 * double(1 << level), dvx, dvy, dvz);
+    const double su = p2 / duz, sv = p2 / dvz;
+    dux *= su; duy *= su; duz *= su;
+    dvx *= sv; dvy *= sv; dvz *= sv;
+    double x, y, z, c0, c1, u0, u1, v0, v1;
+    se3_apply(pose, p0, p1, p2, x, y, z);       cam_project(cam, x, y, z, c0, c1);
+    se3_apply(pose, dux, duy, duz, x, y, z);    cam_project(cam, x, y, z, u0, u1);
+    se3_apply(pose, dvx, dvy, dvz, x, y, z);    cam_project(cam, x, y, z, v0, v1);
+    const double A00 = (u0 - c0) / 5, A10 = (u1 - c1) / 5, A01 = (v0 - c0) / 5, A11 = (v1 - c1) / 5;
+    // GetSearchLevel (matcher.cc:314-323)
+    double det = A00 * A11 - A01 * A10;
+    const double det0 = det;
+    const int maxl = P.max_fast_levels - 1;
+    while (det > 3.0 && slevel < maxl) { slevel += 1; det *= 0.25; }
+    // Matrix2d::inverse (matcher.cc:330)
+    const double invdet = 1.0 / det0;
+    Ai00 = A11 * invdet; Ai01 = -A01 * invdet; Ai10 = -A10 * invdet; Ai11 = A00 * invdet;
+    if (isnan(Ai00)) alive = false;   // the reference keeps a stale patch here (matcher.cc:331-334); we report NOT_FOUND
+  }
+
+  if (alive) {                                          // CreatePatch (matcher.cc:325-357)
+    const int W = A.g.w[level], Hh = A.g.h[level];
+    const uint8_t* __restrict__ img = C.ref_pyr + A.g.off[level];
+    const double pyrx = C.ref_px[0] / double(1 << level), pyry = C.ref_px[1] / double(1 << level);
+    for (int i = lane; i < 100; i += 32) {
+      const int y = i / 10, x = i - y * 10;
+      double ppx = double(x - 5), ppy = double(y - 5);
+      ppx *= double(1 << slevel); ppy *= double(1 << slevel);
+      const double q0 = Ai00 * ppx + Ai01 * ppy + pyrx;
+      const double q1 = Ai10 * ppx + Ai11 * ppy + pyry;
+      uint8_t val = 0;
+      if (!(q0 < 0 || q1 < 0 || q0 >= W - 1 || q1 >= Hh - 1) && finite2(q0, q1)) val = interp8u(img, W, float(q0), float(q1));
+      s_bp[warp][i] = val;
+      if (y >= 1 && y < 9 && x >= 1 && x < 9) s_patch[warp][(y - 1) * 8 + (x - 1)] = val;
+    }
+  }
+  __syncwarp();
+
+  // ---- GetCornersInRange + SearchFeatures (matcher.cc:123-291)
+  unsigned long long best_key = ~0ull;
+  int n_in_range = 0;
+  const int threshold = ps * ps * 500;   // MAX_SSD_PER_PIXEL (matcher.h:36)
+  if (alive) {
+    double range = double(P.search_size);
+    for (int i = 1; i <= slevel; i++) range *= 1.2;
+    const double range2 = range * range;
+    const int margin = 1 + ps / 2;
+    // epipolar-capsule constants (matcher.cc:140-150)
+    double nx = 0, ny = 0, normdist = 0, xdiff = 0, ydiff = 0, vline = 1;
+    if (!fixed) {
+      double ex = pxa0 - pxb0, ey = pxa1 - pxb1;
+      const double en2 = ex * ex + ey * ey;
+      if (en2 > 0) { const double en = sqrt(en2); ex /= en; ey /= en; }
+      nx = ey; ny = -ex;
+      normdist = pxa0 * nx + pxa1 * ny;
+      xdiff = pxb0 - pxa0; ydiff = pxb1 - pxa1;
+      vline = xdiff * xdiff + ydiff * ydiff;
+    }
+    int sumA = 0, sumAA = 0;                            // GetZMSSDScore (matcher.cc:447-457)
+    for (int r = 0; r < 64; r++) { const int v = s_patch[warp][r]; sumA += v; sumAA += v * v; }
+    const int nc = *cur.n_corners;
+    for (int base = 0; base < nc; base += 32) {
+      const int idx = base + lane;
+      bool in = false;
+      int cx = 0, cy = 0, cl = 0;
+      if (idx < nc) {
+        cx = cur.xyl[3 * idx]; cy = cur.xyl[3 * idx + 1]; cl = cur.xyl[3 * idx + 2];
+        in = abs(cl - level) <= 1 && !(cx - margin < 0 || cy - margin < 0) &&
+             !(cy + margin >= A.g.h[cl] || cx + margin >= A.g.w[cl]);
+        if (in) {
+          const double posx = double(cx * (1 << cl)), posy = double(cy * (1 << cl));
+          if (fixed) {
+            const double dx = px0 - posx, dy = px1 - posy;
+            in = !(dx * dx + dy * dy > range2);
+          } else {
+            const double dist = normdist - (posx * nx + posy * ny);
+            if (fabs(dist) > range) in = false;
+            else {
+              const double u = ((posx - pxa0) * xdiff + (posy - pxa1) * ydiff) / vline;
+              if (u > 1) { const double dx = posx - pxb0, dy = posy - pxb1; if (dx * dx + dy * dy > range2) in = false; }
+              if (in && u < 0) { const double dx = posx - pxa0, dy = posy - pxa1; if (dx * dx + dy * dy > range2) in = false; }
+            }
+          }
+        }
+      }
+      n_in_range += __popc(__ballot_sync(0xffffffffu, in));
+      if (in) {                                         // CompareZMSSDScore (matcher.cc:459-476)
+        const int Wc = A.g.w[cl];
+        const uint8_t* __restrict__ cp = cur.pyr + A.g.off[cl] + size_t(cy - half) * Wc + (cx - half);
+        int sB = 0, sBB = 0, sAB = 0;
+        for (int y = 0; y < 8; y++)
+#pragma unroll
+          for (int x = 0; x < 8; x++) {
+            const int pix = __ldg(cp + y * Wc + x);
+            sB += pix; sBB += pix * pix; sAB += pix * int(s_patch[warp][y * 8 + x]);
+          }
+        const int score = sumAA - 2 * sAB + sBB - (sumA * sumA - 2 * sumA * sB + sB * sB) / 64;
+        const unsigned long long key = (static_cast<unsigned long long>(uint32_t(score)) << 32) | uint32_t(idx);
+        if (key < best_key) best_key = key;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best_key, o);
+      if (other < best_key) best_key = other;
+    }
+    m.n_in_range = n_in_range;
+    int best_score = threshold + 1;
+    if (best_key != ~0ull && int(best_key >> 32) < best_score) best_score = int(best_key >> 32);
+    m.zmssd = n_in_range == 0 ? -1 : best_score;
+    if (best_score >= threshold) alive = false;
+  }
+
+  // ---- AlignPatch (matcher.cc:359-445) at the search level
+  if (alive) {
+    const int bidx = int(best_key & 0xffffffffu);
+    const int bl = cur.xyl[3 * bidx + 2];
+    const double bx = double(cur.xyl[3 * bidx] * (1 << bl)), by = double(cur.xyl[3 * bidx + 1] * (1 << bl));
+    const int W = A.g.w[slevel], Hh = A.g.h[slevel];
+    const uint8_t* __restrict__ img = cur.pyr + A.g.off[slevel];
+    // template gradients; each lane owns pixels lane and lane+32
+    float gdx[2], gdy[2], tp[2];
+    float h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int i = lane + 32 * k, y = i >> 3, x = i & 7;
+      const uint8_t* it = &s_bp[warp][(y + 1) * 10 + x + 1];
+      gdx[k] = float(0.5 * double(int(it[1]) - int(it[-1])));
+      gdy[k] = float(0.5 * double(int(it[10]) - int(it[-10])));
+      tp[k] = float(s_patch[warp][i]);
+      h00 += gdx[k] * gdx[k]; h01 += gdx[k] * gdy[k]; h02 += gdx[k];
+      h11 += gdy[k] * gdy[k]; h12 += gdy[k];
+    }
+    // all terms are multiples of 0.25 below 2^24: any summation order is exact
+    h00 = warp_sum(h00); h01 = warp_sum(h01); h02 = warp_sum(h02); h11 = warp_sum(h11); h12 = warp_sum(h12);
+    const float Hm[3][3] = {{h00, h01, h02}, {h01, h11, h12}, {h02, h12, 64.0f}};
+    float Hinv[3][3];
+    {
+      // Eigen Matrix3f::inverse(): cofactor(i,j) = m(i1,j1)*m(i2,j2) - m(i1,j2)*m(i2,j1); inv(i,j) = cof(j,i)/det
+      float cof[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+          cof[i][j] = Hm[i1][j1] * Hm[i2][j2] - Hm[i1][j2] * Hm[i2][j1];
+        }
+      const float det = cof[0][0] * Hm[0][0] + cof[1][0] * Hm[1][0] + cof[2][0] * Hm[2][0];
+      const float invdet = 1.0f / det;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Hinv[i][j] = cof[j][i] * invdet;
+    }
+    float mean_diff = 0.0f;
+    float u = float(bx / double(1 << slevel));
+    float v = float(by / double(1 << slevel));
+    const float min_update_squared = float(0.03 * 0.03);
+    bool converged = false, failed = false;
+    for (int iter = 0; iter < P.max_align_its; iter++) {
+      if (isnan(u) || isnan(v)) { failed = true; break; }
+      if (!(u >= float(half) && v >= float(half) && u < float(W) && v < float(Hh))) break;   // also guards int conversion
+      const int u_r = int(floorf(u)), v_r = int(floorf(v));
+      if (u_r < half || v_r < half || u_r >= W - half || v_r >= Hh - half) break;
+      const float sx = u - float(u_r), sy = v - float(v_r);
+      const float wTL = float((1.0 - sx) * (1.0 - sy));
+      const float wTR = float(sx * (1.0 - sy));
+      const float wBL = float((1.0 - sx) * sy);
+      const float wBR = float(sx * sy);
+      float j0 = 0, j1 = 0, j2 = 0;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int i = lane + 32 * k, y = i >> 3, x = i & 7;
+        const uint8_t* it = img + size_t(v_r + y - half) * W + (u_r - half + x);
+        const float sp = wTL * float(__ldg(it)) + wTR * float(__ldg(it + 1)) + wBL * float(__ldg(it + W)) +
+                         wBR * float(__ldg(it + W + 1));
+        const float res = sp - tp[k] + mean_diff;
+        j0 -= res * gdx[k];
+        j1 -= res * gdy[k];
+        j2 -= res;
+      }
+      j0 = warp_sum(j0); j1 = warp_sum(j1); j2 = warp_sum(j2);
+      const float up0 = Hinv[0][0] * j0 + Hinv[0][1] * j1 + Hinv[0][2] * j2;
+      const float up1 = Hinv[1][0] * j0 + Hinv[1][1] * j1 + Hinv[1][2] * j2;
+      const float up2 = Hinv[2][0] * j0 + Hinv[2][1] * j1 + Hinv[2][2] * j2;
+      u += up0; v += up1; mean_diff += up2;
+      if (up0 * up0 + up1 * up1 < min_update_squared) { converged = true; break; }
+    }
+    if (converged && !failed) {
+      m.status = SDVLB_MATCH_FOUND;
+      m.px[0] = double(u) * double(1 << slevel);
+      m.px[1] = double(v) * double(1 << slevel);
+      m.level = slevel;
+    }
+  }
+  if (lane == 0) out[ci] = m;
+}
+
+}  // namespace
+
+cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const FrameDev* d_frames, sdvlb_match* d_out,
+                                const PyrGeom& g, const DevParams& dp, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  SearchArgs A;
+  A.g = g;
+  A.dp = dp;
+  A.n = n;
+  search_points_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, d_frames, d_out, A);
+  return cudaGetLastError();
+}

@@ -1,0 +1,209 @@
+"""GPU parity tests: the sm_100a path, called through the C-ABI, against the CPU oracle on identical inputs.
+Bars (BASELINE.json): pyramid bytes and FAST corner sets/scores/order bit-exact; H, b, x per Gauss-Newton iteration
+within 1e-4 relative (teacher-forced); LK positions within 0.01 px; discrete outputs of SearchPoint identical."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4     # north_star tolerance for H, b, x (relative to the infinity norm of the quantity)
+LK_PX = 0.01   # north_star tolerance for refined positions
+
+
+def _ctx(binding, cfg):
+    return binding.Context(cfg["params"], cfg["cam"])
+
+
+@pytest.mark.parametrize("name,seed", [("C1", 3), ("C2", 0), ("C5", 1)])
+def test_pyramid_bit_exact(binding, sw, O, name, seed):
+    cfg, poses, imgs = sw.sequence(name, seed, 2)
+    ctx = _ctx(binding, cfg)
+    try:
+        for img in imgs:
+            f = ctx.frame(img, corners=False)
+            ref = O.pyramid(img, cfg["params"].pyramid_levels)
+            for l, r in enumerate(ref):
+                got = f.level(l)
+                assert got.shape == r.shape
+                assert np.array_equal(got, r), f"{name} level {l}: {(got != r).sum()} bytes differ"
+            f.destroy()
+    finally:
+        ctx.close()
+
+
+def test_pyramid_random_and_odd_sizes(binding, abi, O):
+    rng = np.random.default_rng(5)
+    for (w, h, levels) in [(101, 99, 3), (94, 60, 2), (47, 30, 2), (640, 480, 5), (333, 250, 4)]:
+        p = abi.default_params()
+        p.pyramid_levels = levels
+        p.max_align_level = levels - 1
+        p.min_align_level = min(2, levels - 1)
+        p.max_fast_levels = min(3, levels)
+        cam = abi.Camera(w, h, 300, 300, w / 2, h / 2)
+        ctx = binding.Context(p, cam)
+        try:
+            img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            f = ctx.frame(img, corners=False)
+            for l, r in enumerate(O.pyramid(img, levels)):
+                assert np.array_equal(f.level(l), r), f"{w}x{h} level {l}"
+            f.destroy()
+        finally:
+            ctx.close()
+
+
+def _cmp_corners(f, img, P, O, nfeatures, tag):
+    xyl, sc = f.corners()
+    rx, rs = O.detect(P, img, nfeatures)
+    assert len(xyl) == len(rx), f"{tag}: {len(xyl)} corners vs oracle {len(rx)}"
+    same_order = np.array_equal(xyl, rx) and np.array_equal(sc, rs)
+    if not same_order:
+        a = sorted(map(tuple, np.c_[xyl, sc]))
+        b = sorted(map(tuple, np.c_[rx, rs]))
+        assert a == b, f"{tag}: corner SETS differ"
+        raise AssertionError(f"{tag}: same set, different order")
+
+
+@pytest.mark.parametrize("name,seed", [("C1", 3), ("C2", 0), ("C5", 1)])
+def test_fast_bit_exact(binding, sw, O, name, seed):
+    cfg, poses, imgs = sw.sequence(name, seed, 2)
+    ctx = _ctx(binding, cfg)
+    P = cfg["params"]
+    try:
+        for k, img in enumerate(imgs):
+            f = ctx.frame(img, corners=True)
+            _cmp_corners(f, img, P, O, P.num_features, f"{name}[{k}]")
+            # Frame::CreateCorners with another budget (first frame uses 2*num_features, sdvl.cc:135)
+            f.detect(2 * P.num_features)
+            _cmp_corners(f, img, P, O, 2 * P.num_features, f"{name}[{k}] 2x")
+            f.detect(150)
+            _cmp_corners(f, img, P, O, 150, f"{name}[{k}] 150")
+            f.destroy()
+    finally:
+        ctx.close()
+
+
+def test_fast_noise_flat_and_ties(binding, abi, O):
+    """Dense noise (every cell over quota, many score ties), a flat image (no corners) and a blocky image."""
+    rng = np.random.default_rng(11)
+    w, h = 752, 480
+    p = abi.default_params()
+    cam = abi.Camera(w, h, 458.654, 457.296, 367.215, 248.375)
+    ctx = binding.Context(p, cam)
+    try:
+        noise = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        flat = np.full((h, w), 77, np.uint8)
+        blocks = (np.kron(rng.integers(0, 2, (h // 16, w // 16)), np.ones((16, 16))) * 200 + 20).astype(np.uint8)
+        lowc = (noise // 32 * 12).astype(np.uint8)   # few distinct scores -> ties at every retainBest boundary
+        for tag, img in [("noise", noise), ("flat", flat), ("blocks", blocks), ("lowc", lowc)]:
+            f = ctx.frame(img, corners=True)
+            _cmp_corners(f, img, p, O, p.num_features, tag)
+            f.destroy()
+    finally:
+        ctx.close()
+
+
+def _align_case(binding, sw, scenes, O, name, seed, k_ref, k_cur, perturb):
+    cfg, poses, imgs = sw.sequence(name, seed, max(k_ref, k_cur) + 1)
+    P, cam = cfg["params"], cfg["cam"]
+    xyl, _ = O.detect(P, imgs[k_ref], P.num_features)
+    pts = scenes.seed_points(cfg, xyl, poses[k_ref], max_points=cfg["n_feat"])
+    feats = scenes.align_feats(pts, poses[k_ref], invalid_every=17)
+    T_ref = poses[k_ref]
+    T_prior = poses[k_ref].copy() if perturb else poses[k_cur].copy()
+    return cfg, imgs, pts, feats, T_ref, T_prior
+
+
+@pytest.mark.parametrize("name,seed,kc,perturb", [("C2", 0, 1, True), ("C2", 7, 2, True), ("C1", 3, 1, True),
+                                                  ("C3", 2, 1, True), ("C2", 0, 1, False)])
+def test_image_align_teacher_forced(binding, sw, scenes, O, name, seed, kc, perturb):
+    cfg, imgs, pts, feats, T_ref, T_prior = _align_case(binding, sw, scenes, O, name, seed, 0, kc, perturb)
+    P, cam = cfg["params"], cfg["cam"]
+    T_o, nt_o, err_o, tr_o = O.image_align(P, cam, imgs[0], imgs[kc], feats, pts["pos"], T_ref, T_prior)
+    assert len(tr_o) >= 3
+    ctx = _ctx(binding, cfg)
+    try:
+        ref = ctx.frame(imgs[0], corners=False)
+        cur = ctx.frame(imgs[kc], corners=False)
+        iters = np.zeros(8, np.int32)
+        for r in tr_o:
+            iters[r["level"]] += 1
+        T_g, nt_g, err_g, tr_g = ctx.image_align(ref, cur, feats, T_ref, T_prior, forced=(tr_o["T_in"], iters))
+        assert len(tr_g) == len(tr_o)
+        worst = dict(H=0.0, b=0.0, x=0.0, chi2=0.0)
+        for a, b in zip(tr_g, tr_o):
+            assert a["level"] == b["level"] and a["iter"] == b["iter"]
+            assert a["n_meas"] == b["n_meas"], f"n_meas differs at level {a['level']} iter {a['iter']}"
+            for key in ("H", "b", "x"):
+                den = np.abs(b[key]).max()
+                if den > 0:
+                    worst[key] = max(worst[key], np.abs(a[key] - b[key]).max() / den)
+            worst["chi2"] = max(worst["chi2"], abs(a["chi2"] - b["chi2"]) / max(abs(b["chi2"]), 1e-30))
+        print(f"{name} forced GN parity over {len(tr_o)} iterations: {worst}")
+        assert worst["H"] <= REL and worst["b"] <= REL and worst["x"] <= REL and worst["chi2"] <= REL, worst
+
+        # free-running: same pose within GN noise, same tracked count
+        T_f, nt_f, err_f, tr_f = ctx.image_align(ref, cur, feats, T_ref, T_prior)
+        dC = np.linalg.norm(sw.cam_center(T_f) - sw.cam_center(T_o))
+        print(f"{name} free run: iters gpu {len(tr_f)} vs oracle {len(tr_o)}, |dC| = {dC:.3e} m, tracked {nt_f} vs {nt_o}")
+        assert dC < 1e-4
+        assert abs(nt_f - nt_o) <= 2
+        ref.destroy(); cur.destroy()
+    finally:
+        ctx.close()
+
+
+def test_image_align_identity_kat(binding, sw, scenes, O):
+    """Known answer: aligning a frame against itself from the true pose gives b = 0, x = 0."""
+    cfg, poses, imgs = sw.sequence("C2", 4, 1)
+    P = cfg["params"]
+    xyl, _ = O.detect(P, imgs[0], P.num_features)
+    pts = scenes.seed_points(cfg, xyl, poses[0], max_points=200)
+    feats = scenes.align_feats(pts, poses[0])
+    ctx = _ctx(binding, cfg)
+    try:
+        a = ctx.frame(imgs[0], corners=False)
+        b = ctx.frame(imgs[0], corners=False)
+        T, nt, err, tr = ctx.image_align(a, b, feats, poses[0], poses[0])
+        assert nt > 100
+        assert np.abs(tr[0]["b"]).max() < 1e-6 * max(1.0, np.abs(tr[0]["H"]).max())
+        assert np.abs(tr[0]["x"]).max() < 1e-9
+        assert np.allclose(T, poses[0], atol=1e-9)
+        # no features: returns 0 and leaves the pose (image_align.cc:55-58)
+        T2, nt2, _, _ = ctx.image_align(a, b, feats[:0], poses[0], poses[0])
+        assert nt2 == 0 and np.array_equal(T2, poses[0])
+        a.destroy(); b.destroy()
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("name,seed,fixed", [("C2", 0, True), ("C2", 5, False), ("C1", 3, True), ("C3", 2, True)])
+def test_search_points_parity(binding, sw, scenes, abi, O, name, seed, fixed):
+    cfg, poses, imgs = sw.sequence(name, seed, 3)
+    P, cam = cfg["params"], cfg["cam"]
+    xyl, _ = O.detect(P, imgs[0], P.num_features)
+    pts = scenes.seed_points(cfg, xyl, poses[0], one_per_cell=False, margin=0)   # includes points that fail the margins
+    ctx = _ctx(binding, cfg)
+    try:
+        ref = ctx.frame(imgs[0], corners=False)
+        cur = ctx.frame(imgs[2], corners=True)
+        cg = scenes.candidates(pts, poses[0], ref.h, fixed=fixed, project=True, std_frac=0.05 if fixed else 0.02)
+        co = cg.copy()
+        co["ref_frame"] = 0
+        got = ctx.search_points(cur, cg, poses[2])
+        exp = O.search_points(P, cam, imgs[2], poses[2], [imgs[0]], co)
+        assert np.array_equal(got["status"], exp["status"]), \
+            f"status differs for {(got['status'] != exp['status']).sum()} of {len(exp)} candidates"
+        assert np.array_equal(got["n_in_range"], exp["n_in_range"])
+        assert np.array_equal(got["zmssd"], exp["zmssd"])
+        f = exp["status"] == abi.MATCH_FOUND
+        assert f.sum() > 50
+        assert np.array_equal(got["level"][f], exp["level"][f])
+        d = np.abs(got["px"][f] - exp["px"][f]).max()
+        seen = exp["status"] != abi.MATCH_UNSEEN
+        dp = np.abs(got["proj"][seen] - exp["proj"][seen]).max()
+        print(f"{name} fixed={fixed}: {f.sum()} found of {len(exp)}, max |dpx| = {d:.2e}, max |dproj| = {dp:.2e}")
+        assert d <= LK_PX
+        assert dp <= 1e-9
+        ref.destroy(); cur.destroy()
+    finally:
+        ctx.close()
