@@ -113,9 +113,10 @@ void Tracker::HandleFrame(const uint8_t* img, int w, int h, const SE3& gt_pose, 
   for (auto& ft : frame->features)
     if (ft->point && !ft->point->del) nf++;
   s.n_feats = nf;
-  // Frame <-> Feature shared_ptr cycle: the reference breaks it in Map::EmptyTrash (RemoveFeatures); here a
-  // non-keyframe's features are dropped as soon as it stops being the alignment reference.
-  if (last_frame_ && !last_frame_->is_keyframe) last_frame_->features.clear();
+  // Frame <-> Feature shared_ptr cycle: the reference breaks it in Map::EmptyTrash (RemoveFeatures); here a frame's
+  // feature list is dropped as soon as it stops being the alignment reference (keyframes stay alive through the init
+  // features their live points hold).
+  if (last_frame_) last_frame_->features.clear();
   last_frame_ = frame;
   frame_counter_++;
   EmptyTrash();  // sdvl.cc:127

@@ -162,3 +162,93 @@ class Context:
     def track_batch(self, jobs, mirror=1):
         """jobs: ctypes array of TrackJob."""
         _check(load().sdvlb_track_batch(C.c_void_p(self.h), jobs, len(jobs), self.w, self.hh, mirror))
+
+
+# ---------------------------------------------------------------------------------------------- host mirror library
+HOST_LIB_PATH = os.path.join(_HERE, "libsdvl_b200_host.so")
+_HLIB = None
+
+HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", "sdvlh_tracker_destroy",
+                "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_ctx", "sdvlh_tracker_groups"]
+
+
+def build_host(verbose=False):
+    cmd = ["make", "-C", os.path.join(_HERE, "host"), "-j8"]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+    return HOST_LIB_PATH
+
+
+def load_host():
+    global _HLIB
+    if _HLIB is None:
+        load()
+        if not os.path.exists(HOST_LIB_PATH):
+            raise SdvlbError(f"{HOST_LIB_PATH} is missing: build it with slam_sdvl_b200.binding.build_host()")
+        H = C.CDLL(HOST_LIB_PATH)
+        H.sdvlh_last_error.restype = C.c_char_p
+        H.sdvlh_tracker_create.restype = C.c_void_p
+        H.sdvlh_tracker_ctx.restype = C.c_void_p
+        _HLIB = H
+    return _HLIB
+
+
+class HostTracker:
+    """Multi-sequence tracker over the C++ host mirror (Frame / ImageAlign / FeatureAlign classes).
+
+    step(images) takes one image per sequence; `classic=True` drives the reference's per-call class API instead of
+    the batched submission."""
+
+    def __init__(self, params, cam, plane, max_points, kf_every, n_seq, n_groups=1, device=0, timing=False):
+        H = load_host()
+        H.sdvlh_config_set(C.byref(params), C.byref(cam))
+        plane = np.ascontiguousarray(plane, np.float64)
+        self.h = H.sdvlh_tracker_create(ptr(plane), max_points, kf_every, n_seq, n_groups, device, int(timing))
+        if not self.h:
+            raise SdvlbError("sdvlh_tracker_create failed: " + H.sdvlh_last_error().decode())
+        self.n_seq = n_seq
+        self.w, self.hh = int(cam.width), int(cam.height)
+        self._ptrs = (C.c_void_p * n_seq)()
+        self.est = np.zeros((n_seq, 7))
+        self.stats = np.zeros((n_seq, 8), np.int32)
+
+    def step_ptrs(self, ptrs, gt, on_device=False, classic=False):
+        """ptrs: sequence of n_seq raw addresses of w*h u8 images (host, or device when on_device)."""
+        for i, p in enumerate(ptrs):
+            self._ptrs[i] = p
+        gt = np.ascontiguousarray(gt, np.float64)
+        rc = load_host().sdvlh_tracker_step(C.c_void_p(self.h), self._ptrs, int(on_device), int(classic), ptr(gt),
+                                            ptr(self.est), ptr(self.stats))
+        if rc:
+            raise SdvlbError("sdvlh_tracker_step failed: " + load_host().sdvlh_last_error().decode())
+        return self.est, self.stats
+
+    def step(self, images, gt, classic=False):
+        """images: array (n_seq, h, w) u8 (host)."""
+        images = np.ascontiguousarray(images, np.uint8)
+        stride = images.shape[1] * images.shape[2]
+        return self.step_ptrs([images.ctypes.data + i * stride for i in range(self.n_seq)], gt, False, classic)
+
+    def timing_read(self, reset=True):
+        ms = (C.c_double * 5)()
+        n = (C.c_int64 * 5)()
+        load_host().sdvlh_tracker_timing_read(C.c_void_p(self.h), ms, n, int(reset))
+        return {k: (ms[i], n[i]) for i, k in enumerate(K_NAMES)}
+
+    def ctx_handle(self):
+        return load_host().sdvlh_tracker_ctx(C.c_void_p(self.h))
+
+    def groups(self):
+        return load_host().sdvlh_tracker_groups(C.c_void_p(self.h))
+
+    def close(self):
+        if self.h:
+            load_host().sdvlh_tracker_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

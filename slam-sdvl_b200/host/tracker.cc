@@ -1,0 +1,403 @@
+// tracker.cc — sequence drivers over the host mirror + their C entry points (used by tests and bench.py).
+//
+// A sequence is driven like the RUNNING branch of SDVL::HandleFrame (sdvl.cc:55-130): Frame construction
+// (pyramid + FAST), motion-model prior (sdvl.cc:278-281), ProcessFrame = ImageAlign::ComputePose +
+// FeatureAlign::Reproject + OptimizePose (sdvl.cc:179-203), motion-model update (sdvl.cc:266-276), keyframe decision
+// (Map::NeedKeyframe, map.cc:170-188) and EmptyTrash (sdvl.cc:127).  HomographyInit and the mapping thread are out of
+// scope: keyframes get fixed map points seeded from ground-truth depth on a known plane (one per free 32-px cell).
+//
+// Two ways to run the same work:
+//   classic : the reference's own call sequence through the class interfaces, one sequence at a time
+//             (Frame ctor, ImageAlign::ComputePose, FeatureAlign::Reproject, FeatureAlign::OptimizePose);
+//   batched : many sequences in lock-step; per step ONE sdvlb_track_batch submission per group builds all frames,
+//             aligns them and searches every candidate point, then the host replays FeatureAlign's logic.
+//             Groups (one context + one host thread each) overlap one group's host work with another's GPU work.
+// Both give identical results for a sequence (same kernels, same host code, same order of operations).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+
+#include "sdvl_host.h"
+
+using std::shared_ptr;
+using std::vector;
+
+namespace sdvl {
+
+struct SeedPlane { double n[3]; double d; };
+
+struct Sequence {
+  Map map;
+  std::unique_ptr<FeatureAlign> fa;
+  shared_ptr<Frame> last_frame, last_kf;
+  double vel[6] = {0, 0, 0, 0, 0, 0};
+  int frame_counter = 0;
+  int last_matches = 0;
+  // staging for the batched path
+  vector<sdvlb_align_feat> feats;
+  vector<sdvlb_candidate> cands;
+  vector<shared_ptr<Point>> cand_points;
+  vector<sdvlb_match> matches;
+};
+
+class SequenceDriver {
+ public:
+  SequenceDriver(Camera* cam, const SeedPlane& plane, int max_points, int kf_every)
+      : cam_(cam), plane_(plane), max_points_(max_points), kf_every_(kf_every) {}
+
+  void InitSequence(Sequence* s) { s->fa.reset(new FeatureAlign(&s->map, cam_, Config::MaxMatches())); }
+
+  void SeedKeyframe(Sequence* s, const shared_ptr<Frame>& f, const SE3& gt_pose) {
+    f->SetKeyframe();
+    const int cell = Config::CellSize();
+    const int gw = int(std::ceil(cam_->GetWidth() / cell)), gh = int(std::ceil(cam_->GetHeight() / cell));
+    vector<char> occupied(size_t(gw) * gh, 0);
+    int n_points = 0;
+    for (auto& ft : f->GetFeatures()) {
+      if (!ft->GetPoint() || ft->GetPoint()->ToDelete()) continue;
+      n_points++;
+      const int cx = int(ft->GetPosition()(0) / cell), cy = int(ft->GetPosition()(1) / cell);
+      if (cx >= 0 && cx < gw && cy >= 0 && cy < gh) occupied[size_t(cy) * gw + cx] = 1;
+    }
+    const SE3 gt_wc = gt_pose.Inverse();
+    double Rwc[9];
+    gt_wc.GetRotation(Rwc);
+    const Eigen::Vector3d C = gt_wc.GetTranslation();
+    const Eigen::Vector3d est_C = f->GetWorldPosition();
+    const vector<Eigen::Vector3i>& corners = f->GetCorners();
+    const int n = int(corners.size());
+    const int margin = Config::PatchSize() / 2 + 2;
+    for (int i = 0; i < n && n_points < max_points_; i++) {
+      const Eigen::Vector3i& c = corners[size_t((long long)i * 7919 % n)];
+      const int lw = int(cam_->GetWidth()) >> c(2), lh = int(cam_->GetHeight()) >> c(2);
+      if (c(0) < margin || c(1) < margin || c(0) >= lw - margin || c(1) >= lh - margin) continue;
+      const Eigen::Vector2d px(double(c(0) * (1 << c(2))), double(c(1) * (1 << c(2))));
+      const int cx = int(px(0) / cell), cy = int(px(1) / cell);
+      if (occupied[size_t(cy) * gw + cx]) continue;
+      shared_ptr<Feature> ft = std::make_shared<Feature>(f, px, c(2));
+      const Eigen::Vector3d& v = ft->GetVector();
+      const Eigen::Vector3d dir(Rwc[0] * v(0) + Rwc[1] * v(1) + Rwc[2] * v(2), Rwc[3] * v(0) + Rwc[4] * v(1) + Rwc[5] * v(2),
+                                Rwc[6] * v(0) + Rwc[7] * v(1) + Rwc[8] * v(2));
+      const Eigen::Vector3d nrm(plane_.n[0], plane_.n[1], plane_.n[2]);
+      const double denom = nrm.dot(dir);
+      if (std::fabs(denom) < 1e-9) continue;
+      const double sdist = (plane_.d - nrm.dot(C)) / denom;
+      if (sdist <= 0) continue;
+      shared_ptr<Point> pt = std::make_shared<Point>();
+      const Eigen::Vector3d p3d = C + dir * sdist;
+      const double depth = (p3d - est_C).norm();
+      const double rho = 1.0 / depth;
+      pt->InitFixed(ft, p3d, rho, (0.05 * rho) * (0.05 * rho));
+      ft->SetPoint(pt);
+      f->AddFeature(ft);
+      occupied[size_t(cy) * gw + cx] = 1;
+      n_points++;
+    }
+    s->last_kf = f;
+  }
+
+  // Everything SDVL::HandleFrame does after ProcessFrame's GPU part. stats: n_tracked, matches, attempts, inliers,
+  // outliers, n_feats, gn_iters, keyframe.
+  void FinishFrame(Sequence* s, const shared_ptr<Frame>& frame, const SE3& gt_pose, bool first, int32_t* stats) {
+    if (first) {
+      frame->SetPose(gt_pose);
+      SeedKeyframe(s, frame, gt_pose);
+      stats[7] = 1;
+    } else {
+      stats[1] = s->fa->GetMatches();
+      stats[2] = s->fa->GetAttempts();
+      s->fa->OptimizePose(frame);                                   // sdvl.cc:200
+      stats[3] = s->fa->GetInliers();
+      stats[4] = s->fa->GetOutliers();
+      const SE3 mov = frame->GetPose() * s->last_frame->GetPose().Inverse();   // sdvl.cc:266-276
+      double vel[6];
+      SE3::Log(mov, vel);
+      for (int i = 0; i < 6; i++) s->vel[i] = 0.9 * (0.5 * vel[i] + 0.5 * s->vel[i]);
+      const int npoints = frame->GetNumPoints();                   // map.cc:170-188
+      const bool enough_its = (frame->GetID() - s->last_kf->GetID()) >= kf_every_;
+      const bool lost_many = npoints < s->last_matches * 0.7;
+      const bool lost_some = npoints < s->last_matches * 0.9;
+      s->last_matches = std::max(s->last_matches, npoints);
+      if ((enough_its && lost_some) || lost_many) {
+        s->last_matches = npoints;
+        SeedKeyframe(s, frame, gt_pose);
+        stats[7] = 1;
+      }
+    }
+    int nf = 0;
+    for (auto& ft : frame->GetFeatures())
+      if (ft->GetPoint() && !ft->GetPoint()->ToDelete()) nf++;
+    stats[5] = nf;
+    // Frame <-> Feature shared_ptr cycle (the reference breaks it in Map::EmptyTrash / RemoveFeatures): once a frame
+    // stops being the alignment reference nothing on this path reads its feature list again; keyframes stay alive
+    // through the init features their live points hold.
+    if (s->last_frame) s->last_frame->RemoveFeatures();
+    s->last_frame = frame;
+    s->frame_counter++;
+    s->map.EmptyTrash();                                            // sdvl.cc:127
+  }
+
+  // The reference's call sequence through the class interfaces (sdvl.cc:59,92-94,185-200).
+  void ClassicStep(Sequence* s, const uint8_t* img, int w, int h, const SE3& gt_pose, double est[7], int32_t* stats) {
+    std::memset(stats, 0, 8 * sizeof(int32_t));
+    cv::Mat m(h, w, CV_8UC1, const_cast<uint8_t*>(img));
+    shared_ptr<Frame> frame = std::make_shared<Frame>(cam_, static_cast<ORBDetector*>(nullptr), m, true);
+    frame->SetID(s->frame_counter);
+    const bool first = !s->last_frame;
+    if (!first) {
+      frame->SetPose(SE3::Exp(s->vel) * s->last_frame->GetPose());   // SetMotionModel
+      ImageAlign image_align;
+      stats[0] = image_align.ComputePose(s->last_frame, frame);
+      stats[6] = image_align.GetIterations();
+      s->fa->Reproject(frame, s->last_frame, s->last_kf);
+    }
+    FinishFrame(s, frame, gt_pose, first, stats);
+    frame->GetPose().ToArray(est);
+  }
+
+  Camera* cam() { return cam_; }
+
+ private:
+  Camera* cam_;
+  SeedPlane plane_;
+  int max_points_, kf_every_;
+};
+
+// ------------------------------------------------------------------------------------------------ one group
+// One context, one host thread, a fixed subset of the sequences.
+class Group {
+ public:
+  Group(int device, const SeedPlane& plane, int max_points, int kf_every, int n_seq, bool timing)
+      : cam_(), driver_(&cam_, plane, max_points, kf_every), seqs_(n_seq), jobs_(n_seq) {
+    const int rc = sdvlb_ctx_create(device, &Config::Params(), &Config::CameraParams(), &ctx_);
+    if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_create failed: ") + sdvlb_last_error());
+    if (timing) sdvlb_timing_enable(ctx_, 1);
+    for (auto& s : seqs_) driver_.InitSequence(&s);
+  }
+  ~Group() {
+    seqs_.clear();   // frames go back to the pool before the context dies
+    sdvlb_ctx_destroy(ctx_);
+  }
+  int size() const { return int(seqs_.size()); }
+  sdvlb_ctx* ctx() { return ctx_; }
+
+  void StepClassic(const uint8_t* const* images, const double* gt, double* est, int32_t* stats) {
+    Device::SetCurrent(ctx_);
+    const int w = int(cam_.GetWidth()), h = int(cam_.GetHeight());
+    for (int i = 0; i < size(); i++)
+      driver_.ClassicStep(&seqs_[i], images[i], w, h, SE3(gt + 7 * i), est + 7 * i, stats + 8 * i);
+  }
+
+  void StepBatched(const uint8_t* const* images, int on_device, const double* gt, double* est, int32_t* stats) {
+    Device::SetCurrent(ctx_);
+    const int n = size();
+    const int w = int(cam_.GetWidth()), h = int(cam_.GetHeight());
+    std::memset(stats, 0, size_t(n) * 8 * sizeof(int32_t));
+    // ---- phase A: marshal
+    for (int i = 0; i < n; i++) {
+      Sequence& s = seqs_[i];
+      sdvlb_track_job& j = jobs_[i];
+      std::memset(&j, 0, sizeof(j));
+      j.image = images[i];
+      j.image_on_device = on_device;
+      j.want_corners = 1;
+      j.nfeatures = Config::NumFeatures();
+      if (s.last_frame) {
+        (SE3::Exp(s.vel) * s.last_frame->GetPose()).ToArray(j.T_cur);   // sdvl.cc:278-281
+        s.last_frame->GetPose().ToArray(j.T_ref);
+        ImageAlign::CollectFeatures(s.last_frame, &s.feats);
+        s.fa->CollectCandidates(s.frame_counter, s.last_frame, false, &s.cands, &s.cand_points);
+        s.matches.resize(s.cands.size());
+        j.ref = s.last_frame->Handle();
+        j.feats = s.feats.data();
+        j.n_feats = int(s.feats.size());
+        j.cands = s.cands.data();
+        j.n_cands = int(s.cands.size());
+        j.matches = s.matches.data();
+      }
+    }
+    // ---- phase B: one submission
+    const int rc = sdvlb_track_batch(ctx_, jobs_.data(), n, w, h, 1);
+    if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_track_batch failed: ") + sdvlb_last_error());
+    // ---- phase C: host replay
+    for (int i = 0; i < n; i++) {
+      Sequence& s = seqs_[i];
+      sdvlb_track_job& j = jobs_[i];
+      shared_ptr<Frame> frame = std::make_shared<Frame>(&cam_, ctx_, j.cur, s.frame_counter);
+      const bool first = !s.last_frame;
+      int32_t* st = stats + 8 * i;
+      if (!first) {
+        frame->SetPose(SE3(j.T_cur));
+        st[0] = j.n_tracked;
+        s.fa->ApplyMatches(frame, s.cand_points, s.matches.data());
+      }
+      driver_.FinishFrame(&s, frame, SE3(gt + 7 * i), first, st);
+      frame->GetPose().ToArray(est + 7 * i);
+    }
+  }
+
+ private:
+  Camera cam_;
+  SequenceDriver driver_;
+  sdvlb_ctx* ctx_ = nullptr;
+  vector<Sequence> seqs_;
+  vector<sdvlb_track_job> jobs_;
+};
+
+// ------------------------------------------------------------------------------------------------ all groups
+class BatchTracker {
+ public:
+  BatchTracker(const SeedPlane& plane, int max_points, int kf_every, int n_seq, int n_groups, int device, bool timing)
+      : n_seq_(n_seq) {
+    n_groups = std::max(1, std::min(n_groups, n_seq));
+    int left = n_seq;
+    for (int g = 0; g < n_groups; g++) {
+      const int take = (left + (n_groups - g) - 1) / (n_groups - g);
+      offsets_.push_back(n_seq - left);
+      groups_.emplace_back(new Group(device, plane, max_points, kf_every, take, timing));
+      left -= take;
+    }
+    if (n_groups > 1) {
+      for (int g = 0; g < n_groups; g++) workers_.emplace_back([this, g] { WorkerLoop(g); });
+    }
+  }
+  ~BatchTracker() {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      quit_ = true;
+      generation_++;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+    groups_.clear();
+  }
+
+  void Step(const uint8_t* const* images, int on_device, int classic, const double* gt, double* est, int32_t* stats) {
+    images_ = images; on_device_ = on_device; classic_ = classic; gt_ = gt; est_ = est; stats_ = stats;
+    error_.clear();
+    if (workers_.empty()) {
+      RunGroup(0);
+    } else {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        pending_ = int(groups_.size());
+        generation_++;
+      }
+      cv_.notify_all();
+      std::unique_lock<std::mutex> lk(mu_);
+      done_cv_.wait(lk, [this] { return pending_ == 0; });
+    }
+    if (!error_.empty()) throw std::runtime_error(error_);
+  }
+
+  void TimingRead(double ms[SDVLB_K_COUNT], int64_t launches[SDVLB_K_COUNT], int reset) {
+    for (int k = 0; k < SDVLB_K_COUNT; k++) { ms[k] = 0; launches[k] = 0; }
+    for (auto& g : groups_) {
+      double m[SDVLB_K_COUNT];
+      int64_t l[SDVLB_K_COUNT];
+      sdvlb_timing_read(g->ctx(), m, l, reset);
+      for (int k = 0; k < SDVLB_K_COUNT; k++) { ms[k] += m[k]; launches[k] += l[k]; }
+    }
+  }
+  sdvlb_ctx* ctx0() { return groups_[0]->ctx(); }
+  int n_seq() const { return n_seq_; }
+  int n_groups() const { return int(groups_.size()); }
+
+ private:
+  void RunGroup(int g) {
+    try {
+      const int o = offsets_[g];
+      if (classic_) groups_[g]->StepClassic(images_ + o, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
+      else groups_[g]->StepBatched(images_ + o, on_device_, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
+    } catch (const std::exception& e) {
+      std::unique_lock<std::mutex> lk(mu_);
+      error_ = e.what();
+    }
+  }
+  void WorkerLoop(int g) {
+    long seen = 0;
+    while (true) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return generation_ != seen; });
+        seen = generation_;
+        if (quit_) return;
+      }
+      RunGroup(g);
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+
+  int n_seq_;
+  vector<std::unique_ptr<Group>> groups_;
+  vector<int> offsets_;
+  vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  long generation_ = 0;
+  int pending_ = 0;
+  bool quit_ = false;
+  const uint8_t* const* images_ = nullptr;
+  int on_device_ = 0, classic_ = 0;
+  const double* gt_ = nullptr;
+  double* est_ = nullptr;
+  int32_t* stats_ = nullptr;
+  std::string error_;
+};
+
+}  // namespace sdvl
+
+// ================================================================================================ C entry points
+static thread_local std::string g_host_error;
+
+extern "C" {
+
+const char* sdvlh_last_error(void) { return g_host_error.c_str(); }
+
+// Config is process-wide in the reference (singleton, config.h:56); set it before creating trackers.
+void sdvlh_config_set(const sdvlb_params* p, const sdvlb_camera* cam) { sdvl::Config::Set(*p, *cam); }
+
+void* sdvlh_tracker_create(const double plane[4], int max_points, int kf_every, int n_seq, int n_groups, int device,
+                           int timing) {
+  try {
+    sdvl::SeedPlane pl;
+    pl.n[0] = plane[0]; pl.n[1] = plane[1]; pl.n[2] = plane[2]; pl.d = plane[3];
+    return new sdvl::BatchTracker(pl, max_points, kf_every, n_seq, n_groups, device, timing != 0);
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return nullptr;
+  }
+}
+
+void sdvlh_tracker_destroy(void* t) { delete static_cast<sdvl::BatchTracker*>(t); }
+
+// images: n_seq pointers (host, or device when on_device); gt/est: n_seq x 7; stats: n_seq x 8.
+// classic != 0 runs the reference call sequence through the class interfaces instead of the batched submission.
+int sdvlh_tracker_step(void* t, const uint8_t* const* images, int on_device, int classic, const double* gt_poses,
+                       double* est_poses, int32_t* stats) {
+  try {
+    static_cast<sdvl::BatchTracker*>(t)->Step(images, on_device, classic, gt_poses, est_poses, stats);
+    return 0;
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return -1;
+  }
+}
+
+int sdvlh_tracker_timing_read(void* t, double ms[SDVLB_K_COUNT], int64_t launches[SDVLB_K_COUNT], int reset) {
+  static_cast<sdvl::BatchTracker*>(t)->TimingRead(ms, launches, reset);
+  return 0;
+}
+
+void* sdvlh_tracker_ctx(void* t) { return static_cast<sdvl::BatchTracker*>(t)->ctx0(); }
+int sdvlh_tracker_groups(void* t) { return static_cast<sdvl::BatchTracker*>(t)->n_groups(); }
+
+}  // extern "C"
