@@ -111,6 +111,9 @@ int sdvlb_timing_enable(sdvlb_ctx* ctx, int on);
 int sdvlb_timing_read(sdvlb_ctx* ctx, double ms[SDVLB_K_COUNT], int64_t launches[SDVLB_K_COUNT],
                       int reset);
 
+/* Counters since the last reset: kernels launched by this context, bytes copied host->device and device->host. */
+int sdvlb_ctx_counters(sdvlb_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes, int reset);
+
 /* ---- Frame -------------------------------------------------------------- */
 /* Frame::Frame(camera, detector, img, corners): uploads `img` (u8, `stride`
  * bytes per row), builds the pyramid on the device, optionally runs FAST with
@@ -213,7 +216,9 @@ typedef struct sdvlb_track_job {
   int32_t nfeatures;
   int32_t n_feats;
   int32_t n_cands;
-  int32_t n_tracked;        /* out */
+  int32_t n_tracked;        /* out: ImageAlign::ComputePose return value */
+  int32_t gn_iters;         /* out: Gauss-Newton iterations ImageAlign ran */
+  int32_t pad_;
   const sdvlb_frame* ref;   /* last frame (NULL: only build the frame) */
   sdvlb_frame* cur;         /* out: new frame handle (created by the call) */
   const sdvlb_align_feat* feats;

@@ -23,7 +23,7 @@ class SdvlbError(RuntimeError):
 class TrackJob(C.Structure):
     _fields_ = [("image", C.c_void_p), ("image_on_device", C.c_int32), ("want_corners", C.c_int32),
                 ("nfeatures", C.c_int32), ("n_feats", C.c_int32), ("n_cands", C.c_int32), ("n_tracked", C.c_int32),
-                ("ref", C.c_void_p), ("cur", C.c_void_p), ("feats", C.c_void_p), ("cands", C.c_void_p),
+                ("gn_iters", C.c_int32), ("pad_", C.c_int32), ("ref", C.c_void_p), ("cur", C.c_void_p), ("feats", C.c_void_p), ("cands", C.c_void_p),
                 ("matches", C.c_void_p), ("T_ref", C.c_double * 7), ("T_cur", C.c_double * 7), ("error", C.c_double)]
 
 
@@ -57,7 +57,7 @@ def _check(rc):
 EXPORTS = [
     "sdvlb_params_default", "sdvlb_ctx_create", "sdvlb_ctx_destroy", "sdvlb_ctx_sync", "sdvlb_ctx_stream",
     "sdvlb_last_error", "sdvlb_host_alloc", "sdvlb_host_free", "sdvlb_dev_alloc", "sdvlb_dev_free",
-    "sdvlb_dev_upload", "sdvlb_timing_enable", "sdvlb_timing_read", "sdvlb_frame_create", "sdvlb_frame_detect",
+    "sdvlb_dev_upload", "sdvlb_ctx_counters", "sdvlb_timing_enable", "sdvlb_timing_read", "sdvlb_frame_create", "sdvlb_frame_detect",
     "sdvlb_frame_level", "sdvlb_frame_corners", "sdvlb_frame_destroy", "sdvlb_image_align", "sdvlb_search_points",
     "sdvlb_track_batch",
 ]
@@ -169,7 +169,8 @@ HOST_LIB_PATH = os.path.join(_HERE, "libsdvl_b200_host.so")
 _HLIB = None
 
 HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", "sdvlh_tracker_destroy",
-                "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_ctx", "sdvlh_tracker_groups"]
+                "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_ctx",
+                "sdvlh_tracker_groups"]
 
 
 def build_host(verbose=False):
@@ -235,6 +236,12 @@ class HostTracker:
         n = (C.c_int64 * 5)()
         load_host().sdvlh_tracker_timing_read(C.c_void_p(self.h), ms, n, int(reset))
         return {k: (ms[i], n[i]) for i, k in enumerate(K_NAMES)}
+
+    def counters(self, reset=True):
+        """(kernel launches, host->device bytes, device->host bytes) summed over the tracker's contexts."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        load_host().sdvlh_tracker_counters(C.c_void_p(self.h), C.byref(a), C.byref(b), C.byref(c), int(reset))
+        return a.value, b.value, c.value
 
     def ctx_handle(self):
         return load_host().sdvlh_tracker_ctx(C.c_void_p(self.h))

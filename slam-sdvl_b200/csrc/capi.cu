@@ -94,6 +94,8 @@ struct sdvlb_ctx {
   Arena in, out;                 // host->device descriptors, device->host results
   uint8_t* scratch = nullptr;    // device-only scratch for ImageAlign caches
   size_t scratch_cap = 0;
+  // counters
+  int64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   // timing
   bool timing = false;
   std::vector<TimerSlot> timers;
@@ -332,6 +334,14 @@ int sdvlb_dev_upload(sdvlb_ctx* c, void* dst, const void* src, uint64_t bytes) {
   return 0;
 }
 
+int sdvlb_ctx_counters(sdvlb_ctx* c, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes, int reset) {
+  if (kernel_launches) *kernel_launches = c->n_launches;
+  if (h2d_bytes) *h2d_bytes = c->h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = c->d2h_bytes;
+  if (reset) { c->n_launches = 0; c->h2d_bytes = 0; c->d2h_bytes = 0; }
+  return 0;
+}
+
 int sdvlb_timing_enable(sdvlb_ctx* c, int on) { c->timing = on != 0; return 0; }
 int sdvlb_timing_read(sdvlb_ctx* c, double ms[SDVLB_K_COUNT], int64_t launches[SDVLB_K_COUNT], int reset) {
   SDVLB_CUDA_TRY(cudaSetDevice(c->device));
@@ -493,7 +503,11 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
       SDVLB_CUDA_TRY(cudaMemcpyAsync(jobs[i].cur->dev.pyr, jobs[i].image, img_bytes,
                                      jobs[i].image_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                      c->stream));
+  if (build_frames)
+    for (int i = 0; i < n; i++)
+      if (!jobs[i].image_on_device) c->h2d_bytes += int64_t(img_bytes);
   SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, in.used, cudaMemcpyHostToDevice, c->stream));
+  c->h2d_bytes += int64_t(in.used);
   // prior poses for frames that are not aligned (search may still read cur.pose)
   for (int i = 0; i < n; i++)
     if (!jobs[i].ref && jobs[i].n_cands > 0)
@@ -505,6 +519,7 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
     timer_begin(c, SDVLB_K_PYRAMID);
     SDVLB_CUDA_TRY(sdvlb_launch_pyramid(reinterpret_cast<const FrameDev*>(in.d + o_frames), n, g, c->stream));
     timer_end(c);
+    c->n_launches += g.levels - 1;
     if (n_detect > 0) {
       rc = ensure_fast_scratch(c, n_detect);
       if (rc) return rc;
@@ -517,12 +532,14 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
       SDVLB_CUDA_TRY(sdvlb_launch_fast_select(dfr, n_detect, *plan, c->cell_kp, c->cell_cnt, c->level_kp, c->level_cnt,
                                               c->frame_ticket, c->overflow_flag, c->stream));
       timer_end(c);
+      c->n_launches += 2;
     }
   }
   if (n_align > 0) {
     timer_begin(c, SDVLB_K_ALIGN);
     SDVLB_CUDA_TRY(sdvlb_launch_align(in.d + o_align, n_align, g, c->dp, c->stream));
     timer_end(c);
+    c->n_launches += 1;
   }
   if (n_cands > 0) {
     timer_begin(c, SDVLB_K_SEARCH);
@@ -530,17 +547,22 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
                                        reinterpret_cast<const FrameDev*>(in.d + o_frames),
                                        reinterpret_cast<sdvlb_match*>(out.d + o_match), g, c->dp, c->stream));
     timer_end(c);
+    c->n_launches += 1;
   }
 
   // ---- D2H
   SDVLB_CUDA_TRY(cudaMemcpyAsync(out.d + o_flag, c->overflow_flag, 4, cudaMemcpyDeviceToDevice, c->stream));
   SDVLB_CUDA_TRY(cudaMemcpyAsync(out.h, out.d, out.used, cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_bytes += int64_t(out.used);
   if (build_frames && mirror) {
     for (int i = 0; i < n; i++) {
       sdvlb_frame* f = jobs[i].cur;
-      if (mirror >= 2)
+      if (mirror >= 2) {
         SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block, f->d_block, size_t(g.total), cudaMemcpyDeviceToHost, c->stream));
+        c->d2h_bytes += int64_t(g.total);
+      }
       if (jobs[i].want_corners) {
+        c->d2h_bytes += int64_t(c->corner_copy) * 16 + 4;
         SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_xyl, f->d_block + f->off_xyl,
                                        size_t(c->corner_copy) * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_score, f->d_block + f->off_score,
@@ -576,6 +598,7 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
     if (j.ref) {
       memcpy(j.T_cur, res[i].pose, sizeof(j.T_cur));
       j.n_tracked = res[i].info[0] / (c->params.align_patch_size * c->params.align_patch_size);
+      j.gn_iters = res[i].info[1];
       j.error = res[i].error;
       if (first_align) {
         if (trace_n) *trace_n = res[i].info[1];
@@ -641,6 +664,7 @@ int sdvlb_frame_detect(sdvlb_ctx* ctx, sdvlb_frame* f, int nfeatures) {
   SDVLB_CUDA_TRY(sdvlb_launch_fast_select(dfr, 1, *plan, ctx->cell_kp, ctx->cell_cnt, ctx->level_kp, ctx->level_cnt,
                                           ctx->frame_ticket, ctx->overflow_flag, ctx->stream));
   timer_end(ctx);
+  ctx->n_launches += 2;
   int32_t flag = 0;
   SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_cnt, f->d_block + f->off_cnt, sizeof(int32_t),
                                  cudaMemcpyDeviceToHost, ctx->stream));

@@ -234,6 +234,7 @@ class Group {
       if (!first) {
         frame->SetPose(SE3(j.T_cur));
         st[0] = j.n_tracked;
+        st[6] = j.gn_iters;
         s.fa->ApplyMatches(frame, s.cand_points, s.matches.data());
       }
       driver_.FinishFrame(&s, frame, SE3(gt + 7 * i), first, st);
@@ -302,6 +303,14 @@ class BatchTracker {
       int64_t l[SDVLB_K_COUNT];
       sdvlb_timing_read(g->ctx(), m, l, reset);
       for (int k = 0; k < SDVLB_K_COUNT; k++) { ms[k] += m[k]; launches[k] += l[k]; }
+    }
+  }
+  void Counters(int64_t* launches, int64_t* h2d, int64_t* d2h, int reset) {
+    *launches = 0; *h2d = 0; *d2h = 0;
+    for (auto& g : groups_) {
+      int64_t a, b, c;
+      sdvlb_ctx_counters(g->ctx(), &a, &b, &c, reset);
+      *launches += a; *h2d += b; *d2h += c;
     }
   }
   sdvlb_ctx* ctx0() { return groups_[0]->ctx(); }
@@ -394,6 +403,11 @@ int sdvlh_tracker_step(void* t, const uint8_t* const* images, int on_device, int
 
 int sdvlh_tracker_timing_read(void* t, double ms[SDVLB_K_COUNT], int64_t launches[SDVLB_K_COUNT], int reset) {
   static_cast<sdvl::BatchTracker*>(t)->TimingRead(ms, launches, reset);
+  return 0;
+}
+
+int sdvlh_tracker_counters(void* t, int64_t* launches, int64_t* h2d, int64_t* d2h, int reset) {
+  static_cast<sdvl::BatchTracker*>(t)->Counters(launches, h2d, d2h, reset);
   return 0;
 }
 
