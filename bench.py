@@ -182,6 +182,7 @@ def main():
 
     load_pkg()
     sw = importlib.import_module("slam_sdvl_b200.synthworld")
+    sharding = importlib.import_module("slam_sdvl_b200.sharding")
     cfg = sw.config(args.config)
 
     if args.impl == "reference":
@@ -209,8 +210,9 @@ def main():
     host = torch.empty((S, F, h, w), dtype=torch.uint8).pin_memory()
     host_np = host.numpy()
     gt = np.zeros((S, F, 7))
+    seeds = sharding.shard_seeds(rank, world, S)
     for s in range(S):
-        gt[s] = sw.trajectory(cfg, rank * S + s, F)
+        gt[s] = sw.trajectory(cfg, seeds[s], F)
         sw.render(cfg, gt[s], threads=max(1, ncpu // max(1, world)), out=host_np[s])
     frame_bytes = w * h
 
@@ -235,6 +237,7 @@ def main():
             est[:, k] = e
             stats[k] = st
         trk.counters(reset=True)
+        trk.phases(reset=True)
         if timing:
             trk.timing_read(reset=True)
         barrier()
@@ -249,11 +252,8 @@ def main():
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         sec = ev0.elapsed_time(ev1) * 1e-3
-        if world > 1:
-            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            sec = float(t.item())
-        counters = trk.counters(reset=True)
+        sec = sharding.max_over_ranks(sec)
+        counters = trk.counters(reset=True) + (trk.phases(reset=True),)
         ktimes = trk.timing_read(reset=True) if timing else None
         ngroups = trk.groups()
         trk.close()
@@ -336,6 +336,7 @@ def main():
             "max_ate_mm_vs_gt": ate_mm,
             "matches_per_frame": float(stats_v[1 + W:, :, 1].mean()),
             "wall_check_s": {"value": val_wall, "e2e": e2e_wall},
+            "host_phase_thread_seconds": {"value": cnt_v[3], "e2e": cnt_e[3]},
         }
         print(json.dumps(out), flush=True)
     if world > 1:

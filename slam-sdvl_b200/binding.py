@@ -169,7 +169,8 @@ HOST_LIB_PATH = os.path.join(_HERE, "libsdvl_b200_host.so")
 _HLIB = None
 
 HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", "sdvlh_tracker_destroy",
-                "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_ctx",
+                "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_phases",
+                "sdvlh_tracker_ctx",
                 "sdvlh_tracker_groups"]
 
 
@@ -242,6 +243,12 @@ class HostTracker:
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         load_host().sdvlh_tracker_counters(C.c_void_p(self.h), C.byref(a), C.byref(b), C.byref(c), int(reset))
         return a.value, b.value, c.value
+
+    def phases(self, reset=True):
+        """Thread-seconds in host marshalling / GPU submission+wait / host replay, summed over groups."""
+        a = (C.c_double * 3)()
+        load_host().sdvlh_tracker_phases(C.c_void_p(self.h), a, int(reset))
+        return {"marshal_s": a[0], "gpu_submit_wait_s": a[1], "replay_s": a[2]}
 
     def ctx_handle(self):
         return load_host().sdvlh_tracker_ctx(C.c_void_p(self.h))

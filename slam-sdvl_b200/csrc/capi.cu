@@ -60,12 +60,13 @@ struct TimerSlot { cudaEvent_t a, b; int kind; };
 struct sdvlb_frame {
   sdvlb_ctx* ctx = nullptr;
   FrameDev dev{};
-  uint8_t* d_block = nullptr;
-  uint8_t* h_block = nullptr;    // pinned mirror with the same layout
-  size_t off_xyl = 0, off_score = 0, off_cnt = 0, off_pose = 0, block_bytes = 0;
-  bool has_corners = false;
+  uint8_t* d_block = nullptr;    // slot inside one of the context's device slabs
+  size_t off_xyl = 0, off_score = 0, off_cnt = 0, off_pose = 0;
+  uint8_t* h_pyr = nullptr;      // pinned host mirror of the pyramid, allocated on first sdvlb_frame_level()
   bool pyr_mirrored = false;
-  int corners_mirrored = -1;     // number of corners valid in the host mirror, -1 = unknown
+  std::vector<int32_t> h_xyl, h_score;   // host mirror of the corner list
+  bool has_corners = false;
+  int corners_mirrored = -1;     // number of corners valid in the host mirror, -1 = count unknown
   int n_corners = 0;
 };
 
@@ -79,7 +80,10 @@ struct sdvlb_ctx {
   int w = 0, h = 0;
   int corner_cap = 0;
   int corner_copy = 0;           // corners copied eagerly to the host mirror
-  std::vector<sdvlb_frame*> pool;
+  std::vector<sdvlb_frame*> pool;      // free frames (device slot attached)
+  std::vector<sdvlb_frame*> all_frames;
+  std::vector<uint8_t*> slabs;         // device slabs of kSlabFrames frame slots each
+  size_t block_bytes = 0;
   std::vector<FastPlan> plans;   // one per nfeatures budget seen
   // FAST scratch (sized for `fast_frames` frames)
   int fast_frames = 0;
@@ -145,34 +149,38 @@ int ensure_fast_scratch(sdvlb_ctx* c, int n_frames) {
   return 0;
 }
 
+constexpr int kSlabFrames = 32;
+
+// Frames are carved out of device slabs (one cudaMalloc per 32 frames) and recycled through a free list, so the
+// steady state of a tracker performs no CUDA allocation at all.
 int frame_alloc(sdvlb_ctx* c, sdvlb_frame** out) {
-  if (!c->pool.empty()) {
-    sdvlb_frame* f = c->pool.back();
-    c->pool.pop_back();
-    f->has_corners = false; f->pyr_mirrored = false; f->corners_mirrored = -1; f->n_corners = 0;
-    *out = f;
-    return 0;
+  if (c->pool.empty()) {
+    size_t off = align_up(size_t(c->geom.total) + 256, 256);
+    const size_t off_xyl = off;   off = align_up(off + size_t(c->corner_cap) * 3 * sizeof(int32_t), 256);
+    const size_t off_score = off; off = align_up(off + size_t(c->corner_cap) * sizeof(int32_t), 256);
+    const size_t off_cnt = off;   off = align_up(off + 64, 256);
+    const size_t off_pose = off;  off = align_up(off + 7 * sizeof(double), 256);
+    c->block_bytes = off;
+    uint8_t* slab = nullptr;
+    SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&slab), c->block_bytes * kSlabFrames));
+    c->slabs.push_back(slab);
+    for (int i = kSlabFrames - 1; i >= 0; i--) {
+      sdvlb_frame* f = new sdvlb_frame;
+      f->ctx = c;
+      f->d_block = slab + size_t(i) * c->block_bytes;
+      f->off_xyl = off_xyl; f->off_score = off_score; f->off_cnt = off_cnt; f->off_pose = off_pose;
+      f->dev.pyr = f->d_block;
+      f->dev.xyl = reinterpret_cast<int32_t*>(f->d_block + off_xyl);
+      f->dev.score = reinterpret_cast<int32_t*>(f->d_block + off_score);
+      f->dev.n_corners = reinterpret_cast<int32_t*>(f->d_block + off_cnt);
+      f->dev.pose = reinterpret_cast<double*>(f->d_block + off_pose);
+      c->pool.push_back(f);
+      c->all_frames.push_back(f);
+    }
   }
-  sdvlb_frame* f = new sdvlb_frame;
-  f->ctx = c;
-  size_t off = align_up(size_t(c->geom.total) + 256, 256);
-  f->off_xyl = off;   off = align_up(off + size_t(c->corner_cap) * 3 * sizeof(int32_t), 256);
-  f->off_score = off; off = align_up(off + size_t(c->corner_cap) * sizeof(int32_t), 256);
-  f->off_cnt = off;   off = align_up(off + 64, 256);
-  f->off_pose = off;  off = align_up(off + 7 * sizeof(double), 256);
-  f->block_bytes = off;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&f->d_block), f->block_bytes);
-  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&f->h_block), f->block_bytes, cudaHostAllocDefault);
-  if (e != cudaSuccess) {
-    if (f->d_block) cudaFree(f->d_block);
-    delete f;
-    return sdvlb_set_cuda_error(e, "frame_alloc", __FILE__, __LINE__);
-  }
-  f->dev.pyr = f->d_block;
-  f->dev.xyl = reinterpret_cast<int32_t*>(f->d_block + f->off_xyl);
-  f->dev.score = reinterpret_cast<int32_t*>(f->d_block + f->off_score);
-  f->dev.n_corners = reinterpret_cast<int32_t*>(f->d_block + f->off_cnt);
-  f->dev.pose = reinterpret_cast<double*>(f->d_block + f->off_pose);
+  sdvlb_frame* f = c->pool.back();
+  c->pool.pop_back();
+  f->has_corners = false; f->pyr_mirrored = false; f->corners_mirrored = -1; f->n_corners = 0;
   *out = f;
   return 0;
 }
@@ -295,7 +303,8 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (sdvlb_frame* f : c->pool) { cudaFree(f->d_block); cudaFreeHost(f->h_block); delete f; }
+  for (sdvlb_frame* f : c->all_frames) { if (f->h_pyr) cudaFreeHost(f->h_pyr); delete f; }
+  for (uint8_t* slab : c->slabs) cudaFree(slab);
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
   cudaFree(c->frame_ticket); cudaFree(c->overflow_flag); cudaFree(c->scratch);
   if (c->in.h) cudaFreeHost(c->in.h);
@@ -402,8 +411,10 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
   const size_t need_in = 4096 + size_t(n) * (2 * sizeof(FrameDev) + sizeof(AlignJobDev) + 512) +
                          size_t(n_feats) * sizeof(sdvlb_align_feat) + size_t(n_cands) * sizeof(SearchCandDev) +
                          (forced ? size_t(forced->n_total) * 56 + 512 : 0) + 32 * 256;
+  const size_t corner_rec = align_up(size_t(c->corner_copy) * 16 + 256, 256);   // xyl | score | count
   const size_t need_out = 4096 + size_t(n) * sizeof(BatchOut) + size_t(n_cands) * sizeof(sdvlb_match) +
-                          size_t(trace ? trace_cap : 0) * sizeof(sdvlb_gn_iter) + 8 * 256;
+                          size_t(trace ? trace_cap : 0) * sizeof(sdvlb_gn_iter) + 16 * 256 +
+                          ((build_frames && mirror) ? size_t(n) * corner_rec : 0);
   int rc = ensure_arena(&in, need_in, true);
   if (rc) return rc;
   rc = ensure_arena(&out, need_out, true);
@@ -433,6 +444,8 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
   const size_t o_match = out.take(size_t(std::max(n_cands, 1)) * sizeof(sdvlb_match));
   const size_t o_trace = trace ? out.take(size_t(trace_cap) * sizeof(sdvlb_gn_iter)) : 0;
   const size_t o_flag = out.take(64);
+  const size_t dev_out_used = out.used;          // results produced on the device end here
+  const size_t o_corners = (build_frames && mirror) ? out.take(size_t(n) * corner_rec) : 0;   // host-only region
 
   FrameDev* hf = reinterpret_cast<FrameDev*>(in.h + o_frames);
   FrameDev* hd = reinterpret_cast<FrameDev*>(in.h + o_detect);
@@ -552,24 +565,18 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
 
   // ---- D2H
   SDVLB_CUDA_TRY(cudaMemcpyAsync(out.d + o_flag, c->overflow_flag, 4, cudaMemcpyDeviceToDevice, c->stream));
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(out.h, out.d, out.used, cudaMemcpyDeviceToHost, c->stream));
-  c->d2h_bytes += int64_t(out.used);
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(out.h, out.d, dev_out_used, cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_bytes += int64_t(dev_out_used);
   if (build_frames && mirror) {
     for (int i = 0; i < n; i++) {
       sdvlb_frame* f = jobs[i].cur;
-      if (mirror >= 2) {
-        SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block, f->d_block, size_t(g.total), cudaMemcpyDeviceToHost, c->stream));
-        c->d2h_bytes += int64_t(g.total);
-      }
-      if (jobs[i].want_corners) {
-        c->d2h_bytes += int64_t(c->corner_copy) * 16 + 4;
-        SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_xyl, f->d_block + f->off_xyl,
-                                       size_t(c->corner_copy) * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_score, f->d_block + f->off_score,
-                                       size_t(c->corner_copy) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_cnt, f->d_block + f->off_cnt, sizeof(int32_t),
-                                       cudaMemcpyDeviceToHost, c->stream));
-      }
+      if (!jobs[i].want_corners) continue;
+      uint8_t* rec = out.h + o_corners + size_t(i) * corner_rec;   // straight into pinned host memory
+      SDVLB_CUDA_TRY(cudaMemcpyAsync(rec, f->d_block + f->off_xyl, size_t(c->corner_copy) * 12, cudaMemcpyDeviceToHost, c->stream));
+      SDVLB_CUDA_TRY(cudaMemcpyAsync(rec + size_t(c->corner_copy) * 12, f->d_block + f->off_score,
+                                     size_t(c->corner_copy) * 4, cudaMemcpyDeviceToHost, c->stream));
+      SDVLB_CUDA_TRY(cudaMemcpyAsync(rec + size_t(c->corner_copy) * 16, f->d_block + f->off_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+      c->d2h_bytes += int64_t(c->corner_copy) * 16 + 4;
     }
   }
   SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -589,10 +596,14 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
     sdvlb_track_job& j = jobs[i];
     if (build_frames) {
       j.cur->has_corners = j.want_corners != 0;
-      j.cur->pyr_mirrored = mirror >= 2;
       if (j.want_corners && mirror) {
-        memcpy(&j.cur->n_corners, j.cur->h_block + j.cur->off_cnt, sizeof(int32_t));
-        j.cur->corners_mirrored = std::min(j.cur->n_corners, c->corner_copy);
+        const uint8_t* rec = out.h + o_corners + size_t(i) * corner_rec;
+        memcpy(&j.cur->n_corners, rec + size_t(c->corner_copy) * 16, sizeof(int32_t));
+        const int m = std::min(j.cur->n_corners, c->corner_copy);
+        j.cur->h_xyl.assign(reinterpret_cast<const int32_t*>(rec), reinterpret_cast<const int32_t*>(rec) + size_t(m) * 3);
+        j.cur->h_score.assign(reinterpret_cast<const int32_t*>(rec + size_t(c->corner_copy) * 12),
+                              reinterpret_cast<const int32_t*>(rec + size_t(c->corner_copy) * 12) + m);
+        j.cur->corners_mirrored = m;
       }
     }
     if (j.ref) {
@@ -640,7 +651,7 @@ int sdvlb_frame_create(sdvlb_ctx* ctx, const uint8_t* img, int w, int h, int str
   j.image = src;
   j.want_corners = want_corners;
   j.nfeatures = nfeatures;
-  const int rc = run_batch(ctx, &j, 1, 2, nullptr, 0, nullptr, nullptr, true);
+  const int rc = run_batch(ctx, &j, 1, 1, nullptr, 0, nullptr, nullptr, true);
   if (rc) return rc;
   *out = j.cur;
   return 0;
@@ -665,32 +676,34 @@ int sdvlb_frame_detect(sdvlb_ctx* ctx, sdvlb_frame* f, int nfeatures) {
                                           ctx->frame_ticket, ctx->overflow_flag, ctx->stream));
   timer_end(ctx);
   ctx->n_launches += 2;
-  int32_t flag = 0;
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_block + f->off_cnt, f->d_block + f->off_cnt, sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, ctx->stream));
+  int32_t flag = 0, cnt = 0;
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(&cnt, f->d_block + f->off_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   SDVLB_CUDA_TRY(cudaMemcpyAsync(&flag, ctx->overflow_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
   SDVLB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if (flag) {
     cudaMemsetAsync(ctx->overflow_flag, 0, 4, ctx->stream);
     return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in FAST selection");
   }
-  memcpy(&f->n_corners, f->h_block + f->off_cnt, sizeof(int32_t));
+  f->n_corners = cnt;
   f->has_corners = true;
   f->corners_mirrored = 0;
+  f->h_xyl.clear(); f->h_score.clear();
   return 0;
 }
 
 int sdvlb_frame_level(const sdvlb_frame* f, int level, const uint8_t** data, int* w, int* h) {
   if (!f || level < 0 || level >= f->ctx->geom.levels) return sdvlb_set_error(SDVLB_ERR_ARG, "bad level");
   sdvlb_frame* mf = const_cast<sdvlb_frame*>(f);
-  if (!mf->pyr_mirrored) {   // lazy mirror
+  if (!mf->pyr_mirrored) {   // the host mirror is materialised on first use
     sdvlb_ctx* c = f->ctx;
     SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_block, mf->d_block, size_t(c->geom.total), cudaMemcpyDeviceToHost, c->stream));
+    if (!mf->h_pyr) SDVLB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&mf->h_pyr), size_t(c->geom.total), cudaHostAllocDefault));
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_pyr, mf->d_block, size_t(c->geom.total), cudaMemcpyDeviceToHost, c->stream));
     SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += int64_t(c->geom.total);
     mf->pyr_mirrored = true;
   }
-  if (data) *data = f->h_block + f->ctx->geom.off[level];
+  if (data) *data = f->h_pyr + f->ctx->geom.off[level];
   if (w) *w = f->ctx->geom.w[level];
   if (h) *h = f->ctx->geom.h[level];
   return 0;
@@ -703,23 +716,26 @@ int sdvlb_frame_corners(const sdvlb_frame* f, const int32_t** xyl, const int32_t
   sdvlb_ctx* c = f->ctx;
   if (mf->corners_mirrored < 0) {
     SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_block + mf->off_cnt, mf->d_block + mf->off_cnt, sizeof(int32_t),
-                                   cudaMemcpyDeviceToHost, c->stream));
+    int32_t cnt = 0;
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(&cnt, mf->d_block + mf->off_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    memcpy(&mf->n_corners, mf->h_block + mf->off_cnt, sizeof(int32_t));
+    mf->n_corners = cnt;
     mf->corners_mirrored = 0;
   }
   if (mf->corners_mirrored < mf->n_corners) {
     SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_block + mf->off_xyl, mf->d_block + mf->off_xyl,
-                                   size_t(mf->n_corners) * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_block + mf->off_score, mf->d_block + mf->off_score,
-                                   size_t(mf->n_corners) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    mf->h_xyl.resize(size_t(mf->n_corners) * 3);
+    mf->h_score.resize(size_t(mf->n_corners));
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_xyl.data(), mf->d_block + mf->off_xyl, size_t(mf->n_corners) * 12,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_score.data(), mf->d_block + mf->off_score, size_t(mf->n_corners) * 4,
+                                   cudaMemcpyDeviceToHost, c->stream));
     SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += int64_t(mf->n_corners) * 16;
     mf->corners_mirrored = mf->n_corners;
   }
-  if (xyl) *xyl = reinterpret_cast<const int32_t*>(f->h_block + f->off_xyl);
-  if (score) *score = reinterpret_cast<const int32_t*>(f->h_block + f->off_score);
+  if (xyl) *xyl = mf->h_xyl.data();
+  if (score) *score = mf->h_score.data();
   if (n) *n = f->n_corners;
   return 0;
 }

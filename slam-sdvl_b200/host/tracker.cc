@@ -15,6 +15,7 @@
 // Both give identical results for a sequence (same kernels, same host code, same order of operations).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstring>
@@ -198,6 +199,7 @@ class Group {
     const int n = size();
     const int w = int(cam_.GetWidth()), h = int(cam_.GetHeight());
     std::memset(stats, 0, size_t(n) * 8 * sizeof(int32_t));
+    const auto tA = std::chrono::steady_clock::now();
     // ---- phase A: marshal
     for (int i = 0; i < n; i++) {
       Sequence& s = seqs_[i];
@@ -222,8 +224,10 @@ class Group {
       }
     }
     // ---- phase B: one submission
+    const auto tB = std::chrono::steady_clock::now();
     const int rc = sdvlb_track_batch(ctx_, jobs_.data(), n, w, h, 1);
     if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_track_batch failed: ") + sdvlb_last_error());
+    const auto tC = std::chrono::steady_clock::now();
     // ---- phase C: host replay
     for (int i = 0; i < n; i++) {
       Sequence& s = seqs_[i];
@@ -240,7 +244,13 @@ class Group {
       driver_.FinishFrame(&s, frame, SE3(gt + 7 * i), first, st);
       frame->GetPose().ToArray(est + 7 * i);
     }
+    const auto tD = std::chrono::steady_clock::now();
+    phase_s_[0] += std::chrono::duration<double>(tB - tA).count();
+    phase_s_[1] += std::chrono::duration<double>(tC - tB).count();
+    phase_s_[2] += std::chrono::duration<double>(tD - tC).count();
   }
+  const double* phase_seconds() const { return phase_s_; }
+  void reset_phases() { phase_s_[0] = phase_s_[1] = phase_s_[2] = 0; }
 
  private:
   Camera cam_;
@@ -248,6 +258,7 @@ class Group {
   sdvlb_ctx* ctx_ = nullptr;
   vector<Sequence> seqs_;
   vector<sdvlb_track_job> jobs_;
+  double phase_s_[3] = {0, 0, 0};   // host marshal, GPU submission (incl. wait), host replay
 };
 
 // ------------------------------------------------------------------------------------------------ all groups
@@ -311,6 +322,13 @@ class BatchTracker {
       int64_t a, b, c;
       sdvlb_ctx_counters(g->ctx(), &a, &b, &c, reset);
       *launches += a; *h2d += b; *d2h += c;
+    }
+  }
+  void Phases(double out[3], int reset) {   // summed over groups (thread-seconds)
+    out[0] = out[1] = out[2] = 0;
+    for (auto& g : groups_) {
+      for (int i = 0; i < 3; i++) out[i] += g->phase_seconds()[i];
+      if (reset) g->reset_phases();
     }
   }
   sdvlb_ctx* ctx0() { return groups_[0]->ctx(); }
@@ -408,6 +426,12 @@ int sdvlh_tracker_timing_read(void* t, double ms[SDVLB_K_COUNT], int64_t launche
 
 int sdvlh_tracker_counters(void* t, int64_t* launches, int64_t* h2d, int64_t* d2h, int reset) {
   static_cast<sdvl::BatchTracker*>(t)->Counters(launches, h2d, d2h, reset);
+  return 0;
+}
+
+// Thread-seconds spent in: [0] host marshalling, [1] the batched GPU submission (launch + wait), [2] host replay.
+int sdvlh_tracker_phases(void* t, double out[3], int reset) {
+  static_cast<sdvl::BatchTracker*>(t)->Phases(out, reset);
   return 0;
 }
 
