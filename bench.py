@@ -169,7 +169,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU")
-    ap.add_argument("--groups", type=int, default=0, help="host threads / contexts per GPU (0 = auto)")
+    ap.add_argument("--groups", type=int, default=0, help="contexts (stream pairs) per GPU (0 = 2 per host thread)")
+    ap.add_argument("--threads", type=int, default=0, help="host threads per GPU (0 = cores / ranks)")
     ap.add_argument("--kf-every", type=int, default=20)
     ap.add_argument("--config", default="C2")
     args = ap.parse_args()
@@ -204,7 +205,8 @@ def main():
     F = 1 + W + K                       # frame 0 initialises every sequence (ground-truth pose + map seeding)
     w, h = cfg["w"], cfg["h"]
     ncpu = os.cpu_count() or 1
-    groups = args.groups or max(1, min(S, ncpu // max(1, world)))
+    threads = args.threads or max(1, min(S, ncpu // max(1, world)))
+    groups = args.groups or max(1, min(S, 2 * threads))
 
     # ---- synthetic frames, rendered once into pinned host memory
     host = torch.empty((S, F, h, w), dtype=torch.uint8).pin_memory()
@@ -222,20 +224,30 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_run(base_ptr, on_device, n_groups, timing=False):
-        """Fresh tracker; init + warm-up untimed; K timed steps. Returns seconds (max over ranks), est, stats, extras."""
+    def timed_run(base_ptr, on_device, n_groups, timing=False, pipelined=True):
+        """Fresh tracker; init + warm-up untimed; K timed steps. Returns seconds (max over ranks), est, stats, extras.
+        pipelined: sdvlh_tracker_run (frame batches one step ahead, groups free-running); otherwise every step is one
+        synchronous lock-step submission (used for the per-kernel timing pass, where launches must not overlap)."""
         trk = binding.HostTracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], args.kf_every, S, n_groups,
-                                  device=local_rank, timing=timing)
+                                  device=local_rank, timing=timing, n_threads=min(n_groups, threads))
         est = np.zeros((S, F, 7))
         stats = np.zeros((F, S, 8), np.int32)
 
-        def ptrs(k):
-            return [base_ptr + (s * F + k) * frame_bytes for s in range(S)]
+        ptr_tab = (base_ptr + (np.arange(S, dtype=np.uint64)[:, None] * F + np.arange(F, dtype=np.uint64)[None, :])
+                   * np.uint64(frame_bytes))
+        def go(k0, k1):
+            if pipelined:
+                e, st = trk.run_ptrs(ptr_tab[:, k0:k1], gt[:, k0:k1], on_device=on_device)
+                est[:, k0:k1] = e
+                stats[k0:k1] = st.transpose(1, 0, 2)
+            else:
+                for k in range(k0, k1):
+                    e, st = trk.step_ptrs([int(p) for p in ptr_tab[:, k]], gt[:, k], on_device=on_device)
+                    est[:, k] = e
+                    stats[k] = st
 
-        for k in range(1 + W):
-            e, st = trk.step_ptrs(ptrs(k), gt[:, k], on_device=on_device)
-            est[:, k] = e
-            stats[k] = st
+        # init frame + warm-up steps (untimed), then K timed steps
+        go(0, 1 + W)
         trk.counters(reset=True)
         trk.phases(reset=True)
         if timing:
@@ -244,10 +256,7 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record()
-        for k in range(1 + W, F):
-            e, st = trk.step_ptrs(ptrs(k), gt[:, k], on_device=on_device)
-            est[:, k] = e
-            stats[k] = st
+        go(1 + W, F)
         ev1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -268,7 +277,8 @@ def main():
     val_sec, val_wall, est_v, stats_v, cnt_v, _, _ = timed_run(dev.data_ptr(), True, groups)
     clock_info = clocks.stop()
     # ---- kernel pass: one context so launches do not overlap, per-kernel CUDA events on the launching stream
-    k_sec, _, _, stats_k, _, ktimes, _ = timed_run(dev.data_ptr(), True, 1, timing=True)
+    k_sec, _, est_k, stats_k, _, ktimes, _ = timed_run(dev.data_ptr(), True, 1, timing=True, pipelined=False)
+    assert np.array_equal(est_k, est_v), "pipelined and lock-step runs must be the same computation"
 
     assert np.array_equal(est_e, est_v), "host-resident and HBM-resident runs must be the same computation"
     total_frames = S * K * world
@@ -321,7 +331,7 @@ def main():
             "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
             "config": {"workload": "C2: 752x480 EuRoC-shaped synthetic sequences, 5-level pyramid, 200 features, "
                                    "pyramid+FAST+ImageAlign+FeatureAlign", "sequences_per_gpu": S,
-                       "step": "one new frame for every sequence of the GPU", "host_groups_per_gpu": ngroups,
+                       "step": "one new frame for every sequence of the GPU", "host_groups_per_gpu": ngroups, "host_threads_per_gpu": min(ngroups, threads),
                        "cache": "every step consumes frames never seen before (inputs 0.36 MB x sequences per step, "
                                 f"{S * F * frame_bytes / 1e6:.0f} MB total, larger than L2); no L2 flush needed",
                        "kf_every": args.kf_every},

@@ -6,7 +6,7 @@
  * four C++ classes.  Each entry point below names the reference interface it
  * replaces (file:line relative to the reference tree):
  *
- *   sdvlb_frame_create / _detect / _level / _corners
+ *   sdvlb_frame_create / _detect / _level / _corners / sdvlb_frames_submit
  *        -> Frame::Frame, Frame::CreatePyramid, Frame::CreateCorners,
  *           Frame::GetPyramid, Frame::GetCorners
  *           (frame.h:45,58-60,139; frame.cc:34-56,114-131;
@@ -125,10 +125,12 @@ int sdvlb_frame_create(sdvlb_ctx* ctx, const uint8_t* img, int w, int h, int str
 int sdvlb_frame_detect(sdvlb_ctx* ctx, sdvlb_frame* f, int nfeatures);
 /* Frame::GetPyramid()[l]: continuous u8 host mirror (stride == *w). */
 int sdvlb_frame_level(const sdvlb_frame* f, int level, const uint8_t** data, int* w, int* h);
-/* Frame::GetCorners(): n triplets (x, y, level) in level coordinates, in the
- * reference's order; `score` holds cv::KeyPoint::response (not kept by the
- * reference, exposed for parity checks). */
-int sdvlb_frame_corners(const sdvlb_frame* f, const int32_t** xyl, const int32_t** score, int* n);
+/* Frame::GetCorners(): n records (x, y, level, score), 4 x int32 each, in level
+ * coordinates and in the reference's order; score = cv::KeyPoint::response
+ * (not kept by the reference, exposed for parity checks).  The pointer aims
+ * into the frame's pinned host mirror and stays valid until the frame is
+ * destroyed or re-detected. */
+int sdvlb_frame_corners(const sdvlb_frame* f, const int32_t** xyls, int* n);
 int sdvlb_frame_destroy(sdvlb_ctx* ctx, sdvlb_frame* f);
 
 /* ---- ImageAlign --------------------------------------------------------- */
@@ -210,7 +212,8 @@ int sdvlb_search_points(sdvlb_ctx* ctx, const sdvlb_frame* cur, const sdvlb_cand
 
 /* ---- batched front half of ProcessFrame -------------------------------- */
 typedef struct sdvlb_track_job {
-  const uint8_t* image;     /* w*h u8, continuous; host (pinned preferred) or device */
+  const uint8_t* image;     /* w*h u8, continuous; host (pinned preferred) or device.
+                               NULL: `cur` is a frame made by sdvlb_frames_submit */
   int32_t image_on_device;
   int32_t want_corners;
   int32_t nfeatures;
@@ -220,7 +223,7 @@ typedef struct sdvlb_track_job {
   int32_t gn_iters;         /* out: Gauss-Newton iterations ImageAlign ran */
   int32_t pad_;
   const sdvlb_frame* ref;   /* last frame (NULL: only build the frame) */
-  sdvlb_frame* cur;         /* out: new frame handle (created by the call) */
+  sdvlb_frame* cur;         /* out: new frame handle (created by the call); in: prebuilt frame when image == NULL */
   const sdvlb_align_feat* feats;
   const sdvlb_candidate* cands;
   sdvlb_match* matches;     /* out, n_cands entries */
@@ -234,6 +237,27 @@ typedef struct sdvlb_track_job {
  * launches with a single synchronisation at the end.  `mirror` != 0 also
  * copies pyramids and corners to the pinned host mirrors of the new frames. */
 int sdvlb_track_batch(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, int mirror);
+
+/* ---- asynchronous forms ("frame batches" + overlapped tracking) ----------
+ * Frames of one sequence depend on each other only through ImageAlign and
+ * FeatureAlign (sdvl.cc:93,119,278-281); Frame construction (frame.cc:34-56)
+ * does not.  sdvlb_frames_submit enqueues upload + pyramid (+ FAST when
+ * want_corners) for n images on the context's BUILD stream and returns at
+ * once; the handles can be given to sdvlb_track_batch / _submit as jobs with
+ * image == NULL (ordered after the build on the device), or waited for on the
+ * host with sdvlb_frames_wait / any sdvlb_frame_* accessor.  Images must stay
+ * valid until then.  All jobs of one batch either carry images or prebuilt
+ * frames. */
+int sdvlb_frames_submit(sdvlb_ctx* ctx, const uint8_t* const* images, int n, int images_on_device,
+                        int want_corners, int nfeatures, sdvlb_frame** out);
+int sdvlb_frames_wait(sdvlb_ctx* ctx, sdvlb_frame* const* frames, int n);
+/* sdvlb_track_batch split in two: _submit enqueues everything on the TRACKING
+ * stream and returns; _poll returns 1 when the device has finished (0 while
+ * running, <0 on error); _collect waits and fills the jobs' outputs.  `jobs`
+ * must stay valid until _collect; one submission in flight per context. */
+int sdvlb_track_submit(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, int mirror);
+int sdvlb_track_poll(sdvlb_ctx* ctx);
+int sdvlb_track_collect(sdvlb_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -59,7 +59,8 @@ EXPORTS = [
     "sdvlb_last_error", "sdvlb_host_alloc", "sdvlb_host_free", "sdvlb_dev_alloc", "sdvlb_dev_free",
     "sdvlb_dev_upload", "sdvlb_ctx_counters", "sdvlb_timing_enable", "sdvlb_timing_read", "sdvlb_frame_create", "sdvlb_frame_detect",
     "sdvlb_frame_level", "sdvlb_frame_corners", "sdvlb_frame_destroy", "sdvlb_image_align", "sdvlb_search_points",
-    "sdvlb_track_batch",
+    "sdvlb_track_batch", "sdvlb_frames_submit", "sdvlb_frames_wait", "sdvlb_track_submit", "sdvlb_track_poll",
+    "sdvlb_track_collect",
 ]
 
 
@@ -74,13 +75,12 @@ class Frame:
         return np.frombuffer(buf, np.uint8).reshape(h.value, w.value).copy()
 
     def corners(self):
-        xyl, sc, n = C.c_void_p(), C.c_void_p(), C.c_int()
-        _check(load().sdvlb_frame_corners(C.c_void_p(self.h), C.byref(xyl), C.byref(sc), C.byref(n)))
+        xyls, n = C.c_void_p(), C.c_int()
+        _check(load().sdvlb_frame_corners(C.c_void_p(self.h), C.byref(xyls), C.byref(n)))
         if n.value == 0:
             return np.zeros((0, 3), np.int32), np.zeros(0, np.int32)
-        a = np.frombuffer((C.c_int32 * (3 * n.value)).from_address(xyl.value), np.int32).reshape(-1, 3).copy()
-        s = np.frombuffer((C.c_int32 * n.value).from_address(sc.value), np.int32).copy()
-        return a, s
+        a = np.frombuffer((C.c_int32 * (4 * n.value)).from_address(xyls.value), np.int32).reshape(-1, 4)
+        return a[:, :3].copy(), a[:, 3].copy()
 
     def detect(self, nfeatures):
         _check(load().sdvlb_frame_detect(C.c_void_p(self.ctx.h), C.c_void_p(self.h), nfeatures))
@@ -170,8 +170,7 @@ _HLIB = None
 
 HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", "sdvlh_tracker_destroy",
                 "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_phases",
-                "sdvlh_tracker_ctx",
-                "sdvlh_tracker_groups"]
+                "sdvlh_tracker_ctx", "sdvlh_tracker_groups", "sdvlh_tracker_threads", "sdvlh_tracker_run"]
 
 
 def build_host(verbose=False):
@@ -202,11 +201,13 @@ class HostTracker:
     step(images) takes one image per sequence; `classic=True` drives the reference's per-call class API instead of
     the batched submission."""
 
-    def __init__(self, params, cam, plane, max_points, kf_every, n_seq, n_groups=1, device=0, timing=False):
+    def __init__(self, params, cam, plane, max_points, kf_every, n_seq, n_groups=1, device=0, timing=False,
+                 n_threads=0):
         H = load_host()
         H.sdvlh_config_set(C.byref(params), C.byref(cam))
         plane = np.ascontiguousarray(plane, np.float64)
-        self.h = H.sdvlh_tracker_create(ptr(plane), max_points, kf_every, n_seq, n_groups, device, int(timing))
+        self.h = H.sdvlh_tracker_create(ptr(plane), max_points, kf_every, n_seq, n_groups, n_threads, device,
+                                        int(timing))
         if not self.h:
             raise SdvlbError("sdvlh_tracker_create failed: " + H.sdvlh_last_error().decode())
         self.n_seq = n_seq
@@ -231,6 +232,32 @@ class HostTracker:
         images = np.ascontiguousarray(images, np.uint8)
         stride = images.shape[1] * images.shape[2]
         return self.step_ptrs([images.ctypes.data + i * stride for i in range(self.n_seq)], gt, False, classic)
+
+    def run_ptrs(self, ptrs, gt, on_device=False):
+        """Pipelined run. ptrs: (n_seq, n_steps) array of raw image addresses; gt: (n_seq, n_steps, 7).
+        Returns est (n_seq, n_steps, 7) and stats (n_seq, n_steps, 8)."""
+        ptrs = np.ascontiguousarray(ptrs, np.uint64)
+        n_steps = ptrs.shape[1]
+        assert ptrs.shape[0] == self.n_seq
+        gt = np.ascontiguousarray(gt, np.float64)
+        est = np.zeros((self.n_seq, n_steps, 7))
+        stats = np.zeros((self.n_seq, n_steps, 8), np.int32)
+        rc = load_host().sdvlh_tracker_run(C.c_void_p(self.h), ptr(ptrs), int(on_device), n_steps, ptr(gt), ptr(est),
+                                           ptr(stats))
+        if rc:
+            raise SdvlbError("sdvlh_tracker_run failed: " + load_host().sdvlh_last_error().decode())
+        return est, stats
+
+    def run(self, images, gt):
+        """images: (n_seq, n_steps, h, w) u8 host array."""
+        images = np.ascontiguousarray(images, np.uint8)
+        s0, s1 = images.strides[0], images.strides[1]
+        ptrs = images.ctypes.data + np.arange(images.shape[0], dtype=np.uint64)[:, None] * s0 + \
+            np.arange(images.shape[1], dtype=np.uint64)[None, :] * s1
+        return self.run_ptrs(ptrs, gt)
+
+    def threads(self):
+        return load_host().sdvlh_tracker_threads(C.c_void_p(self.h))
 
     def timing_read(self, reset=True):
         ms = (C.c_double * 5)()

@@ -55,24 +55,54 @@ struct Arena {   // bump allocator over a (pinned host, device) buffer pair with
 
 struct TimerSlot { cudaEvent_t a, b; int kind; };
 
+struct BuildSlot {   // staging of one asynchronous frame-batch submission
+  Arena a;
+  cudaEvent_t done = nullptr;
+  bool used = false;
+};
+constexpr int kBuildSlots = 4;
+
 }  // namespace
 
 struct sdvlb_frame {
   sdvlb_ctx* ctx = nullptr;
   FrameDev dev{};
   uint8_t* d_block = nullptr;    // slot inside one of the context's device slabs
-  size_t off_xyl = 0, off_score = 0, off_cnt = 0, off_pose = 0;
+  size_t off_hdr = 0, off_pose = 0;   // corner header (count) + int4 corner list; pose
   uint8_t* h_pyr = nullptr;      // pinned host mirror of the pyramid, allocated on first sdvlb_frame_level()
   bool pyr_mirrored = false;
-  std::vector<int32_t> h_xyl, h_score;   // host mirror of the corner list
+  uint8_t* h_corners = nullptr;  // pinned host mirror: 16-byte header (count) + the first corner_copy corners
+  std::vector<int32_t> h_more;   // whole corner list, only when it is longer than corner_copy
+  cudaEvent_t built = nullptr;   // recorded on the build stream after the frame's last build command
+  bool build_pending = false;    // submitted with sdvlb_frames_submit, completion not yet observed by the host
+  bool build_corners = false, build_mirror = false;
   bool has_corners = false;
   int corners_mirrored = -1;     // number of corners valid in the host mirror, -1 = count unknown
   int n_corners = 0;
 };
 
+// Everything sdvlb_track_collect needs to finish a submission made by submit_batch.
+struct PendingTrack {
+  bool active = false;
+  sdvlb_track_job* jobs = nullptr;
+  int n = 0;
+  bool build_frames = false;
+  sdvlb_gn_iter* trace = nullptr;
+  int trace_cap = 0;
+  int* trace_n = nullptr;
+  size_t o_res = 0, o_match = 0, o_trace = 0, o_flag = 0;
+};
+
 struct sdvlb_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;    // tracking stream (ImageAlign, SearchPoint, synchronous frame construction)
+  cudaStream_t bstream = nullptr;   // build stream (asynchronous frame batches: upload, pyramid, FAST)
+  BuildSlot bslots[kBuildSlots];
+  int bslot_next = 0;
+  cudaEvent_t last_build = nullptr; // last command of the most recent asynchronous build
+  bool build_in_flight = false;
+  cudaEvent_t track_done = nullptr;
+  PendingTrack* pending = nullptr;
   sdvlb_params params{};
   sdvlb_camera cam{};
   PyrGeom geom{};
@@ -104,6 +134,7 @@ struct sdvlb_ctx {
   bool timing = false;
   std::vector<TimerSlot> timers;
   size_t timers_used = 0;
+  cudaStream_t timer_stream = nullptr;
   double t_ms[SDVLB_K_COUNT] = {0, 0, 0, 0, 0};
   int64_t t_launches[SDVLB_K_COUNT] = {0, 0, 0, 0, 0};
 };
@@ -156,9 +187,7 @@ constexpr int kSlabFrames = 32;
 int frame_alloc(sdvlb_ctx* c, sdvlb_frame** out) {
   if (c->pool.empty()) {
     size_t off = align_up(size_t(c->geom.total) + 256, 256);
-    const size_t off_xyl = off;   off = align_up(off + size_t(c->corner_cap) * 3 * sizeof(int32_t), 256);
-    const size_t off_score = off; off = align_up(off + size_t(c->corner_cap) * sizeof(int32_t), 256);
-    const size_t off_cnt = off;   off = align_up(off + 64, 256);
+    const size_t off_hdr = off;   off = align_up(off + 16 + size_t(c->corner_cap) * sizeof(int4), 256);
     const size_t off_pose = off;  off = align_up(off + 7 * sizeof(double), 256);
     c->block_bytes = off;
     uint8_t* slab = nullptr;
@@ -168,12 +197,12 @@ int frame_alloc(sdvlb_ctx* c, sdvlb_frame** out) {
       sdvlb_frame* f = new sdvlb_frame;
       f->ctx = c;
       f->d_block = slab + size_t(i) * c->block_bytes;
-      f->off_xyl = off_xyl; f->off_score = off_score; f->off_cnt = off_cnt; f->off_pose = off_pose;
+      f->off_hdr = off_hdr; f->off_pose = off_pose;
       f->dev.pyr = f->d_block;
-      f->dev.xyl = reinterpret_cast<int32_t*>(f->d_block + off_xyl);
-      f->dev.score = reinterpret_cast<int32_t*>(f->d_block + off_score);
-      f->dev.n_corners = reinterpret_cast<int32_t*>(f->d_block + off_cnt);
+      f->dev.n_corners = reinterpret_cast<int32_t*>(f->d_block + off_hdr);
+      f->dev.corners = reinterpret_cast<int4*>(f->d_block + off_hdr + 16);
       f->dev.pose = reinterpret_cast<double*>(f->d_block + off_pose);
+      SDVLB_CUDA_TRY(cudaEventCreateWithFlags(&f->built, cudaEventDisableTiming));
       c->pool.push_back(f);
       c->all_frames.push_back(f);
     }
@@ -181,6 +210,7 @@ int frame_alloc(sdvlb_ctx* c, sdvlb_frame** out) {
   sdvlb_frame* f = c->pool.back();
   c->pool.pop_back();
   f->has_corners = false; f->pyr_mirrored = false; f->corners_mirrored = -1; f->n_corners = 0;
+  f->build_pending = false; f->build_corners = false; f->build_mirror = false;
   *out = f;
   return 0;
 }
@@ -188,8 +218,10 @@ int frame_alloc(sdvlb_ctx* c, sdvlb_frame** out) {
 void frame_release(sdvlb_ctx* c, sdvlb_frame* f) { c->pool.push_back(f); }
 
 // ---- timing helpers
-void timer_begin(sdvlb_ctx* c, int kind) {
+void timer_begin(sdvlb_ctx* c, int kind, cudaStream_t stream = nullptr) {
   if (!c->timing) return;
+  if (!stream) stream = c->stream;
+  c->timer_stream = stream;
   if (c->timers_used == c->timers.size()) {
     TimerSlot s;
     cudaEventCreate(&s.a);
@@ -198,11 +230,11 @@ void timer_begin(sdvlb_ctx* c, int kind) {
   }
   TimerSlot& s = c->timers[c->timers_used];
   s.kind = kind;
-  cudaEventRecord(s.a, c->stream);
+  cudaEventRecord(s.a, stream);
 }
 void timer_end(sdvlb_ctx* c) {
   if (!c->timing) return;
-  cudaEventRecord(c->timers[c->timers_used].b, c->stream);
+  cudaEventRecord(c->timers[c->timers_used].b, c->timer_stream);
   c->timers_used++;
 }
 void timer_collect(sdvlb_ctx* c) {   // stream must be idle
@@ -288,7 +320,14 @@ int sdvlb_ctx_create(int device, const sdvlb_params* params, const sdvlb_camera*
   build_geom(p, w, h, &c->geom);
   c->corner_cap = std::max(8192, 8 * p.num_features);
   c->corner_copy = std::min(c->corner_cap, std::max(2048, 2 * p.num_features));
-  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  // tracking is the latency-critical chain of a sequence; frame batches are prefetch work
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, prio_lo);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->last_build, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->track_done, cudaEventDisableTiming);
+  for (int i = 0; i < kBuildSlots && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->bslots[i].done, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete c; return sdvlb_set_cuda_error(e, "cudaStreamCreate", __FILE__, __LINE__); }
   e = cudaMalloc(reinterpret_cast<void**>(&c->overflow_flag), 64);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->overflow_flag, 0, 64, c->stream);
@@ -303,7 +342,21 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (sdvlb_frame* f : c->all_frames) { if (f->h_pyr) cudaFreeHost(f->h_pyr); delete f; }
+  cudaStreamSynchronize(c->bstream);
+  for (sdvlb_frame* f : c->all_frames) {
+    if (f->h_pyr) cudaFreeHost(f->h_pyr);
+    if (f->h_corners) cudaFreeHost(f->h_corners);
+    if (f->built) cudaEventDestroy(f->built);
+    delete f;
+  }
+  for (int i = 0; i < kBuildSlots; i++) {
+    if (c->bslots[i].a.h) cudaFreeHost(c->bslots[i].a.h);
+    if (c->bslots[i].a.d) cudaFree(c->bslots[i].a.d);
+    if (c->bslots[i].done) cudaEventDestroy(c->bslots[i].done);
+  }
+  if (c->last_build) cudaEventDestroy(c->last_build);
+  if (c->track_done) cudaEventDestroy(c->track_done);
+  delete c->pending;
   for (uint8_t* slab : c->slabs) cudaFree(slab);
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
   cudaFree(c->frame_ticket); cudaFree(c->overflow_flag); cudaFree(c->scratch);
@@ -313,12 +366,14 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   if (c->out.d) cudaFree(c->out.d);
   for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->bstream);
   delete c;
   return 0;
 }
 
 int sdvlb_ctx_sync(sdvlb_ctx* c) {
   SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->bstream));
   SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -354,6 +409,7 @@ int sdvlb_ctx_counters(sdvlb_ctx* c, int64_t* kernel_launches, int64_t* h2d_byte
 int sdvlb_timing_enable(sdvlb_ctx* c, int on) { c->timing = on != 0; return 0; }
 int sdvlb_timing_read(sdvlb_ctx* c, double ms[SDVLB_K_COUNT], int64_t launches[SDVLB_K_COUNT], int reset) {
   SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->bstream));
   SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
   timer_collect(c);
   for (int i = 0; i < SDVLB_K_COUNT; i++) {
@@ -366,6 +422,7 @@ int sdvlb_timing_read(sdvlb_ctx* c, double ms[SDVLB_K_COUNT], int64_t launches[S
 
 }  // extern "C"
 
+
 // ================================================================================================ batched core
 namespace {
 
@@ -376,10 +433,68 @@ struct BatchOut {   // per-job results in the `out` arena
   int32_t pad[2];
 };
 
-// Submits pyramid (+FAST) (+align) (+search) for n jobs and synchronises once.
-int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_iter* trace, int trace_cap,
-              int* trace_n, const sdvlb_gn_forced* forced, bool build_frames, int fast = 0) {
+}  // namespace
+
+namespace {
+
+inline size_t corner_mirror_bytes(const sdvlb_ctx* c) { return 16 + size_t(c->corner_copy) * sizeof(int4); }
+
+// D2H of the corner header + first corner_copy corners into the frame's own pinned mirror.
+int enqueue_corner_mirror(sdvlb_ctx* c, sdvlb_frame* f, cudaStream_t stream) {
+  if (!f->h_corners) SDVLB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&f->h_corners), corner_mirror_bytes(c), cudaHostAllocDefault));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_corners, f->d_block + f->off_hdr, corner_mirror_bytes(c), cudaMemcpyDeviceToHost, stream));
+  c->d2h_bytes += int64_t(corner_mirror_bytes(c));
+  return 0;
+}
+
+// Host bookkeeping once a frame's build commands are known to have completed.
+void finalize_build(sdvlb_ctx* c, sdvlb_frame* f, bool want_corners, bool mirrored) {
+  f->has_corners = want_corners;
+  f->corners_mirrored = -1;
+  if (want_corners && mirrored && f->h_corners) {
+    memcpy(&f->n_corners, f->h_corners, sizeof(int32_t));
+    f->corners_mirrored = std::min(f->n_corners, c->corner_copy);
+  }
+  f->build_pending = false;
+}
+
+int ensure_built(sdvlb_frame* f) {
+  if (!f->build_pending) return 0;
+  SDVLB_CUDA_TRY(cudaSetDevice(f->ctx->device));
+  SDVLB_CUDA_TRY(cudaEventSynchronize(f->built));
+  finalize_build(f->ctx, f, f->build_corners, f->build_mirror);
+  return 0;
+}
+
+// Enqueues pyramid (+ FAST + selection) for `n` frames whose level 0 is already on its way on `stream`.
+// d_all / d_detect: device arrays of FrameDev (all frames / frames that want corners).
+int enqueue_build_kernels(sdvlb_ctx* c, const FrameDev* d_all, int n, const FrameDev* d_detect, int n_detect, int nfeatures,
+                          cudaStream_t stream) {
+  timer_begin(c, SDVLB_K_PYRAMID, stream);
+  SDVLB_CUDA_TRY(sdvlb_launch_pyramid(d_all, n, c->geom, stream));
+  timer_end(c);
+  c->n_launches += c->geom.levels - 1;
+  if (n_detect > 0) {
+    const FastPlan* plan = get_plan(c, nfeatures);
+    timer_begin(c, SDVLB_K_FAST, stream);
+    SDVLB_CUDA_TRY(sdvlb_launch_fast_cells(d_detect, n_detect, *plan, c->cell_kp, c->cell_cnt, stream));
+    timer_end(c);
+    timer_begin(c, SDVLB_K_SELECT, stream);
+    SDVLB_CUDA_TRY(sdvlb_launch_fast_select(d_detect, n_detect, *plan, c->cell_kp, c->cell_cnt, c->level_kp, c->level_cnt,
+                                            c->frame_ticket, c->overflow_flag, stream));
+    timer_end(c);
+    c->n_launches += 2;
+  }
+  return 0;
+}
+
+// Submits (pyramid + FAST for jobs that carry an image) + align + search for n jobs on the tracking stream; does not
+// wait.  collect_batch() synchronises and copies the results into the jobs.
+int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_iter* trace, int trace_cap,
+                 int* trace_n, const sdvlb_gn_forced* forced, bool build_frames, int fast = 0) {
   SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  if (!c->pending) c->pending = new PendingTrack;
+  if (c->pending->active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
   const PyrGeom& g = c->geom;
   const size_t img_bytes = size_t(c->w) * c->h;
 
@@ -411,10 +526,8 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
   const size_t need_in = 4096 + size_t(n) * (2 * sizeof(FrameDev) + sizeof(AlignJobDev) + 512) +
                          size_t(n_feats) * sizeof(sdvlb_align_feat) + size_t(n_cands) * sizeof(SearchCandDev) +
                          (forced ? size_t(forced->n_total) * 56 + 512 : 0) + 32 * 256;
-  const size_t corner_rec = align_up(size_t(c->corner_copy) * 16 + 256, 256);   // xyl | score | count
   const size_t need_out = 4096 + size_t(n) * sizeof(BatchOut) + size_t(n_cands) * sizeof(sdvlb_match) +
-                          size_t(trace ? trace_cap : 0) * sizeof(sdvlb_gn_iter) + 16 * 256 +
-                          ((build_frames && mirror) ? size_t(n) * corner_rec : 0);
+                          size_t(trace ? trace_cap : 0) * sizeof(sdvlb_gn_iter) + 16 * 256;
   int rc = ensure_arena(&in, need_in, true);
   if (rc) return rc;
   rc = ensure_arena(&out, need_out, true);
@@ -444,8 +557,6 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
   const size_t o_match = out.take(size_t(std::max(n_cands, 1)) * sizeof(sdvlb_match));
   const size_t o_trace = trace ? out.take(size_t(trace_cap) * sizeof(sdvlb_gn_iter)) : 0;
   const size_t o_flag = out.take(64);
-  const size_t dev_out_used = out.used;          // results produced on the device end here
-  const size_t o_corners = (build_frames && mirror) ? out.take(size_t(n) * corner_rec) : 0;   // host-only region
 
   FrameDev* hf = reinterpret_cast<FrameDev*>(in.h + o_frames);
   FrameDev* hd = reinterpret_cast<FrameDev*>(in.h + o_detect);
@@ -510,15 +621,22 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
     }
   }
 
+  // ---- ordering against asynchronous frame batches: frames still being built, and the shared FAST scratch
+  if (build_frames && c->build_in_flight) SDVLB_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_build, 0));
+  for (int i = 0; i < n; i++) {
+    if (!build_frames && jobs[i].cur->build_pending) SDVLB_CUDA_TRY(cudaStreamWaitEvent(c->stream, jobs[i].cur->built, 0));
+    if (jobs[i].ref && jobs[i].ref->build_pending) SDVLB_CUDA_TRY(cudaStreamWaitEvent(c->stream, jobs[i].ref->built, 0));
+  }
+
   // ---- H2D
-  if (build_frames)
-    for (int i = 0; i < n; i++)
+  if (build_frames) {
+    for (int i = 0; i < n; i++) {
       SDVLB_CUDA_TRY(cudaMemcpyAsync(jobs[i].cur->dev.pyr, jobs[i].image, img_bytes,
                                      jobs[i].image_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                      c->stream));
-  if (build_frames)
-    for (int i = 0; i < n; i++)
       if (!jobs[i].image_on_device) c->h2d_bytes += int64_t(img_bytes);
+    }
+  }
   SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, in.used, cudaMemcpyHostToDevice, c->stream));
   c->h2d_bytes += int64_t(in.used);
   // prior poses for frames that are not aligned (search may still read cur.pose)
@@ -529,24 +647,13 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
 
   // ---- kernels
   if (build_frames) {
-    timer_begin(c, SDVLB_K_PYRAMID);
-    SDVLB_CUDA_TRY(sdvlb_launch_pyramid(reinterpret_cast<const FrameDev*>(in.d + o_frames), n, g, c->stream));
-    timer_end(c);
-    c->n_launches += g.levels - 1;
     if (n_detect > 0) {
       rc = ensure_fast_scratch(c, n_detect);
       if (rc) return rc;
-      const FastPlan* plan = get_plan(c, nfeatures);
-      const FrameDev* dfr = reinterpret_cast<const FrameDev*>(in.d + o_detect);
-      timer_begin(c, SDVLB_K_FAST);
-      SDVLB_CUDA_TRY(sdvlb_launch_fast_cells(dfr, n_detect, *plan, c->cell_kp, c->cell_cnt, c->stream));
-      timer_end(c);
-      timer_begin(c, SDVLB_K_SELECT);
-      SDVLB_CUDA_TRY(sdvlb_launch_fast_select(dfr, n_detect, *plan, c->cell_kp, c->cell_cnt, c->level_kp, c->level_cnt,
-                                              c->frame_ticket, c->overflow_flag, c->stream));
-      timer_end(c);
-      c->n_launches += 2;
     }
+    rc = enqueue_build_kernels(c, reinterpret_cast<const FrameDev*>(in.d + o_frames), n,
+                               reinterpret_cast<const FrameDev*>(in.d + o_detect), n_detect, nfeatures, c->stream);
+    if (rc) return rc;
   }
   if (n_align > 0) {
     timer_begin(c, SDVLB_K_ALIGN);
@@ -565,55 +672,59 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
 
   // ---- D2H
   SDVLB_CUDA_TRY(cudaMemcpyAsync(out.d + o_flag, c->overflow_flag, 4, cudaMemcpyDeviceToDevice, c->stream));
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(out.h, out.d, dev_out_used, cudaMemcpyDeviceToHost, c->stream));
-  c->d2h_bytes += int64_t(dev_out_used);
-  if (build_frames && mirror) {
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(out.h, out.d, out.used, cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_bytes += int64_t(out.used);
+  if (build_frames && mirror)
+    for (int i = 0; i < n; i++)
+      if (jobs[i].want_corners) {
+        rc = enqueue_corner_mirror(c, jobs[i].cur, c->stream);
+        if (rc) return rc;
+      }
+  if (build_frames)
     for (int i = 0; i < n; i++) {
-      sdvlb_frame* f = jobs[i].cur;
-      if (!jobs[i].want_corners) continue;
-      uint8_t* rec = out.h + o_corners + size_t(i) * corner_rec;   // straight into pinned host memory
-      SDVLB_CUDA_TRY(cudaMemcpyAsync(rec, f->d_block + f->off_xyl, size_t(c->corner_copy) * 12, cudaMemcpyDeviceToHost, c->stream));
-      SDVLB_CUDA_TRY(cudaMemcpyAsync(rec + size_t(c->corner_copy) * 12, f->d_block + f->off_score,
-                                     size_t(c->corner_copy) * 4, cudaMemcpyDeviceToHost, c->stream));
-      SDVLB_CUDA_TRY(cudaMemcpyAsync(rec + size_t(c->corner_copy) * 16, f->d_block + f->off_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
-      c->d2h_bytes += int64_t(c->corner_copy) * 16 + 4;
+      jobs[i].cur->build_corners = jobs[i].want_corners != 0;
+      jobs[i].cur->build_mirror = mirror != 0;
     }
-  }
-  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  SDVLB_CUDA_TRY(cudaEventRecord(c->track_done, c->stream));
 
-  // ---- results
+  PendingTrack& P = *c->pending;
+  P.active = true;
+  P.jobs = jobs; P.n = n; P.build_frames = build_frames;
+  P.trace = trace; P.trace_cap = trace_cap; P.trace_n = trace_n;
+  P.o_res = o_res; P.o_match = o_match; P.o_trace = o_trace; P.o_flag = o_flag;
+  return 0;
+}
+
+int collect_batch(sdvlb_ctx* c) {
+  if (!c->pending || !c->pending->active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
+  PendingTrack& P = *c->pending;
+  P.active = false;
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  SDVLB_CUDA_TRY(cudaEventSynchronize(c->track_done));
+  Arena& out = c->out;
   int32_t flag;
-  memcpy(&flag, out.h + o_flag, 4);
+  memcpy(&flag, out.h + P.o_flag, 4);
   if (flag) {
     cudaMemsetAsync(c->overflow_flag, 0, 4, c->stream);
     return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in FAST selection");
   }
-  const BatchOut* res = reinterpret_cast<const BatchOut*>(out.h + o_res);
-  const sdvlb_match* hm = reinterpret_cast<const sdvlb_match*>(out.h + o_match);
+  const BatchOut* res = reinterpret_cast<const BatchOut*>(out.h + P.o_res);
+  const sdvlb_match* hm = reinterpret_cast<const sdvlb_match*>(out.h + P.o_match);
   int mo = 0;
   bool first_align = true;
-  for (int i = 0; i < n; i++) {
-    sdvlb_track_job& j = jobs[i];
-    if (build_frames) {
-      j.cur->has_corners = j.want_corners != 0;
-      if (j.want_corners && mirror) {
-        const uint8_t* rec = out.h + o_corners + size_t(i) * corner_rec;
-        memcpy(&j.cur->n_corners, rec + size_t(c->corner_copy) * 16, sizeof(int32_t));
-        const int m = std::min(j.cur->n_corners, c->corner_copy);
-        j.cur->h_xyl.assign(reinterpret_cast<const int32_t*>(rec), reinterpret_cast<const int32_t*>(rec) + size_t(m) * 3);
-        j.cur->h_score.assign(reinterpret_cast<const int32_t*>(rec + size_t(c->corner_copy) * 12),
-                              reinterpret_cast<const int32_t*>(rec + size_t(c->corner_copy) * 12) + m);
-        j.cur->corners_mirrored = m;
-      }
-    }
+  for (int i = 0; i < P.n; i++) {
+    sdvlb_track_job& j = P.jobs[i];
+    // the tracking stream ran after this frame's build (same stream, or ordered by its `built` event)
+    if (P.build_frames) finalize_build(c, j.cur, j.cur->build_corners, j.cur->build_mirror);
+    else if (j.cur->build_pending) finalize_build(c, j.cur, j.cur->build_corners, j.cur->build_mirror);
     if (j.ref) {
       memcpy(j.T_cur, res[i].pose, sizeof(j.T_cur));
       j.n_tracked = res[i].info[0] / (c->params.align_patch_size * c->params.align_patch_size);
       j.gn_iters = res[i].info[1];
       j.error = res[i].error;
       if (first_align) {
-        if (trace_n) *trace_n = res[i].info[1];
-        if (trace) memcpy(trace, out.h + o_trace, size_t(std::min(res[i].info[1], trace_cap)) * sizeof(sdvlb_gn_iter));
+        if (P.trace_n) *P.trace_n = res[i].info[1];
+        if (P.trace) memcpy(P.trace, out.h + P.o_trace, size_t(std::min(res[i].info[1], P.trace_cap)) * sizeof(sdvlb_gn_iter));
         first_align = false;
       }
     }
@@ -623,16 +734,128 @@ int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_i
   return 0;
 }
 
+int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_iter* trace, int trace_cap,
+              int* trace_n, const sdvlb_gn_forced* forced, bool build_frames, int fast = 0) {
+  const int rc = submit_batch(c, jobs, n, mirror, trace, trace_cap, trace_n, forced, build_frames, fast);
+  if (rc) { if (c->pending) c->pending->active = false; return rc; }
+  return collect_batch(c);
+}
+
+int check_track_args(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, bool* build) {
+  if (!ctx || !jobs || n_jobs <= 0) return sdvlb_set_error(SDVLB_ERR_ARG, "bad batch");
+  if (w != ctx->w || h != ctx->h) return sdvlb_set_error(SDVLB_ERR_ARG, "image size differs from the context camera");
+  int with_image = 0;
+  for (int i = 0; i < n_jobs; i++) {
+    if (jobs[i].image) with_image++;
+    else if (!jobs[i].cur) return sdvlb_set_error(SDVLB_ERR_ARG, "job with neither an image nor a prebuilt frame");
+  }
+  if (with_image != 0 && with_image != n_jobs)
+    return sdvlb_set_error(SDVLB_ERR_ARG, "a batch must either build all its frames or use prebuilt frames only");
+  *build = with_image == n_jobs;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
 
 int sdvlb_track_batch(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, int mirror) {
-  if (!ctx || !jobs || n_jobs <= 0) return sdvlb_set_error(SDVLB_ERR_ARG, "bad batch");
-  if (w != ctx->w || h != ctx->h) return sdvlb_set_error(SDVLB_ERR_ARG, "image size differs from the context camera");
-  for (int i = 0; i < n_jobs; i++)
-    if (!jobs[i].image) return sdvlb_set_error(SDVLB_ERR_ARG, "job without image");
-  return run_batch(ctx, jobs, n_jobs, mirror, nullptr, 0, nullptr, nullptr, true);
+  bool build = false;
+  const int rc = check_track_args(ctx, jobs, n_jobs, w, h, &build);
+  if (rc) return rc;
+  return run_batch(ctx, jobs, n_jobs, mirror, nullptr, 0, nullptr, nullptr, build);
+}
+
+int sdvlb_track_submit(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, int mirror) {
+  bool build = false;
+  int rc = check_track_args(ctx, jobs, n_jobs, w, h, &build);
+  if (rc) return rc;
+  rc = submit_batch(ctx, jobs, n_jobs, mirror, nullptr, 0, nullptr, nullptr, build);
+  if (rc && ctx->pending) ctx->pending->active = false;
+  return rc;
+}
+
+int sdvlb_track_poll(sdvlb_ctx* ctx) {
+  if (!ctx || !ctx->pending || !ctx->pending->active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
+  const cudaError_t e = cudaEventQuery(ctx->track_done);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  return sdvlb_set_cuda_error(e, "cudaEventQuery", __FILE__, __LINE__);
+}
+
+int sdvlb_track_collect(sdvlb_ctx* ctx) {
+  if (!ctx) return sdvlb_set_error(SDVLB_ERR_ARG, "null context");
+  return collect_batch(ctx);
+}
+
+int sdvlb_frames_submit(sdvlb_ctx* c, const uint8_t* const* images, int n, int images_on_device, int want_corners,
+                        int nfeatures, sdvlb_frame** out) {
+  if (!c || !images || !out || n <= 0) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  const size_t img_bytes = size_t(c->w) * c->h;
+  BuildSlot& slot = c->bslots[c->bslot_next];
+  c->bslot_next = (c->bslot_next + 1) % kBuildSlots;
+  if (slot.used) SDVLB_CUDA_TRY(cudaEventSynchronize(slot.done));   // its staging may still be read by the device
+  int rc = ensure_arena(&slot.a, size_t(n) * sizeof(FrameDev) + 512, true);
+  if (rc) return rc;
+  if (want_corners) {
+    if (n > c->fast_frames) {   // growing the FAST scratch frees device memory: drain both streams first
+      SDVLB_CUDA_TRY(cudaStreamSynchronize(c->bstream));
+      SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    rc = ensure_fast_scratch(c, n);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < n; i++) {
+    sdvlb_frame* f = nullptr;
+    rc = frame_alloc(c, &f);
+    if (rc) { for (int k = 0; k < i; k++) frame_release(c, out[k]); return rc; }
+    out[i] = f;
+    reinterpret_cast<FrameDev*>(slot.a.h)[i] = f->dev;
+  }
+  for (int i = 0; i < n; i++) {
+    if (!images[i]) return sdvlb_set_error(SDVLB_ERR_ARG, "null image");
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(out[i]->dev.pyr, images[i], img_bytes,
+                                   images_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->bstream));
+    if (!images_on_device) c->h2d_bytes += int64_t(img_bytes);
+  }
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(slot.a.d, slot.a.h, size_t(n) * sizeof(FrameDev), cudaMemcpyHostToDevice, c->bstream));
+  c->h2d_bytes += int64_t(n) * sizeof(FrameDev);
+  const FrameDev* d = reinterpret_cast<const FrameDev*>(slot.a.d);
+  rc = enqueue_build_kernels(c, d, n, d, want_corners ? n : 0, nfeatures, c->bstream);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++) {
+    sdvlb_frame* f = out[i];
+    if (want_corners) {
+      rc = enqueue_corner_mirror(c, f, c->bstream);
+      if (rc) return rc;
+    }
+    f->build_pending = true;
+    f->build_corners = want_corners != 0;
+    f->build_mirror = want_corners != 0;
+    SDVLB_CUDA_TRY(cudaEventRecord(f->built, c->bstream));
+  }
+  SDVLB_CUDA_TRY(cudaEventRecord(slot.done, c->bstream));
+  SDVLB_CUDA_TRY(cudaEventRecord(c->last_build, c->bstream));
+  slot.used = true;
+  c->build_in_flight = true;
+  return 0;
+}
+
+int sdvlb_frames_wait(sdvlb_ctx* c, sdvlb_frame* const* frames, int n) {
+  if (!c || (n > 0 && !frames)) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  for (int i = 0; i < n; i++) {
+    const int rc = ensure_built(frames[i]);
+    if (rc) return rc;
+  }
+  int32_t flag = 0;
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(&flag, c->overflow_flag, 4, cudaMemcpyDeviceToHost, c->bstream));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->bstream));
+  if (flag) {
+    cudaMemsetAsync(c->overflow_flag, 0, 4, c->bstream);
+    return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in FAST selection");
+  }
+  return 0;
 }
 
 int sdvlb_frame_create(sdvlb_ctx* ctx, const uint8_t* img, int w, int h, int stride, int want_corners, int nfeatures,
@@ -660,7 +883,10 @@ int sdvlb_frame_create(sdvlb_ctx* ctx, const uint8_t* img, int w, int h, int str
 int sdvlb_frame_detect(sdvlb_ctx* ctx, sdvlb_frame* f, int nfeatures) {
   if (!ctx || !f) return sdvlb_set_error(SDVLB_ERR_ARG, "null argument");
   SDVLB_CUDA_TRY(cudaSetDevice(ctx->device));
-  int rc = ensure_fast_scratch(ctx, 1);
+  int rc = ensure_built(f);
+  if (rc) return rc;
+  if (ctx->build_in_flight) SDVLB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->last_build, 0));
+  rc = ensure_fast_scratch(ctx, 1);
   if (rc) return rc;
   rc = ensure_arena(&ctx->in, 4096, true);
   if (rc) return rc;
@@ -676,18 +902,17 @@ int sdvlb_frame_detect(sdvlb_ctx* ctx, sdvlb_frame* f, int nfeatures) {
                                           ctx->frame_ticket, ctx->overflow_flag, ctx->stream));
   timer_end(ctx);
   ctx->n_launches += 2;
-  int32_t flag = 0, cnt = 0;
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(&cnt, f->d_block + f->off_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  int32_t flag = 0;
+  rc = enqueue_corner_mirror(ctx, f, ctx->stream);
+  if (rc) return rc;
   SDVLB_CUDA_TRY(cudaMemcpyAsync(&flag, ctx->overflow_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
   SDVLB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if (flag) {
     cudaMemsetAsync(ctx->overflow_flag, 0, 4, ctx->stream);
     return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in FAST selection");
   }
-  f->n_corners = cnt;
-  f->has_corners = true;
-  f->corners_mirrored = 0;
-  f->h_xyl.clear(); f->h_score.clear();
+  finalize_build(ctx, f, true, true);
+  f->h_more.clear();
   return 0;
 }
 
@@ -697,6 +922,8 @@ int sdvlb_frame_level(const sdvlb_frame* f, int level, const uint8_t** data, int
   if (!mf->pyr_mirrored) {   // the host mirror is materialised on first use
     sdvlb_ctx* c = f->ctx;
     SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+    const int rc = ensure_built(mf);
+    if (rc) return rc;
     if (!mf->h_pyr) SDVLB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&mf->h_pyr), size_t(c->geom.total), cudaHostAllocDefault));
     SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_pyr, mf->d_block, size_t(c->geom.total), cudaMemcpyDeviceToHost, c->stream));
     SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -709,33 +936,33 @@ int sdvlb_frame_level(const sdvlb_frame* f, int level, const uint8_t** data, int
   return 0;
 }
 
-int sdvlb_frame_corners(const sdvlb_frame* f, const int32_t** xyl, const int32_t** score, int* n) {
+int sdvlb_frame_corners(const sdvlb_frame* f, const int32_t** xyls, int* n) {
   if (!f) return sdvlb_set_error(SDVLB_ERR_ARG, "null frame");
-  if (!f->has_corners) return sdvlb_set_error(SDVLB_ERR_STATE, "corners were not detected on this frame");
   sdvlb_frame* mf = const_cast<sdvlb_frame*>(f);
   sdvlb_ctx* c = f->ctx;
-  if (mf->corners_mirrored < 0) {
+  int rc = ensure_built(mf);
+  if (rc) return rc;
+  if (!f->has_corners) return sdvlb_set_error(SDVLB_ERR_STATE, "corners were not detected on this frame");
+  if (mf->corners_mirrored < 0) {   // built without a mirror: fetch header + first block now
     SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-    int32_t cnt = 0;
-    SDVLB_CUDA_TRY(cudaMemcpyAsync(&cnt, mf->d_block + mf->off_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    rc = enqueue_corner_mirror(c, mf, c->stream);
+    if (rc) return rc;
     SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    mf->n_corners = cnt;
-    mf->corners_mirrored = 0;
+    finalize_build(c, mf, true, true);
   }
-  if (mf->corners_mirrored < mf->n_corners) {
-    SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-    mf->h_xyl.resize(size_t(mf->n_corners) * 3);
-    mf->h_score.resize(size_t(mf->n_corners));
-    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_xyl.data(), mf->d_block + mf->off_xyl, size_t(mf->n_corners) * 12,
-                                   cudaMemcpyDeviceToHost, c->stream));
-    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_score.data(), mf->d_block + mf->off_score, size_t(mf->n_corners) * 4,
-                                   cudaMemcpyDeviceToHost, c->stream));
-    SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    c->d2h_bytes += int64_t(mf->n_corners) * 16;
-    mf->corners_mirrored = mf->n_corners;
+  const int32_t* src = reinterpret_cast<const int32_t*>(mf->h_corners + 16);
+  if (mf->corners_mirrored < mf->n_corners) {   // longer than the eager mirror: fetch the whole list once
+    if (mf->h_more.size() != size_t(mf->n_corners) * 4) {
+      SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+      mf->h_more.resize(size_t(mf->n_corners) * 4);
+      SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_more.data(), mf->d_block + mf->off_hdr + 16, size_t(mf->n_corners) * 16,
+                                     cudaMemcpyDeviceToHost, c->stream));
+      SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+      c->d2h_bytes += int64_t(mf->n_corners) * 16;
+    }
+    src = mf->h_more.data();
   }
-  if (xyl) *xyl = mf->h_xyl.data();
-  if (score) *score = mf->h_score.data();
+  if (xyls) *xyls = src;
   if (n) *n = f->n_corners;
   return 0;
 }
@@ -743,6 +970,11 @@ int sdvlb_frame_corners(const sdvlb_frame* f, const int32_t** xyl, const int32_t
 int sdvlb_frame_destroy(sdvlb_ctx* ctx, sdvlb_frame* f) {
   if (!f) return 0;
   if (!ctx) ctx = f->ctx;
+  if (f->build_pending) {   // the slot must not be recycled while its build is in flight
+    cudaSetDevice(ctx->device);
+    cudaEventSynchronize(f->built);
+    f->build_pending = false;
+  }
   frame_release(ctx, f);
   return 0;
 }
@@ -777,6 +1009,8 @@ int sdvlb_image_align(sdvlb_ctx* ctx, const sdvlb_frame* ref, sdvlb_frame* cur, 
 int sdvlb_search_points(sdvlb_ctx* ctx, const sdvlb_frame* cur, const sdvlb_candidate* cands, int n,
                         const double T_cur[7], sdvlb_match* out) {
   if (!ctx || !cur || n < 0 || (n > 0 && (!cands || !out))) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  const int rcb = ensure_built(const_cast<sdvlb_frame*>(cur));
+  if (rcb) return rcb;
   if (!cur->has_corners) return sdvlb_set_error(SDVLB_ERR_STATE, "current frame has no corners");
   if (n == 0) return 0;
   sdvlb_track_job j;

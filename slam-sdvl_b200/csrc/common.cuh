@@ -25,9 +25,8 @@ struct PyrGeom {
 // Device view of one frame.
 struct FrameDev {
   uint8_t* pyr;        // levels at PyrGeom::off
-  int32_t* xyl;        // corners: (x, y, level) triplets in level coordinates, reference order
-  int32_t* score;      // FAST score per corner
-  int32_t* n_corners;  // device counter
+  int4* corners;       // corners in the reference's order: (x, y, level, FAST score), level coordinates
+  int32_t* n_corners;  // device counter; lives in the 16-byte header right before `corners` (one D2H mirrors both)
   double* pose;        // 7 doubles, world->camera, written by the ImageAlign kernel / uploaded by the host
 };
 

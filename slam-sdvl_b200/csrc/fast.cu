@@ -334,10 +334,7 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const FrameDev
     }
     for (int i = tid; i < n; i += SEL_THREADS) {
       const uint32_t key = __ldcg(src + i);
-      fr.xyl[3 * (base + i) + 0] = int32_t(key & 2047);
-      fr.xyl[3 * (base + i) + 1] = int32_t((key >> 11) & 2047);
-      fr.xyl[3 * (base + i) + 2] = l;
-      fr.score[base + i] = int32_t(key >> 22);
+      fr.corners[base + i] = make_int4(int32_t(key & 2047), int32_t((key >> 11) & 2047), l, int32_t(key >> 22));
     }
     base += n;
   }

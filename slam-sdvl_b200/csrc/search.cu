@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
       bool in = false;
       int cx = 0, cy = 0, cl = 0;
       if (idx < nc) {
-        cx = cur.xyl[3 * idx]; cy = cur.xyl[3 * idx + 1]; cl = cur.xyl[3 * idx + 2];
+        const int4 cc = __ldg(cur.corners + idx);
+        cx = cc.x; cy = cc.y; cl = cc.z;
         in = abs(cl - level) <= 1 && !(cx - margin < 0 || cy - margin < 0) &&
              !(cy + margin >= A.g.h[cl] || cx + margin >= A.g.w[cl]);
         if (in) {
@@ -246,8 +247,9 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
   // ---- AlignPatch (matcher.cc:359-445) at the search level
   if (alive) {
     const int bidx = int(best_key & 0xffffffffu);
-    const int bl = cur.xyl[3 * bidx + 2];
-    const double bx = double(cur.xyl[3 * bidx] * (1 << bl)), by = double(cur.xyl[3 * bidx + 1] * (1 << bl));
+    const int4 bc = __ldg(cur.corners + bidx);
+    const int bl = bc.z;
+    const double bx = double(bc.x * (1 << bl)), by = double(bc.y * (1 << bl));
     const int W = A.g.w[slevel], Hh = A.g.h[slevel];
     const uint8_t* __restrict__ img = cur.pyr + A.g.off[slevel];
     // template gradients; each lane owns pixels lane and lane+32

@@ -63,17 +63,16 @@ std::vector<cv::Mat>& Frame::GetPyramid() {
 
 std::vector<Eigen::Vector3i>& Frame::GetCorners() {
   if (!corners_fetched_) {
-    const int32_t* xyl = nullptr;
-    const int32_t* score = nullptr;
+    const int32_t* xyls = nullptr;
     int n = 0;
-    const int rc = sdvlb_frame_corners(handle_, &xyl, &score, &n);
+    const int rc = sdvlb_frame_corners(handle_, &xyls, &n);
     corners_.clear();
     corner_scores_.clear();
     if (rc == 0) {
       corners_.reserve(n);
       for (int i = 0; i < n; i++) {
-        corners_.push_back(Eigen::Vector3i(xyl[3 * i], xyl[3 * i + 1], xyl[3 * i + 2]));
-        corner_scores_.push_back(score[i]);
+        corners_.push_back(Eigen::Vector3i(xyls[4 * i], xyls[4 * i + 1], xyls[4 * i + 2]));
+        corner_scores_.push_back(xyls[4 * i + 3]);
       }
     } else if (rc != SDVLB_ERR_STATE) {   // a frame built with corners=false simply has none (frame.cc:52-53)
       Check(rc, "GetCorners");

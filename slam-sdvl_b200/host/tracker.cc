@@ -201,49 +201,14 @@ class Group {
     std::memset(stats, 0, size_t(n) * 8 * sizeof(int32_t));
     const auto tA = std::chrono::steady_clock::now();
     // ---- phase A: marshal
-    for (int i = 0; i < n; i++) {
-      Sequence& s = seqs_[i];
-      sdvlb_track_job& j = jobs_[i];
-      std::memset(&j, 0, sizeof(j));
-      j.image = images[i];
-      j.image_on_device = on_device;
-      j.want_corners = 1;
-      j.nfeatures = Config::NumFeatures();
-      if (s.last_frame) {
-        (SE3::Exp(s.vel) * s.last_frame->GetPose()).ToArray(j.T_cur);   // sdvl.cc:278-281
-        s.last_frame->GetPose().ToArray(j.T_ref);
-        ImageAlign::CollectFeatures(s.last_frame, &s.feats);
-        s.fa->CollectCandidates(s.frame_counter, s.last_frame, false, &s.cands, &s.cand_points);
-        s.matches.resize(s.cands.size());
-        j.ref = s.last_frame->Handle();
-        j.feats = s.feats.data();
-        j.n_feats = int(s.feats.size());
-        j.cands = s.cands.data();
-        j.n_cands = int(s.cands.size());
-        j.matches = s.matches.data();
-      }
-    }
+    for (int i = 0; i < n; i++) MarshalJob(i, images[i], on_device);
     // ---- phase B: one submission
     const auto tB = std::chrono::steady_clock::now();
     const int rc = sdvlb_track_batch(ctx_, jobs_.data(), n, w, h, 1);
     if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_track_batch failed: ") + sdvlb_last_error());
     const auto tC = std::chrono::steady_clock::now();
     // ---- phase C: host replay
-    for (int i = 0; i < n; i++) {
-      Sequence& s = seqs_[i];
-      sdvlb_track_job& j = jobs_[i];
-      shared_ptr<Frame> frame = std::make_shared<Frame>(&cam_, ctx_, j.cur, s.frame_counter);
-      const bool first = !s.last_frame;
-      int32_t* st = stats + 8 * i;
-      if (!first) {
-        frame->SetPose(SE3(j.T_cur));
-        st[0] = j.n_tracked;
-        st[6] = j.gn_iters;
-        s.fa->ApplyMatches(frame, s.cand_points, s.matches.data());
-      }
-      driver_.FinishFrame(&s, frame, SE3(gt + 7 * i), first, st);
-      frame->GetPose().ToArray(est + 7 * i);
-    }
+    for (int i = 0; i < n; i++) ReplayJob(i, SE3(gt + 7 * i), est + 7 * i, stats + 8 * i);
     const auto tD = std::chrono::steady_clock::now();
     phase_s_[0] += std::chrono::duration<double>(tB - tA).count();
     phase_s_[1] += std::chrono::duration<double>(tC - tB).count();
@@ -252,21 +217,139 @@ class Group {
   const double* phase_seconds() const { return phase_s_; }
   void reset_phases() { phase_s_[0] = phase_s_[1] = phase_s_[2] = 0; }
 
+  // ---- pipelined run: frame batches are built one step ahead of the tracking they feed (sdvlb_frames_submit on the
+  // context's build stream), tracking is submitted asynchronously and collected when the device is done, so a host
+  // thread can interleave several groups.  Tables are [sequence][step] with row stride `table_stride`.
+  void BeginRun(const uint8_t* const* images, int on_device, int n_steps, int table_stride, const double* gt,
+                double* est, int32_t* stats) {
+    images_ = images; on_device_ = on_device; n_steps_ = n_steps; stride_ = table_stride; gt_ = gt; est_ = est;
+    stats_ = stats;
+    step_ = 0; in_flight_ = false;
+    built_.assign(size(), nullptr);
+    next_built_.assign(size(), nullptr);
+    if (n_steps_ > 0) SubmitBuild(0, &built_);
+  }
+  bool RunDone() const { return step_ >= n_steps_; }
+  bool InFlight() const { return in_flight_; }
+
+  void SubmitStep() {   // build(step+1) then track(step)
+    Device::SetCurrent(ctx_);
+    const auto tA = std::chrono::steady_clock::now();
+    if (step_ + 1 < n_steps_) SubmitBuild(step_ + 1, &next_built_);
+    const int n = size();
+    const int w = int(cam_.GetWidth()), h = int(cam_.GetHeight());
+    for (int i = 0; i < n; i++) {
+      MarshalJob(i, nullptr);
+      jobs_[i].cur = built_[i];
+    }
+    const auto tB = std::chrono::steady_clock::now();
+    const int rc = sdvlb_track_submit(ctx_, jobs_.data(), n, w, h, 1);
+    if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_track_submit failed: ") + sdvlb_last_error());
+    in_flight_ = true;
+    const auto tC = std::chrono::steady_clock::now();
+    phase_s_[0] += std::chrono::duration<double>(tB - tA).count();
+    phase_s_[1] += std::chrono::duration<double>(tC - tB).count();
+  }
+  bool Poll() {
+    const int rc = sdvlb_track_poll(ctx_);
+    if (rc < 0) throw std::runtime_error(std::string("sdvl-b200: sdvlb_track_poll failed: ") + sdvlb_last_error());
+    return rc == 1;
+  }
+  void FinishStep() {   // waits if the device is not done yet
+    Device::SetCurrent(ctx_);
+    const auto tA = std::chrono::steady_clock::now();
+    const int rc = sdvlb_track_collect(ctx_);
+    if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_track_collect failed: ") + sdvlb_last_error());
+    in_flight_ = false;
+    const auto tB = std::chrono::steady_clock::now();
+    const int n = size();
+    for (int i = 0; i < n; i++) {
+      const size_t o = size_t(i) * stride_ + step_;
+      int32_t* st = stats_ + 8 * o;
+      std::memset(st, 0, 8 * sizeof(int32_t));
+      ReplayJob(i, SE3(gt_ + 7 * o), est_ + 7 * o, st);
+    }
+    built_.swap(next_built_);
+    step_++;
+    const auto tC = std::chrono::steady_clock::now();
+    phase_s_[1] += std::chrono::duration<double>(tB - tA).count();
+    phase_s_[2] += std::chrono::duration<double>(tC - tB).count();
+  }
+
  private:
+  // Fills job i from sequence i's state: motion-model prior, ImageAlign features, FeatureAlign candidates.
+  void MarshalJob(int i, const uint8_t* image, int on_device = 0) {
+    Sequence& s = seqs_[i];
+    sdvlb_track_job& j = jobs_[i];
+    std::memset(&j, 0, sizeof(j));
+    j.image = image;
+    j.image_on_device = on_device;
+    j.want_corners = 1;
+    j.nfeatures = Config::NumFeatures();
+    if (s.last_frame) {
+      (SE3::Exp(s.vel) * s.last_frame->GetPose()).ToArray(j.T_cur);   // sdvl.cc:278-281
+      s.last_frame->GetPose().ToArray(j.T_ref);
+      ImageAlign::CollectFeatures(s.last_frame, &s.feats);
+      s.fa->CollectCandidates(s.frame_counter, s.last_frame, false, &s.cands, &s.cand_points);
+      s.matches.resize(s.cands.size());
+      j.ref = s.last_frame->Handle();
+      j.feats = s.feats.data();
+      j.n_feats = int(s.feats.size());
+      j.cands = s.cands.data();
+      j.n_cands = int(s.cands.size());
+      j.matches = s.matches.data();
+    }
+  }
+  // Host half of ProcessFrame for job i once the device results are in.
+  void ReplayJob(int i, const SE3& gt_pose, double* est, int32_t* st) {
+    Sequence& s = seqs_[i];
+    sdvlb_track_job& j = jobs_[i];
+    shared_ptr<Frame> frame = std::make_shared<Frame>(&cam_, ctx_, j.cur, s.frame_counter);
+    const bool first = !s.last_frame;
+    if (!first) {
+      frame->SetPose(SE3(j.T_cur));
+      st[0] = j.n_tracked;
+      st[6] = j.gn_iters;
+      s.fa->ApplyMatches(frame, s.cand_points, s.matches.data());
+    }
+    driver_.FinishFrame(&s, frame, gt_pose, first, st);
+    frame->GetPose().ToArray(est);
+  }
+  void SubmitBuild(int step, vector<sdvlb_frame*>* out) {
+    const int n = size();
+    img_ptrs_.resize(n);
+    for (int i = 0; i < n; i++) img_ptrs_[i] = images_[size_t(i) * stride_ + step];
+    const int rc = sdvlb_frames_submit(ctx_, img_ptrs_.data(), n, on_device_, 1, Config::NumFeatures(), out->data());
+    if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_frames_submit failed: ") + sdvlb_last_error());
+  }
+
   Camera cam_;
   SequenceDriver driver_;
   sdvlb_ctx* ctx_ = nullptr;
   vector<Sequence> seqs_;
   vector<sdvlb_track_job> jobs_;
   double phase_s_[3] = {0, 0, 0};   // host marshal, GPU submission (incl. wait), host replay
+  // pipelined run state
+  const uint8_t* const* images_ = nullptr;
+  int on_device_ = 0, n_steps_ = 0, stride_ = 0, step_ = 0;
+  const double* gt_ = nullptr;
+  double* est_ = nullptr;
+  int32_t* stats_ = nullptr;
+  bool in_flight_ = false;
+  vector<sdvlb_frame*> built_, next_built_;
+  vector<const uint8_t*> img_ptrs_;
 };
 
 // ------------------------------------------------------------------------------------------------ all groups
+// `n_groups` contexts (each with its own streams, staging and sequences) driven by `n_threads` host threads; thread t
+// owns groups t, t + n_threads, ...
 class BatchTracker {
  public:
-  BatchTracker(const SeedPlane& plane, int max_points, int kf_every, int n_seq, int n_groups, int device, bool timing)
+  BatchTracker(const SeedPlane& plane, int max_points, int kf_every, int n_seq, int n_groups, int n_threads, int device,
+               bool timing)
       : n_seq_(n_seq) {
     n_groups = std::max(1, std::min(n_groups, n_seq));
+    n_threads_ = n_threads <= 0 ? n_groups : std::max(1, std::min(n_threads, n_groups));
     int left = n_seq;
     for (int g = 0; g < n_groups; g++) {
       const int take = (left + (n_groups - g) - 1) / (n_groups - g);
@@ -275,7 +358,7 @@ class BatchTracker {
       left -= take;
     }
     if (n_groups > 1) {
-      for (int g = 0; g < n_groups; g++) workers_.emplace_back([this, g] { WorkerLoop(g); });
+      for (int t = 0; t < n_threads_; t++) workers_.emplace_back([this, t] { WorkerLoop(t); });
     }
   }
   ~BatchTracker() {
@@ -289,22 +372,19 @@ class BatchTracker {
     groups_.clear();
   }
 
+  // One frame for every sequence, all groups in lock-step.
   void Step(const uint8_t* const* images, int on_device, int classic, const double* gt, double* est, int32_t* stats) {
-    images_ = images; on_device_ = on_device; classic_ = classic; gt_ = gt; est_ = est; stats_ = stats;
-    error_.clear();
-    if (workers_.empty()) {
-      RunGroup(0);
-    } else {
-      {
-        std::unique_lock<std::mutex> lk(mu_);
-        pending_ = int(groups_.size());
-        generation_++;
-      }
-      cv_.notify_all();
-      std::unique_lock<std::mutex> lk(mu_);
-      done_cv_.wait(lk, [this] { return pending_ == 0; });
-    }
-    if (!error_.empty()) throw std::runtime_error(error_);
+    mode_ = classic ? 1 : 0;
+    images_ = images; on_device_ = on_device; gt_ = gt; est_ = est; stats_ = stats;
+    Dispatch();
+  }
+
+  // n_steps frames for every sequence; groups run free (no barrier between steps), frame batches one step ahead.
+  // images: n_seq x n_steps pointers ([sequence][step]); gt/est: n_seq x n_steps x 7; stats: n_seq x n_steps x 8.
+  void Run(const uint8_t* const* images, int on_device, int n_steps, const double* gt, double* est, int32_t* stats) {
+    mode_ = 2;
+    images_ = images; on_device_ = on_device; n_steps_ = n_steps; gt_ = gt; est_ = est; stats_ = stats;
+    Dispatch();
   }
 
   void TimingRead(double ms[SDVLB_K_COUNT], int64_t launches[SDVLB_K_COUNT], int reset) {
@@ -334,19 +414,67 @@ class BatchTracker {
   sdvlb_ctx* ctx0() { return groups_[0]->ctx(); }
   int n_seq() const { return n_seq_; }
   int n_groups() const { return int(groups_.size()); }
+  int n_threads() const { return workers_.empty() ? 1 : n_threads_; }
 
  private:
-  void RunGroup(int g) {
+  void Dispatch() {
+    error_.clear();
+    if (workers_.empty()) {
+      RunThread(0, 1);
+    } else {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        pending_ = int(workers_.size());
+        generation_++;
+      }
+      cv_.notify_all();
+      std::unique_lock<std::mutex> lk(mu_);
+      done_cv_.wait(lk, [this] { return pending_ == 0; });
+    }
+    if (!error_.empty()) throw std::runtime_error(error_);
+  }
+
+  void RunThread(int t, int stride) {
     try {
-      const int o = offsets_[g];
-      if (classic_) groups_[g]->StepClassic(images_ + o, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
-      else groups_[g]->StepBatched(images_ + o, on_device_, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
+      vector<int> mine;
+      for (int g = t; g < int(groups_.size()); g += stride) mine.push_back(g);
+      if (mode_ != 2) {
+        for (int g : mine) {
+          const int o = offsets_[g];
+          if (mode_ == 1) groups_[g]->StepClassic(images_ + o, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
+          else groups_[g]->StepBatched(images_ + o, on_device_, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
+        }
+        return;
+      }
+      // free-running pipelined groups, interleaved on this thread
+      for (int g : mine) {
+        const size_t o = size_t(offsets_[g]) * n_steps_;
+        groups_[g]->BeginRun(images_ + o, on_device_, n_steps_, n_steps_, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
+      }
+      int active = 0;
+      for (int g : mine) if (!groups_[g]->RunDone()) active++;
+      while (active > 0) {
+        bool progressed = false;
+        for (int g : mine) {
+          Group& G = *groups_[g];
+          if (G.RunDone()) continue;
+          if (!G.InFlight()) {
+            G.SubmitStep();
+            progressed = true;
+          } else if (active == 1 || G.Poll()) {   // the only unfinished group: block in collect
+            G.FinishStep();
+            if (G.RunDone()) active--;
+            progressed = true;
+          }
+        }
+        if (!progressed) std::this_thread::yield();
+      }
     } catch (const std::exception& e) {
       std::unique_lock<std::mutex> lk(mu_);
       error_ = e.what();
     }
   }
-  void WorkerLoop(int g) {
+  void WorkerLoop(int t) {
     long seen = 0;
     while (true) {
       {
@@ -355,7 +483,7 @@ class BatchTracker {
         seen = generation_;
         if (quit_) return;
       }
-      RunGroup(g);
+      RunThread(t, n_threads_);
       {
         std::unique_lock<std::mutex> lk(mu_);
         if (--pending_ == 0) done_cv_.notify_all();
@@ -363,7 +491,7 @@ class BatchTracker {
     }
   }
 
-  int n_seq_;
+  int n_seq_, n_threads_ = 1;
   vector<std::unique_ptr<Group>> groups_;
   vector<int> offsets_;
   vector<std::thread> workers_;
@@ -372,8 +500,9 @@ class BatchTracker {
   long generation_ = 0;
   int pending_ = 0;
   bool quit_ = false;
+  int mode_ = 0;   // 0 batched lock-step, 1 classic lock-step, 2 pipelined run
   const uint8_t* const* images_ = nullptr;
-  int on_device_ = 0, classic_ = 0;
+  int on_device_ = 0, n_steps_ = 0;
   const double* gt_ = nullptr;
   double* est_ = nullptr;
   int32_t* stats_ = nullptr;
@@ -392,12 +521,12 @@ const char* sdvlh_last_error(void) { return g_host_error.c_str(); }
 // Config is process-wide in the reference (singleton, config.h:56); set it before creating trackers.
 void sdvlh_config_set(const sdvlb_params* p, const sdvlb_camera* cam) { sdvl::Config::Set(*p, *cam); }
 
-void* sdvlh_tracker_create(const double plane[4], int max_points, int kf_every, int n_seq, int n_groups, int device,
-                           int timing) {
+void* sdvlh_tracker_create(const double plane[4], int max_points, int kf_every, int n_seq, int n_groups, int n_threads,
+                           int device, int timing) {
   try {
     sdvl::SeedPlane pl;
     pl.n[0] = plane[0]; pl.n[1] = plane[1]; pl.n[2] = plane[2]; pl.d = plane[3];
-    return new sdvl::BatchTracker(pl, max_points, kf_every, n_seq, n_groups, device, timing != 0);
+    return new sdvl::BatchTracker(pl, max_points, kf_every, n_seq, n_groups, n_threads, device, timing != 0);
   } catch (const std::exception& e) {
     g_host_error = e.what();
     return nullptr;
@@ -412,6 +541,18 @@ int sdvlh_tracker_step(void* t, const uint8_t* const* images, int on_device, int
                        double* est_poses, int32_t* stats) {
   try {
     static_cast<sdvl::BatchTracker*>(t)->Step(images, on_device, classic, gt_poses, est_poses, stats);
+    return 0;
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return -1;
+  }
+}
+
+// Pipelined run of n_steps frames per sequence (tables are [sequence][step]); see BatchTracker::Run.
+int sdvlh_tracker_run(void* t, const uint8_t* const* images, int on_device, int n_steps, const double* gt_poses,
+                      double* est_poses, int32_t* stats) {
+  try {
+    static_cast<sdvl::BatchTracker*>(t)->Run(images, on_device, n_steps, gt_poses, est_poses, stats);
     return 0;
   } catch (const std::exception& e) {
     g_host_error = e.what();
@@ -437,5 +578,6 @@ int sdvlh_tracker_phases(void* t, double out[3], int reset) {
 
 void* sdvlh_tracker_ctx(void* t) { return static_cast<sdvl::BatchTracker*>(t)->ctx0(); }
 int sdvlh_tracker_groups(void* t) { return static_cast<sdvl::BatchTracker*>(t)->n_groups(); }
+int sdvlh_tracker_threads(void* t) { return static_cast<sdvl::BatchTracker*>(t)->n_threads(); }
 
 }  // extern "C"

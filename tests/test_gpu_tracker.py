@@ -56,3 +56,52 @@ def test_trajectory_vs_oracle(binding, sw, O, name, n_frames):
         assert ate_vs_oracle <= ATE_MM
         assert ate_gt_gpu <= 5.0
         assert st_b[i][1:, 1].mean() > 0.4 * cfg["n_feat"]
+
+
+@pytest.mark.parametrize("n_groups,n_threads", [(1, 1), (3, 2), (5, 0)])
+def test_pipelined_run_equals_lockstep(binding, sw, n_groups, n_threads):
+    """sdvlh_tracker_run (frame batches built one step ahead, asynchronous tracking, groups interleaved on fewer host
+    threads) is the same computation as stepping all sequences in lock-step."""
+    cfg = sw.config("C2")
+    n_seq, n = 5, 12
+    seqs = []
+    for seed in range(n_seq):
+        poses = sw.trajectory(cfg, 10 + seed, n)
+        seqs.append((poses, sw.render(cfg, poses)))
+    est_s, st_s = _run_host(binding, sw, cfg, seqs, classic=False, n_groups=2)
+    imgs = np.stack([s[1] for s in seqs])
+    gt = np.stack([s[0] for s in seqs])
+    t = binding.HostTracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], 20, n_seq, n_groups, n_threads=n_threads)
+    # two consecutive runs on the same tracker continue the sequences
+    e1, s1 = t.run(imgs[:, :5], gt[:, :5])
+    e2, s2 = t.run(imgs[:, 5:], gt[:, 5:])
+    t.close()
+    est_r = np.concatenate([e1, e2], axis=1)
+    st_r = np.concatenate([s1, s2], axis=1)
+    assert np.array_equal(est_r, est_s)
+    assert np.array_equal(st_r, st_s)
+
+
+def test_async_frame_batches_match_sync_frames(binding, sw, O):
+    """sdvlb_frames_submit (build stream) produces the same pyramid bytes and corner list as sdvlb_frame_create."""
+    import ctypes as C
+    cfg, poses, imgs = sw.sequence("C2", 4, 3)
+    ctx = binding.Context(cfg["params"], cfg["cam"])
+    L = binding.load()
+    n = len(imgs)
+    ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+    out = (C.c_void_p * n)()
+    rc = L.sdvlb_frames_submit(C.c_void_p(ctx.h), ptrs, n, 0, 1, cfg["params"].num_features, out)
+    assert rc == 0, L.sdvlb_last_error()
+    assert L.sdvlb_frames_wait(C.c_void_p(ctx.h), out, n) == 0
+    for i in range(n):
+        fa = binding.Frame(ctx, out[i])
+        fs = ctx.frame(imgs[i], corners=True)
+        xa, sa = fa.corners()
+        xs, ss = fs.corners()
+        assert len(xa) > 500 and np.array_equal(xa, xs) and np.array_equal(sa, ss)
+        for l in range(cfg["params"].pyramid_levels):
+            assert np.array_equal(fa.level(l), fs.level(l))
+        fa.destroy()
+        fs.destroy()
+    ctx.close()

@@ -128,7 +128,8 @@ rank, world = dist.get_rank(), dist.get_world_size()
 seeds = sh.shard_seeds(rank, world, 3)
 sec = sh.max_over_ranks(1.0 + rank, device="cpu")
 tot = sh.sum_over_ranks(len(seeds), device="cpu")
-print(json.dumps(dict(rank=rank, seeds=seeds, sec=sec, tot=tot)), flush=True)
+with open(os.path.join({out!r}, "rank%d.json" % rank), "w") as f:   # one file per rank: stdout lines can interleave
+    json.dump(dict(rank=rank, seeds=seeds, sec=sec, tot=tot), f)
 dist.barrier()
 dist.destroy_process_group()
 """
@@ -137,15 +138,14 @@ dist.destroy_process_group()
 def test_sequence_sharding_two_ranks_gloo(tmp_path):
     """world_size-2 gloo run of the sharding helpers the multi-GPU bench uses: disjoint sequences, max-over-ranks time."""
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT))
+    script.write_text(WORKER.format(root=ROOT, out=str(tmp_path)))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     import json
-    rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
-    assert len(rows) == 2
+    rows = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(2)]
     seeds = sorted(sum((r["seeds"] for r in rows), []))
     assert seeds == list(range(6))
     assert all(r["sec"] == 2.0 for r in rows) and all(r["tot"] == 6 for r in rows)
