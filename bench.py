@@ -28,6 +28,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+IMG_HOST, IMG_DEVICE, IMG_PINNED = 0, 1, 2   # SDVLB_IMG_* (include/sdvl_b200.h)
 
 
 def load_pkg():
@@ -271,13 +272,13 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     # ---- e2e: frames in pinned host memory
-    e2e_sec, e2e_wall, est_e, stats_e, cnt_e, _, ngroups = timed_run(host.data_ptr(), False, groups)
+    e2e_sec, e2e_wall, est_e, stats_e, cnt_e, _, ngroups = timed_run(host.data_ptr(), IMG_PINNED, groups)
     # ---- value: frames resident in HBM
     dev = host.cuda(non_blocking=False)
-    val_sec, val_wall, est_v, stats_v, cnt_v, _, _ = timed_run(dev.data_ptr(), True, groups)
+    val_sec, val_wall, est_v, stats_v, cnt_v, _, _ = timed_run(dev.data_ptr(), IMG_DEVICE, groups)
     clock_info = clocks.stop()
     # ---- kernel pass: one context so launches do not overlap, per-kernel CUDA events on the launching stream
-    k_sec, _, est_k, stats_k, _, ktimes, _ = timed_run(dev.data_ptr(), True, 1, timing=True, pipelined=False)
+    k_sec, _, est_k, stats_k, _, ktimes, _ = timed_run(dev.data_ptr(), IMG_DEVICE, 1, timing=True, pipelined=False)
     assert np.array_equal(est_k, est_v), "pipelined and lock-step runs must be the same computation"
 
     assert np.array_equal(est_e, est_v), "host-resident and HBM-resident runs must be the same computation"

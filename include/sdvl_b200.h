@@ -86,6 +86,9 @@ typedef struct sdvlb_frame sdvlb_frame; /* device pyramid + corners, pinned host
 int sdvlb_ctx_create(int device, const sdvlb_params* params, const sdvlb_camera* cam,
                      sdvlb_ctx** out);
 int sdvlb_ctx_destroy(sdvlb_ctx* ctx);
+/* Pre-sizes the context's frame pool (device slots + pinned corner mirrors)
+ * so that a steady-state tracker performs no CUDA allocation. */
+int sdvlb_ctx_reserve_frames(sdvlb_ctx* ctx, int n_frames);
 /* Blocks until everything submitted on this context has finished. */
 int sdvlb_ctx_sync(sdvlb_ctx* ctx);
 /* The cudaStream_t every kernel of this context is launched on (for external
@@ -211,10 +214,15 @@ int sdvlb_search_points(sdvlb_ctx* ctx, const sdvlb_frame* cur, const sdvlb_cand
                         int n, const double T_cur[7], sdvlb_match* out);
 
 /* ---- batched front half of ProcessFrame -------------------------------- */
+/* Where a level-0 image lives.  HOST: any host memory (one cudaMemcpyAsync per
+ * frame); DEVICE: device memory; PINNED: page-locked host memory the device
+ * can read (cudaHostAlloc / cudaHostRegister): a whole batch is uploaded by
+ * one kernel reading it over PCIe. */
+enum { SDVLB_IMG_HOST = 0, SDVLB_IMG_DEVICE = 1, SDVLB_IMG_PINNED = 2 };
 typedef struct sdvlb_track_job {
   const uint8_t* image;     /* w*h u8, continuous; host (pinned preferred) or device.
                                NULL: `cur` is a frame made by sdvlb_frames_submit */
-  int32_t image_on_device;
+  int32_t image_on_device;  /* SDVLB_IMG_* : where `image` lives */
   int32_t want_corners;
   int32_t nfeatures;
   int32_t n_feats;
@@ -248,7 +256,7 @@ int sdvlb_track_batch(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, 
  * host with sdvlb_frames_wait / any sdvlb_frame_* accessor.  Images must stay
  * valid until then.  All jobs of one batch either carry images or prebuilt
  * frames. */
-int sdvlb_frames_submit(sdvlb_ctx* ctx, const uint8_t* const* images, int n, int images_on_device,
+int sdvlb_frames_submit(sdvlb_ctx* ctx, const uint8_t* const* images, int n, int images_on_device /* SDVLB_IMG_* */,
                         int want_corners, int nfeatures, sdvlb_frame** out);
 int sdvlb_frames_wait(sdvlb_ctx* ctx, sdvlb_frame* const* frames, int n);
 /* sdvlb_track_batch split in two: _submit enqueues everything on the TRACKING

@@ -60,7 +60,7 @@ EXPORTS = [
     "sdvlb_dev_upload", "sdvlb_ctx_counters", "sdvlb_timing_enable", "sdvlb_timing_read", "sdvlb_frame_create", "sdvlb_frame_detect",
     "sdvlb_frame_level", "sdvlb_frame_corners", "sdvlb_frame_destroy", "sdvlb_image_align", "sdvlb_search_points",
     "sdvlb_track_batch", "sdvlb_frames_submit", "sdvlb_frames_wait", "sdvlb_track_submit", "sdvlb_track_poll",
-    "sdvlb_track_collect",
+    "sdvlb_track_collect", "sdvlb_ctx_reserve_frames",
 ]
 
 

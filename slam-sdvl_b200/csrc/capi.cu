@@ -1,6 +1,11 @@
 // capi.cu — implementation of the C-ABI in include/sdvl_b200.h: contexts, frame storage pool, pinned staging,
 // batched submission of the K1..K4 kernels and per-kernel CUDA-event timing.  No CPU fallback: every entry point
 // either runs the sm_100a kernels or fails with a negative status.
+//
+// Submission cost is part of the design (a tracked frame is a handful of short kernels): frame batches reach the build
+// kernels BY VALUE in kernel parameter space (no descriptor upload), level 0 of a whole batch is uploaded by ONE kernel
+// reading pinned host memory, and every result the host needs (corner lists, poses, matches, overflow flag) is written
+// by the kernels straight into pinned, device-visible host memory, so the steady state issues no D2H copy at all.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -13,13 +18,15 @@
 #include "common.cuh"
 
 // ---- kernel launchers (other translation units)
-cudaError_t sdvlb_launch_pyramid(const FrameDev* d_frames, int n_frames, const PyrGeom& g, cudaStream_t stream);
+cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, cudaStream_t stream);
+cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStream_t stream);
+int sdvlb_pyramid_launches(const PyrGeom& g);
 void sdvlb_fast_plan(const PyrGeom& g, const sdvlb_params& p, int nfeatures, int corner_cap, FastPlan* plan);
-cudaError_t sdvlb_launch_fast_cells(const FrameDev* d_frames, int n_frames, const FastPlan& plan, uint32_t* cell_kp,
-                                    int32_t* cell_cnt, cudaStream_t stream);
-cudaError_t sdvlb_launch_fast_select(const FrameDev* d_frames, int n_frames, const FastPlan& plan, uint32_t* cell_kp,
-                                     int32_t* cell_cnt, uint32_t* level_kp, int32_t* level_cnt, int32_t* frame_ticket,
-                                     int32_t* overflow_flag, cudaStream_t stream);
+cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
+                                    cudaStream_t stream);
+cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
+                                     uint32_t* level_kp, int32_t* level_cnt, int32_t* frame_ticket,
+                                     cudaStream_t stream);
 cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, const PyrGeom& g, const DevParams& dp,
                                cudaStream_t stream);
 cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const FrameDev* d_frames, sdvlb_match* d_out,
@@ -42,7 +49,7 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct Arena {   // bump allocator over a (pinned host, device) buffer pair with identical layout
+struct Arena {   // bump allocator over a pinned host buffer and (optionally) a device buffer with identical layout
   uint8_t* h = nullptr;
   uint8_t* d = nullptr;
   size_t cap = 0, used = 0;
@@ -55,29 +62,32 @@ struct Arena {   // bump allocator over a (pinned host, device) buffer pair with
 
 struct TimerSlot { cudaEvent_t a, b; int kind; };
 
-struct BuildSlot {   // staging of one asynchronous frame-batch submission
-  Arena a;
-  cudaEvent_t done = nullptr;
-  bool used = false;
+constexpr int kBuildEvents = 8;   // ring of "frame batch enqueued" events; a frame borrows the one of its batch
+constexpr int kSlabFrames = 32;
+
+struct BatchOut {   // per-job results in the `out` arena
+  double pose[7];
+  double error;
+  int32_t info[2];
+  int32_t pad[2];
 };
-constexpr int kBuildSlots = 4;
 
 }  // namespace
 
 struct sdvlb_frame {
   sdvlb_ctx* ctx = nullptr;
-  FrameDev dev{};
+  FrameDev dev{};                // host_mirror left null here; set per submission when a mirror is wanted
   uint8_t* d_block = nullptr;    // slot inside one of the context's device slabs
   size_t off_hdr = 0, off_pose = 0;   // corner header (count) + int4 corner list; pose
   uint8_t* h_pyr = nullptr;      // pinned host mirror of the pyramid, allocated on first sdvlb_frame_level()
   bool pyr_mirrored = false;
-  uint8_t* h_corners = nullptr;  // pinned host mirror: 16-byte header (count) + the first corner_copy corners
+  uint8_t* h_corners = nullptr;  // pinned, device-visible: 16-byte header (count) + the first corner_copy corners
   std::vector<int32_t> h_more;   // whole corner list, only when it is longer than corner_copy
-  cudaEvent_t built = nullptr;   // recorded on the build stream after the frame's last build command
+  cudaEvent_t built = nullptr;   // borrowed from the context's ring: recorded after the frame's batch was enqueued
   bool build_pending = false;    // submitted with sdvlb_frames_submit, completion not yet observed by the host
   bool build_corners = false, build_mirror = false;
   bool has_corners = false;
-  int corners_mirrored = -1;     // number of corners valid in the host mirror, -1 = count unknown
+  int corners_mirrored = -1;     // number of corners valid in the host mirror, -1 = not mirrored
   int n_corners = 0;
 };
 
@@ -90,29 +100,30 @@ struct PendingTrack {
   sdvlb_gn_iter* trace = nullptr;
   int trace_cap = 0;
   int* trace_n = nullptr;
-  size_t o_res = 0, o_match = 0, o_trace = 0, o_flag = 0;
+  size_t o_res = 0, o_match = 0, o_trace = 0;
 };
 
 struct sdvlb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;    // tracking stream (ImageAlign, SearchPoint, synchronous frame construction)
   cudaStream_t bstream = nullptr;   // build stream (asynchronous frame batches: upload, pyramid, FAST)
-  BuildSlot bslots[kBuildSlots];
-  int bslot_next = 0;
-  cudaEvent_t last_build = nullptr; // last command of the most recent asynchronous build
-  bool build_in_flight = false;
+  cudaEvent_t bevents[kBuildEvents] = {};
+  int bevent_next = 0;
+  cudaEvent_t last_build = nullptr; // event of the most recent asynchronous build (null: none yet)
+  int32_t* h_overflow = nullptr;    // pinned, device-visible overflow flag written by the selector
   cudaEvent_t track_done = nullptr;
-  PendingTrack* pending = nullptr;
+  PendingTrack pending;
   sdvlb_params params{};
   sdvlb_camera cam{};
   PyrGeom geom{};
   DevParams dp{};
   int w = 0, h = 0;
   int corner_cap = 0;
-  int corner_copy = 0;           // corners copied eagerly to the host mirror
+  int corner_copy = 0;           // corners the pinned host mirror of a frame holds
   std::vector<sdvlb_frame*> pool;      // free frames (device slot attached)
   std::vector<sdvlb_frame*> all_frames;
   std::vector<uint8_t*> slabs;         // device slabs of kSlabFrames frame slots each
+  std::vector<uint8_t*> mirror_slabs;  // pinned host slabs: one corner mirror per frame slot
   size_t block_bytes = 0;
   std::vector<FastPlan> plans;   // one per nfeatures budget seen
   // FAST scratch (sized for `fast_frames` frames)
@@ -122,10 +133,10 @@ struct sdvlb_ctx {
   uint32_t* level_kp = nullptr;
   int32_t* level_cnt = nullptr;
   int32_t* frame_ticket = nullptr;
-  int32_t* overflow_flag = nullptr;   // device
   size_t level_kp_total = 0;
   // staging
-  Arena in, out;                 // host->device descriptors, device->host results
+  Arena in;                      // host->device descriptors (pinned + device copy)
+  Arena out;                     // results: pinned, device-visible host memory the kernels write directly
   uint8_t* scratch = nullptr;    // device-only scratch for ImageAlign caches
   size_t scratch_cap = 0;
   // counters
@@ -163,8 +174,11 @@ int ensure_scratch(sdvlb_ctx* c, size_t bytes) {
   return 0;
 }
 
+// Growing the FAST scratch frees device memory that work in flight on either stream may still use: drain first.
 int ensure_fast_scratch(sdvlb_ctx* c, int n_frames) {
   if (n_frames <= c->fast_frames) return 0;
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->bstream));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
   const int nf = std::max(n_frames, c->fast_frames * 2);
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt); cudaFree(c->frame_ticket);
   c->cell_kp = nullptr; c->cell_cnt = nullptr; c->level_kp = nullptr; c->level_cnt = nullptr; c->frame_ticket = nullptr;
@@ -175,42 +189,56 @@ int ensure_fast_scratch(sdvlb_ctx* c, int n_frames) {
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->level_kp), c->level_kp_total * nf * sizeof(uint32_t)));
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->level_cnt), size_t(nf) * SDVLB_MAX_LEVELS * sizeof(int32_t)));
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->frame_ticket), size_t(nf) * sizeof(int32_t)));
-  SDVLB_CUDA_TRY(cudaMemsetAsync(c->frame_ticket, 0, size_t(nf) * sizeof(int32_t), c->stream));
+  SDVLB_CUDA_TRY(cudaMemset(c->frame_ticket, 0, size_t(nf) * sizeof(int32_t)));
   c->fast_frames = nf;
   return 0;
 }
 
-constexpr int kSlabFrames = 32;
+inline size_t corner_mirror_bytes(const sdvlb_ctx* c) { return align_up(16 + size_t(c->corner_copy) * sizeof(int4), 256); }
 
-// Frames are carved out of device slabs (one cudaMalloc per 32 frames) and recycled through a free list, so the
-// steady state of a tracker performs no CUDA allocation at all.
+// One more slab: kSlabFrames device slots (one cudaMalloc) + their pinned corner mirrors (one cudaHostAlloc).
+int grow_pool(sdvlb_ctx* c) {
+  size_t off = align_up(size_t(c->geom.total) + 256, 256);
+  const size_t off_hdr = off;   off = align_up(off + 16 + size_t(c->corner_cap) * sizeof(int4), 256);
+  const size_t off_pose = off;  off = align_up(off + 7 * sizeof(double), 256);
+  c->block_bytes = off;
+  uint8_t* slab = nullptr;
+  uint8_t* mslab = nullptr;
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&slab), c->block_bytes * kSlabFrames));
+  c->slabs.push_back(slab);
+  SDVLB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&mslab), corner_mirror_bytes(c) * kSlabFrames, cudaHostAllocDefault));
+  c->mirror_slabs.push_back(mslab);
+  for (int i = kSlabFrames - 1; i >= 0; i--) {
+    sdvlb_frame* f = new sdvlb_frame;
+    f->ctx = c;
+    f->d_block = slab + size_t(i) * c->block_bytes;
+    f->h_corners = mslab + size_t(i) * corner_mirror_bytes(c);
+    f->off_hdr = off_hdr; f->off_pose = off_pose;
+    f->dev.pyr = f->d_block;
+    f->dev.n_corners = reinterpret_cast<int32_t*>(f->d_block + off_hdr);
+    f->dev.corners = reinterpret_cast<int4*>(f->d_block + off_hdr + 16);
+    f->dev.pose = reinterpret_cast<double*>(f->d_block + off_pose);
+    f->dev.host_mirror = nullptr;
+    f->dev.mirror_cap = c->corner_copy;
+    c->pool.push_back(f);
+    c->all_frames.push_back(f);
+  }
+  return 0;
+}
+
+// Frames are carved out of slabs and recycled through a free list, so the steady state of a tracker performs no CUDA
+// allocation at all (sdvlb_ctx_reserve_frames pre-sizes the pool).
 int frame_alloc(sdvlb_ctx* c, sdvlb_frame** out) {
   if (c->pool.empty()) {
-    size_t off = align_up(size_t(c->geom.total) + 256, 256);
-    const size_t off_hdr = off;   off = align_up(off + 16 + size_t(c->corner_cap) * sizeof(int4), 256);
-    const size_t off_pose = off;  off = align_up(off + 7 * sizeof(double), 256);
-    c->block_bytes = off;
-    uint8_t* slab = nullptr;
-    SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&slab), c->block_bytes * kSlabFrames));
-    c->slabs.push_back(slab);
-    for (int i = kSlabFrames - 1; i >= 0; i--) {
-      sdvlb_frame* f = new sdvlb_frame;
-      f->ctx = c;
-      f->d_block = slab + size_t(i) * c->block_bytes;
-      f->off_hdr = off_hdr; f->off_pose = off_pose;
-      f->dev.pyr = f->d_block;
-      f->dev.n_corners = reinterpret_cast<int32_t*>(f->d_block + off_hdr);
-      f->dev.corners = reinterpret_cast<int4*>(f->d_block + off_hdr + 16);
-      f->dev.pose = reinterpret_cast<double*>(f->d_block + off_pose);
-      SDVLB_CUDA_TRY(cudaEventCreateWithFlags(&f->built, cudaEventDisableTiming));
-      c->pool.push_back(f);
-      c->all_frames.push_back(f);
-    }
+    const int rc = grow_pool(c);
+    if (rc) return rc;
   }
   sdvlb_frame* f = c->pool.back();
   c->pool.pop_back();
   f->has_corners = false; f->pyr_mirrored = false; f->corners_mirrored = -1; f->n_corners = 0;
   f->build_pending = false; f->build_corners = false; f->build_mirror = false;
+  f->built = nullptr;
+  f->h_more.clear();
   *out = f;
   return 0;
 }
@@ -237,7 +265,7 @@ void timer_end(sdvlb_ctx* c) {
   cudaEventRecord(c->timers[c->timers_used].b, c->timer_stream);
   c->timers_used++;
 }
-void timer_collect(sdvlb_ctx* c) {   // stream must be idle
+void timer_collect(sdvlb_ctx* c) {   // streams must be idle
   for (size_t i = 0; i < c->timers_used; i++) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->timers[i].a, c->timers[i].b) == cudaSuccess) {
@@ -276,8 +304,338 @@ const FastPlan* get_plan(sdvlb_ctx* c, int nfeatures) {
   c->plans.reserve(16);
   FastPlan p;
   sdvlb_fast_plan(c->geom, c->params, nfeatures, c->corner_cap, &p);
+  p.args.overflow_flag = c->h_overflow;
   c->plans.push_back(p);
   return &c->plans.back();
+}
+
+int check_overflow(sdvlb_ctx* c) {   // the stream that ran the selector must have been synchronised
+  volatile int32_t* flag = c->h_overflow;
+  if (*flag) {
+    *flag = 0;
+    return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in FAST selection");
+  }
+  return 0;
+}
+
+// Host bookkeeping once a frame's build commands are known to have completed.
+void finalize_build(sdvlb_ctx* c, sdvlb_frame* f) {
+  f->has_corners = f->build_corners;
+  f->corners_mirrored = -1;
+  if (f->build_corners && f->build_mirror) {
+    memcpy(&f->n_corners, f->h_corners, sizeof(int32_t));
+    f->corners_mirrored = std::min(f->n_corners, c->corner_copy);
+    c->d2h_bytes += 16 + int64_t(f->corners_mirrored) * 16;
+  }
+  f->build_pending = false;
+}
+
+int ensure_built(sdvlb_frame* f) {
+  if (!f->build_pending) return 0;
+  SDVLB_CUDA_TRY(cudaSetDevice(f->ctx->device));
+  SDVLB_CUDA_TRY(cudaEventSynchronize(f->built));
+  finalize_build(f->ctx, f);
+  return check_overflow(f->ctx);
+}
+
+// Enqueues level-0 upload + pyramid (+ FAST + selection) for n frames on `stream`, in chunks of SDVLB_BATCH_MAX.
+// image_loc: 0 host memory of any kind (one cudaMemcpyAsync per frame), 1 device memory, 2 pinned device-visible host
+// memory (both uploaded by one kernel per chunk).
+int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const* images, const int32_t* image_loc,
+                  int n, bool want_corners, int nfeatures, bool mirror, cudaStream_t stream) {
+  const size_t img_bytes = size_t(c->w) * c->h;
+  const FastPlan* plan = want_corners ? get_plan(c, nfeatures) : nullptr;
+  for (int base = 0; base < n; base += SDVLB_BATCH_MAX) {
+    const int m = std::min(SDVLB_BATCH_MAX, n - base);
+    FrameBatch B;
+    ImageBatch I;
+    B.n = m;
+    B.scratch_base = base;
+    bool by_kernel = true;
+    for (int i = 0; i < m; i++) {
+      sdvlb_frame* f = frames[base + i];
+      B.f[i] = f->dev;
+      B.f[i].host_mirror = (want_corners && mirror) ? reinterpret_cast<int32_t*>(f->h_corners) : nullptr;
+      I.src[i] = images[base + i];
+      if (image_loc[base + i] == 0) by_kernel = false;
+      f->build_corners = want_corners;
+      f->build_mirror = want_corners && mirror;
+    }
+    if (by_kernel) {
+      SDVLB_CUDA_TRY(sdvlb_launch_upload(B, I, int(img_bytes), stream));
+      c->n_launches += 1;
+    } else {
+      for (int i = 0; i < m; i++)
+        SDVLB_CUDA_TRY(cudaMemcpyAsync(B.f[i].pyr, I.src[i], img_bytes,
+                                       image_loc[base + i] == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    }
+    for (int i = 0; i < m; i++)
+      if (image_loc[base + i] != 1) c->h2d_bytes += int64_t(img_bytes);
+    timer_begin(c, SDVLB_K_PYRAMID, stream);
+    SDVLB_CUDA_TRY(sdvlb_launch_pyramid(B, c->geom, stream));
+    timer_end(c);
+    c->n_launches += sdvlb_pyramid_launches(c->geom);
+    if (want_corners) {
+      timer_begin(c, SDVLB_K_FAST, stream);
+      SDVLB_CUDA_TRY(sdvlb_launch_fast_cells(B, *plan, c->cell_kp, c->cell_cnt, stream));
+      timer_end(c);
+      timer_begin(c, SDVLB_K_SELECT, stream);
+      SDVLB_CUDA_TRY(sdvlb_launch_fast_select(B, *plan, c->cell_kp, c->cell_cnt, c->level_kp, c->level_cnt,
+                                              c->frame_ticket, stream));
+      timer_end(c);
+      c->n_launches += 2;
+    }
+  }
+  return 0;
+}
+
+// Submits (upload + pyramid + FAST for jobs that carry an image) + align + search for n jobs on the tracking stream;
+// does not wait.  collect_batch() synchronises and copies the results into the jobs.
+int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_iter* trace, int trace_cap,
+                 int* trace_n, const sdvlb_gn_forced* forced, bool build_frames, int fast = 0) {
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  if (c->pending.active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
+  const PyrGeom& g = c->geom;
+
+  int n_detect = 0, n_align = 0, n_cands = 0, n_feats = 0, nfeatures = -1;
+  for (int i = 0; i < n; i++) {
+    if (build_frames && jobs[i].want_corners) {
+      n_detect++;
+      if (nfeatures < 0) nfeatures = jobs[i].nfeatures;
+      else if (nfeatures != jobs[i].nfeatures) return sdvlb_set_error(SDVLB_ERR_ARG, "mixed nfeatures in one batch");
+    }
+    if (jobs[i].ref) { n_align++; n_feats += jobs[i].n_feats; }
+    if (jobs[i].n_cands < 0 || jobs[i].n_feats < 0) return sdvlb_set_error(SDVLB_ERR_ARG, "negative count");
+    n_cands += jobs[i].n_cands;
+  }
+  if (build_frames && n_detect != 0 && n_detect != n)
+    return sdvlb_set_error(SDVLB_ERR_ARG, "mixed want_corners in one batch");
+
+  // ---- frames
+  if (build_frames) {
+    if (n_detect > 0) {
+      const int rc = ensure_fast_scratch(c, n);
+      if (rc) return rc;
+    }
+    for (int i = 0; i < n; i++) {
+      sdvlb_frame* f = nullptr;
+      const int rc = frame_alloc(c, &f);
+      if (rc) { for (int k = 0; k < i; k++) { frame_release(c, jobs[k].cur); jobs[k].cur = nullptr; } return rc; }
+      jobs[i].cur = f;
+    }
+  }
+
+  // ---- stage inputs
+  Arena& in = c->in;
+  Arena& out = c->out;
+  in.used = 0; out.used = 0;
+  const size_t need_in = 4096 + size_t(n) * (sizeof(FrameDev) + sizeof(AlignJobDev) + 512) +
+                         size_t(n_feats) * sizeof(sdvlb_align_feat) + size_t(n_cands) * sizeof(SearchCandDev) +
+                         (forced ? size_t(forced->n_total) * 56 + 512 : 0) + 32 * 256;
+  const size_t need_out = 4096 + size_t(n) * sizeof(BatchOut) + size_t(n_cands) * sizeof(sdvlb_match) +
+                          size_t(trace ? trace_cap : 0) * sizeof(sdvlb_gn_iter) + 16 * 256;
+  int rc = ensure_arena(&in, need_in, true);
+  if (rc) return rc;
+  rc = ensure_arena(&out, need_out, false);
+  if (rc) return rc;
+  size_t scratch_need = 0;
+  for (int i = 0; i < n; i++)
+    if (jobs[i].ref) scratch_need += align_up(size_t(jobs[i].n_feats) * (48 * 4 + 18 * 8 + 4) + 1024, 256);
+  rc = ensure_scratch(c, scratch_need);
+  if (rc) return rc;
+
+  const size_t o_frames = in.take(size_t(n) * sizeof(FrameDev));
+  const size_t o_align = in.take(size_t(std::max(n_align, 1)) * sizeof(AlignJobDev));
+  const size_t o_feats = in.take(size_t(std::max(n_feats, 1)) * sizeof(sdvlb_align_feat));
+  const size_t o_cands = in.take(size_t(std::max(n_cands, 1)) * sizeof(SearchCandDev));
+  size_t o_forced_T = 0, o_forced_it = 0;
+  if (forced) {
+    o_forced_T = in.take(size_t(forced->n_total) * 7 * sizeof(double));
+    o_forced_it = in.take(SDVLB_MAX_LEVELS * sizeof(int32_t));
+    memcpy(in.h + o_forced_T, forced->T, size_t(forced->n_total) * 7 * sizeof(double));
+    memset(in.h + o_forced_it, 0, SDVLB_MAX_LEVELS * sizeof(int32_t));
+    memcpy(in.h + o_forced_it, forced->iters, size_t(c->params.pyramid_levels) * sizeof(int32_t));
+  }
+  const size_t o_prior = in.take(size_t(n) * 7 * sizeof(double));
+  for (int i = 0; i < n; i++) memcpy(in.h + o_prior + size_t(i) * 56, jobs[i].T_cur, 56);
+  const size_t o_res = out.take(size_t(n) * sizeof(BatchOut));
+  const size_t o_match = out.take(size_t(std::max(n_cands, 1)) * sizeof(sdvlb_match));
+  const size_t o_trace = trace ? out.take(size_t(trace_cap) * sizeof(sdvlb_gn_iter)) : 0;
+
+  FrameDev* hf = reinterpret_cast<FrameDev*>(in.h + o_frames);
+  AlignJobDev* ha = reinterpret_cast<AlignJobDev*>(in.h + o_align);
+  sdvlb_align_feat* hfe = reinterpret_cast<sdvlb_align_feat*>(in.h + o_feats);
+  SearchCandDev* hc = reinterpret_cast<SearchCandDev*>(in.h + o_cands);
+  int ai = 0, fi = 0, cidx = 0;
+  size_t sc_off = 0;
+  for (int i = 0; i < n; i++) {
+    sdvlb_track_job& j = jobs[i];
+    if (!j.cur) return sdvlb_set_error(SDVLB_ERR_ARG, "job without current frame");
+    hf[i] = j.cur->dev;
+    if (j.ref) {
+      AlignJobDev& a = ha[ai];
+      memset(&a, 0, sizeof(a));
+      a.ref = j.ref->dev;
+      a.cur = j.cur->dev;
+      a.feats = reinterpret_cast<const sdvlb_align_feat*>(in.d + o_feats) + fi;
+      a.n = j.n_feats;
+      a.fast = fast;
+      memcpy(a.T_ref, j.T_ref, sizeof(a.T_ref));
+      memcpy(a.T_cur, j.T_cur, sizeof(a.T_cur));
+      BatchOut* hres = reinterpret_cast<BatchOut*>(out.h + o_res) + i;   // pinned host memory, written by the kernel
+      a.out_pose = hres->pose;
+      a.out_info = hres->info;
+      a.out_error = &hres->error;
+      a.trace = (trace && ai == 0) ? reinterpret_cast<sdvlb_gn_iter*>(out.h + o_trace) : nullptr;
+      a.trace_cap = trace ? trace_cap : 0;
+      if (forced && ai == 0) {
+        a.forced_T = reinterpret_cast<const double*>(in.d + o_forced_T);
+        a.forced_iters = reinterpret_cast<const int32_t*>(in.d + o_forced_it);
+        a.forced_n = forced->n_total;
+      }
+      uint8_t* sc = c->scratch + sc_off;
+      a.sc_d = reinterpret_cast<double*>(sc);
+      a.sc_f = reinterpret_cast<float*>(sc + align_up(size_t(j.n_feats) * 18 * 8, 256));
+      a.sc_flags = reinterpret_cast<int32_t*>(sc + align_up(size_t(j.n_feats) * 18 * 8, 256) +
+                                              align_up(size_t(j.n_feats) * 48 * 4, 256));
+      sc_off += align_up(size_t(j.n_feats) * (48 * 4 + 18 * 8 + 4) + 1024, 256);
+      if (j.n_feats > 0) memcpy(hfe + fi, j.feats, size_t(j.n_feats) * sizeof(sdvlb_align_feat));
+      fi += j.n_feats;
+      ai++;
+    }
+    for (int k = 0; k < j.n_cands; k++) {
+      const sdvlb_candidate& s = j.cands[k];
+      SearchCandDev& d = hc[cidx++];
+      if (!s.ref_frame) return sdvlb_set_error(SDVLB_ERR_ARG, "candidate without reference frame");
+      d.ref_pyr = s.ref_frame->dev.pyr;
+      memcpy(d.ref_T, s.ref_T, sizeof(d.ref_T));
+      d.ref_px[0] = s.ref_px[0]; d.ref_px[1] = s.ref_px[1];
+      d.ref_v[0] = s.ref_v[0]; d.ref_v[1] = s.ref_v[1]; d.ref_v[2] = s.ref_v[2];
+      d.idepth = s.idepth; d.idepth_std = s.idepth_std;
+      d.px[0] = s.px[0]; d.px[1] = s.px[1];
+      d.pos[0] = s.pos[0]; d.pos[1] = s.pos[1]; d.pos[2] = s.pos[2];
+      d.ref_level = s.ref_level;
+      d.flags = s.flags;
+      d.cur_index = i;
+      d.pad_ = 0;
+      if (s.ref_level < 0 || s.ref_level >= c->params.pyramid_levels)
+        return sdvlb_set_error(SDVLB_ERR_ARG, "candidate level out of range");
+    }
+  }
+
+  // ---- ordering against asynchronous frame batches: frames still being built (wait for THEIR batch only, not for
+  // batches enqueued later as prefetch), and the FAST scratch both streams share when this call builds frames itself
+  {
+    cudaEvent_t waited[4] = {nullptr, nullptr, nullptr, nullptr};
+    int nw = 0;
+    auto wait_for = [&](cudaEvent_t ev) -> cudaError_t {
+      for (int k = 0; k < nw; k++) if (waited[k] == ev) return cudaSuccess;
+      if (nw < 4) waited[nw++] = ev;
+      return cudaStreamWaitEvent(c->stream, ev, 0);
+    };
+    if (build_frames && c->last_build) SDVLB_CUDA_TRY(wait_for(c->last_build));
+    for (int i = 0; i < n; i++) {
+      if (!build_frames && jobs[i].cur->build_pending) SDVLB_CUDA_TRY(wait_for(jobs[i].cur->built));
+      if (jobs[i].ref && jobs[i].ref->build_pending) SDVLB_CUDA_TRY(wait_for(jobs[i].ref->built));
+    }
+  }
+
+  // ---- H2D of the descriptors (one copy)
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, in.used, cudaMemcpyHostToDevice, c->stream));
+  c->h2d_bytes += int64_t(in.used);
+  // prior poses for frames that are not aligned (search may still read cur.pose)
+  for (int i = 0; i < n; i++)
+    if (!jobs[i].ref && jobs[i].n_cands > 0)
+      SDVLB_CUDA_TRY(cudaMemcpyAsync(jobs[i].cur->dev.pose, in.d + o_prior + size_t(i) * 56, 56,
+                                     cudaMemcpyDeviceToDevice, c->stream));
+
+  // ---- kernels
+  if (build_frames) {
+    std::vector<sdvlb_frame*> fr(n);
+    std::vector<const uint8_t*> img(n);
+    std::vector<int32_t> loc(n);
+    for (int i = 0; i < n; i++) { fr[i] = jobs[i].cur; img[i] = jobs[i].image; loc[i] = jobs[i].image_on_device; }
+    rc = enqueue_build(c, fr.data(), img.data(), loc.data(), n, n_detect > 0, nfeatures, mirror != 0, c->stream);
+    if (rc) return rc;
+  }
+  if (n_align > 0) {
+    timer_begin(c, SDVLB_K_ALIGN);
+    SDVLB_CUDA_TRY(sdvlb_launch_align(in.d + o_align, n_align, g, c->dp, c->stream));
+    timer_end(c);
+    c->n_launches += 1;
+  }
+  if (n_cands > 0) {
+    timer_begin(c, SDVLB_K_SEARCH);
+    SDVLB_CUDA_TRY(sdvlb_launch_search(reinterpret_cast<const SearchCandDev*>(in.d + o_cands), n_cands,
+                                       reinterpret_cast<const FrameDev*>(in.d + o_frames),
+                                       reinterpret_cast<sdvlb_match*>(out.h + o_match), g, c->dp, c->stream));
+    timer_end(c);
+    c->n_launches += 1;
+  }
+  c->d2h_bytes += int64_t(out.used);   // written over PCIe by the kernels themselves
+  SDVLB_CUDA_TRY(cudaEventRecord(c->track_done, c->stream));
+
+  PendingTrack& P = c->pending;
+  P.active = true;
+  P.jobs = jobs; P.n = n; P.build_frames = build_frames;
+  P.trace = trace; P.trace_cap = trace_cap; P.trace_n = trace_n;
+  P.o_res = o_res; P.o_match = o_match; P.o_trace = o_trace;
+  return 0;
+}
+
+int collect_batch(sdvlb_ctx* c) {
+  PendingTrack& P = c->pending;
+  if (!P.active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
+  P.active = false;
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  SDVLB_CUDA_TRY(cudaEventSynchronize(c->track_done));
+  Arena& out = c->out;
+  const int rc = check_overflow(c);
+  if (rc) return rc;
+  const BatchOut* res = reinterpret_cast<const BatchOut*>(out.h + P.o_res);
+  const sdvlb_match* hm = reinterpret_cast<const sdvlb_match*>(out.h + P.o_match);
+  int mo = 0;
+  bool first_align = true;
+  for (int i = 0; i < P.n; i++) {
+    sdvlb_track_job& j = P.jobs[i];
+    // the tracking stream ran after this frame's build (same stream, or ordered by its `built` event)
+    if (P.build_frames || j.cur->build_pending) finalize_build(c, j.cur);
+    if (j.ref) {
+      memcpy(j.T_cur, res[i].pose, sizeof(j.T_cur));
+      j.n_tracked = res[i].info[0] / (c->params.align_patch_size * c->params.align_patch_size);
+      j.gn_iters = res[i].info[1];
+      j.error = res[i].error;
+      if (first_align) {
+        if (P.trace_n) *P.trace_n = res[i].info[1];
+        if (P.trace) memcpy(P.trace, out.h + P.o_trace, size_t(std::min(res[i].info[1], P.trace_cap)) * sizeof(sdvlb_gn_iter));
+        first_align = false;
+      }
+    }
+    if (j.n_cands > 0) memcpy(j.matches, hm + mo, size_t(j.n_cands) * sizeof(sdvlb_match));
+    mo += j.n_cands;
+  }
+  return 0;
+}
+
+int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_iter* trace, int trace_cap,
+              int* trace_n, const sdvlb_gn_forced* forced, bool build_frames, int fast = 0) {
+  const int rc = submit_batch(c, jobs, n, mirror, trace, trace_cap, trace_n, forced, build_frames, fast);
+  if (rc) { c->pending.active = false; return rc; }
+  return collect_batch(c);
+}
+
+int check_track_args(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, bool* build) {
+  if (!ctx || !jobs || n_jobs <= 0) return sdvlb_set_error(SDVLB_ERR_ARG, "bad batch");
+  if (w != ctx->w || h != ctx->h) return sdvlb_set_error(SDVLB_ERR_ARG, "image size differs from the context camera");
+  int with_image = 0;
+  for (int i = 0; i < n_jobs; i++) {
+    if (jobs[i].image) with_image++;
+    else if (!jobs[i].cur) return sdvlb_set_error(SDVLB_ERR_ARG, "job with neither an image nor a prebuilt frame");
+  }
+  if (with_image != 0 && with_image != n_jobs)
+    return sdvlb_set_error(SDVLB_ERR_ARG, "a batch must either build all its frames or use prebuilt frames only");
+  *build = with_image == n_jobs;
+  return 0;
 }
 
 }  // namespace
@@ -325,13 +683,11 @@ int sdvlb_ctx_create(int device, const sdvlb_params* params, const sdvlb_camera*
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, prio_lo);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->last_build, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->track_done, cudaEventDisableTiming);
-  for (int i = 0; i < kBuildSlots && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->bslots[i].done, cudaEventDisableTiming);
-  if (e != cudaSuccess) { delete c; return sdvlb_set_cuda_error(e, "cudaStreamCreate", __FILE__, __LINE__); }
-  e = cudaMalloc(reinterpret_cast<void**>(&c->overflow_flag), 64);
-  if (e == cudaSuccess) e = cudaMemsetAsync(c->overflow_flag, 0, 64, c->stream);
-  if (e != cudaSuccess) { delete c; return sdvlb_set_cuda_error(e, "overflow flag", __FILE__, __LINE__); }
+  for (int i = 0; i < kBuildEvents && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->bevents[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_overflow), 64, cudaHostAllocDefault);
+  if (e != cudaSuccess) { delete c; return sdvlb_set_cuda_error(e, "context resources", __FILE__, __LINE__); }
+  memset(c->h_overflow, 0, 64);
   const FastPlan* plan = get_plan(c, p.num_features);
   c->level_kp_total = size_t(plan->args.level_kp_total);
   *out = c;
@@ -345,25 +701,18 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   cudaStreamSynchronize(c->bstream);
   for (sdvlb_frame* f : c->all_frames) {
     if (f->h_pyr) cudaFreeHost(f->h_pyr);
-    if (f->h_corners) cudaFreeHost(f->h_corners);
-    if (f->built) cudaEventDestroy(f->built);
     delete f;
   }
-  for (int i = 0; i < kBuildSlots; i++) {
-    if (c->bslots[i].a.h) cudaFreeHost(c->bslots[i].a.h);
-    if (c->bslots[i].a.d) cudaFree(c->bslots[i].a.d);
-    if (c->bslots[i].done) cudaEventDestroy(c->bslots[i].done);
-  }
-  if (c->last_build) cudaEventDestroy(c->last_build);
-  if (c->track_done) cudaEventDestroy(c->track_done);
-  delete c->pending;
   for (uint8_t* slab : c->slabs) cudaFree(slab);
+  for (uint8_t* slab : c->mirror_slabs) cudaFreeHost(slab);
+  for (int i = 0; i < kBuildEvents; i++) if (c->bevents[i]) cudaEventDestroy(c->bevents[i]);
+  if (c->track_done) cudaEventDestroy(c->track_done);
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
-  cudaFree(c->frame_ticket); cudaFree(c->overflow_flag); cudaFree(c->scratch);
+  cudaFree(c->frame_ticket); cudaFree(c->scratch);
+  if (c->h_overflow) cudaFreeHost(c->h_overflow);
   if (c->in.h) cudaFreeHost(c->in.h);
   if (c->in.d) cudaFree(c->in.d);
   if (c->out.h) cudaFreeHost(c->out.h);
-  if (c->out.d) cudaFree(c->out.d);
   for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->bstream);
@@ -378,6 +727,16 @@ int sdvlb_ctx_sync(sdvlb_ctx* c) {
   return 0;
 }
 void* sdvlb_ctx_stream(sdvlb_ctx* c) { return c->stream; }
+
+int sdvlb_ctx_reserve_frames(sdvlb_ctx* c, int n_frames) {
+  if (!c || n_frames < 0) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  while (int(c->all_frames.size()) < n_frames) {
+    const int rc = grow_pool(c);
+    if (rc) return rc;
+  }
+  return 0;
+}
 
 int sdvlb_host_alloc(void** p, uint64_t bytes) { SDVLB_CUDA_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault)); return 0; }
 int sdvlb_host_free(void* p) { SDVLB_CUDA_TRY(cudaFreeHost(p)); return 0; }
@@ -420,345 +779,7 @@ int sdvlb_timing_read(sdvlb_ctx* c, double ms[SDVLB_K_COUNT], int64_t launches[S
   return 0;
 }
 
-}  // extern "C"
-
-
-// ================================================================================================ batched core
-namespace {
-
-struct BatchOut {   // per-job results in the `out` arena
-  double pose[7];
-  double error;
-  int32_t info[2];
-  int32_t pad[2];
-};
-
-}  // namespace
-
-namespace {
-
-inline size_t corner_mirror_bytes(const sdvlb_ctx* c) { return 16 + size_t(c->corner_copy) * sizeof(int4); }
-
-// D2H of the corner header + first corner_copy corners into the frame's own pinned mirror.
-int enqueue_corner_mirror(sdvlb_ctx* c, sdvlb_frame* f, cudaStream_t stream) {
-  if (!f->h_corners) SDVLB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&f->h_corners), corner_mirror_bytes(c), cudaHostAllocDefault));
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(f->h_corners, f->d_block + f->off_hdr, corner_mirror_bytes(c), cudaMemcpyDeviceToHost, stream));
-  c->d2h_bytes += int64_t(corner_mirror_bytes(c));
-  return 0;
-}
-
-// Host bookkeeping once a frame's build commands are known to have completed.
-void finalize_build(sdvlb_ctx* c, sdvlb_frame* f, bool want_corners, bool mirrored) {
-  f->has_corners = want_corners;
-  f->corners_mirrored = -1;
-  if (want_corners && mirrored && f->h_corners) {
-    memcpy(&f->n_corners, f->h_corners, sizeof(int32_t));
-    f->corners_mirrored = std::min(f->n_corners, c->corner_copy);
-  }
-  f->build_pending = false;
-}
-
-int ensure_built(sdvlb_frame* f) {
-  if (!f->build_pending) return 0;
-  SDVLB_CUDA_TRY(cudaSetDevice(f->ctx->device));
-  SDVLB_CUDA_TRY(cudaEventSynchronize(f->built));
-  finalize_build(f->ctx, f, f->build_corners, f->build_mirror);
-  return 0;
-}
-
-// Enqueues pyramid (+ FAST + selection) for `n` frames whose level 0 is already on its way on `stream`.
-// d_all / d_detect: device arrays of FrameDev (all frames / frames that want corners).
-int enqueue_build_kernels(sdvlb_ctx* c, const FrameDev* d_all, int n, const FrameDev* d_detect, int n_detect, int nfeatures,
-                          cudaStream_t stream) {
-  timer_begin(c, SDVLB_K_PYRAMID, stream);
-  SDVLB_CUDA_TRY(sdvlb_launch_pyramid(d_all, n, c->geom, stream));
-  timer_end(c);
-  c->n_launches += c->geom.levels - 1;
-  if (n_detect > 0) {
-    const FastPlan* plan = get_plan(c, nfeatures);
-    timer_begin(c, SDVLB_K_FAST, stream);
-    SDVLB_CUDA_TRY(sdvlb_launch_fast_cells(d_detect, n_detect, *plan, c->cell_kp, c->cell_cnt, stream));
-    timer_end(c);
-    timer_begin(c, SDVLB_K_SELECT, stream);
-    SDVLB_CUDA_TRY(sdvlb_launch_fast_select(d_detect, n_detect, *plan, c->cell_kp, c->cell_cnt, c->level_kp, c->level_cnt,
-                                            c->frame_ticket, c->overflow_flag, stream));
-    timer_end(c);
-    c->n_launches += 2;
-  }
-  return 0;
-}
-
-// Submits (pyramid + FAST for jobs that carry an image) + align + search for n jobs on the tracking stream; does not
-// wait.  collect_batch() synchronises and copies the results into the jobs.
-int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_iter* trace, int trace_cap,
-                 int* trace_n, const sdvlb_gn_forced* forced, bool build_frames, int fast = 0) {
-  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-  if (!c->pending) c->pending = new PendingTrack;
-  if (c->pending->active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
-  const PyrGeom& g = c->geom;
-  const size_t img_bytes = size_t(c->w) * c->h;
-
-  // ---- frames
-  if (build_frames) {
-    for (int i = 0; i < n; i++) {
-      sdvlb_frame* f = nullptr;
-      const int rc = frame_alloc(c, &f);
-      if (rc) { for (int k = 0; k < i; k++) { frame_release(c, jobs[k].cur); jobs[k].cur = nullptr; } return rc; }
-      jobs[i].cur = f;
-    }
-  }
-  int n_detect = 0, n_align = 0, n_cands = 0, n_feats = 0, nfeatures = -1;
-  for (int i = 0; i < n; i++) {
-    if (build_frames && jobs[i].want_corners) {
-      n_detect++;
-      if (nfeatures < 0) nfeatures = jobs[i].nfeatures;
-      else if (nfeatures != jobs[i].nfeatures) return sdvlb_set_error(SDVLB_ERR_ARG, "mixed nfeatures in one batch");
-    }
-    if (jobs[i].ref) { n_align++; n_feats += jobs[i].n_feats; }
-    if (jobs[i].n_cands < 0 || jobs[i].n_feats < 0) return sdvlb_set_error(SDVLB_ERR_ARG, "negative count");
-    n_cands += jobs[i].n_cands;
-  }
-
-  // ---- stage inputs
-  Arena& in = c->in;
-  Arena& out = c->out;
-  in.used = 0; out.used = 0;
-  const size_t need_in = 4096 + size_t(n) * (2 * sizeof(FrameDev) + sizeof(AlignJobDev) + 512) +
-                         size_t(n_feats) * sizeof(sdvlb_align_feat) + size_t(n_cands) * sizeof(SearchCandDev) +
-                         (forced ? size_t(forced->n_total) * 56 + 512 : 0) + 32 * 256;
-  const size_t need_out = 4096 + size_t(n) * sizeof(BatchOut) + size_t(n_cands) * sizeof(sdvlb_match) +
-                          size_t(trace ? trace_cap : 0) * sizeof(sdvlb_gn_iter) + 16 * 256;
-  int rc = ensure_arena(&in, need_in, true);
-  if (rc) return rc;
-  rc = ensure_arena(&out, need_out, true);
-  if (rc) return rc;
-  size_t scratch_need = 0;
-  for (int i = 0; i < n; i++)
-    if (jobs[i].ref) scratch_need += align_up(size_t(jobs[i].n_feats) * (48 * 4 + 18 * 8 + 4) + 1024, 256);
-  rc = ensure_scratch(c, scratch_need);
-  if (rc) return rc;
-
-  const size_t o_frames = in.take(size_t(n) * sizeof(FrameDev));
-  const size_t o_detect = in.take(size_t(std::max(n_detect, 1)) * sizeof(FrameDev));
-  const size_t o_align = in.take(size_t(std::max(n_align, 1)) * sizeof(AlignJobDev));
-  const size_t o_feats = in.take(size_t(std::max(n_feats, 1)) * sizeof(sdvlb_align_feat));
-  const size_t o_cands = in.take(size_t(std::max(n_cands, 1)) * sizeof(SearchCandDev));
-  size_t o_forced_T = 0, o_forced_it = 0;
-  if (forced) {
-    o_forced_T = in.take(size_t(forced->n_total) * 7 * sizeof(double));
-    o_forced_it = in.take(SDVLB_MAX_LEVELS * sizeof(int32_t));
-    memcpy(in.h + o_forced_T, forced->T, size_t(forced->n_total) * 7 * sizeof(double));
-    memset(in.h + o_forced_it, 0, SDVLB_MAX_LEVELS * sizeof(int32_t));
-    memcpy(in.h + o_forced_it, forced->iters, size_t(c->params.pyramid_levels) * sizeof(int32_t));
-  }
-  const size_t o_prior = in.take(size_t(n) * 7 * sizeof(double));
-  for (int i = 0; i < n; i++) memcpy(in.h + o_prior + size_t(i) * 56, jobs[i].T_cur, 56);
-  const size_t o_res = out.take(size_t(n) * sizeof(BatchOut));
-  const size_t o_match = out.take(size_t(std::max(n_cands, 1)) * sizeof(sdvlb_match));
-  const size_t o_trace = trace ? out.take(size_t(trace_cap) * sizeof(sdvlb_gn_iter)) : 0;
-  const size_t o_flag = out.take(64);
-
-  FrameDev* hf = reinterpret_cast<FrameDev*>(in.h + o_frames);
-  FrameDev* hd = reinterpret_cast<FrameDev*>(in.h + o_detect);
-  AlignJobDev* ha = reinterpret_cast<AlignJobDev*>(in.h + o_align);
-  sdvlb_align_feat* hfe = reinterpret_cast<sdvlb_align_feat*>(in.h + o_feats);
-  SearchCandDev* hc = reinterpret_cast<SearchCandDev*>(in.h + o_cands);
-  int di = 0, ai = 0, fi = 0, cidx = 0;
-  size_t sc_off = 0;
-  for (int i = 0; i < n; i++) {
-    sdvlb_track_job& j = jobs[i];
-    if (!j.cur) return sdvlb_set_error(SDVLB_ERR_ARG, "job without current frame");
-    hf[i] = j.cur->dev;
-    if (build_frames && j.want_corners) hd[di++] = j.cur->dev;
-    if (j.ref) {
-      AlignJobDev& a = ha[ai];
-      memset(&a, 0, sizeof(a));
-      a.ref = j.ref->dev;
-      a.cur = j.cur->dev;
-      a.feats = reinterpret_cast<const sdvlb_align_feat*>(in.d + o_feats) + fi;
-      a.n = j.n_feats;
-      a.fast = fast;
-      memcpy(a.T_ref, j.T_ref, sizeof(a.T_ref));
-      memcpy(a.T_cur, j.T_cur, sizeof(a.T_cur));
-      BatchOut* dres = reinterpret_cast<BatchOut*>(out.d + o_res) + i;
-      a.out_pose = dres->pose;
-      a.out_info = dres->info;
-      a.out_error = &dres->error;
-      a.trace = (trace && ai == 0) ? reinterpret_cast<sdvlb_gn_iter*>(out.d + o_trace) : nullptr;
-      a.trace_cap = trace ? trace_cap : 0;
-      if (forced && ai == 0) {
-        a.forced_T = reinterpret_cast<const double*>(in.d + o_forced_T);
-        a.forced_iters = reinterpret_cast<const int32_t*>(in.d + o_forced_it);
-        a.forced_n = forced->n_total;
-      }
-      uint8_t* sc = c->scratch + sc_off;
-      a.sc_d = reinterpret_cast<double*>(sc);
-      a.sc_f = reinterpret_cast<float*>(sc + align_up(size_t(j.n_feats) * 18 * 8, 256));
-      a.sc_flags = reinterpret_cast<int32_t*>(sc + align_up(size_t(j.n_feats) * 18 * 8, 256) +
-                                              align_up(size_t(j.n_feats) * 48 * 4, 256));
-      sc_off += align_up(size_t(j.n_feats) * (48 * 4 + 18 * 8 + 4) + 1024, 256);
-      if (j.n_feats > 0) memcpy(hfe + fi, j.feats, size_t(j.n_feats) * sizeof(sdvlb_align_feat));
-      fi += j.n_feats;
-      ai++;
-    }
-    for (int k = 0; k < j.n_cands; k++) {
-      const sdvlb_candidate& s = j.cands[k];
-      SearchCandDev& d = hc[cidx++];
-      if (!s.ref_frame) return sdvlb_set_error(SDVLB_ERR_ARG, "candidate without reference frame");
-      d.ref_pyr = s.ref_frame->dev.pyr;
-      memcpy(d.ref_T, s.ref_T, sizeof(d.ref_T));
-      d.ref_px[0] = s.ref_px[0]; d.ref_px[1] = s.ref_px[1];
-      d.ref_v[0] = s.ref_v[0]; d.ref_v[1] = s.ref_v[1]; d.ref_v[2] = s.ref_v[2];
-      d.idepth = s.idepth; d.idepth_std = s.idepth_std;
-      d.px[0] = s.px[0]; d.px[1] = s.px[1];
-      d.pos[0] = s.pos[0]; d.pos[1] = s.pos[1]; d.pos[2] = s.pos[2];
-      d.ref_level = s.ref_level;
-      d.flags = s.flags;
-      d.cur_index = i;
-      d.pad_ = 0;
-      if (s.ref_level < 0 || s.ref_level >= c->params.pyramid_levels)
-        return sdvlb_set_error(SDVLB_ERR_ARG, "candidate level out of range");
-    }
-  }
-
-  // ---- ordering against asynchronous frame batches: frames still being built, and the shared FAST scratch
-  if (build_frames && c->build_in_flight) SDVLB_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_build, 0));
-  for (int i = 0; i < n; i++) {
-    if (!build_frames && jobs[i].cur->build_pending) SDVLB_CUDA_TRY(cudaStreamWaitEvent(c->stream, jobs[i].cur->built, 0));
-    if (jobs[i].ref && jobs[i].ref->build_pending) SDVLB_CUDA_TRY(cudaStreamWaitEvent(c->stream, jobs[i].ref->built, 0));
-  }
-
-  // ---- H2D
-  if (build_frames) {
-    for (int i = 0; i < n; i++) {
-      SDVLB_CUDA_TRY(cudaMemcpyAsync(jobs[i].cur->dev.pyr, jobs[i].image, img_bytes,
-                                     jobs[i].image_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                     c->stream));
-      if (!jobs[i].image_on_device) c->h2d_bytes += int64_t(img_bytes);
-    }
-  }
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, in.used, cudaMemcpyHostToDevice, c->stream));
-  c->h2d_bytes += int64_t(in.used);
-  // prior poses for frames that are not aligned (search may still read cur.pose)
-  for (int i = 0; i < n; i++)
-    if (!jobs[i].ref && jobs[i].n_cands > 0)
-      SDVLB_CUDA_TRY(cudaMemcpyAsync(jobs[i].cur->dev.pose, in.d + o_prior + size_t(i) * 56, 56,
-                                     cudaMemcpyDeviceToDevice, c->stream));
-
-  // ---- kernels
-  if (build_frames) {
-    if (n_detect > 0) {
-      rc = ensure_fast_scratch(c, n_detect);
-      if (rc) return rc;
-    }
-    rc = enqueue_build_kernels(c, reinterpret_cast<const FrameDev*>(in.d + o_frames), n,
-                               reinterpret_cast<const FrameDev*>(in.d + o_detect), n_detect, nfeatures, c->stream);
-    if (rc) return rc;
-  }
-  if (n_align > 0) {
-    timer_begin(c, SDVLB_K_ALIGN);
-    SDVLB_CUDA_TRY(sdvlb_launch_align(in.d + o_align, n_align, g, c->dp, c->stream));
-    timer_end(c);
-    c->n_launches += 1;
-  }
-  if (n_cands > 0) {
-    timer_begin(c, SDVLB_K_SEARCH);
-    SDVLB_CUDA_TRY(sdvlb_launch_search(reinterpret_cast<const SearchCandDev*>(in.d + o_cands), n_cands,
-                                       reinterpret_cast<const FrameDev*>(in.d + o_frames),
-                                       reinterpret_cast<sdvlb_match*>(out.d + o_match), g, c->dp, c->stream));
-    timer_end(c);
-    c->n_launches += 1;
-  }
-
-  // ---- D2H
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(out.d + o_flag, c->overflow_flag, 4, cudaMemcpyDeviceToDevice, c->stream));
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(out.h, out.d, out.used, cudaMemcpyDeviceToHost, c->stream));
-  c->d2h_bytes += int64_t(out.used);
-  if (build_frames && mirror)
-    for (int i = 0; i < n; i++)
-      if (jobs[i].want_corners) {
-        rc = enqueue_corner_mirror(c, jobs[i].cur, c->stream);
-        if (rc) return rc;
-      }
-  if (build_frames)
-    for (int i = 0; i < n; i++) {
-      jobs[i].cur->build_corners = jobs[i].want_corners != 0;
-      jobs[i].cur->build_mirror = mirror != 0;
-    }
-  SDVLB_CUDA_TRY(cudaEventRecord(c->track_done, c->stream));
-
-  PendingTrack& P = *c->pending;
-  P.active = true;
-  P.jobs = jobs; P.n = n; P.build_frames = build_frames;
-  P.trace = trace; P.trace_cap = trace_cap; P.trace_n = trace_n;
-  P.o_res = o_res; P.o_match = o_match; P.o_trace = o_trace; P.o_flag = o_flag;
-  return 0;
-}
-
-int collect_batch(sdvlb_ctx* c) {
-  if (!c->pending || !c->pending->active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
-  PendingTrack& P = *c->pending;
-  P.active = false;
-  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-  SDVLB_CUDA_TRY(cudaEventSynchronize(c->track_done));
-  Arena& out = c->out;
-  int32_t flag;
-  memcpy(&flag, out.h + P.o_flag, 4);
-  if (flag) {
-    cudaMemsetAsync(c->overflow_flag, 0, 4, c->stream);
-    return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in FAST selection");
-  }
-  const BatchOut* res = reinterpret_cast<const BatchOut*>(out.h + P.o_res);
-  const sdvlb_match* hm = reinterpret_cast<const sdvlb_match*>(out.h + P.o_match);
-  int mo = 0;
-  bool first_align = true;
-  for (int i = 0; i < P.n; i++) {
-    sdvlb_track_job& j = P.jobs[i];
-    // the tracking stream ran after this frame's build (same stream, or ordered by its `built` event)
-    if (P.build_frames) finalize_build(c, j.cur, j.cur->build_corners, j.cur->build_mirror);
-    else if (j.cur->build_pending) finalize_build(c, j.cur, j.cur->build_corners, j.cur->build_mirror);
-    if (j.ref) {
-      memcpy(j.T_cur, res[i].pose, sizeof(j.T_cur));
-      j.n_tracked = res[i].info[0] / (c->params.align_patch_size * c->params.align_patch_size);
-      j.gn_iters = res[i].info[1];
-      j.error = res[i].error;
-      if (first_align) {
-        if (P.trace_n) *P.trace_n = res[i].info[1];
-        if (P.trace) memcpy(P.trace, out.h + P.o_trace, size_t(std::min(res[i].info[1], P.trace_cap)) * sizeof(sdvlb_gn_iter));
-        first_align = false;
-      }
-    }
-    if (j.n_cands > 0) memcpy(j.matches, hm + mo, size_t(j.n_cands) * sizeof(sdvlb_match));
-    mo += j.n_cands;
-  }
-  return 0;
-}
-
-int run_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_iter* trace, int trace_cap,
-              int* trace_n, const sdvlb_gn_forced* forced, bool build_frames, int fast = 0) {
-  const int rc = submit_batch(c, jobs, n, mirror, trace, trace_cap, trace_n, forced, build_frames, fast);
-  if (rc) { if (c->pending) c->pending->active = false; return rc; }
-  return collect_batch(c);
-}
-
-int check_track_args(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, bool* build) {
-  if (!ctx || !jobs || n_jobs <= 0) return sdvlb_set_error(SDVLB_ERR_ARG, "bad batch");
-  if (w != ctx->w || h != ctx->h) return sdvlb_set_error(SDVLB_ERR_ARG, "image size differs from the context camera");
-  int with_image = 0;
-  for (int i = 0; i < n_jobs; i++) {
-    if (jobs[i].image) with_image++;
-    else if (!jobs[i].cur) return sdvlb_set_error(SDVLB_ERR_ARG, "job with neither an image nor a prebuilt frame");
-  }
-  if (with_image != 0 && with_image != n_jobs)
-    return sdvlb_set_error(SDVLB_ERR_ARG, "a batch must either build all its frames or use prebuilt frames only");
-  *build = with_image == n_jobs;
-  return 0;
-}
-
-}  // namespace
-
-extern "C" {
-
+// ---------------------------------------------------------------------------------------------- tracking batches
 int sdvlb_track_batch(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, int mirror) {
   bool build = false;
   const int rc = check_track_args(ctx, jobs, n_jobs, w, h, &build);
@@ -771,12 +792,12 @@ int sdvlb_track_submit(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w,
   int rc = check_track_args(ctx, jobs, n_jobs, w, h, &build);
   if (rc) return rc;
   rc = submit_batch(ctx, jobs, n_jobs, mirror, nullptr, 0, nullptr, nullptr, build);
-  if (rc && ctx->pending) ctx->pending->active = false;
+  if (rc) ctx->pending.active = false;
   return rc;
 }
 
 int sdvlb_track_poll(sdvlb_ctx* ctx) {
-  if (!ctx || !ctx->pending || !ctx->pending->active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
+  if (!ctx || !ctx->pending.active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
   const cudaError_t e = cudaEventQuery(ctx->track_done);
   if (e == cudaSuccess) return 1;
   if (e == cudaErrorNotReady) return 0;
@@ -788,57 +809,30 @@ int sdvlb_track_collect(sdvlb_ctx* ctx) {
   return collect_batch(ctx);
 }
 
+// ---------------------------------------------------------------------------------------------- frame batches
 int sdvlb_frames_submit(sdvlb_ctx* c, const uint8_t* const* images, int n, int images_on_device, int want_corners,
                         int nfeatures, sdvlb_frame** out) {
   if (!c || !images || !out || n <= 0) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  if (images_on_device < 0 || images_on_device > 2) return sdvlb_set_error(SDVLB_ERR_ARG, "bad image location");
+  for (int i = 0; i < n; i++)
+    if (!images[i]) return sdvlb_set_error(SDVLB_ERR_ARG, "null image");
   SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-  const size_t img_bytes = size_t(c->w) * c->h;
-  BuildSlot& slot = c->bslots[c->bslot_next];
-  c->bslot_next = (c->bslot_next + 1) % kBuildSlots;
-  if (slot.used) SDVLB_CUDA_TRY(cudaEventSynchronize(slot.done));   // its staging may still be read by the device
-  int rc = ensure_arena(&slot.a, size_t(n) * sizeof(FrameDev) + 512, true);
+  int rc = want_corners ? ensure_fast_scratch(c, n) : 0;
   if (rc) return rc;
-  if (want_corners) {
-    if (n > c->fast_frames) {   // growing the FAST scratch frees device memory: drain both streams first
-      SDVLB_CUDA_TRY(cudaStreamSynchronize(c->bstream));
-      SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    }
-    rc = ensure_fast_scratch(c, n);
-    if (rc) return rc;
-  }
   for (int i = 0; i < n; i++) {
     sdvlb_frame* f = nullptr;
     rc = frame_alloc(c, &f);
     if (rc) { for (int k = 0; k < i; k++) frame_release(c, out[k]); return rc; }
     out[i] = f;
-    reinterpret_cast<FrameDev*>(slot.a.h)[i] = f->dev;
   }
-  for (int i = 0; i < n; i++) {
-    if (!images[i]) return sdvlb_set_error(SDVLB_ERR_ARG, "null image");
-    SDVLB_CUDA_TRY(cudaMemcpyAsync(out[i]->dev.pyr, images[i], img_bytes,
-                                   images_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->bstream));
-    if (!images_on_device) c->h2d_bytes += int64_t(img_bytes);
-  }
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(slot.a.d, slot.a.h, size_t(n) * sizeof(FrameDev), cudaMemcpyHostToDevice, c->bstream));
-  c->h2d_bytes += int64_t(n) * sizeof(FrameDev);
-  const FrameDev* d = reinterpret_cast<const FrameDev*>(slot.a.d);
-  rc = enqueue_build_kernels(c, d, n, d, want_corners ? n : 0, nfeatures, c->bstream);
+  std::vector<int32_t> loc(n, images_on_device);
+  rc = enqueue_build(c, out, images, loc.data(), n, want_corners != 0, nfeatures, true, c->bstream);
   if (rc) return rc;
-  for (int i = 0; i < n; i++) {
-    sdvlb_frame* f = out[i];
-    if (want_corners) {
-      rc = enqueue_corner_mirror(c, f, c->bstream);
-      if (rc) return rc;
-    }
-    f->build_pending = true;
-    f->build_corners = want_corners != 0;
-    f->build_mirror = want_corners != 0;
-    SDVLB_CUDA_TRY(cudaEventRecord(f->built, c->bstream));
-  }
-  SDVLB_CUDA_TRY(cudaEventRecord(slot.done, c->bstream));
-  SDVLB_CUDA_TRY(cudaEventRecord(c->last_build, c->bstream));
-  slot.used = true;
-  c->build_in_flight = true;
+  cudaEvent_t ev = c->bevents[c->bevent_next];
+  c->bevent_next = (c->bevent_next + 1) % kBuildEvents;
+  SDVLB_CUDA_TRY(cudaEventRecord(ev, c->bstream));
+  for (int i = 0; i < n; i++) { out[i]->build_pending = true; out[i]->built = ev; }
+  c->last_build = ev;
   return 0;
 }
 
@@ -848,16 +842,10 @@ int sdvlb_frames_wait(sdvlb_ctx* c, sdvlb_frame* const* frames, int n) {
     const int rc = ensure_built(frames[i]);
     if (rc) return rc;
   }
-  int32_t flag = 0;
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(&flag, c->overflow_flag, 4, cudaMemcpyDeviceToHost, c->bstream));
-  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->bstream));
-  if (flag) {
-    cudaMemsetAsync(c->overflow_flag, 0, 4, c->bstream);
-    return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in FAST selection");
-  }
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- Frame
 int sdvlb_frame_create(sdvlb_ctx* ctx, const uint8_t* img, int w, int h, int stride, int want_corners, int nfeatures,
                        sdvlb_frame** out) {
   if (!ctx || !img || !out) return sdvlb_set_error(SDVLB_ERR_ARG, "null argument");
@@ -885,33 +873,29 @@ int sdvlb_frame_detect(sdvlb_ctx* ctx, sdvlb_frame* f, int nfeatures) {
   SDVLB_CUDA_TRY(cudaSetDevice(ctx->device));
   int rc = ensure_built(f);
   if (rc) return rc;
-  if (ctx->build_in_flight) SDVLB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->last_build, 0));
   rc = ensure_fast_scratch(ctx, 1);
   if (rc) return rc;
-  rc = ensure_arena(&ctx->in, 4096, true);
-  if (rc) return rc;
-  memcpy(ctx->in.h, &f->dev, sizeof(FrameDev));
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(ctx->in.d, ctx->in.h, sizeof(FrameDev), cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->last_build) SDVLB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->last_build, 0));   // shared FAST scratch
+  FrameBatch B;
+  B.n = 1;
+  B.scratch_base = 0;
+  B.f[0] = f->dev;
+  B.f[0].host_mirror = reinterpret_cast<int32_t*>(f->h_corners);
   const FastPlan* plan = get_plan(ctx, nfeatures);
-  const FrameDev* dfr = reinterpret_cast<const FrameDev*>(ctx->in.d);
   timer_begin(ctx, SDVLB_K_FAST);
-  SDVLB_CUDA_TRY(sdvlb_launch_fast_cells(dfr, 1, *plan, ctx->cell_kp, ctx->cell_cnt, ctx->stream));
+  SDVLB_CUDA_TRY(sdvlb_launch_fast_cells(B, *plan, ctx->cell_kp, ctx->cell_cnt, ctx->stream));
   timer_end(ctx);
   timer_begin(ctx, SDVLB_K_SELECT);
-  SDVLB_CUDA_TRY(sdvlb_launch_fast_select(dfr, 1, *plan, ctx->cell_kp, ctx->cell_cnt, ctx->level_kp, ctx->level_cnt,
-                                          ctx->frame_ticket, ctx->overflow_flag, ctx->stream));
+  SDVLB_CUDA_TRY(sdvlb_launch_fast_select(B, *plan, ctx->cell_kp, ctx->cell_cnt, ctx->level_kp, ctx->level_cnt,
+                                          ctx->frame_ticket, ctx->stream));
   timer_end(ctx);
   ctx->n_launches += 2;
-  int32_t flag = 0;
-  rc = enqueue_corner_mirror(ctx, f, ctx->stream);
-  if (rc) return rc;
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(&flag, ctx->overflow_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
   SDVLB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (flag) {
-    cudaMemsetAsync(ctx->overflow_flag, 0, 4, ctx->stream);
-    return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in FAST selection");
-  }
-  finalize_build(ctx, f, true, true);
+  rc = check_overflow(ctx);
+  if (rc) return rc;
+  f->build_corners = true;
+  f->build_mirror = true;
+  finalize_build(ctx, f);
   f->h_more.clear();
   return 0;
 }
@@ -940,15 +924,17 @@ int sdvlb_frame_corners(const sdvlb_frame* f, const int32_t** xyls, int* n) {
   if (!f) return sdvlb_set_error(SDVLB_ERR_ARG, "null frame");
   sdvlb_frame* mf = const_cast<sdvlb_frame*>(f);
   sdvlb_ctx* c = f->ctx;
-  int rc = ensure_built(mf);
+  const int rc = ensure_built(mf);
   if (rc) return rc;
   if (!f->has_corners) return sdvlb_set_error(SDVLB_ERR_STATE, "corners were not detected on this frame");
   if (mf->corners_mirrored < 0) {   // built without a mirror: fetch header + first block now
     SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-    rc = enqueue_corner_mirror(c, mf, c->stream);
-    if (rc) return rc;
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(mf->h_corners, mf->d_block + mf->off_hdr, 16 + size_t(c->corner_copy) * 16,
+                                   cudaMemcpyDeviceToHost, c->stream));
     SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    finalize_build(c, mf, true, true);
+    mf->build_corners = true;
+    mf->build_mirror = true;
+    finalize_build(c, mf);
   }
   const int32_t* src = reinterpret_cast<const int32_t*>(mf->h_corners + 16);
   if (mf->corners_mirrored < mf->n_corners) {   // longer than the eager mirror: fetch the whole list once
@@ -979,6 +965,7 @@ int sdvlb_frame_destroy(sdvlb_ctx* ctx, sdvlb_frame* f) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- ImageAlign / Matcher
 int sdvlb_image_align(sdvlb_ctx* ctx, const sdvlb_frame* ref, sdvlb_frame* cur, const sdvlb_align_feat* feats, int n,
                       const double T_ref[7], double T_cur[7], int fast, int* n_tracked, double* error,
                       sdvlb_gn_iter* trace, int trace_cap, int* trace_n, const sdvlb_gn_forced* forced) {

@@ -28,6 +28,22 @@ struct FrameDev {
   int4* corners;       // corners in the reference's order: (x, y, level, FAST score), level coordinates
   int32_t* n_corners;  // device counter; lives in the 16-byte header right before `corners` (one D2H mirrors both)
   double* pose;        // 7 doubles, world->camera, written by the ImageAlign kernel / uploaded by the host
+  int32_t* host_mirror;  // pinned, device-visible host copy of header + corners the selector writes directly
+                         // (16-byte header then int4 records), or nullptr
+  int32_t mirror_cap;    // corners the host mirror can hold
+  int32_t pad_;
+};
+
+// Frames of one build submission, passed to the build kernels BY VALUE (kernel parameter space), so a frame batch
+// needs no descriptor upload.
+#define SDVLB_BATCH_MAX 64
+struct FrameBatch {
+  int n;
+  int scratch_base;    // index of frame 0 of this batch in the FAST scratch arrays
+  FrameDev f[SDVLB_BATCH_MAX];
+};
+struct ImageBatch {    // level-0 sources of a frame batch (device-visible pinned host memory or device memory)
+  const uint8_t* src[SDVLB_BATCH_MAX];
 };
 
 struct DevParams {
@@ -85,6 +101,7 @@ struct FastArgs {
   int level_cap[SDVLB_MAX_LEVELS];   // capacity of the per-level scratch list
   int level_kp_off[SDVLB_MAX_LEVELS];
   int level_kp_total;
+  int32_t* overflow_flag;   // pinned, device-visible: set when a fixed capacity was exceeded
 };
 struct FastPlan {
   FastArgs args;

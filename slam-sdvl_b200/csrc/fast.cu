@@ -33,7 +33,7 @@ __constant__ int8_t c_ring[16][2] = {{0, 3},  {1, 3},   {2, 2},   {3, 1},   {3, 
 
 constexpr int TS = 36;  // shared tile row stride (bytes)
 
-__global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const FrameDev* __restrict__ frames,
+__global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_constant__ FrameBatch B,
                                                                  const __grid_constant__ FastArgs A,
                                                                  uint32_t* __restrict__ cell_kp,
                                                                  int32_t* __restrict__ cell_cnt) {
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const FrameDev*
   const int wc = A.g.wcells[level];
   const int ci = cell / wc, cj = cell - ci * wc;
   const int W = A.g.w[level], H = A.g.h[level];
-  const int out_idx = frame * A.g.total_cells + blockIdx.x;
+  const int out_idx = (B.scratch_base + frame) * A.g.total_cells + blockIdx.x;
 
   const int inity = max(A.margin, ci * SDVLB_CELL), maxy = min(H - A.margin, ci * SDVLB_CELL + SDVLB_CELL);
   const int initx = max(A.margin, cj * SDVLB_CELL), maxx = min(W - A.margin, cj * SDVLB_CELL + SDVLB_CELL);
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const FrameDev*
     if (tid == 0) cell_cnt[out_idx] = 0;
     return;
   }
-  const uint8_t* __restrict__ img = frames[frame].pyr + A.g.off[level];
+  const uint8_t* __restrict__ img = B.f[frame].pyr + A.g.off[level];
 
   // ---- stage ROI
   if (((initx & 3) == 0) && ((W & 3) == 0)) {
@@ -198,21 +198,20 @@ __device__ __forceinline__ T block_sum(T v, T* s_tmp) {   // all threads get the
   return r;
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const FrameDev* __restrict__ frames,
+__global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_constant__ FrameBatch B,
                                                                   const __grid_constant__ FastArgs A,
                                                                   uint32_t* __restrict__ cell_kp,
                                                                   const int32_t* __restrict__ cell_cnt,
                                                                   uint32_t* __restrict__ level_kp,
                                                                   int32_t* __restrict__ level_cnt,
-                                                                  int32_t* __restrict__ frame_ticket,
-                                                                  int32_t* __restrict__ overflow_flag) {
+                                                                  int32_t* __restrict__ frame_ticket) {
   extern __shared__ int s_dyn[];   // nleft[ncells], nsel[ncells], kept_off[ncells+1]
   __shared__ int s_tmp[SEL_THREADS / 32];
   __shared__ uint32_t s_keys[SEL_SMEM_KEYS];
   __shared__ int s_final, s_ticket;
 
   const int tid = threadIdx.x;
-  const int level = blockIdx.x, frame = blockIdx.y;
+  const int level = blockIdx.x, frame = B.scratch_base + blockIdx.y;   // `frame` indexes the scratch arrays
   const int ncells = A.g.wcells[level] * A.g.hcells[level];
   int* nleft = s_dyn;
   int* nsel = s_dyn + ncells;
@@ -284,7 +283,7 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const FrameDev
   uint32_t* __restrict__ lk = level_kp + size_t(frame) * A.level_kp_total + A.level_kp_off[level];
   const bool use_smem = total <= SEL_SMEM_KEYS;
   const bool fits = total <= A.level_cap[level];
-  if (!fits && tid == 0) atomicExch(overflow_flag, 1);
+  if (!fits && tid == 0) *reinterpret_cast<volatile int32_t*>(A.overflow_flag) = 1;
 
   // ---- gather to the level list (fast_detector.cc:141-142): key = score<<22 | y<<11 | x (level coordinates)
   const int wc = A.g.wcells[level];
@@ -323,23 +322,27 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const FrameDev
   __syncthreads();
   if (s_ticket != A.n_fast_levels - 1) return;
   __threadfence();
-  const FrameDev fr = frames[frame];
+  const FrameDev& fr = B.f[blockIdx.y];
+  int4* const mirror = reinterpret_cast<int4*>(fr.host_mirror);   // header at [0], records from [1]
   int base = 0;
   for (int l = 0; l < A.n_fast_levels; l++) {
     const int n = *reinterpret_cast<volatile int32_t*>(&level_cnt[frame * SDVLB_MAX_LEVELS + l]);
     const uint32_t* src = level_kp + size_t(frame) * A.level_kp_total + A.level_kp_off[l];
     if (base + n > A.corner_cap) {
-      if (tid == 0) atomicExch(overflow_flag, 1);
+      if (tid == 0) *reinterpret_cast<volatile int32_t*>(A.overflow_flag) = 1;
       break;
     }
     for (int i = tid; i < n; i += SEL_THREADS) {
       const uint32_t key = __ldcg(src + i);
-      fr.corners[base + i] = make_int4(int32_t(key & 2047), int32_t((key >> 11) & 2047), l, int32_t(key >> 22));
+      const int4 rec = make_int4(int32_t(key & 2047), int32_t((key >> 11) & 2047), l, int32_t(key >> 22));
+      fr.corners[base + i] = rec;
+      if (mirror && base + i < fr.mirror_cap) mirror[1 + base + i] = rec;
     }
     base += n;
   }
   if (tid == 0) {
     *fr.n_corners = base;
+    if (mirror) mirror[0] = make_int4(base, 0, 0, 0);
     frame_ticket[frame] = 0;
   }
 }
@@ -374,21 +377,20 @@ void sdvlb_fast_plan(const PyrGeom& g, const sdvlb_params& p, int nfeatures, int
   plan->nfeatures = nfeatures;
 }
 
-cudaError_t sdvlb_launch_fast_cells(const FrameDev* d_frames, int n_frames, const FastPlan& plan, uint32_t* cell_kp,
-                                    int32_t* cell_cnt, cudaStream_t stream) {
+cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
+                                    cudaStream_t stream) {
   const FastArgs& A = plan.args;
-  dim3 g1(A.g.total_cells, n_frames);
-  fast_cells_kernel<<<g1, DET_THREADS, 0, stream>>>(d_frames, A, cell_kp, cell_cnt);
+  dim3 g1(A.g.total_cells, B.n);
+  fast_cells_kernel<<<g1, DET_THREADS, 0, stream>>>(B, A, cell_kp, cell_cnt);
   return cudaGetLastError();
 }
 
-cudaError_t sdvlb_launch_fast_select(const FrameDev* d_frames, int n_frames, const FastPlan& plan, uint32_t* cell_kp,
-                                     int32_t* cell_cnt, uint32_t* level_kp, int32_t* level_cnt, int32_t* frame_ticket,
-                                     int32_t* overflow_flag, cudaStream_t stream) {
+cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
+                                     uint32_t* level_kp, int32_t* level_cnt, int32_t* frame_ticket,
+                                     cudaStream_t stream) {
   const FastArgs& A = plan.args;
-  dim3 g2(A.n_fast_levels, n_frames);
+  dim3 g2(A.n_fast_levels, B.n);
   const size_t dyn = size_t(3 * plan.max_cells_level + 1) * sizeof(int);
-  fast_select_kernel<<<g2, SEL_THREADS, dyn, stream>>>(d_frames, A, cell_kp, cell_cnt, level_kp, level_cnt,
-                                                       frame_ticket, overflow_flag);
+  fast_select_kernel<<<g2, SEL_THREADS, dyn, stream>>>(B, A, cell_kp, cell_cnt, level_kp, level_cnt, frame_ticket);
   return cudaGetLastError();
 }

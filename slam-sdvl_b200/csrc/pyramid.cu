@@ -23,14 +23,14 @@ __device__ __forceinline__ int reflect101(int t, int n) {
   return t;
 }
 
-__global__ void __launch_bounds__(THREADS) pyr_down_kernel(const FrameDev* __restrict__ frames, int src_off, int sw,
+__global__ void __launch_bounds__(THREADS) pyr_down_kernel(const __grid_constant__ FrameBatch B, int src_off, int sw,
                                                            int sh, int dst_off, int dw, int dh) {
   __shared__ __align__(16) uint8_t s_src[SROWS][SCOLS];
   __shared__ uint16_t s_h[SROWS][TW];
 
-  const FrameDev fr = frames[blockIdx.z];
-  const uint8_t* __restrict__ src = fr.pyr + src_off;
-  uint8_t* __restrict__ dst = fr.pyr + dst_off;
+  uint8_t* const pyr = B.f[blockIdx.z].pyr;
+  const uint8_t* __restrict__ src = pyr + src_off;
+  uint8_t* __restrict__ dst = pyr + dst_off;
   const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
   const int sx0 = 2 * tx0 - 4;          // source x of s_src[.][0]
   const int sy0 = 2 * ty0 - 2;          // source y of s_src[0][.]
@@ -90,14 +90,39 @@ __global__ void __launch_bounds__(THREADS) pyr_down_kernel(const FrameDev* __res
   }
 }
 
+// Level 0 of every frame of the batch from device-visible memory (pinned host memory read over PCIe, or device
+// memory): one launch instead of one cudaMemcpyAsync per frame.  16-byte accesses when both sides allow it.
+__global__ void __launch_bounds__(256) upload_kernel(const __grid_constant__ FrameBatch B,
+                                                     const __grid_constant__ ImageBatch I, int bytes) {
+  const uint8_t* __restrict__ src = I.src[blockIdx.y];
+  uint8_t* __restrict__ dst = B.f[blockIdx.y].pyr;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const int n16 = bytes >> 4;
+    const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src);
+    uint4* __restrict__ d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = tid; i < n16; i += nth) d4[i] = __ldcs(s4 + i);
+    for (int i = (n16 << 4) + tid; i < bytes; i += nth) dst[i] = src[i];
+  } else {
+    for (int i = tid; i < bytes; i += nth) dst[i] = src[i];
+  }
+}
+
 }  // namespace
 
-// Builds levels 1..L-1 for n frames (level 0 already resident). One launch per level.
-cudaError_t sdvlb_launch_pyramid(const FrameDev* d_frames, int n_frames, const PyrGeom& g, cudaStream_t stream) {
+cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, cudaStream_t stream) {
+  dim3 grid(24, B.n);
+  upload_kernel<<<grid, 256, 0, stream>>>(B, I, bytes);
+  return cudaGetLastError();
+}
+
+int sdvlb_pyramid_launches(const PyrGeom& g) { return g.levels - 1; }
+
+// Builds levels 1..L-1 for the frames of the batch (level 0 already resident). One launch per level.
+cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStream_t stream) {
   for (int l = 1; l < g.levels; l++) {
-    dim3 grid((g.w[l] + TW - 1) / TW, (g.h[l] + TH - 1) / TH, n_frames);
-    pyr_down_kernel<<<grid, THREADS, 0, stream>>>(d_frames, g.off[l - 1], g.w[l - 1], g.h[l - 1], g.off[l], g.w[l],
-                                                  g.h[l]);
+    dim3 grid((g.w[l] + TW - 1) / TW, (g.h[l] + TH - 1) / TH, B.n);
+    pyr_down_kernel<<<grid, THREADS, 0, stream>>>(B, g.off[l - 1], g.w[l - 1], g.h[l - 1], g.off[l], g.w[l], g.h[l]);
   }
   return cudaGetLastError();
 }

@@ -178,6 +178,9 @@ class Group {
     const int rc = sdvlb_ctx_create(device, &Config::Params(), &Config::CameraParams(), &ctx_);
     if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_create failed: ") + sdvlb_last_error());
     if (timing) sdvlb_timing_enable(ctx_, 1);
+    // current + prefetched + reference frame and a handful of live keyframes per sequence: no allocation while tracking
+    if (sdvlb_ctx_reserve_frames(ctx_, 16 * n_seq))
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_reserve_frames failed: ") + sdvlb_last_error());
     for (auto& s : seqs_) driver_.InitSequence(&s);
   }
   ~Group() {

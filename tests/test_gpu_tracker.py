@@ -82,16 +82,25 @@ def test_pipelined_run_equals_lockstep(binding, sw, n_groups, n_threads):
     assert np.array_equal(st_r, st_s)
 
 
-def test_async_frame_batches_match_sync_frames(binding, sw, O):
-    """sdvlb_frames_submit (build stream) produces the same pyramid bytes and corner list as sdvlb_frame_create."""
+@pytest.mark.parametrize("loc", [0, 1, 2])
+def test_async_frame_batches_match_sync_frames(binding, sw, O, loc):
+    """sdvlb_frames_submit (build stream; images in pageable host, device or pinned host memory) produces the same
+    pyramid bytes and corner list as sdvlb_frame_create."""
     import ctypes as C
+    import torch
     cfg, poses, imgs = sw.sequence("C2", 4, 3)
     ctx = binding.Context(cfg["params"], cfg["cam"])
     L = binding.load()
     n = len(imgs)
-    ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+    t = torch.from_numpy(np.ascontiguousarray(imgs))
+    if loc == 1:
+        t = t.cuda()
+    elif loc == 2:
+        t = t.pin_memory()
+    stride = imgs.shape[1] * imgs.shape[2]
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() + i * stride for i in range(n)])
     out = (C.c_void_p * n)()
-    rc = L.sdvlb_frames_submit(C.c_void_p(ctx.h), ptrs, n, 0, 1, cfg["params"].num_features, out)
+    rc = L.sdvlb_frames_submit(C.c_void_p(ctx.h), ptrs, n, loc, 1, cfg["params"].num_features, out)
     assert rc == 0, L.sdvlb_last_error()
     assert L.sdvlb_frames_wait(C.c_void_p(ctx.h), out, n) == 0
     for i in range(n):
