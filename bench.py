@@ -28,6 +28,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: see slam-sdvl_b200/binding.py
 IMG_HOST, IMG_DEVICE, IMG_PINNED = 0, 1, 2   # SDVLB_IMG_* (include/sdvl_b200.h)
 
 

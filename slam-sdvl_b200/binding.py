@@ -9,6 +9,10 @@ import numpy as np
 from . import abi
 from .abi import ptr
 
+# A tracker drives many short kernels from several stream pairs at once; with the default of 8 hardware work queues
+# unrelated streams share a queue and serialise behind each other.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdvl_b200.so")
 _LIB = None
@@ -273,9 +277,10 @@ class HostTracker:
 
     def phases(self, reset=True):
         """Thread-seconds in host marshalling / GPU submission+wait / host replay, summed over groups."""
-        a = (C.c_double * 3)()
+        a = (C.c_double * 8)()
         load_host().sdvlh_tracker_phases(C.c_void_p(self.h), a, int(reset))
-        return {"marshal_s": a[0], "gpu_submit_wait_s": a[1], "replay_s": a[2]}
+        return {"marshal_s": a[0], "gpu_submit_wait_s": a[1], "replay_s": a[2], "replay_apply_matches_s": a[3],
+                "replay_ransac_s": a[4], "replay_finish_frame_s": a[5], "gpu_wait_only_s": a[6], "idle_poll_s": a[7]}
 
     def ctx_handle(self):
         return load_host().sdvlh_tracker_ctx(C.c_void_p(self.h))

@@ -31,6 +31,7 @@ cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, const PyrGeom& g,
                                cudaStream_t stream);
 cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const FrameDev* d_frames, sdvlb_match* d_out,
                                 const PyrGeom& g, const DevParams& dp, cudaStream_t stream);
+cudaError_t sdvlb_launch_signal(uint32_t* h_flag, uint32_t seq, cudaStream_t stream);
 
 // ---- error reporting
 static thread_local std::string g_last_error;
@@ -110,8 +111,9 @@ struct sdvlb_ctx {
   cudaEvent_t bevents[kBuildEvents] = {};
   int bevent_next = 0;
   cudaEvent_t last_build = nullptr; // event of the most recent asynchronous build (null: none yet)
-  int32_t* h_overflow = nullptr;    // pinned, device-visible overflow flag written by the selector
-  cudaEvent_t track_done = nullptr;
+  int32_t* h_overflow = nullptr;    // pinned, device-visible: [0] overflow flag written by the selector,
+                                    // [16] sequence number of the last finished tracking submission (signal kernel)
+  uint32_t track_seq = 0;
   PendingTrack pending;
   sdvlb_params params{};
   sdvlb_camera cam{};
@@ -573,7 +575,9 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
     c->n_launches += 1;
   }
   c->d2h_bytes += int64_t(out.used);   // written over PCIe by the kernels themselves
-  SDVLB_CUDA_TRY(cudaEventRecord(c->track_done, c->stream));
+  c->track_seq++;
+  c->n_launches += 1;
+  SDVLB_CUDA_TRY(sdvlb_launch_signal(reinterpret_cast<uint32_t*>(c->h_overflow) + 16, c->track_seq, c->stream));
 
   PendingTrack& P = c->pending;
   P.active = true;
@@ -587,8 +591,22 @@ int collect_batch(sdvlb_ctx* c) {
   PendingTrack& P = c->pending;
   if (!P.active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
   P.active = false;
-  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-  SDVLB_CUDA_TRY(cudaEventSynchronize(c->track_done));
+  {   // spin on the pinned completion word; fall back to the driver now and then so that device errors surface
+    volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(c->h_overflow) + 16;
+    uint64_t spins = 0;
+    while (*done != c->track_seq) {
+      if ((++spins & 0xFFFFF) == 0) {
+        SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+        const cudaError_t e = cudaStreamQuery(c->stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return sdvlb_set_cuda_error(e, "cudaStreamQuery", __FILE__, __LINE__);
+        if (e == cudaSuccess && *done != c->track_seq)
+          return sdvlb_set_error(SDVLB_ERR_CUDA, "tracking stream drained without publishing its completion word");
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
   Arena& out = c->out;
   const int rc = check_overflow(c);
   if (rc) return rc;
@@ -683,11 +701,10 @@ int sdvlb_ctx_create(int device, const sdvlb_params* params, const sdvlb_camera*
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, prio_lo);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->track_done, cudaEventDisableTiming);
   for (int i = 0; i < kBuildEvents && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->bevents[i], cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_overflow), 64, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_overflow), 128, cudaHostAllocDefault);
   if (e != cudaSuccess) { delete c; return sdvlb_set_cuda_error(e, "context resources", __FILE__, __LINE__); }
-  memset(c->h_overflow, 0, 64);
+  memset(c->h_overflow, 0, 128);
   const FastPlan* plan = get_plan(c, p.num_features);
   c->level_kp_total = size_t(plan->args.level_kp_total);
   *out = c;
@@ -706,7 +723,6 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   for (uint8_t* slab : c->slabs) cudaFree(slab);
   for (uint8_t* slab : c->mirror_slabs) cudaFreeHost(slab);
   for (int i = 0; i < kBuildEvents; i++) if (c->bevents[i]) cudaEventDestroy(c->bevents[i]);
-  if (c->track_done) cudaEventDestroy(c->track_done);
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
   cudaFree(c->frame_ticket); cudaFree(c->scratch);
   if (c->h_overflow) cudaFreeHost(c->h_overflow);
@@ -798,10 +814,8 @@ int sdvlb_track_submit(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w,
 
 int sdvlb_track_poll(sdvlb_ctx* ctx) {
   if (!ctx || !ctx->pending.active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
-  const cudaError_t e = cudaEventQuery(ctx->track_done);
-  if (e == cudaSuccess) return 1;
-  if (e == cudaErrorNotReady) return 0;
-  return sdvlb_set_cuda_error(e, "cudaEventQuery", __FILE__, __LINE__);
+  const volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(ctx->h_overflow) + 16;
+  return *done == ctx->track_seq ? 1 : 0;   // a plain read of pinned memory: no driver call, no lock
 }
 
 int sdvlb_track_collect(sdvlb_ctx* ctx) {

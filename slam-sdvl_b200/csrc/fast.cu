@@ -2,10 +2,10 @@
 // FastDetector::DetectPyramid / SelectPixels (extra/fast_detector.cc:58-175), i.e. with cv::FAST(roi, thr, nms=true)
 // and cv::KeyPointsFilter::retainBest as SDVL calls them.
 //
-//  fast_cells_kernel : one CTA per (cell, frame). The cell's ROI [max(m,32i), min(rows-m,32i+32)) is staged in shared
+//  fast_cells_kernel : one warp per (cell, frame). The cell's ROI [max(m,32i), min(rows-m,32i+32)) is staged in shared
 //                      memory (cv::FAST never reads outside the ROI, so cells are independent and the outer 3 px of
-//                      every ROI never fire). Phase 1: 16-bit bright/dark ring masks, 9-contiguous test. Phase 2:
-//                      exact cornerScore for candidates only. Phase 3: strict 3x3 NMS, raster-ordered compaction.
+//                      every ROI never fire). One warp per cell: exact cornerScore of every tested pixel with 16-bit
+//                      SIMD min/max (two pixels per register), strict 3x3 NMS on the corners, raster-ordered output.
 //  fast_select_kernel: one CTA per (level, frame): water-filling quota (fast_detector.cc:114-135), per-cell
 //                      retainBest, level-wide retainBest, and — by the last CTA of a frame — concatenation of the
 //                      levels into Frame::corners_ order.
@@ -14,174 +14,201 @@
 
 namespace {
 
-constexpr int DET_THREADS = 128;
+constexpr int DET_WARPS = 4;          // one warp per 32x32 cell, no block-level synchronisation at all
+constexpr int DET_THREADS = DET_WARPS * 32;
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_SMEM_KEYS = 4096;   // level-wide retainBest runs in shared memory up to this many keypoints
+constexpr int TSE = 40;               // shared tile row stride in 16-bit elements
+constexpr int TSW = TSE / 2;          // ... in 32-bit words (one word = one horizontally adjacent pixel pair)
+constexpr int LIST_CAP = 26 * 26 + 28;
 
-__device__ __forceinline__ bool has9(uint32_t m) {  // 9 contiguous set bits in a circular 16-bit mask
-  uint32_t mm = m | (m << 16);
-  uint32_t x = mm & (mm >> 1);
-  x &= x >> 2;
-  x &= x >> 4;       // 8 contiguous
-  x &= mm >> 8;      // 9 contiguous
-  return (x & 0xFFFFu) != 0;
-}
+// upper half of a | lower half of b << 16: the pixel pair that starts one element to the right of word a
+__device__ __forceinline__ uint32_t mid_pair(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5432); }
 
-// ring offsets in OpenCV order (dx, dy)
-__constant__ int8_t c_ring[16][2] = {{0, 3},  {1, 3},   {2, 2},   {3, 1},   {3, 0},  {3, -1}, {2, -2}, {1, -3},
-                                     {0, -3}, {-1, -3}, {-2, -2}, {-3, -1}, {-3, 0}, {-3, 1}, {-2, 2}, {-1, 3}};
-
-constexpr int TS = 36;  // shared tile row stride (bytes)
-
+// FAST-9/16 on 32x32 cells, one WARP per cell.  Scoring is branch-free: every lane scores one horizontally adjacent
+// PIXEL PAIR held as two 16-bit lanes of a register (VIMNMX3.S16x2 / VIADD.16x2 are native on sm_100a):
+//   S1 = v - min over the 16 arcs of (max of the 9 arc pixels)      centre brighter than a whole arc
+//   S2 = (max over the 16 arcs of (min of the 9 arc pixels)) - v    centre darker than a whole arc
+//   corner <=> max(S1, S2) > threshold, score = max(S1, S2) - 1     == cv::FAST's cornerScore<16> for corners
+// arc minima/maxima come from 3-input min/max: x3[k] = op(r[k], r[k+1], r[k+2]), x9[k] = op(x3[k], x3[k+3], x3[k+6]).
+// The cell is staged in shared memory as 16-bit pixels at element x+1 (tested pixels start at x = 3, so pairs are
+// word-aligned).  Corners are appended to a raster-ordered list with warp ballots; the strict 3x3 NMS then only visits
+// listed corners and compacts the survivors, again in raster order (the order cv::FAST emits keypoints in).
 __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_constant__ FrameBatch B,
                                                                  const __grid_constant__ FastArgs A,
                                                                  uint32_t* __restrict__ cell_kp,
                                                                  int32_t* __restrict__ cell_cnt) {
-  __shared__ __align__(16) uint8_t tile[32 * TS];
-  __shared__ int16_t s_score[32 * 32];
-  __shared__ uint16_t s_cand[32 * 32];
-  __shared__ int s_ncand;
-  __shared__ int s_warp_cnt[DET_THREADS / 32];
-  __shared__ int s_base;
+  __shared__ __align__(16) uint32_t s_tile[DET_WARPS][32 * TSW];
+  __shared__ __align__(16) uint32_t s_score[DET_WARPS][32 * TSW];
+  __shared__ uint16_t s_list[DET_WARPS][LIST_CAP];
 
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int frame = blockIdx.y;
-  int cell = blockIdx.x;
+  const int gcell = blockIdx.x * DET_WARPS + warp;
+  if (gcell >= A.g.total_cells) return;
+  int cell = gcell;
   int level = 0;
   while (level + 1 < A.n_fast_levels && cell >= A.g.cell_off[level + 1]) level++;
   cell -= A.g.cell_off[level];
   const int wc = A.g.wcells[level];
   const int ci = cell / wc, cj = cell - ci * wc;
   const int W = A.g.w[level], H = A.g.h[level];
-  const int out_idx = (B.scratch_base + frame) * A.g.total_cells + blockIdx.x;
+  const int out_idx = (B.scratch_base + frame) * A.g.total_cells + gcell;
 
   const int inity = max(A.margin, ci * SDVLB_CELL), maxy = min(H - A.margin, ci * SDVLB_CELL + SDVLB_CELL);
   const int initx = max(A.margin, cj * SDVLB_CELL), maxx = min(W - A.margin, cj * SDVLB_CELL + SDVLB_CELL);
   if (maxy <= inity || maxx <= initx) {   // `continue` in the reference: cell neither empty nor populated
-    if (tid == 0) cell_cnt[out_idx] = -1;
+    if (lane == 0) cell_cnt[out_idx] = -1;
     return;
   }
   const int cols = maxx - initx, rows = maxy - inity;
   if (cols < 7 || rows < 7) {             // cv::FAST finds nothing in ROIs narrower than the ring
-    if (tid == 0) cell_cnt[out_idx] = 0;
+    if (lane == 0) cell_cnt[out_idx] = 0;
     return;
   }
   const uint8_t* __restrict__ img = B.f[frame].pyr + A.g.off[level];
+  uint32_t* const tile = s_tile[warp];
+  uint32_t* const score = s_score[warp];
+  uint16_t* const list = s_list[warp];
+  uint16_t* const tile16 = reinterpret_cast<uint16_t*>(tile);
 
-  // ---- stage ROI
+  // ---- stage the ROI as 16-bit pixels (element x + 1 of row y); scores start at zero
+#pragma unroll
+  for (int i = 0; i < (32 * TSW / 4) / 32; i++) reinterpret_cast<uint4*>(score)[i * 32 + lane] = make_uint4(0, 0, 0, 0);
   if (((initx & 3) == 0) && ((W & 3) == 0)) {
-    const int wpr = (cols + 3) >> 2;
-    for (int i = tid; i < rows * wpr; i += DET_THREADS) {
-      const int r = i / wpr, c = i - r * wpr;
-      const uint8_t* p = img + size_t(inity + r) * W + initx + 4 * c;
-      uint32_t v;
-      if (initx + 4 * c + 3 < W) v = __ldg(reinterpret_cast<const uint32_t*>(p));
-      else {
-        v = 0;
-        for (int k = 0; k < 4; k++)
-          if (initx + 4 * c + k < W) v |= uint32_t(__ldg(p + k)) << (8 * k);
+    const int wpr = (cols + 3) >> 2;                      // <= 8 words per row
+    const int lr = lane >> 3, c4 = (lane & 7) * 4;        // 4 rows x 8 words per pass
+    if (c4 < cols) {
+      const uint8_t* p0 = img + size_t(inity + lr) * W + initx + c4;
+      const bool whole = (initx + c4 + 3 < W);
+      for (int r0 = 0; r0 < rows; r0 += 16) {
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int r = r0 + 4 * k + lr;
+          v[k] = 0;
+          if (r < rows) {
+            const uint8_t* p = p0 + size_t(r0 + 4 * k) * W;
+            if (whole) v[k] = __ldg(reinterpret_cast<const uint32_t*>(p));
+            else
+              for (int b = 0; b < 4; b++)
+                if (initx + c4 + b < W) v[k] |= uint32_t(__ldg(p + b)) << (8 * b);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int r = r0 + 4 * k + lr;
+          if (r < rows) {
+            uint16_t* d = tile16 + r * TSE + c4 + 1;      // elements c4+1 .. c4+4: the middle two are word-aligned
+            d[0] = uint16_t(v[k] & 255u);
+            *reinterpret_cast<uint32_t*>(d + 1) = __byte_perm(v[k], 0, 0x4241);
+            d[3] = uint16_t(v[k] >> 24);
+          }
+        }
       }
-      *reinterpret_cast<uint32_t*>(&tile[r * TS + 4 * c]) = v;
     }
+    (void)wpr;
   } else {
-    for (int i = tid; i < rows * cols; i += DET_THREADS) {
+    for (int i = lane; i < rows * cols; i += 32) {
       const int r = i / cols, c = i - r * cols;
-      tile[r * TS + c] = __ldg(img + size_t(inity + r) * W + initx + c);
+      tile16[r * TSE + c + 1] = __ldg(img + size_t(inity + r) * W + initx + c);
     }
   }
-  for (int i = tid; i < 32 * 32; i += DET_THREADS) s_score[i] = 0;
-  if (tid == 0) s_ncand = 0;
-  __syncthreads();
+  __syncwarp();
 
-  // ---- phase 1: candidate test on the ROI interior
-  const int tw = cols - 6, th = rows - 6;
-  const int npix = tw * th;
-  int off[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) off[k] = c_ring[k][1] * TS + c_ring[k][0];
-  const int t = A.threshold;
-  for (int p = tid; p < npix; p += DET_THREADS) {
-    const int y = p / tw + 3, x = p - (p / tw) * tw + 3;
-    const uint8_t* c = &tile[y * TS + x];
-    const int v = c[0];
-    uint32_t bright = 0, dark = 0;
+  // ---- scores: task t = (q, p) is the pixel pair x = 3 + 2p, x + 1 of row y = 3 + q
+  const int np = (cols - 6 + 1) >> 1;     // pairs per row
+  const int nq = rows - 6;                // tested rows
+  const int ntask = np * nq;
+  const int dq = 32 / np, dp = 32 - dq * np;
+  const uint32_t t2 = uint32_t(A.threshold) * 0x00010001u;
+  const uint32_t lt = (1u << lane) - 1u;
+  int q = lane / np, p = lane - q * np;
+  int nlist = 0;
+  for (int t0 = 0; t0 < ntask; t0 += 32) {
+    const bool active = t0 + lane < ntask;
+    const int qq = active ? q : 0, pp = active ? p : 0;
+    const int y = 3 + qq, x = 3 + 2 * pp;
+    const int wi = y * TSW + 2 + pp;       // word holding elements (x + 1, x + 2)
+    const uint32_t* T = tile + wi;
+    uint32_t r[16];
+    {
+      const uint32_t a = T[3 * TSW - 1], b = T[3 * TSW], c = T[3 * TSW + 1];          // row +3: dx -1, 0, 1
+      r[15] = mid_pair(a, b); r[0] = b; r[1] = mid_pair(b, c);
+    }
+    r[14] = T[2 * TSW - 1]; r[2] = T[2 * TSW + 1];                                      // row +2: dx -2, 2
+    r[13] = mid_pair(T[TSW - 2], T[TSW - 1]); r[3] = mid_pair(T[TSW + 1], T[TSW + 2]);  // row +1: dx -3, 3
+    r[12] = mid_pair(T[-2], T[-1]); r[4] = mid_pair(T[1], T[2]);                        // row  0
+    r[11] = mid_pair(T[-TSW - 2], T[-TSW - 1]); r[5] = mid_pair(T[-TSW + 1], T[-TSW + 2]);   // row -1
+    r[10] = T[-2 * TSW - 1]; r[6] = T[-2 * TSW + 1];                                    // row -2
+    {
+      const uint32_t a = T[-3 * TSW - 1], b = T[-3 * TSW], c = T[-3 * TSW + 1];        // row -3: dx -1, 0, 1
+      r[9] = mid_pair(a, b); r[8] = b; r[7] = mid_pair(b, c);
+    }
+    const uint32_t v2 = T[0];
+    uint32_t lo3[16], hi3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-      const int r = c[off[k]];
-      bright |= uint32_t(r > v + t) << k;
-      dark |= uint32_t(r < v - t) << k;
+      lo3[k] = __vimin3_s16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+      hi3[k] = __vimax3_s16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
     }
-    if (has9(bright) || has9(dark)) {
-      const int slot = atomicAdd(&s_ncand, 1);
-      s_cand[slot] = uint16_t(y * 32 + x);
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 2: exact score for candidates (cornerScore<16>: max over arcs of min(d) / min(-d), minus 1)
-  const int ncand = s_ncand;
-  for (int i = tid; i < ncand; i += DET_THREADS) {
-    const int yx = s_cand[i];
-    const int y = yx >> 5, x = yx & 31;
-    const uint8_t* c = &tile[y * TS + x];
-    const int v = c[0];
-    int d[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = v - int(c[off[k]]);
-    int lo2[16], hi2[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
-    int lo4[16], hi4[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
-    int a0 = t, b0 = -t;   // a0 = max(thr, S+), b0 = min(-thr, -S-)
+    uint32_t lo9[16], hi9[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-      const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
-      const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-      a0 = max(a0, lo9);
-      b0 = min(b0, hi9);
+      lo9[k] = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+      hi9[k] = __vimax3_s16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
     }
-    const int score = max(a0, -b0) - 1;
-    s_score[yx] = int16_t(score);
+    uint32_t m = __vimax3_s16x2(lo9[0], lo9[1], lo9[2]);
+    uint32_t M = __vimin3_s16x2(hi9[0], hi9[1], hi9[2]);
+#pragma unroll
+    for (int k = 3; k < 15; k += 2) {
+      m = __vimax3_s16x2(m, lo9[k], lo9[k + 1]);
+      M = __vimin3_s16x2(M, hi9[k], hi9[k + 1]);
+    }
+    m = __vmaxs2(m, lo9[15]);
+    M = __vmins2(M, hi9[15]);
+    const uint32_t S = __vmaxs2(__vsub2(v2, M), __vsub2(m, v2));
+    uint32_t sc = __vsub2(S, 0x00010001u) & __vcmpgts2(S, t2);
+    if (x + 1 >= cols - 3) sc &= 0x0000FFFFu;   // second pixel of the pair is outside the tested columns
+    if (!active) sc = 0;
+    if (active) score[wi] = sc;
+    // raster-ordered list of corners (score > 0)
+    const bool c0 = (sc & 0xFFFFu) != 0, c1 = (sc >> 16) != 0;
+    const uint32_t b0 = __ballot_sync(0xffffffffu, c0), b1 = __ballot_sync(0xffffffffu, c1);
+    int pos = nlist + __popc(b0 & lt) + __popc(b1 & lt);
+    if (c0) list[pos++] = uint16_t((y << 5) | x);
+    if (c1) list[pos] = uint16_t((y << 5) | (x + 1));
+    nlist += __popc(b0) + __popc(b1);
+    q += dq; p += dp;
+    if (p >= np) { p -= np; q++; }
   }
-  __syncthreads();
+  __syncwarp();
 
-  // ---- phase 3: strict NMS against the 8 neighbours (non-corners are 0), raster-ordered compaction
+  // ---- strict NMS against the 8 neighbours (non-corners are 0) for listed corners, raster-ordered compaction
   uint32_t* __restrict__ out = cell_kp + size_t(out_idx) * SDVLB_CELL_CAP;
   const int ox = initx - cj * SDVLB_CELL, oy = inity - ci * SDVLB_CELL;   // ROI origin relative to the cell origin
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int p0 = 0; p0 < npix; p0 += DET_THREADS) {
-    const int p = p0 + tid;
+  const uint16_t* sc16 = reinterpret_cast<const uint16_t*>(score);
+  int nout = 0;
+  for (int i0 = 0; i0 < nlist; i0 += 32) {
+    const int i = i0 + lane;
     bool keep = false;
     int s = 0, x = 0, y = 0;
-    if (p < npix) {
-      y = p / tw + 3; x = p - (p / tw) * tw + 3;
-      const int16_t* c = &s_score[y * 32 + x];
+    if (i < nlist) {
+      const int yx = list[i];
+      y = yx >> 5; x = yx & 31;
+      const uint16_t* c = sc16 + y * TSE + x + 1;
       s = c[0];
-      keep = s > 0 && s >= t && s > c[-1] && s > c[1] && s > c[-33] && s > c[-32] && s > c[-31] && s > c[31] &&
-             s > c[32] && s > c[33];
+      keep = s > c[-1] && s > c[1] && s > c[-TSE - 1] && s > c[-TSE] && s > c[-TSE + 1] && s > c[TSE - 1] &&
+             s > c[TSE] && s > c[TSE + 1];
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    int base = s_base;
-    for (int w = 0; w < warp; w++) base += s_warp_cnt[w];
     if (keep) {
-      const int slot = base + __popc(bal & ((1u << lane) - 1));
+      const int slot = nout + __popc(bal & lt);
       if (slot < SDVLB_CELL_CAP) out[slot] = (uint32_t(s) << 10) | (uint32_t(y + oy) << 5) | uint32_t(x + ox);
     }
-    __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int w = 0; w < DET_THREADS / 32; w++) tot += s_warp_cnt[w];
-      s_base += tot;
-    }
-    __syncthreads();
+    nout += __popc(bal);
   }
-  if (tid == 0) cell_cnt[out_idx] = s_base;   // <= 169 by construction of NMS
+  if (lane == 0) cell_cnt[out_idx] = nout;   // <= 169 by construction of NMS
 }
 
 // ------------------------------------------------------------------------------------------------ selection
@@ -380,7 +407,7 @@ void sdvlb_fast_plan(const PyrGeom& g, const sdvlb_params& p, int nfeatures, int
 cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
                                     cudaStream_t stream) {
   const FastArgs& A = plan.args;
-  dim3 g1(A.g.total_cells, B.n);
+  dim3 g1((A.g.total_cells + DET_WARPS - 1) / DET_WARPS, B.n);
   fast_cells_kernel<<<g1, DET_THREADS, 0, stream>>>(B, A, cell_kp, cell_cnt);
   return cudaGetLastError();
 }

@@ -330,7 +330,20 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
   if (lane == 0) out[ci] = m;
 }
 
+// Completion signal of a tracking submission: the stream reaches this 1-thread kernel after ImageAlign and SearchPoint
+// have finished (their results are already in pinned host memory); it publishes the submission's sequence number in
+// pinned host memory, so the host can poll a plain memory word instead of calling into the CUDA driver.
+__global__ void signal_kernel(volatile uint32_t* flag, uint32_t seq) {
+  __threadfence_system();
+  *flag = seq;
+}
+
 }  // namespace
+
+cudaError_t sdvlb_launch_signal(uint32_t* h_flag, uint32_t seq, cudaStream_t stream) {
+  signal_kernel<<<1, 1, 0, stream>>>(h_flag, seq);
+  return cudaGetLastError();
+}
 
 cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const FrameDev* d_frames, sdvlb_match* d_out,
                                 const PyrGeom& g, const DevParams& dp, cudaStream_t stream) {

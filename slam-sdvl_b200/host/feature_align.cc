@@ -7,6 +7,7 @@
 // exits, same Promote/Unpromote/DeletePoint side effects, same rand() consumption.  RANSAC inlier selection and the
 // Tukey-weighted pose refinement stay on the host (tiny 6x6 fp64 problems), as in the reference.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <stdexcept>
 #include <string>
@@ -134,7 +135,9 @@ void FeatureAlign::ApplyMatches(const shared_ptr<Frame>& frame, const vector<sha
       }
     }
   }
+  const auto t0 = std::chrono::steady_clock::now();
   SelectInliers(frame, fs_found, &inliers_, &outliers_);   // :68
+  ransac_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 void FeatureAlign::Reproject(const shared_ptr<Frame>& frame, const shared_ptr<Frame>& last_frame,

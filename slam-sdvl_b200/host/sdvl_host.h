@@ -288,6 +288,7 @@ class FeatureAlign {
                     const sdvlb_match* matches);
   int GetInliers() const { return int(inliers_.size()); }
   int GetOutliers() const { return int(outliers_.size()); }
+  double ransac_seconds = 0;   // time spent in SelectInliers (host phase accounting)
  private:
   void SelectInliers(const std::shared_ptr<Frame>& frame, std::vector<std::shared_ptr<Feature>>& fs_found,
                      std::vector<std::shared_ptr<Feature>>* inliers, std::vector<std::shared_ptr<Feature>>* outliers);

@@ -217,8 +217,15 @@ class Group {
     phase_s_[1] += std::chrono::duration<double>(tC - tB).count();
     phase_s_[2] += std::chrono::duration<double>(tD - tC).count();
   }
-  const double* phase_seconds() const { return phase_s_; }
-  void reset_phases() { phase_s_[0] = phase_s_[1] = phase_s_[2] = 0; }
+  const double* phase_seconds() {
+    phase_s_[4] = 0;
+    for (auto& s : seqs_) phase_s_[4] += s.fa->ransac_seconds;
+    return phase_s_;
+  }
+  void reset_phases() {
+    for (double& v : phase_s_) v = 0;
+    for (auto& s : seqs_) s.fa->ransac_seconds = 0;
+  }
 
   // ---- pipelined run: frame batches are built one step ahead of the tracking they feed (sdvlb_frames_submit on the
   // context's build stream), tracking is submitted asynchronously and collected when the device is done, so a host
@@ -233,6 +240,7 @@ class Group {
     if (n_steps_ > 0) SubmitBuild(0, &built_);
   }
   bool RunDone() const { return step_ >= n_steps_; }
+  void AddIdle(double s) { phase_s_[7] += s; }
   bool InFlight() const { return in_flight_; }
 
   void SubmitStep() {   // build(step+1) then track(step)
@@ -276,6 +284,7 @@ class Group {
     step_++;
     const auto tC = std::chrono::steady_clock::now();
     phase_s_[1] += std::chrono::duration<double>(tB - tA).count();
+    phase_s_[6] += std::chrono::duration<double>(tB - tA).count();
     phase_s_[2] += std::chrono::duration<double>(tC - tB).count();
   }
 
@@ -309,14 +318,18 @@ class Group {
     sdvlb_track_job& j = jobs_[i];
     shared_ptr<Frame> frame = std::make_shared<Frame>(&cam_, ctx_, j.cur, s.frame_counter);
     const bool first = !s.last_frame;
+    const auto t0 = std::chrono::steady_clock::now();
     if (!first) {
       frame->SetPose(SE3(j.T_cur));
       st[0] = j.n_tracked;
       st[6] = j.gn_iters;
       s.fa->ApplyMatches(frame, s.cand_points, s.matches.data());
     }
+    const auto t1 = std::chrono::steady_clock::now();
     driver_.FinishFrame(&s, frame, gt_pose, first, st);
     frame->GetPose().ToArray(est);
+    phase_s_[3] += std::chrono::duration<double>(t1 - t0).count();
+    phase_s_[5] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
   }
   void SubmitBuild(int step, vector<sdvlb_frame*>* out) {
     const int n = size();
@@ -331,7 +344,10 @@ class Group {
   sdvlb_ctx* ctx_ = nullptr;
   vector<Sequence> seqs_;
   vector<sdvlb_track_job> jobs_;
-  double phase_s_[3] = {0, 0, 0};   // host marshal, GPU submission (incl. wait), host replay
+  // thread-seconds: [0] marshal (+ frame-batch submission), [1] tracking submission + wait, [2] host replay total,
+  // of which [3] FeatureAlign::ApplyMatches, [4] its RANSAC (SelectInliers), [5] FinishFrame (OptimizePose, motion
+  // model, keyframe seeding), [6] waiting only
+  double phase_s_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // pipelined run state
   const uint8_t* const* images_ = nullptr;
   int on_device_ = 0, n_steps_ = 0, stride_ = 0, step_ = 0;
@@ -407,10 +423,11 @@ class BatchTracker {
       *launches += a; *h2d += b; *d2h += c;
     }
   }
-  void Phases(double out[3], int reset) {   // summed over groups (thread-seconds)
-    out[0] = out[1] = out[2] = 0;
+  void Phases(double out[8], int reset) {   // summed over groups (thread-seconds)
+    for (int i = 0; i < 8; i++) out[i] = 0;
     for (auto& g : groups_) {
-      for (int i = 0; i < 3; i++) out[i] += g->phase_seconds()[i];
+      const double* ph = g->phase_seconds();
+      for (int i = 0; i < 8; i++) out[i] += ph[i];
       if (reset) g->reset_phases();
     }
   }
@@ -470,7 +487,11 @@ class BatchTracker {
             progressed = true;
           }
         }
-        if (!progressed) std::this_thread::yield();
+        if (!progressed) {   // everything in flight: nothing to do but wait (plain memory polls, no driver calls)
+          const auto t0 = std::chrono::steady_clock::now();
+          std::this_thread::yield();
+          groups_[mine[0]]->AddIdle(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        }
       }
     } catch (const std::exception& e) {
       std::unique_lock<std::mutex> lk(mu_);
@@ -573,8 +594,10 @@ int sdvlh_tracker_counters(void* t, int64_t* launches, int64_t* h2d, int64_t* d2
   return 0;
 }
 
-// Thread-seconds spent in: [0] host marshalling, [1] the batched GPU submission (launch + wait), [2] host replay.
-int sdvlh_tracker_phases(void* t, double out[3], int reset) {
+// Thread-seconds spent in: [0] host marshalling (+ frame-batch submission), [1] tracking submission + wait, [2] host
+// replay, of which [3] ApplyMatches, [4] its RANSAC, [5] FinishFrame; [6] blocked waiting for the device; [7] idle
+// polling (every group of the thread in flight).
+int sdvlh_tracker_phases(void* t, double out[8], int reset) {
   static_cast<sdvl::BatchTracker*>(t)->Phases(out, reset);
   return 0;
 }
