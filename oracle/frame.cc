@@ -16,25 +16,28 @@ static inline int Reflect101(int t, int n) {  // cv::BORDER_REFLECT_101
 }
 
 // cv::pyrDown for CV_8UC1 with dst = (cols/2, rows/2): separable [1 4 6 4 1], (sum + 128) >> 8.
+// Integer arithmetic, so the column pass can run first (contiguous, auto-vectorised) and the strided row pass second:
+// the result is bit-identical to OpenCV's rows-then-columns order.  Written to run at a speed comparable to OpenCV's
+// SIMD pyrDown, because this oracle is also the timed CPU baseline.
 void PyrDown(const Mat8& src, Mat8* dst) {
-  const int dw = src.cols / 2, dh = src.rows / 2;
+  const int sw = src.cols, sh = src.rows;
+  const int dw = sw / 2, dh = sh / 2;
   *dst = Mat8(dw, dh);
-  static const int k[5] = {1, 4, 6, 4, 1};
-  std::vector<int> row(size_t(5) * dw);
+  std::vector<uint16_t> col(size_t(sw) + 8);
+  uint16_t* v = col.data() + 4;   // v[-2 .. sw+1] addressable
   for (int y = 0; y < dh; y++) {
-    for (int i = 0; i < 5; i++) {
-      const uint8_t* s = src.ptr(Reflect101(2 * y + i - 2, src.rows));
-      for (int x = 0; x < dw; x++) {
-        int acc = 0;
-        for (int j = 0; j < 5; j++) acc += k[j] * s[Reflect101(2 * x + j - 2, src.cols)];
-        row[size_t(i) * dw + x] = acc;
-      }
-    }
+    const uint8_t* s0 = src.ptr(Reflect101(2 * y - 2, sh));
+    const uint8_t* s1 = src.ptr(Reflect101(2 * y - 1, sh));
+    const uint8_t* s2 = src.ptr(2 * y);
+    const uint8_t* s3 = src.ptr(Reflect101(2 * y + 1, sh));
+    const uint8_t* s4 = src.ptr(Reflect101(2 * y + 2, sh));
+    for (int x = 0; x < sw; x++) v[x] = uint16_t(s0[x] + 4 * s1[x] + 6 * s2[x] + 4 * s3[x] + s4[x]);
+    v[-1] = v[1]; v[-2] = v[2];                          // BORDER_REFLECT_101 in x
+    v[sw] = v[sw - 2]; v[sw + 1] = v[sw - 3];
     uint8_t* d = dst->data.data() + size_t(y) * dw;
     for (int x = 0; x < dw; x++) {
-      int acc = 0;
-      for (int i = 0; i < 5; i++) acc += k[i] * row[size_t(i) * dw + x];
-      d[x] = uint8_t((acc + 128) >> 8);
+      const uint16_t* c = v + 2 * x;
+      d[x] = uint8_t((c[-2] + 4 * c[-1] + 6 * c[0] + 4 * c[1] + c[2] + 128) >> 8);
     }
   }
 }
@@ -49,45 +52,83 @@ static inline int CornerScore16(const uint8_t* p, const int* off, int threshold)
   const int v = p[0];
   for (int k = 0; k < 25; k++) d[k] = v - p[off[k & 15]];
   int a0 = threshold;
-  for (int k = 0; k < 16; k++) {
-    int a = d[k];
-    for (int j = 1; j < 9; j++) a = std::min(a, d[k + j]);
-    a0 = std::max(a0, a);
+  for (int k = 0; k < 16; k += 2) {   // same pairing of arcs as OpenCV's scalar cornerScore<16>
+    int a = std::min(d[k + 1], d[k + 2]);
+    a = std::min(a, d[k + 3]);
+    if (a <= a0) continue;
+    a = std::min(a, d[k + 4]); a = std::min(a, d[k + 5]); a = std::min(a, d[k + 6]);
+    a = std::min(a, d[k + 7]); a = std::min(a, d[k + 8]);
+    a0 = std::max(a0, std::min(a, d[k]));
+    a0 = std::max(a0, std::min(a, d[k + 9]));
   }
   int b0 = -a0;
-  for (int k = 0; k < 16; k++) {
-    int b = d[k];
-    for (int j = 1; j < 9; j++) b = std::max(b, d[k + j]);
-    b0 = std::min(b0, b);
+  for (int k = 0; k < 16; k += 2) {
+    int b = std::max(d[k + 1], d[k + 2]);
+    b = std::max(b, d[k + 3]); b = std::max(b, d[k + 4]); b = std::max(b, d[k + 5]);
+    if (b >= b0) continue;
+    b = std::max(b, d[k + 6]); b = std::max(b, d[k + 7]); b = std::max(b, d[k + 8]);
+    b0 = std::min(b0, std::max(b, d[k]));
+    b0 = std::min(b0, std::max(b, d[k + 9]));
   }
   return -b0 - 1;
 }
 
+// cv::FAST(roi, threshold, nonmax = true), TYPE_9_16: the structure of OpenCV's FAST_t<16> (threshold table, early
+// rejection on opposite ring pixels, run-length test, score only for corners, 3-row NMS), so that its cost on the CPU
+// is representative of the library the reference calls.
 void FastRoi(const uint8_t* roi, int stride, int cols, int rows, int threshold, std::vector<KeyPoint>* out) {
   out->clear();
   if (cols < 7 || rows < 7) return;
   threshold = std::min(std::max(threshold, 0), 255);
-  int off[16];
+  int off[25];
   for (int k = 0; k < 16; k++) off[k] = kRing[k][0] + kRing[k][1] * stride;
-  std::vector<int> score(size_t(cols) * rows, 0);
+  for (int k = 16; k < 25; k++) off[k] = off[k - 16];
+  uint8_t tab[512];   // tab[d + 255]: 1 = ring pixel darker than centre - t, 2 = brighter than centre + t
+  for (int i = -255; i <= 255; i++) tab[i + 255] = uint8_t(i < -threshold ? 1 : i > threshold ? 2 : 0);
+  std::vector<uint8_t> score(size_t(cols) * rows, 0);   // corner scores fit a byte (<= 254); 0 = no corner
   for (int y = 3; y < rows - 3; y++) {
     const uint8_t* p = roi + size_t(y) * stride;
+    uint8_t* srow = &score[size_t(y) * cols];
     for (int x = 3; x < cols - 3; x++) {
-      const int s = CornerScore16(p + x, off, threshold);
-      // a pixel is a corner iff some 9-arc is entirely brighter/darker than +-threshold,
-      // i.e. iff the un-clamped arc score exceeds the threshold: score = S-1 >= threshold
-      if (s >= threshold) score[size_t(y) * cols + x] = s;
-      else score[size_t(y) * cols + x] = 0;
+      const uint8_t* c = p + x;
+      const uint8_t* t = tab + 255 - int(c[0]);   // t[ring] classifies ring - centre
+      int d = t[c[off[0]]] | t[c[off[8]]];
+      if (d == 0) continue;
+      d &= t[c[off[2]]] | t[c[off[10]]];
+      d &= t[c[off[4]]] | t[c[off[12]]];
+      d &= t[c[off[6]]] | t[c[off[14]]];
+      if (d == 0) continue;
+      d &= t[c[off[1]]] | t[c[off[9]]];
+      d &= t[c[off[3]]] | t[c[off[11]]];
+      d &= t[c[off[5]]] | t[c[off[13]]];
+      d &= t[c[off[7]]] | t[c[off[15]]];
+      bool corner = false;
+      if (d & 1) {
+        const int vt = int(c[0]) - threshold;
+        int count = 0;
+        for (int k = 0; k < 25; k++) {
+          if (int(c[off[k]]) < vt) { if (++count > 8) { corner = true; break; } }
+          else count = 0;
+        }
+      }
+      if (!corner && (d & 2)) {
+        const int vt = int(c[0]) + threshold;
+        int count = 0;
+        for (int k = 0; k < 25; k++) {
+          if (int(c[off[k]]) > vt) { if (++count > 8) { corner = true; break; } }
+          else count = 0;
+        }
+      }
+      if (corner) srow[x] = uint8_t(CornerScore16(c, off, threshold));
     }
   }
-  // A corner needs S > threshold; CornerScore16 returns max(threshold, S) - 1, so S > threshold <=> s >= threshold
-  // except S == threshold... handled: S == threshold gives s = threshold-1 < threshold.
+  // keep a corner iff its score is strictly greater than its 8 neighbours' (non-corners count as 0); raster order
   for (int y = 3; y < rows - 3; y++) {
+    const uint8_t* c0 = &score[size_t(y) * cols];
     for (int x = 3; x < cols - 3; x++) {
-      const int s = score[size_t(y) * cols + x];
-      if (s == 0 && threshold > 0) continue;
-      if (s < threshold) continue;
-      const int* c = &score[size_t(y) * cols + x];
+      const int s = c0[x];
+      if (s == 0 || s < threshold) continue;
+      const uint8_t* c = c0 + x;
       if (s > c[-1] && s > c[1] && s > c[-cols - 1] && s > c[-cols] && s > c[-cols + 1] && s > c[cols - 1] &&
           s > c[cols] && s > c[cols + 1]) {
         KeyPoint kp;

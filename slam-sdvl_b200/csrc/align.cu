@@ -237,16 +237,28 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
 
       // ---- Optimize step on thread 0 (image_align.cc:91-124)
       if (tid == 0) {
-        double H[36], b[6], x[6];
-        int k = 0;
-        for (int r = 0; r < 6; r++)
-          for (int q = r; q < 6; q++) { H[r * 6 + q] = s_red[k]; H[q * 6 + r] = s_red[k]; k++; }
+        double Hm[6][6], b[6], x[6];
+        {
+          int k = 0;
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int q = r; q < 6; q++) { Hm[r][q] = s_red[k]; Hm[q][r] = s_red[k]; k++; }
+        }
+#pragma unroll
         for (int r = 0; r < 6; r++) b[r] = s_red[21 + r];
         const int nm = int(s_red[28]);
         n_meas_last = nm;
         const double new_chi2 = double(float(s_red[27]) / float(nm));   // float / size_t -> float (image_align.cc:205)
         if (nm == 0) stop_ = true;
-        ldlt_solve6(H, b, x);
+        // H.ldlt().solve(Jres) (image_align.cc:102): register-only LDL^T when H is safely positive definite (the normal
+        // case), Eigen's pivoted algorithm otherwise (singular / empty systems, NaN propagation)
+        if (!ldlt_solve6_spd(Hm, b, x)) {
+          double H[36];
+          for (int r = 0; r < 6; r++)
+            for (int q = 0; q < 6; q++) H[r * 6 + q] = Hm[r][q];
+          ldlt_solve6(H, b, x);
+        }
         bool nan = false;
         if (isnan(x[0])) { stop_ = true; nan = true; }
         int flags = (nan ? 2 : 0) | (nm == 0 ? 4 : 0);
@@ -273,7 +285,8 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
           sdvlb_gn_iter& rec = J.trace[trace_n];
           rec.level = level; rec.iter = it; rec.n_meas = nm; rec.flags = flags;
           for (int i = 0; i < 7; i++) rec.T_in[i] = s_T[i];
-          for (int i = 0; i < 36; i++) rec.H[i] = H[i];
+          for (int r = 0; r < 6; r++)
+            for (int q = 0; q < 6; q++) rec.H[r * 6 + q] = Hm[r][q];
           for (int i = 0; i < 6; i++) { rec.b[i] = b[i]; rec.x[i] = x[i]; }
           rec.chi2 = new_chi2;
         }

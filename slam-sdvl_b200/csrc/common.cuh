@@ -6,6 +6,12 @@
 
 #include "../../include/sdvl_b200.h"
 
+#if defined(__CUDACC__)
+#define SDVLB_UNROLL _Pragma("unroll")
+#else
+#define SDVLB_UNROLL _Pragma("GCC unroll 8")
+#endif
+
 #define SDVLB_MAX_LEVELS 8
 #define SDVLB_CELL 32
 #define SDVLB_CELL_CAP 176          // > 13*13: upper bound of NMS survivors in a 26x26 tested area
@@ -182,7 +188,8 @@ __host__ __device__ inline DSE3 se3_mul(const DSE3& a, const DSE3& b) {
   return r;
 }
 
-// SE3::Exp (extra/se3.cc:72-94,114-130); u = [upsilon; omega]
+// SE3::Exp (extra/se3.cc:72-94,114-130); u = [upsilon; omega].  Loop-free: V = I + a*Om + b*Om*Om with the products of
+// the skew matrix written out (the same sums the reference's 3x3 product forms).
 __host__ __device__ inline DSE3 se3_exp(const double u[6]) {
   const double SMALL_EPS = 1e-10;
   const double ox = u[3], oy = u[4], oz = u[5];
@@ -203,21 +210,68 @@ __host__ __device__ inline DSE3 se3_exp(const double u[6]) {
   if (theta < SMALL_EPS) {
     se3_rot(r, V);
   } else {
-    const double Om[9] = {0, -oz, oy, oz, 0, -ox, -oy, ox, 0};
-    double Om2[9];
-    for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) {
-        double s = 0;
-        for (int k = 0; k < 3; k++) s += Om[i * 3 + k] * Om[k * 3 + j];
-        Om2[i * 3 + j] = s;
-      }
     const double theta_sq = theta * theta;
     const double a = (1 - cos(theta)) / theta_sq;
     const double b = (theta - sin(theta)) / (theta_sq * theta);
-    for (int i = 0; i < 9; i++) V[i] = ((i == 0 || i == 4 || i == 8) ? 1.0 : 0.0) + a * Om[i] + b * Om2[i];
+    // Om = [0 -oz oy; oz 0 -ox; -oy ox 0], Om2 = Om * Om
+    const double m00 = -(oz * oz) - oy * oy, m01 = oy * ox, m02 = oz * ox;
+    const double m11 = -(oz * oz) - ox * ox, m12 = oz * oy;
+    const double m22 = -(oy * oy) - ox * ox;
+    V[0] = 1.0 + b * m00;          V[1] = a * -oz + b * m01;      V[2] = a * oy + b * m02;
+    V[3] = a * oz + b * m01;       V[4] = 1.0 + b * m11;          V[5] = a * -ox + b * m12;
+    V[6] = a * -oy + b * m02;      V[7] = a * ox + b * m12;       V[8] = 1.0 + b * m22;
   }
   mat3_mul_vec(V, u[0], u[1], u[2], r.tx, r.ty, r.tz);
   return r;
+}
+
+// Unpivoted LDL^T solve of a symmetric positive definite 6x6 system held entirely in registers (every loop has a
+// compile-time trip count).  Returns false -- leaving x untouched -- when a pivot is not safely positive; the caller
+// then uses ldlt_solve6 below, which reproduces Eigen's pivoted LDLT including its handling of singular systems.  For a
+// well-conditioned SPD matrix the two differ only in rounding (~1e-15 relative).
+__host__ __device__ inline bool ldlt_solve6_spd(const double A[6][6], const double b[6], double x[6]) {
+  double L[6][6], D[6], W[6][6];
+  double dmax = 0.0;
+SDVLB_UNROLL
+  for (int i = 0; i < 6; i++) dmax = fmax(dmax, A[i][i]);
+  const double tiny = dmax * 1e-13;
+  bool ok = dmax > 0.0;
+SDVLB_UNROLL
+  for (int k = 0; k < 6; k++) {
+    double d = A[k][k];
+SDVLB_UNROLL
+    for (int j = 0; j < k; j++) d -= L[k][j] * W[k][j];
+    D[k] = d;
+    ok = ok && (d > tiny);
+    const double inv = 1.0 / d;
+SDVLB_UNROLL
+    for (int i = k + 1; i < 6; i++) {
+      double s = A[i][k];
+SDVLB_UNROLL
+      for (int j = 0; j < k; j++) s -= L[i][j] * W[k][j];
+      W[i][k] = s;           // L[i][k] * D[k]
+      L[i][k] = s * inv;
+    }
+  }
+  if (!ok) return false;
+  double y[6];
+SDVLB_UNROLL
+  for (int i = 0; i < 6; i++) {
+    double s = b[i];
+SDVLB_UNROLL
+    for (int j = 0; j < i; j++) s -= L[i][j] * y[j];
+    y[i] = s;
+  }
+SDVLB_UNROLL
+  for (int i = 0; i < 6; i++) y[i] = y[i] / D[i];
+SDVLB_UNROLL
+  for (int i = 5; i >= 0; i--) {
+    double s = y[i];
+SDVLB_UNROLL
+    for (int j = i + 1; j < 6; j++) s -= L[j][i] * x[j];
+    x[i] = s;
+  }
+  return true;
 }
 
 // Eigen LDLT<Matrix6d>::solve (image_align.cc:102): diagonal-pivoted LDL^T, pseudo-inverse of D.
