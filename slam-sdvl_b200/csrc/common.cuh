@@ -6,7 +6,7 @@
 
 #include "../../include/sdvl_b200.h"
 
-#if defined(__CUDACC__)
+#if defined(__CUDA_ARCH__)
 #define SDVLB_UNROLL _Pragma("unroll")
 #else
 #define SDVLB_UNROLL _Pragma("GCC unroll 8")
