@@ -8,6 +8,8 @@
 
 #if defined(__CUDA_ARCH__)
 #define SDVLB_UNROLL _Pragma("unroll")
+#elif defined(__CUDACC__)
+#define SDVLB_UNROLL
 #else
 #define SDVLB_UNROLL _Pragma("GCC unroll 8")
 #endif
