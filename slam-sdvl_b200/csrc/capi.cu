@@ -203,6 +203,8 @@ int grow_pool(sdvlb_ctx* c) {
   size_t off = align_up(size_t(c->geom.total) + 256, 256);
   const size_t off_hdr = off;   off = align_up(off + 16 + size_t(c->corner_cap) * sizeof(int4), 256);
   const size_t off_pose = off;  off = align_up(off + 7 * sizeof(double), 256);
+  const size_t gcells = size_t(c->geom.wcells[0]) * c->geom.hcells[0];
+  const size_t off_grid = off;  off = align_up(off + (2 * gcells + 1 + size_t(c->corner_cap)) * sizeof(int32_t), 256);
   c->block_bytes = off;
   uint8_t* slab = nullptr;
   uint8_t* mslab = nullptr;
@@ -220,6 +222,7 @@ int grow_pool(sdvlb_ctx* c) {
     f->dev.n_corners = reinterpret_cast<int32_t*>(f->d_block + off_hdr);
     f->dev.corners = reinterpret_cast<int4*>(f->d_block + off_hdr + 16);
     f->dev.pose = reinterpret_cast<double*>(f->d_block + off_pose);
+    f->dev.grid = reinterpret_cast<int32_t*>(f->d_block + off_grid);
     f->dev.host_mirror = nullptr;
     f->dev.mirror_cap = c->corner_copy;
     c->pool.push_back(f);

@@ -40,6 +40,9 @@ struct FrameDev {
                          // (16-byte header then int4 records), or nullptr
   int32_t mirror_cap;    // corners the host mirror can hold
   int32_t pad_;
+  // Spatial index of the corners for Matcher::GetCornersInRange: 32-px cells of the level-0 image (the level-0 FAST
+  // grid), corners binned by their level-0 position.  Layout: start[cells + 1], cursor[cells], item[corner_cap].
+  int32_t* grid;
 };
 
 // Frames of one build submission, passed to the build kernels BY VALUE (kernel parameter space), so a frame batch

@@ -18,8 +18,12 @@ constexpr int DET_WARPS = 4;          // one warp per 32x32 cell, no block-level
 constexpr int DET_THREADS = DET_WARPS * 32;
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_SMEM_KEYS = 4096;   // level-wide retainBest runs in shared memory up to this many keypoints
-constexpr int TSE = 40;               // shared tile row stride in 16-bit elements
+constexpr int TSE = 40;               // score tile row stride in 16-bit elements
 constexpr int TSW = TSE / 2;          // ... in 32-bit words (one word = one horizontally adjacent pixel pair)
+// Pixel tile row stride in words: 45 = 13 (mod 32), so the 13 + 13 + 6 pairs of three consecutive tile rows that one warp
+// pass of a full cell touches fall into 32 distinct banks (a stride of 20 makes 6 of them collide).
+constexpr int PSW = 45;
+constexpr int PSE = 2 * PSW;
 constexpr int LIST_CAP = 26 * 26 + 28;
 
 // upper half of a | lower half of b << 16: the pixel pair that starts one element to the right of word a
@@ -38,7 +42,7 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
                                                                  const __grid_constant__ FastArgs A,
                                                                  uint32_t* __restrict__ cell_kp,
                                                                  int32_t* __restrict__ cell_cnt) {
-  __shared__ __align__(16) uint32_t s_tile[DET_WARPS][32 * TSW];
+  __shared__ __align__(16) uint32_t s_tile[DET_WARPS][32 * PSW];
   __shared__ __align__(16) uint32_t s_score[DET_WARPS][32 * TSW];
   __shared__ uint16_t s_list[DET_WARPS][LIST_CAP];
 
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
         for (int k = 0; k < 4; k++) {
           const int r = r0 + 4 * k + lr;
           if (r < rows) {
-            uint16_t* d = tile16 + r * TSE + c4 + 1;      // elements c4+1 .. c4+4: the middle two are word-aligned
+            uint16_t* d = tile16 + r * PSE + c4 + 1;      // elements c4+1 .. c4+4: the middle two are word-aligned
             d[0] = uint16_t(v[k] & 255u);
             *reinterpret_cast<uint32_t*>(d + 1) = __byte_perm(v[k], 0, 0x4241);
             d[3] = uint16_t(v[k] >> 24);
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
   } else {
     for (int i = lane; i < rows * cols; i += 32) {
       const int r = i / cols, c = i - r * cols;
-      tile16[r * TSE + c + 1] = __ldg(img + size_t(inity + r) * W + initx + c);
+      tile16[r * PSE + c + 1] = __ldg(img + size_t(inity + r) * W + initx + c);
     }
   }
   __syncwarp();
@@ -129,20 +133,20 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
     const bool active = t0 + lane < ntask;
     const int qq = active ? q : 0, pp = active ? p : 0;
     const int y = 3 + qq, x = 3 + 2 * pp;
-    const int wi = y * TSW + 2 + pp;       // word holding elements (x + 1, x + 2)
-    const uint32_t* T = tile + wi;
+    const int wi = y * TSW + 2 + pp;       // score word of the pair (elements x + 1, x + 2)
+    const uint32_t* T = tile + y * PSW + 2 + pp;
     uint32_t r[16];
     {
-      const uint32_t a = T[3 * TSW - 1], b = T[3 * TSW], c = T[3 * TSW + 1];          // row +3: dx -1, 0, 1
+      const uint32_t a = T[3 * PSW - 1], b = T[3 * PSW], c = T[3 * PSW + 1];          // row +3: dx -1, 0, 1
       r[15] = mid_pair(a, b); r[0] = b; r[1] = mid_pair(b, c);
     }
-    r[14] = T[2 * TSW - 1]; r[2] = T[2 * TSW + 1];                                      // row +2: dx -2, 2
-    r[13] = mid_pair(T[TSW - 2], T[TSW - 1]); r[3] = mid_pair(T[TSW + 1], T[TSW + 2]);  // row +1: dx -3, 3
+    r[14] = T[2 * PSW - 1]; r[2] = T[2 * PSW + 1];                                      // row +2: dx -2, 2
+    r[13] = mid_pair(T[PSW - 2], T[PSW - 1]); r[3] = mid_pair(T[PSW + 1], T[PSW + 2]);  // row +1: dx -3, 3
     r[12] = mid_pair(T[-2], T[-1]); r[4] = mid_pair(T[1], T[2]);                        // row  0
-    r[11] = mid_pair(T[-TSW - 2], T[-TSW - 1]); r[5] = mid_pair(T[-TSW + 1], T[-TSW + 2]);   // row -1
-    r[10] = T[-2 * TSW - 1]; r[6] = T[-2 * TSW + 1];                                    // row -2
+    r[11] = mid_pair(T[-PSW - 2], T[-PSW - 1]); r[5] = mid_pair(T[-PSW + 1], T[-PSW + 2]);   // row -1
+    r[10] = T[-2 * PSW - 1]; r[6] = T[-2 * PSW + 1];                                    // row -2
     {
-      const uint32_t a = T[-3 * TSW - 1], b = T[-3 * TSW], c = T[-3 * TSW + 1];        // row -3: dx -1, 0, 1
+      const uint32_t a = T[-3 * PSW - 1], b = T[-3 * PSW], c = T[-3 * PSW + 1];        // row -3: dx -1, 0, 1
       r[9] = mid_pair(a, b); r[8] = b; r[7] = mid_pair(b, c);
     }
     const uint32_t v2 = T[0];
@@ -371,6 +375,48 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
     *fr.n_corners = base;
     if (mirror) mirror[0] = make_int4(base, 0, 0, 0);
     frame_ticket[frame] = 0;
+  }
+
+  // ---- spatial index for the matcher: counting sort of the corner indices by 32-px cell of their level-0 position
+  const int gw = A.g.wcells[0], gcells = gw * A.g.hcells[0];
+  int32_t* const start = fr.grid;
+  int32_t* const cursor = fr.grid + gcells + 1;
+  int32_t* const item = cursor + gcells;
+  for (int i = tid; i < gcells; i += SEL_THREADS) cursor[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < base; i += SEL_THREADS) {
+    const int4 c = fr.corners[i];
+    atomicAdd(&cursor[((c.y << c.z) >> 5) * gw + ((c.x << c.z) >> 5)], 1);
+  }
+  __syncthreads();
+  {   // exclusive scan of the counts (block-wide, contiguous chunk per thread)
+    const int per = (gcells + SEL_THREADS - 1) / SEL_THREADS;
+    const int c0 = min(gcells, tid * per), c1 = min(gcells, c0 + per);
+    int local = 0;
+    for (int c = c0; c < c1; c++) local += cursor[c];
+    const int lane = tid & 31, warp = tid >> 5;
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_tmp[warp] = incl;
+    __syncthreads();
+    int run = incl - local;
+    for (int w = 0; w < warp; w++) run += s_tmp[w];
+    for (int c = c0; c < c1; c++) {
+      const int n = cursor[c];
+      start[c] = run;
+      cursor[c] = run;
+      run += n;
+    }
+    if (tid == SEL_THREADS - 1) start[gcells] = run;
+  }
+  __syncthreads();
+  for (int i = tid; i < base; i += SEL_THREADS) {
+    const int4 c = fr.corners[i];
+    item[atomicAdd(&cursor[((c.y << c.z) >> 5) * gw + ((c.x << c.z) >> 5)], 1)] = i;
   }
 }
 

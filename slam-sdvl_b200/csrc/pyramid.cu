@@ -2,20 +2,24 @@
 // Frame::CreatePyramid (frame.cc:114-120): dst(y,x) = (sum_{i,j} k_i k_j src(r(2y+i-2), r(2x+j-2)) + 128) >> 8,
 // k = [1 4 6 4 1], r = BORDER_REFLECT_101, dst size = (cols/2, rows/2).  Pure integer arithmetic.
 //
-// One launch per destination level, batched over frames (grid.z).  A CTA produces a 64x16 tile: it stages the
-// (2*64+8) x (2*16+3) source window in shared memory with aligned 32-bit loads (byte loads at borders / unaligned
-// rows), filters rows into a u16 buffer, then columns, and stores packed 32-bit words.
+// The 25-tap sum is evaluated with the 4-way byte dot product (IDP.4A): for a source row r with vertical weight k_r and
+// three consecutive aligned source words w0 w1 w2 (w1 starting at column 2x, x even),
+//   dst(x)   += dp4a(w0, k_r*(0,0,1,4)) + dp4a(w1, k_r*(6,4,1,0))
+//   dst(x+1) += dp4a(w1, k_r*(1,4,6,4)) + dp4a(w2, k_r*(1,0,0,0))
+// i.e. 10 instructions per output pixel and no byte unpacking (all weights k_r*k_j <= 36 fit a byte).
+//
+//   upload_kernel   : level 0 of a whole frame batch from device-visible memory (pinned host memory over PCIe, or
+//                     device memory) in one launch.
+//   pyr_down_kernel : one level -> next level for a frame batch, 8 outputs per thread straight from global memory
+//                     (the 5 source rows of neighbouring outputs overlap in L1).
+//   pyr_tail_kernel : all remaining levels once a level and its successor fit in shared memory, one CTA per frame
+//                     (levels 2..4 of a 752x480 frame from level 1: one launch instead of three).
 #include "common.cuh"
 
 namespace {
 
-constexpr int TW = 64, TH = 16;
-constexpr int SROWS = 2 * TH + 3;     // 35 source rows
-constexpr int SCOLS = 2 * TW + 8;     // 136 bytes: source x in [2*tx0-4, 2*tx0+132)
-constexpr int THREADS = 256;
-
-// BORDER_REFLECT_101; t is first clamped into the range where one reflection suffices (taps that need more are
-// only ever requested for outputs that are discarded, the clamp just keeps their addresses valid).
+// BORDER_REFLECT_101; t is first clamped into the range where one reflection suffices (taps that need more are only
+// ever requested for outputs that are discarded, the clamp just keeps their addresses valid).
 __device__ __forceinline__ int reflect101(int t, int n) {
   t = max(-(n - 1), min(2 * n - 2, t));
   if (t < 0) return -t;
@@ -23,70 +27,149 @@ __device__ __forceinline__ int reflect101(int t, int n) {
   return t;
 }
 
-__global__ void __launch_bounds__(THREADS) pyr_down_kernel(const __grid_constant__ FrameBatch B, int src_off, int sw,
-                                                           int sh, int dst_off, int dw, int dh) {
-  __shared__ __align__(16) uint8_t s_src[SROWS][SCOLS];
-  __shared__ uint16_t s_h[SROWS][TW];
+// k_r * (0,0,1,4), k_r * (6,4,1,0), k_r * (1,4,6,4), k_r * (1,0,0,0) as little-endian byte vectors
+__device__ __forceinline__ void pair_acc(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t kr, uint32_t& e, uint32_t& o) {
+  e = __dp4a(w0, 0x04010000u * kr, e);
+  e = __dp4a(w1, 0x00010406u * kr, e);
+  o = __dp4a(w1, 0x04060401u * kr, o);
+  o = __dp4a(w2, 0x00000001u * kr, o);
+}
 
-  uint8_t* const pyr = B.f[blockIdx.z].pyr;
+// 8 consecutive outputs x0 .. x0+7 (x0 % 8 == 0) of destination row y from a source whose rows are word-aligned
+// (sw % 4 == 0, stride % 4 == 0, base 4-byte aligned).  Works on global or shared memory.  Returns the outputs packed
+// in two words.  Borders cost two register patches, no extra memory access: the only out-of-row taps that reach a kept
+// output are columns -2, -1 (reflected to 2, 1, which sit in the first word) and column sw (reflected to sw - 2, which
+// sits in the last in-row word); words beyond the row are loaded from a clamped in-row address and ignored.
+template <bool kGlobal>
+__device__ __forceinline__ uint2 down8(const uint8_t* __restrict__ src, int stride, int sw, int sh, int y, int x0) {
+  uint32_t e[4] = {0, 0, 0, 0}, o[4] = {0, 0, 0, 0};
+  const int c0 = 2 * x0 - 4;                 // column of w[0]
+  const int kb = (sw - c0) >> 2;             // index of the first word that lies beyond the row (>= 6: none)
+#pragma unroll
+  for (int r = 0; r < 5; r++) {
+    const uint32_t kr = (r == 0 || r == 4) ? 1u : (r == 2 ? 6u : 4u);
+    const uint8_t* __restrict__ p = src + size_t(reflect101(2 * y - 2 + r, sh)) * stride;
+    uint32_t w[6];   // w[k] = columns c0 + 4k .. + 3
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const int c = min(max(c0 + 4 * k, 0), sw - 4);
+      const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(p + c);
+      w[k] = kGlobal ? __ldg(q) : *q;
+    }
+    if (x0 == 0) w[0] = __byte_perm(w[1], 0, 0x1200);          // columns -2, -1 <- 2, 1
+#pragma unroll
+    for (int k = 1; k < 6; k++)
+      if (k == kb) w[k] = (w[k - 1] >> 16) & 255u;             // column sw <- sw - 2
+#pragma unroll
+    for (int j = 0; j < 4; j++) pair_acc(w[j], w[j + 1], w[j + 2], kr, e[j], o[j]);
+  }
+  uint2 out;
+  out.x = ((e[0] + 128) >> 8) | (((o[0] + 128) >> 8) << 8) | (((e[1] + 128) >> 8) << 16) | (((o[1] + 128) >> 8) << 24);
+  out.y = ((e[2] + 128) >> 8) | (((o[2] + 128) >> 8) << 8) | (((e[3] + 128) >> 8) << 16) | (((o[3] + 128) >> 8) << 24);
+  return out;
+}
+
+// Stores up to 8 packed outputs at drow + x0 (bound: x0 + k < dw); word stores when the row allows it.
+__device__ __forceinline__ void store8(uint8_t* __restrict__ drow, int x0, int dw, uint2 v, bool words_ok) {
+  if (words_ok && x0 + 8 <= dw) {
+    *reinterpret_cast<uint32_t*>(drow + x0) = v.x;
+    *reinterpret_cast<uint32_t*>(drow + x0 + 4) = v.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (x0 + k < dw) drow[x0 + k] = uint8_t(((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 255u);
+  }
+}
+
+// Generic output (any alignment): byte taps with reflection.
+__device__ __forceinline__ uint8_t down1(const uint8_t* __restrict__ src, int stride, int sw, int sh, int y, int x) {
+  int acc = 0;
+#pragma unroll
+  for (int r = 0; r < 5; r++) {
+    const int kr = (r == 0 || r == 4) ? 1 : (r == 2 ? 6 : 4);
+    const uint8_t* __restrict__ p = src + size_t(reflect101(2 * y - 2 + r, sh)) * stride;
+    const int h = p[reflect101(2 * x - 2, sw)] + 4 * p[reflect101(2 * x - 1, sw)] + 6 * p[reflect101(2 * x, sw)] +
+                  4 * p[reflect101(2 * x + 1, sw)] + p[reflect101(2 * x + 2, sw)];
+    acc += kr * h;
+  }
+  return uint8_t((acc + 128) >> 8);
+}
+
+constexpr int PD_THREADS = 256;
+
+__global__ void __launch_bounds__(PD_THREADS) pyr_down_kernel(const __grid_constant__ FrameBatch B, int src_off, int sw,
+                                                              int sh, int dst_off, int dw, int dh) {
+  uint8_t* const pyr = B.f[blockIdx.y].pyr;
   const uint8_t* __restrict__ src = pyr + src_off;
   uint8_t* __restrict__ dst = pyr + dst_off;
-  const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-  const int sx0 = 2 * tx0 - 4;          // source x of s_src[.][0]
-  const int sy0 = 2 * ty0 - 2;          // source y of s_src[0][.]
-  const int tid = threadIdx.x;
-
-  // ---- stage source window
-  const bool row_words_ok = (sx0 >= 0) && (sx0 + SCOLS <= sw) && ((sw & 3) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
-  if (row_words_ok) {
-    constexpr int WPR = SCOLS / 4;  // 34 words per row
-    for (int i = tid; i < SROWS * WPR; i += THREADS) {
-      const int r = i / WPR, c = i - r * WPR;
-      const int sy = reflect101(sy0 + r, sh);
-      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + size_t(sy) * sw + sx0) + c);
-      *reinterpret_cast<uint32_t*>(&s_src[r][4 * c]) = v;
-    }
+  const int gpr = (dw + 7) >> 3;                       // groups of 8 outputs per row
+  const int task = blockIdx.x * PD_THREADS + threadIdx.x;
+  if (task >= gpr * dh) return;
+  const int y = task / gpr, x0 = (task - y * gpr) * 8;
+  if ((sw & 3) == 0) {                                 // rows are word-aligned (level offsets are 256-byte aligned)
+    const uint2 v = down8<true>(src, sw, sw, sh, y, x0);
+    store8(dst + size_t(y) * dw, x0, dw, v, (dw & 3) == 0);
   } else {
-    for (int i = tid; i < SROWS * SCOLS; i += THREADS) {
-      const int r = i / SCOLS, c = i - r * SCOLS;
-      const int sy = reflect101(sy0 + r, sh);
-      const int sx = reflect101(sx0 + c, sw);
-      s_src[r][c] = __ldg(src + size_t(sy) * sw + sx);
-    }
+    for (int k = 0; k < 8; k++)
+      if (x0 + k < dw) dst[size_t(y) * dw + x0 + k] = down1(src, sw, sw, sh, y, x0 + k);
   }
-  __syncthreads();
+}
 
-  // ---- horizontal pass: s_h[r][x] = sum_j k_j * src(r, 2(tx0+x)+j-2)  -> s_src column 2x+j+2
-  for (int i = tid; i < SROWS * TW; i += THREADS) {
-    const int r = i / TW, x = i - r * TW;
-    const uint8_t* p = &s_src[r][2 * x + 2];
-    s_h[r][x] = uint16_t(p[0] + 4 * p[1] + 6 * p[2] + 4 * p[3] + p[4]);
-  }
-  __syncthreads();
+// All levels after `first` for one frame per CTA: level `first` is staged in shared memory (row stride padded to a
+// multiple of 4), every further level is computed from its predecessor in shared memory and written to global memory.
+constexpr int PT_THREADS = 1024;
+constexpr size_t kTailSmemMax = 64 * 1024;   // small on purpose: one CTA per frame only pays off for the tiny levels
 
-  // ---- vertical pass + store: each thread 4 consecutive x of one row
-  const int qy = tid / (TW / 4), qx = (tid - qy * (TW / 4)) * 4;
-  const int oy = ty0 + qy, ox = tx0 + qx;
-  if (oy < dh && ox < dw) {
-    uint32_t packed = 0;
-    uint8_t o[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int x = qx + k;
-      const int acc = s_h[2 * qy][x] + 4 * s_h[2 * qy + 1][x] + 6 * s_h[2 * qy + 2][x] + 4 * s_h[2 * qy + 3][x] +
-                      s_h[2 * qy + 4][x];
-      o[k] = uint8_t((acc + 128) >> 8);
-      packed |= uint32_t(o[k]) << (8 * k);
-    }
-    uint8_t* d = dst + size_t(oy) * dw + ox;
-    if (ox + 3 < dw && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
-      *reinterpret_cast<uint32_t*>(d) = packed;
+__device__ __host__ inline size_t level_smem(int w, int h) { return (size_t((w + 3) & ~3) * h + 15) & ~size_t(15); }
+
+__global__ void __launch_bounds__(PT_THREADS) pyr_tail_kernel(const __grid_constant__ FrameBatch B,
+                                                              const __grid_constant__ PyrGeom G, int first) {
+  extern __shared__ __align__(16) uint8_t s_buf[];
+  uint8_t* const pyr = B.f[blockIdx.x].pyr;
+  const int tid = threadIdx.x;
+  int sw = G.w[first], sh = G.h[first];
+  int sst = (sw + 3) & ~3;
+  uint8_t* s_a = s_buf;                                  // source level
+  uint8_t* s_b = s_buf + level_smem(sw, sh);             // its successor (levels shrink, so ping-pong always fits)
+  {
+    const uint8_t* __restrict__ g = pyr + G.off[first];
+    if ((sw & 3) == 0) {
+      const int n4 = (sw * sh) >> 2;
+      for (int i = tid; i < n4; i += PT_THREADS)
+        reinterpret_cast<uint32_t*>(s_a)[i] = __ldg(reinterpret_cast<const uint32_t*>(g) + i);
     } else {
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (ox + k < dw) d[k] = o[k];
+      for (int i = tid; i < sw * sh; i += PT_THREADS) {
+        const int r = i / sw;
+        s_a[r * sst + (i - r * sw)] = __ldg(g + i);
+      }
     }
+  }
+  __syncthreads();
+  for (int l = first + 1; l < G.levels; l++) {
+    const int dw = G.w[l], dh = G.h[l];
+    const int dst_st = (dw + 3) & ~3;
+    uint8_t* __restrict__ gdst = pyr + G.off[l];
+    const bool last = (l + 1 == G.levels);
+    const int gpr = (dw + 7) >> 3;
+    for (int task = tid; task < gpr * dh; task += PT_THREADS) {
+      const int y = task / gpr, x0 = (task - y * gpr) * 8;
+      uint2 v;
+      if ((sw & 3) == 0) {
+        v = down8<false>(s_a, sst, sw, sh, y, x0);
+      } else {                                         // odd-sized source: byte taps
+        v.x = v.y = 0;
+        for (int k = 0; k < 8; k++)
+          if (x0 + k < dw) {
+            const uint32_t px = down1(s_a, sst, sw, sh, y, x0 + k);
+            if (k < 4) v.x |= px << (8 * k); else v.y |= px << (8 * (k - 4));
+          }
+      }
+      store8(gdst + size_t(y) * dw, x0, dw, v, (dw & 3) == 0);
+      if (!last) store8(s_b + size_t(y) * dst_st, x0, dst_st, v, true);   // padding columns are never used as taps
+    }
+    __syncthreads();
+    uint8_t* t = s_a; s_a = s_b; s_b = t;
+    sw = dw; sh = dh; sst = dst_st;
   }
 }
 
@@ -108,6 +191,19 @@ __global__ void __launch_bounds__(256) upload_kernel(const __grid_constant__ Fra
   }
 }
 
+// The level the tail kernel starts from: the first one that fits in shared memory together with its successor
+// (-1: none, every level is produced by pyr_down_kernel).
+int tail_source_level(const PyrGeom& g, size_t* smem_bytes) {
+  for (int l = 1; l + 1 < g.levels; l++) {
+    const size_t need = level_smem(g.w[l], g.h[l]) + level_smem(g.w[l + 1], g.h[l + 1]);
+    if (need <= kTailSmemMax) {
+      if (smem_bytes) *smem_bytes = need;
+      return l;
+    }
+  }
+  return -1;
+}
+
 }  // namespace
 
 cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, cudaStream_t stream) {
@@ -116,13 +212,30 @@ cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int by
   return cudaGetLastError();
 }
 
-int sdvlb_pyramid_launches(const PyrGeom& g) { return g.levels - 1; }
+int sdvlb_pyramid_launches(const PyrGeom& g) {
+  const int src = tail_source_level(g, nullptr);
+  return src > 0 ? src + 1 : g.levels - 1;
+}
 
-// Builds levels 1..L-1 for the frames of the batch (level 0 already resident). One launch per level.
+// Builds levels 1..L-1 for the frames of the batch (level 0 already resident).
 cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStream_t stream) {
-  for (int l = 1; l < g.levels; l++) {
-    dim3 grid((g.w[l] + TW - 1) / TW, (g.h[l] + TH - 1) / TH, B.n);
-    pyr_down_kernel<<<grid, THREADS, 0, stream>>>(B, g.off[l - 1], g.w[l - 1], g.h[l - 1], g.off[l], g.w[l], g.h[l]);
+  size_t smem = 0;
+  const int tail_src = tail_source_level(g, &smem);
+  const int direct_to = tail_src > 0 ? tail_src : g.levels - 1;   // levels 1..direct_to by pyr_down_kernel
+  for (int l = 1; l <= direct_to; l++) {
+    const int tasks = ((g.w[l] + 7) >> 3) * g.h[l];
+    dim3 grid((tasks + PD_THREADS - 1) / PD_THREADS, B.n);
+    pyr_down_kernel<<<grid, PD_THREADS, 0, stream>>>(B, g.off[l - 1], g.w[l - 1], g.h[l - 1], g.off[l], g.w[l], g.h[l]);
+  }
+  if (tail_src > 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      const cudaError_t e = cudaFuncSetAttribute(pyr_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 int(kTailSmemMax));
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    pyr_tail_kernel<<<B.n, PT_THREADS, smem, stream>>>(B, g, tail_src);
   }
   return cudaGetLastError();
 }

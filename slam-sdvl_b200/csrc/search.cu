@@ -188,54 +188,81 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
       xdiff = pxb0 - pxa0; ydiff = pxb1 - pxa1;
       vline = xdiff * xdiff + ydiff * ydiff;
     }
-    int sumA = 0, sumAA = 0;                            // GetZMSSDScore (matcher.cc:447-457)
-    for (int r = 0; r < 64; r++) { const int v = s_patch[warp][r]; sumA += v; sumAA += v * v; }
+    // GetZMSSDScore (matcher.cc:447-457): template sums, two pixels per lane
+    const int ta0 = s_patch[warp][lane], ta1 = s_patch[warp][lane + 32];
+    const int sumA = int(__reduce_add_sync(0xffffffffu, unsigned(ta0 + ta1)));
+    const int sumAA = int(__reduce_add_sync(0xffffffffu, unsigned(ta0 * ta0 + ta1 * ta1)));
     const int nc = *cur.n_corners;
-    for (int base = 0; base < nc; base += 32) {
-      const int idx = base + lane;
-      bool in = false;
-      int cx = 0, cy = 0, cl = 0;
-      if (idx < nc) {
-        const int4 cc = __ldg(cur.corners + idx);
-        cx = cc.x; cy = cc.y; cl = cc.z;
-        in = abs(cl - level) <= 1 && !(cx - margin < 0 || cy - margin < 0) &&
-             !(cy + margin >= A.g.h[cl] || cx + margin >= A.g.w[cl]);
-        if (in) {
-          const double posx = double(cx * (1 << cl)), posy = double(cy * (1 << cl));
-          if (fixed) {
-            const double dx = px0 - posx, dy = px1 - posy;
-            in = !(dx * dx + dy * dy > range2);
-          } else {
-            const double dist = normdist - (posx * nx + posy * ny);
-            if (fabs(dist) > range) in = false;
-            else {
-              const double u = ((posx - pxa0) * xdiff + (posy - pxa1) * ydiff) / vline;
-              if (u > 1) { const double dx = posx - pxb0, dy = posy - pxb1; if (dx * dx + dy * dy > range2) in = false; }
-              if (in && u < 0) { const double dx = posx - pxa0, dy = posy - pxa1; if (dx * dx + dy * dy > range2) in = false; }
+    // GetCornersInRange scans every corner of the frame (matcher.cc:123-230); only corners within `range` of the
+    // predicted position (fixed points) or of the epipolar segment can pass, so only the 32-px index cells that
+    // overlap that region are visited.  The exact test below is the reference's.
+    const int gw = A.g.wcells[0], gh = A.g.hcells[0];
+    const int32_t* __restrict__ g_start = cur.grid;
+    const int32_t* __restrict__ g_item = cur.grid + 2 * gw * gh + 1;
+    double bx0, bx1, by0, by1;
+    if (fixed) { bx0 = bx1 = px0; by0 = by1 = px1; }
+    else { bx0 = fmin(pxa0, pxb0); bx1 = fmax(pxa0, pxb0); by0 = fmin(pxa1, pxb1); by1 = fmax(pxa1, pxb1); }
+    const double pad = range + 1.0;
+    // Degenerate inputs make the reference's test accept every corner (NaN comparisons are false; a zero-length
+    // epipolar segment gives u = NaN): visit the whole index then.
+    int cx0 = 0, cx1 = gw - 1, cy0 = 0, cy1 = gh - 1;
+    const bool box_ok = isfinite(bx0) && isfinite(bx1) && isfinite(by0) && isfinite(by1) && (fixed || vline > 0.0);
+    if (box_ok) {
+      cx0 = int(fmax(0.0, floor((bx0 - pad) * (1.0 / 32.0))));
+      cy0 = int(fmax(0.0, floor((by0 - pad) * (1.0 / 32.0))));
+      cx1 = int(fmin(double(gw - 1), floor((bx1 + pad) * (1.0 / 32.0))));
+      cy1 = int(fmin(double(gh - 1), floor((by1 + pad) * (1.0 / 32.0))));
+    }
+    for (int gy = cy0; gy <= cy1; gy++) {
+      // cells of one grid row are contiguous in the item list
+      const int i0 = __ldg(g_start + gy * gw + cx0), i1 = __ldg(g_start + gy * gw + cx1 + 1);
+      for (int base = i0; base < i1; base += 32) {
+        const int it = base + lane;
+        bool in = false;
+        int idx = 0, cx = 0, cy = 0, cl = 0;
+        if (it < i1) {
+          idx = __ldg(g_item + it);
+          const int4 cc = __ldg(cur.corners + idx);
+          cx = cc.x; cy = cc.y; cl = cc.z;
+          in = idx < nc && abs(cl - level) <= 1 && !(cx - margin < 0 || cy - margin < 0) &&
+               !(cy + margin >= A.g.h[cl] || cx + margin >= A.g.w[cl]);
+          if (in) {
+            const double posx = double(cx * (1 << cl)), posy = double(cy * (1 << cl));
+            if (fixed) {
+              const double dx = px0 - posx, dy = px1 - posy;
+              in = !(dx * dx + dy * dy > range2);
+            } else {
+              const double dist = normdist - (posx * nx + posy * ny);
+              if (fabs(dist) > range) in = false;
+              else {
+                const double u = ((posx - pxa0) * xdiff + (posy - pxa1) * ydiff) / vline;
+                if (u > 1) { const double dx = posx - pxb0, dy = posy - pxb1; if (dx * dx + dy * dy > range2) in = false; }
+                if (in && u < 0) { const double dx = posx - pxa0, dy = posy - pxa1; if (dx * dx + dy * dy > range2) in = false; }
+              }
             }
           }
         }
+        uint32_t todo = __ballot_sync(0xffffffffu, in);
+        n_in_range += __popc(todo);
+        // CompareZMSSDScore (matcher.cc:459-476) for each in-range corner, the 8x8 pixels spread over the warp
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int bcx = __shfl_sync(0xffffffffu, cx, src), bcy = __shfl_sync(0xffffffffu, cy, src);
+          const int bcl = __shfl_sync(0xffffffffu, cl, src), bidx = __shfl_sync(0xffffffffu, idx, src);
+          const int Wc = A.g.w[bcl];
+          const int py = lane >> 2, pxx = (lane & 3) * 2;
+          const uint8_t* __restrict__ cp = cur.pyr + A.g.off[bcl] + size_t(bcy - half + py) * Wc + (bcx - half + pxx);
+          const int b0 = __ldg(cp), b1 = __ldg(cp + 1);
+          const int a0 = s_patch[warp][py * 8 + pxx], a1 = s_patch[warp][py * 8 + pxx + 1];
+          const int sB = int(__reduce_add_sync(0xffffffffu, unsigned(b0 + b1)));
+          const int sBB = int(__reduce_add_sync(0xffffffffu, unsigned(b0 * b0 + b1 * b1)));
+          const int sAB = int(__reduce_add_sync(0xffffffffu, unsigned(a0 * b0 + a1 * b1)));
+          const int score = sumAA - 2 * sAB + sBB - (sumA * sumA - 2 * sumA * sB + sB * sB) / 64;
+          const unsigned long long key = (static_cast<unsigned long long>(uint32_t(score)) << 32) | uint32_t(bidx);
+          if (key < best_key) best_key = key;
+        }
       }
-      n_in_range += __popc(__ballot_sync(0xffffffffu, in));
-      if (in) {                                         // CompareZMSSDScore (matcher.cc:459-476)
-        const int Wc = A.g.w[cl];
-        const uint8_t* __restrict__ cp = cur.pyr + A.g.off[cl] + size_t(cy - half) * Wc + (cx - half);
-        int sB = 0, sBB = 0, sAB = 0;
-        for (int y = 0; y < 8; y++)
-#pragma unroll
-          for (int x = 0; x < 8; x++) {
-            const int pix = __ldg(cp + y * Wc + x);
-            sB += pix; sBB += pix * pix; sAB += pix * int(s_patch[warp][y * 8 + x]);
-          }
-        const int score = sumAA - 2 * sAB + sBB - (sumA * sumA - 2 * sumA * sB + sB * sB) / 64;
-        const unsigned long long key = (static_cast<unsigned long long>(uint32_t(score)) << 32) | uint32_t(idx);
-        if (key < best_key) best_key = key;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best_key, o);
-      if (other < best_key) best_key = other;
     }
     m.n_in_range = n_in_range;
     int best_score = threshold + 1;

@@ -33,7 +33,11 @@ def test_pyramid_bit_exact(binding, sw, O, name, seed):
 
 def test_pyramid_random_and_odd_sizes(binding, abi, O):
     rng = np.random.default_rng(5)
-    for (w, h, levels) in [(101, 99, 3), (94, 60, 2), (47, 30, 2), (640, 480, 5), (333, 250, 4)]:
+    # word-aligned rows (dp4a path, incl. widths that are not a multiple of 8), unaligned rows (generic path), sizes
+    # whose tail levels run from shared memory and sizes too large for that
+    for (w, h, levels) in [(101, 99, 3), (94, 60, 2), (47, 30, 2), (640, 480, 5), (333, 250, 4), (752, 480, 5),
+                           (376, 240, 4), (188, 120, 3), (72, 40, 3), (20, 16, 2), (1920, 1080, 5), (1284, 724, 5),
+                           (2048, 2048, 4)]:
         p = abi.default_params()
         p.pyramid_levels = levels
         p.max_align_level = levels - 1
