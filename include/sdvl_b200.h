@@ -106,7 +106,7 @@ int sdvlb_dev_upload(sdvlb_ctx* ctx, void* dst, const void* src, uint64_t bytes)
 /* ---- per-kernel timing (CUDA events on the context stream) -------------- */
 enum {
   SDVLB_K_PYRAMID = 0, SDVLB_K_FAST = 1, SDVLB_K_SELECT = 2, SDVLB_K_ALIGN = 3,
-  SDVLB_K_SEARCH = 4, SDVLB_K_COUNT = 5
+  SDVLB_K_SEARCH = 4, SDVLB_K_PREP = 5, SDVLB_K_POSE = 6, SDVLB_K_COUNT = 7
 };
 int sdvlb_timing_enable(sdvlb_ctx* ctx, int on);
 /* Accumulated milliseconds and launch counts per kernel since the last reset.
@@ -266,6 +266,106 @@ int sdvlb_frames_wait(sdvlb_ctx* ctx, sdvlb_frame* const* frames, int n);
 int sdvlb_track_submit(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, int mirror);
 int sdvlb_track_poll(sdvlb_ctx* ctx);
 int sdvlb_track_collect(sdvlb_ctx* ctx);
+
+/* ---- FeatureAlign pose refinement (feature_align.cc:152-283,341-431) ------
+ * RANSAC inlier selection and the Tukey-weighted Gauss-Newton on SE3 that
+ * FeatureAlign runs on the matches of a frame, as device kernels
+ * (SURVEY.md section 8(f), row 1). */
+typedef struct sdvlb_pose_obs {
+  double v[3];      /* feature->GetVector() (unit bearing in the frame) */
+  double pos[3];    /* feature->GetPoint()->GetPosition() (world) */
+  int32_t level;    /* feature->GetLevel() */
+  int32_t flags;    /* SDVLB_OBS_*: which of the two FeatureAlign lists the feature is in */
+} sdvlb_pose_obs;
+enum { SDVLB_OBS_INLIER = 1, SDVLB_OBS_OUTLIER = 2 };
+
+/* glibc rand() (random_r TYPE_3) as an explicit state.  The reference draws
+ * from the process-wide rand() (feature_align.cc:53,103,180, never seeded);
+ * here every FeatureAlign owns one stream that starts like srand(1). */
+typedef struct sdvlb_rand { uint32_t r[34]; int32_t n; int32_t pad_; } sdvlb_rand;
+void sdvlb_rand_seed(sdvlb_rand* s, unsigned seed);
+int sdvlb_rand_next(sdvlb_rand* s);
+/* std::random_shuffle(v, v + n) of libstdc++ driven by this stream. */
+void sdvlb_rand_shuffle(sdvlb_rand* s, int32_t* v, int n);
+
+/* FeatureAlign::SelectInliers(frame, fs_found, inliers, outliers)
+ * (feature_align.cc:152-216): obs = fs_found in order; on return every
+ * obs[i].flags is SDVLB_OBS_INLIER or SDVLB_OBS_OUTLIER and *rng has advanced
+ * by the number of rand() calls the reference would have made. */
+int sdvlb_select_inliers(sdvlb_ctx* ctx, sdvlb_pose_obs* obs, int n, const double T_frame[7], sdvlb_rand* rng);
+/* FeatureAlign::OptimizePose(frame) (feature_align.cc:73-82) up to, not
+ * including, RemoveOutliers: OptimizePose(inliers) + RescueOutliers +
+ * OptimizePose again when something was rescued.  T_frame: in = frame pose,
+ * out = refined pose; flags in/out. */
+int sdvlb_optimize_pose(sdvlb_ctx* ctx, sdvlb_pose_obs* obs, int n, double T_frame[7]);
+
+/* ---- resident sequences ----------------------------------------------------
+ * The whole per-frame chain of SDVL::ProcessFrame (sdvl.cc:179-203) plus the
+ * motion model (sdvl.cc:266-281) with the tracked state of a sequence -- the
+ * features of its last frame and the map points they observe -- kept in HBM:
+ *   prior pose -> ImageAlign::ComputePose -> FeatureAlign::Reproject
+ *   (ProjectPoints, SelectPoints, Matcher::SearchPoint, SelectInliers) ->
+ *   FeatureAlign::OptimizePose -> RemoveOutliers -> GetMotionModel
+ * runs as one chain of kernels per submission for many sequences; the host
+ * only reads the result (pose, statistics, the new frame's feature list) and
+ * plays the mapping thread's role (sdvlb_seq_add_points). */
+typedef struct sdvlb_seq sdvlb_seq;
+#define SDVLB_SEQ_KF_CAP 64   /* keyframes that may be referenced by live points of one sequence */
+
+typedef struct sdvlb_seq_point {   /* a map point handed to the tracker with its observation in the current frame */
+  double pos[3];       /* Point::GetPosition() */
+  double ref_px[2];    /* Point::GetInitFeature()->GetPosition() in the keyframe, level-0 pixels */
+  double cur_px[2];    /* position of the feature observing it in the sequence's current frame */
+  double idepth;       /* Point::GetInverseDepth() */
+  double idepth_std;   /* Point::GetStd() */
+  int64_t user_id;     /* caller's handle of the point; returned in sdvlb_seq_feat */
+  int32_t ref_level;   /* init feature level */
+  int32_t cur_level;   /* level of the observing feature */
+  int32_t flags;       /* SDVLB_CAND_FIXED = Point::IsFixed() */
+  int32_t n_successful;/* Point::Score() so far */
+  int32_t n_failed;
+  int32_t pad_;
+} sdvlb_seq_point;
+
+enum { SDVLB_FEAT_HAS_POINT = 1 };
+typedef struct sdvlb_seq_feat {    /* one feature of the sequence's current frame (frame->GetFeatures() order) */
+  double px[2];        /* Feature::GetPosition() */
+  int64_t user_id;
+  int32_t level;       /* Feature::GetLevel() */
+  int32_t flags;       /* SDVLB_FEAT_HAS_POINT: cleared for outliers (RemoveOutliers, feature_align.cc:245-256) */
+} sdvlb_seq_feat;
+
+typedef struct sdvlb_seq_result {
+  double pose[7];      /* frame->GetPose() after OptimizePose */
+  int32_t n_tracked;   /* ImageAlign::ComputePose return value */
+  int32_t matches;     /* FeatureAlign::GetMatches() */
+  int32_t attempts;    /* FeatureAlign::GetAttempts() */
+  int32_t inliers, outliers;
+  int32_t n_points;    /* Frame::GetNumPoints() */
+  int32_t gn_iters;    /* ImageAlign Gauss-Newton iterations */
+  int32_t n_feats;     /* entries in feats */
+  const sdvlb_seq_feat* feats;             /* pinned host memory, valid until the sequence is submitted again */
+  int32_t kf_live[SDVLB_SEQ_KF_CAP];       /* live points per keyframe slot (see sdvlb_seq_add_points) */
+} sdvlb_seq_result;
+
+/* FeatureAlign(map, camera, max_matches) + an empty track: RNG seeded like srand(1), cell order shuffled once
+ * (feature_align.cc:33-54).  max_feats = capacity of a frame's feature list (0: 2 * max_matches, at least 256). */
+int sdvlb_seq_create(sdvlb_ctx* ctx, int max_feats, sdvlb_seq** out);
+int sdvlb_seq_destroy(sdvlb_ctx* ctx, sdvlb_seq* seq);
+/* (Re)starts the track at `frame` with pose T (world->camera), no features, zero velocity (what SDVL's
+ * initialisation leaves behind, sdvl.cc:132-177).  Applied in order with later calls on the context's stream. */
+int sdvlb_seq_reset(sdvlb_ctx* ctx, sdvlb_seq* seq, const sdvlb_frame* frame, const double T[7]);
+/* Mapping thread -> tracker: n points whose init features live in keyframe `kf` (pose T_kf) are appended, in order,
+ * to the feature list of the sequence's current frame.  *kf_slot receives the keyframe slot the points reference;
+ * `kf` must stay alive until a result reports kf_live[slot] == 0.  Takes effect before the next tracked frame. */
+int sdvlb_seq_add_points(sdvlb_ctx* ctx, sdvlb_seq* seq, const sdvlb_frame* kf, const double T_kf[7],
+                         const sdvlb_seq_point* pts, int n, int* kf_slot);
+/* One new frame for each of n sequences (frames built by sdvlb_frames_submit / sdvlb_frame_create with corners).
+ * Asynchronous: _poll returns 1 when finished, _collect waits and fills n results in submission order.  One
+ * submission in flight per context; a frame must stay alive until the sequence has tracked the next one. */
+int sdvlb_seq_track_submit(sdvlb_ctx* ctx, sdvlb_seq* const* seqs, sdvlb_frame* const* frames, int n);
+int sdvlb_seq_track_poll(sdvlb_ctx* ctx);
+int sdvlb_seq_track_collect(sdvlb_ctx* ctx, sdvlb_seq_result* results);
 
 #ifdef __cplusplus
 }

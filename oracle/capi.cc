@@ -172,6 +172,12 @@ void orc_rand_seq(unsigned seed, int n, int32_t* out) {
   r.Seed(seed);
   for (int i = 0; i < n; i++) out[i] = r.Next();
 }
+void orc_rand_state(unsigned seed, sdvlb_rand* out) {   // the stream's state right after srand(seed)
+  GlibcRand r;
+  r.Seed(seed);
+  std::memcpy(out->r, r.r, sizeof(r.r));
+  out->n = r.n;
+}
 void orc_shuffle(int n, int32_t* v, unsigned seed) {
   GlibcRand r;
   r.Seed(seed);
@@ -192,6 +198,54 @@ int orc_align_patch(const sdvlb_params* P, const uint8_t* img, int w, int h, con
   const bool ok = m.AlignPatch(im, bp, patch, &p);
   px[0] = p.x; px[1] = p.y;
   return ok ? 1 : 0;
+}
+
+// ---- FeatureAlign pose refinement alone (parity of sdvlb_select_inliers / sdvlb_optimize_pose) -----------------
+// obs: n x {v[3], pos[3], level, flags} (sdvlb_pose_obs).  mode 0: SelectInliers (rng = glibc state in/out),
+// mode 1: OptimizePose(frame) including RemoveOutliers; flags out: 1 inlier, 2 outlier.
+int orc_pose_refine(const sdvlb_params* P, const sdvlb_camera* cam_, sdvlb_pose_obs* obs, int n, double T[7],
+                    sdvlb_rand* rng, int mode) {
+  const Camera cam = CamFrom(cam_);
+  GlibcRand r;
+  if (rng) { std::memcpy(r.r, rng->r, sizeof(r.r)); r.n = rng->n; }
+  std::vector<std::shared_ptr<Point>> trash;
+  // the constructor shuffles cell_order_ with the stream: give it a scratch stream so `r` only sees RANSAC draws
+  GlibcRand scratch;
+  FeatureAlign fa(*P, &cam, P->max_matches, &scratch, &trash);
+  auto frame = std::make_shared<Frame>();
+  frame->cam = &cam;
+  frame->pose = SE3::FromArray(T);
+  std::vector<std::shared_ptr<Feature>> fs;
+  for (int i = 0; i < n; i++) {
+    auto ft = std::make_shared<Feature>();
+    ft->frame = frame;
+    ft->v = V3(obs[i].v[0], obs[i].v[1], obs[i].v[2]);
+    ft->level = obs[i].level;
+    auto pt = std::make_shared<Point>();
+    pt->fixed = true;
+    pt->p3d = V3(obs[i].pos[0], obs[i].pos[1], obs[i].pos[2]);
+    ft->point = pt;
+    fs.push_back(ft);
+  }
+  if (mode == 0) {
+    fa.SetRng(&r);   // from here on the draws come from the caller's stream
+    fa.SelectInliersHook(frame, fs);
+    for (int i = 0; i < n; i++) obs[i].flags = SDVLB_OBS_OUTLIER;
+    for (auto& f : fa.inliers())
+      for (int i = 0; i < n; i++) if (fs[i] == f) obs[i].flags = SDVLB_OBS_INLIER;
+    if (rng) { std::memcpy(rng->r, r.r, sizeof(r.r)); rng->n = r.n; }
+    return int(fa.inliers().size());
+  }
+  for (int i = 0; i < n; i++) {
+    if (obs[i].flags == SDVLB_OBS_INLIER) fa.inliers().push_back(fs[i]);
+    else if (obs[i].flags == SDVLB_OBS_OUTLIER) fa.outliers().push_back(fs[i]);
+  }
+  fa.OptimizePose(frame);
+  frame->pose.ToArray(T);
+  for (int i = 0; i < n; i++) obs[i].flags = SDVLB_OBS_OUTLIER;
+  for (auto& f : fa.inliers())
+    for (int i = 0; i < n; i++) if (fs[i] == f) obs[i].flags = SDVLB_OBS_INLIER;
+  return int(fa.inliers().size());
 }
 
 // ---- sequence driver -----------------------------------------------------------------------------

@@ -239,6 +239,13 @@ class FeatureAlign {
   int n_inliers() const { return int(inliers_.size()); }
   int n_outliers() const { return int(outliers_.size()); }
   std::vector<std::shared_ptr<Feature>> selected_;   // fs_found of the last Reproject
+  // test hooks for the pose-refinement parity tests: run SelectInliers on a given fs_found / preset the two lists
+  void SelectInliersHook(const std::shared_ptr<Frame>& frame, std::vector<std::shared_ptr<Feature>>& fs_found) {
+    SelectInliers(frame, fs_found, &inliers_, &outliers_);
+  }
+  void SetRng(GlibcRand* rng) { rng_ = rng; }
+  std::vector<std::shared_ptr<Feature>>& inliers() { return inliers_; }
+  std::vector<std::shared_ptr<Feature>>& outliers() { return outliers_; }
  private:
   void SelectPoints(const std::shared_ptr<Frame>& frame, const std::shared_ptr<Frame>& last_frame,
                     std::vector<std::shared_ptr<Feature>>* fs_found);

@@ -118,6 +118,17 @@ def search_points(params, cam, cur_img, T_cur, ref_imgs, cands):
     return out
 
 
+def pose_refine(params, cam, obs, T, rng=None, mode=0):
+    """Oracle FeatureAlign::SelectInliers (mode 0, rng = abi.Rand advanced in place) or OptimizePose (mode 1).
+    Returns (obs with flags, pose)."""
+    obs = np.ascontiguousarray(obs).copy()
+    assert obs.dtype == abi.POSE_OBS_DT
+    T = np.array(T, np.float64)
+    lib().orc_pose_refine(C.byref(params), C.byref(cam), ptr(obs), obs.shape[0], ptr(T),
+                          C.byref(rng) if rng is not None else None, mode)
+    return obs, T
+
+
 class Tracker:
     def __init__(self, params, cam, plane, max_points, kf_every):
         plane = np.ascontiguousarray(plane, np.float64)

@@ -42,6 +42,18 @@ class Match(C.Structure):
                 ("zmssd", C.c_int32), ("n_in_range", C.c_int32)]
 
 
+class PoseObs(C.Structure):
+    _fields_ = [("v", C.c_double * 3), ("pos", C.c_double * 3), ("level", C.c_int32), ("flags", C.c_int32)]
+
+
+class Rand(C.Structure):
+    _fields_ = [("r", C.c_uint32 * 34), ("n", C.c_int32), ("pad_", C.c_int32)]
+
+
+OBS_INLIER, OBS_OUTLIER = 1, 2
+POSE_OBS_DT = np.dtype([("v", "f8", 3), ("pos", "f8", 3), ("level", "i4"), ("flags", "i4")])
+assert POSE_OBS_DT.itemsize == C.sizeof(PoseObs)
+
 CAND_FIXED, CAND_PROJECT = 1, 2
 MATCH_UNSEEN, MATCH_NOT_FOUND, MATCH_FOUND = 0, 1, 2
 

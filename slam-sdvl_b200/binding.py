@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdvl_b200.so")
 _LIB = None
 
-K_NAMES = ("pyramid", "fast", "select", "align", "search")
+K_NAMES = ("pyramid", "fast", "select", "align", "search", "prep", "pose")
 
 
 class SdvlbError(RuntimeError):
@@ -65,6 +65,9 @@ EXPORTS = [
     "sdvlb_frame_level", "sdvlb_frame_corners", "sdvlb_frame_destroy", "sdvlb_image_align", "sdvlb_search_points",
     "sdvlb_track_batch", "sdvlb_frames_submit", "sdvlb_frames_wait", "sdvlb_track_submit", "sdvlb_track_poll",
     "sdvlb_track_collect", "sdvlb_ctx_reserve_frames",
+    "sdvlb_rand_seed", "sdvlb_rand_next", "sdvlb_rand_shuffle", "sdvlb_select_inliers", "sdvlb_optimize_pose",
+    "sdvlb_seq_create", "sdvlb_seq_destroy", "sdvlb_seq_reset", "sdvlb_seq_add_points", "sdvlb_seq_track_submit",
+    "sdvlb_seq_track_poll", "sdvlb_seq_track_collect",
 ]
 
 
@@ -118,8 +121,8 @@ class Context:
         load().sdvlb_timing_enable(C.c_void_p(self.h), int(on))
 
     def timing_read(self, reset=True):
-        ms = (C.c_double * 5)()
-        n = (C.c_int64 * 5)()
+        ms = (C.c_double * len(K_NAMES))()
+        n = (C.c_int64 * len(K_NAMES))()
         _check(load().sdvlb_timing_read(C.c_void_p(self.h), ms, n, int(reset)))
         return {k: (ms[i], n[i]) for i, k in enumerate(K_NAMES)}
 
@@ -163,6 +166,22 @@ class Context:
                                           ptr(out)))
         return out
 
+    def select_inliers(self, obs, T_frame, rng):
+        """FeatureAlign::SelectInliers on the device. obs: POSE_OBS_DT array (flags overwritten); rng: abi.Rand (advanced)."""
+        obs = np.ascontiguousarray(obs)
+        assert obs.dtype == abi.POSE_OBS_DT
+        T = np.ascontiguousarray(T_frame, np.float64)
+        _check(load().sdvlb_select_inliers(C.c_void_p(self.h), ptr(obs), obs.shape[0], ptr(T), C.byref(rng)))
+        return obs
+
+    def optimize_pose(self, obs, T_frame):
+        """FeatureAlign::OptimizePose(frame) on the device (without RemoveOutliers). Returns (obs, refined pose)."""
+        obs = np.ascontiguousarray(obs)
+        assert obs.dtype == abi.POSE_OBS_DT
+        T = np.array(T_frame, np.float64)
+        _check(load().sdvlb_optimize_pose(C.c_void_p(self.h), ptr(obs), obs.shape[0], ptr(T)))
+        return obs, T
+
     def track_batch(self, jobs, mirror=1):
         """jobs: ctypes array of TrackJob."""
         _check(load().sdvlb_track_batch(C.c_void_p(self.h), jobs, len(jobs), self.w, self.hh, mirror))
@@ -174,7 +193,8 @@ _HLIB = None
 
 HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", "sdvlh_tracker_destroy",
                 "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_phases",
-                "sdvlh_tracker_ctx", "sdvlh_tracker_groups", "sdvlh_tracker_threads", "sdvlh_tracker_run"]
+                "sdvlh_tracker_ctx", "sdvlh_tracker_groups", "sdvlh_tracker_threads", "sdvlh_tracker_run",
+                "sdvlh_tracker_create2"]
 
 
 def build_host(verbose=False):
@@ -194,6 +214,7 @@ def load_host():
         H = C.CDLL(HOST_LIB_PATH)
         H.sdvlh_last_error.restype = C.c_char_p
         H.sdvlh_tracker_create.restype = C.c_void_p
+        H.sdvlh_tracker_create2.restype = C.c_void_p
         H.sdvlh_tracker_ctx.restype = C.c_void_p
         _HLIB = H
     return _HLIB
@@ -206,12 +227,13 @@ class HostTracker:
     the batched submission."""
 
     def __init__(self, params, cam, plane, max_points, kf_every, n_seq, n_groups=1, device=0, timing=False,
-                 n_threads=0):
+                 n_threads=0, resident=False):
+        """resident=True keeps the sequences on the device (sdvlb_seq_*): no host marshalling / match replay."""
         H = load_host()
         H.sdvlh_config_set(C.byref(params), C.byref(cam))
         plane = np.ascontiguousarray(plane, np.float64)
-        self.h = H.sdvlh_tracker_create(ptr(plane), max_points, kf_every, n_seq, n_groups, n_threads, device,
-                                        int(timing))
+        self.h = H.sdvlh_tracker_create2(ptr(plane), max_points, kf_every, n_seq, n_groups, n_threads, device,
+                                         int(timing), int(resident))
         if not self.h:
             raise SdvlbError("sdvlh_tracker_create failed: " + H.sdvlh_last_error().decode())
         self.n_seq = n_seq
@@ -264,8 +286,8 @@ class HostTracker:
         return load_host().sdvlh_tracker_threads(C.c_void_p(self.h))
 
     def timing_read(self, reset=True):
-        ms = (C.c_double * 5)()
-        n = (C.c_int64 * 5)()
+        ms = (C.c_double * len(K_NAMES))()
+        n = (C.c_int64 * len(K_NAMES))()
         load_host().sdvlh_tracker_timing_read(C.c_void_p(self.h), ms, n, int(reset))
         return {k: (ms[i], n[i]) for i, k in enumerate(K_NAMES)}
 

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
   int forced_k = 0;
   DSE3 T, T_bk;
 
+  if (n < 0) return;   // resident sequence without a reference frame yet: nothing to align
   if (n == 0) {   // image_align.cc:55-58: nothing to track, frame2 keeps its pose
     if (tid == 0) {
       for (int i = 0; i < 7; i++) { J.out_pose[i] = J.T_cur[i]; J.cur.pose[i] = J.T_cur[i]; }

@@ -46,113 +46,10 @@ int sdvlb_set_error(int code, const char* msg) {
   return code;
 }
 
-namespace {
+#include "capi_internal.h"
 
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct Arena {   // bump allocator over a pinned host buffer and (optionally) a device buffer with identical layout
-  uint8_t* h = nullptr;
-  uint8_t* d = nullptr;
-  size_t cap = 0, used = 0;
-  size_t take(size_t bytes) {
-    const size_t off = align_up(used, 256);
-    used = off + bytes;
-    return off;
-  }
-};
-
-struct TimerSlot { cudaEvent_t a, b; int kind; };
-
-constexpr int kBuildEvents = 8;   // ring of "frame batch enqueued" events; a frame borrows the one of its batch
-constexpr int kSlabFrames = 32;
-
-struct BatchOut {   // per-job results in the `out` arena
-  double pose[7];
-  double error;
-  int32_t info[2];
-  int32_t pad[2];
-};
-
-}  // namespace
-
-struct sdvlb_frame {
-  sdvlb_ctx* ctx = nullptr;
-  FrameDev dev{};                // host_mirror left null here; set per submission when a mirror is wanted
-  uint8_t* d_block = nullptr;    // slot inside one of the context's device slabs
-  size_t off_hdr = 0, off_pose = 0;   // corner header (count) + int4 corner list; pose
-  uint8_t* h_pyr = nullptr;      // pinned host mirror of the pyramid, allocated on first sdvlb_frame_level()
-  bool pyr_mirrored = false;
-  uint8_t* h_corners = nullptr;  // pinned, device-visible: 16-byte header (count) + the first corner_copy corners
-  std::vector<int32_t> h_more;   // whole corner list, only when it is longer than corner_copy
-  cudaEvent_t built = nullptr;   // borrowed from the context's ring: recorded after the frame's batch was enqueued
-  bool build_pending = false;    // submitted with sdvlb_frames_submit, completion not yet observed by the host
-  bool build_corners = false, build_mirror = false;
-  bool has_corners = false;
-  int corners_mirrored = -1;     // number of corners valid in the host mirror, -1 = not mirrored
-  int n_corners = 0;
-};
-
-// Everything sdvlb_track_collect needs to finish a submission made by submit_batch.
-struct PendingTrack {
-  bool active = false;
-  sdvlb_track_job* jobs = nullptr;
-  int n = 0;
-  bool build_frames = false;
-  sdvlb_gn_iter* trace = nullptr;
-  int trace_cap = 0;
-  int* trace_n = nullptr;
-  size_t o_res = 0, o_match = 0, o_trace = 0;
-};
-
-struct sdvlb_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;    // tracking stream (ImageAlign, SearchPoint, synchronous frame construction)
-  cudaStream_t bstream = nullptr;   // build stream (asynchronous frame batches: upload, pyramid, FAST)
-  cudaEvent_t bevents[kBuildEvents] = {};
-  int bevent_next = 0;
-  cudaEvent_t last_build = nullptr; // event of the most recent asynchronous build (null: none yet)
-  int32_t* h_overflow = nullptr;    // pinned, device-visible: [0] overflow flag written by the selector,
-                                    // [16] sequence number of the last finished tracking submission (signal kernel)
-  uint32_t track_seq = 0;
-  PendingTrack pending;
-  sdvlb_params params{};
-  sdvlb_camera cam{};
-  PyrGeom geom{};
-  DevParams dp{};
-  int w = 0, h = 0;
-  int corner_cap = 0;
-  int corner_copy = 0;           // corners the pinned host mirror of a frame holds
-  std::vector<sdvlb_frame*> pool;      // free frames (device slot attached)
-  std::vector<sdvlb_frame*> all_frames;
-  std::vector<uint8_t*> slabs;         // device slabs of kSlabFrames frame slots each
-  std::vector<uint8_t*> mirror_slabs;  // pinned host slabs: one corner mirror per frame slot
-  size_t block_bytes = 0;
-  std::vector<FastPlan> plans;   // one per nfeatures budget seen
-  // FAST scratch (sized for `fast_frames` frames)
-  int fast_frames = 0;
-  uint32_t* cell_kp = nullptr;
-  int32_t* cell_cnt = nullptr;
-  uint32_t* level_kp = nullptr;
-  int32_t* level_cnt = nullptr;
-  int32_t* frame_ticket = nullptr;
-  size_t level_kp_total = 0;
-  // staging
-  Arena in;                      // host->device descriptors (pinned + device copy)
-  Arena out;                     // results: pinned, device-visible host memory the kernels write directly
-  uint8_t* scratch = nullptr;    // device-only scratch for ImageAlign caches
-  size_t scratch_cap = 0;
-  // counters
-  int64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
-  // timing
-  bool timing = false;
-  std::vector<TimerSlot> timers;
-  size_t timers_used = 0;
-  cudaStream_t timer_stream = nullptr;
-  double t_ms[SDVLB_K_COUNT] = {0, 0, 0, 0, 0};
-  int64_t t_launches[SDVLB_K_COUNT] = {0, 0, 0, 0, 0};
-};
-
-namespace {
+namespace sdvlb_detail {
 
 int ensure_arena(Arena* a, size_t bytes, bool need_device) {
   if (bytes <= a->cap) return 0;
@@ -251,7 +148,7 @@ int frame_alloc(sdvlb_ctx* c, sdvlb_frame** out) {
 void frame_release(sdvlb_ctx* c, sdvlb_frame* f) { c->pool.push_back(f); }
 
 // ---- timing helpers
-void timer_begin(sdvlb_ctx* c, int kind, cudaStream_t stream = nullptr) {
+void timer_begin(sdvlb_ctx* c, int kind, cudaStream_t stream) {
   if (!c->timing) return;
   if (!stream) stream = c->stream;
   c->timer_stream = stream;
@@ -335,6 +232,11 @@ void finalize_build(sdvlb_ctx* c, sdvlb_frame* f) {
   f->build_pending = false;
 }
 
+int wait_frame_built(sdvlb_ctx* c, const sdvlb_frame* f, cudaStream_t stream) {
+  if (f->build_pending) SDVLB_CUDA_TRY(cudaStreamWaitEvent(stream, f->built, 0));
+  return 0;
+}
+
 int ensure_built(sdvlb_frame* f) {
   if (!f->build_pending) return 0;
   SDVLB_CUDA_TRY(cudaSetDevice(f->ctx->device));
@@ -399,7 +301,7 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
 int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_iter* trace, int trace_cap,
                  int* trace_n, const sdvlb_gn_forced* forced, bool build_frames, int fast = 0) {
   SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-  if (c->pending.active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
+  if (c->pending.active || c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
   const PyrGeom& g = c->geom;
 
   int n_detect = 0, n_align = 0, n_cands = 0, n_feats = 0, nfeatures = -1;
@@ -590,25 +492,32 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
   return 0;
 }
 
+// Spins on the pinned completion word; falls back to the driver now and then so that device errors surface.
+int wait_signal(sdvlb_ctx* c) {
+  volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(c->h_overflow) + 16;
+  uint64_t spins = 0;
+  while (*done != c->track_seq) {
+    if ((++spins & 0xFFFFF) == 0) {
+      SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+      const cudaError_t e = cudaStreamQuery(c->stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) return sdvlb_set_cuda_error(e, "cudaStreamQuery", __FILE__, __LINE__);
+      if (e == cudaSuccess && *done != c->track_seq)
+        return sdvlb_set_error(SDVLB_ERR_CUDA, "tracking stream drained without publishing its completion word");
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  return 0;
+}
+
 int collect_batch(sdvlb_ctx* c) {
   PendingTrack& P = c->pending;
   if (!P.active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
   P.active = false;
-  {   // spin on the pinned completion word; fall back to the driver now and then so that device errors surface
-    volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(c->h_overflow) + 16;
-    uint64_t spins = 0;
-    while (*done != c->track_seq) {
-      if ((++spins & 0xFFFFF) == 0) {
-        SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-        const cudaError_t e = cudaStreamQuery(c->stream);
-        if (e != cudaSuccess && e != cudaErrorNotReady) return sdvlb_set_cuda_error(e, "cudaStreamQuery", __FILE__, __LINE__);
-        if (e == cudaSuccess && *done != c->track_seq)
-          return sdvlb_set_error(SDVLB_ERR_CUDA, "tracking stream drained without publishing its completion word");
-      }
-#if defined(__x86_64__)
-      __builtin_ia32_pause();
-#endif
-    }
+  {
+    const int rcw = wait_signal(c);
+    if (rcw) return rcw;
   }
   Arena& out = c->out;
   const int rc = check_overflow(c);
@@ -659,7 +568,9 @@ int check_track_args(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, i
   return 0;
 }
 
-}  // namespace
+}  // namespace sdvlb_detail
+
+using namespace sdvlb_detail;
 
 extern "C" {
 
@@ -729,6 +640,10 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
   cudaFree(c->frame_ticket); cudaFree(c->scratch);
   if (c->h_overflow) cudaFreeHost(c->h_overflow);
+  while (!c->seqs.empty()) sdvlb_seq_destroy(c, c->seqs.back());
+  if (c->seq_in.h) cudaFreeHost(c->seq_in.h);
+  if (c->seq_in.d) cudaFree(c->seq_in.d);
+  cudaFree(c->d_seq_jobs); cudaFree(c->d_seq_frames);
   if (c->in.h) cudaFreeHost(c->in.h);
   if (c->in.d) cudaFree(c->in.d);
   if (c->out.h) cudaFreeHost(c->out.h);

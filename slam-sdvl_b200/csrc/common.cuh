@@ -230,6 +230,62 @@ __host__ __device__ inline DSE3 se3_exp(const double u[6]) {
   return r;
 }
 
+// SE3::Log (extra/se3.cc:96-112,140-164); out = [upsilon; omega]
+__host__ __device__ inline void se3_log(const DSE3& s, double out[6]) {
+  const double SMALL_EPS = 1e-10;
+  const double n = sqrt(s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3);
+  const double w = s.q0;
+  double two_atan_nbyw_by_n;
+  if (n < SMALL_EPS) two_atan_nbyw_by_n = 2. / w - 2. * (n * n) / (w * w * w);
+  else two_atan_nbyw_by_n = 2 * atan(n / w) / n;   // the |w|<eps branch is overwritten in the reference (se3.cc:152-160)
+  const double theta = two_atan_nbyw_by_n * n;
+  const double ox = two_atan_nbyw_by_n * s.q1, oy = two_atan_nbyw_by_n * s.q2, oz = two_atan_nbyw_by_n * s.q3;
+  const double Om[9] = {0, -oz, oy, oz, 0, -ox, -oy, ox, 0};
+  double Om2[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double a = 0;
+      for (int k = 0; k < 3; k++) a += Om[i * 3 + k] * Om[k * 3 + j];
+      Om2[i * 3 + j] = a;
+    }
+  const double c = (theta < SMALL_EPS) ? (1. / 12.) : (1 - theta / (2 * tan(theta / 2))) / (theta * theta);
+  double V[9];
+  for (int i = 0; i < 9; i++) V[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * Om[i] + c * Om2[i];
+  mat3_mul_vec(V, s.tx, s.ty, s.tz, out[0], out[1], out[2]);
+  out[3] = ox; out[4] = oy; out[5] = oz;
+}
+
+// Camera::Unproject (camera.cc:74-79): unit bearing of a pixel
+__host__ __device__ inline void cam_unproject_unit(const sdvlb_camera& c, double u, double v, double out[3]) {
+  const double x = (u - c.u0) / c.fx, y = (v - c.v0) / c.fy, z = 1.0;
+  const double n = sqrt(x * x + y * y + z * z);
+  out[0] = x / n; out[1] = y / n; out[2] = z / n;
+}
+
+// glibc rand() (random_r TYPE_3, 31-word additive feedback) as an explicit state: the reference draws from the
+// process-wide rand() (feature_align.cc:53,103,180); every FeatureAlign here owns one stream seeded like srand(1).
+__host__ __device__ inline void rand_seed(sdvlb_rand* s, unsigned seed) {   // srandom_r
+  if (seed == 0) seed = 1;
+  int32_t init[34];
+  init[0] = int32_t(seed);
+  for (int i = 1; i < 31; i++) {
+    const long long hi = init[i - 1] / 127773, lo = init[i - 1] % 127773;
+    long long word = 16807 * lo - 2836 * hi;
+    if (word < 0) word += 2147483647;
+    init[i] = int32_t(word);
+  }
+  for (int i = 31; i < 34; i++) init[i] = init[i - 31];
+  for (int i = 0; i < 34; i++) s->r[i] = uint32_t(init[i]);
+  s->n = 34;
+  for (int i = 34; i < 344; i++) { s->r[s->n % 34] = s->r[(s->n - 31) % 34] + s->r[(s->n - 3) % 34]; s->n++; }
+}
+__host__ __device__ inline int rand_next(sdvlb_rand* s) {
+  const uint32_t v = s->r[(s->n - 31) % 34] + s->r[(s->n - 3) % 34];
+  s->r[s->n % 34] = v;
+  s->n = s->n >= 34 * 1000000 ? s->n - 34 * 999999 : s->n + 1;   // keep the counter bounded, same position mod 34
+  return int(v >> 1);
+}
+
 // Unpivoted LDL^T solve of a symmetric positive definite 6x6 system held entirely in registers (every loop has a
 // compile-time trip count).  Returns false -- leaving x untouched -- when a pivot is not safely positive; the caller
 // then uses ldlt_solve6 below, which reproduces Eigen's pivoted LDLT including its handling of singular systems.  For a

@@ -7,6 +7,7 @@
 // pixels are spread over the lanes; the LK normal equations are reduced with xor-butterfly shuffles (every lane ends
 // with the same bits).  Ties in ZMSSD resolve to the lowest corner index, as the reference's in-order scan does.
 #include "common.cuh"
+#include "seq.cuh"
 
 namespace {
 
@@ -53,19 +54,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchCandDev* __restrict__ cands,
-                                                                   const FrameDev* __restrict__ frames,
-                                                                   sdvlb_match* __restrict__ out,
-                                                                   const __grid_constant__ SearchArgs A) {
-  __shared__ uint8_t s_bp[SE_WARPS][104];
-  __shared__ uint8_t s_patch[SE_WARPS][64];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ci = blockIdx.x * SE_WARPS + warp;
-  if (ci >= A.n) return;
-  const SearchCandDev& C = cands[ci];
-  const sdvlb_params& P = A.dp.p;
-  const sdvlb_camera& cam = A.dp.cam;
-  const FrameDev cur = frames[C.cur_index];
+// One Matcher::SearchPoint by one warp.  s_bp / s_patch: this warp's 10x10 border patch and 8x8 patch in shared memory.
+__device__ __forceinline__ void search_one(const SearchCandDev& C, const FrameDev& cur, sdvlb_match* __restrict__ out_m,
+                                           const PyrGeom& G, const DevParams& dp, uint8_t* s_bp_w, uint8_t* s_patch_w) {
+  const int lane = threadIdx.x & 31;
+  const sdvlb_params& P = dp.p;
+  const sdvlb_camera& cam = dp.cam;
   const int ps = 8, half = 4;
 
   sdvlb_match m;
@@ -151,8 +145,8 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
   }
 
   if (alive) {                                          // CreatePatch (matcher.cc:325-357)
-    const int W = A.g.w[level], Hh = A.g.h[level];
-    const uint8_t* __restrict__ img = C.ref_pyr + A.g.off[level];
+    const int W = G.w[level], Hh = G.h[level];
+    const uint8_t* __restrict__ img = C.ref_pyr + G.off[level];
     const double pyrx = C.ref_px[0] / double(1 << level), pyry = C.ref_px[1] / double(1 << level);
     for (int i = lane; i < 100; i += 32) {
       const int y = i / 10, x = i - y * 10;
@@ -162,8 +156,8 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
       const double q1 = Ai10 * ppx + Ai11 * ppy + pyry;
       uint8_t val = 0;
       if (!(q0 < 0 || q1 < 0 || q0 >= W - 1 || q1 >= Hh - 1) && finite2(q0, q1)) val = interp8u(img, W, float(q0), float(q1));
-      s_bp[warp][i] = val;
-      if (y >= 1 && y < 9 && x >= 1 && x < 9) s_patch[warp][(y - 1) * 8 + (x - 1)] = val;
+      s_bp_w[i] = val;
+      if (y >= 1 && y < 9 && x >= 1 && x < 9) s_patch_w[(y - 1) * 8 + (x - 1)] = val;
     }
   }
   __syncwarp();
@@ -189,14 +183,14 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
       vline = xdiff * xdiff + ydiff * ydiff;
     }
     // GetZMSSDScore (matcher.cc:447-457): template sums, two pixels per lane
-    const int ta0 = s_patch[warp][lane], ta1 = s_patch[warp][lane + 32];
+    const int ta0 = s_patch_w[lane], ta1 = s_patch_w[lane + 32];
     const int sumA = int(__reduce_add_sync(0xffffffffu, unsigned(ta0 + ta1)));
     const int sumAA = int(__reduce_add_sync(0xffffffffu, unsigned(ta0 * ta0 + ta1 * ta1)));
     const int nc = *cur.n_corners;
     // GetCornersInRange scans every corner of the frame (matcher.cc:123-230); only corners within `range` of the
     // predicted position (fixed points) or of the epipolar segment can pass, so only the 32-px index cells that
     // overlap that region are visited.  The exact test below is the reference's.
-    const int gw = A.g.wcells[0], gh = A.g.hcells[0];
+    const int gw = G.wcells[0], gh = G.hcells[0];
     const int32_t* __restrict__ g_start = cur.grid;
     const int32_t* __restrict__ g_item = cur.grid + 2 * gw * gh + 1;
     double bx0, bx1, by0, by1;
@@ -225,7 +219,7 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
           const int4 cc = __ldg(cur.corners + idx);
           cx = cc.x; cy = cc.y; cl = cc.z;
           in = idx < nc && abs(cl - level) <= 1 && !(cx - margin < 0 || cy - margin < 0) &&
-               !(cy + margin >= A.g.h[cl] || cx + margin >= A.g.w[cl]);
+               !(cy + margin >= G.h[cl] || cx + margin >= G.w[cl]);
           if (in) {
             const double posx = double(cx * (1 << cl)), posy = double(cy * (1 << cl));
             if (fixed) {
@@ -250,11 +244,11 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
           todo &= todo - 1;
           const int bcx = __shfl_sync(0xffffffffu, cx, src), bcy = __shfl_sync(0xffffffffu, cy, src);
           const int bcl = __shfl_sync(0xffffffffu, cl, src), bidx = __shfl_sync(0xffffffffu, idx, src);
-          const int Wc = A.g.w[bcl];
+          const int Wc = G.w[bcl];
           const int py = lane >> 2, pxx = (lane & 3) * 2;
-          const uint8_t* __restrict__ cp = cur.pyr + A.g.off[bcl] + size_t(bcy - half + py) * Wc + (bcx - half + pxx);
+          const uint8_t* __restrict__ cp = cur.pyr + G.off[bcl] + size_t(bcy - half + py) * Wc + (bcx - half + pxx);
           const int b0 = __ldg(cp), b1 = __ldg(cp + 1);
-          const int a0 = s_patch[warp][py * 8 + pxx], a1 = s_patch[warp][py * 8 + pxx + 1];
+          const int a0 = s_patch_w[py * 8 + pxx], a1 = s_patch_w[py * 8 + pxx + 1];
           const int sB = int(__reduce_add_sync(0xffffffffu, unsigned(b0 + b1)));
           const int sBB = int(__reduce_add_sync(0xffffffffu, unsigned(b0 * b0 + b1 * b1)));
           const int sAB = int(__reduce_add_sync(0xffffffffu, unsigned(a0 * b0 + a1 * b1)));
@@ -277,18 +271,18 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
     const int4 bc = __ldg(cur.corners + bidx);
     const int bl = bc.z;
     const double bx = double(bc.x * (1 << bl)), by = double(bc.y * (1 << bl));
-    const int W = A.g.w[slevel], Hh = A.g.h[slevel];
-    const uint8_t* __restrict__ img = cur.pyr + A.g.off[slevel];
+    const int W = G.w[slevel], Hh = G.h[slevel];
+    const uint8_t* __restrict__ img = cur.pyr + G.off[slevel];
     // template gradients; each lane owns pixels lane and lane+32
     float gdx[2], gdy[2], tp[2];
     float h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       const int i = lane + 32 * k, y = i >> 3, x = i & 7;
-      const uint8_t* it = &s_bp[warp][(y + 1) * 10 + x + 1];
+      const uint8_t* it = &s_bp_w[(y + 1) * 10 + x + 1];
       gdx[k] = float(0.5 * double(int(it[1]) - int(it[-1])));
       gdy[k] = float(0.5 * double(int(it[10]) - int(it[-10])));
-      tp[k] = float(s_patch[warp][i]);
+      tp[k] = float(s_patch_w[i]);
       h00 += gdx[k] * gdx[k]; h01 += gdx[k] * gdy[k]; h02 += gdx[k];
       h11 += gdy[k] * gdy[k]; h12 += gdy[k];
     }
@@ -354,7 +348,33 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
       m.level = slevel;
     }
   }
-  if (lane == 0) out[ci] = m;
+  if (lane == 0) *out_m = m;
+}
+
+__global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchCandDev* __restrict__ cands,
+                                                                   const FrameDev* __restrict__ frames,
+                                                                   sdvlb_match* __restrict__ out,
+                                                                   const __grid_constant__ SearchArgs A) {
+  __shared__ uint8_t s_bp[SE_WARPS][104];
+  __shared__ uint8_t s_patch[SE_WARPS][64];
+  const int warp = threadIdx.x >> 5;
+  const int ci = blockIdx.x * SE_WARPS + warp;
+  if (ci >= A.n) return;
+  const SearchCandDev& C = cands[ci];
+  const FrameDev cur = frames[C.cur_index];
+  search_one(C, cur, out + ci, A.g, A.dp, s_bp[warp], s_patch[warp]);
+}
+
+// Resident sequences: blockIdx.y = sequence of the step; candidates, their count and the matches live in the
+// sequence's own device state (written by seq_prep_kernel).
+__global__ void __launch_bounds__(SE_THREADS) search_seq_kernel(const __grid_constant__ SeqStepArgs A) {
+  __shared__ uint8_t s_bp[SE_WARPS][104];
+  __shared__ uint8_t s_patch[SE_WARPS][64];
+  const int warp = threadIdx.x >> 5;
+  const SeqState* S = A.seq[blockIdx.y];
+  const int ci = blockIdx.x * SE_WARPS + warp;
+  if (ci >= S->n_cands) return;
+  search_one(S->cands[ci], A.cur[blockIdx.y], S->matches + ci, A.g, A.dp, s_bp[warp], s_patch[warp]);
 }
 
 // Completion signal of a tracking submission: the stream reaches this 1-thread kernel after ImageAlign and SearchPoint
@@ -380,5 +400,11 @@ cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const Frame
   A.dp = dp;
   A.n = n;
   search_points_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, d_frames, d_out, A);
+  return cudaGetLastError();
+}
+
+cudaError_t sdvlb_launch_search_seq(const SeqStepArgs& A, cudaStream_t stream) {
+  const dim3 grid((A.max_feats + SE_WARPS - 1) / SE_WARPS, A.n);
+  search_seq_kernel<<<grid, SE_THREADS, 0, stream>>>(A);
   return cudaGetLastError();
 }

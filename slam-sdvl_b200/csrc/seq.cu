@@ -1,0 +1,812 @@
+// seq.cu — resident sequences: everything SDVL::ProcessFrame does around ImageAlign and SearchPoint, on the device.
+//
+//   seq_apply_kernel : host commands (restart a track, append the mapping thread's new points to the current frame)
+//   seq_prep_kernel  : SetMotionModel (sdvl.cc:278-281), ImageAlign feature marshalling (image_align.cc:154-160,
+//                      229-235), FeatureAlign::ProjectPoints candidate list (feature_align.cc:296-321)
+//   [image_align_kernel, search_points_kernel: align.cu / search.cu]
+//   seq_post_kernel  : FeatureAlign::ProjectPoint binning + SelectPoints (feature_align.cc:88-150,323-339),
+//                      SelectInliers (RANSAC, :152-216), OptimizePose / RescueOutliers / RemoveOutliers (:73-82,
+//                      :218-256), ConvergePose (:341-421), GetMotionModel (sdvl.cc:266-276); writes the sequence's
+//                      next feature list and its pinned host result
+//   pose_call_kernel : SelectInliers / OptimizePose alone (sdvlb_select_inliers, sdvlb_optimize_pose)
+//
+// One CTA per sequence.  SelectPoints is order-exact without walking the reference's per-cell std::list: the reference
+// visits the 32-px cells in cell_order_ order, inside a cell the points by descending Point::Score() (stable), stops a
+// cell at its first match and everything at max_matches matches.  Here every candidate gets its rank inside its cell
+// (score desc, candidate index asc), a cell's match is its lowest-ranked found candidate, a prefix sum over the cells in
+// cell_order_ gives both the max_matches cut-off and each match's index in fs_found.  RANSAC evaluates all
+// max_ransac_its hypotheses at once (one thread each, 5-point Gauss-Newton in registers), then one thread replays the
+// reference's adaptive iteration count over the results, so the same hypothesis wins and rand() advances by exactly the
+// number of draws the reference makes.  The next frame's random_shuffle of cell_order_ (the only other rand() consumer)
+// runs on a ninth warp while the other eight refine the pose.
+#include <climits>
+
+#include "seq.cuh"
+
+namespace {
+
+constexpr int PO_MAIN = 256;      // threads doing the FeatureAlign work (named barrier 1)
+constexpr int PO_THREADS = 288;   // + the shuffle warp
+constexpr int NVP = 28;           // A (21, upper triangle) + b (6) + chi2
+constexpr int RANSAC_MAX_PTS = 8;
+constexpr int HYP_MAX = PO_MAIN;
+constexpr int MAX_CELLS = 4096;   // 2048 x 2048 / 32^2
+
+constexpr double KMADNorm = 1.4826;            // feature_align.h
+constexpr double KTukeyC = 4.6851 * 4.6851;
+
+__device__ __forceinline__ void main_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ double tukey(double x) {   // feature_align.cc:423-431
+  const double x_square = x * x;
+  if (x_square <= KTukeyC) {
+    const double tmp = 1.0 - x_square / KTukeyC;
+    return tmp * tmp;
+  }
+  return 0.0;
+}
+
+__device__ __forceinline__ void store_Rt(const DSE3& T, double* Rt) {
+  double R[9];
+  se3_rot(T, R);
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rt[i] = R[i];
+  Rt[9] = T.tx; Rt[10] = T.ty; Rt[11] = T.tz;
+}
+
+// error = (SimpleProject(v) - SimpleProject(se3 * pos)) * 2^-level (feature_align.cc:269-273)
+__device__ __forceinline__ void reproj(const double* __restrict__ Rt, double a0, double a1, double X, double Y, double Z,
+                                       double s, double& x, double& y, double& z, double& ex, double& ey) {
+  x = Rt[0] * X + Rt[1] * Y + Rt[2] * Z + Rt[9];
+  y = Rt[3] * X + Rt[4] * Y + Rt[5] * Z + Rt[10];
+  z = Rt[6] * X + Rt[7] * Y + Rt[8] * Z + Rt[11];
+  ex = (a0 - x / z) * s;
+  ey = (a1 - y / z) * s;
+}
+
+// One observation's contribution to A, b, chi2 (feature_align.cc:389-398)
+__device__ __forceinline__ void accumulate_obs(const double* __restrict__ Rt, const PoseProblem& P, int i, double scale,
+                                               double acc[NVP]) {
+  double x, y, z, ex, ey;
+  const double s = P.o_scale[i];
+  reproj(Rt, P.o_a[2 * i], P.o_a[2 * i + 1], P.o_pos[3 * i], P.o_pos[3 * i + 1], P.o_pos[3 * i + 2], s, x, y, z, ex, ey);
+  double J0[6], J1[6];
+  jacobian3d_to_plane(x, y, z, J0, J1);
+#pragma unroll
+  for (int r = 0; r < 6; r++) { J0[r] *= s; J1[r] *= s; }
+  const double w = tukey(sqrt(ex * ex + ey * ey) / scale);
+  int k = 0;
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+#pragma unroll
+    for (int q = r; q < 6; q++) { acc[k] += (J0[r] * J0[q] + J1[r] * J1[q]) * w; k++; }
+    acc[21 + r] -= (J0[r] * ex + J1[r] * ey) * w;
+  }
+  acc[27] += (ex * ex + ey * ey) * w;
+}
+
+// A.ldlt().solve(b): register LDL^T when A is safely positive definite, Eigen's pivoted algorithm otherwise
+__device__ __forceinline__ void solve6(const double acc[NVP], double x[6]) {
+  double Hm[6][6], b[6];
+  int k = 0;
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int q = r; q < 6; q++) { Hm[r][q] = acc[k]; Hm[q][r] = acc[k]; k++; }
+#pragma unroll
+  for (int r = 0; r < 6; r++) b[r] = acc[21 + r];
+  if (!ldlt_solve6_spd(Hm, b, x)) {
+    double H[36];
+    for (int r = 0; r < 6; r++)
+      for (int q = 0; q < 6; q++) H[r * 6 + q] = Hm[r][q];
+    ldlt_solve6(H, b, x);
+  }
+}
+
+struct PoseShared {
+  double red[NVP];
+  double T[7];        // *se3 of ConvergePose
+  double Rt[12];
+  double scale;
+  int ctrl[4];        // [0] continue, [1] number of selected observations
+};
+
+// FeatureAlign::ConvergePose (feature_align.cc:341-421) over the observations whose flag == sel, by the 256 main
+// threads.  The result is left in sh.T; returns false (uniformly) when no observation is selected.
+__device__ bool converge_pose_cta(const PoseProblem& P, int sel, const double* T_init, const DevParams& dp,
+                                  PoseShared& sh, double (*part)[PO_MAIN]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  DSE3 T, last_T;
+  double chi2 = 0.0;
+  if (tid == 0) {
+    T = se3_load(T_init);
+    last_T = T;
+    se3_store(T, sh.T);
+    store_Rt(T, sh.Rt);
+    sh.ctrl[1] = 0;
+    sh.scale = 0.0;
+  }
+  main_sync();
+  int cnt = 0;
+  for (int i = tid; i < P.n; i += PO_MAIN) {
+    double e = -1.0;
+    if (P.o_flag[i] == sel) {
+      double x, y, z, ex, ey;
+      reproj(sh.Rt, P.o_a[2 * i], P.o_a[2 * i + 1], P.o_pos[3 * i], P.o_pos[3 * i + 1], P.o_pos[3 * i + 2], P.o_scale[i],
+             x, y, z, ex, ey);
+      e = sqrt(ex * ex + ey * ey);
+      cnt++;
+    }
+    P.o_err[i] = e;
+  }
+  if (cnt) atomicAdd(&sh.ctrl[1], cnt);
+  main_sync();
+  const int m = sh.ctrl[1];
+  if (m == 0) return false;
+  // GetMedianVector (utils.cc:215-220): nth_element at size/2 == the value of rank size/2
+  const int mid = m / 2;
+  for (int i = tid; i < P.n; i += PO_MAIN) {
+    const double e = P.o_err[i];
+    if (!(e >= 0.0)) continue;
+    int rank = 0;
+    for (int j = 0; j < P.n; j++) {
+      const double ej = P.o_err[j];
+      rank += (ej >= 0.0 && (ej < e || (ej == e && j < i))) ? 1 : 0;
+    }
+    if (rank == mid) sh.scale = KMADNorm * e;
+  }
+  main_sync();
+
+  const int max_its = dp.p.max_optim_pose_its;
+  for (int it = 0; it < max_its; it++) {
+    const double scale = it >= 5 ? 0.85 / dp.cam.fx : sh.scale;   // "force estimator after 5th iteration"
+    double acc[NVP];
+#pragma unroll
+    for (int k = 0; k < NVP; k++) acc[k] = 0.0;
+    for (int i = tid; i < P.n; i += PO_MAIN)
+      if (P.o_flag[i] == sel) accumulate_obs(sh.Rt, P, i, scale, acc);
+#pragma unroll
+    for (int k = 0; k < NVP; k++) part[k][tid] = acc[k];
+    main_sync();
+    for (int v = warp; v < NVP; v += PO_MAIN / 32) {   // fixed-order tree
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < PO_MAIN / 32; k++) s += part[v][lane + 32 * k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) sh.red[v] = s;
+    }
+    main_sync();
+    if (tid == 0) {
+      double dT[6], a[NVP];
+#pragma unroll
+      for (int k = 0; k < NVP; k++) a[k] = sh.red[k];
+      solve6(a, dT);
+      const double new_chi2 = a[27];
+      int cont = 1;
+      if ((it > 0 && new_chi2 > chi2) || isnan(dT[0])) {
+        T = last_T;   // roll-back
+        cont = 0;
+      } else {
+        const DSE3 T_new = se3_mul(se3_exp(dT), T);
+        last_T = T;
+        T = T_new;
+        chi2 = new_chi2;
+        double amax = -1;
+#pragma unroll
+        for (int r = 0; r < 6; r++) amax = fmax(amax, fabs(dT[r]));
+        if (amax <= 1e-10) cont = 0;
+      }
+      se3_store(T, sh.T);
+      store_Rt(T, sh.Rt);
+      sh.ctrl[0] = cont;
+    }
+    main_sync();
+    if (!sh.ctrl[0]) break;
+  }
+  return true;
+}
+
+// ConvergePose for one RANSAC hypothesis (np <= 8 observations (base + k) % size), entirely by one thread.
+__device__ bool converge_pose_small(const PoseProblem& P, int base, int np, int size, const DSE3& T0, const DevParams& dp,
+                                    DSE3* out) {
+  DSE3 T = T0, last_T = T0;
+  double chi2 = 0.0;
+  double Rt[12];
+  store_Rt(T, Rt);
+  if (np <= 0) return false;
+  double e[RANSAC_MAX_PTS];
+#pragma unroll
+  for (int k = 0; k < RANSAC_MAX_PTS; k++) {
+    e[k] = -1.0;
+    if (k < np) {
+      const int i = (base + k) % size;
+      double x, y, z, ex, ey;
+      reproj(Rt, P.o_a[2 * i], P.o_a[2 * i + 1], P.o_pos[3 * i], P.o_pos[3 * i + 1], P.o_pos[3 * i + 2], P.o_scale[i],
+             x, y, z, ex, ey);
+      e[k] = sqrt(ex * ex + ey * ey);
+    }
+  }
+  double med = 0.0;
+  const int mid = np / 2;
+#pragma unroll
+  for (int k = 0; k < RANSAC_MAX_PTS; k++) {
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < RANSAC_MAX_PTS; j++) rank += (j < np && (e[j] < e[k] || (e[j] == e[k] && j < k))) ? 1 : 0;
+    if (k < np && rank == mid) med = e[k];
+  }
+  const double scale0 = KMADNorm * med;
+  const int max_its = dp.p.max_optim_pose_its;
+  for (int it = 0; it < max_its; it++) {
+    const double scale = it >= 5 ? 0.85 / dp.cam.fx : scale0;
+    double acc[NVP];
+#pragma unroll
+    for (int k = 0; k < NVP; k++) acc[k] = 0.0;
+    for (int k = 0; k < np; k++) accumulate_obs(Rt, P, (base + k) % size, scale, acc);
+    double dT[6];
+    solve6(acc, dT);
+    const double new_chi2 = acc[27];
+    if ((it > 0 && new_chi2 > chi2) || isnan(dT[0])) {
+      T = last_T;
+      break;
+    }
+    const DSE3 T_new = se3_mul(se3_exp(dT), T);
+    last_T = T;
+    T = T_new;
+    chi2 = new_chi2;
+    store_Rt(T, Rt);
+    double amax = -1;
+#pragma unroll
+    for (int r = 0; r < 6; r++) amax = fmax(amax, fabs(dT[r]));
+    if (amax <= 1e-10) break;
+  }
+  *out = T;
+  return true;
+}
+
+struct RansacShared {
+  double hRt[HYP_MAX][12];   // pose of every hypothesis as rotation + translation
+  int hsup[HYP_MAX];         // supporters
+  int hconv[HYP_MAX];        // ConvergePose returned true
+  int rnd[HYP_MAX];
+  int best, draws;
+};
+
+// FeatureAlign::SelectInliers (feature_align.cc:152-216) over P (= fs_found): flags every observation INLIER/OUTLIER.
+// T_frame: frame->GetPose().  *rng advances by the reference's number of rand() calls.  Main threads only.
+__device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, const DevParams& dp, sdvlb_rand* rng,
+                                   RansacShared& rs) {
+  const int tid = threadIdx.x;
+  const int size = P.n;
+  if (size == 0) return;
+  const int R = min(dp.p.max_ransac_its, HYP_MAX);
+  const int np = min(min(dp.p.max_ransac_points, size), RANSAC_MAX_PTS);
+  const double thr = dp.p.inlier_error_threshold / dp.cam.fx;
+  if (tid == 0) {
+    sdvlb_rand copy = *rng;   // speculative draws; the stream itself advances by `draws` below
+    for (int h = 0; h < R; h++) rs.rnd[h] = rand_next(&copy);
+  }
+  if (tid < R) rs.hsup[tid] = 0;
+  main_sync();
+  if (tid < R) {
+    DSE3 T;
+    const bool ok = converge_pose_small(P, rs.rnd[tid] % size, np, size, se3_load(T_frame), dp, &T);
+    rs.hconv[tid] = ok ? 1 : 0;
+    store_Rt(T, rs.hRt[tid]);
+  }
+  main_sync();
+  // CheckReprojectionError of every hypothesis against every match (feature_align.cc:258-283)
+  for (int p = tid; p < R * size; p += PO_MAIN) {
+    const int h = p / size, i = p - h * size;
+    double x, y, z, ex, ey;
+    reproj(rs.hRt[h], P.o_a[2 * i], P.o_a[2 * i + 1], P.o_pos[3 * i], P.o_pos[3 * i + 1], P.o_pos[3 * i + 2],
+           P.o_scale[i], x, y, z, ex, ey);
+    if (sqrt(ex * ex + ey * ey) <= thr) atomicAdd(&rs.hsup[h], 1);
+  }
+  main_sync();
+  if (tid == 0) {   // the reference's loop, replayed over the precomputed hypotheses
+    const double sprob = 0.99;
+    int nits = dp.p.max_ransac_its, it = 0, best_supporters = 0, best = -1;
+    while (it < nits && it < R) {
+      if (rs.hconv[it] && rs.hsup[it] > best_supporters) {
+        best = it;
+        best_supporters = rs.hsup[it];
+        const double epsilon = 1.0 - (double(best_supporters) / double(size));
+        double tmp = 1.0 - epsilon;
+        for (int k = 1; k < np; k++) tmp *= tmp;
+        if (tmp < 1e-5) nits = dp.p.max_ransac_its;
+        else nits = min(dp.p.max_ransac_its, int(log(1.0 - sprob) / log(1.0 - tmp)));
+      }
+      it++;
+    }
+    rs.best = best;
+    rs.draws = it;
+    for (int k = 0; k < it; k++) rand_next(rng);
+  }
+  main_sync();
+  // "Get low innovation inliers" with best_se3 (identity when no hypothesis ever had a supporter)
+  double Rt[12];
+  if (rs.best >= 0) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) Rt[k] = rs.hRt[rs.best][k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12; k++) Rt[k] = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0;
+  }
+  for (int i = tid; i < size; i += PO_MAIN) {
+    double x, y, z, ex, ey;
+    reproj(Rt, P.o_a[2 * i], P.o_a[2 * i + 1], P.o_pos[3 * i], P.o_pos[3 * i + 1], P.o_pos[3 * i + 2], P.o_scale[i], x, y,
+           z, ex, ey);
+    P.o_flag[i] = sqrt(ex * ex + ey * ey) <= thr ? SDVLB_OBS_INLIER : SDVLB_OBS_OUTLIER;
+  }
+  main_sync();
+}
+
+// Re-partition after a pose change: observations flagged `from` whose error at sh.Rt exceeds / is within thr.
+// Returns (uniformly) how many changed list.
+__device__ int recheck_cta(const PoseProblem& P, const double* Rt, int from, bool move_if_within, double thr, int to,
+                           PoseShared& sh) {
+  const int tid = threadIdx.x;
+  if (tid == 0) sh.ctrl[2] = 0;
+  main_sync();
+  int moved = 0;
+  for (int i = tid; i < P.n; i += PO_MAIN) {
+    if (P.o_flag[i] != from) continue;
+    double x, y, z, ex, ey;
+    reproj(Rt, P.o_a[2 * i], P.o_a[2 * i + 1], P.o_pos[3 * i], P.o_pos[3 * i + 1], P.o_pos[3 * i + 2], P.o_scale[i], x, y,
+           z, ex, ey);
+    const bool within = sqrt(ex * ex + ey * ey) <= thr;
+    if (within == move_if_within) { P.o_flag[i] = to; moved++; }
+  }
+  if (moved) atomicAdd(&sh.ctrl[2], moved);
+  main_sync();
+  return sh.ctrl[2];
+}
+
+// FeatureAlign::OptimizePose(frame) without RemoveOutliers (feature_align.cc:73-82,218-243).  T_frame (shared, 7
+// doubles) holds frame->GetPose() on entry and the refined pose on return.
+__device__ void optimize_pose_cta(const PoseProblem& P, double* T_frame, const DevParams& dp, PoseShared& sh,
+                                  double (*part)[PO_MAIN]) {
+  const int tid = threadIdx.x;
+  const double thr = dp.p.inlier_error_threshold / dp.cam.fx;
+  for (int round = 0; round < 2; round++) {
+    if (converge_pose_cta(P, SDVLB_OBS_INLIER, T_frame, dp, sh, part)) {
+      if (tid < 7) T_frame[tid] = sh.T[tid];   // frame->SetPose(se3)
+      main_sync();
+      recheck_cta(P, sh.Rt, SDVLB_OBS_INLIER, false, thr, SDVLB_OBS_OUTLIER, sh);
+    }
+    if (round == 1) break;
+    // RescueOutliers at the frame pose
+    if (tid == 0) store_Rt(se3_load(T_frame), sh.Rt);
+    main_sync();
+    if (recheck_cta(P, sh.Rt, SDVLB_OBS_OUTLIER, true, 2 * thr, SDVLB_OBS_INLIER, sh) == 0) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ commands
+__global__ void __launch_bounds__(128) seq_apply_kernel(const SeqCmd* __restrict__ cmds, const __grid_constant__ DevParams dp) {
+  const SeqCmd& C = cmds[blockIdx.x];
+  SeqState* S = C.seq;
+  const int tid = threadIdx.x;
+  if (C.kind == 0) {
+    if (tid == 0) {
+      for (int i = 0; i < 7; i++) S->T_last[i] = C.T[i];
+      for (int i = 0; i < 6; i++) S->vel[i] = 0.0;
+      S->last = C.frame;
+      S->has_last = 1;
+      S->n_list = 0;
+      S->n_cands = 0;
+      for (int i = 0; i < 7; i++) C.frame.pose[i] = C.T[i];
+    }
+    return;
+  }
+  // append points to the current list (keyframe seeding / mapping thread output)
+  __shared__ int s_base;
+  if (tid == 0) {
+    s_base = S->n_list;
+    SeqKf& K = S->kf[C.kf_slot];
+    K.pyr = C.kf_pyr;
+    for (int i = 0; i < 7; i++) K.T[i] = C.T[i];
+  }
+  __syncthreads();
+  const int base = s_base;
+  SeqFeat* L = S->list[S->cur];
+  for (int k = tid; k < C.n; k += blockDim.x) {
+    if (base + k >= S->max_feats) break;
+    const sdvlb_seq_point p = C.pts[k];
+    SeqFeat f;
+    f.px[0] = p.cur_px[0]; f.px[1] = p.cur_px[1];
+    cam_unproject_unit(dp.cam, p.cur_px[0], p.cur_px[1], f.v);
+    f.pos[0] = p.pos[0]; f.pos[1] = p.pos[1]; f.pos[2] = p.pos[2];
+    f.ref_px[0] = p.ref_px[0]; f.ref_px[1] = p.ref_px[1];
+    cam_unproject_unit(dp.cam, p.ref_px[0], p.ref_px[1], f.ref_v);
+    f.idepth = p.idepth; f.idepth_std = p.idepth_std;
+    f.user_id = p.user_id;
+    f.level = p.cur_level; f.ref_level = p.ref_level;
+    f.kf = C.kf_slot;
+    f.flags = SEQF_HAS_POINT | ((p.flags & SDVLB_CAND_FIXED) ? SEQF_FIXED : 0);
+    f.n_successful = p.n_successful; f.n_failed = p.n_failed;
+    f.status = SEQP_FOUND;
+    f.n_unpromoted = 0;
+    L[base + k] = f;
+  }
+  __syncthreads();
+  if (tid == 0) S->n_list = min(base + C.n, S->max_feats);
+}
+
+// ------------------------------------------------------------------------------------------------ prep
+__global__ void __launch_bounds__(128) seq_prep_kernel(const __grid_constant__ SeqStepArgs A) {
+  SeqState* S = A.seq[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double s_C[3];
+  __shared__ int s_warp_cnt[4];
+  __shared__ int s_base;
+  AlignJobDev& J = A.jobs[blockIdx.x];
+  const int n = S->has_last ? S->n_list : 0;
+  if (tid == 0) {
+    A.frames[blockIdx.x] = A.cur[blockIdx.x];
+    s_base = 0;
+    const DSE3 T_last = se3_load(S->T_last);
+    const DSE3 Twc = se3_inverse(T_last);   // Frame::GetWorldPosition (frame.h)
+    s_C[0] = Twc.tx; s_C[1] = Twc.ty; s_C[2] = Twc.tz;
+    const DSE3 prior = se3_mul(se3_exp(S->vel), T_last);   // SDVL::SetMotionModel (sdvl.cc:278-281)
+    J.ref = S->last;
+    J.cur = A.cur[blockIdx.x];
+    J.feats = S->afeat;
+    J.n = S->has_last ? n : -1;
+    J.fast = 0;
+    for (int i = 0; i < 7; i++) J.T_ref[i] = S->T_last[i];
+    se3_store(prior, J.T_cur);
+    J.out_pose = S->align_pose;
+    J.out_info = S->align_info;
+    J.out_error = &S->align_error;
+    J.trace = nullptr; J.trace_cap = 0; J.forced_n = 0; J.forced_T = nullptr; J.forced_iters = nullptr;
+    const size_t nn = size_t(A.max_feats);
+    uint8_t* sc = S->align_scratch;
+    J.sc_d = reinterpret_cast<double*>(sc);
+    J.sc_f = reinterpret_cast<float*>(sc + nn * 18 * 8);
+    J.sc_flags = reinterpret_cast<int32_t*>(sc + nn * 18 * 8 + nn * 48 * 4);
+    S->align_info[0] = 0; S->align_info[1] = 0;
+    if (n == 0) {   // ImageAlign::ComputePose returns at once (image_align.cc:55-58); frame2 keeps the prior
+      se3_store(prior, S->align_pose);
+      se3_store(prior, A.cur[blockIdx.x].pose);
+    }
+  }
+  __syncthreads();
+  const SeqFeat* __restrict__ L = S->list[S->cur];
+  // ImageAlign features: every feature of the last frame; candidates: the ones that still observe a point
+  for (int b = 0; b < n; b += blockDim.x) {
+    const int f = b + tid;
+    bool valid = false;
+    SeqFeat ft;
+    if (f < n) {
+      ft = L[f];
+      valid = (ft.flags & SEQF_HAS_POINT) != 0;
+      sdvlb_align_feat a;
+      a.px[0] = ft.px[0]; a.px[1] = ft.px[1];
+      a.v[0] = ft.v[0]; a.v[1] = ft.v[1]; a.v[2] = ft.v[2];
+      const double dx = ft.pos[0] - s_C[0], dy = ft.pos[1] - s_C[1], dz = ft.pos[2] - s_C[2];
+      a.depth = valid ? sqrt(dx * dx + dy * dy + dz * dz) : 1.0;   // image_align.cc:159,234
+      a.valid = valid ? 1 : 0;
+      a.pad_ = 0;
+      S->afeat[f] = a;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; w++) off += s_warp_cnt[w];
+    if (valid) {
+      const int ci = off + __popc(bal & ((1u << lane) - 1));
+      SearchCandDev c;
+      const SeqKf& K = S->kf[ft.kf];
+      c.ref_pyr = K.pyr;
+#pragma unroll
+      for (int i = 0; i < 7; i++) c.ref_T[i] = K.T[i];
+      c.ref_px[0] = ft.ref_px[0]; c.ref_px[1] = ft.ref_px[1];
+      c.ref_v[0] = ft.ref_v[0]; c.ref_v[1] = ft.ref_v[1]; c.ref_v[2] = ft.ref_v[2];
+      c.idepth = ft.idepth; c.idepth_std = ft.idepth_std;
+      c.px[0] = 0.0; c.px[1] = 0.0;
+      c.pos[0] = ft.pos[0]; c.pos[1] = ft.pos[1]; c.pos[2] = ft.pos[2];
+      c.ref_level = ft.ref_level;
+      c.flags = SDVLB_CAND_PROJECT | ((ft.flags & SEQF_FIXED) ? SDVLB_CAND_FIXED : 0);
+      c.cur_index = blockIdx.x;
+      c.pad_ = 0;
+      S->cands[ci] = c;
+      S->cand_feat[ci] = f;
+    }
+    __syncthreads();
+    if (tid == 0) { for (int w = 0; w < 4; w++) s_base += s_warp_cnt[w]; }
+    __syncthreads();
+  }
+  if (tid == 0) S->n_cands = s_base;
+}
+
+// ------------------------------------------------------------------------------------------------ post
+struct PostShared {
+  PoseShared ps;
+  RansacShared rs;
+  double T_frame[7];
+  sdvlb_rand rng;
+  int win[MAX_CELLS];          // per cell: rank of its match (INT_MAX: none)
+  int slot[MAX_CELLS];         // per cell: index of its match in fs_found, -1: cell not visited / no match
+  int order[MAX_CELLS];        // cell_order_
+  int scan[PO_MAIN];
+  int attempts, n_found, n_inl, n_outl;
+  int kf_live[SDVLB_SEQ_KF_CAP];
+};
+
+__global__ void __launch_bounds__(PO_THREADS) seq_post_kernel(const __grid_constant__ SeqStepArgs A) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  PostShared& sh = *reinterpret_cast<PostShared*>(s_raw);
+  double (*part)[PO_MAIN] = reinterpret_cast<double (*)[PO_MAIN]>(s_raw + ((sizeof(PostShared) + 15) / 16) * 16);
+  SeqState* S = A.seq[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int n_cells = S->n_cells;
+  const int gw = A.g.wcells[0];
+  if (!S->has_last) return;   // uniform: nothing was tracked (no reset yet)
+
+  // ---- load the persistent FeatureAlign state (all 288 threads)
+  for (int i = tid; i < n_cells; i += PO_THREADS) { sh.order[i] = S->cell_order[i]; sh.win[i] = INT_MAX; sh.slot[i] = -1; }
+  if (tid < 34) sh.rng.r[tid] = S->rng.r[tid];
+  if (tid == 0) {
+    sh.rng.n = S->rng.n;
+    sh.attempts = 0; sh.n_found = 0; sh.n_inl = 0; sh.n_outl = 0;
+    for (int i = 0; i < 7; i++) sh.T_frame[i] = A.cur[blockIdx.x].pose[i];   // ImageAlign's result
+  }
+  if (tid < SDVLB_SEQ_KF_CAP) sh.kf_live[tid] = 0;
+  __syncthreads();
+
+  if (tid >= PO_MAIN) {
+    // ---- shuffle warp: std::random_shuffle(cell_order_) for the NEXT frame (feature_align.cc:103), once SelectInliers
+    // has taken its draws.  Waits on barrier 2 (all 288 threads).
+    asm volatile("bar.sync 2, 288;" ::: "memory");
+    if (tid == PO_MAIN) {
+      for (int i = 1; i < n_cells; ++i) {
+        const int j = rand_next(&sh.rng) % (i + 1);
+        const int a = sh.order[i], b = sh.order[j];
+        sh.order[i] = b; sh.order[j] = a;
+      }
+    }
+    __syncwarp();
+    const int lane = tid - PO_MAIN;
+    for (int i = lane; i < n_cells; i += 32) S->cell_order[i] = sh.order[i];
+    for (int i = lane; i < 34; i += 32) S->rng.r[i] = sh.rng.r[i];
+    if (lane == 0) S->rng.n = sh.rng.n;
+    return;
+  }
+
+  // =============================== main threads (barrier 1) ===============================
+  const SeqFeat* __restrict__ L = S->list[S->cur];
+  SeqFeat* __restrict__ NL = S->list[S->cur ^ 1];
+  const int nc = S->n_cands;
+  const sdvlb_match* __restrict__ M = S->matches;
+  int32_t* __restrict__ c_cell = S->c_cell;
+  int32_t* __restrict__ c_score = S->c_score;
+  int32_t* __restrict__ c_rank = S->c_rank;
+
+  // ---- ProjectPoint bookkeeping (feature_align.cc:323-339): cell of every seen point
+  for (int i = tid; i < nc; i += PO_MAIN) {
+    const sdvlb_match m = M[i];
+    int cell = -1;
+    if (m.status != SDVLB_MATCH_UNSEEN) cell = int(m.proj[1] / SDVLB_CELL) * gw + int(m.proj[0] / SDVLB_CELL);
+    if (cell >= n_cells) cell = -1;
+    c_cell[i] = cell;
+    c_score[i] = L[S->cand_feat[i]].n_successful;
+  }
+  main_sync();
+  // ---- rank inside the cell: Score() descending, stable (std::list::sort, feature_align.cc:111)
+  for (int i = tid; i < nc; i += PO_MAIN) {
+    const int cell = c_cell[i];
+    if (cell < 0) { c_rank[i] = -1; continue; }
+    const int sc = c_score[i];
+    int rank = 0;
+    for (int j = 0; j < nc; j++) {
+      const int cj = c_cell[j], sj = c_score[j];
+      rank += (cj == cell && (sj > sc || (sj == sc && j < i))) ? 1 : 0;
+    }
+    c_rank[i] = rank;
+    if (M[i].status == SDVLB_MATCH_FOUND) atomicMin(&sh.win[cell], rank);
+  }
+  main_sync();
+  // ---- cells in cell_order_: exclusive prefix sum of "has a match" -> max_matches cut-off and fs_found index
+  {
+    const int per = (n_cells + PO_MAIN - 1) / PO_MAIN;
+    const int q0 = tid * per, q1 = min(n_cells, q0 + per);
+    int local = 0;
+    for (int q = q0; q < q1; q++) local += sh.win[sh.order[q]] != INT_MAX ? 1 : 0;
+    sh.scan[tid] = local;
+    main_sync();
+    if (tid == 0) {
+      int run = 0;
+      for (int t = 0; t < PO_MAIN; t++) { const int v = sh.scan[t]; sh.scan[t] = run; run += v; }
+      sh.n_found = min(run, A.dp.p.max_matches);
+    }
+    main_sync();
+    int pre = sh.scan[tid];
+    const int max_matches = A.dp.p.max_matches;
+    for (int q = q0; q < q1; q++) {
+      const int c = sh.order[q];
+      const bool has = sh.win[c] != INT_MAX;
+      // the loop `for (i < size && matches_ < max_matches_)` visits this cell iff fewer than max_matches so far
+      if (pre < max_matches) sh.slot[c] = has ? pre : -2;   // -2: visited, no match
+      pre += has ? 1 : 0;
+    }
+  }
+  main_sync();
+  const int n_found = sh.n_found;
+  PoseProblem P;
+  P.o_a = S->o_a; P.o_pos = S->o_pos; P.o_scale = S->o_scale; P.o_err = S->o_err; P.o_flag = S->o_flag;
+  P.n = n_found;
+  // ---- SelectPoints side effects (feature_align.cc:112-147): attempts, Promote / Unpromote, new features
+  {
+    int my_attempts = 0;
+    for (int i = tid; i < nc; i += PO_MAIN) {
+      const int cell = c_cell[i];
+      if (cell < 0) continue;
+      const int slot = sh.slot[cell];
+      if (slot == -1) continue;                       // cell never visited
+      const int rank = c_rank[i], win = sh.win[cell];
+      if (rank > win) continue;                       // the cell was left at its first match
+      my_attempts++;
+      if (rank == win && slot >= 0) {                 // found: Promote, new Feature(frame, px, level)
+        const sdvlb_match m = M[i];
+        SeqFeat f = L[S->cand_feat[i]];
+        f.px[0] = m.px[0]; f.px[1] = m.px[1];
+        cam_unproject_unit(A.dp.cam, m.px[0], m.px[1], f.v);
+        f.level = m.level;
+        f.n_successful += 1; f.n_failed = 0;          // Point::Promote (point.cc:102-106)
+        f.status = SEQP_FOUND;
+        NL[slot] = f;
+        P.o_a[2 * slot] = f.v[0] / f.v[2];            // Camera::SimpleProject(feature->GetVector())
+        P.o_a[2 * slot + 1] = f.v[1] / f.v[2];
+        P.o_pos[3 * slot] = f.pos[0]; P.o_pos[3 * slot + 1] = f.pos[1]; P.o_pos[3 * slot + 2] = f.pos[2];
+        P.o_scale[slot] = 1.0 / double(1 << m.level);
+        P.o_flag[slot] = 0;
+      }
+      // not found: Point::Unpromote / Map::DeletePoint (point.cc:108-115); the point leaves the track either way,
+      // because the next frame's candidates are this frame's features
+    }
+    if (my_attempts) atomicAdd(&sh.attempts, my_attempts);
+  }
+  main_sync();
+
+  // ---- SelectInliers (RANSAC)
+  select_inliers_cta(P, sh.T_frame, A.dp, &sh.rng, sh.rs);
+  asm volatile("bar.sync 2, 288;" ::: "memory");   // releases the shuffle warp: rand() is its from here on
+
+  // ---- OptimizePose + RescueOutliers + OptimizePose (feature_align.cc:73-82)
+  optimize_pose_cta(P, sh.T_frame, A.dp, sh.ps, part);
+  main_sync();
+
+  // ---- RemoveOutliers (feature_align.cc:245-256), result, GetMotionModel, state update
+  SeqResultHost* Rz = S->result;
+  sdvlb_seq_feat* hfe = reinterpret_cast<sdvlb_seq_feat*>(reinterpret_cast<unsigned char*>(Rz) + sizeof(SeqResultHost));
+  {
+    int inl = 0, outl = 0;
+    for (int i = tid; i < n_found; i += PO_MAIN) {
+      const bool is_in = P.o_flag[i] == SDVLB_OBS_INLIER;
+      SeqFeat& f = NL[i];
+      if (is_in) { inl++; atomicAdd(&sh.kf_live[f.kf], 1); }
+      else { outl++; f.flags &= ~SEQF_HAS_POINT; f.status = SEQP_NOT_FOUND; }
+      sdvlb_seq_feat o;
+      o.px[0] = f.px[0]; o.px[1] = f.px[1];
+      o.user_id = f.user_id;
+      o.level = f.level;
+      o.flags = is_in ? SDVLB_FEAT_HAS_POINT : 0;
+      hfe[i] = o;
+    }
+    if (inl) atomicAdd(&sh.n_inl, inl);
+    if (outl) atomicAdd(&sh.n_outl, outl);
+  }
+  main_sync();
+  if (tid < SDVLB_SEQ_KF_CAP) Rz->kf_live[tid] = sh.kf_live[tid];
+  if (tid == 0) {
+    const DSE3 T_new = se3_load(sh.T_frame);
+    const DSE3 mov = se3_mul(T_new, se3_inverse(se3_load(S->T_last)));   // sdvl.cc:266-276
+    double vel[6];
+    se3_log(mov, vel);
+    for (int i = 0; i < 6; i++) S->vel[i] = 0.9 * (0.5 * vel[i] + 0.5 * S->vel[i]);
+    for (int i = 0; i < 7; i++) { S->T_last[i] = sh.T_frame[i]; Rz->pose[i] = sh.T_frame[i]; A.cur[blockIdx.x].pose[i] = sh.T_frame[i]; }
+    S->last = A.cur[blockIdx.x];
+    S->n_list = n_found;
+    S->cur ^= 1;
+    S->frame_id += 1;
+    Rz->stats[0] = S->align_info[0];
+    Rz->stats[1] = n_found;
+    Rz->stats[2] = sh.attempts;
+    Rz->stats[3] = sh.n_inl;
+    Rz->stats[4] = sh.n_outl;
+    Rz->stats[5] = sh.n_inl;        // Frame::GetNumPoints(): features that still have a point
+    Rz->stats[6] = S->align_info[1];
+    Rz->stats[7] = n_found;
+    Rz->error = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ standalone calls
+struct PoseCallShared {
+  PoseShared ps;
+  RansacShared rs;
+  double T_frame[7];
+  sdvlb_rand rng;
+};
+
+__global__ void __launch_bounds__(PO_MAIN) pose_call_kernel(const __grid_constant__ PoseCallArgs A) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  PoseCallShared& sh = *reinterpret_cast<PoseCallShared*>(s_raw);
+  double (*part)[PO_MAIN] = reinterpret_cast<double (*)[PO_MAIN]>(s_raw + ((sizeof(PoseCallShared) + 15) / 16) * 16);
+  const int tid = threadIdx.x;
+  PoseProblem P;
+  P.n = A.n;
+  P.o_a = A.scratch; P.o_pos = A.scratch + 2 * size_t(A.n); P.o_scale = A.scratch + 5 * size_t(A.n);
+  P.o_err = A.scratch + 6 * size_t(A.n);
+  P.o_flag = A.iscratch;
+  for (int i = tid; i < A.n; i += PO_MAIN) {
+    const sdvlb_pose_obs o = A.obs[i];
+    P.o_a[2 * i] = o.v[0] / o.v[2]; P.o_a[2 * i + 1] = o.v[1] / o.v[2];
+    P.o_pos[3 * i] = o.pos[0]; P.o_pos[3 * i + 1] = o.pos[1]; P.o_pos[3 * i + 2] = o.pos[2];
+    P.o_scale[i] = 1.0 / double(1 << o.level);
+    P.o_flag[i] = o.flags;
+  }
+  if (tid < 7) sh.T_frame[tid] = A.T[tid];
+  if (A.mode == 0) {
+    if (tid < 34) sh.rng.r[tid] = A.rng->r[tid];
+    if (tid == 0) sh.rng.n = A.rng->n;
+  }
+  main_sync();
+  if (A.mode == 0) {
+    select_inliers_cta(P, sh.T_frame, A.dp, &sh.rng, sh.rs);
+    if (tid < 34) A.rng->r[tid] = sh.rng.r[tid];
+    if (tid == 0) A.rng->n = sh.rng.n;
+  } else {
+    optimize_pose_cta(P, sh.T_frame, A.dp, sh.ps, part);
+    main_sync();
+    if (tid < 7) A.T[tid] = sh.T_frame[tid];
+  }
+  main_sync();
+  for (int i = tid; i < A.n; i += PO_MAIN) A.obs[i].flags = P.o_flag[i];
+}
+
+template <typename K>
+cudaError_t opt_in_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+}
+
+}  // namespace
+
+cudaError_t sdvlb_launch_seq_apply(const SeqCmd* d_cmds, int n, const DevParams& dp, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  seq_apply_kernel<<<n, 128, 0, stream>>>(d_cmds, dp);
+  return cudaGetLastError();
+}
+
+cudaError_t sdvlb_launch_seq_prep(const SeqStepArgs& A, cudaStream_t stream) {
+  seq_prep_kernel<<<A.n, 128, 0, stream>>>(A);
+  return cudaGetLastError();
+}
+
+cudaError_t sdvlb_launch_seq_post(const SeqStepArgs& A, cudaStream_t stream) {
+  const size_t dyn = ((sizeof(PostShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN;
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = opt_in_smem(seq_post_kernel, dyn);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  seq_post_kernel<<<A.n, PO_THREADS, dyn, stream>>>(A);
+  return cudaGetLastError();
+}
+
+cudaError_t sdvlb_launch_pose_call(const PoseCallArgs& A, cudaStream_t stream) {
+  const size_t dyn = ((sizeof(PoseCallShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN;
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = opt_in_smem(pose_call_kernel, dyn);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  pose_call_kernel<<<1, PO_MAIN, dyn, stream>>>(A);
+  return cudaGetLastError();
+}

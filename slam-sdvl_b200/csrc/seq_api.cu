@@ -1,0 +1,400 @@
+// seq_api.cu — host side of the resident-sequence entry points and of the standalone FeatureAlign pose refinement
+// (include/sdvl_b200.h: sdvlb_seq_*, sdvlb_select_inliers, sdvlb_optimize_pose, sdvlb_rand_*).
+//
+// A tracked frame of n sequences is one submission of five kernels on the context's tracking stream
+// (apply-commands, prep, image_align, search, post) followed by the completion signal; nothing is copied to the device
+// except the mapping thread's commands (new points), and every result lands in pinned host memory by itself.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "capi_internal.h"
+
+using namespace sdvlb_detail;
+
+cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, const PyrGeom& g, const DevParams& dp, cudaStream_t stream);
+cudaError_t sdvlb_launch_signal(uint32_t* h_flag, uint32_t seq, cudaStream_t stream);
+
+namespace {
+
+struct SeqLayout {
+  size_t list[2], cell_order, afeat, cands, cand_feat, matches, align_scratch, c_cell, c_score, c_rank, o_a, o_pos, o_scale,
+      o_err, o_flag, total;
+};
+
+SeqLayout seq_layout(int max_feats, int n_cells) {
+  SeqLayout L;
+  size_t off = align_up(sizeof(SeqState), 256);
+  auto take = [&off](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t n = size_t(max_feats);
+  L.list[0] = take(n * sizeof(SeqFeat));
+  L.list[1] = take(n * sizeof(SeqFeat));
+  L.cell_order = take(size_t(n_cells) * sizeof(int32_t));
+  L.afeat = take(n * sizeof(sdvlb_align_feat));
+  L.cands = take(n * sizeof(SearchCandDev));
+  L.cand_feat = take(n * sizeof(int32_t));
+  L.matches = take(n * sizeof(sdvlb_match));
+  L.align_scratch = take(n * (18 * 8 + 48 * 4 + 4) + 256);
+  L.c_cell = take(n * sizeof(int32_t));
+  L.c_score = take(n * sizeof(int32_t));
+  L.c_rank = take(n * sizeof(int32_t));
+  L.o_a = take(n * 2 * sizeof(double));
+  L.o_pos = take(n * 3 * sizeof(double));
+  L.o_scale = take(n * sizeof(double));
+  L.o_err = take(n * sizeof(double));
+  L.o_flag = take(n * sizeof(int32_t));
+  L.total = off;
+  return L;
+}
+
+int ensure_step_buffers(sdvlb_ctx* c) {
+  if (c->d_seq_jobs) return 0;
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_seq_jobs), SDVLB_SEQ_BATCH * sizeof(AlignJobDev)));
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_seq_frames), SDVLB_SEQ_BATCH * sizeof(FrameDev)));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------- rand()
+void sdvlb_rand_seed(sdvlb_rand* s, unsigned seed) { rand_seed(s, seed); }
+int sdvlb_rand_next(sdvlb_rand* s) { return rand_next(s); }
+void sdvlb_rand_shuffle(sdvlb_rand* s, int32_t* v, int n) {   // libstdc++ std::random_shuffle(first, last)
+  for (int i = 1; i < n; ++i) {
+    const int j = rand_next(s) % (i + 1);
+    if (i != j) std::swap(v[i], v[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- pose refinement
+static int pose_call(sdvlb_ctx* c, sdvlb_pose_obs* obs, int n, double T[7], sdvlb_rand* rng, int mode) {
+  if (!c || n < 0 || (n > 0 && !obs) || !T) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  if (c->pending.active || c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
+  if (n == 0) return 0;   // SelectInliers returns at once (feature_align.cc:163-164); ConvergePose has no errors (:373-374)
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  Arena& in = c->in;
+  in.used = 0;
+  const size_t need = 4096 + size_t(n) * (sizeof(sdvlb_pose_obs) + 7 * 8 + 4) + 1024;
+  const int rc = ensure_arena(&in, need, true);
+  if (rc) return rc;
+  const size_t o_obs = in.take(size_t(n) * sizeof(sdvlb_pose_obs));
+  const size_t o_T = in.take(7 * sizeof(double));
+  const size_t o_rng = in.take(sizeof(sdvlb_rand));
+  const size_t o_sc = in.take(size_t(n) * 7 * sizeof(double));
+  const size_t o_isc = in.take(size_t(n) * sizeof(int32_t));
+  memcpy(in.h + o_obs, obs, size_t(n) * sizeof(sdvlb_pose_obs));
+  memcpy(in.h + o_T, T, 7 * sizeof(double));
+  if (rng) memcpy(in.h + o_rng, rng, sizeof(sdvlb_rand));
+  const size_t up = o_rng + sizeof(sdvlb_rand);
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, up, cudaMemcpyHostToDevice, c->stream));
+  c->h2d_bytes += int64_t(up);
+  PoseCallArgs A;
+  A.obs = reinterpret_cast<sdvlb_pose_obs*>(in.d + o_obs);
+  A.n = n;
+  A.mode = mode;
+  A.T = reinterpret_cast<double*>(in.d + o_T);
+  A.rng = reinterpret_cast<sdvlb_rand*>(in.d + o_rng);
+  A.scratch = reinterpret_cast<double*>(in.d + o_sc);
+  A.iscratch = reinterpret_cast<int32_t*>(in.d + o_isc);
+  A.dp = c->dp;
+  timer_begin(c, SDVLB_K_POSE);
+  SDVLB_CUDA_TRY(sdvlb_launch_pose_call(A, c->stream));
+  timer_end(c);
+  c->n_launches += 1;
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(in.h, in.d, up, cudaMemcpyDeviceToHost, c->stream));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += int64_t(up);
+  memcpy(obs, in.h + o_obs, size_t(n) * sizeof(sdvlb_pose_obs));
+  memcpy(T, in.h + o_T, 7 * sizeof(double));
+  if (rng) memcpy(rng, in.h + o_rng, sizeof(sdvlb_rand));
+  return 0;
+}
+
+int sdvlb_select_inliers(sdvlb_ctx* ctx, sdvlb_pose_obs* obs, int n, const double T_frame[7], sdvlb_rand* rng) {
+  if (!rng || !T_frame) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  if (ctx && (ctx->params.max_ransac_its > 256 || ctx->params.max_ransac_points > 8))
+    return sdvlb_set_error(SDVLB_ERR_ARG, "max_ransac_its <= 256 and max_ransac_points <= 8 are supported");
+  double T[7];
+  memcpy(T, T_frame, sizeof(T));
+  return pose_call(ctx, obs, n, T, rng, 0);
+}
+
+int sdvlb_optimize_pose(sdvlb_ctx* ctx, sdvlb_pose_obs* obs, int n, double T_frame[7]) {
+  return pose_call(ctx, obs, n, T_frame, nullptr, 1);
+}
+
+// ---------------------------------------------------------------------------------------------- sequences
+int sdvlb_seq_create(sdvlb_ctx* c, int max_feats, sdvlb_seq** out) {
+  if (!c || !out) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  if (c->params.max_ransac_its > 256 || c->params.max_ransac_points > 8)
+    return sdvlb_set_error(SDVLB_ERR_ARG, "max_ransac_its <= 256 and max_ransac_points <= 8 are supported");
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  if (max_feats <= 0) max_feats = std::max(256, 2 * c->params.max_matches);
+  max_feats = int(align_up(size_t(max_feats), 64));
+  // FeatureAlign's grid (feature_align.cc:44-46) is the level-0 FAST grid
+  const int n_cells = c->geom.wcells[0] * c->geom.hcells[0];
+  if (n_cells > 4096) return sdvlb_set_error(SDVLB_ERR_ARG, "image too large for the FeatureAlign grid");
+  const SeqLayout L = seq_layout(max_feats, n_cells);
+  sdvlb_seq* s = new sdvlb_seq;
+  s->ctx = c;
+  s->max_feats = max_feats;
+  s->n_cells = n_cells;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->d_block), L.total);
+  if (e == cudaSuccess)
+    e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_result), sizeof(SeqResultHost) + size_t(max_feats) * sizeof(sdvlb_seq_feat),
+                      cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    if (s->d_block) cudaFree(s->d_block);
+    delete s;
+    return sdvlb_set_cuda_error(e, "sequence storage", __FILE__, __LINE__);
+  }
+  memset(s->h_result, 0, sizeof(SeqResultHost));
+  // initial state: FeatureAlign constructor (cell order shuffled once, feature_align.cc:47-53) + the shuffle that
+  // opens the first tracked frame's SelectPoints (:103), which the device always holds one frame ahead
+  std::vector<uint8_t> init(L.cell_order + size_t(n_cells) * sizeof(int32_t), 0);
+  SeqState* st = reinterpret_cast<SeqState*>(init.data());
+  st->T_last[0] = 1.0;
+  rand_seed(&st->rng, 1);
+  int32_t* order = reinterpret_cast<int32_t*>(init.data() + L.cell_order);
+  for (int i = 0; i < n_cells; i++) order[i] = i;
+  sdvlb_rand_shuffle(&st->rng, order, n_cells);
+  sdvlb_rand_shuffle(&st->rng, order, n_cells);
+  st->max_feats = max_feats;
+  st->n_cells = n_cells;
+  uint8_t* d = s->d_block;
+  st->list[0] = reinterpret_cast<SeqFeat*>(d + L.list[0]);
+  st->list[1] = reinterpret_cast<SeqFeat*>(d + L.list[1]);
+  st->cell_order = reinterpret_cast<int32_t*>(d + L.cell_order);
+  st->afeat = reinterpret_cast<sdvlb_align_feat*>(d + L.afeat);
+  st->cands = reinterpret_cast<SearchCandDev*>(d + L.cands);
+  st->cand_feat = reinterpret_cast<int32_t*>(d + L.cand_feat);
+  st->matches = reinterpret_cast<sdvlb_match*>(d + L.matches);
+  st->align_scratch = d + L.align_scratch;
+  st->c_cell = reinterpret_cast<int32_t*>(d + L.c_cell);
+  st->c_score = reinterpret_cast<int32_t*>(d + L.c_score);
+  st->c_rank = reinterpret_cast<int32_t*>(d + L.c_rank);
+  st->o_a = reinterpret_cast<double*>(d + L.o_a);
+  st->o_pos = reinterpret_cast<double*>(d + L.o_pos);
+  st->o_scale = reinterpret_cast<double*>(d + L.o_scale);
+  st->o_err = reinterpret_cast<double*>(d + L.o_err);
+  st->o_flag = reinterpret_cast<int32_t*>(d + L.o_flag);
+  st->result = s->h_result;
+  e = cudaMemcpyAsync(d, init.data(), init.size(), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    cudaFree(s->d_block);
+    cudaFreeHost(s->h_result);
+    delete s;
+    return sdvlb_set_cuda_error(e, "sequence upload", __FILE__, __LINE__);
+  }
+  c->seqs.push_back(s);
+  *out = s;
+  return 0;
+}
+
+int sdvlb_seq_destroy(sdvlb_ctx* c, sdvlb_seq* s) {
+  if (!s) return 0;
+  if (!c) c = s->ctx;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  // drop queued commands of this sequence
+  for (size_t i = 0; i < c->seq_cmds.size();) {
+    if (c->seq_cmds[i].seq == reinterpret_cast<SeqState*>(s->d_block)) {
+      c->seq_cmds.erase(c->seq_cmds.begin() + i);
+      c->seq_cmd_frames.erase(c->seq_cmd_frames.begin() + i);
+    } else {
+      i++;
+    }
+  }
+  c->seqs.erase(std::remove(c->seqs.begin(), c->seqs.end(), s), c->seqs.end());
+  cudaFree(s->d_block);
+  cudaFreeHost(s->h_result);
+  delete s;
+  return 0;
+}
+
+int sdvlb_seq_reset(sdvlb_ctx* c, sdvlb_seq* s, const sdvlb_frame* frame, const double T[7]) {
+  if (!c || !s || !frame || !T) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  SeqCmd cmd;
+  memset(&cmd, 0, sizeof(cmd));
+  cmd.seq = reinterpret_cast<SeqState*>(s->d_block);
+  cmd.kind = 0;
+  cmd.frame = frame->dev;
+  cmd.frame.host_mirror = nullptr;
+  memcpy(cmd.T, T, sizeof(cmd.T));
+  c->seq_cmds.push_back(cmd);
+  c->seq_cmd_frames.push_back(frame);
+  for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++) s->kf_state[k] = 0;
+  return 0;
+}
+
+int sdvlb_seq_add_points(sdvlb_ctx* c, sdvlb_seq* s, const sdvlb_frame* kf, const double T_kf[7],
+                         const sdvlb_seq_point* pts, int n, int* kf_slot) {
+  if (!c || !s || !kf || !T_kf || n < 0 || (n > 0 && !pts)) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  if (n > s->max_feats) return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "more points than the sequence's feature capacity");
+  for (int k = 0; k < n; k++)
+    if (pts[k].ref_level < 0 || pts[k].ref_level >= c->params.pyramid_levels || pts[k].cur_level < 0 ||
+        pts[k].cur_level >= c->params.pyramid_levels)
+      return sdvlb_set_error(SDVLB_ERR_ARG, "point level out of range");
+  int slot = -1;
+  for (int k = 0; k < SDVLB_SEQ_KF_CAP && slot < 0; k++)
+    if (s->kf_state[k] == 0) slot = k;
+  if (slot < 0) return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "every keyframe slot of the sequence is referenced by live points");
+  s->kf_state[slot] = 1;
+  SeqCmd cmd;
+  memset(&cmd, 0, sizeof(cmd));
+  cmd.seq = reinterpret_cast<SeqState*>(s->d_block);
+  cmd.kind = 1;
+  cmd.n = n;
+  cmd.kf_slot = slot;
+  cmd.kf_pyr = kf->dev.pyr;
+  memcpy(cmd.T, T_kf, sizeof(cmd.T));
+  cmd.pts = reinterpret_cast<const sdvlb_seq_point*>(c->seq_pts.size());   // index for now, device pointer at submission
+  c->seq_cmds.push_back(cmd);
+  c->seq_cmd_frames.push_back(kf);
+  c->seq_pts.insert(c->seq_pts.end(), pts, pts + n);
+  if (kf_slot) *kf_slot = slot;
+  return 0;
+}
+
+int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* const* frames, int n) {
+  if (!c || !seqs || !frames || n <= 0 || n > SDVLB_SEQ_BATCH)
+    return sdvlb_set_error(SDVLB_ERR_ARG, "a sequence submission takes 1..64 sequences");
+  if (c->pending.active || c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  int rc = ensure_step_buffers(c);
+  if (rc) return rc;
+  int max_feats = 0;
+  for (int i = 0; i < n; i++) {
+    if (!seqs[i] || !frames[i] || seqs[i]->ctx != c) return sdvlb_set_error(SDVLB_ERR_ARG, "null / foreign sequence or frame");
+    if (!(frames[i]->has_corners || (frames[i]->build_pending && frames[i]->build_corners)))
+      return sdvlb_set_error(SDVLB_ERR_STATE, "a tracked frame needs corners");
+    max_feats = std::max(max_feats, seqs[i]->max_feats);
+  }
+  // ---- order the tracking stream after the builds of every frame it touches
+  for (int i = 0; i < n; i++) { rc = wait_frame_built(c, frames[i], c->stream); if (rc) return rc; }
+  for (const sdvlb_frame* f : c->seq_cmd_frames) { rc = wait_frame_built(c, f, c->stream); if (rc) return rc; }
+
+  // ---- queued commands: one upload, one kernel
+  const int n_cmds = int(c->seq_cmds.size());
+  if (n_cmds > 0) {
+    Arena& in = c->seq_in;
+    in.used = 0;
+    const size_t need = 1024 + size_t(n_cmds) * sizeof(SeqCmd) + c->seq_pts.size() * sizeof(sdvlb_seq_point);
+    rc = ensure_arena(&in, need, true);
+    if (rc) return rc;
+    const size_t o_cmds = in.take(size_t(n_cmds) * sizeof(SeqCmd));
+    const size_t o_pts = in.take(std::max<size_t>(1, c->seq_pts.size()) * sizeof(sdvlb_seq_point));
+    SeqCmd* hc = reinterpret_cast<SeqCmd*>(in.h + o_cmds);
+    for (int k = 0; k < n_cmds; k++) {
+      hc[k] = c->seq_cmds[k];
+      if (hc[k].kind == 1)
+        hc[k].pts = reinterpret_cast<const sdvlb_seq_point*>(in.d + o_pts) + reinterpret_cast<size_t>(c->seq_cmds[k].pts);
+    }
+    if (!c->seq_pts.empty()) memcpy(in.h + o_pts, c->seq_pts.data(), c->seq_pts.size() * sizeof(sdvlb_seq_point));
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, in.used, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += int64_t(in.used);
+    timer_begin(c, SDVLB_K_PREP);
+    // commands of one sequence must apply in order: one launch per run of distinct sequences would be needed in
+    // general; commands are rare (keyframes), so they are simply applied one launch each when a sequence repeats
+    int k0 = 0;
+    while (k0 < n_cmds) {
+      int k1 = k0 + 1;
+      while (k1 < n_cmds) {
+        bool repeat = false;
+        for (int q = k0; q < k1 && !repeat; q++) repeat = c->seq_cmds[q].seq == c->seq_cmds[k1].seq;
+        if (repeat) break;
+        k1++;
+      }
+      SDVLB_CUDA_TRY(sdvlb_launch_seq_apply(reinterpret_cast<const SeqCmd*>(in.d + o_cmds) + k0, k1 - k0, c->dp, c->stream));
+      c->n_launches += 1;
+      k0 = k1;
+    }
+    timer_end(c);
+    for (sdvlb_seq* s : c->seqs)
+      for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++)
+        if (s->kf_state[k] == 1) s->kf_state[k] = 2;
+    c->seq_cmds.clear();
+    c->seq_pts.clear();
+    c->seq_cmd_frames.clear();
+  }
+
+  // ---- the step
+  SeqStepArgs A;
+  A.n = n;
+  A.max_feats = max_feats;
+  for (int i = 0; i < n; i++) {
+    A.seq[i] = reinterpret_cast<SeqState*>(seqs[i]->d_block);
+    A.cur[i] = frames[i]->dev;
+    A.cur[i].host_mirror = nullptr;
+  }
+  A.jobs = c->d_seq_jobs;
+  A.frames = c->d_seq_frames;
+  A.dp = c->dp;
+  A.g = c->geom;
+  timer_begin(c, SDVLB_K_PREP);
+  SDVLB_CUDA_TRY(sdvlb_launch_seq_prep(A, c->stream));
+  timer_end(c);
+  timer_begin(c, SDVLB_K_ALIGN);
+  SDVLB_CUDA_TRY(sdvlb_launch_align(c->d_seq_jobs, n, c->geom, c->dp, c->stream));
+  timer_end(c);
+  timer_begin(c, SDVLB_K_SEARCH);
+  SDVLB_CUDA_TRY(sdvlb_launch_search_seq(A, c->stream));
+  timer_end(c);
+  timer_begin(c, SDVLB_K_POSE);
+  SDVLB_CUDA_TRY(sdvlb_launch_seq_post(A, c->stream));
+  timer_end(c);
+  c->track_seq++;
+  SDVLB_CUDA_TRY(sdvlb_launch_signal(reinterpret_cast<uint32_t*>(c->h_overflow) + 16, c->track_seq, c->stream));
+  c->n_launches += 5;
+  c->seq_active = true;
+  c->seq_inflight.assign(seqs, seqs + n);
+  c->seq_inflight_frames.assign(frames, frames + n);
+  return 0;
+}
+
+int sdvlb_seq_track_poll(sdvlb_ctx* c) {
+  if (!c || !c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
+  const volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(c->h_overflow) + 16;
+  return *done == c->track_seq ? 1 : 0;
+}
+
+int sdvlb_seq_track_collect(sdvlb_ctx* c, sdvlb_seq_result* results) {
+  if (!c || !results) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  if (!c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
+  c->seq_active = false;
+  int rc = wait_signal(c);
+  if (rc) return rc;
+  rc = check_overflow(c);
+  if (rc) return rc;
+  const int pa = c->params.align_patch_size * c->params.align_patch_size;
+  for (size_t i = 0; i < c->seq_inflight.size(); i++) {
+    sdvlb_seq* s = c->seq_inflight[i];
+    sdvlb_frame* f = c->seq_inflight_frames[i];
+    if (f->build_pending) finalize_build(c, f);   // the tracking stream ran after this frame's build
+    const SeqResultHost* R = s->h_result;
+    if (R->error) return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "a sequence exceeded its feature capacity");
+    sdvlb_seq_result& o = results[i];
+    memcpy(o.pose, R->pose, sizeof(o.pose));
+    o.n_tracked = R->stats[0] / pa;
+    o.matches = R->stats[1];
+    o.attempts = R->stats[2];
+    o.inliers = R->stats[3];
+    o.outliers = R->stats[4];
+    o.n_points = R->stats[5];
+    o.gn_iters = R->stats[6];
+    o.n_feats = R->stats[7];
+    o.feats = reinterpret_cast<const sdvlb_seq_feat*>(reinterpret_cast<const uint8_t*>(R) + sizeof(SeqResultHost));
+    memcpy(o.kf_live, R->kf_live, sizeof(o.kf_live));
+    for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++) {
+      if (R->kf_live[k] > 0) { if (s->kf_state[k] != 1) s->kf_state[k] = 3; }
+      else if (s->kf_state[k] == 2 || s->kf_state[k] == 3) s->kf_state[k] = 0;
+    }
+    c->d2h_bytes += int64_t(sizeof(SeqResultHost)) + int64_t(o.n_feats) * int64_t(sizeof(sdvlb_seq_feat));
+  }
+  return 0;
+}
+
+}  // extern "C"

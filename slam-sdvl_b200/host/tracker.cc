@@ -46,6 +46,17 @@ struct Sequence {
   vector<sdvlb_match> matches;
 };
 
+// Host side of a resident sequence (sdvlb_seq): the tracked state lives on the device; the host keeps the frame handles
+// the device still references and plays the mapping thread (keyframe decision + seeding).
+struct ResidentSeq {
+  sdvlb_seq* h = nullptr;
+  sdvlb_frame* last_frame = nullptr;
+  sdvlb_frame* kf_frames[SDVLB_SEQ_KF_CAP] = {};
+  int frame_counter = 0, last_kf_id = 0, last_matches = 0;
+  int64_t next_point_id = 0;
+  vector<sdvlb_seq_point> seeds;
+};
+
 class SequenceDriver {
  public:
   SequenceDriver(Camera* cam, const SeedPlane& plane, int max_points, int kf_every)
@@ -163,6 +174,72 @@ class SequenceDriver {
 
   Camera* cam() { return cam_; }
 
+  // SeedKeyframe for a resident sequence: same rule, fed from the device's feature list of the frame and the pinned
+  // corner mirror; the new points go to the device with sdvlb_seq_add_points.  Returns the number of seeded points.
+  int SeedResident(sdvlb_ctx* ctx, ResidentSeq* s, sdvlb_frame* f, const SE3& est_pose, const SE3& gt_pose,
+                   const sdvlb_seq_feat* feats, int n_feats) {
+    const int cell = Config::CellSize();
+    const int gw = int(std::ceil(cam_->GetWidth() / cell)), gh = int(std::ceil(cam_->GetHeight() / cell));
+    vector<char> occupied(size_t(gw) * gh, 0);
+    int n_points = 0;
+    for (int i = 0; i < n_feats; i++) {
+      if (!(feats[i].flags & SDVLB_FEAT_HAS_POINT)) continue;
+      n_points++;
+      const int cx = int(feats[i].px[0] / cell), cy = int(feats[i].px[1] / cell);
+      if (cx >= 0 && cx < gw && cy >= 0 && cy < gh) occupied[size_t(cy) * gw + cx] = 1;
+    }
+    const SE3 gt_wc = gt_pose.Inverse();
+    double Rwc[9];
+    gt_wc.GetRotation(Rwc);
+    const Eigen::Vector3d C = gt_wc.GetTranslation();
+    const Eigen::Vector3d est_C = est_pose.Inverse().GetTranslation();
+    const int32_t* xyls = nullptr;
+    int n = 0;
+    if (sdvlb_frame_corners(f, &xyls, &n)) throw std::runtime_error(std::string("sdvl-b200: corners: ") + sdvlb_last_error());
+    const int margin = Config::PatchSize() / 2 + 2;
+    s->seeds.clear();
+    const int before = n_points;
+    for (int i = 0; i < n && n_points < max_points_; i++) {
+      const int32_t* c = xyls + 4 * size_t((long long)i * 7919 % n);
+      const int lw = int(cam_->GetWidth()) >> c[2], lh = int(cam_->GetHeight()) >> c[2];
+      if (c[0] < margin || c[1] < margin || c[0] >= lw - margin || c[1] >= lh - margin) continue;
+      const Eigen::Vector2d px(double(c[0] * (1 << c[2])), double(c[1] * (1 << c[2])));
+      const int cx = int(px(0) / cell), cy = int(px(1) / cell);
+      if (occupied[size_t(cy) * gw + cx]) continue;
+      const Eigen::Vector3d v = cam_->Unproject(px);
+      const Eigen::Vector3d dir(Rwc[0] * v(0) + Rwc[1] * v(1) + Rwc[2] * v(2), Rwc[3] * v(0) + Rwc[4] * v(1) + Rwc[5] * v(2),
+                                Rwc[6] * v(0) + Rwc[7] * v(1) + Rwc[8] * v(2));
+      const Eigen::Vector3d nrm(plane_.n[0], plane_.n[1], plane_.n[2]);
+      const double denom = nrm.dot(dir);
+      if (std::fabs(denom) < 1e-9) continue;
+      const double sdist = (plane_.d - nrm.dot(C)) / denom;
+      if (sdist <= 0) continue;
+      const Eigen::Vector3d p3d = C + dir * sdist;
+      const double depth = (p3d - est_C).norm();
+      const double rho = 1.0 / depth;
+      sdvlb_seq_point p;
+      std::memset(&p, 0, sizeof(p));
+      p.pos[0] = p3d(0); p.pos[1] = p3d(1); p.pos[2] = p3d(2);
+      p.ref_px[0] = p.cur_px[0] = px(0); p.ref_px[1] = p.cur_px[1] = px(1);
+      p.idepth = rho;
+      p.idepth_std = std::sqrt((0.05 * rho) * (0.05 * rho));
+      p.user_id = s->next_point_id++;
+      p.ref_level = p.cur_level = c[2];
+      p.flags = SDVLB_CAND_FIXED;
+      s->seeds.push_back(p);
+      occupied[size_t(cy) * gw + cx] = 1;
+      n_points++;
+    }
+    double T[7];
+    est_pose.ToArray(T);
+    int slot = -1;
+    if (sdvlb_seq_add_points(ctx, s->h, f, T, s->seeds.data(), int(s->seeds.size()), &slot))
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_add_points failed: ") + sdvlb_last_error());
+    s->kf_frames[slot] = f;
+    s->last_kf_id = s->frame_counter;
+    return n_points - before;
+  }
+
  private:
   Camera* cam_;
   SeedPlane plane_;
@@ -173,8 +250,9 @@ class SequenceDriver {
 // One context, one host thread, a fixed subset of the sequences.
 class Group {
  public:
-  Group(int device, const SeedPlane& plane, int max_points, int kf_every, int n_seq, bool timing)
-      : cam_(), driver_(&cam_, plane, max_points, kf_every), seqs_(n_seq), jobs_(n_seq) {
+  Group(int device, const SeedPlane& plane, int max_points, int kf_every, int n_seq, bool timing, bool resident)
+      : cam_(), driver_(&cam_, plane, max_points, kf_every), seqs_(resident ? 0 : n_seq), jobs_(n_seq), kf_every_(kf_every),
+        resident_(resident), rseqs_(resident ? n_seq : 0) {
     const int rc = sdvlb_ctx_create(device, &Config::Params(), &Config::CameraParams(), &ctx_);
     if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_create failed: ") + sdvlb_last_error());
     if (timing) sdvlb_timing_enable(ctx_, 1);
@@ -182,12 +260,37 @@ class Group {
     if (sdvlb_ctx_reserve_frames(ctx_, 16 * n_seq))
       throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_reserve_frames failed: ") + sdvlb_last_error());
     for (auto& s : seqs_) driver_.InitSequence(&s);
+    for (auto& r : rseqs_) {
+      if (sdvlb_seq_create(ctx_, std::max(256, 2 * std::max(max_points, Config::MaxMatches())), &r.h))
+        throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_create failed: ") + sdvlb_last_error());
+      seq_handles_.push_back(r.h);
+    }
+    results_.resize(rseqs_.size());
   }
   ~Group() {
     seqs_.clear();   // frames go back to the pool before the context dies
     sdvlb_ctx_destroy(ctx_);
   }
-  int size() const { return int(seqs_.size()); }
+  int size() const { return resident_ ? int(rseqs_.size()) : int(seqs_.size()); }
+  bool resident() const { return resident_; }
+
+  // ---- resident sequences: one frame for every sequence, synchronously
+  void StepResident(const uint8_t* const* images, int on_device, const double* gt, double* est, int32_t* stats) {
+    Device::SetCurrent(ctx_);
+    const int n = size();
+    built_.assign(n, nullptr);
+    const auto tA = std::chrono::steady_clock::now();
+    if (sdvlb_frames_submit(ctx_, images, n, on_device, 1, Config::NumFeatures(), built_.data()))
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_frames_submit failed: ") + sdvlb_last_error());
+    const auto tB = std::chrono::steady_clock::now();
+    const bool tracked = SubmitResident();
+    const auto tC = std::chrono::steady_clock::now();
+    FinishResident(tracked, gt, 1, 0, est, stats);
+    const auto tD = std::chrono::steady_clock::now();
+    phase_s_[0] += std::chrono::duration<double>(tB - tA).count();
+    phase_s_[1] += std::chrono::duration<double>(tC - tB).count();
+    phase_s_[2] += std::chrono::duration<double>(tD - tC).count();
+  }
   sdvlb_ctx* ctx() { return ctx_; }
 
   void StepClassic(const uint8_t* const* images, const double* gt, double* est, int32_t* stats) {
@@ -247,6 +350,14 @@ class Group {
     Device::SetCurrent(ctx_);
     const auto tA = std::chrono::steady_clock::now();
     if (step_ + 1 < n_steps_) SubmitBuild(step_ + 1, &next_built_);
+    if (resident_) {
+      const auto tB = std::chrono::steady_clock::now();
+      tracked_ = SubmitResident();
+      in_flight_ = true;
+      phase_s_[0] += std::chrono::duration<double>(tB - tA).count();
+      phase_s_[1] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tB).count();
+      return;
+    }
     const int n = size();
     const int w = int(cam_.GetWidth()), h = int(cam_.GetHeight());
     for (int i = 0; i < n; i++) {
@@ -262,13 +373,26 @@ class Group {
     phase_s_[1] += std::chrono::duration<double>(tC - tB).count();
   }
   bool Poll() {
-    const int rc = sdvlb_track_poll(ctx_);
+    if (resident_ && !tracked_) return true;
+    const int rc = resident_ ? sdvlb_seq_track_poll(ctx_) : sdvlb_track_poll(ctx_);
     if (rc < 0) throw std::runtime_error(std::string("sdvl-b200: sdvlb_track_poll failed: ") + sdvlb_last_error());
     return rc == 1;
   }
   void FinishStep() {   // waits if the device is not done yet
     Device::SetCurrent(ctx_);
     const auto tA = std::chrono::steady_clock::now();
+    if (resident_) {
+      const double waited = FinishResident(tracked_, gt_ + 7 * size_t(step_), stride_, step_, est_ + 7 * size_t(step_),
+                                           stats_ + 8 * size_t(step_));
+      in_flight_ = false;
+      built_.swap(next_built_);
+      step_++;
+      const double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - tA).count();
+      phase_s_[1] += waited;
+      phase_s_[6] += waited;
+      phase_s_[2] += total - waited;
+      return;
+    }
     const int rc = sdvlb_track_collect(ctx_);
     if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_track_collect failed: ") + sdvlb_last_error());
     in_flight_ = false;
@@ -331,6 +455,78 @@ class Group {
     phase_s_[3] += std::chrono::duration<double>(t1 - t0).count();
     phase_s_[5] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
   }
+  // Submits the tracking of built_ for every sequence; sequences without a track yet are started instead (host only).
+  // Returns whether a device submission is in flight.
+  bool SubmitResident() {
+    if (rseqs_[0].last_frame == nullptr) return false;   // the sequences of a group run in lock-step
+    if (sdvlb_seq_track_submit(ctx_, seq_handles_.data(), built_.data(), size()))
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_track_submit failed: ") + sdvlb_last_error());
+    return true;
+  }
+  // Host half of a resident step: results, keyframe decision (Map::NeedKeyframe, map.cc:170-188) and seeding, frame
+  // lifetimes.  Tables are indexed [i * stride + offset].  Returns the seconds spent waiting for the device.
+  double FinishResident(bool tracked, const double* gt, int stride, int /*step*/, double* est, int32_t* stats) {
+    const int n = size();
+    double waited = 0;
+    if (tracked) {
+      const auto t0 = std::chrono::steady_clock::now();
+      if (sdvlb_seq_track_collect(ctx_, results_.data()))
+        throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_track_collect failed: ") + sdvlb_last_error());
+      waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    } else {
+      if (sdvlb_frames_wait(ctx_, built_.data(), n))
+        throw std::runtime_error(std::string("sdvl-b200: sdvlb_frames_wait failed: ") + sdvlb_last_error());
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; i++) {
+      ResidentSeq& s = rseqs_[i];
+      const size_t o = size_t(i) * stride;
+      int32_t* st = stats + 8 * o;
+      std::memset(st, 0, 8 * sizeof(int32_t));
+      const SE3 gt_pose(gt + 7 * o);
+      sdvlb_frame* frame = built_[i];
+      if (!tracked) {   // first frame of the sequence: ground-truth pose + seeding (stand-in for the initialisation)
+        if (sdvlb_seq_reset(ctx_, s.h, frame, gt + 7 * o))
+          throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_reset failed: ") + sdvlb_last_error());
+        for (auto& k : s.kf_frames) k = nullptr;
+        st[5] = driver_.SeedResident(ctx_, &s, frame, gt_pose, gt_pose, nullptr, 0);
+        st[7] = 1;
+        gt_pose.ToArray(est + 7 * o);
+      } else {
+        const sdvlb_seq_result& r = results_[i];
+        st[0] = r.n_tracked; st[1] = r.matches; st[2] = r.attempts; st[3] = r.inliers; st[4] = r.outliers;
+        st[6] = r.gn_iters;
+        std::memcpy(est + 7 * o, r.pose, 7 * sizeof(double));
+        // keyframe slots nothing references any more give their frames back
+        for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++)
+          if (s.kf_frames[k] && r.kf_live[k] == 0) {
+            if (s.kf_frames[k] != s.last_frame) sdvlb_frame_destroy(ctx_, s.kf_frames[k]);
+            s.kf_frames[k] = nullptr;
+          }
+        const int npoints = r.n_points;
+        const bool enough_its = (s.frame_counter - s.last_kf_id) >= kf_every_;
+        const bool lost_many = npoints < s.last_matches * 0.7;
+        const bool lost_some = npoints < s.last_matches * 0.9;
+        s.last_matches = std::max(s.last_matches, npoints);
+        int seeded = 0;
+        if ((enough_its && lost_some) || lost_many) {
+          s.last_matches = npoints;
+          seeded = driver_.SeedResident(ctx_, &s, frame, SE3(r.pose), gt_pose, r.feats, r.n_feats);
+          st[7] = 1;
+        }
+        st[5] = npoints + seeded;
+      }
+      if (s.last_frame) {
+        bool held = false;
+        for (int k = 0; k < SDVLB_SEQ_KF_CAP && !held; k++) held = s.kf_frames[k] == s.last_frame;
+        if (!held) sdvlb_frame_destroy(ctx_, s.last_frame);
+      }
+      s.last_frame = frame;
+      s.frame_counter++;
+    }
+    phase_s_[5] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    return waited;
+  }
   void SubmitBuild(int step, vector<sdvlb_frame*>* out) {
     const int n = size();
     img_ptrs_.resize(n);
@@ -344,6 +540,11 @@ class Group {
   sdvlb_ctx* ctx_ = nullptr;
   vector<Sequence> seqs_;
   vector<sdvlb_track_job> jobs_;
+  int kf_every_ = 0;
+  bool resident_ = false, tracked_ = false;
+  vector<ResidentSeq> rseqs_;
+  vector<sdvlb_seq*> seq_handles_;
+  vector<sdvlb_seq_result> results_;
   // thread-seconds: [0] marshal (+ frame-batch submission), [1] tracking submission + wait, [2] host replay total,
   // of which [3] FeatureAlign::ApplyMatches, [4] its RANSAC (SelectInliers), [5] FinishFrame (OptimizePose, motion
   // model, keyframe seeding), [6] waiting only
@@ -365,15 +566,15 @@ class Group {
 class BatchTracker {
  public:
   BatchTracker(const SeedPlane& plane, int max_points, int kf_every, int n_seq, int n_groups, int n_threads, int device,
-               bool timing)
-      : n_seq_(n_seq) {
+               bool timing, bool resident)
+      : n_seq_(n_seq), resident_(resident) {
     n_groups = std::max(1, std::min(n_groups, n_seq));
     n_threads_ = n_threads <= 0 ? n_groups : std::max(1, std::min(n_threads, n_groups));
     int left = n_seq;
     for (int g = 0; g < n_groups; g++) {
       const int take = (left + (n_groups - g) - 1) / (n_groups - g);
       offsets_.push_back(n_seq - left);
-      groups_.emplace_back(new Group(device, plane, max_points, kf_every, take, timing));
+      groups_.emplace_back(new Group(device, plane, max_points, kf_every, take, timing, resident));
       left -= take;
     }
     if (n_groups > 1) {
@@ -393,7 +594,8 @@ class BatchTracker {
 
   // One frame for every sequence, all groups in lock-step.
   void Step(const uint8_t* const* images, int on_device, int classic, const double* gt, double* est, int32_t* stats) {
-    mode_ = classic ? 1 : 0;
+    if (resident_ && classic) throw std::runtime_error("sdvl-b200: a resident tracker has no classic mode");
+    mode_ = resident_ ? 3 : (classic ? 1 : 0);
     images_ = images; on_device_ = on_device; gt_ = gt; est_ = est; stats_ = stats;
     Dispatch();
   }
@@ -462,6 +664,7 @@ class BatchTracker {
         for (int g : mine) {
           const int o = offsets_[g];
           if (mode_ == 1) groups_[g]->StepClassic(images_ + o, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
+          else if (mode_ == 3) groups_[g]->StepResident(images_ + o, on_device_, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
           else groups_[g]->StepBatched(images_ + o, on_device_, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
         }
         return;
@@ -516,6 +719,7 @@ class BatchTracker {
   }
 
   int n_seq_, n_threads_ = 1;
+  bool resident_ = false;
   vector<std::unique_ptr<Group>> groups_;
   vector<int> offsets_;
   vector<std::thread> workers_;
@@ -545,16 +749,22 @@ const char* sdvlh_last_error(void) { return g_host_error.c_str(); }
 // Config is process-wide in the reference (singleton, config.h:56); set it before creating trackers.
 void sdvlh_config_set(const sdvlb_params* p, const sdvlb_camera* cam) { sdvl::Config::Set(*p, *cam); }
 
-void* sdvlh_tracker_create(const double plane[4], int max_points, int kf_every, int n_seq, int n_groups, int n_threads,
-                           int device, int timing) {
+// resident != 0: the sequences live on the device (sdvlb_seq_*): the host neither marshals features nor replays matches.
+void* sdvlh_tracker_create2(const double plane[4], int max_points, int kf_every, int n_seq, int n_groups, int n_threads,
+                            int device, int timing, int resident) {
   try {
     sdvl::SeedPlane pl;
     pl.n[0] = plane[0]; pl.n[1] = plane[1]; pl.n[2] = plane[2]; pl.d = plane[3];
-    return new sdvl::BatchTracker(pl, max_points, kf_every, n_seq, n_groups, n_threads, device, timing != 0);
+    return new sdvl::BatchTracker(pl, max_points, kf_every, n_seq, n_groups, n_threads, device, timing != 0, resident != 0);
   } catch (const std::exception& e) {
     g_host_error = e.what();
     return nullptr;
   }
+}
+
+void* sdvlh_tracker_create(const double plane[4], int max_points, int kf_every, int n_seq, int n_groups, int n_threads,
+                           int device, int timing) {
+  return sdvlh_tracker_create2(plane, max_points, kf_every, n_seq, n_groups, n_threads, device, timing, 0);
 }
 
 void sdvlh_tracker_destroy(void* t) { delete static_cast<sdvl::BatchTracker*>(t); }

@@ -1,0 +1,192 @@
+"""GPU parity of the device-side FeatureAlign (SelectPoints / SelectInliers / OptimizePose) and of resident sequences
+(sdvlb_seq_*): against the CPU oracle and against the class-API (classic) path of the host mirror."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ATE_MM = 1.0
+
+
+def _quat_mul_vec(sw, T, p):
+    return sw.quat_R(T[:4]) @ p + T[4:]
+
+
+def _make_obs(abi, sw, O, cfg, rng, n, outlier_frac=0.2, noise_px=0.3):
+    """n observations of random world points from a known pose, some of them gross outliers."""
+    cam = cfg["cam"]
+    T_true = sw.trajectory(cfg, int(rng.integers(1000)), 3)[2]
+    R = sw.quat_R(T_true[:4])
+    obs = np.zeros(n, abi.POSE_OBS_DT)
+    for i in range(n):
+        u = rng.uniform(20, cam.width - 20)
+        v = rng.uniform(20, cam.height - 20)
+        depth = rng.uniform(1.0, 4.0)
+        ray = np.array([(u - cam.u0) / cam.fx, (v - cam.v0) / cam.fy, 1.0])
+        pc = ray * depth
+        obs["pos"][i] = R.T @ (pc - T_true[4:])
+        if rng.uniform() < outlier_frac:
+            u += rng.uniform(-40, 40)
+            v += rng.uniform(-40, 40)
+        else:
+            u += rng.normal(0, noise_px)
+            v += rng.normal(0, noise_px)
+        b = np.array([(u - cam.u0) / cam.fx, (v - cam.v0) / cam.fy, 1.0])
+        obs["v"][i] = b / np.linalg.norm(b)
+        obs["level"][i] = int(rng.integers(0, 3))
+    # the frame pose FeatureAlign starts from: the true pose, slightly off (what ImageAlign leaves)
+    du = np.concatenate([rng.normal(0, 0.004, 3), rng.normal(0, 0.002, 3)])
+    import ctypes as C
+    T0 = np.zeros(7)
+    dT = np.zeros(7)
+    O.lib().orc_se3_exp(abi.ptr(du), abi.ptr(dT))
+    O.lib().orc_se3_mul(abi.ptr(dT), abi.ptr(np.ascontiguousarray(T_true)), abi.ptr(T0))
+    return obs, T0, T_true
+
+
+def _pose_dist(a, b):
+    return max(np.abs(a[4:] - b[4:]).max(), min(np.abs(a[:4] - b[:4]).max(), np.abs(a[:4] + b[:4]).max()))
+
+
+@pytest.mark.parametrize("n,seed", [(3, 0), (5, 1), (17, 2), (60, 3), (120, 4), (200, 5), (200, 6), (400, 7)])
+def test_select_inliers_and_optimize_pose_vs_oracle(binding, abi, sw, O, n, seed):
+    """sdvlb_select_inliers / sdvlb_optimize_pose == the oracle's FeatureAlign::SelectInliers / OptimizePose: same
+    inlier sets, the same number of rand() draws, poses within 1e-9 (fp64, different summation order)."""
+    cfg = sw.config("C2")
+    rng = np.random.default_rng(100 + seed)
+    obs, T0, T_true = _make_obs(abi, sw, O, cfg, rng, n)
+    ctx = binding.Context(cfg["params"], cfg["cam"])
+    r_gpu, r_cpu = abi.Rand(), abi.Rand()
+    L = binding.load()
+    import ctypes as C
+    L.sdvlb_rand_seed(C.byref(r_gpu), 7 + seed)
+    L.sdvlb_rand_seed(C.byref(r_cpu), 7 + seed)
+    g = ctx.select_inliers(obs.copy(), T0, r_gpu)
+    o, _ = O.pose_refine(cfg["params"], cfg["cam"], obs, T0, r_cpu, mode=0)
+    assert np.array_equal(g["flags"], o["flags"]), f"inlier sets differ: {np.flatnonzero(g['flags'] != o['flags'])}"
+    assert r_gpu.n == r_cpu.n and list(r_gpu.r) == list(r_cpu.r), "rand() stream advanced differently"
+    assert (g["flags"] == abi.OBS_INLIER).sum() >= min(n, 3) * 0.5
+    g2, Tg = ctx.optimize_pose(g.copy(), T0)
+    o2, To = O.pose_refine(cfg["params"], cfg["cam"], o, T0, None, mode=1)
+    assert np.array_equal(g2["flags"], o2["flags"])
+    d = _pose_dist(Tg, To)
+    print(f"n={n}: inliers {int((g2['flags'] == abi.OBS_INLIER).sum())}, draws {r_gpu.n - 344 if False else ''} pose diff {d:.2e}, "
+          f"error vs truth {_pose_dist(Tg, T_true):.2e}")
+    assert d < 1e-9
+    if n >= 17:
+        assert _pose_dist(Tg, T_true) < _pose_dist(T0, T_true)
+    ctx.close()
+
+
+def test_pose_refine_degenerate_inputs(binding, abi, sw, O):
+    """Empty list, a single observation, all observations identical: same outcome as the oracle, no hang."""
+    cfg = sw.config("C2")
+    ctx = binding.Context(cfg["params"], cfg["cam"])
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    obs, T0, _ = _make_obs(abi, sw, O, cfg, rng, 8)
+    for sub in (obs[:0], obs[:1], np.repeat(obs[:1], 6)):
+        r_gpu, r_cpu = abi.Rand(), abi.Rand()
+        binding.load().sdvlb_rand_seed(C.byref(r_gpu), 1)
+        binding.load().sdvlb_rand_seed(C.byref(r_cpu), 1)
+        g = ctx.select_inliers(sub.copy(), T0, r_gpu)
+        o, _ = O.pose_refine(cfg["params"], cfg["cam"], sub, T0, r_cpu, mode=0)
+        assert np.array_equal(g["flags"], o["flags"])
+        assert r_gpu.n == r_cpu.n
+        g2, Tg = ctx.optimize_pose(g.copy(), T0)
+        o2, To = O.pose_refine(cfg["params"], cfg["cam"], o, T0, None, mode=1)
+        assert np.array_equal(g2["flags"], o2["flags"])
+        assert _pose_dist(Tg, To) < 1e-9
+    ctx.close()
+
+
+def _run_tracker(binding, sw, cfg, seqs, resident, classic=False, n_groups=1, kf_every=20, pipelined=False):
+    n_seq = len(seqs)
+    n = seqs[0][1].shape[0]
+    t = binding.HostTracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], kf_every, n_seq, n_groups,
+                            resident=resident)
+    if pipelined:
+        imgs = np.stack([s[1] for s in seqs])
+        gt = np.stack([s[0] for s in seqs])
+        h = n // 2
+        e1, s1 = t.run(imgs[:, :h], gt[:, :h])
+        e2, s2 = t.run(imgs[:, h:], gt[:, h:])
+        t.close()
+        return np.concatenate([e1, e2], axis=1), np.concatenate([s1, s2], axis=1)
+    est = np.zeros((n_seq, n, 7))
+    stats = np.zeros((n_seq, n, 8), np.int32)
+    for k in range(n):
+        imgs = np.stack([s[1][k] for s in seqs])
+        gt = np.stack([s[0][k] for s in seqs])
+        e, st = t.step(imgs, gt, classic=classic)
+        est[:, k] = e
+        stats[:, k] = st
+    t.close()
+    return est, stats
+
+
+@pytest.mark.parametrize("name,n_frames", [("C2", 45), ("C1", 30), ("C3", 30)])
+def test_resident_sequences_vs_classic_and_oracle(binding, sw, O, name, n_frames):
+    """The resident chain (everything on the device) tracks like the class-API path (same kernels for ImageAlign and
+    SearchPoint; FeatureAlign's arithmetic in a different summation order) and within 1 mm ATE of the CPU oracle."""
+    cfg = sw.config(name)
+    seqs = []
+    for seed in (0, 1, 2):
+        poses = sw.trajectory(cfg, seed, n_frames)
+        seqs.append((poses, sw.render(cfg, poses)))
+    est_r, st_r = _run_tracker(binding, sw, cfg, seqs, resident=True, n_groups=2)
+    est_c, st_c = _run_tracker(binding, sw, cfg, seqs[:2], resident=False, classic=True)
+    for i in range(2):
+        dc = np.array([np.linalg.norm(sw.cam_center(a) - sw.cam_center(b)) for a, b in zip(est_r[i], est_c[i])])
+        same = float((st_r[i][:, [1, 2, 3, 4, 5, 7]] == st_c[i][:, [1, 2, 3, 4, 5, 7]]).all(axis=1).mean())
+        print(f"{name} seq {i}: resident vs classic max {dc.max()*1e3:.6f} mm, identical stats {same:.2%}")
+        assert dc.max() < 1e-4, "resident and classic trajectories diverge"
+        assert same >= 0.9
+    for i, (poses, imgs) in enumerate(seqs):
+        tr = O.Tracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], 20)
+        est_o, st_o, _ = tr.run(imgs, poses)
+        tr.close()
+        d = np.array([np.linalg.norm(sw.cam_center(a) - sw.cam_center(b)) for a, b in zip(est_r[i], est_o)])
+        ate = float(np.sqrt((d ** 2).mean())) * 1e3
+        same = float((st_r[i][:, 1:6] == st_o[:, 1:6]).all(axis=1).mean())
+        print(f"{name} seq {i}: resident vs oracle ATE {ate:.4f} mm (max {d.max()*1e3:.4f}), vs GT {sw.ate(est_r[i], poses)*1e3:.3f} mm, "
+              f"identical stats {same:.2%}, matches/frame {st_r[i][1:,1].mean():.0f}, keyframes {st_r[i][:,7].sum()}")
+        assert ate <= ATE_MM
+        assert sw.ate(est_r[i], poses) * 1e3 <= 5.0
+        assert st_r[i][1:, 1].mean() > 0.4 * cfg["n_feat"]
+
+
+@pytest.mark.parametrize("n_groups", [1, 3])
+def test_resident_pipelined_equals_lockstep(binding, sw, n_groups):
+    """Free-running groups with frame batches one step ahead == stepping all sequences synchronously (bit-exact)."""
+    cfg = sw.config("C2")
+    seqs = []
+    for seed in range(5):
+        poses = sw.trajectory(cfg, 20 + seed, 14)
+        seqs.append((poses, sw.render(cfg, poses)))
+    est_s, st_s = _run_tracker(binding, sw, cfg, seqs, resident=True, n_groups=2)
+    est_p, st_p = _run_tracker(binding, sw, cfg, seqs, resident=True, n_groups=n_groups, pipelined=True)
+    assert np.array_equal(est_s, est_p)
+    assert np.array_equal(st_s, st_p)
+
+
+def test_resident_max_matches_cutoff(binding, sw, O):
+    """max_matches below the number of trackable points: SelectPoints stops early, in cell_order_ order, exactly as the
+    reference's loop does (compared with the oracle, which walks the per-cell lists)."""
+    cfg = sw.config("C2")
+    import copy
+    params = copy.copy(cfg["params"])
+    params.max_matches = 60
+    cfg2 = dict(cfg, params=params)
+    poses = sw.trajectory(cfg, 3, 25)
+    imgs = sw.render(cfg, poses)
+    est_r, st_r = _run_tracker(binding, sw, cfg2, [(poses, imgs)], resident=True)
+    tr = O.Tracker(params, cfg["cam"], sw.PLANE, cfg["n_feat"], 20)
+    est_o, st_o, _ = tr.run(imgs, poses)
+    tr.close()
+    assert st_r[0][1:, 1].max() <= 60 and (st_r[0][1:, 1] == 60).any()
+    same = float((st_r[0][:, 1:6] == st_o[:, 1:6]).all(axis=1).mean())
+    d = np.array([np.linalg.norm(sw.cam_center(a) - sw.cam_center(b)) for a, b in zip(est_r[0], est_o)])
+    print(f"cut-off: identical stats {same:.2%}, max diff {d.max()*1e3:.4f} mm")
+    assert same >= 0.9
+    assert float(np.sqrt((d ** 2).mean())) * 1e3 <= ATE_MM

@@ -149,3 +149,28 @@ def test_sequence_sharding_two_ranks_gloo(tmp_path):
     seeds = sorted(sum((r["seeds"] for r in rows), []))
     assert seeds == list(range(6))
     assert all(r["sec"] == 2.0 for r in rows) and all(r["tot"] == 6 for r in rows)
+
+
+def test_product_rand_matches_glibc_and_libstdcxx(binding, abi):
+    """sdvlb_rand_* (the rand() stream every FeatureAlign / resident sequence owns) == glibc rand() after srand(seed),
+    and sdvlb_rand_shuffle == libstdc++ std::random_shuffle driven by it (same loop as the oracle's, which
+    tests/test_oracle_cpu.py pins against the real libstdc++)."""
+    libc = C.CDLL("libc.so.6")
+    L = binding.load()
+    for seed in (1, 7, 12345):
+        libc.srand(seed)
+        ref = [libc.rand() for _ in range(2000)]
+        r = abi.Rand()
+        L.sdvlb_rand_seed(C.byref(r), seed)
+        assert [L.sdvlb_rand_next(C.byref(r)) for _ in range(2000)] == ref
+    for n in (1, 2, 17, 360):
+        libc.srand(1)
+        v = np.arange(n, dtype=np.int32)
+        expect = v.copy()
+        for i in range(1, n):
+            j = libc.rand() % (i + 1)
+            expect[i], expect[j] = expect[j], expect[i]
+        r = abi.Rand()
+        L.sdvlb_rand_seed(C.byref(r), 1)
+        L.sdvlb_rand_shuffle(C.byref(r), abi.ptr(v), n)
+        assert np.array_equal(v, expect)

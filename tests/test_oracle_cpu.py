@@ -218,3 +218,38 @@ def test_tracker_follows_ground_truth(O, sw):
     tr.close()
     assert sw.ate(est, poses) < 1e-3
     assert stats[1:, 1].mean() > 80
+
+
+def test_pose_refine_recovers_pose_and_rejects_outliers(O, sw, abi):
+    """Oracle FeatureAlign::SelectInliers + OptimizePose on exact observations of a known pose with a few gross
+    outliers: RANSAC flags exactly the corrupted ones and the refined pose is the true one (analytic KAT)."""
+    cfg = sw.config("C2")
+    cam = cfg["cam"]
+    rng = np.random.default_rng(0)
+    T_true = sw.trajectory(cfg, 4, 3)[2]
+    R = sw.quat_R(T_true[:4])
+    n = 80
+    obs = np.zeros(n, abi.POSE_OBS_DT)
+    bad = set(range(0, n, 9))
+    for i in range(n):
+        u, v, depth = rng.uniform(20, cam.width - 20), rng.uniform(20, cam.height - 20), rng.uniform(1, 4)
+        ray = np.array([(u - cam.u0) / cam.fx, (v - cam.v0) / cam.fy, 1.0])
+        obs["pos"][i] = R.T @ (ray * depth - T_true[4:])
+        if i in bad:
+            u += 35.0
+        b = np.array([(u - cam.u0) / cam.fx, (v - cam.v0) / cam.fy, 1.0])
+        obs["v"][i] = b / np.linalg.norm(b)
+    du = np.array([0.004, -0.003, 0.002, 0.001, -0.002, 0.001])
+    dT, T0 = np.zeros(7), np.zeros(7)
+    O.lib().orc_se3_exp(O.ptr(du), O.ptr(dT))
+    O.lib().orc_se3_mul(O.ptr(dT), O.ptr(np.ascontiguousarray(T_true)), O.ptr(T0))
+    r = abi.Rand()
+    st = np.zeros(1, np.int32)
+    O.lib().orc_rand_state(1, C.byref(r))   # srand(1)
+    o, _ = O.pose_refine(cfg["params"], cam, obs, T0, r, mode=0)
+    assert set(np.flatnonzero(o["flags"] == abi.OBS_OUTLIER)) == bad
+    assert r.n > 344   # RANSAC drew from the stream
+    o2, T = O.pose_refine(cfg["params"], cam, o, T0, None, mode=1)
+    assert set(np.flatnonzero(o2["flags"] == abi.OBS_OUTLIER)) == bad
+    assert np.abs(T[4:] - T_true[4:]).max() < 1e-9
+    assert min(np.abs(T[:4] - T_true[:4]).max(), np.abs(T[:4] + T_true[:4]).max()) < 1e-9
