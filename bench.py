@@ -122,6 +122,11 @@ def algorithmic_bytes(cfg, kernel, stats_prev, stats_cur, n_corners=1000, kbar=3
         return int((levels * n_feat * 49 + iters * n_feat * 25 + 64 * n_feat).sum())
     if kernel == "search":
         return int((n_feat * (121 + 64 * kbar + 810)).sum())
+    if kernel == "prep":     # read the last frame's feature list (160 B each), write align features + candidates
+        return int((n_feat * (160 + 56 + 168)).sum())
+    if kernel == "pose":     # read matches (40 B) + features, write the new list, its host mirror and the obs arrays
+        found = stats_cur[:, 1].astype(np.int64)
+        return int((n_feat * (40 + 160)).sum() + (found * (160 + 32 + 7 * 8)).sum())
     raise ValueError(kernel)
 
 
@@ -175,6 +180,9 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host threads per GPU (0 = cores / ranks)")
     ap.add_argument("--kf-every", type=int, default=20)
     ap.add_argument("--config", default="C2")
+    ap.add_argument("--sweep", default="", help="comma list of GROUPSxTHREADS to time (e2e only), e.g. 8x4,16x8")
+    ap.add_argument("--host-replay", action="store_true",
+                    help="previous design: FeatureAlign bookkeeping + pose refinement on the host (for comparison)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -207,8 +215,13 @@ def main():
     F = 1 + W + K                       # frame 0 initialises every sequence (ground-truth pose + map seeding)
     w, h = cfg["w"], cfg["h"]
     ncpu = os.cpu_count() or 1
-    threads = args.threads or max(1, min(S, ncpu // max(1, world)))
-    groups = args.groups or max(1, min(S, 2 * threads))
+    cores = max(1, ncpu // max(1, world))
+    if args.host_replay:     # the host replays FeatureAlign: every core is needed
+        threads = args.threads or max(1, min(S, cores))
+        groups = args.groups or max(1, min(S, 2 * threads))
+    else:                    # resident sequences: the host only submits; a few threads keep 8 groups in flight
+        threads = args.threads or max(1, min(4, cores))
+        groups = args.groups or max(1, min(S, 8))
 
     # ---- synthetic frames, rendered once into pinned host memory
     host = torch.empty((S, F, h, w), dtype=torch.uint8).pin_memory()
@@ -231,7 +244,8 @@ def main():
         pipelined: sdvlh_tracker_run (frame batches one step ahead, groups free-running); otherwise every step is one
         synchronous lock-step submission (used for the per-kernel timing pass, where launches must not overlap)."""
         trk = binding.HostTracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], args.kf_every, S, n_groups,
-                                  device=local_rank, timing=timing, n_threads=min(n_groups, threads))
+                                  device=local_rank, timing=timing, n_threads=min(n_groups, threads),
+                                  resident=not args.host_replay)
         est = np.zeros((S, F, 7))
         stats = np.zeros((F, S, 8), np.int32)
 
@@ -269,6 +283,15 @@ def main():
         ngroups = trk.groups()
         trk.close()
         return sec, wall, est, stats, counters, ktimes, ngroups
+
+    if args.sweep:   # host-side configuration sweep (groups x threads), e2e placement; prints a table and exits
+        for spec in args.sweep.split(","):
+            g_, t_ = (int(v) for v in spec.split("x"))
+            threads = t_
+            sec, wall, *_ = timed_run(host.data_ptr(), IMG_PINNED, g_)
+            print(f"sweep groups={g_:3d} threads={t_:3d}: {S * K * world / sec:10.0f} frames/s  ({sec / K * 1e3:.3f} ms/step)",
+                  file=sys.stderr, flush=True)
+        return
 
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -336,7 +359,8 @@ def main():
                        "step": "one new frame for every sequence of the GPU", "host_groups_per_gpu": ngroups, "host_threads_per_gpu": min(ngroups, threads),
                        "cache": "every step consumes frames never seen before (inputs 0.36 MB x sequences per step, "
                                 f"{S * F * frame_bytes / 1e6:.0f} MB total, larger than L2); no L2 flush needed",
-                       "kf_every": args.kf_every},
+                       "kf_every": args.kf_every,
+                       "sequence_state": "host replay" if args.host_replay else "resident in HBM (sdvlb_seq_*)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": cnt_e[1] / K, "d2h_bytes_per_step": cnt_e[2] / K,
                     "ms_per_step": e2e_sec / K * 1e3},
             "gpu_launches": cnt_v[0],
