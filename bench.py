@@ -239,6 +239,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    extras = {}
+
     def timed_run(base_ptr, on_device, n_groups, timing=False, pipelined=True):
         """Fresh tracker; init + warm-up untimed; K timed steps. Returns seconds (max over ranks), est, stats, extras.
         pipelined: sdvlh_tracker_run (frame batches one step ahead, groups free-running); otherwise every step is one
@@ -280,6 +282,8 @@ def main():
         sec = sharding.max_over_ranks(sec)
         counters = trk.counters(reset=True) + (trk.phases(reset=True),)
         ktimes = trk.timing_read(reset=True) if timing else None
+        if timing and not args.host_replay:
+            extras["post_cycles"] = trk.post_cycles(reset=True)
         ngroups = trk.groups()
         trk.close()
         return sec, wall, est, stats, counters, ktimes, ngroups
@@ -368,6 +372,8 @@ def main():
             "cpu_baseline": cpu_baseline,
             "clocks": clock_info,
             "us_per_gn_iter": us_per_gn_iter,
+            "feature_align_kernel_us_per_frame": {k: v / (clock_info.get("sm_mhz") or 1965.0) for k, v in
+                                                  extras.get("post_cycles", {}).items()},
             "gn_iters_per_frame": gn_iters / (S * K),
             "max_ate_mm_vs_gt": ate_mm,
             "matches_per_frame": float(stats_v[1 + W:, :, 1].mean()),

@@ -346,6 +346,9 @@ typedef struct sdvlb_seq_result {
   int32_t n_feats;     /* entries in feats */
   const sdvlb_seq_feat* feats;             /* pinned host memory, valid until the sequence is submitted again */
   int32_t kf_live[SDVLB_SEQ_KF_CAP];       /* live points per keyframe slot (see sdvlb_seq_add_points) */
+  int32_t phase_cycles[8];                 /* latency breakdown of the FeatureAlign kernel for this sequence, SM cycles:
+                                              cell ranks, SelectPoints, RANSAC hypotheses, RANSAC supporters, RANSAC
+                                              replay + inlier flags, OptimizePose, the rest, (unused) */
 } sdvlb_seq_result;
 
 /* FeatureAlign(map, camera, max_matches) + an empty track: RNG seeded like srand(1), cell order shuffled once

@@ -25,26 +25,17 @@
 
 namespace {
 
-constexpr int PO_MAIN = 256;      // threads doing the FeatureAlign work (named barrier 1)
-constexpr int PO_THREADS = 288;   // + the shuffle warp
+constexpr int PO_MAIN = 128;      // threads doing the FeatureAlign work (named barrier 1)
+constexpr int PO_THREADS = 160;   // + the shuffle warp
 constexpr int NVP = 28;           // A (21, upper triangle) + b (6) + chi2
 constexpr int RANSAC_MAX_PTS = 8;
-constexpr int HYP_MAX = PO_MAIN;
+constexpr int HYP_MAX = 256;      // max_ransac_its supported
 constexpr int MAX_CELLS = 4096;   // 2048 x 2048 / 32^2
 
 constexpr double KMADNorm = 1.4826;            // feature_align.h
 constexpr double KTukeyC = 4.6851 * 4.6851;
 
-__device__ __forceinline__ void main_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-__device__ __forceinline__ double tukey(double x) {   // feature_align.cc:423-431
-  const double x_square = x * x;
-  if (x_square <= KTukeyC) {
-    const double tmp = 1.0 - x_square / KTukeyC;
-    return tmp * tmp;
-  }
-  return 0.0;
-}
+__device__ __forceinline__ void main_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ void store_Rt(const DSE3& T, double* Rt) {
   double R[9];
@@ -64,25 +55,74 @@ __device__ __forceinline__ void reproj(const double* __restrict__ Rt, double a0,
   ey = (a1 - y / z) * s;
 }
 
-// One observation's contribution to A, b, chi2 (feature_align.cc:389-398)
-__device__ __forceinline__ void accumulate_obs(const double* __restrict__ Rt, const PoseProblem& P, int i, double scale,
+// One observation's contribution to A, b, chi2 (feature_align.cc:389-398).  fp64 issue rate is what bounds these
+// kernels, so the reference's expressions are regrouped to the fewest fp64 instructions (same mathematics, rounding
+// differs in the last bits): one reciprocal of z serves the projection and the Jacobian, the Tukey argument
+// (|e|/scale)^2 is e.e * 1/scale^2 (no square root, no division), 2^-level multiplies the weights instead of the
+// twelve Jacobian entries, and the structural zeros of Jacobian3DToPlane (J0[1] = J1[0] = 0) are not multiplied out.
+// inv_scale2 = 1 / scale^2.
+__device__ __forceinline__ void accumulate_obs(const double* __restrict__ Rt, const PoseProblem& P, int i, double inv_scale2,
                                                double acc[NVP]) {
-  double x, y, z, ex, ey;
   const double s = P.o_scale[i];
-  reproj(Rt, P.o_a[2 * i], P.o_a[2 * i + 1], P.o_pos[3 * i], P.o_pos[3 * i + 1], P.o_pos[3 * i + 2], s, x, y, z, ex, ey);
-  double J0[6], J1[6];
-  jacobian3d_to_plane(x, y, z, J0, J1);
-#pragma unroll
-  for (int r = 0; r < 6; r++) { J0[r] *= s; J1[r] *= s; }
-  const double w = tukey(sqrt(ex * ex + ey * ey) / scale);
-  int k = 0;
-#pragma unroll
-  for (int r = 0; r < 6; r++) {
-#pragma unroll
-    for (int q = r; q < 6; q++) { acc[k] += (J0[r] * J0[q] + J1[r] * J1[q]) * w; k++; }
-    acc[21 + r] -= (J0[r] * ex + J1[r] * ey) * w;
+  const double X = P.o_pos[3 * i], Y = P.o_pos[3 * i + 1], Z = P.o_pos[3 * i + 2];
+  const double x = Rt[0] * X + Rt[1] * Y + Rt[2] * Z + Rt[9];
+  const double y = Rt[3] * X + Rt[4] * Y + Rt[5] * Z + Rt[10];
+  const double z = Rt[6] * X + Rt[7] * Y + Rt[8] * Z + Rt[11];
+  const double zi = pivot_rcp(z);
+  const double bx = x * zi, by = y * zi;
+  const double ex = (P.o_a[2 * i] - bx) * s, ey = (P.o_a[2 * i + 1] - by) * s;   // error * 2^-level
+  // Jacobian3DToPlane (extra/utils.cc:99-118) without the level factor
+  const double a = -zi;                 // J0[0] = J1[1]
+  const double j02 = bx * zi, j12 = by * zi;
+  const double j03 = bx * by;           // x y / z^2 = -J1[4]
+  const double j04 = -(1.0 + bx * bx);
+  const double j05 = by;
+  const double j13 = 1.0 + by * by;
+  const double j15 = -bx;
+  const double J0[6] = {a, 0.0, j02, j03, j04, j05};
+  const double J1[6] = {0.0, a, j12, j13, -j03, j15};
+  const double e2 = ex * ex + ey * ey;
+  const double x_square = e2 * inv_scale2;
+  double w = 0.0;
+  if (x_square <= KTukeyC) {            // GetTukeyValue (feature_align.cc:423-431)
+    const double tmp = 1.0 - x_square * (1.0 / KTukeyC);
+    w = tmp * tmp;
   }
-  acc[27] += (ex * ex + ey * ey) * w;
+  const double ws = w * s, wss = ws * s;   // J rows carry 2^-level each
+  // rows 0 and 1 of A: only one of the two Jacobian rows is non-zero there
+  acc[0] += (a * a) * wss;              // (0,0)
+  // (0,1) = 0
+  acc[2] += (a * j02) * wss;  acc[3] += (a * j03) * wss;  acc[4] += (a * j04) * wss;  acc[5] += (a * j05) * wss;
+  acc[6] += (a * a) * wss;              // (1,1)
+  acc[7] += (a * j12) * wss;  acc[8] += (a * j13) * wss;  acc[9] += (a * -j03) * wss; acc[10] += (a * j15) * wss;
+  int k = 11;
+#pragma unroll
+  for (int r = 2; r < 6; r++)
+#pragma unroll
+    for (int q = r; q < 6; q++) { acc[k] += (J0[r] * J0[q] + J1[r] * J1[q]) * wss; k++; }
+#pragma unroll
+  for (int r = 0; r < 6; r++) acc[21 + r] -= (J0[r] * ex + J1[r] * ey) * ws;
+  acc[27] += e2 * w;
+}
+
+// error.norm() <= thr for error = (a - SimpleProject(Rt * pos)) * s (feature_align.cc:269-274), without the two
+// divisions and the square root: |a z - (x, y)|^2 s^2 <= thr^2 z^2.  Both sides carry a relative rounding error below
+// 1e-14; inside a 1e-11 band around equality the reference's own expression decides, so the outcome is always the
+// reference's.
+__device__ __forceinline__ bool within_threshold(const double* __restrict__ Rt, const PoseProblem& P, int i, double thr) {
+  const double s = P.o_scale[i];
+  const double X = P.o_pos[3 * i], Y = P.o_pos[3 * i + 1], Z = P.o_pos[3 * i + 2];
+  const double a0 = P.o_a[2 * i], a1 = P.o_a[2 * i + 1];
+  const double x = Rt[0] * X + Rt[1] * Y + Rt[2] * Z + Rt[9];
+  const double y = Rt[3] * X + Rt[4] * Y + Rt[5] * Z + Rt[10];
+  const double z = Rt[6] * X + Rt[7] * Y + Rt[8] * Z + Rt[11];
+  const double dx = a0 * z - x, dy = a1 * z - y;
+  const double lhs = (dx * dx + dy * dy) * (s * s);
+  const double tz = thr * z;
+  const double rhs = tz * tz;
+  if (fabs(lhs - rhs) > 1e-11 * rhs) return lhs < rhs;
+  const double ex = (a0 - x / z) * s, ey = (a1 - y / z) * s;
+  return sqrt(ex * ex + ey * ey) <= thr;
 }
 
 // A.ldlt().solve(b): register LDL^T when A is safely positive definite, Eigen's pivoted algorithm otherwise
@@ -111,7 +151,7 @@ struct PoseShared {
   int ctrl[4];        // [0] continue, [1] number of selected observations
 };
 
-// FeatureAlign::ConvergePose (feature_align.cc:341-421) over the observations whose flag == sel, by the 256 main
+// FeatureAlign::ConvergePose (feature_align.cc:341-421) over the observations whose flag == sel, by the PO_MAIN main
 // threads.  The result is left in sh.T; returns false (uniformly) when no observation is selected.
 __device__ bool converge_pose_cta(const PoseProblem& P, int sel, const double* T_init, const DevParams& dp,
                                   PoseShared& sh, double (*part)[PO_MAIN]) {
@@ -160,11 +200,12 @@ __device__ bool converge_pose_cta(const PoseProblem& P, int sel, const double* T
   const int max_its = dp.p.max_optim_pose_its;
   for (int it = 0; it < max_its; it++) {
     const double scale = it >= 5 ? 0.85 / dp.cam.fx : sh.scale;   // "force estimator after 5th iteration"
+    const double inv_scale2 = 1.0 / (scale * scale);
     double acc[NVP];
 #pragma unroll
     for (int k = 0; k < NVP; k++) acc[k] = 0.0;
     for (int i = tid; i < P.n; i += PO_MAIN)
-      if (P.o_flag[i] == sel) accumulate_obs(sh.Rt, P, i, scale, acc);
+      if (P.o_flag[i] == sel) accumulate_obs(sh.Rt, P, i, inv_scale2, acc);
 #pragma unroll
     for (int k = 0; k < NVP; k++) part[k][tid] = acc[k];
     main_sync();
@@ -208,8 +249,12 @@ __device__ bool converge_pose_cta(const PoseProblem& P, int sel, const double* T
 }
 
 // ConvergePose for one RANSAC hypothesis (np <= 8 observations (base + k) % size), entirely by one thread.
-__device__ bool converge_pose_small(const PoseProblem& P, int base, int np, int size, const DSE3& T0, const DevParams& dp,
-                                    DSE3* out) {
+// NP > 0: np == NP known at compile time, so the per-observation chains (two divisions, a square root, the Tukey
+// weight) of one Gauss-Newton iteration are interleaved by the scheduler instead of running back to back.
+template <int NP>
+__device__ __forceinline__ bool converge_pose_small(const PoseProblem& P, int base, int np_rt, int size, const DSE3& T0,
+                                                    const DevParams& dp, DSE3* out) {
+  const int np = NP > 0 ? NP : np_rt;
   DSE3 T = T0, last_T = T0;
   double chi2 = 0.0;
   double Rt[12];
@@ -240,10 +285,16 @@ __device__ bool converge_pose_small(const PoseProblem& P, int base, int np, int 
   const int max_its = dp.p.max_optim_pose_its;
   for (int it = 0; it < max_its; it++) {
     const double scale = it >= 5 ? 0.85 / dp.cam.fx : scale0;
+    const double inv_scale2 = 1.0 / (scale * scale);
     double acc[NVP];
 #pragma unroll
     for (int k = 0; k < NVP; k++) acc[k] = 0.0;
-    for (int k = 0; k < np; k++) accumulate_obs(Rt, P, (base + k) % size, scale, acc);
+    if (NP > 0) {
+#pragma unroll
+      for (int k = 0; k < (NP > 0 ? NP : 1); k++) accumulate_obs(Rt, P, (base + k) % size, inv_scale2, acc);
+    } else {
+      for (int k = 0; k < np; k++) accumulate_obs(Rt, P, (base + k) % size, inv_scale2, acc);
+    }
     double dT[6];
     solve6(acc, dT);
     const double new_chi2 = acc[27];
@@ -266,6 +317,7 @@ __device__ bool converge_pose_small(const PoseProblem& P, int base, int np, int 
 }
 
 struct RansacShared {
+  sdvlb_rand backup;         // the stream before the speculative draws
   double hRt[HYP_MAX][12];   // pose of every hypothesis as rotation + translation
   int hsup[HYP_MAX];         // supporters
   int hconv[HYP_MAX];        // ConvergePose returned true
@@ -276,35 +328,37 @@ struct RansacShared {
 // FeatureAlign::SelectInliers (feature_align.cc:152-216) over P (= fs_found): flags every observation INLIER/OUTLIER.
 // T_frame: frame->GetPose().  *rng advances by the reference's number of rand() calls.  Main threads only.
 __device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, const DevParams& dp, sdvlb_rand* rng,
-                                   RansacShared& rs) {
+                                   RansacShared& rs, long long* stamps = nullptr) {
   const int tid = threadIdx.x;
   const int size = P.n;
   if (size == 0) return;
   const int R = min(dp.p.max_ransac_its, HYP_MAX);
   const int np = min(min(dp.p.max_ransac_points, size), RANSAC_MAX_PTS);
   const double thr = dp.p.inlier_error_threshold / dp.cam.fx;
-  if (tid == 0) {
-    sdvlb_rand copy = *rng;   // speculative draws; the stream itself advances by `draws` below
-    for (int h = 0; h < R; h++) rs.rnd[h] = rand_next(&copy);
-  }
-  if (tid < R) rs.hsup[tid] = 0;
+  if (tid < 34) rs.backup.r[tid] = rng->r[tid];
+  if (tid == 0) rs.backup.n = rng->n;
   main_sync();
-  if (tid < R) {
+  if (tid == 0)   // speculative draws for every hypothesis; the stream is rewound to the reference's count below
+    for (int h = 0; h < R; h++) rs.rnd[h] = rand_next(rng);
+  main_sync();
+  for (int h = tid; h < R; h += PO_MAIN) {
     DSE3 T;
-    const bool ok = converge_pose_small(P, rs.rnd[tid] % size, np, size, se3_load(T_frame), dp, &T);
-    rs.hconv[tid] = ok ? 1 : 0;
-    store_Rt(T, rs.hRt[tid]);
+    const bool ok = np == 5 ? converge_pose_small<5>(P, rs.rnd[h] % size, np, size, se3_load(T_frame), dp, &T)
+                            : converge_pose_small<0>(P, rs.rnd[h] % size, np, size, se3_load(T_frame), dp, &T);
+    rs.hconv[h] = ok ? 1 : 0;
+    double Rt[12];
+    store_Rt(T, Rt);
+#pragma unroll
+    for (int k = 0; k < 12; k++) rs.hRt[h][k] = Rt[k];
+    // CheckReprojectionError of this hypothesis against every match (feature_align.cc:258-283); the observation
+    // loads are warp-uniform
+    int sup = 0;
+    for (int i = 0; i < size; i++) sup += within_threshold(Rt, P, i, thr) ? 1 : 0;
+    rs.hsup[h] = sup;
   }
   main_sync();
-  // CheckReprojectionError of every hypothesis against every match (feature_align.cc:258-283)
-  for (int p = tid; p < R * size; p += PO_MAIN) {
-    const int h = p / size, i = p - h * size;
-    double x, y, z, ex, ey;
-    reproj(rs.hRt[h], P.o_a[2 * i], P.o_a[2 * i + 1], P.o_pos[3 * i], P.o_pos[3 * i + 1], P.o_pos[3 * i + 2],
-           P.o_scale[i], x, y, z, ex, ey);
-    if (sqrt(ex * ex + ey * ey) <= thr) atomicAdd(&rs.hsup[h], 1);
-  }
-  main_sync();
+  if (stamps) stamps[0] = clock64();
+  if (stamps) stamps[1] = clock64();
   if (tid == 0) {   // the reference's loop, replayed over the precomputed hypotheses
     const double sprob = 0.99;
     int nits = dp.p.max_ransac_its, it = 0, best_supporters = 0, best = -1;
@@ -322,7 +376,11 @@ __device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, 
     }
     rs.best = best;
     rs.draws = it;
-    for (int k = 0; k < it; k++) rand_next(rng);
+    if (it < R) {   // rewind: the reference drew `it` numbers only
+      for (int k = 0; k < 34; k++) rng->r[k] = rs.backup.r[k];
+      rng->n = rs.backup.n;
+      for (int k = 0; k < it; k++) rand_next(rng);
+    }
   }
   main_sync();
   // "Get low innovation inliers" with best_se3 (identity when no hypothesis ever had a supporter)
@@ -385,54 +443,61 @@ __device__ void optimize_pose_cta(const PoseProblem& P, double* T_frame, const D
 }
 
 // ------------------------------------------------------------------------------------------------ commands
-__global__ void __launch_bounds__(128) seq_apply_kernel(const SeqCmd* __restrict__ cmds, const __grid_constant__ DevParams dp) {
-  const SeqCmd& C = cmds[blockIdx.x];
-  SeqState* S = C.seq;
+// One CTA per sequence that has commands; its commands are contiguous and applied in order.
+__global__ void __launch_bounds__(128) seq_apply_kernel(const SeqCmd* __restrict__ cmds, const int2* __restrict__ ranges,
+                                                        const __grid_constant__ DevParams dp) {
+  const int2 range = ranges[blockIdx.x];   // (first command, count)
   const int tid = threadIdx.x;
-  if (C.kind == 0) {
-    if (tid == 0) {
-      for (int i = 0; i < 7; i++) S->T_last[i] = C.T[i];
-      for (int i = 0; i < 6; i++) S->vel[i] = 0.0;
-      S->last = C.frame;
-      S->has_last = 1;
-      S->n_list = 0;
-      S->n_cands = 0;
-      for (int i = 0; i < 7; i++) C.frame.pose[i] = C.T[i];
-    }
-    return;
-  }
-  // append points to the current list (keyframe seeding / mapping thread output)
   __shared__ int s_base;
-  if (tid == 0) {
-    s_base = S->n_list;
-    SeqKf& K = S->kf[C.kf_slot];
-    K.pyr = C.kf_pyr;
-    for (int i = 0; i < 7; i++) K.T[i] = C.T[i];
+  for (int ci = range.x; ci < range.x + range.y; ci++) {
+    const SeqCmd& C = cmds[ci];
+    SeqState* S = C.seq;
+    if (C.kind == 0) {
+      if (tid == 0) {
+        for (int i = 0; i < 7; i++) S->T_last[i] = C.T[i];
+        for (int i = 0; i < 6; i++) S->vel[i] = 0.0;
+        S->last = C.frame;
+        S->has_last = 1;
+        S->n_list = 0;
+        S->n_cands = 0;
+        for (int i = 0; i < 7; i++) C.frame.pose[i] = C.T[i];
+      }
+      __syncthreads();
+      continue;
+    }
+    // append points to the current list (keyframe seeding / mapping thread output)
+    if (tid == 0) {
+      s_base = S->n_list;
+      SeqKf& K = S->kf[C.kf_slot];
+      K.pyr = C.kf_pyr;
+      for (int i = 0; i < 7; i++) K.T[i] = C.T[i];
+    }
+    __syncthreads();
+    const int base = s_base;
+    SeqFeat* L = S->list[S->cur];
+    for (int k = tid; k < C.n; k += blockDim.x) {
+      if (base + k >= S->max_feats) break;
+      const sdvlb_seq_point p = C.pts[k];
+      SeqFeat f;
+      f.px[0] = p.cur_px[0]; f.px[1] = p.cur_px[1];
+      cam_unproject_unit(dp.cam, p.cur_px[0], p.cur_px[1], f.v);
+      f.pos[0] = p.pos[0]; f.pos[1] = p.pos[1]; f.pos[2] = p.pos[2];
+      f.ref_px[0] = p.ref_px[0]; f.ref_px[1] = p.ref_px[1];
+      cam_unproject_unit(dp.cam, p.ref_px[0], p.ref_px[1], f.ref_v);
+      f.idepth = p.idepth; f.idepth_std = p.idepth_std;
+      f.user_id = p.user_id;
+      f.level = p.cur_level; f.ref_level = p.ref_level;
+      f.kf = C.kf_slot;
+      f.flags = SEQF_HAS_POINT | ((p.flags & SDVLB_CAND_FIXED) ? SEQF_FIXED : 0);
+      f.n_successful = p.n_successful; f.n_failed = p.n_failed;
+      f.status = SEQP_FOUND;
+      f.n_unpromoted = 0;
+      L[base + k] = f;
+    }
+    __syncthreads();
+    if (tid == 0) S->n_list = min(base + C.n, S->max_feats);
+    __syncthreads();
   }
-  __syncthreads();
-  const int base = s_base;
-  SeqFeat* L = S->list[S->cur];
-  for (int k = tid; k < C.n; k += blockDim.x) {
-    if (base + k >= S->max_feats) break;
-    const sdvlb_seq_point p = C.pts[k];
-    SeqFeat f;
-    f.px[0] = p.cur_px[0]; f.px[1] = p.cur_px[1];
-    cam_unproject_unit(dp.cam, p.cur_px[0], p.cur_px[1], f.v);
-    f.pos[0] = p.pos[0]; f.pos[1] = p.pos[1]; f.pos[2] = p.pos[2];
-    f.ref_px[0] = p.ref_px[0]; f.ref_px[1] = p.ref_px[1];
-    cam_unproject_unit(dp.cam, p.ref_px[0], p.ref_px[1], f.ref_v);
-    f.idepth = p.idepth; f.idepth_std = p.idepth_std;
-    f.user_id = p.user_id;
-    f.level = p.cur_level; f.ref_level = p.ref_level;
-    f.kf = C.kf_slot;
-    f.flags = SEQF_HAS_POINT | ((p.flags & SDVLB_CAND_FIXED) ? SEQF_FIXED : 0);
-    f.n_successful = p.n_successful; f.n_failed = p.n_failed;
-    f.status = SEQP_FOUND;
-    f.n_unpromoted = 0;
-    L[base + k] = f;
-  }
-  __syncthreads();
-  if (tid == 0) S->n_list = min(base + C.n, S->max_feats);
 }
 
 // ------------------------------------------------------------------------------------------------ prep
@@ -537,7 +602,7 @@ struct PostShared {
   int kf_live[SDVLB_SEQ_KF_CAP];
 };
 
-__global__ void __launch_bounds__(PO_THREADS) seq_post_kernel(const __grid_constant__ SeqStepArgs A) {
+__global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_constant__ SeqStepArgs A) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   PostShared& sh = *reinterpret_cast<PostShared*>(s_raw);
   double (*part)[PO_MAIN] = reinterpret_cast<double (*)[PO_MAIN]>(s_raw + ((sizeof(PostShared) + 15) / 16) * 16);
@@ -547,7 +612,7 @@ __global__ void __launch_bounds__(PO_THREADS) seq_post_kernel(const __grid_const
   const int gw = A.g.wcells[0];
   if (!S->has_last) return;   // uniform: nothing was tracked (no reset yet)
 
-  // ---- load the persistent FeatureAlign state (all 288 threads)
+  // ---- load the persistent FeatureAlign state (all PO_THREADS threads)
   for (int i = tid; i < n_cells; i += PO_THREADS) { sh.order[i] = S->cell_order[i]; sh.win[i] = INT_MAX; sh.slot[i] = -1; }
   if (tid < 34) sh.rng.r[tid] = S->rng.r[tid];
   if (tid == 0) {
@@ -560,8 +625,8 @@ __global__ void __launch_bounds__(PO_THREADS) seq_post_kernel(const __grid_const
 
   if (tid >= PO_MAIN) {
     // ---- shuffle warp: std::random_shuffle(cell_order_) for the NEXT frame (feature_align.cc:103), once SelectInliers
-    // has taken its draws.  Waits on barrier 2 (all 288 threads).
-    asm volatile("bar.sync 2, 288;" ::: "memory");
+    // has taken its draws.  Waits on barrier 2 (all PO_THREADS threads).
+    asm volatile("bar.sync 2, 160;" ::: "memory");
     if (tid == PO_MAIN) {
       for (int i = 1; i < n_cells; ++i) {
         const int j = rand_next(&sh.rng) % (i + 1);
@@ -578,6 +643,8 @@ __global__ void __launch_bounds__(PO_THREADS) seq_post_kernel(const __grid_const
   }
 
   // =============================== main threads (barrier 1) ===============================
+  long long t_phase[8];
+  t_phase[0] = clock64();
   const SeqFeat* __restrict__ L = S->list[S->cur];
   SeqFeat* __restrict__ NL = S->list[S->cur ^ 1];
   const int nc = S->n_cands;
@@ -610,6 +677,7 @@ __global__ void __launch_bounds__(PO_THREADS) seq_post_kernel(const __grid_const
     if (M[i].status == SDVLB_MATCH_FOUND) atomicMin(&sh.win[cell], rank);
   }
   main_sync();
+  t_phase[1] = clock64();
   // ---- cells in cell_order_: exclusive prefix sum of "has a match" -> max_matches cut-off and fs_found index
   {
     const int per = (n_cells + PO_MAIN - 1) / PO_MAIN;
@@ -673,12 +741,16 @@ __global__ void __launch_bounds__(PO_THREADS) seq_post_kernel(const __grid_const
   main_sync();
 
   // ---- SelectInliers (RANSAC)
-  select_inliers_cta(P, sh.T_frame, A.dp, &sh.rng, sh.rs);
-  asm volatile("bar.sync 2, 288;" ::: "memory");   // releases the shuffle warp: rand() is its from here on
+  t_phase[2] = clock64();
+  t_phase[6] = t_phase[7] = t_phase[2];
+  select_inliers_cta(P, sh.T_frame, A.dp, &sh.rng, sh.rs, t_phase + 6);
+  t_phase[3] = clock64();
+  asm volatile("bar.sync 2, 160;" ::: "memory");   // releases the shuffle warp: rand() is its from here on
 
   // ---- OptimizePose + RescueOutliers + OptimizePose (feature_align.cc:73-82)
   optimize_pose_cta(P, sh.T_frame, A.dp, sh.ps, part);
   main_sync();
+  t_phase[4] = clock64();
 
   // ---- RemoveOutliers (feature_align.cc:245-256), result, GetMotionModel, state update
   SeqResultHost* Rz = S->result;
@@ -722,6 +794,16 @@ __global__ void __launch_bounds__(PO_THREADS) seq_post_kernel(const __grid_const
     Rz->stats[6] = S->align_info[1];
     Rz->stats[7] = n_found;
     Rz->error = 0;
+    // latency breakdown of this kernel in SM cycles
+    t_phase[5] = clock64();
+    Rz->phase_cycles[0] = int(t_phase[1] - t_phase[0]);
+    Rz->phase_cycles[1] = int(t_phase[2] - t_phase[1]);
+    Rz->phase_cycles[2] = int(t_phase[6] - t_phase[2]);   // RANSAC: draws + hypotheses
+    Rz->phase_cycles[3] = int(t_phase[7] - t_phase[6]);   //         supporters
+    Rz->phase_cycles[4] = int(t_phase[3] - t_phase[7]);   //         replay + final inlier flags
+    Rz->phase_cycles[5] = int(t_phase[4] - t_phase[3]);
+    Rz->phase_cycles[6] = int(t_phase[5] - t_phase[4]);
+    Rz->phase_cycles[7] = 0;
   }
 }
 
@@ -733,7 +815,7 @@ struct PoseCallShared {
   sdvlb_rand rng;
 };
 
-__global__ void __launch_bounds__(PO_MAIN) pose_call_kernel(const __grid_constant__ PoseCallArgs A) {
+__global__ void __launch_bounds__(PO_MAIN, 1) pose_call_kernel(const __grid_constant__ PoseCallArgs A) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   PoseCallShared& sh = *reinterpret_cast<PoseCallShared*>(s_raw);
   double (*part)[PO_MAIN] = reinterpret_cast<double (*)[PO_MAIN]>(s_raw + ((sizeof(PoseCallShared) + 15) / 16) * 16);
@@ -776,9 +858,10 @@ cudaError_t opt_in_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
-cudaError_t sdvlb_launch_seq_apply(const SeqCmd* d_cmds, int n, const DevParams& dp, cudaStream_t stream) {
-  if (n <= 0) return cudaSuccess;
-  seq_apply_kernel<<<n, 128, 0, stream>>>(d_cmds, dp);
+cudaError_t sdvlb_launch_seq_apply(const SeqCmd* d_cmds, const int2* d_ranges, int n_ranges, const DevParams& dp,
+                                   cudaStream_t stream) {
+  if (n_ranges <= 0) return cudaSuccess;
+  seq_apply_kernel<<<n_ranges, 128, 0, stream>>>(d_cmds, d_ranges, dp);
   return cudaGetLastError();
 }
 

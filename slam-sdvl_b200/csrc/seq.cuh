@@ -38,6 +38,7 @@ struct SeqResultHost {
   int32_t stats[8];    // n_tracked(n_meas), matches, attempts, inliers, outliers, n_points, gn_iters, n_feats
   int32_t kf_live[SDVLB_SEQ_KF_CAP];
   int32_t error;       // != 0: a capacity was exceeded
+  int32_t phase_cycles[8];   // seq_post_kernel latency breakdown (SM cycles of the sequence's CTA)
   int32_t pad_[7];
   // sdvlb_seq_feat feats[max_feats] follows
 };
@@ -118,7 +119,8 @@ struct PoseCallArgs {
   DevParams dp;
 };
 
-cudaError_t sdvlb_launch_seq_apply(const SeqCmd* d_cmds, int n, const DevParams& dp, cudaStream_t stream);
+cudaError_t sdvlb_launch_seq_apply(const SeqCmd* d_cmds, const int2* d_ranges, int n_ranges, const DevParams& dp,
+                                   cudaStream_t stream);
 cudaError_t sdvlb_launch_seq_prep(const SeqStepArgs& A, cudaStream_t stream);
 cudaError_t sdvlb_launch_seq_post(const SeqStepArgs& A, cudaStream_t stream);
 cudaError_t sdvlb_launch_pose_call(const PoseCallArgs& A, cudaStream_t stream);

@@ -282,37 +282,32 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
   if (n_cmds > 0) {
     Arena& in = c->seq_in;
     in.used = 0;
-    const size_t need = 1024 + size_t(n_cmds) * sizeof(SeqCmd) + c->seq_pts.size() * sizeof(sdvlb_seq_point);
+    const size_t need = 2048 + size_t(n_cmds) * (sizeof(SeqCmd) + sizeof(int2)) + c->seq_pts.size() * sizeof(sdvlb_seq_point);
     rc = ensure_arena(&in, need, true);
     if (rc) return rc;
     const size_t o_cmds = in.take(size_t(n_cmds) * sizeof(SeqCmd));
+    const size_t o_ranges = in.take(size_t(n_cmds) * sizeof(int2));
     const size_t o_pts = in.take(std::max<size_t>(1, c->seq_pts.size()) * sizeof(sdvlb_seq_point));
+    // commands grouped by sequence, order kept inside a sequence: one CTA applies a sequence's commands in order
+    std::vector<int> idx(n_cmds);
+    for (int k = 0; k < n_cmds; k++) idx[k] = k;
+    std::stable_sort(idx.begin(), idx.end(), [c](int a, int b) { return c->seq_cmds[a].seq < c->seq_cmds[b].seq; });
     SeqCmd* hc = reinterpret_cast<SeqCmd*>(in.h + o_cmds);
+    int2* hr = reinterpret_cast<int2*>(in.h + o_ranges);
+    int n_ranges = 0;
     for (int k = 0; k < n_cmds; k++) {
-      hc[k] = c->seq_cmds[k];
-      if (hc[k].kind == 1)
-        hc[k].pts = reinterpret_cast<const sdvlb_seq_point*>(in.d + o_pts) + reinterpret_cast<size_t>(c->seq_cmds[k].pts);
+      const SeqCmd& src = c->seq_cmds[idx[k]];
+      hc[k] = src;
+      if (src.kind == 1) hc[k].pts = reinterpret_cast<const sdvlb_seq_point*>(in.d + o_pts) + reinterpret_cast<size_t>(src.pts);
+      if (k == 0 || src.seq != c->seq_cmds[idx[k - 1]].seq) { hr[n_ranges].x = k; hr[n_ranges].y = 1; n_ranges++; }
+      else hr[n_ranges - 1].y++;
     }
     if (!c->seq_pts.empty()) memcpy(in.h + o_pts, c->seq_pts.data(), c->seq_pts.size() * sizeof(sdvlb_seq_point));
     SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, in.used, cudaMemcpyHostToDevice, c->stream));
     c->h2d_bytes += int64_t(in.used);
-    timer_begin(c, SDVLB_K_PREP);
-    // commands of one sequence must apply in order: one launch per run of distinct sequences would be needed in
-    // general; commands are rare (keyframes), so they are simply applied one launch each when a sequence repeats
-    int k0 = 0;
-    while (k0 < n_cmds) {
-      int k1 = k0 + 1;
-      while (k1 < n_cmds) {
-        bool repeat = false;
-        for (int q = k0; q < k1 && !repeat; q++) repeat = c->seq_cmds[q].seq == c->seq_cmds[k1].seq;
-        if (repeat) break;
-        k1++;
-      }
-      SDVLB_CUDA_TRY(sdvlb_launch_seq_apply(reinterpret_cast<const SeqCmd*>(in.d + o_cmds) + k0, k1 - k0, c->dp, c->stream));
-      c->n_launches += 1;
-      k0 = k1;
-    }
-    timer_end(c);
+    SDVLB_CUDA_TRY(sdvlb_launch_seq_apply(reinterpret_cast<const SeqCmd*>(in.d + o_cmds),
+                                          reinterpret_cast<const int2*>(in.d + o_ranges), n_ranges, c->dp, c->stream));
+    c->n_launches += 1;
     for (sdvlb_seq* s : c->seqs)
       for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++)
         if (s->kf_state[k] == 1) s->kf_state[k] = 2;
@@ -388,6 +383,7 @@ int sdvlb_seq_track_collect(sdvlb_ctx* c, sdvlb_seq_result* results) {
     o.n_feats = R->stats[7];
     o.feats = reinterpret_cast<const sdvlb_seq_feat*>(reinterpret_cast<const uint8_t*>(R) + sizeof(SeqResultHost));
     memcpy(o.kf_live, R->kf_live, sizeof(o.kf_live));
+    memcpy(o.phase_cycles, R->phase_cycles, sizeof(o.phase_cycles));
     for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++) {
       if (R->kf_live[k] > 0) { if (s->kf_state[k] != 1) s->kf_state[k] = 3; }
       else if (s->kf_state[k] == 2 || s->kf_state[k] == 3) s->kf_state[k] = 0;

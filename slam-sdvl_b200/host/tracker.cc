@@ -494,6 +494,8 @@ class Group {
         gt_pose.ToArray(est + 7 * o);
       } else {
         const sdvlb_seq_result& r = results_[i];
+        for (int k = 0; k < 8; k++) post_cycles_[k] += r.phase_cycles[k];
+        post_cycles_[8] += 1;
         st[0] = r.n_tracked; st[1] = r.matches; st[2] = r.attempts; st[3] = r.inliers; st[4] = r.outliers;
         st[6] = r.gn_iters;
         std::memcpy(est + 7 * o, r.pose, 7 * sizeof(double));
@@ -542,6 +544,9 @@ class Group {
   vector<sdvlb_track_job> jobs_;
   int kf_every_ = 0;
   bool resident_ = false, tracked_ = false;
+ public:
+  double post_cycles_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // seq_post_kernel phase cycles summed over frames, [8] = frames
+ private:
   vector<ResidentSeq> rseqs_;
   vector<sdvlb_seq*> seq_handles_;
   vector<sdvlb_seq_result> results_;
@@ -632,6 +637,11 @@ class BatchTracker {
       for (int i = 0; i < 8; i++) out[i] += ph[i];
       if (reset) g->reset_phases();
     }
+  }
+  void PostCycles(double out[9], int reset) {
+    for (int i = 0; i < 9; i++) out[i] = 0;
+    for (auto& g : groups_)
+      for (int i = 0; i < 9; i++) { out[i] += g->post_cycles_[i]; if (reset) g->post_cycles_[i] = 0; }
   }
   sdvlb_ctx* ctx0() { return groups_[0]->ctx(); }
   int n_seq() const { return n_seq_; }
@@ -809,6 +819,13 @@ int sdvlh_tracker_counters(void* t, int64_t* launches, int64_t* h2d, int64_t* d2
 // polling (every group of the thread in flight).
 int sdvlh_tracker_phases(void* t, double out[8], int reset) {
   static_cast<sdvl::BatchTracker*>(t)->Phases(out, reset);
+  return 0;
+}
+
+// Latency breakdown of the device-side FeatureAlign kernel, summed over tracked frames (SM cycles): cell ranks,
+// SelectPoints, RANSAC hypotheses / supporters / replay, OptimizePose, the rest, (unused); out[8] = number of frames.
+int sdvlh_tracker_post_cycles(void* t, double out[9], int reset) {
+  static_cast<sdvl::BatchTracker*>(t)->PostCycles(out, reset);
   return 0;
 }
 
