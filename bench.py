@@ -181,6 +181,11 @@ def main():
     ap.add_argument("--kf-every", type=int, default=20)
     ap.add_argument("--config", default="C2")
     ap.add_argument("--sweep", default="", help="comma list of GROUPSxTHREADS to time (e2e only), e.g. 8x4,16x8")
+    ap.add_argument("--prefetch", type=int, default=2, help="frame batches are built this many steps ahead")
+    ap.add_argument("--sweep-device", action="store_true", help="sweep with the frames resident in HBM")
+    ap.add_argument("--e2e-upload", default="kernel", choices=["dma", "kernel"],
+                    help="how level 0 crosses PCIe in the e2e run: copy engine (cudaMemcpyAsync per frame) or the "
+                         "one-kernel upload reading pinned host memory")
     ap.add_argument("--host-replay", action="store_true",
                     help="previous design: FeatureAlign bookkeeping + pose refinement on the host (for comparison)")
     args = ap.parse_args()
@@ -248,6 +253,7 @@ def main():
         trk = binding.HostTracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], args.kf_every, S, n_groups,
                                   device=local_rank, timing=timing, n_threads=min(n_groups, threads),
                                   resident=not args.host_replay)
+        trk.set_prefetch(args.prefetch)
         est = np.zeros((S, F, 7))
         stats = np.zeros((F, S, 8), np.int32)
 
@@ -288,11 +294,17 @@ def main():
         trk.close()
         return sec, wall, est, stats, counters, ktimes, ngroups
 
+    e2e_loc = IMG_HOST if args.e2e_upload == "dma" else IMG_PINNED
     if args.sweep:   # host-side configuration sweep (groups x threads), e2e placement; prints a table and exits
         for spec in args.sweep.split(","):
             g_, t_ = (int(v) for v in spec.split("x"))
             threads = t_
-            sec, wall, *_ = timed_run(host.data_ptr(), IMG_PINNED, g_)
+            if args.sweep_device:
+                if "dev" not in extras:
+                    extras["dev"] = host.cuda(non_blocking=False)
+                sec, wall, *_ = timed_run(extras["dev"].data_ptr(), IMG_DEVICE, g_)
+            else:
+                sec, wall, *_ = timed_run(host.data_ptr(), e2e_loc, g_)
             print(f"sweep groups={g_:3d} threads={t_:3d}: {S * K * world / sec:10.0f} frames/s  ({sec / K * 1e3:.3f} ms/step)",
                   file=sys.stderr, flush=True)
         return
@@ -300,7 +312,7 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     # ---- e2e: frames in pinned host memory
-    e2e_sec, e2e_wall, est_e, stats_e, cnt_e, _, ngroups = timed_run(host.data_ptr(), IMG_PINNED, groups)
+    e2e_sec, e2e_wall, est_e, stats_e, cnt_e, _, ngroups = timed_run(host.data_ptr(), e2e_loc, groups)
     # ---- value: frames resident in HBM
     dev = host.cuda(non_blocking=False)
     val_sec, val_wall, est_v, stats_v, cnt_v, _, _ = timed_run(dev.data_ptr(), IMG_DEVICE, groups)

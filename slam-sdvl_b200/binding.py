@@ -194,7 +194,7 @@ _HLIB = None
 HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", "sdvlh_tracker_destroy",
                 "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_phases",
                 "sdvlh_tracker_ctx", "sdvlh_tracker_groups", "sdvlh_tracker_threads", "sdvlh_tracker_run",
-                "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles"]
+                "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles", "sdvlh_tracker_set_prefetch"]
 
 
 def build_host(verbose=False):
@@ -303,6 +303,9 @@ class HostTracker:
         load_host().sdvlh_tracker_phases(C.c_void_p(self.h), a, int(reset))
         return {"marshal_s": a[0], "gpu_submit_wait_s": a[1], "replay_s": a[2], "replay_apply_matches_s": a[3],
                 "replay_ransac_s": a[4], "replay_finish_frame_s": a[5], "gpu_wait_only_s": a[6], "idle_poll_s": a[7]}
+
+    def set_prefetch(self, depth):
+        load_host().sdvlh_tracker_set_prefetch(C.c_void_p(self.h), int(depth))
 
     def post_cycles(self, reset=True):
         """Average SM cycles per tracked frame in the phases of the device-side FeatureAlign kernel."""

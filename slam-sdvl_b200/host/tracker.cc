@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <deque>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -257,7 +258,7 @@ class Group {
     if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_create failed: ") + sdvlb_last_error());
     if (timing) sdvlb_timing_enable(ctx_, 1);
     // current + prefetched + reference frame and a handful of live keyframes per sequence: no allocation while tracking
-    if (sdvlb_ctx_reserve_frames(ctx_, 16 * n_seq))
+    if (sdvlb_ctx_reserve_frames(ctx_, 20 * n_seq))
       throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_reserve_frames failed: ") + sdvlb_last_error());
     for (auto& s : seqs_) driver_.InitSequence(&s);
     for (auto& r : rseqs_) {
@@ -340,7 +341,14 @@ class Group {
     step_ = 0; in_flight_ = false;
     built_.assign(size(), nullptr);
     next_built_.assign(size(), nullptr);
+    ahead_.clear();
     if (n_steps_ > 0) SubmitBuild(0, &built_);
+    // frame batches are built `prefetch_` steps ahead of the tracking they feed, so that the PCIe link (uploads) and
+    // the build stream never wait for the host between steps
+    for (int k = 1; k < prefetch_ && k < n_steps_; k++) {
+      ahead_.emplace_back(size(), nullptr);
+      SubmitBuild(k, &ahead_.back());
+    }
   }
   bool RunDone() const { return step_ >= n_steps_; }
   void AddIdle(double s) { phase_s_[7] += s; }
@@ -349,7 +357,10 @@ class Group {
   void SubmitStep() {   // build(step+1) then track(step)
     Device::SetCurrent(ctx_);
     const auto tA = std::chrono::steady_clock::now();
-    if (step_ + 1 < n_steps_) SubmitBuild(step_ + 1, &next_built_);
+    if (step_ + prefetch_ < n_steps_) {
+      ahead_.emplace_back(size(), nullptr);
+      SubmitBuild(step_ + prefetch_, &ahead_.back());
+    }
     if (resident_) {
       const auto tB = std::chrono::steady_clock::now();
       tracked_ = SubmitResident();
@@ -385,7 +396,7 @@ class Group {
       const double waited = FinishResident(tracked_, gt_ + 7 * size_t(step_), stride_, step_, est_ + 7 * size_t(step_),
                                            stats_ + 8 * size_t(step_));
       in_flight_ = false;
-      built_.swap(next_built_);
+      AdvanceBuilt();
       step_++;
       const double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - tA).count();
       phase_s_[1] += waited;
@@ -404,7 +415,7 @@ class Group {
       std::memset(st, 0, 8 * sizeof(int32_t));
       ReplayJob(i, SE3(gt_ + 7 * o), est_ + 7 * o, st);
     }
-    built_.swap(next_built_);
+    AdvanceBuilt();
     step_++;
     const auto tC = std::chrono::steady_clock::now();
     phase_s_[1] += std::chrono::duration<double>(tB - tA).count();
@@ -529,6 +540,12 @@ class Group {
     phase_s_[5] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
     return waited;
   }
+  void AdvanceBuilt() {
+    if (!ahead_.empty()) {
+      built_.swap(ahead_.front());
+      ahead_.pop_front();
+    }
+  }
   void SubmitBuild(int step, vector<sdvlb_frame*>* out) {
     const int n = size();
     img_ptrs_.resize(n);
@@ -562,6 +579,10 @@ class Group {
   int32_t* stats_ = nullptr;
   bool in_flight_ = false;
   vector<sdvlb_frame*> built_, next_built_;
+  std::deque<vector<sdvlb_frame*>> ahead_;   // frame batches of the steps after the current one, oldest first
+ public:
+  int prefetch_ = 2;
+ private:
   vector<const uint8_t*> img_ptrs_;
 };
 
@@ -638,6 +659,7 @@ class BatchTracker {
       if (reset) g->reset_phases();
     }
   }
+  void SetPrefetch(int depth) { for (auto& g : groups_) g->prefetch_ = std::max(1, std::min(depth, 6)); }
   void PostCycles(double out[9], int reset) {
     for (int i = 0; i < 9; i++) out[i] = 0;
     for (auto& g : groups_)
@@ -828,6 +850,9 @@ int sdvlh_tracker_post_cycles(void* t, double out[9], int reset) {
   static_cast<sdvl::BatchTracker*>(t)->PostCycles(out, reset);
   return 0;
 }
+
+// How many steps ahead of the tracking the frame batches (upload + pyramid + FAST) are submitted in sdvlh_tracker_run.
+void sdvlh_tracker_set_prefetch(void* t, int depth) { static_cast<sdvl::BatchTracker*>(t)->SetPrefetch(depth); }
 
 void* sdvlh_tracker_ctx(void* t) { return static_cast<sdvl::BatchTracker*>(t)->ctx0(); }
 int sdvlh_tracker_groups(void* t) { return static_cast<sdvl::BatchTracker*>(t)->n_groups(); }
