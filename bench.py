@@ -384,7 +384,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "clocks": clock_info,
             "us_per_gn_iter": us_per_gn_iter,
-            "feature_align_kernel_us_per_frame": {k: v / (clock_info.get("sm_mhz") or 1965.0) for k, v in
+            "align_and_feature_align_kernel_us_per_frame": {k: v / (clock_info.get("sm_mhz") or 1965.0) for k, v in
                                                   extras.get("post_cycles", {}).items()},
             "gn_iters_per_frame": gn_iters / (S * K),
             "max_ate_mm_vs_gt": ate_mm,

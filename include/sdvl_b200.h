@@ -349,6 +349,8 @@ typedef struct sdvlb_seq_result {
   int32_t phase_cycles[8];                 /* latency breakdown of the FeatureAlign kernel for this sequence, SM cycles:
                                               cell ranks, SelectPoints, RANSAC hypotheses, RANSAC supporters, RANSAC
                                               replay + inlier flags, OptimizePose, the rest, (unused) */
+  int32_t align_cycles[4];                 /* same for the ImageAlign kernel: PrecomputePatches, residuals,
+                                              reduction, solve + pose update */
 } sdvlb_seq_result;
 
 /* FeatureAlign(map, camera, max_matches) + an empty track: RNG seeded like srand(1), cell order shuffled once

@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
   }
   __syncthreads();
 
+  long long cyc[4] = {0, 0, 0, 0};   // thread 0: PrecomputePatches, residuals, reduction, solve + update (SM cycles)
+  long long t_mark = clock64();
   bool level_break = false;   // uniform (derived from shared state)
   for (int level = P.max_align_level; level >= P.min_align_level && !level_break; level--) {
     const int W = A.g.w[level], Hh = A.g.h[level];
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
         }
       }
       __syncthreads();
+      if (tid == 0) { const long long t = clock64(); cyc[0] += t - t_mark; t_mark = t; }
 
       // ---- ComputeResiduals (image_align.cc:127-206)
       double acc[NV];
@@ -225,6 +228,7 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
 #pragma unroll
       for (int i = 0; i < NV; i++) s_part[i][tid] = acc[i];
       __syncthreads();
+      if (tid == 0) { const long long t = clock64(); cyc[1] += t - t_mark; t_mark = t; }
       // fixed-order tree: warp w reduces rows w, w+8, ...
       for (int v = warp; v < 29; v += AL_THREADS / 32) {
         double s = 0;
@@ -238,6 +242,7 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
 
       // ---- Optimize step on thread 0 (image_align.cc:91-124)
       if (tid == 0) {
+        { const long long t = clock64(); cyc[2] += t - t_mark; t_mark = t; }
         double Hm[6][6], b[6], x[6];
         {
           int k = 0;
@@ -294,6 +299,7 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
         trace_n++;
         se3_store(T, s_T);
         s_ctrl[0] = cont;
+        { const long long t = clock64(); cyc[3] += t - t_mark; t_mark = t; }
       }
       __syncthreads();
       if (!s_ctrl[0]) break;
@@ -315,6 +321,8 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
     J.out_info[0] = n_meas_last;
     J.out_info[1] = trace_n;
     *J.out_error = error_;
+    if (J.out_cycles)
+      for (int i = 0; i < 4; i++) J.out_cycles[i] = int(cyc[i]);
   }
 }
 

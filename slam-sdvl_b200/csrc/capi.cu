@@ -393,6 +393,7 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
       a.out_pose = hres->pose;
       a.out_info = hres->info;
       a.out_error = &hres->error;
+      a.out_cycles = nullptr;
       a.trace = (trace && ai == 0) ? reinterpret_cast<sdvlb_gn_iter*>(out.h + o_trace) : nullptr;
       a.trace_cap = trace ? trace_cap : 0;
       if (forced && ai == 0) {

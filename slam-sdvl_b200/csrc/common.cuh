@@ -74,6 +74,7 @@ struct AlignJobDev {
   double* out_pose;        // 7 doubles (also written to cur.pose)
   int32_t* out_info;       // [0] = n_meas of the last ComputeResiduals, [1] = iterations run
   double* out_error;       // GetError()
+  int32_t* out_cycles;     // optional: [4] SM cycles in PrecomputePatches / residuals / reduction / solve+update
   sdvlb_gn_iter* trace;    // optional
   int trace_cap;
   int forced_n;

@@ -526,6 +526,7 @@ __global__ void __launch_bounds__(128) seq_prep_kernel(const __grid_constant__ S
     J.out_pose = S->align_pose;
     J.out_info = S->align_info;
     J.out_error = &S->align_error;
+    J.out_cycles = S->align_cycles;
     J.trace = nullptr; J.trace_cap = 0; J.forced_n = 0; J.forced_T = nullptr; J.forced_iters = nullptr;
     const size_t nn = size_t(A.max_feats);
     uint8_t* sc = S->align_scratch;
@@ -804,6 +805,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     Rz->phase_cycles[5] = int(t_phase[4] - t_phase[3]);
     Rz->phase_cycles[6] = int(t_phase[5] - t_phase[4]);
     Rz->phase_cycles[7] = 0;
+    for (int i = 0; i < 4; i++) Rz->align_cycles[i] = S->align_cycles[i];
   }
 }
 

@@ -39,7 +39,8 @@ struct SeqResultHost {
   int32_t kf_live[SDVLB_SEQ_KF_CAP];
   int32_t error;       // != 0: a capacity was exceeded
   int32_t phase_cycles[8];   // seq_post_kernel latency breakdown (SM cycles of the sequence's CTA)
-  int32_t pad_[7];
+  int32_t align_cycles[4];   // image_align_kernel: PrecomputePatches, residuals, reduction, solve + update
+  int32_t pad_[3];
   // sdvlb_seq_feat feats[max_feats] follows
 };
 
@@ -61,6 +62,7 @@ struct SeqState {
   double align_pose[7];
   double align_error;
   int32_t align_info[2];
+  int32_t align_cycles[4];
   // ---- static layout
   int32_t max_feats, n_cells;
   SeqFeat* list[2];

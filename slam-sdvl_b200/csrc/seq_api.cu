@@ -384,6 +384,7 @@ int sdvlb_seq_track_collect(sdvlb_ctx* c, sdvlb_seq_result* results) {
     o.feats = reinterpret_cast<const sdvlb_seq_feat*>(reinterpret_cast<const uint8_t*>(R) + sizeof(SeqResultHost));
     memcpy(o.kf_live, R->kf_live, sizeof(o.kf_live));
     memcpy(o.phase_cycles, R->phase_cycles, sizeof(o.phase_cycles));
+    memcpy(o.align_cycles, R->align_cycles, sizeof(o.align_cycles));
     for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++) {
       if (R->kf_live[k] > 0) { if (s->kf_state[k] != 1) s->kf_state[k] = 3; }
       else if (s->kf_state[k] == 2 || s->kf_state[k] == 3) s->kf_state[k] = 0;

@@ -130,27 +130,6 @@ sdvlb_ctx* Device::Current() {
 void Device::SetCurrent(sdvlb_ctx* ctx) { t_ctx = ctx; }
 
 // ---------------------------------------------------------------- randomness (feature_align.cc:53,103,180)
-void HostRand::Seed(unsigned s) {   // glibc srandom_r, TYPE_3
-  if (s == 0) s = 1;
-  int32_t init[34];
-  init[0] = int32_t(s);
-  for (int i = 1; i < 31; i++) {
-    const long hi = init[i - 1] / 127773, lo = init[i - 1] % 127773;
-    long word = 16807 * lo - 2836 * hi;
-    if (word < 0) word += 2147483647;
-    init[i] = int32_t(word);
-  }
-  for (int i = 31; i < 34; i++) init[i] = init[i - 31];
-  for (int i = 0; i < 34; i++) r_[i] = uint32_t(init[i]);
-  n_ = 34;
-  for (int i = 34; i < 344; i++) { r_[n_ % 34] = r_[(n_ - 31) % 34] + r_[(n_ - 3) % 34]; n_++; }
-}
-int HostRand::Next() {
-  const uint32_t v = r_[(n_ - 31) % 34] + r_[(n_ - 3) % 34];
-  r_[n_ % 34] = v;
-  n_++;
-  return int(v >> 1);
-}
 void RandomShuffle(std::vector<int>* v, HostRand* rng) {
   const int size = int(v->size());
   for (int i = 1; i < size; ++i) {

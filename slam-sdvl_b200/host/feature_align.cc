@@ -156,7 +156,43 @@ void FeatureAlign::Reproject(const shared_ptr<Frame>& frame, const shared_ptr<Fr
   ApplyMatches(frame, points, res.data());
 }
 
+bool FeatureAlign::device_pose_refinement_ = false;
+
+// fs -> C-ABI observations (FeatureAlign lists as arrays); flag = which list each feature is in
+static void FillObs(const vector<shared_ptr<Feature>>& fs, int flag, vector<sdvlb_pose_obs>* obs) {
+  for (const auto& f : fs) {
+    shared_ptr<Point> p = f->GetPoint();
+    if (!p) continue;
+    sdvlb_pose_obs o;
+    const Eigen::Vector3d pos = p->GetPosition();
+    o.v[0] = f->GetVector()(0); o.v[1] = f->GetVector()(1); o.v[2] = f->GetVector()(2);
+    o.pos[0] = pos(0); o.pos[1] = pos(1); o.pos[2] = pos(2);
+    o.level = f->GetLevel();
+    o.flags = flag;
+    obs->push_back(o);
+  }
+}
+
 bool FeatureAlign::OptimizePose(const shared_ptr<Frame>& frame) {   // :73-82
+  if (device_pose_refinement_) {   // the same three steps as one device call (sdvlb_optimize_pose)
+    vector<shared_ptr<Feature>> all;
+    vector<sdvlb_pose_obs> obs;
+    for (const auto& f : inliers_) if (f->GetPoint()) all.push_back(f);
+    FillObs(inliers_, SDVLB_OBS_INLIER, &obs);
+    for (const auto& f : outliers_) if (f->GetPoint()) all.push_back(f);
+    FillObs(outliers_, SDVLB_OBS_OUTLIER, &obs);
+    double T[7];
+    frame->GetPose().ToArray(T);
+    if (sdvlb_optimize_pose(frame->Context(), obs.data(), int(obs.size()), T))
+      throw std::runtime_error(std::string("sdvl-b200: FeatureAlign::OptimizePose failed: ") + sdvlb_last_error());
+    frame->SetPose(SE3(T));
+    inliers_.clear();
+    outliers_.clear();
+    for (size_t i = 0; i < all.size(); i++)
+      (obs[i].flags == SDVLB_OBS_INLIER ? inliers_ : outliers_).push_back(all[i]);
+    RemoveOutliers(frame, &outliers_);
+    return true;
+  }
   OptimizePose(frame, &inliers_, &outliers_);
   if (RescueOutliers(frame, &inliers_, &outliers_)) OptimizePose(frame, &inliers_, &outliers_);
   RemoveOutliers(frame, &outliers_);
@@ -171,6 +207,20 @@ void FeatureAlign::SelectInliers(const shared_ptr<Frame>& frame, vector<shared_p
   inliers->clear();
   outliers->clear();
   if (fs_found.empty()) return;
+  if (device_pose_refinement_) {   // RANSAC on the device; rng_ advances by the reference's number of rand() calls
+    vector<sdvlb_pose_obs> obs;
+    FillObs(fs_found, 0, &obs);
+    double T[7];
+    frame->GetPose().ToArray(T);
+    if (sdvlb_select_inliers(frame->Context(), obs.data(), int(obs.size()), T, rng_.State()))
+      throw std::runtime_error(std::string("sdvl-b200: FeatureAlign::SelectInliers failed: ") + sdvlb_last_error());
+    size_t k = 0;
+    for (const auto& f : fs_found) {
+      if (!f->GetPoint()) continue;
+      (obs[k++].flags == SDVLB_OBS_INLIER ? inliers : outliers)->push_back(f);
+    }
+    return;
+  }
   const int size = int(fs_found.size());
   const int npoints = std::min(Config::MaxRansacPoints(), size);
   vector<int> indexes(npoints);

@@ -259,11 +259,11 @@ typedef std::list<PointInfo> GridCell;
 class HostRand {   // glibc rand() stream (TYPE_3, seed 1), one per FeatureAlign so sequences do not interleave
  public:
   HostRand() { Seed(1); }
-  void Seed(unsigned s);
-  int Next();
+  void Seed(unsigned s) { sdvlb_rand_seed(&s_, s); }
+  int Next() { return sdvlb_rand_next(&s_); }
+  sdvlb_rand* State() { return &s_; }
  private:
-  uint32_t r_[34];
-  int n_;
+  sdvlb_rand s_;
 };
 
 class FeatureAlign {
@@ -286,6 +286,9 @@ class FeatureAlign {
                          std::vector<sdvlb_candidate>* cands, std::vector<std::shared_ptr<Point>>* points);
   void ApplyMatches(const std::shared_ptr<Frame>& frame, const std::vector<std::shared_ptr<Point>>& points,
                     const sdvlb_match* matches);
+  // SelectInliers / OptimizePose on the device (sdvlb_select_inliers, sdvlb_optimize_pose) instead of the CPU bodies
+  // below; same lists, same rand() consumption.  Process-wide, like Config.
+  static void SetDevicePoseRefinement(bool on) { device_pose_refinement_ = on; }
   int GetInliers() const { return int(inliers_.size()); }
   int GetOutliers() const { return int(outliers_.size()); }
   double ransac_seconds = 0;   // time spent in SelectInliers (host phase accounting)
@@ -312,6 +315,7 @@ class FeatureAlign {
   bool relocalizing_;
   std::vector<std::shared_ptr<Feature>> inliers_, outliers_;
   HostRand rng_;
+  static bool device_pose_refinement_;
   static constexpr double KMADNorm = 1.4826;
   static constexpr double KTukeyC = 4.6851 * 4.6851;
 };

@@ -507,6 +507,7 @@ class Group {
         const sdvlb_seq_result& r = results_[i];
         for (int k = 0; k < 8; k++) post_cycles_[k] += r.phase_cycles[k];
         post_cycles_[8] += 1;
+        for (int k = 0; k < 4; k++) align_cycles_[k] += r.align_cycles[k];
         st[0] = r.n_tracked; st[1] = r.matches; st[2] = r.attempts; st[3] = r.inliers; st[4] = r.outliers;
         st[6] = r.gn_iters;
         std::memcpy(est + 7 * o, r.pose, 7 * sizeof(double));
@@ -562,6 +563,7 @@ class Group {
   int kf_every_ = 0;
   bool resident_ = false, tracked_ = false;
  public:
+  double align_cycles_[4] = {0, 0, 0, 0};
   double post_cycles_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // seq_post_kernel phase cycles summed over frames, [8] = frames
  private:
   vector<ResidentSeq> rseqs_;
@@ -660,10 +662,12 @@ class BatchTracker {
     }
   }
   void SetPrefetch(int depth) { for (auto& g : groups_) g->prefetch_ = std::max(1, std::min(depth, 6)); }
-  void PostCycles(double out[9], int reset) {
-    for (int i = 0; i < 9; i++) out[i] = 0;
-    for (auto& g : groups_)
+  void PostCycles(double out[13], int reset) {
+    for (int i = 0; i < 13; i++) out[i] = 0;
+    for (auto& g : groups_) {
       for (int i = 0; i < 9; i++) { out[i] += g->post_cycles_[i]; if (reset) g->post_cycles_[i] = 0; }
+      for (int i = 0; i < 4; i++) { out[9 + i] += g->align_cycles_[i]; if (reset) g->align_cycles_[i] = 0; }
+    }
   }
   sdvlb_ctx* ctx0() { return groups_[0]->ctx(); }
   int n_seq() const { return n_seq_; }
@@ -780,6 +784,8 @@ const char* sdvlh_last_error(void) { return g_host_error.c_str(); }
 
 // Config is process-wide in the reference (singleton, config.h:56); set it before creating trackers.
 void sdvlh_config_set(const sdvlb_params* p, const sdvlb_camera* cam) { sdvl::Config::Set(*p, *cam); }
+// FeatureAlign::SelectInliers / OptimizePose of the class-API path on the device (1) or on the host (0, default).
+void sdvlh_device_pose_refinement(int on) { sdvl::FeatureAlign::SetDevicePoseRefinement(on != 0); }
 
 // resident != 0: the sequences live on the device (sdvlb_seq_*): the host neither marshals features nor replays matches.
 void* sdvlh_tracker_create2(const double plane[4], int max_points, int kf_every, int n_seq, int n_groups, int n_threads,
@@ -846,7 +852,8 @@ int sdvlh_tracker_phases(void* t, double out[8], int reset) {
 
 // Latency breakdown of the device-side FeatureAlign kernel, summed over tracked frames (SM cycles): cell ranks,
 // SelectPoints, RANSAC hypotheses / supporters / replay, OptimizePose, the rest, (unused); out[8] = number of frames.
-int sdvlh_tracker_post_cycles(void* t, double out[9], int reset) {
+// out[9..12]: the ImageAlign kernel (PrecomputePatches, residuals, reduction, solve + update).
+int sdvlh_tracker_post_cycles(void* t, double out[13], int reset) {
   static_cast<sdvl::BatchTracker*>(t)->PostCycles(out, reset);
   return 0;
 }

@@ -191,3 +191,24 @@ def test_resident_max_matches_cutoff(binding, sw, O):
     print(f"cut-off: identical stats {same:.2%}, max diff {d.max()*1e3:.4f} mm")
     assert same >= 0.9
     assert float(np.sqrt((d ** 2).mean())) * 1e3 <= ATE_MM
+
+
+def test_class_api_with_device_pose_refinement(binding, sw):
+    """FeatureAlign::Reproject / OptimizePose of the class-API path with SelectInliers and OptimizePose on the device
+    (sdvlb_select_inliers / sdvlb_optimize_pose) == the same path with the CPU bodies: same match / inlier statistics,
+    same rand() consumption (a different number of draws would change every later frame), poses within 1e-9 m."""
+    cfg = sw.config("C2")
+    poses = sw.trajectory(cfg, 5, 30)
+    seqs = [(poses, sw.render(cfg, poses))]
+    H = binding.load_host()
+    est_h, st_h = _run_tracker(binding, sw, cfg, seqs, resident=False, classic=True)
+    H.sdvlh_device_pose_refinement(1)
+    try:
+        est_d, st_d = _run_tracker(binding, sw, cfg, seqs, resident=False, classic=True)
+    finally:
+        H.sdvlh_device_pose_refinement(0)
+    d = np.array([np.linalg.norm(sw.cam_center(a) - sw.cam_center(b)) for a, b in zip(est_h[0], est_d[0])])
+    same = float((st_h[0][:, 1:6] == st_d[0][:, 1:6]).all(axis=1).mean())
+    print(f"class API, device vs host pose refinement: max {d.max():.2e} m, identical stats {same:.2%}")
+    assert d.max() < 1e-9
+    assert same == 1.0
