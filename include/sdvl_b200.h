@@ -135,6 +135,13 @@ int sdvlb_frame_level(const sdvlb_frame* f, int level, const uint8_t** data, int
  * destroyed or re-detected. */
 int sdvlb_frame_corners(const sdvlb_frame* f, const int32_t** xyls, int* n);
 int sdvlb_frame_destroy(sdvlb_ctx* ctx, sdvlb_frame* f);
+/* Frame::FilterCorners() (frame.cc:133-146) -> FastDetector::FilterCorners (extra/fast_detector.cc:177-218):
+ * per free 32-px cell the corner with the best Shi-Tomasi score (FindShiTomasiScoreAtPoint, extra/utils.cc:61-97)
+ * above min_feature_score (Config::MinFeatureScore(), 50).  locked_px: level-0 positions of the frame's features
+ * (FastDetector::LockCell), n_locked x (x, y).  indices receives up to cap indices into the frame's corner list, in
+ * cell order (Frame::filtered_corners_); *n = how many there are. */
+int sdvlb_frame_filter_corners(sdvlb_ctx* ctx, const sdvlb_frame* f, const double* locked_px, int n_locked,
+                               int min_feature_score, int32_t* indices, int cap, int* n);
 
 /* ---- ImageAlign --------------------------------------------------------- */
 /* One feature of frame1 (frame1->GetFeatures() order). */

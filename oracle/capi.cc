@@ -200,6 +200,26 @@ int orc_align_patch(const sdvlb_params* P, const uint8_t* img, int w, int h, con
   return ok ? 1 : 0;
 }
 
+// Frame::FilterCorners on a frame built from img (corners detected with nfeatures); locked: n_locked x (x, y).
+int orc_filter_corners(const sdvlb_params* P, const uint8_t* img, int w, int h, int nfeatures, const double* locked,
+                       int n_locked, int min_feature_score, int32_t* indices, int cap) {
+  sdvlb_params p = *P;
+  p.num_features = nfeatures;
+  Camera cam{double(w), double(h), 1, 1, 0, 0};
+  auto f = MakeFrame(p, &cam, img, w, h, true, 0);
+  std::vector<V2> lk(n_locked);
+  for (int i = 0; i < n_locked; i++) { lk[i].x = locked[2 * i]; lk[i].y = locked[2 * i + 1]; }
+  std::vector<int> out;
+  FilterCorners(p, f->pyramid, f->corners, lk, min_feature_score, &out);
+  for (int i = 0; i < int(out.size()) && i < cap; i++) indices[i] = out[i];
+  return int(out.size());
+}
+double orc_shi_tomasi(const uint8_t* img, int w, int h, int px, int py) {
+  Mat8 m(w, h);
+  std::memcpy(m.data.data(), img, size_t(w) * h);
+  return FindShiTomasiScoreAtPoint(m, px, py);
+}
+
 // ---- FeatureAlign pose refinement alone (parity of sdvlb_select_inliers / sdvlb_optimize_pose) -----------------
 // obs: n x {v[3], pos[3], level, flags} (sdvlb_pose_obs).  mode 0: SelectInliers (rng = glibc state in/out),
 // mode 1: OptimizePose(frame) including RemoveOutliers; flags out: 1 inlier, 2 outlier.

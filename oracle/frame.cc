@@ -256,4 +256,65 @@ V3 Point::GetPosition() const {  // point.cc:128-142
   return se3 * (feature->v * (1.0 / rho));
 }
 
+// ---------------------------------------------------------------- FilterCorners
+// extra/utils.cc:61-97.  The sums are integer-valued floats below 2^24 (exact in any order); the divisions are
+// float / double -> float; the last line is float arithmetic with the float sqrt overload (g++ >= 6, <math.h> wrapper)
+// and a final double product.  Whether a*b - c*d is contracted into an FMA depends on the reference's compiler flags
+// (-O3 -march=native, CMakeLists.txt:20); the oracle pins the uncontracted IEEE reading.
+double FindShiTomasiScoreAtPoint(const Mat8& img, int px, int py) {
+  float dXX = 0.0, dYY = 0.0, dXY = 0.0;
+  const int halfbox_size = 4;
+  const int box_size = 2 * halfbox_size;
+  const int box_area = box_size * box_size;
+  const int x_min = px - halfbox_size, x_max = px + halfbox_size;
+  const int y_min = py - halfbox_size, y_max = py + halfbox_size;
+  if (x_min < 1 || x_max >= img.cols - 1 || y_min < 1 || y_max >= img.rows - 1) return 0.0;
+  for (int y = y_min; y < y_max; y++) {
+    const uint8_t* row = img.ptr(y);
+    const uint8_t* top = img.ptr(y - 1);
+    const uint8_t* bot = img.ptr(y + 1);
+    for (int x = 0; x < box_size; x++) {
+      const float dx = float(int(row[x_min + 1 + x]) - int(row[x_min - 1 + x]));
+      const float dy = float(int(bot[x_min + x]) - int(top[x_min + x]));
+      dXX += dx * dx;
+      dYY += dy * dy;
+      dXY += dx * dy;
+    }
+  }
+  dXX = float(dXX / (2.0 * box_area));
+  dYY = float(dYY / (2.0 * box_area));
+  dXY = float(dXY / (2.0 * box_area));
+  // every product rounded to float on its own (no FMA contraction)
+  volatile float tr = dXX + dYY;
+  volatile float p1 = dXX * dYY, p2 = dXY * dXY, t2 = tr * tr;
+  volatile float det = p1 - p2;
+  volatile float f4 = 4 * det;
+  volatile float disc = t2 - f4;
+  volatile float root = sqrtf(disc);
+  const float diff = tr - root;
+  return 0.5 * diff;
+}
+
+// fast_detector.cc:177-218 + LockCell (:46-49) + InitGrid (:38-41): cgrid_ holds (index, int score)
+void FilterCorners(const sdvlb_params& P, const std::vector<Mat8>& pyr, const std::vector<Corner>& corners,
+                   const std::vector<V2>& locked, int min_feature_score, std::vector<int>* indices) {
+  const int cell = P.cell_size;
+  const int gw = int(std::ceil(double(pyr[0].cols) / cell)), gh = int(std::ceil(double(pyr[0].rows) / cell));
+  std::vector<std::pair<int, int>> cgrid(size_t(gw) * gh, std::make_pair(0, min_feature_score));
+  std::vector<bool> mask(size_t(gw) * gh, false);
+  for (const V2& p : locked) mask.at(size_t(int(p.y / cell) * gw + int(p.x / cell))) = true;
+  const int margin = 1 + P.patch_size / 2;
+  int index = 0;
+  for (auto it = corners.begin(); it != corners.end(); it++, index++) {
+    const int px = it->x, py = it->y, level = it->level, scale = 1 << level;
+    if (px < margin || py < margin || px >= pyr[level].cols - margin || py >= pyr[level].rows - margin) continue;
+    const int pos = int((py * scale) / cell) * gw + int((px * scale) / cell);
+    if (mask[pos]) continue;
+    const double score = FindShiTomasiScoreAtPoint(pyr[level], px, py);
+    if (score > cgrid.at(pos).second) cgrid.at(pos) = std::make_pair(index, int(score));
+  }
+  for (auto& c : cgrid)
+    if (c.second > min_feature_score) indices->push_back(c.first);
+}
+
 }  // namespace oracle

@@ -107,6 +107,12 @@ void SelectPixels(const sdvlb_params& P, const Mat8& src, int level, int nfeatur
 void DetectPyramid(const sdvlb_params& P, const std::vector<Mat8>& pyr, int nfeatures,
                    std::vector<Corner>* corners, std::vector<int>* scores);
 
+// FindShiTomasiScoreAtPoint (extra/utils.cc:61-97) and FastDetector::FilterCorners (fast_detector.cc:177-218) as
+// Frame::FilterCorners drives it (frame.cc:133-146): locked = level-0 positions of the frame's features.
+double FindShiTomasiScoreAtPoint(const Mat8& img, int px, int py);
+void FilterCorners(const sdvlb_params& P, const std::vector<Mat8>& pyr, const std::vector<Corner>& corners,
+                   const std::vector<V2>& locked, int min_feature_score, std::vector<int>* indices);
+
 // ---------------------------------------------------------------- utils (extra/utils.cc)
 double AbsMax6(const Vec6 v);                              // utils.cc:28-42
 float Interpolate8U(const Mat8& m, float u, float v);      // utils.cc:44-59

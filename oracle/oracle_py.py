@@ -118,6 +118,22 @@ def search_points(params, cam, cur_img, T_cur, ref_imgs, cands):
     return out
 
 
+def filter_corners(params, img, nfeatures, locked, min_feature_score=50):
+    """Oracle Frame::FilterCorners: indices into the frame's corner list, one per free cell."""
+    img = np.ascontiguousarray(img, np.uint8)
+    locked = np.ascontiguousarray(locked, np.float64).reshape(-1, 2)
+    out = np.zeros(8192, np.int32)
+    n = lib().orc_filter_corners(C.byref(params), ptr(img), img.shape[1], img.shape[0], nfeatures, ptr(locked),
+                                 locked.shape[0], min_feature_score, ptr(out), out.shape[0])
+    return out[:n].copy()
+
+
+def shi_tomasi(img, px, py):
+    img = np.ascontiguousarray(img, np.uint8)
+    lib().orc_shi_tomasi.restype = C.c_double
+    return lib().orc_shi_tomasi(ptr(img), img.shape[1], img.shape[0], int(px), int(py))
+
+
 def pose_refine(params, cam, obs, T, rng=None, mode=0):
     """Oracle FeatureAlign::SelectInliers (mode 0, rng = abi.Rand advanced in place) or OptimizePose (mode 1).
     Returns (obs with flags, pose)."""

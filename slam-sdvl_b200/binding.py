@@ -67,7 +67,7 @@ EXPORTS = [
     "sdvlb_track_collect", "sdvlb_ctx_reserve_frames",
     "sdvlb_rand_seed", "sdvlb_rand_next", "sdvlb_rand_shuffle", "sdvlb_select_inliers", "sdvlb_optimize_pose",
     "sdvlb_seq_create", "sdvlb_seq_destroy", "sdvlb_seq_reset", "sdvlb_seq_add_points", "sdvlb_seq_track_submit",
-    "sdvlb_seq_track_poll", "sdvlb_seq_track_collect",
+    "sdvlb_seq_track_poll", "sdvlb_seq_track_collect", "sdvlb_frame_filter_corners",
 ]
 
 
@@ -88,6 +88,15 @@ class Frame:
             return np.zeros((0, 3), np.int32), np.zeros(0, np.int32)
         a = np.frombuffer((C.c_int32 * (4 * n.value)).from_address(xyls.value), np.int32).reshape(-1, 4)
         return a[:, :3].copy(), a[:, 3].copy()
+
+    def filter_corners(self, locked_px, min_feature_score=50):
+        """Frame::FilterCorners: indices into corners(), one per free cell with a good enough Shi-Tomasi score."""
+        locked = np.ascontiguousarray(locked_px, np.float64).reshape(-1, 2)
+        out = np.zeros(8192, np.int32)
+        n = C.c_int()
+        _check(load().sdvlb_frame_filter_corners(C.c_void_p(self.ctx.h), C.c_void_p(self.h), ptr(locked), locked.shape[0],
+                                                 min_feature_score, ptr(out), out.shape[0], C.byref(n)))
+        return out[:n.value].copy()
 
     def detect(self, nfeatures):
         _check(load().sdvlb_frame_detect(C.c_void_p(self.ctx.h), C.c_void_p(self.h), nfeatures))

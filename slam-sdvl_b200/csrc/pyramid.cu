@@ -14,6 +14,8 @@
 //                     (the 5 source rows of neighbouring outputs overlap in L1).
 //   pyr_tail_kernel : all remaining levels once a level and its successor fit in shared memory, one CTA per frame
 //                     (levels 2..4 of a 752x480 frame from level 1: one launch instead of three).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -184,7 +186,12 @@ __global__ void __launch_bounds__(256) upload_kernel(const __grid_constant__ Fra
     const int n16 = bytes >> 4;
     const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src);
     uint4* __restrict__ d4 = reinterpret_cast<uint4*>(dst);
-    for (int i = tid; i < n16; i += nth) d4[i] = __ldcs(s4 + i);
+    int i = tid;
+    for (; i + 3 * nth < n16; i += 4 * nth) {   // four PCIe reads in flight per thread
+      const uint4 a = __ldcs(s4 + i), b = __ldcs(s4 + i + nth), c = __ldcs(s4 + i + 2 * nth), d = __ldcs(s4 + i + 3 * nth);
+      d4[i] = a; d4[i + nth] = b; d4[i + 2 * nth] = c; d4[i + 3 * nth] = d;
+    }
+    for (; i < n16; i += nth) d4[i] = __ldcs(s4 + i);
     for (int i = (n16 << 4) + tid; i < bytes; i += nth) dst[i] = src[i];
   } else {
     for (int i = tid; i < bytes; i += nth) dst[i] = src[i];
@@ -207,7 +214,14 @@ int tail_source_level(const PyrGeom& g, size_t* smem_bytes) {
 }  // namespace
 
 cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, cudaStream_t stream) {
-  dim3 grid(24, B.n);
+  // PCIe needs ~100 KB in flight, not SM residency: few CTAs per frame leave the SMs to the compute kernels
+  static int ctas = 0;
+  if (ctas == 0) {
+    const char* e = getenv("SDVLB_UPLOAD_CTAS");
+    ctas = e ? atoi(e) : 6;
+    if (ctas < 1 || ctas > 64) ctas = 6;
+  }
+  dim3 grid(ctas, B.n);
   upload_kernel<<<grid, 256, 0, stream>>>(B, I, bytes);
   return cudaGetLastError();
 }

@@ -111,6 +111,24 @@ void Frame::RemoveFeatures() {
   features_.clear();
 }
 
+void Frame::FilterCorners() {   // frame.cc:133-146: lock the cells that already hold features, best corner per free cell
+  assert(filtered_corners_.empty());
+  std::vector<double> locked;
+  locked.reserve(2 * features_.size());
+  for (auto it = features_.begin(); it != features_.end(); it++) {
+    assert(*it != nullptr);
+    locked.push_back((*it)->GetPosition()(0));
+    locked.push_back((*it)->GetPosition()(1));
+  }
+  const int cap = int(std::ceil(width_ / double(Config::CellSize())) * std::ceil(height_ / double(Config::CellSize())));
+  filtered_corners_.resize(size_t(cap));
+  int n = 0;
+  Check(sdvlb_frame_filter_corners(ctx_, handle_, locked.data(), int(locked.size() / 2), Config::MinFeatureScore(),
+                                   filtered_corners_.data(), cap, &n),
+        "FilterCorners");
+  filtered_corners_.resize(size_t(n));
+}
+
 // ---------------------------------------------------------------- ImageAlign
 ImageAlign::ImageAlign() { error_ = 1e10; }
 ImageAlign::~ImageAlign() {}

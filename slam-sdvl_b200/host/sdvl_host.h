@@ -68,6 +68,7 @@ class Config {
   static int MaxRansacIts() { return params_().max_ransac_its; }
   static int MinMatches() { return params_().min_matches; }
   static double InlierErrorThreshold() { return params_().inlier_error_threshold; }
+  static int MinFeatureScore() { return 50; }   // kMinFeatureScore_ (config.cc:84)
   static bool UseORB() { return false; }
  private:
   static sdvlb_params& params_();
@@ -199,6 +200,8 @@ class Frame {
   bool Project(const Eigen::Vector3d& p3D, Eigen::Vector2d* p2D);   // frame.cc:93-102
   void CreateCorners(int levels, int nfeatures);               // frame.cc:122-131
   void RemoveFeatures();                                       // frame.cc:214-219
+  void FilterCorners();                                        // frame.cc:133-163 (use_orb == 0)
+  std::vector<int>& GetFilteredCorners() { return filtered_corners_; }
   // device side
   sdvlb_frame* Handle() const { return handle_; }
   sdvlb_ctx* Context() const { return ctx_; }
@@ -217,6 +220,7 @@ class Frame {
   std::vector<Eigen::Vector3i> corners_;
   std::vector<int> corner_scores_;
   std::vector<Eigen::Vector2d> outliers_;
+  std::vector<int> filtered_corners_;
   static int counter_;
 };
 

@@ -211,3 +211,22 @@ def test_search_points_parity(binding, sw, scenes, abi, O, name, seed, fixed):
         ref.destroy(); cur.destroy()
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("name,seed,n_locked", [("C2", 0, 0), ("C2", 3, 120), ("C1", 3, 40), ("C5", 1, 300)])
+def test_filter_corners_bit_exact(binding, sw, O, name, seed, n_locked):
+    """Frame::FilterCorners (Shi-Tomasi best corner per free cell, SURVEY 8(f) row 3): same index list as the oracle."""
+    cfg, poses, imgs = sw.sequence(name, seed, 2)
+    P = cfg["params"]
+    rng = np.random.default_rng(seed)
+    locked = np.stack([rng.uniform(0, cfg["w"] - 1, n_locked), rng.uniform(0, cfg["h"] - 1, n_locked)], axis=1)
+    ctx = binding.Context(P, cfg["cam"])
+    f = ctx.frame(imgs[1], corners=True)
+    got = f.filter_corners(locked, 50)
+    ref = O.filter_corners(P, imgs[1], P.num_features, locked, 50)
+    n_cells = int(np.ceil(cfg["w"] / 32) * np.ceil(cfg["h"] / 32))
+    print(f"{name}: {len(got)} filtered corners over {n_cells} cells ({n_locked} locked positions)")
+    assert len(ref) > 0.3 * (n_cells - n_locked)
+    assert np.array_equal(got, ref)
+    f.destroy()
+    ctx.close()

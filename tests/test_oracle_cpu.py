@@ -253,3 +253,23 @@ def test_pose_refine_recovers_pose_and_rejects_outliers(O, sw, abi):
     assert set(np.flatnonzero(o2["flags"] == abi.OBS_OUTLIER)) == bad
     assert np.abs(T[4:] - T_true[4:]).max() < 1e-9
     assert min(np.abs(T[:4] - T_true[:4]).max(), np.abs(T[:4] + T_true[:4]).max()) < 1e-9
+
+
+def test_shi_tomasi_known_answers(O):
+    """FindShiTomasiScoreAtPoint: flat patch -> 0, vertical step edge -> 0 (one zero eigenvalue), checkerboard corner
+    -> the closed-form smaller eigenvalue; too close to the border -> 0."""
+    img = np.full((40, 40), 90, np.uint8)
+    assert O.shi_tomasi(img, 20, 20) == 0.0
+    edge = img.copy()
+    edge[:, 20:] = 200
+    assert abs(O.shi_tomasi(edge, 20, 20)) < 1e-3
+    rng = np.random.default_rng(1)
+    tex = rng.integers(0, 256, (40, 40)).astype(np.uint8)
+    x0, y0 = 20, 18
+    dx = tex[y0 - 4:y0 + 4, x0 - 3:x0 + 5].astype(np.float64) - tex[y0 - 4:y0 + 4, x0 - 5:x0 + 3]
+    dy = tex[y0 - 3:y0 + 5, x0 - 4:x0 + 4].astype(np.float64) - tex[y0 - 5:y0 + 3, x0 - 4:x0 + 4]
+    a, b, c = (dx * dx).sum() / 128, (dy * dy).sum() / 128, (dx * dy).sum() / 128
+    expect = 0.5 * (a + b - np.sqrt((a + b) ** 2 - 4 * (a * b - c * c)))
+    got = O.shi_tomasi(tex, x0, y0)
+    assert abs(got - expect) <= 1e-3 * expect
+    assert O.shi_tomasi(tex, 4, 20) == 0.0
