@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--sweep", default="", help="comma list of GROUPSxTHREADS to time (e2e only), e.g. 8x4,16x8")
     ap.add_argument("--prefetch", type=int, default=2, help="frame batches are built this many steps ahead")
+    ap.add_argument("--sweep-cycles", action="store_true", help="print the in-kernel latency breakdown per sweep entry")
     ap.add_argument("--sweep-device", action="store_true", help="sweep with the frames resident in HBM")
     ap.add_argument("--e2e-upload", default="kernel", choices=["dma", "kernel"],
                     help="how level 0 crosses PCIe in the e2e run: copy engine (cudaMemcpyAsync per frame) or the "
@@ -288,8 +289,10 @@ def main():
         sec = sharding.max_over_ranks(sec)
         counters = trk.counters(reset=True) + (trk.phases(reset=True),)
         ktimes = trk.timing_read(reset=True) if timing else None
-        if timing and not args.host_replay:
-            extras["post_cycles"] = trk.post_cycles(reset=True)
+        if not args.host_replay:
+            extras["post_cycles_timing" if timing else "post_cycles_run"] = trk.post_cycles(reset=True)
+            if timing:
+                extras["post_cycles"] = extras["post_cycles_timing"]
         ngroups = trk.groups()
         trk.close()
         return sec, wall, est, stats, counters, ktimes, ngroups
@@ -307,6 +310,9 @@ def main():
                 sec, wall, *_ = timed_run(host.data_ptr(), e2e_loc, g_)
             print(f"sweep groups={g_:3d} threads={t_:3d}: {S * K * world / sec:10.0f} frames/s  ({sec / K * 1e3:.3f} ms/step)",
                   file=sys.stderr, flush=True)
+            if args.sweep_cycles:
+                print("   in-kernel us/frame:", {k: round(v / 1965.0, 1) for k, v in extras["post_cycles_run"].items()},
+                      file=sys.stderr, flush=True)
         return
 
     clocks = ClockSampler(local_rank)

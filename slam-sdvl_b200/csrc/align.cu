@@ -16,6 +16,19 @@ namespace {
 constexpr int AL_THREADS = 256;
 constexpr int NV = 30;   // reduced values: H(21) b(6) chi2 n_meas + pad
 
+// Eight consecutive pixels starting at p, from aligned 32-bit words: a row of the 5x5 / 7x7 footprints costs two or
+// three loads instead of five or seven byte loads (the load/store unit is what the residual phase waits for).
+// Reads up to 3 bytes before p and up to 11 after it, inside the frame's pyramid allocation (256-B slack).
+__device__ __forceinline__ uint64_t load_pixels8(const uint8_t* __restrict__ p, bool third) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  const unsigned sh = unsigned(a & 3) * 8;
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+  const uint32_t w2 = third ? __ldg(w + 2) : 0u;
+  const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+  return (uint64_t(hi) << 32) | lo;
+}
+
 struct AlignArgs {
   PyrGeom g;
   DevParams dp;
@@ -42,7 +55,7 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
   double* __restrict__ c_xyz = J.sc_d;
   double* __restrict__ c_j0 = J.sc_d + size_t(n) * 3;
   double* __restrict__ c_j1 = J.sc_d + size_t(n) * 9;
-  double* __restrict__ c_abc = J.sc_d + size_t(n) * 15;
+  double* __restrict__ c_H = J.sc_d + size_t(n) * 15;   // per-feature J J^T sum of the level, [k * n + f], k < 21
   int32_t* __restrict__ c_flags = J.sc_flags;
 
   // thread-0 state (image_align.cc:35-41)
@@ -122,9 +135,11 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
             // 7x7 footprint: rows vi-3..vi+3, cols ui-3..ui+3
             float px[7][7];
 #pragma unroll
-            for (int r = 0; r < 7; r++)
+            for (int r = 0; r < 7; r++) {
+              const uint64_t v = load_pixels8(img1 + size_t(vi - 3 + r) * W + (ui - 3), true);
 #pragma unroll
-              for (int c = 0; c < 7; c++) px[r][c] = float(__ldg(img1 + size_t(vi - 3 + r) * W + (ui - 3 + c)));
+              for (int c = 0; c < 7; c++) px[r][c] = float(unsigned(v >> (8 * c)) & 0xffu);
+            }
             double sa = 0, sb = 0, sc = 0;
 #pragma unroll
             for (int y = 0; y < 4; y++)
@@ -145,8 +160,17 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
                 sc += double(dy) * double(dy);
               }
 #pragma unroll
-            for (int r = 0; r < 6; r++) { c_j0[6 * f + r] = j0[r] * fs; c_j1[6 * f + r] = j1[r] * fs; }
-            c_abc[3 * f] = sa; c_abc[3 * f + 1] = sb; c_abc[3 * f + 2] = sc;
+            for (int r = 0; r < 6; r++) { j0[r] *= fs; j1[r] *= fs; c_j0[6 * f + r] = j0[r]; c_j1[6 * f + r] = j1[r]; }
+            // sum over the 16 pixels of J J^T: constant for the whole level (inverse compositional), so it is formed
+            // once here instead of in every Gauss-Newton iteration
+            int k = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+              for (int q = r; q < 6; q++) {
+                c_H[size_t(k) * n + f] = sa * j0[r] * j0[q] + sb * (j0[r] * j1[q] + j1[r] * j0[q]) + sc * j1[r] * j1[q];
+                k++;
+              }
           }
           c_flags[f] = flags;
         }
@@ -181,9 +205,11 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
         const float wbr = float(su * sv);
         float px[5][5];
 #pragma unroll
-        for (int r = 0; r < 5; r++)
+        for (int r = 0; r < 5; r++) {
+          const uint64_t v = load_pixels8(img2 + size_t(vi - 2 + r) * W + (ui - 2), false);
 #pragma unroll
-          for (int c = 0; c < 5; c++) px[r][c] = float(__ldg(img2 + size_t(vi - 2 + r) * W + (ui - 2 + c)));
+          for (int c = 0; c < 5; c++) px[r][c] = float(unsigned(v >> (8 * c)) & 0xffu);
+        }
         double sdx = 0, sdy = 0;
         float chi = 0.0f;
         const float4* pp = reinterpret_cast<const float4*>(c_patch + f * 16);
@@ -210,17 +236,10 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
           double j0[6], j1[6];
 #pragma unroll
           for (int r = 0; r < 6; r++) { j0[r] = c_j0[6 * f + r]; j1[r] = c_j1[6 * f + r]; }
-          const double a = c_abc[3 * f], b = c_abc[3 * f + 1], c = c_abc[3 * f + 2];
-          int k = 0;
 #pragma unroll
-          for (int r = 0; r < 6; r++) {
+          for (int k = 0; k < 21; k++) acc[k] += c_H[size_t(k) * n + f];
 #pragma unroll
-            for (int q = r; q < 6; q++) {
-              acc[k] += a * j0[r] * j0[q] + b * (j0[r] * j1[q] + j1[r] * j0[q]) + c * j1[r] * j1[q];
-              k++;
-            }
-            acc[21 + r] -= j0[r] * sdx + j1[r] * sdy;
-          }
+          for (int r = 0; r < 6; r++) acc[21 + r] -= j0[r] * sdx + j1[r] * sdy;
         }
       }
       acc[27] = double(chi2_f);
@@ -329,7 +348,7 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
 }  // namespace
 
 size_t sdvlb_align_scratch_floats(int n) { return size_t(n) * 48; }
-size_t sdvlb_align_scratch_doubles(int n) { return size_t(n) * 18; }
+size_t sdvlb_align_scratch_doubles(int n) { return size_t(n) * SDVLB_ALIGN_SC_DOUBLES; }
 
 cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, const PyrGeom& g, const DevParams& dp,
                                cudaStream_t stream) {
@@ -343,6 +362,7 @@ cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, const PyrGeom& g,
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  sdvlb_common_carveout(image_align_kernel);
   image_align_kernel<<<n_jobs, AL_THREADS, dyn, stream>>>(static_cast<const AlignJobDev*>(d_jobs), A);
   return cudaGetLastError();
 }

@@ -347,7 +347,7 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
   if (rc) return rc;
   size_t scratch_need = 0;
   for (int i = 0; i < n; i++)
-    if (jobs[i].ref) scratch_need += align_up(size_t(jobs[i].n_feats) * (48 * 4 + 18 * 8 + 4) + 1024, 256);
+    if (jobs[i].ref) scratch_need += align_up(size_t(jobs[i].n_feats) * (48 * 4 + SDVLB_ALIGN_SC_DOUBLES * 8 + 4) + 1024, 256);
   rc = ensure_scratch(c, scratch_need);
   if (rc) return rc;
 
@@ -403,10 +403,10 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
       }
       uint8_t* sc = c->scratch + sc_off;
       a.sc_d = reinterpret_cast<double*>(sc);
-      a.sc_f = reinterpret_cast<float*>(sc + align_up(size_t(j.n_feats) * 18 * 8, 256));
-      a.sc_flags = reinterpret_cast<int32_t*>(sc + align_up(size_t(j.n_feats) * 18 * 8, 256) +
+      a.sc_f = reinterpret_cast<float*>(sc + align_up(size_t(j.n_feats) * SDVLB_ALIGN_SC_DOUBLES * 8, 256));
+      a.sc_flags = reinterpret_cast<int32_t*>(sc + align_up(size_t(j.n_feats) * SDVLB_ALIGN_SC_DOUBLES * 8, 256) +
                                               align_up(size_t(j.n_feats) * 48 * 4, 256));
-      sc_off += align_up(size_t(j.n_feats) * (48 * 4 + 18 * 8 + 4) + 1024, 256);
+      sc_off += align_up(size_t(j.n_feats) * (48 * 4 + SDVLB_ALIGN_SC_DOUBLES * 8 + 4) + 1024, 256);
       if (j.n_feats > 0) memcpy(hfe + fi, j.feats, size_t(j.n_feats) * sizeof(sdvlb_align_feat));
       fi += j.n_feats;
       ai++;
@@ -614,6 +614,10 @@ int sdvlb_ctx_create(int device, const sdvlb_params* params, const sdvlb_camera*
   // tracking is the latency-critical chain of a sequence; frame batches are prefetch work
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (const char* env = getenv("SDVLB_STREAM_PRIO")) {   // experiment knob: 0 = equal priorities, -1 = build stream first
+    if (atoi(env) == 0) prio_hi = prio_lo;
+    else if (atoi(env) < 0) std::swap(prio_hi, prio_lo);
+  }
   cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, prio_lo);
   for (int i = 0; i < kBuildEvents && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->bevents[i], cudaEventDisableTiming);

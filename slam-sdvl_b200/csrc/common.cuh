@@ -62,6 +62,8 @@ struct DevParams {
   sdvlb_camera cam;
 };
 
+// doubles of ImageAlign scratch per feature: xyz[3], j0[6], j1[6], per-level J J^T sum [21]
+#define SDVLB_ALIGN_SC_DOUBLES 36
 // One ImageAlign::ComputePose call (device descriptor).
 struct AlignJobDev {
   FrameDev ref, cur;
@@ -83,7 +85,7 @@ struct AlignJobDev {
   const int32_t* forced_iters;
   // scratch
   float* sc_f;             // patch[n*16], dx[n*16], dy[n*16]
-  double* sc_d;            // xyz[n*3], j0[n*6], j1[n*6], abc[n*3]
+  double* sc_d;            // xyz[n*3], j0[n*6], j1[n*6], H[21][n]
   int32_t* sc_flags;       // bit0 visible (sticky), bit1 has a Jacobian at this level
 };
 
@@ -432,6 +434,26 @@ __host__ __device__ inline void jacobian3d_to_plane(double x, double y, double z
   J1[4] = -J0[3];
   J1[5] = -x * z_inv;
 }
+
+// Every kernel of the library asks for the SAME shared-memory carve-out.  An SM runs CTAs of different kernels side by
+// side only if they agree on the L1 / shared-memory split; with per-kernel defaults the big-smem kernels (ImageAlign,
+// FeatureAlign) and the small-smem ones (FAST, pyramid, SearchPoint) of different streams could not share SMs and the
+// build stream serialised against the tracking stream.
+#if defined(__CUDACC__)
+#include <cstdlib>
+template <typename K>
+inline void sdvlb_common_carveout(K kernel) {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  static int pct = -2;
+  if (pct == -2) {
+    const char* e = getenv("SDVLB_CARVEOUT");
+    pct = e ? atoi(e) : 100;
+  }
+  if (pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+#endif
 
 // error handling shared by the host side
 #define SDVLB_CUDA_TRY(expr)                                                   \

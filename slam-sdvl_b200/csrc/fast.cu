@@ -454,6 +454,7 @@ cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, u
                                     cudaStream_t stream) {
   const FastArgs& A = plan.args;
   dim3 g1((A.g.total_cells + DET_WARPS - 1) / DET_WARPS, B.n);
+  sdvlb_common_carveout(fast_cells_kernel);
   fast_cells_kernel<<<g1, DET_THREADS, 0, stream>>>(B, A, cell_kp, cell_cnt);
   return cudaGetLastError();
 }
@@ -464,6 +465,7 @@ cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, 
   const FastArgs& A = plan.args;
   dim3 g2(A.n_fast_levels, B.n);
   const size_t dyn = size_t(3 * plan.max_cells_level + 1) * sizeof(int);
+  sdvlb_common_carveout(fast_select_kernel);
   fast_select_kernel<<<g2, SEL_THREADS, dyn, stream>>>(B, A, cell_kp, cell_cnt, level_kp, level_cnt, frame_ticket);
   return cudaGetLastError();
 }

@@ -142,6 +142,7 @@ extern "C" int sdvlb_frame_filter_corners(sdvlb_ctx* c, const sdvlb_frame* f, co
   A.score = reinterpret_cast<double*>(in.d + o_score);
   A.cell = reinterpret_cast<int32_t*>(in.d + o_cell);
   A.out = reinterpret_cast<int32_t*>(in.d + o_out);
+  sdvlb_common_carveout(filter_corners_kernel);
   filter_corners_kernel<<<1, FC_THREADS, 0, c->stream>>>(A);
   SDVLB_CUDA_TRY(cudaGetLastError());
   c->n_launches += 1;

@@ -222,6 +222,7 @@ cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int by
     if (ctas < 1 || ctas > 64) ctas = 6;
   }
   dim3 grid(ctas, B.n);
+  sdvlb_common_carveout(upload_kernel);
   upload_kernel<<<grid, 256, 0, stream>>>(B, I, bytes);
   return cudaGetLastError();
 }
@@ -239,6 +240,7 @@ cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStre
   for (int l = 1; l <= direct_to; l++) {
     const int tasks = ((g.w[l] + 7) >> 3) * g.h[l];
     dim3 grid((tasks + PD_THREADS - 1) / PD_THREADS, B.n);
+    sdvlb_common_carveout(pyr_down_kernel);
     pyr_down_kernel<<<grid, PD_THREADS, 0, stream>>>(B, g.off[l - 1], g.w[l - 1], g.h[l - 1], g.off[l], g.w[l], g.h[l]);
   }
   if (tail_src > 0) {
@@ -249,6 +251,7 @@ cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStre
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
+    sdvlb_common_carveout(pyr_tail_kernel);
     pyr_tail_kernel<<<B.n, PT_THREADS, smem, stream>>>(B, g, tail_src);
   }
   return cudaGetLastError();

@@ -388,6 +388,7 @@ __global__ void signal_kernel(volatile uint32_t* flag, uint32_t seq) {
 }  // namespace
 
 cudaError_t sdvlb_launch_signal(uint32_t* h_flag, uint32_t seq, cudaStream_t stream) {
+  sdvlb_common_carveout(signal_kernel);
   signal_kernel<<<1, 1, 0, stream>>>(h_flag, seq);
   return cudaGetLastError();
 }
@@ -399,12 +400,14 @@ cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const Frame
   A.g = g;
   A.dp = dp;
   A.n = n;
+  sdvlb_common_carveout(search_points_kernel);
   search_points_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, d_frames, d_out, A);
   return cudaGetLastError();
 }
 
 cudaError_t sdvlb_launch_search_seq(const SeqStepArgs& A, cudaStream_t stream) {
   const dim3 grid((A.max_feats + SE_WARPS - 1) / SE_WARPS, A.n);
+  sdvlb_common_carveout(search_seq_kernel);
   search_seq_kernel<<<grid, SE_THREADS, 0, stream>>>(A);
   return cudaGetLastError();
 }

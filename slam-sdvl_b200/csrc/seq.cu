@@ -30,7 +30,6 @@ constexpr int PO_THREADS = 160;   // + the shuffle warp
 constexpr int NVP = 28;           // A (21, upper triangle) + b (6) + chi2
 constexpr int RANSAC_MAX_PTS = 8;
 constexpr int HYP_MAX = 256;      // max_ransac_its supported
-constexpr int MAX_CELLS = 4096;   // 2048 x 2048 / 32^2
 
 constexpr double KMADNorm = 1.4826;            // feature_align.h
 constexpr double KTukeyC = 4.6851 * 4.6851;
@@ -318,12 +317,19 @@ __device__ __forceinline__ bool converge_pose_small(const PoseProblem& P, int ba
 
 struct RansacShared {
   sdvlb_rand backup;         // the stream before the speculative draws
-  double hRt[HYP_MAX][12];   // pose of every hypothesis as rotation + translation
-  int hsup[HYP_MAX];         // supporters
-  int hconv[HYP_MAX];        // ConvergePose returned true
-  int rnd[HYP_MAX];
+  double (*hRt)[12];         // [R] pose of every hypothesis as rotation + translation   } carved from dynamic shared
+  int* hsup;                 // [R] supporters                                            } memory by ransac_carve()
+  int* hconv;                // [R] ConvergePose returned true
+  int* rnd;                  // [R] speculative draws
   int best, draws;
 };
+__host__ __device__ inline size_t ransac_bytes(int R) { return size_t(R) * (12 * sizeof(double) + 3 * sizeof(int)); }
+__device__ inline void ransac_carve(RansacShared& rs, unsigned char* mem, int R) {   // mem 8-byte aligned
+  rs.hRt = reinterpret_cast<double (*)[12]>(mem);
+  rs.hsup = reinterpret_cast<int*>(mem + size_t(R) * 12 * sizeof(double));
+  rs.hconv = rs.hsup + R;
+  rs.rnd = rs.hconv + R;
+}
 
 // FeatureAlign::SelectInliers (feature_align.cc:152-216) over P (= fs_found): flags every observation INLIER/OUTLIER.
 // T_frame: frame->GetPose().  *rng advances by the reference's number of rand() calls.  Main threads only.
@@ -531,8 +537,8 @@ __global__ void __launch_bounds__(128) seq_prep_kernel(const __grid_constant__ S
     const size_t nn = size_t(A.max_feats);
     uint8_t* sc = S->align_scratch;
     J.sc_d = reinterpret_cast<double*>(sc);
-    J.sc_f = reinterpret_cast<float*>(sc + nn * 18 * 8);
-    J.sc_flags = reinterpret_cast<int32_t*>(sc + nn * 18 * 8 + nn * 48 * 4);
+    J.sc_f = reinterpret_cast<float*>(sc + nn * SDVLB_ALIGN_SC_DOUBLES * 8);
+    J.sc_flags = reinterpret_cast<int32_t*>(sc + nn * SDVLB_ALIGN_SC_DOUBLES * 8 + nn * 48 * 4);
     S->align_info[0] = 0; S->align_info[1] = 0;
     if (n == 0) {   // ImageAlign::ComputePose returns at once (image_align.cc:55-58); frame2 keeps the prior
       se3_store(prior, S->align_pose);
@@ -595,9 +601,9 @@ struct PostShared {
   RansacShared rs;
   double T_frame[7];
   sdvlb_rand rng;
-  int win[MAX_CELLS];          // per cell: rank of its match (INT_MAX: none)
-  int slot[MAX_CELLS];         // per cell: index of its match in fs_found, -1: cell not visited / no match
-  int order[MAX_CELLS];        // cell_order_
+  int* win;                    // [n_cells] per cell: rank of its match (INT_MAX: none)          } dynamic shared
+  int* slot;                   // [n_cells] index of its match in fs_found, -1: not visited     } memory
+  int* order;                  // [n_cells] cell_order_
   int scan[PO_MAIN];
   int attempts, n_found, n_inl, n_outl;
   int kf_live[SDVLB_SEQ_KF_CAP];
@@ -609,9 +615,18 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   double (*part)[PO_MAIN] = reinterpret_cast<double (*)[PO_MAIN]>(s_raw + ((sizeof(PostShared) + 15) / 16) * 16);
   SeqState* S = A.seq[blockIdx.x];
   const int tid = threadIdx.x;
-  const int n_cells = S->n_cells;
+  const int n_cells = A.g.wcells[0] * A.g.hcells[0];
   const int gw = A.g.wcells[0];
   if (!S->has_last) return;   // uniform: nothing was tracked (no reset yet)
+  if (tid == 0) {             // small shared memory on purpose: this CTA must fit beside the build stream's kernels
+    unsigned char* mem = reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN;
+    ransac_carve(sh.rs, mem, A.dp.p.max_ransac_its);
+    mem += (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16;
+    sh.win = reinterpret_cast<int*>(mem);
+    sh.slot = sh.win + n_cells;
+    sh.order = sh.slot + n_cells;
+  }
+  __syncthreads();
 
   // ---- load the persistent FeatureAlign state (all PO_THREADS threads)
   for (int i = tid; i < n_cells; i += PO_THREADS) { sh.order[i] = S->cell_order[i]; sh.win[i] = INT_MAX; sh.slot[i] = -1; }
@@ -650,8 +665,10 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   SeqFeat* __restrict__ NL = S->list[S->cur ^ 1];
   const int nc = S->n_cands;
   const sdvlb_match* __restrict__ M = S->matches;
-  int32_t* __restrict__ c_cell = S->c_cell;
-  int32_t* __restrict__ c_score = S->c_score;
+  // cell / score of every candidate: in shared memory (the GN partials area is idle here) unless there are too many
+  constexpr int kSmemCands = NVP * PO_MAIN;   // two int arrays in NVP * PO_MAIN doubles
+  int32_t* __restrict__ c_cell = nc <= kSmemCands ? reinterpret_cast<int32_t*>(&part[0][0]) : S->c_cell;
+  int32_t* __restrict__ c_score = nc <= kSmemCands ? reinterpret_cast<int32_t*>(&part[0][0]) + kSmemCands : S->c_score;
   int32_t* __restrict__ c_rank = S->c_rank;
 
   // ---- ProjectPoint bookkeeping (feature_align.cc:323-339): cell of every seen point
@@ -685,15 +702,25 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     const int q0 = tid * per, q1 = min(n_cells, q0 + per);
     int local = 0;
     for (int q = q0; q < q1; q++) local += sh.win[sh.order[q]] != INT_MAX ? 1 : 0;
-    sh.scan[tid] = local;
-    main_sync();
-    if (tid == 0) {
-      int run = 0;
-      for (int t = 0; t < PO_MAIN; t++) { const int v = sh.scan[t]; sh.scan[t] = run; run += v; }
-      sh.n_found = min(run, A.dp.p.max_matches);
+    // exclusive scan over the PO_MAIN per-thread counts: shuffles inside a warp, then the warp totals
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += v;
     }
+    if ((tid & 31) == 31) sh.scan[tid >> 5] = incl;
     main_sync();
-    int pre = sh.scan[tid];
+    int pre = incl - local;
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < PO_MAIN / 32; w++) {
+      const int v = sh.scan[w];
+      if (w < (tid >> 5)) pre += v;
+      total += v;
+    }
+    if (tid == 0) sh.n_found = min(total, A.dp.p.max_matches);
+    main_sync();
     const int max_matches = A.dp.p.max_matches;
     for (int q = q0; q < q1; q++) {
       const int c = sh.order[q];
@@ -822,6 +849,8 @@ __global__ void __launch_bounds__(PO_MAIN, 1) pose_call_kernel(const __grid_cons
   PoseCallShared& sh = *reinterpret_cast<PoseCallShared*>(s_raw);
   double (*part)[PO_MAIN] = reinterpret_cast<double (*)[PO_MAIN]>(s_raw + ((sizeof(PoseCallShared) + 15) / 16) * 16);
   const int tid = threadIdx.x;
+  if (tid == 0)
+    ransac_carve(sh.rs, reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN, A.dp.p.max_ransac_its);
   PoseProblem P;
   P.n = A.n;
   P.o_a = A.scratch; P.o_pos = A.scratch + 2 * size_t(A.n); P.o_scale = A.scratch + 5 * size_t(A.n);
@@ -863,35 +892,42 @@ cudaError_t opt_in_smem(K kernel, size_t bytes) {
 cudaError_t sdvlb_launch_seq_apply(const SeqCmd* d_cmds, const int2* d_ranges, int n_ranges, const DevParams& dp,
                                    cudaStream_t stream) {
   if (n_ranges <= 0) return cudaSuccess;
+  sdvlb_common_carveout(seq_apply_kernel);
   seq_apply_kernel<<<n_ranges, 128, 0, stream>>>(d_cmds, d_ranges, dp);
   return cudaGetLastError();
 }
 
 cudaError_t sdvlb_launch_seq_prep(const SeqStepArgs& A, cudaStream_t stream) {
+  sdvlb_common_carveout(seq_prep_kernel);
   seq_prep_kernel<<<A.n, 128, 0, stream>>>(A);
   return cudaGetLastError();
 }
 
 cudaError_t sdvlb_launch_seq_post(const SeqStepArgs& A, cudaStream_t stream) {
-  const size_t dyn = ((sizeof(PostShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN;
+  const int n_cells = A.g.wcells[0] * A.g.hcells[0];
+  const size_t dyn = ((sizeof(PostShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN +
+                     (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16 + size_t(3 * n_cells) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
-    const cudaError_t e = opt_in_smem(seq_post_kernel, dyn);
+    const cudaError_t e = opt_in_smem(seq_post_kernel, 160 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  sdvlb_common_carveout(seq_post_kernel);
   seq_post_kernel<<<A.n, PO_THREADS, dyn, stream>>>(A);
   return cudaGetLastError();
 }
 
 cudaError_t sdvlb_launch_pose_call(const PoseCallArgs& A, cudaStream_t stream) {
-  const size_t dyn = ((sizeof(PoseCallShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN;
+  const size_t dyn = ((sizeof(PoseCallShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN +
+                     (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16;
   static bool attr_set = false;
   if (!attr_set) {
     const cudaError_t e = opt_in_smem(pose_call_kernel, dyn);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  sdvlb_common_carveout(pose_call_kernel);
   pose_call_kernel<<<1, PO_MAIN, dyn, stream>>>(A);
   return cudaGetLastError();
 }

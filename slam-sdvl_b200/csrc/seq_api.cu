@@ -34,7 +34,7 @@ SeqLayout seq_layout(int max_feats, int n_cells) {
   L.cands = take(n * sizeof(SearchCandDev));
   L.cand_feat = take(n * sizeof(int32_t));
   L.matches = take(n * sizeof(sdvlb_match));
-  L.align_scratch = take(n * (18 * 8 + 48 * 4 + 4) + 256);
+  L.align_scratch = take(n * (SDVLB_ALIGN_SC_DOUBLES * 8 + 48 * 4 + 4) + 256);
   L.c_cell = take(n * sizeof(int32_t));
   L.c_score = take(n * sizeof(int32_t));
   L.c_rank = take(n * sizeof(int32_t));
