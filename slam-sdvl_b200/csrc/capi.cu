@@ -648,7 +648,7 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   while (!c->seqs.empty()) sdvlb_seq_destroy(c, c->seqs.back());
   if (c->seq_in.h) cudaFreeHost(c->seq_in.h);
   if (c->seq_in.d) cudaFree(c->seq_in.d);
-  cudaFree(c->d_seq_jobs); cudaFree(c->d_seq_frames);
+  cudaFree(c->d_seq_jobs); cudaFree(c->d_seq_frames); cudaFree(c->d_seq_done);
   if (c->in.h) cudaFreeHost(c->in.h);
   if (c->in.d) cudaFree(c->in.d);
   if (c->out.h) cudaFreeHost(c->out.h);

@@ -116,6 +116,7 @@ struct sdvlb_ctx {
   std::vector<const sdvlb_frame*> seq_cmd_frames;
   AlignJobDev* d_seq_jobs = nullptr;
   FrameDev* d_seq_frames = nullptr;
+  uint32_t* d_seq_done = nullptr;
   bool seq_active = false;
   std::vector<sdvlb_seq*> seq_inflight;
   std::vector<sdvlb_frame*> seq_inflight_frames;

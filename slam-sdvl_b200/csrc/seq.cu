@@ -449,12 +449,9 @@ __device__ void optimize_pose_cta(const PoseProblem& P, double* T_frame, const D
 }
 
 // ------------------------------------------------------------------------------------------------ commands
-// One CTA per sequence that has commands; its commands are contiguous and applied in order.
-__global__ void __launch_bounds__(128) seq_apply_kernel(const SeqCmd* __restrict__ cmds, const int2* __restrict__ ranges,
-                                                        const __grid_constant__ DevParams dp) {
-  const int2 range = ranges[blockIdx.x];   // (first command, count)
+// The commands of one sequence (contiguous, applied in order) by the threads of one CTA.
+__device__ void apply_commands(const SeqCmd* __restrict__ cmds, int2 range, const DevParams& dp, int* s_base) {
   const int tid = threadIdx.x;
-  __shared__ int s_base;
   for (int ci = range.x; ci < range.x + range.y; ci++) {
     const SeqCmd& C = cmds[ci];
     SeqState* S = C.seq;
@@ -473,13 +470,13 @@ __global__ void __launch_bounds__(128) seq_apply_kernel(const SeqCmd* __restrict
     }
     // append points to the current list (keyframe seeding / mapping thread output)
     if (tid == 0) {
-      s_base = S->n_list;
+      *s_base = S->n_list;
       SeqKf& K = S->kf[C.kf_slot];
       K.pyr = C.kf_pyr;
       for (int i = 0; i < 7; i++) K.T[i] = C.T[i];
     }
     __syncthreads();
-    const int base = s_base;
+    const int base = *s_base;
     SeqFeat* L = S->list[S->cur];
     for (int k = tid; k < C.n; k += blockDim.x) {
       if (base + k >= S->max_feats) break;
@@ -506,6 +503,13 @@ __global__ void __launch_bounds__(128) seq_apply_kernel(const SeqCmd* __restrict
   }
 }
 
+// One CTA per sequence that has commands (sequences that are not part of the step being submitted).
+__global__ void __launch_bounds__(128) seq_apply_kernel(const SeqCmd* __restrict__ cmds, const int2* __restrict__ ranges,
+                                                        const __grid_constant__ DevParams dp) {
+  __shared__ int s_base;
+  apply_commands(cmds, ranges[blockIdx.x], dp, &s_base);
+}
+
 // ------------------------------------------------------------------------------------------------ prep
 __global__ void __launch_bounds__(128) seq_prep_kernel(const __grid_constant__ SeqStepArgs A) {
   SeqState* S = A.seq[blockIdx.x];
@@ -513,6 +517,11 @@ __global__ void __launch_bounds__(128) seq_prep_kernel(const __grid_constant__ S
   __shared__ double s_C[3];
   __shared__ int s_warp_cnt[4];
   __shared__ int s_base;
+  if (A.cmd_range[blockIdx.x].y > 0) {   // the mapping thread's commands for this sequence (keyframes), in order
+    apply_commands(A.cmds, A.cmd_range[blockIdx.x], A.dp, &s_base);
+    __threadfence_block();
+    __syncthreads();
+  }
   AlignJobDev& J = A.jobs[blockIdx.x];
   const int n = S->has_last ? S->n_list : 0;
   if (tid == 0) {
@@ -596,6 +605,19 @@ __global__ void __launch_bounds__(128) seq_prep_kernel(const __grid_constant__ S
 }
 
 // ------------------------------------------------------------------------------------------------ post
+// Completion of a submission without a separate 1-thread kernel: every CTA checks in after its results are fenced to
+// the host; the last one publishes the submission's sequence number in the pinned completion word.
+__device__ __forceinline__ void signal_done(const SeqStepArgs& A) {
+  if (!A.h_flag) return;
+  __threadfence_system();
+  const unsigned arrived = atomicAdd(A.d_done, 1u) + 1u;
+  if (arrived == unsigned(A.n)) {
+    *A.d_done = 0u;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(A.h_flag) = A.seq_no;
+  }
+}
+
 struct PostShared {
   PoseShared ps;
   RansacShared rs;
@@ -617,7 +639,10 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   const int tid = threadIdx.x;
   const int n_cells = A.g.wcells[0] * A.g.hcells[0];
   const int gw = A.g.wcells[0];
-  if (!S->has_last) return;   // uniform: nothing was tracked (no reset yet)
+  if (!S->has_last) {         // uniform: nothing was tracked (no reset yet)
+    if (tid == 0) signal_done(A);
+    return;
+  }
   if (tid == 0) {             // small shared memory on purpose: this CTA must fit beside the build stream's kernels
     unsigned char* mem = reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN;
     ransac_carve(sh.rs, mem, A.dp.p.max_ransac_its);
@@ -834,6 +859,10 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     Rz->phase_cycles[7] = 0;
     for (int i = 0; i < 4; i++) Rz->align_cycles[i] = S->align_cycles[i];
   }
+  // everything the host reads is in pinned memory by now: publish the submission's completion
+  __threadfence_system();
+  main_sync();
+  if (tid == 0) signal_done(A);
 }
 
 // ------------------------------------------------------------------------------------------------ standalone calls

@@ -92,6 +92,12 @@ struct SeqStepArgs {
   FrameDev cur[SDVLB_SEQ_BATCH];
   AlignJobDev* jobs;     // n entries, written by the prep kernel
   FrameDev* frames;      // n entries (SearchCandDev::cur_index)
+  const struct SeqCmd* cmds;            // commands of this step's sequences, applied by the prep kernel
+  int2 cmd_range[SDVLB_SEQ_BATCH];      // (first, count) per sequence of the step
+  uint32_t* d_done;      // device counter of CTAs that finished the post kernel
+  uint32_t* h_flag;      // pinned completion word (nullptr: the caller launches signal_kernel itself)
+  uint32_t seq_no;       // value to publish
+  uint32_t pad_;
   DevParams dp;
   PyrGeom g;
 };

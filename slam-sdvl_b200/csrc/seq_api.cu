@@ -51,6 +51,8 @@ int ensure_step_buffers(sdvlb_ctx* c) {
   if (c->d_seq_jobs) return 0;
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_seq_jobs), SDVLB_SEQ_BATCH * sizeof(AlignJobDev)));
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_seq_frames), SDVLB_SEQ_BATCH * sizeof(FrameDev)));
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_seq_done), 256));
+  SDVLB_CUDA_TRY(cudaMemsetAsync(c->d_seq_done, 0, 256, c->stream));
   return 0;
 }
 
@@ -274,10 +276,23 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
     max_feats = std::max(max_feats, seqs[i]->max_feats);
   }
   // ---- order the tracking stream after the builds of every frame it touches
-  for (int i = 0; i < n; i++) { rc = wait_frame_built(c, frames[i], c->stream); if (rc) return rc; }
-  for (const sdvlb_frame* f : c->seq_cmd_frames) { rc = wait_frame_built(c, f, c->stream); if (rc) return rc; }
+  {
+    cudaEvent_t waited[8];
+    int nw = 0;
+    auto wait_once = [&](const sdvlb_frame* f) -> int {
+      if (!f->build_pending) return 0;
+      for (int k = 0; k < nw; k++) if (waited[k] == f->built) return 0;
+      if (nw < 8) waited[nw++] = f->built;
+      return wait_frame_built(c, f, c->stream);
+    };
+    for (int i = 0; i < n; i++) { rc = wait_once(frames[i]); if (rc) return rc; }
+    for (const sdvlb_frame* f : c->seq_cmd_frames) { rc = wait_once(f); if (rc) return rc; }
+  }
 
-  // ---- queued commands: one upload, one kernel
+  // ---- queued commands: one upload; applied by the prep kernel
+  int2 cmd_range[SDVLB_SEQ_BATCH];
+  for (int i = 0; i < SDVLB_SEQ_BATCH; i++) { cmd_range[i].x = 0; cmd_range[i].y = 0; }
+  const SeqCmd* d_cmds = nullptr;
   const int n_cmds = int(c->seq_cmds.size());
   if (n_cmds > 0) {
     Arena& in = c->seq_in;
@@ -288,26 +303,35 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
     const size_t o_cmds = in.take(size_t(n_cmds) * sizeof(SeqCmd));
     const size_t o_ranges = in.take(size_t(n_cmds) * sizeof(int2));
     const size_t o_pts = in.take(std::max<size_t>(1, c->seq_pts.size()) * sizeof(sdvlb_seq_point));
-    // commands grouped by sequence, order kept inside a sequence: one CTA applies a sequence's commands in order
+    // commands grouped by sequence, order kept inside a sequence.  Sequences of this step get theirs applied by their
+    // own prep CTA; the others (not tracked now) by one extra launch.
     std::vector<int> idx(n_cmds);
     for (int k = 0; k < n_cmds; k++) idx[k] = k;
     std::stable_sort(idx.begin(), idx.end(), [c](int a, int b) { return c->seq_cmds[a].seq < c->seq_cmds[b].seq; });
     SeqCmd* hc = reinterpret_cast<SeqCmd*>(in.h + o_cmds);
     int2* hr = reinterpret_cast<int2*>(in.h + o_ranges);
-    int n_ranges = 0;
+    int n_foreign = 0;
     for (int k = 0; k < n_cmds; k++) {
       const SeqCmd& src = c->seq_cmds[idx[k]];
       hc[k] = src;
       if (src.kind == 1) hc[k].pts = reinterpret_cast<const sdvlb_seq_point*>(in.d + o_pts) + reinterpret_cast<size_t>(src.pts);
-      if (k == 0 || src.seq != c->seq_cmds[idx[k - 1]].seq) { hr[n_ranges].x = k; hr[n_ranges].y = 1; n_ranges++; }
-      else hr[n_ranges - 1].y++;
+      if (k > 0 && src.seq == c->seq_cmds[idx[k - 1]].seq) continue;   // same run as the previous command
+      int cnt = 1;
+      while (k + cnt < n_cmds && c->seq_cmds[idx[k + cnt]].seq == src.seq) cnt++;
+      int owner = -1;
+      for (int i = 0; i < n && owner < 0; i++)
+        if (reinterpret_cast<SeqState*>(seqs[i]->d_block) == src.seq) owner = i;
+      if (owner >= 0) { cmd_range[owner].x = k; cmd_range[owner].y = cnt; }
+      else { hr[n_foreign].x = k; hr[n_foreign].y = cnt; n_foreign++; }
     }
     if (!c->seq_pts.empty()) memcpy(in.h + o_pts, c->seq_pts.data(), c->seq_pts.size() * sizeof(sdvlb_seq_point));
     SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, in.used, cudaMemcpyHostToDevice, c->stream));
     c->h2d_bytes += int64_t(in.used);
-    SDVLB_CUDA_TRY(sdvlb_launch_seq_apply(reinterpret_cast<const SeqCmd*>(in.d + o_cmds),
-                                          reinterpret_cast<const int2*>(in.d + o_ranges), n_ranges, c->dp, c->stream));
-    c->n_launches += 1;
+    d_cmds = reinterpret_cast<const SeqCmd*>(in.d + o_cmds);
+    if (n_foreign > 0) {
+      SDVLB_CUDA_TRY(sdvlb_launch_seq_apply(d_cmds, reinterpret_cast<const int2*>(in.d + o_ranges), n_foreign, c->dp, c->stream));
+      c->n_launches += 1;
+    }
     for (sdvlb_seq* s : c->seqs)
       for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++)
         if (s->kf_state[k] == 1) s->kf_state[k] = 2;
@@ -327,6 +351,13 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
   }
   A.jobs = c->d_seq_jobs;
   A.frames = c->d_seq_frames;
+  A.cmds = d_cmds;
+  memcpy(A.cmd_range, cmd_range, sizeof(cmd_range));
+  c->track_seq++;
+  A.d_done = c->d_seq_done;
+  A.h_flag = reinterpret_cast<uint32_t*>(c->h_overflow) + 16;
+  A.seq_no = c->track_seq;
+  A.pad_ = 0;
   A.dp = c->dp;
   A.g = c->geom;
   timer_begin(c, SDVLB_K_PREP);
@@ -341,9 +372,7 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
   timer_begin(c, SDVLB_K_POSE);
   SDVLB_CUDA_TRY(sdvlb_launch_seq_post(A, c->stream));
   timer_end(c);
-  c->track_seq++;
-  SDVLB_CUDA_TRY(sdvlb_launch_signal(reinterpret_cast<uint32_t*>(c->h_overflow) + 16, c->track_seq, c->stream));
-  c->n_launches += 5;
+  c->n_launches += 4;   // the post kernel publishes the completion word itself
   c->seq_active = true;
   c->seq_inflight.assign(seqs, seqs + n);
   c->seq_inflight_frames.assign(frames, frames + n);

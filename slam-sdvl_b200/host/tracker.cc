@@ -357,17 +357,21 @@ class Group {
   void SubmitStep() {   // build(step+1) then track(step)
     Device::SetCurrent(ctx_);
     const auto tA = std::chrono::steady_clock::now();
+    if (resident_) {   // the tracking chain is the critical path: submit it first, then the prefetch work
+      tracked_ = SubmitResident();
+      in_flight_ = true;
+      const auto tB = std::chrono::steady_clock::now();
+      if (step_ + prefetch_ < n_steps_) {
+        ahead_.emplace_back(size(), nullptr);
+        SubmitBuild(step_ + prefetch_, &ahead_.back());
+      }
+      phase_s_[1] += std::chrono::duration<double>(tB - tA).count();
+      phase_s_[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tB).count();
+      return;
+    }
     if (step_ + prefetch_ < n_steps_) {
       ahead_.emplace_back(size(), nullptr);
       SubmitBuild(step_ + prefetch_, &ahead_.back());
-    }
-    if (resident_) {
-      const auto tB = std::chrono::steady_clock::now();
-      tracked_ = SubmitResident();
-      in_flight_ = true;
-      phase_s_[0] += std::chrono::duration<double>(tB - tA).count();
-      phase_s_[1] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tB).count();
-      return;
     }
     const int n = size();
     const int w = int(cam_.GetWidth()), h = int(cam_.GetHeight());
