@@ -19,6 +19,7 @@ sw = importlib.import_module("slam_sdvl_b200.synthworld")
 binding = importlib.import_module("slam_sdvl_b200.binding")
 G, T = int(sys.argv[1]), int(sys.argv[2])
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+LOC = int(sys.argv[4]) if len(sys.argv) > 4 else 1   # 1 frames in HBM, 2 pinned host memory (upload kernel), 0 DMA
 cfg = sw.config("C2")
 w, h = cfg["w"], cfg["h"]
 F = 1 + 5 + 8
@@ -29,14 +30,14 @@ for s in range(S):
     sw.render(cfg, gt[s], threads=16, out=host.numpy()[s])
 dev = host.cuda()
 trk = binding.HostTracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], 20, S, G, n_threads=T, resident=True)
-ptr_tab = (dev.data_ptr() + (np.arange(S, dtype=np.uint64)[:, None] * F + np.arange(F, dtype=np.uint64)[None, :]) * np.uint64(w * h))
-trk.run_ptrs(ptr_tab[:, :6], gt[:, :6], on_device=1)
+ptr_tab = ((dev.data_ptr() if LOC == 1 else host.data_ptr()) + (np.arange(S, dtype=np.uint64)[:, None] * F + np.arange(F, dtype=np.uint64)[None, :]) * np.uint64(w * h))
+trk.run_ptrs(ptr_tab[:, :6], gt[:, :6], on_device=LOC)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    trk.run_ptrs(ptr_tab[:, 6:], gt[:, 6:], on_device=1)
+    trk.run_ptrs(ptr_tab[:, 6:], gt[:, 6:], on_device=LOC)
     torch.cuda.synchronize()
 trk.close()
-out = os.path.join(ROOT, "gpurun_out", f"timeline_{G}.json")
+out = os.path.join(ROOT, "gpurun_out", f"timeline_{G}_{LOC}.json")
 prof.export_chrome_trace(out)
 ev = [e for e in json.load(open(out))["traceEvents"] if e.get("cat") == "kernel"]
 ev.sort(key=lambda e: e["ts"])

@@ -248,8 +248,12 @@ int ensure_built(sdvlb_frame* f) {
 // Enqueues level-0 upload + pyramid (+ FAST + selection) for n frames on `stream`, in chunks of SDVLB_BATCH_MAX.
 // image_loc: 0 host memory of any kind (one cudaMemcpyAsync per frame), 1 device memory, 2 pinned device-visible host
 // memory (both uploaded by one kernel per chunk).
+// ustream (optional): the level-0 upload goes on that stream instead and `stream` waits for it, so that the PCIe
+// transfer of a later batch overlaps the pyramid / FAST kernels of an earlier one of the same context.
 int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const* images, const int32_t* image_loc,
-                  int n, bool want_corners, int nfeatures, bool mirror, cudaStream_t stream) {
+                  int n, bool want_corners, int nfeatures, bool mirror, cudaStream_t stream,
+                  cudaStream_t ustream = nullptr) {
+  if (!ustream) ustream = stream;
   const size_t img_bytes = size_t(c->w) * c->h;
   const FastPlan* plan = want_corners ? get_plan(c, nfeatures) : nullptr;
   for (int base = 0; base < n; base += SDVLB_BATCH_MAX) {
@@ -269,12 +273,18 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
       f->build_mirror = want_corners && mirror;
     }
     if (by_kernel) {
-      SDVLB_CUDA_TRY(sdvlb_launch_upload(B, I, int(img_bytes), stream));
+      SDVLB_CUDA_TRY(sdvlb_launch_upload(B, I, int(img_bytes), ustream));
       c->n_launches += 1;
     } else {
       for (int i = 0; i < m; i++)
         SDVLB_CUDA_TRY(cudaMemcpyAsync(B.f[i].pyr, I.src[i], img_bytes,
-                                       image_loc[base + i] == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+                                       image_loc[base + i] == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ustream));
+    }
+    if (ustream != stream) {
+      cudaEvent_t ev = c->uevents[c->uevent_next];
+      c->uevent_next = (c->uevent_next + 1) % kBuildEvents;
+      SDVLB_CUDA_TRY(cudaEventRecord(ev, ustream));
+      SDVLB_CUDA_TRY(cudaStreamWaitEvent(stream, ev, 0));
     }
     for (int i = 0; i < m; i++)
       if (image_loc[base + i] != 1) c->h2d_bytes += int64_t(img_bytes);
@@ -621,6 +631,8 @@ int sdvlb_ctx_create(int device, const sdvlb_params* params, const sdvlb_camera*
   cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, prio_lo);
   for (int i = 0; i < kBuildEvents && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->bevents[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->ustream, cudaStreamNonBlocking, prio_lo);
+  for (int i = 0; i < kBuildEvents && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->uevents[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_overflow), 128, cudaHostAllocDefault);
   if (e != cudaSuccess) { delete c; return sdvlb_set_cuda_error(e, "context resources", __FILE__, __LINE__); }
   memset(c->h_overflow, 0, 128);
@@ -642,6 +654,8 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   for (uint8_t* slab : c->slabs) cudaFree(slab);
   for (uint8_t* slab : c->mirror_slabs) cudaFreeHost(slab);
   for (int i = 0; i < kBuildEvents; i++) if (c->bevents[i]) cudaEventDestroy(c->bevents[i]);
+  for (int i = 0; i < kBuildEvents; i++) if (c->uevents[i]) cudaEventDestroy(c->uevents[i]);
+  if (c->ustream) { cudaStreamSynchronize(c->ustream); cudaStreamDestroy(c->ustream); }
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
   cudaFree(c->frame_ticket); cudaFree(c->scratch);
   if (c->h_overflow) cudaFreeHost(c->h_overflow);
@@ -763,7 +777,8 @@ int sdvlb_frames_submit(sdvlb_ctx* c, const uint8_t* const* images, int n, int i
     out[i] = f;
   }
   std::vector<int32_t> loc(n, images_on_device);
-  rc = enqueue_build(c, out, images, loc.data(), n, want_corners != 0, nfeatures, true, c->bstream);
+  rc = enqueue_build(c, out, images, loc.data(), n, want_corners != 0, nfeatures, true, c->bstream,
+                     images_on_device == SDVLB_IMG_DEVICE ? nullptr : c->ustream);
   if (rc) return rc;
   cudaEvent_t ev = c->bevents[c->bevent_next];
   c->bevent_next = (c->bevent_next + 1) % kBuildEvents;

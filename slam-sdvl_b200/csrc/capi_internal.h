@@ -78,6 +78,9 @@ struct sdvlb_ctx {
   cudaStream_t bstream = nullptr;   // build stream (asynchronous frame batches: upload, pyramid, FAST)
   cudaEvent_t bevents[kBuildEvents] = {};
   int bevent_next = 0;
+  cudaStream_t ustream = nullptr;   // upload stream: level 0 of asynchronous frame batches (PCIe), ahead of bstream
+  cudaEvent_t uevents[kBuildEvents] = {};
+  int uevent_next = 0;
   cudaEvent_t last_build = nullptr; // event of the most recent asynchronous build (null: none yet)
   int32_t* h_overflow = nullptr;    // pinned, device-visible: [0] overflow flag written by the selector,
                                     // [16] sequence number of the last finished tracking submission (signal kernel)

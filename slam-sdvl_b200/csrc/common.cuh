@@ -123,6 +123,21 @@ struct FastPlan {
   int nfeatures;
 };
 
+// 1/d on the serial chains of the Gauss-Newton steps (LDL^T pivots, quaternion normalisation, the Rodrigues factors):
+// on the device a MUFU seed (about 20 good bits) and two Newton steps, accurate to an ulp for normal operands, a fifth
+// of the fp64 instructions of the IEEE division sequence.  fp64 issue is what bounds those single-thread phases.
+__host__ __device__ inline double pivot_rcp(double d) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(fma(-d, r, 1.0), r, r);
+  r = fma(fma(-d, r, 1.0), r, r);
+  return r;
+#else
+  return 1.0 / d;
+#endif
+}
+
 // ----------------------------------------------------------------------------- fp64 SE3
 struct DSE3 {
   double q0, q1, q2, q3, tx, ty, tz;
@@ -169,7 +184,8 @@ __host__ __device__ inline DSE3 se3_inverse(const DSE3& s) {
   DSE3 r;
   const double n2 = s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3;
   if (n2 > 0.0) {
-    r.q0 = s.q0 / n2; r.q1 = -s.q1 / n2; r.q2 = -s.q2 / n2; r.q3 = -s.q3 / n2;
+    const double inv = pivot_rcp(n2);
+    r.q0 = s.q0 * inv; r.q1 = -s.q1 * inv; r.q2 = -s.q2 * inv; r.q3 = -s.q3 * inv;
   } else {
     r.q0 = r.q1 = r.q2 = r.q3 = 0.0;
   }
@@ -187,8 +203,8 @@ __host__ __device__ inline DSE3 se3_mul(const DSE3& a, const DSE3& b) {
   const double x = a.q0 * b.q1 + a.q1 * b.q0 + a.q2 * b.q3 - a.q3 * b.q2;
   const double y = a.q0 * b.q2 + a.q2 * b.q0 + a.q3 * b.q1 - a.q1 * b.q3;
   const double z = a.q0 * b.q3 + a.q3 * b.q0 + a.q1 * b.q2 - a.q2 * b.q1;
-  const double n = sqrt(w * w + x * x + y * y + z * z);
-  r.q0 = w / n; r.q1 = x / n; r.q2 = y / n; r.q3 = z / n;
+  const double inv = pivot_rcp(sqrt(w * w + x * x + y * y + z * z));
+  r.q0 = w * inv; r.q1 = x * inv; r.q2 = y * inv; r.q3 = z * inv;
   double R[9], ox, oy, oz;
   se3_rot(a, R);
   mat3_mul_vec(R, b.tx, b.ty, b.tz, ox, oy, oz);
@@ -211,7 +227,7 @@ __host__ __device__ inline DSE3 se3_exp(const double u[6]) {
     const double theta_po4 = theta_sq * theta_sq;
     imag_factor = 0.5 - 0.0208333 * theta_sq + 0.000260417 * theta_po4;
   } else {
-    imag_factor = sin_half / theta;
+    imag_factor = sin_half * pivot_rcp(theta);
   }
   DSE3 r;
   r.q0 = real_factor; r.q1 = imag_factor * ox; r.q2 = imag_factor * oy; r.q3 = imag_factor * oz;
@@ -219,11 +235,11 @@ __host__ __device__ inline DSE3 se3_exp(const double u[6]) {
   if (theta < SMALL_EPS) {
     se3_rot(r, V);
   } else {
-    const double theta_sq = theta * theta;
     double sin_theta, cos_theta;
     sincos(theta, &sin_theta, &cos_theta);
-    const double a = (1 - cos_theta) / theta_sq;
-    const double b = (theta - sin_theta) / (theta_sq * theta);
+    const double inv_t = pivot_rcp(theta), inv_t2 = inv_t * inv_t;
+    const double a = (1 - cos_theta) * inv_t2;
+    const double b = (theta - sin_theta) * (inv_t2 * inv_t);
     // Om = [0 -oz oy; oz 0 -ox; -oy ox 0], Om2 = Om * Om
     const double m00 = -(oz * oz) - oy * oy, m01 = oy * ox, m02 = oz * ox;
     const double m11 = -(oz * oz) - ox * ox, m12 = oz * oy;
@@ -290,20 +306,6 @@ __host__ __device__ inline int rand_next(sdvlb_rand* s) {
   s->r[s->n % 34] = v;
   s->n = s->n >= 34 * 1000000 ? s->n - 34 * 999999 : s->n + 1;   // keep the counter bounded, same position mod 34
   return int(v >> 1);
-}
-
-// 1/d for the pivots of the register LDL^T: on the device a MUFU seed (about 20 good bits) and two Newton steps,
-// accurate to an ulp for normal operands, a third of the latency of the IEEE division sequence in a chain of six.
-__host__ __device__ inline double pivot_rcp(double d) {
-#if defined(__CUDA_ARCH__)
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  r = fma(fma(-d, r, 1.0), r, r);
-  r = fma(fma(-d, r, 1.0), r, r);
-  return r;
-#else
-  return 1.0 / d;
-#endif
 }
 
 // Unpivoted LDL^T solve of a symmetric positive definite 6x6 system held entirely in registers (every loop has a

@@ -218,8 +218,8 @@ cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int by
   static int ctas = 0;
   if (ctas == 0) {
     const char* e = getenv("SDVLB_UPLOAD_CTAS");
-    ctas = e ? atoi(e) : 6;
-    if (ctas < 1 || ctas > 64) ctas = 6;
+    ctas = e ? atoi(e) : 3;
+    if (ctas < 1 || ctas > 64) ctas = 3;
   }
   dim3 grid(ctas, B.n);
   sdvlb_common_carveout(upload_kernel);
