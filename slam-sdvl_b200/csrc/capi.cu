@@ -245,6 +245,33 @@ int ensure_built(sdvlb_frame* f) {
   return check_overflow(f->ctx);
 }
 
+// Upload streams are shared by all contexts of a device: the level-0 uploads of every group then run one after the
+// other (round-robin over SDVLB_UPLOAD_STREAMS streams, default 2, so that the tail of one overlaps the head of the
+// next) and what is outstanding on PCIe stays bounded by the upload kernel's own depth instead of growing with the
+// number of contexts.
+cudaError_t shared_upload_stream(int device, int prio, cudaStream_t* out, std::mutex** mu) {
+  static std::mutex g_mu;
+  static std::mutex g_stream_mu[16][4];
+  static cudaStream_t g_streams[16][4] = {};
+  static int g_next[16] = {};
+  static int n_streams = 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (n_streams == 0) {
+    const char* e = getenv("SDVLB_UPLOAD_STREAMS");
+    n_streams = e ? atoi(e) : 2;
+    if (n_streams < 1 || n_streams > 4) n_streams = 2;
+  }
+  if (device < 0 || device >= 16) return cudaErrorInvalidDevice;
+  const int k = g_next[device]++ % n_streams;
+  if (!g_streams[device][k]) {
+    const cudaError_t e = cudaStreamCreateWithPriority(&g_streams[device][k], cudaStreamNonBlocking, prio);
+    if (e != cudaSuccess) return e;
+  }
+  *out = g_streams[device][k];
+  *mu = &g_stream_mu[device][k];
+  return cudaSuccess;
+}
+
 // Enqueues level-0 upload + pyramid (+ FAST + selection) for n frames on `stream`, in chunks of SDVLB_BATCH_MAX.
 // image_loc: 0 host memory of any kind (one cudaMemcpyAsync per frame), 1 device memory, 2 pinned device-visible host
 // memory (both uploaded by one kernel per chunk).
@@ -272,6 +299,9 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
       f->build_corners = want_corners;
       f->build_mirror = want_corners && mirror;
     }
+    // launch + event record are one unit on the shared upload stream
+    std::unique_lock<std::mutex> ulock;
+    if (ustream != stream && c->umutex) ulock = std::unique_lock<std::mutex>(*c->umutex);
     if (by_kernel) {
       SDVLB_CUDA_TRY(sdvlb_launch_upload(B, I, int(img_bytes), ustream));
       c->n_launches += 1;
@@ -284,6 +314,7 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
       cudaEvent_t ev = c->uevents[c->uevent_next];
       c->uevent_next = (c->uevent_next + 1) % kBuildEvents;
       SDVLB_CUDA_TRY(cudaEventRecord(ev, ustream));
+      if (ulock.owns_lock()) ulock.unlock();
       SDVLB_CUDA_TRY(cudaStreamWaitEvent(stream, ev, 0));
     }
     for (int i = 0; i < m; i++)
@@ -631,7 +662,7 @@ int sdvlb_ctx_create(int device, const sdvlb_params* params, const sdvlb_camera*
   cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, prio_lo);
   for (int i = 0; i < kBuildEvents && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->bevents[i], cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->ustream, cudaStreamNonBlocking, prio_lo);
+  if (e == cudaSuccess) e = shared_upload_stream(device, prio_lo, &c->ustream, &c->umutex);
   for (int i = 0; i < kBuildEvents && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->uevents[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_overflow), 128, cudaHostAllocDefault);
   if (e != cudaSuccess) { delete c; return sdvlb_set_cuda_error(e, "context resources", __FILE__, __LINE__); }
@@ -655,7 +686,7 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   for (uint8_t* slab : c->mirror_slabs) cudaFreeHost(slab);
   for (int i = 0; i < kBuildEvents; i++) if (c->bevents[i]) cudaEventDestroy(c->bevents[i]);
   for (int i = 0; i < kBuildEvents; i++) if (c->uevents[i]) cudaEventDestroy(c->uevents[i]);
-  if (c->ustream) { cudaStreamSynchronize(c->ustream); cudaStreamDestroy(c->ustream); }
+  if (c->ustream) cudaStreamSynchronize(c->ustream);   // shared by the contexts of the device: never destroyed
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
   cudaFree(c->frame_ticket); cudaFree(c->scratch);
   if (c->h_overflow) cudaFreeHost(c->h_overflow);

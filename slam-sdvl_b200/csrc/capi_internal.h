@@ -3,6 +3,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -78,7 +79,9 @@ struct sdvlb_ctx {
   cudaStream_t bstream = nullptr;   // build stream (asynchronous frame batches: upload, pyramid, FAST)
   cudaEvent_t bevents[kBuildEvents] = {};
   int bevent_next = 0;
-  cudaStream_t ustream = nullptr;   // upload stream: level 0 of asynchronous frame batches (PCIe), ahead of bstream
+  cudaStream_t ustream = nullptr;   // upload stream (shared by the contexts of the device): level 0 of asynchronous
+                                    // frame batches (PCIe), ahead of bstream
+  std::mutex* umutex = nullptr;     // serialises launch + event record on the shared stream
   cudaEvent_t uevents[kBuildEvents] = {};
   int uevent_next = 0;
   cudaEvent_t last_build = nullptr; // event of the most recent asynchronous build (null: none yet)
