@@ -64,6 +64,8 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        if self.index is None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -101,6 +103,35 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU boxes have one PCIe root per socket: a rank whose pinned frame buffers sit on the other socket pays the
+    socket interconnect on every upload.  Restrict the rank to the cores of its GPU's NUMA node before anything is
+    allocated (first touch then places the pinned memory there).  Returns a short description for the JSON line."""
+    if os.environ.get("SDVLB_NUMA_BIND", "1") == "0":
+        return {"bound": False, "why": "SDVLB_NUMA_BIND=0"}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"bound": False, "why": "no NUMA node reported", "pci": bus}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "why": "node has no usable cpus", "pci": bus, "node": node}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "pci": bus, "node": node, "cpus": len(cpus)}
+    except Exception as e:   # sysfs layout differs / attribute missing: run unbound
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
 
 
 def algorithmic_bytes(cfg, kernel, stats_prev, stats_cur, n_corners=1000, kbar=3.0):
@@ -172,7 +203,7 @@ def run_reference(args, cfg, sw, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU")
@@ -212,6 +243,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else {"bound": False, "why": "single GPU"}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     binding.load()
@@ -222,6 +254,8 @@ def main():
     w, h = cfg["w"], cfg["h"]
     ncpu = os.cpu_count() or 1
     cores = max(1, ncpu // max(1, world))
+    if world > 1 and cores <= 4:
+        cores = max(1, cores - 1)    # leave a core per rank to the Python thread, the driver's threads and the sampler
     if args.host_replay:     # the host replays FeatureAlign: every core is needed
         threads = args.threads or max(1, min(S, cores))
         groups = args.groups or max(1, min(S, 2 * threads))
@@ -246,6 +280,25 @@ def main():
         torch.cuda.synchronize()
 
     extras = {}
+
+    def pcie_h2d_gbs():
+        """Host->device copy bandwidth of this box with every rank copying at once (copy engine, pinned source): what
+        the e2e leg could reach if the front-end cost nothing, i.e. its roofline."""
+        n = 256 << 20
+        src = torch.empty(n, dtype=torch.uint8).pin_memory()
+        dst = torch.empty(n, dtype=torch.uint8, device="cuda")
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        sec = sharding.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+        return 4 * n / sec / 1e9
+
+    pcie_gbs = pcie_h2d_gbs()
 
     def timed_run(base_ptr, on_device, n_groups, timing=False, pipelined=True):
         """Fresh tracker; init + warm-up untimed; K timed steps. Returns seconds (max over ranks), est, stats, extras.
@@ -315,7 +368,7 @@ def main():
                       file=sys.stderr, flush=True)
         return
 
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank if rank == 0 else None)   # rank 0 samples its GPU; 8 samplers only add noise
     clocks.start()
     # ---- e2e: frames in pinned host memory
     e2e_sec, e2e_wall, est_e, stats_e, cnt_e, _, ngroups = timed_run(host.data_ptr(), e2e_loc, groups)
@@ -381,10 +434,14 @@ def main():
                        "step": "one new frame for every sequence of the GPU", "host_groups_per_gpu": ngroups, "host_threads_per_gpu": min(ngroups, threads),
                        "cache": "every step consumes frames never seen before (inputs 0.36 MB x sequences per step, "
                                 f"{S * F * frame_bytes / 1e6:.0f} MB total, larger than L2); no L2 flush needed",
-                       "kf_every": args.kf_every,
+                       "kf_every": args.kf_every, "numa": numa,
                        "sequence_state": "host replay" if args.host_replay else "resident in HBM (sdvlb_seq_*)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": cnt_e[1] / K, "d2h_bytes_per_step": cnt_e[2] / K,
-                    "ms_per_step": e2e_sec / K * 1e3},
+                    "ms_per_step": e2e_sec / K * 1e3,
+                    "pcie": {"h2d_gbs_per_gpu_achieved": cnt_e[1] / e2e_sec / 1e9,
+                             "h2d_gbs_per_gpu_peak": pcie_gbs, "frac": cnt_e[1] / e2e_sec / 1e9 / pcie_gbs,
+                             "peak_source": "pinned cudaMemcpyAsync 4 x 256 MB, all ranks at once, slowest rank",
+                             "frames_per_s_at_peak": pcie_gbs * 1e9 / frame_bytes * world}},
             "gpu_launches": cnt_v[0],
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -12,14 +12,19 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 fname, hdr, data, seen_kernel = "", None, {}, 0
+first_file = None
 for r in rows:
     if len(r) >= 2 and r[0] == "Kernel Name":
         seen_kernel += 1
         if seen_kernel > 1:
             break
         continue
-    if len(r) >= 2 and r[0] == "File Name":
+    if len(r) >= 2 and r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]
+        if first_file is None:
+            first_file = fname
+        elif fname == first_file:
+            break   # the next captured launch starts over with the first file
         continue
     if r and r[0] == "Line No":
         hdr = r

@@ -323,7 +323,8 @@ class HostTracker:
         n = max(1.0, a[8])
         return {"align_precompute": a[9] / n, "align_residuals": a[10] / n, "align_reduce": a[11] / n,
                 "align_solve": a[12] / n, "cell_ranks": a[0] / n, "select_points": a[1] / n, "ransac_hypotheses": a[2] / n,
-                "ransac_supporters": a[3] / n, "ransac_replay": a[4] / n, "optimize_pose": a[5] / n, "finish": a[6] / n}
+                "startup": a[3] / n, "ransac_replay": a[4] / n, "optimize_pose": a[5] / n, "finish": a[6] / n,
+                "shuffle_warp_done_since_entry": a[7] / n}
 
     def ctx_handle(self):
         return load_host().sdvlh_tracker_ctx(C.c_void_p(self.h))

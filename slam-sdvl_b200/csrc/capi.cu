@@ -246,7 +246,7 @@ int ensure_built(sdvlb_frame* f) {
 }
 
 // Upload streams are shared by all contexts of a device: the level-0 uploads of every group then run one after the
-// other (round-robin over SDVLB_UPLOAD_STREAMS streams, default 2, so that the tail of one overlaps the head of the
+// other (round-robin over SDVLB_UPLOAD_STREAMS streams, default 4, so that the tail of one overlaps the head of the
 // next) and what is outstanding on PCIe stays bounded by the upload kernel's own depth instead of growing with the
 // number of contexts.
 cudaError_t shared_upload_stream(int device, int prio, cudaStream_t* out, std::mutex** mu) {
@@ -258,8 +258,8 @@ cudaError_t shared_upload_stream(int device, int prio, cudaStream_t* out, std::m
   std::lock_guard<std::mutex> lk(g_mu);
   if (n_streams == 0) {
     const char* e = getenv("SDVLB_UPLOAD_STREAMS");
-    n_streams = e ? atoi(e) : 2;
-    if (n_streams < 1 || n_streams > 4) n_streams = 2;
+    n_streams = e ? atoi(e) : 4;
+    if (n_streams < 1 || n_streams > 4) n_streams = 4;
   }
   if (device < 0 || device >= 16) return cudaErrorInvalidDevice;
   const int k = g_next[device]++ % n_streams;
@@ -809,7 +809,7 @@ int sdvlb_frames_submit(sdvlb_ctx* c, const uint8_t* const* images, int n, int i
   }
   std::vector<int32_t> loc(n, images_on_device);
   rc = enqueue_build(c, out, images, loc.data(), n, want_corners != 0, nfeatures, true, c->bstream,
-                     images_on_device == SDVLB_IMG_DEVICE ? nullptr : c->ustream);
+                     (images_on_device == SDVLB_IMG_DEVICE && !getenv("SDVLB_UPLOAD_MIN_NS_PER_FRAME")) ? nullptr : c->ustream);
   if (rc) return rc;
   cudaEvent_t ev = c->bevents[c->bevent_next];
   c->bevent_next = (c->bevent_next + 1) % kBuildEvents;

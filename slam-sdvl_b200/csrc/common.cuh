@@ -304,7 +304,7 @@ __host__ __device__ inline void rand_seed(sdvlb_rand* s, unsigned seed) {   // s
 __host__ __device__ inline int rand_next(sdvlb_rand* s) {
   const uint32_t v = s->r[(s->n - 31) % 34] + s->r[(s->n - 3) % 34];
   s->r[s->n % 34] = v;
-  s->n = s->n >= 34 * 1000000 ? s->n - 34 * 999999 : s->n + 1;   // keep the counter bounded, same position mod 34
+  s->n = s->n >= 34 * 1000000 ? s->n + 1 - 34 * 999999 : s->n + 1;   // keep the counter bounded (same value mod 34)
   return int(v >> 1);
 }
 

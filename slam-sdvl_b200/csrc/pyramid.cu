@@ -209,10 +209,13 @@ constexpr int UB_CHUNK = 8192;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
 __global__ void __launch_bounds__(32) upload_bulk_kernel(const __grid_constant__ FrameBatch B,
-                                                         const __grid_constant__ ImageBatch I, int bytes) {
+                                                         const __grid_constant__ ImageBatch I, int bytes,
+                                                         unsigned long long min_ns) {
   __shared__ __align__(128) uint8_t stage[UB_STAGES][UB_CHUNK];
   __shared__ __align__(8) uint64_t full[UB_STAGES];
   if (threadIdx.x != 0) return;
+  unsigned long long t_start = 0;
+  if (min_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   // the chunks of all frames of the batch form one list, dealt round-robin to the CTAs of the (small) grid: what is in
   // flight on PCIe is gridDim.x * UB_STAGES * UB_CHUNK bytes whatever the batch size
   const int per_frame = (bytes + UB_CHUNK - 1) / UB_CHUNK;
@@ -256,6 +259,10 @@ __global__ void __launch_bounds__(32) upload_bulk_kernel(const __grid_constant__
     }
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (min_ns) {   // experiment knob (SDVLB_UPLOAD_MIN_NS_PER_FRAME): emulate the duration of a PCIe transfer
+    unsigned long long t;
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t_start < min_ns);
+  }
 }
 
 // The level the tail kernel starts from: the first one that fits in shared memory together with its successor
@@ -291,7 +298,9 @@ cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int by
   for (int i = 0; i < B.n && aligned; i++)
     aligned = ((reinterpret_cast<uintptr_t>(I.src[i]) | reinterpret_cast<uintptr_t>(B.f[i].pyr)) & 15) == 0;
   if (bulk && aligned) {
-    upload_bulk_kernel<<<ctas, 32, 0, stream>>>(B, I, bytes);
+    static long long min_ns = -1;
+    if (min_ns < 0) { const char* e = getenv("SDVLB_UPLOAD_MIN_NS_PER_FRAME"); min_ns = e ? atoll(e) : 0; }
+    upload_bulk_kernel<<<ctas, 32, 0, stream>>>(B, I, bytes, (unsigned long long)(min_ns * B.n));
   } else {
     dim3 grid(bulk ? 1 : ctas, B.n);
     sdvlb_common_carveout(upload_kernel);

@@ -633,6 +633,7 @@ struct PostShared {
 
 __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_constant__ SeqStepArgs A) {
   extern __shared__ __align__(16) unsigned char s_raw[];
+  const long long t_entry = clock64();
   PostShared& sh = *reinterpret_cast<PostShared*>(s_raw);
   double (*part)[PO_MAIN] = reinterpret_cast<double (*)[PO_MAIN]>(s_raw + ((sizeof(PostShared) + 15) / 16) * 16);
   SeqState* S = A.seq[blockIdx.x];
@@ -668,6 +669,46 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     // ---- shuffle warp: std::random_shuffle(cell_order_) for the NEXT frame (feature_align.cc:103), once SelectInliers
     // has taken its draws.  Waits on barrier 2 (all PO_THREADS threads).
     asm volatile("bar.sync 2, 160;" ::: "memory");
+    const int lane = tid - PO_MAIN;
+    if (n_cells >= 64) {
+      // The n_cells - 1 draws in one go.  rand() is r[n] = r[n-3] + r[n-31] (mod 2^32): the 30 values of a round only
+      // need values of earlier rounds through the lag-31 term, so a round is three interleaved prefix sums (stride 3)
+      // of known terms -- four shuffle steps instead of 30 dependent updates.  seq[] = the last 34 values in
+      // chronological order, then the new ones; it lives in win/slot, idle since SelectPoints.
+      uint32_t* seq = reinterpret_cast<uint32_t*>(sh.win);
+      const int nd = n_cells - 1, n0 = sh.rng.n;
+      for (int k = lane; k < 34; k += 32) seq[k] = sh.rng.r[(n0 - 34 + k) % 34];
+      __syncwarp();
+      for (int m0 = 0; m0 < nd; m0 += 30) {
+        uint32_t t = lane < 30 ? seq[34 + m0 + lane - 31] : 0u;
+#pragma unroll
+        for (int o = 3; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, t, o);
+          if (lane >= o) t += v;
+        }
+        if (lane < 30) seq[34 + m0 + lane] = t + seq[34 + m0 + (lane % 3) - 3];
+        __syncwarp();
+      }
+      // state after exactly nd draws, then value -> swap partner j = rand() % (i + 1)
+      const int n1 = n0 + nd;
+      for (int k = lane; k < 34; k += 32) S->rng.r[(n1 - 34 + k) % 34] = seq[nd + k];
+      if (lane == 0) S->rng.n = n1 >= 34 * 1000000 ? n1 - 34 * 999999 : n1;
+      __syncwarp();
+      for (int i = 1 + lane; i < n_cells; i += 32) seq[34 + i - 1] = (seq[34 + i - 1] >> 1) % uint32_t(i + 1);
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll 4
+        for (int i = 1; i < n_cells; ++i) {
+          const int j = int(seq[34 + i - 1]);
+          const int a = sh.order[i], b = sh.order[j];
+          sh.order[i] = b; sh.order[j] = a;
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < n_cells; i += 32) S->cell_order[i] = sh.order[i];
+      if (lane == 0) S->result->phase_cycles[7] = int(clock64() - t_entry);
+      return;
+    }
     if (tid == PO_MAIN) {
       for (int i = 1; i < n_cells; ++i) {
         const int j = rand_next(&sh.rng) % (i + 1);
@@ -676,10 +717,9 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
       }
     }
     __syncwarp();
-    const int lane = tid - PO_MAIN;
     for (int i = lane; i < n_cells; i += 32) S->cell_order[i] = sh.order[i];
     for (int i = lane; i < 34; i += 32) S->rng.r[i] = sh.rng.r[i];
-    if (lane == 0) S->rng.n = sh.rng.n;
+    if (lane == 0) { S->rng.n = sh.rng.n; S->result->phase_cycles[7] = int(clock64() - t_entry); }
     return;
   }
 
@@ -852,11 +892,10 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     Rz->phase_cycles[0] = int(t_phase[1] - t_phase[0]);
     Rz->phase_cycles[1] = int(t_phase[2] - t_phase[1]);
     Rz->phase_cycles[2] = int(t_phase[6] - t_phase[2]);   // RANSAC: draws + hypotheses
-    Rz->phase_cycles[3] = int(t_phase[7] - t_phase[6]);   //         supporters
-    Rz->phase_cycles[4] = int(t_phase[3] - t_phase[7]);   //         replay + final inlier flags
+    Rz->phase_cycles[3] = int(t_phase[0] - t_entry);      // kernel entry -> state loaded
+    Rz->phase_cycles[4] = int(t_phase[3] - t_phase[6]);   //         supporters, replay + final inlier flags
     Rz->phase_cycles[5] = int(t_phase[4] - t_phase[3]);
     Rz->phase_cycles[6] = int(t_phase[5] - t_phase[4]);
-    Rz->phase_cycles[7] = 0;
     for (int i = 0; i < 4; i++) Rz->align_cycles[i] = S->align_cycles[i];
   }
   // everything the host reads is in pinned memory by now: publish the submission's completion

@@ -26,6 +26,13 @@
 
 #include "sdvl_host.h"
 
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+static inline void CpuRelax() { _mm_pause(); }
+#else
+static inline void CpuRelax() { std::this_thread::yield(); }
+#endif
+
 using std::shared_ptr;
 using std::vector;
 
@@ -732,7 +739,7 @@ class BatchTracker {
         }
         if (!progressed) {   // everything in flight: nothing to do but wait (plain memory polls, no driver calls)
           const auto t0 = std::chrono::steady_clock::now();
-          std::this_thread::yield();
+          for (int k = 0; k < 32; k++) CpuRelax();   // ~1 us: leaves the core's issue slots to a sibling hardware thread
           groups_[mine[0]]->AddIdle(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
         }
       }
