@@ -18,6 +18,9 @@
  *        -> Matcher::SearchPoint (matcher.h:45-46; matcher.cc:45-121) as it is
  *           driven by FeatureAlign::SelectPoints/ProjectPoint
  *           (feature_align.cc:88-150,323-339)
+ *   sdvlb_update_candidates
+ *        -> the loop body of Map::UpdateCandidates (map.cc:397-498) with
+ *           Point::Update / HasConverged (point.cc:63-100,162-176)
  *   sdvlb_track_batch
  *        -> one SDVL::ProcessFrame front half (sdvl.cc:59,185-193) for many
  *           independent sequences in one submission (no reference equivalent;
@@ -378,6 +381,58 @@ int sdvlb_seq_add_points(sdvlb_ctx* ctx, sdvlb_seq* seq, const sdvlb_frame* kf, 
 int sdvlb_seq_track_submit(sdvlb_ctx* ctx, sdvlb_seq* const* seqs, sdvlb_frame* const* frames, int n);
 int sdvlb_seq_track_poll(sdvlb_ctx* ctx);
 int sdvlb_seq_track_collect(sdvlb_ctx* ctx, sdvlb_seq_result* results);
+
+/* ---- depth-filter seeds: Map::UpdateCandidates (map.cc:397-498) -------------
+ * The mapping thread's per-frame pass over its candidate points (SURVEY.md
+ * section 8(f), row 2): visibility and baseline checks, Matcher::SearchPoint
+ * along the epipolar segment of the current depth estimate (matcher.cc:45-121,
+ * non-fixed branch), GetDepthFromTriangulation and GetParallax
+ * (extra/utils.cc:193-213), and the Bayesian inverse-depth update Point::Update
+ * / ComputeTau / PDFNormal / HasConverged (point.cc:63-100,162-216).  One warp
+ * per candidate, all candidates of a frame in one launch. */
+typedef struct sdvlb_seed {
+  const sdvlb_frame* ref_frame; /* point->GetInitFeature()->GetFrame() (a keyframe) */
+  double ref_T[7];              /* its pose */
+  double ref_px[2];             /* init feature position, level-0 pixels */
+  double ref_v[3];              /* init feature unit bearing */
+  double rho, sigma2;           /* Point::rho_, sigma2_ (inverse depth and its variance) */
+  double a, b, z_range;         /* Point::a_, b_, z_range_ (Beta inlier model, uniform outlier range) */
+  double cos_alpha;             /* Point::cos_alpha_ */
+  double last_distance;         /* Point::last_distance_ */
+  double p3d[3];                /* out, SDVLB_SEED_CONVERGED: Point::p3d_ (the point becomes fixed) */
+  double depth;                 /* out: triangulated depth of this frame's observation (when one was made) */
+  double px[2];                 /* out: matched position in the current frame, level-0 pixels (when found) */
+  int32_t ref_level;            /* init feature level */
+  int32_t n_failed;             /* Point::n_failed_ */
+  int32_t last_kf_id;           /* point->GetLastFeature()->GetFrame()->GetKeyframeID() */
+  int32_t status;               /* out: SDVLB_SEED_* */
+} sdvlb_seed;
+
+enum {
+  SDVLB_SEED_NOT_VISIBLE = 0,   /* map.cc:428-436, kept */
+  SDVLB_SEED_DELETE_OLD = 1,    /* not visible and last seen before min_kf_id: DeletePoint */
+  SDVLB_SEED_SHORT_BASELINE = 2,/* map.cc:440-445 */
+  SDVLB_SEED_NOT_FOUND = 3,     /* SearchPoint failed, Unpromote (n_failed, b updated) */
+  SDVLB_SEED_DELETE_FAILED = 4, /* Unpromote returned true: DeletePoint */
+  SDVLB_SEED_NO_DEPTH = 5,      /* GetDepthFromTriangulation failed */
+  SDVLB_SEED_NO_PARALLAX = 6,   /* cos_alpha >= 0.999999 */
+  SDVLB_SEED_TOO_CLOSE = 7,     /* map.cc:474-478 */
+  SDVLB_SEED_UPDATED = 8,       /* Point::Update ran */
+  SDVLB_SEED_CONVERGED = 9      /* ... and Point::HasConverged(): remove from the candidates */
+};
+
+typedef struct sdvlb_seed_params {
+  double depth_mean;       /* frame->GetSceneDepth() */
+  double map_scale;        /* Config::MapScale()      1.0  */
+  double scale_min_dist;   /* Config::ScaleMinDist()  0.25 */
+  int32_t min_kf_id;       /* last_kf->GetKeyframeID() - 2 * Config::MaxSearchKeyframes() */
+  int32_t pad_;
+} sdvlb_seed_params;
+
+/* The loop body of Map::UpdateCandidates for n candidates against `cur` (with corners) at pose T_cur.  Seeds are
+ * updated in place; the caller applies the list surgery (erase / DeletePoint) that the statuses call for. */
+int sdvlb_update_candidates(sdvlb_ctx* ctx, const sdvlb_frame* cur, const double T_cur[7], sdvlb_seed* seeds, int n,
+                            const sdvlb_seed_params* sp);
 
 #ifdef __cplusplus
 }

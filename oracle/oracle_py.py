@@ -118,6 +118,23 @@ def search_points(params, cam, cur_img, T_cur, ref_imgs, cands):
     return out
 
 
+def update_candidates(params, cam, cur_img, T_cur, ref_imgs, seeds, depth_mean, min_kf_id=-1000, map_scale=1.0,
+                      scale_min_dist=0.25):
+    """Oracle Map::UpdateCandidates loop body. seeds: abi.SEED_DT array whose ref_frame fields index ref_imgs."""
+    cur_img = np.ascontiguousarray(cur_img)
+    h, w = cur_img.shape
+    refs = [np.ascontiguousarray(r) for r in ref_imgs]
+    arr = (C.c_void_p * len(refs))(*[r.ctypes.data for r in refs])
+    seeds = np.ascontiguousarray(seeds).copy()
+    assert seeds.dtype == abi.SEED_DT
+    T_cur = np.ascontiguousarray(T_cur, np.float64)
+    sp = abi.SeedParams(depth_mean, map_scale, scale_min_dist, min_kf_id, 0)
+    rc = lib().orc_update_candidates(C.byref(params), C.byref(cam), ptr(cur_img), w, h, ptr(T_cur), arr, len(refs),
+                                     ptr(seeds), seeds.shape[0], C.byref(sp))
+    assert rc == 0
+    return seeds
+
+
 def filter_corners(params, img, nfeatures, locked, min_feature_score=50):
     """Oracle Frame::FilterCorners: indices into the frame's corner list, one per free cell."""
     img = np.ascontiguousarray(img, np.uint8)

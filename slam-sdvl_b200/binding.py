@@ -67,7 +67,7 @@ EXPORTS = [
     "sdvlb_track_collect", "sdvlb_ctx_reserve_frames",
     "sdvlb_rand_seed", "sdvlb_rand_next", "sdvlb_rand_shuffle", "sdvlb_select_inliers", "sdvlb_optimize_pose",
     "sdvlb_seq_create", "sdvlb_seq_destroy", "sdvlb_seq_reset", "sdvlb_seq_add_points", "sdvlb_seq_track_submit",
-    "sdvlb_seq_track_poll", "sdvlb_seq_track_collect", "sdvlb_frame_filter_corners",
+    "sdvlb_seq_track_poll", "sdvlb_seq_track_collect", "sdvlb_frame_filter_corners", "sdvlb_update_candidates",
 ]
 
 
@@ -174,6 +174,17 @@ class Context:
         _check(load().sdvlb_search_points(C.c_void_p(self.h), C.c_void_p(cur.h), ptr(cands), cands.shape[0], Tp,
                                           ptr(out)))
         return out
+
+    def update_candidates(self, cur, T_cur, seeds, depth_mean, min_kf_id=-1000, map_scale=1.0, scale_min_dist=0.25):
+        """Map::UpdateCandidates loop body on the device. seeds: abi.SEED_DT array whose ref_frame fields hold Frame
+        handles; returns the updated copy."""
+        seeds = np.ascontiguousarray(seeds).copy()
+        assert seeds.dtype == abi.SEED_DT
+        T = np.ascontiguousarray(T_cur, np.float64)
+        sp = abi.SeedParams(depth_mean, map_scale, scale_min_dist, min_kf_id, 0)
+        _check(load().sdvlb_update_candidates(C.c_void_p(self.h), C.c_void_p(cur.h), ptr(T), ptr(seeds), seeds.shape[0],
+                                              C.byref(sp)))
+        return seeds
 
     def select_inliers(self, obs, T_frame, rng):
         """FeatureAlign::SelectInliers on the device. obs: POSE_OBS_DT array (flags overwritten); rng: abi.Rand (advanced)."""

@@ -19,6 +19,8 @@
 
 // ---- kernel launchers (other translation units)
 cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, cudaStream_t stream);
+cudaError_t sdvlb_launch_seed_update(sdvlb_seed* d_seeds, int n, const FrameDev& cur, const PyrGeom& g,
+                                     const DevParams& dp, const sdvlb_seed_params& sp, cudaStream_t stream);
 cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStream_t stream);
 int sdvlb_pyramid_launches(const PyrGeom& g);
 void sdvlb_fast_plan(const PyrGeom& g, const sdvlb_params& p, int nfeatures, int corner_cap, FastPlan* plan);
@@ -79,6 +81,8 @@ int ensure_fast_scratch(sdvlb_ctx* c, int n_frames) {
   SDVLB_CUDA_TRY(cudaStreamSynchronize(c->bstream));
   SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
   const int nf = std::max(n_frames, c->fast_frames * 2);
+  if (c->d_seeds) cudaFree(c->d_seeds);
+  if (c->h_seeds) cudaFreeHost(c->h_seeds);
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt); cudaFree(c->frame_ticket);
   c->cell_kp = nullptr; c->cell_cnt = nullptr; c->level_kp = nullptr; c->level_cnt = nullptr; c->frame_ticket = nullptr;
   c->fast_frames = 0;
@@ -687,6 +691,8 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   for (int i = 0; i < kBuildEvents; i++) if (c->bevents[i]) cudaEventDestroy(c->bevents[i]);
   for (int i = 0; i < kBuildEvents; i++) if (c->uevents[i]) cudaEventDestroy(c->uevents[i]);
   if (c->ustream) cudaStreamSynchronize(c->ustream);   // shared by the contexts of the device: never destroyed
+  if (c->d_seeds) cudaFree(c->d_seeds);
+  if (c->h_seeds) cudaFreeHost(c->h_seeds);
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
   cudaFree(c->frame_ticket); cudaFree(c->scratch);
   if (c->h_overflow) cudaFreeHost(c->h_overflow);
@@ -997,6 +1003,52 @@ int sdvlb_search_points(sdvlb_ctx* ctx, const sdvlb_frame* cur, const sdvlb_cand
     SDVLB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   }
   return run_batch(ctx, &j, 1, 0, nullptr, 0, nullptr, nullptr, false);
+}
+
+// Map::UpdateCandidates (map.cc:397-498) for n seeds against `cur`: one upload, one kernel, one read-back.
+int sdvlb_update_candidates(sdvlb_ctx* c, const sdvlb_frame* cur, const double T_cur[7], sdvlb_seed* seeds, int n,
+                            const sdvlb_seed_params* sp) {
+  if (!c || !cur || !T_cur || !sp || n < 0 || (n > 0 && !seeds)) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  int rc = ensure_built(const_cast<sdvlb_frame*>(cur));
+  if (rc) return rc;
+  if (!cur->has_corners) return sdvlb_set_error(SDVLB_ERR_STATE, "current frame has no corners");
+  if (n == 0) return 0;
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  for (int i = 0; i < n; i++) {
+    if (!seeds[i].ref_frame) return sdvlb_set_error(SDVLB_ERR_ARG, "seed without a reference frame");
+    if (seeds[i].ref_level < 0 || seeds[i].ref_level >= c->params.pyramid_levels)
+      return sdvlb_set_error(SDVLB_ERR_ARG, "seed level out of range");
+    rc = ensure_built(const_cast<sdvlb_frame*>(seeds[i].ref_frame));
+    if (rc) return rc;
+  }
+  if (n > c->seeds_cap) {
+    const int cap = std::max(n, std::max(256, 2 * c->seeds_cap));
+    if (c->d_seeds) cudaFree(c->d_seeds);
+    if (c->h_seeds) cudaFreeHost(c->h_seeds);
+    c->d_seeds = nullptr; c->h_seeds = nullptr; c->seeds_cap = 0;
+    SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_seeds), sizeof(sdvlb_seed) * cap));
+    SDVLB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_seeds), sizeof(sdvlb_seed) * cap, cudaHostAllocDefault));
+    c->seeds_cap = cap;
+  }
+  for (int i = 0; i < n; i++) {   // frame handles -> device pyramids
+    c->h_seeds[i] = seeds[i];
+    c->h_seeds[i].ref_frame = reinterpret_cast<const sdvlb_frame*>(seeds[i].ref_frame->dev.pyr);
+  }
+  const size_t bytes = sizeof(sdvlb_seed) * size_t(n);
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(cur->dev.pose, T_cur, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(c->d_seeds, c->h_seeds, bytes, cudaMemcpyHostToDevice, c->stream));
+  SDVLB_CUDA_TRY(sdvlb_launch_seed_update(c->d_seeds, n, cur->dev, c->geom, c->dp, *sp, c->stream));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(c->h_seeds, c->d_seeds, bytes, cudaMemcpyDeviceToHost, c->stream));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->n_launches += 1;
+  c->h2d_bytes += int64_t(bytes) + 56;
+  c->d2h_bytes += int64_t(bytes);
+  for (int i = 0; i < n; i++) {
+    const sdvlb_frame* ref = seeds[i].ref_frame;
+    seeds[i] = c->h_seeds[i];
+    seeds[i].ref_frame = ref;
+  }
+  return check_overflow(c);
 }
 
 }  // extern "C"

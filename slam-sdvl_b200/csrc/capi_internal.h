@@ -82,6 +82,9 @@ struct sdvlb_ctx {
   cudaStream_t ustream = nullptr;   // upload stream (shared by the contexts of the device): level 0 of asynchronous
                                     // frame batches (PCIe), ahead of bstream
   std::mutex* umutex = nullptr;     // serialises launch + event record on the shared stream
+  sdvlb_seed* d_seeds = nullptr;    // sdvlb_update_candidates staging (device + pinned host), grown on demand
+  sdvlb_seed* h_seeds = nullptr;
+  int seeds_cap = 0;
   cudaEvent_t uevents[kBuildEvents] = {};
   int uevent_next = 0;
   cudaEvent_t last_build = nullptr; // event of the most recent asynchronous build (null: none yet)

@@ -377,6 +377,173 @@ __global__ void __launch_bounds__(SE_THREADS) search_seq_kernel(const __grid_con
   search_one(S->cands[ci], A.cur[blockIdx.y], S->matches + ci, A.g, A.dp, s_bp[warp], s_patch[warp]);
 }
 
+// ---- Map::UpdateCandidates (map.cc:397-498): one warp per depth-filter seed.  The geometry is a few dozen fp64
+// operations, evaluated by every lane (uniform control flow into search_one); lane 0 writes the seed back.
+struct SeedArgs {
+  PyrGeom g;
+  DevParams dp;
+  sdvlb_seed_params sp;
+  int n;
+};
+
+__device__ __forceinline__ double parallax_cos(const double a[3], const double b[3], const double p[3]) {   // utils.cc:207-213
+  double v1[3] = {a[0] - p[0], a[1] - p[1], a[2] - p[2]}, v2[3] = {b[0] - p[0], b[1] - p[1], b[2] - p[2]};
+  const double n1 = sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
+  const double n2 = sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
+  for (int i = 0; i < 3; i++) { v1[i] /= n1; v2[i] /= n2; }
+  return v1[0] * v2[0] + v1[1] * v2[1] + v1[2] * v2[2];
+}
+
+__global__ void __launch_bounds__(SE_THREADS) seed_update_kernel(sdvlb_seed* __restrict__ seeds, const FrameDev cur,
+                                                                 const __grid_constant__ SeedArgs A) {
+  __shared__ uint8_t s_bp[SE_WARPS][104];
+  __shared__ uint8_t s_patch[SE_WARPS][64];
+  __shared__ SearchCandDev s_cand[SE_WARPS];
+  __shared__ sdvlb_match s_match[SE_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int si = blockIdx.x * SE_WARPS + warp;
+  if (si >= A.n) return;
+  sdvlb_seed& S = seeds[si];
+  const sdvlb_camera& cam = A.dp.cam;
+  const DSE3 T_cur = se3_load(cur.pose), T_ref = se3_load(S.ref_T);
+  const DSE3 T_ref_w = se3_inverse(T_ref), T_cur_w = se3_inverse(T_cur);
+  const double c_ref[3] = {T_ref_w.tx, T_ref_w.ty, T_ref_w.tz}, c_cur[3] = {T_cur_w.tx, T_cur_w.ty, T_cur_w.tz};
+  const double v[3] = {S.ref_v[0], S.ref_v[1], S.ref_v[2]};
+  double rho = S.rho, sigma2 = S.sigma2, a = S.a, b = S.b;
+  int status;
+  double depth = 0.0;
+
+  // Point::GetPosition (point.cc:128-142) and Frame::IsPointVisible (frame.cc:104-112)
+  double pos[3], rel[3];
+  se3_apply(T_ref_w, v[0] / rho, v[1] / rho, v[2] / rho, pos[0], pos[1], pos[2]);
+  se3_apply(T_cur, pos[0], pos[1], pos[2], rel[0], rel[1], rel[2]);
+  bool visible = !(rel[2] < 0.0);
+  if (visible) {
+    double pu, pv;
+    cam_project(cam, rel[0], rel[1], rel[2], pu, pv);
+    visible = finite2(pu, pv) && fabs(pu) < 1e9 && fabs(pv) < 1e9;
+    if (visible) {
+      const int iu = int(pu), iv = int(pv);   // Vector2d::cast<int>() truncates
+      visible = iu >= 0 && iu < cam.width && iv >= 0 && iv < cam.height;
+    }
+  }
+  const double dx = c_cur[0] - c_ref[0], dy = c_cur[1] - c_ref[1], dz = c_cur[2] - c_ref[2];
+  const double baseline = sqrt(dx * dx + dy * dy + dz * dz);   // Frame::DistanceTo (frame.h:129-131)
+  if (!visible) {
+    status = S.last_kf_id < A.sp.min_kf_id ? SDVLB_SEED_DELETE_OLD : SDVLB_SEED_NOT_VISIBLE;
+  } else if (baseline / A.sp.depth_mean < 0.01) {
+    status = SDVLB_SEED_SHORT_BASELINE;
+  } else {
+    // matcher.SearchPoint(frame, feature, point->GetInverseDepth(), point->GetStd(), false, &imgpos, &level)
+    if (lane == 0) {
+      SearchCandDev& C = s_cand[warp];
+      C.ref_pyr = reinterpret_cast<const uint8_t*>(S.ref_frame);   // resolved to the device pyramid by the host
+      for (int i = 0; i < 7; i++) C.ref_T[i] = S.ref_T[i];
+      C.ref_px[0] = S.ref_px[0]; C.ref_px[1] = S.ref_px[1];
+      for (int i = 0; i < 3; i++) { C.ref_v[i] = v[i]; C.pos[i] = 0.0; }
+      C.idepth = rho; C.idepth_std = sqrt(sigma2);
+      C.px[0] = C.px[1] = 0.0;
+      C.ref_level = S.ref_level; C.flags = 0; C.cur_index = 0; C.pad_ = 0;
+    }
+    __syncwarp();
+    search_one(s_cand[warp], cur, &s_match[warp], A.g, A.dp, s_bp[warp], s_patch[warp]);
+    __syncwarp();
+    const sdvlb_match m = s_match[warp];
+    if (m.status != SDVLB_MATCH_FOUND) {
+      const int nf = S.n_failed + 1;          // Point::Unpromote (point.cc:109-116)
+      b += 1.0;
+      status = nf > A.dp.p.max_failed ? SDVLB_SEED_DELETE_FAILED : SDVLB_SEED_NOT_FOUND;
+      if (lane == 0) { S.n_failed = nf; S.b = b; }
+    } else {
+      // GetDepthFromTriangulation(pose, feature->GetVector(), v3d, &depth) (utils.cc:193-205)
+      const DSE3 pose = se3_mul(T_cur, T_ref_w);
+      double R[9], rv[3], vc[3];
+      se3_rot(pose, R);
+      mat3_mul_vec(R, v[0], v[1], v[2], rv[0], rv[1], rv[2]);
+      cam_unproject_unit(cam, m.px[0], m.px[1], vc);
+      const double t[3] = {pose.tx, pose.ty, pose.tz};
+      const double a00 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
+      const double a01 = rv[0] * vc[0] + rv[1] * vc[1] + rv[2] * vc[2];
+      const double a11 = vc[0] * vc[0] + vc[1] * vc[1] + vc[2] * vc[2];
+      const double det = a00 * a11 - a01 * a01;
+      if (lane == 0) { S.px[0] = m.px[0]; S.px[1] = m.px[1]; }
+      if (det < 0.000001) {
+        status = SDVLB_SEED_NO_DEPTH;
+      } else {
+        const double at0 = rv[0] * t[0] + rv[1] * t[1] + rv[2] * t[2];
+        const double at1 = vc[0] * t[0] + vc[1] * t[1] + vc[2] * t[2];
+        depth = fabs(-((a11 / det) * at0 + (-a01 / det) * at1));
+        double p3d[3];
+        se3_apply(T_ref_w, depth * v[0], depth * v[1], depth * v[2], p3d[0], p3d[1], p3d[2]);
+        const double cos_alpha = parallax_cos(c_ref, c_cur, p3d);   // map.cc:467-472
+        if (cos_alpha >= 0.999999) {
+          status = SDVLB_SEED_NO_PARALLAX;
+        } else if (depth < A.sp.map_scale * A.sp.scale_min_dist || depth < A.sp.depth_mean * A.sp.scale_min_dist) {
+          status = SDVLB_SEED_TOO_CLOSE;
+        } else {
+          // Point::Update(frame, depth, px_error_angle) (point.cc:63-100)
+          status = SDVLB_SEED_UPDATED;
+          const double px_error_angle = atan(1.0 / (2.0 * cam.fx)) * 2.0;   // camera.h:104-107
+          const DSE3 pu = se3_mul(T_ref, T_cur_w);
+          const double PI = 3.14159265;
+          const double tt[3] = {pu.tx, pu.ty, pu.tz};
+          const double av[3] = {v[0] * depth - tt[0], v[1] * depth - tt[1], v[2] * depth - tt[2]};
+          const double t_norm = sqrt(tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2]);
+          const double a_norm = sqrt(av[0] * av[0] + av[1] * av[1] + av[2] * av[2]);
+          const double alpha = acos((v[0] * tt[0] + v[1] * tt[1] + v[2] * tt[2]) / t_norm);
+          const double beta = acos(-(av[0] * tt[0] + av[1] * tt[1] + av[2] * tt[2]) / (t_norm * a_norm));
+          const double beta_plus = beta + px_error_angle;
+          const double gamma_plus = PI - alpha - beta_plus;
+          const double depth_plus = t_norm * sin(beta_plus) / sin(gamma_plus);
+          const double tau = depth_plus - depth;
+          const double tau_inverse = 0.5 * (1.0 / fmax(0.0000001, depth - tau) - 1.0 / (depth + tau));
+          const double tau2 = tau_inverse * tau_inverse;
+          const double x = 1. / depth;
+          const double norm_scale = sqrt(sigma2 + tau2);
+          double ca = S.cos_alpha, ld = S.last_distance;
+          if (!isnan(norm_scale)) {
+            const double s2 = 1. / (1. / sigma2 + 1. / tau2);
+            const double mm = s2 * (rho / sigma2 + x / tau2);
+            double pdf = 0.0;
+            if (norm_scale > 0) {   // PDFNormal (point.cc:200-216)
+              double ex = x - rho;
+              ex *= -ex;
+              ex /= 2 * norm_scale * norm_scale;
+              pdf = exp(ex) / (norm_scale * sqrt(2.0 * PI));
+            }
+            double C1 = a / (a + b) * pdf;
+            double C2 = b / (a + b) * 1. / S.z_range;
+            const double nc = C1 + C2;
+            C1 /= nc;
+            C2 /= nc;
+            const double f = C1 * (a + 1.) / (a + b + 1.) + C2 * a / (a + b + 1.);
+            const double e = C1 * (a + 1.) * (a + 2.) / ((a + b + 1.) * (a + b + 2.)) +
+                             C2 * a * (a + 1.0) / ((a + b + 1.0) * (a + b + 2.0));
+            const double rho_new = C1 * mm + C2 * rho;
+            sigma2 = C1 * (s2 + mm * mm) + C2 * (sigma2 + rho * rho) - rho_new * rho_new;
+            rho = rho_new;
+            a = (e - f) / (f - e / f);
+            b = a * (1.0 - f) / f;
+            se3_apply(T_ref_w, v[0] / rho, v[1] / rho, v[2] / rho, pos[0], pos[1], pos[2]);
+            ca = parallax_cos(c_ref, c_cur, pos);
+            const double ex = c_cur[0] - pos[0], ey = c_cur[1] - pos[1], ez = c_cur[2] - pos[2];
+            ld = sqrt(ex * ex + ey * ey + ez * ez);   // Frame::DistanceTo(point)
+            // Point::HasConverged (point.cc:162-176)
+            const double std_d = sqrt(sigma2) / (rho * rho);
+            if (4 * std_d * ca / ld < 0.1) status = SDVLB_SEED_CONVERGED;
+          }
+          if (lane == 0) {
+            S.rho = rho; S.sigma2 = sigma2; S.a = a; S.b = b; S.cos_alpha = ca; S.last_distance = ld;
+            if (!isnan(norm_scale)) S.n_failed = 0;
+            if (status == SDVLB_SEED_CONVERGED) { S.p3d[0] = pos[0]; S.p3d[1] = pos[1]; S.p3d[2] = pos[2]; }
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) { S.status = status; S.depth = depth; }
+}
+
 // Completion signal of a tracking submission: the stream reaches this 1-thread kernel after ImageAlign and SearchPoint
 // have finished (their results are already in pinned host memory); it publishes the submission's sequence number in
 // pinned host memory, so the host can poll a plain memory word instead of calling into the CUDA driver.
@@ -402,6 +569,19 @@ cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const Frame
   A.n = n;
   sdvlb_common_carveout(search_points_kernel);
   search_points_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, d_frames, d_out, A);
+  return cudaGetLastError();
+}
+
+cudaError_t sdvlb_launch_seed_update(sdvlb_seed* d_seeds, int n, const FrameDev& cur, const PyrGeom& g,
+                                     const DevParams& dp, const sdvlb_seed_params& sp, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  SeedArgs A;
+  A.g = g;
+  A.dp = dp;
+  A.sp = sp;
+  A.n = n;
+  sdvlb_common_carveout(seed_update_kernel);
+  seed_update_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_seeds, cur, A);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,133 @@
+"""Map::UpdateCandidates (map.cc:397-498) on the device vs the CPU oracle: depth-filter seeds searched along their
+epipolar segments, triangulated and updated, frame after frame."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def make_seeds(cfg, scenes, abi, xyl, T_ref, ref_handle, depth_mean, seed=0):
+    """Candidates the way Map::InitCandidates leaves them (Point::InitCandidate, point.cc:48-61): a = b = 10,
+    sigma2 = 1, z_range = 6, rho = 1 / (a first triangulated depth: here truth +-10 %)."""
+    pts = scenes.seed_points(cfg, xyl, T_ref, one_per_cell=False, margin=0)
+    n = len(pts["px"])
+    rng = np.random.default_rng(seed)
+    s = np.zeros(n, abi.SEED_DT)
+    s["ref_frame"] = ref_handle
+    s["ref_T"] = np.asarray(T_ref)
+    s["ref_px"] = pts["px"]
+    s["ref_v"] = pts["v"]
+    s["rho"] = 1.0 / (pts["depth"] * (1.0 + rng.uniform(-0.1, 0.1, n)))
+    s["sigma2"] = 1.0
+    s["a"] = 10.0
+    s["b"] = 10.0
+    s["z_range"] = 6.0
+    s["cos_alpha"] = 1.0
+    s["last_distance"] = 1.0 / s["rho"]
+    s["ref_level"] = pts["level"]
+    s["last_kf_id"] = 0
+    return s, pts
+
+
+LIVE = lambda abi: (abi.SEED_NOT_VISIBLE, abi.SEED_SHORT_BASELINE, abi.SEED_NOT_FOUND, abi.SEED_NO_DEPTH,
+                    abi.SEED_NO_PARALLAX, abi.SEED_TOO_CLOSE, abi.SEED_UPDATED)
+
+
+@pytest.mark.parametrize("name,seed,step", [("C2", 0, 3), ("C1", 3, 3), ("C3", 2, 1)])
+def test_update_candidates_vs_oracle(binding, sw, scenes, abi, O, name, seed, step):
+    cfg, poses, imgs = sw.sequence(name, seed, 1 + 8 * step)
+    P, cam = cfg["params"], cfg["cam"]
+    xyl, _ = O.detect(P, imgs[0], P.num_features)
+    depth_mean = float(np.median(scenes.seed_points(cfg, xyl, poses[0])["depth"]))
+    ctx = binding.Context(P, cam)
+    try:
+        ref = ctx.frame(imgs[0], corners=False)
+        s0, pts = make_seeds(cfg, scenes, abi, xyl, poses[0], ref.h, depth_mean, seed)
+        assert len(s0) > 400
+        so = s0.copy()
+        so["ref_frame"] = 0
+        sg_free = s0.copy()
+        live_o = np.ones(len(so), bool)
+        live_g = np.ones(len(so), bool)
+        worst = dict(rho=0.0, sigma2=0.0, a=0.0, b=0.0, px=0.0)
+        n_status = n_cmp = 0
+        for k in range(step, len(imgs), step):
+            cur = ctx.frame(imgs[k], corners=True)
+            # teacher forcing: the device starts every frame from the oracle's state
+            sg_in = so.copy()
+            sg_in["ref_frame"] = ref.h
+            got = ctx.update_candidates(cur, poses[k], sg_in[live_o], depth_mean)
+            so[live_o] = O.update_candidates(P, cam, imgs[k], poses[k], [imgs[0]], so[live_o], depth_mean)
+            exp = so[live_o]
+            same = got["status"] == exp["status"]
+            n_status += int((~same).sum())
+            n_cmp += len(exp)
+            upd = same & (exp["status"] >= abi.SEED_UPDATED)
+            for key in ("rho", "sigma2", "a", "b"):
+                if upd.any():
+                    worst[key] = max(worst[key], float(np.max(np.abs(got[key][upd] - exp[key][upd]) /
+                                                              np.maximum(np.abs(exp[key][upd]), 1e-12))))
+            found = same & (exp["status"] >= abi.SEED_NO_DEPTH)
+            if found.any():
+                worst["px"] = max(worst["px"], float(np.abs(got["px"][found] - exp["px"][found]).max()))
+            nf = same & np.isin(exp["status"], (abi.SEED_NOT_FOUND, abi.SEED_DELETE_FAILED))
+            assert np.array_equal(got["n_failed"][nf], exp["n_failed"][nf]) and np.array_equal(got["b"][nf], exp["b"][nf])
+            # free run of the device, its own state from frame to frame
+            sg_free[live_g] = ctx.update_candidates(cur, poses[k], sg_free[live_g], depth_mean)
+            live_o &= np.isin(so["status"], LIVE(abi))
+            live_g &= np.isin(sg_free["status"], LIVE(abi))
+            cur.destroy()
+        conv_o = so["status"] == abi.SEED_CONVERGED
+        conv_g = sg_free["status"] == abi.SEED_CONVERGED
+        print(f"{name}: {len(so)} seeds, {n_status} of {n_cmp} statuses differ, worst relative {worst}, "
+              f"converged oracle {conv_o.sum()} device {conv_g.sum()}")
+        assert n_status <= max(2, n_cmp // 500)
+        assert worst["px"] <= 0.01                       # FeatureAlign / Matcher bar of BASELINE.json
+        assert worst["rho"] <= 1e-4 and worst["sigma2"] <= 1e-3 and worst["a"] <= 1e-3 and worst["b"] <= 1e-3
+        assert conv_o.sum() >= 20
+        assert abs(int(conv_o.sum()) - int(conv_g.sum())) <= max(3, len(so) // 100)
+        both = conv_o & conv_g
+        assert np.abs(so["p3d"][both] - sg_free["p3d"][both]).max() < 1e-3      # 1 mm
+        # converged points lie on the plane z = 0 of the synthetic world
+        assert np.median(np.abs(sg_free["p3d"][conv_g][:, 2])) < 0.02
+        ref.destroy()
+    finally:
+        ctx.close()
+
+
+def test_update_candidates_edge_cases(binding, sw, scenes, abi, O):
+    cfg, poses, imgs = sw.sequence("C2", 1, 7)
+    P, cam = cfg["params"], cfg["cam"]
+    xyl, _ = O.detect(P, imgs[0], P.num_features)
+    ctx = binding.Context(P, cam)
+    try:
+        ref = ctx.frame(imgs[0], corners=False)
+        cur = ctx.frame(imgs[6], corners=True)
+        s, _ = make_seeds(cfg, scenes, abi, xyl, poses[0], ref.h, 2.0)
+        s = s[:64].copy()
+        # empty batch
+        assert len(ctx.update_candidates(cur, poses[6], s[:0], 2.0)) == 0
+        # behind the camera / far outside the image: not visible; old ones are deleted
+        s["rho"][:8] = -0.5
+        s["last_kf_id"][:4] = -50
+        # same pose as the reference: baseline too short
+        got0 = ctx.update_candidates(cur, poses[0], s, 2.0, min_kf_id=-10)
+        so = s.copy(); so["ref_frame"] = 0
+        exp0 = O.update_candidates(P, cam, imgs[6], poses[0], [imgs[0]], so, 2.0, min_kf_id=-10)
+        assert np.array_equal(got0["status"], exp0["status"])
+        assert (got0["status"][:4] == abi.SEED_DELETE_OLD).all() and (got0["status"][4:8] == abi.SEED_NOT_VISIBLE).all()
+        assert (got0["status"][8:] == abi.SEED_SHORT_BASELINE).all()
+        # a failing seed is deleted once n_failed exceeds max_failed
+        s2 = s[8:16].copy()
+        s2["ref_px"] = [[3.0, 3.0]] * 8          # reference patch leaves the image: SearchPoint fails
+        s2["n_failed"] = P.max_failed
+        got = ctx.update_candidates(cur, poses[6], s2, 2.0)
+        s2o = s2.copy(); s2o["ref_frame"] = 0
+        exp = O.update_candidates(P, cam, imgs[6], poses[6], [imgs[0]], s2o, 2.0)
+        assert np.array_equal(got["status"], exp["status"])
+        vis = exp["status"] != abi.SEED_NOT_VISIBLE
+        assert (got["status"][vis] == abi.SEED_DELETE_FAILED).all() and vis.any()
+        assert np.array_equal(got["b"], exp["b"]) and np.array_equal(got["n_failed"], exp["n_failed"])
+        ref.destroy(); cur.destroy()
+    finally:
+        ctx.close()

@@ -273,3 +273,37 @@ def test_shi_tomasi_known_answers(O):
     got = O.shi_tomasi(tex, x0, y0)
     assert abs(got - expect) <= 1e-3 * expect
     assert O.shi_tomasi(tex, 4, 20) == 0.0
+
+
+def test_depth_filter_converges_to_the_plane(O, sw, scenes, abi):
+    """Known answer for Map::UpdateCandidates + Point::Update: candidates started 10 % off converge onto the synthetic
+    plane z = 0 when updated with frames of known pose."""
+    cfg, poses, imgs = sw.sequence("C2", 0, 25)
+    P, cam = cfg["params"], cfg["cam"]
+    xyl, _ = O.detect(P, imgs[0], P.num_features)
+    pts = scenes.seed_points(cfg, xyl, poses[0], one_per_cell=True, margin=12)
+    n = len(pts["px"])
+    assert n > 150
+    rng = np.random.default_rng(0)
+    s = np.zeros(n, abi.SEED_DT)
+    s["ref_frame"] = 0
+    s["ref_T"] = poses[0]
+    s["ref_px"] = pts["px"]; s["ref_v"] = pts["v"]; s["ref_level"] = pts["level"]
+    s["rho"] = 1.0 / (pts["depth"] * (1.0 + rng.uniform(-0.1, 0.1, n)))
+    s["sigma2"] = 1.0; s["a"] = 10.0; s["b"] = 10.0; s["z_range"] = 6.0; s["cos_alpha"] = 1.0
+    s["last_distance"] = 1.0 / s["rho"]
+    depth_mean = float(np.median(pts["depth"]))
+    live = np.ones(n, bool)
+    sig0 = s["sigma2"].copy()
+    for k in range(3, 25, 3):
+        s[live] = O.update_candidates(P, cam, imgs[k], poses[k], [imgs[0]], s[live], depth_mean)
+        live &= ~np.isin(s["status"], (abi.SEED_CONVERGED, abi.SEED_DELETE_OLD, abi.SEED_DELETE_FAILED))
+    conv = s["status"] == abi.SEED_CONVERGED
+    assert conv.sum() > 0.4 * n, f"only {conv.sum()} of {n} candidates converged"
+    z = np.abs(s["p3d"][conv][:, 2])
+    assert np.median(z) < 0.01 and np.percentile(z, 90) < 0.05, (np.median(z), np.percentile(z, 90))
+    # the variance of every updated seed shrank, and converged depths are within 1 % of the truth
+    upd = s["status"] >= abi.SEED_UPDATED
+    assert (s["sigma2"][upd] < sig0[upd]).all()
+    err = np.abs(1.0 / s["rho"][conv] - pts["depth"][conv]) / pts["depth"][conv]
+    assert np.median(err) < 0.01
