@@ -214,7 +214,8 @@ _HLIB = None
 HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", "sdvlh_tracker_destroy",
                 "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_phases",
                 "sdvlh_tracker_ctx", "sdvlh_tracker_groups", "sdvlh_tracker_threads", "sdvlh_tracker_run",
-                "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles", "sdvlh_tracker_set_prefetch", "sdvlh_device_pose_refinement"]
+                "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles", "sdvlh_tracker_set_prefetch", "sdvlh_device_pose_refinement",
+                "sdvlh_map_update_candidates"]
 
 
 def build_host(verbose=False):
@@ -238,6 +239,28 @@ def load_host():
         H.sdvlh_tracker_ctx.restype = C.c_void_p
         _HLIB = H
     return _HLIB
+
+
+def host_map_update_candidates(params, cam, ref_img, ref_T, cur_imgs, cur_poses, seeds, depth_mean, min_kf_id=-1000):
+    """sdvl::Map::UpdateCandidates of the C++ host mirror over a list of frames (test hook). Returns (seeds, n_left)."""
+    lib = load_host()
+    lib.sdvlh_config_set(C.byref(params), C.byref(cam))
+    ref_img = np.ascontiguousarray(ref_img, np.uint8)
+    h, w = ref_img.shape
+    curs = [np.ascontiguousarray(i, np.uint8) for i in cur_imgs]
+    arr = (C.c_void_p * len(curs))(*[c.ctypes.data for c in curs])
+    poses = np.ascontiguousarray(cur_poses, np.float64).reshape(-1, 7)
+    ref_T = np.ascontiguousarray(ref_T, np.float64)
+    seeds = np.ascontiguousarray(seeds).copy()
+    assert seeds.dtype == abi.SEED_DT
+    left = C.c_int(0)
+    lib.sdvlh_map_update_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
+    rc = lib.sdvlh_map_update_candidates(ptr(ref_img), ptr(ref_T), arr, ptr(poses), len(curs), w, h, ptr(seeds),
+                                         seeds.shape[0], depth_mean, min_kf_id, C.byref(left))
+    if rc:
+        raise RuntimeError(lib.sdvlh_last_error().decode())
+    return seeds, left.value
 
 
 class HostTracker:

@@ -92,6 +92,39 @@ void Point::InitFixed(const std::shared_ptr<Feature>& f, const Eigen::Vector3d& 
   fixed_ = true;
 }
 
+void Point::InitCandidate(const std::shared_ptr<Feature>& p, double depth) {   // point.cc:48-61
+  feature_ = p;
+  a_ = 10;
+  b_ = 10;
+  rho_ = 1.0 / depth;
+  sigma2_ = 1.0;
+  z_range_ = std::sqrt(sigma2_ * 36);
+  cos_alpha_ = 1.0;
+  last_distance_ = 1.0 / rho_;
+}
+void Point::ToSeed(sdvlb_seed* s) const {
+  const std::shared_ptr<Frame> rf = feature_->GetFrame();
+  std::memset(s, 0, sizeof(*s));
+  s->ref_frame = rf->Handle();
+  rf->GetPose().ToArray(s->ref_T);
+  s->ref_px[0] = feature_->GetPosition()(0); s->ref_px[1] = feature_->GetPosition()(1);
+  for (int i = 0; i < 3; i++) s->ref_v[i] = feature_->GetVector()(i);
+  s->rho = rho_; s->sigma2 = sigma2_; s->a = a_; s->b = b_; s->z_range = z_range_;
+  s->cos_alpha = cos_alpha_; s->last_distance = last_distance_;
+  s->ref_level = feature_->GetLevel();
+  s->n_failed = n_failed_;
+  s->last_kf_id = last_kf_id_;
+}
+void Point::FromSeed(const sdvlb_seed& s) {
+  rho_ = s.rho; sigma2_ = s.sigma2; a_ = s.a; b_ = s.b;
+  cos_alpha_ = s.cos_alpha; last_distance_ = s.last_distance;
+  n_failed_ = s.n_failed;
+  if (s.status == SDVLB_SEED_CONVERGED) {   // Point::HasConverged (point.cc:168-174)
+    p3d_ = Eigen::Vector3d(s.p3d[0], s.p3d[1], s.p3d[2]);
+    fixed_ = true;
+  }
+}
+
 Feature::Feature(const std::shared_ptr<Frame>& f, const Eigen::Vector2d& p, int l) {
   frame_ = f;
   point_ = nullptr;
@@ -104,6 +137,46 @@ void Map::DeletePoint(const std::shared_ptr<Point>& point) {
   std::unique_lock<std::mutex> lock(mutex_map_);
   points_trash_.push_back(point);
 }
+// map.cc:397-498.  The reference walks candidates_ and erases as it goes; every candidate's outcome depends only on
+// its own state and the frame, so all SearchPoint / triangulation / Point::Update calls go to the device in one batch
+// and the walk is replayed over the results (same erase / DeletePoint decisions, same order).  The reference's
+// candidates_updating_halt_ early return (map.cc:414-420) belongs to its two-thread protocol and is the caller's.
+void Map::UpdateCandidates(const std::shared_ptr<Frame>& frame, double depth_mean, int min_kf_id) {
+  std::vector<std::shared_ptr<Point>> kept;
+  std::vector<int> slot(candidates_.size(), -1);
+  seeds_.clear();
+  for (size_t i = 0; i < candidates_.size(); i++) {
+    const std::shared_ptr<Point>& p = candidates_[i];
+    if (p->ToDelete()) continue;   // map.cc:426-430: DeletePoint + erase below
+    slot[i] = int(seeds_.size());
+    seeds_.emplace_back();
+    p->ToSeed(&seeds_.back());
+  }
+  sdvlb_seed_params sp;
+  sp.depth_mean = depth_mean;
+  sp.map_scale = 1.0;          // Config::MapScale()      (config.cc:70)
+  sp.scale_min_dist = 0.25;    // Config::ScaleMinDist()  (config.cc:75)
+  sp.min_kf_id = min_kf_id;
+  sp.pad_ = 0;
+  double T[7];
+  frame->GetPose().ToArray(T);
+  const int rc = sdvlb_update_candidates(frame->Context(), frame->Handle(), T, seeds_.data(), int(seeds_.size()), &sp);
+  if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_update_candidates failed: ") + sdvlb_last_error());
+  for (size_t i = 0; i < candidates_.size(); i++) {
+    const std::shared_ptr<Point>& p = candidates_[i];
+    if (slot[i] < 0) { DeletePoint(p); continue; }
+    const sdvlb_seed& s = seeds_[slot[i]];
+    p->FromSeed(s);
+    switch (s.status) {
+      case SDVLB_SEED_DELETE_OLD: DeletePoint(p); break;                 // map.cc:433-436: erased
+      case SDVLB_SEED_DELETE_FAILED: DeletePoint(p); kept.push_back(p); break;   // map.cc:449-452: deleted, `it++`
+      case SDVLB_SEED_CONVERGED: break;                                  // map.cc:486-489: erased, now a fixed point
+      default: kept.push_back(p);
+    }
+  }
+  candidates_.swap(kept);
+}
+
 void Map::EmptyTrash() {
   std::vector<std::shared_ptr<Point>> cp;
   {

@@ -120,12 +120,19 @@ class Point {
   bool Unpromote() { n_failed_++; b_++; return n_failed_ > Config::MaxFailed(); }    // point.cc:108-115
   // map seeding (stand-in for InitCandidate + depth-filter convergence, point.cc:46-60,162-176)
   void InitFixed(const std::shared_ptr<Feature>& f, const Eigen::Vector3d& p3d, double rho, double sigma2);
+  void InitCandidate(const std::shared_ptr<Feature>& p, double depth);                // point.cc:48-61
+  // The depth-filter state as the device sees it (Map::UpdateCandidates): Point::Update and HasConverged
+  // (point.cc:63-100,162-176) run inside sdvlb_update_candidates; these copy the state in and out.
+  void ToSeed(sdvlb_seed* s) const;
+  void FromSeed(const sdvlb_seed& s);
+  int GetLastKeyframeID() const { return last_kf_id_; }        // GetLastFeature()->GetFrame()->GetKeyframeID()
+  void SetLastKeyframeID(int id) { last_kf_id_ = id; }
  private:
   int id_;
   PointStatus status_ = P_FOUND;
   bool delete_ = false, fixed_ = false;
-  int last_frame_ = -1, n_successful_ = 0, n_failed_ = 0;
-  double a_ = 10, b_ = 10, rho_ = 1.0, sigma2_ = 1.0;
+  int last_frame_ = -1, n_successful_ = 0, n_failed_ = 0, last_kf_id_ = 0;
+  double a_ = 10, b_ = 10, rho_ = 1.0, sigma2_ = 1.0, z_range_ = 6.0, cos_alpha_ = 1.0, last_distance_ = 1.0;
   std::shared_ptr<Feature> feature_;
   Eigen::Vector3d p3d_;
 };
@@ -150,15 +157,24 @@ class Feature {
 };
 
 // ------------------------------------------------------------------------------------------------ Map stand-in (map.h)
-// Only what FeatureAlign needs: DeletePoint (map.cc:165-168) and EmptyTrash (map.cc:207-253, points part).
+// What FeatureAlign needs -- DeletePoint (map.cc:165-168), EmptyTrash (map.cc:207-253, points part) -- and the
+// mapping thread's candidate pass, UpdateCandidates (map.cc:397-498), which evaluates all candidates of a frame in one
+// device call (sdvlb_update_candidates) and then applies the list surgery in the reference's order.
 class Map {
  public:
   void DeletePoint(const std::shared_ptr<Point>& point);
   void EmptyTrash();
   std::mutex& GetMutex() { return mutex_map_; }
+  void AddCandidate(const std::shared_ptr<Point>& p) { candidates_.push_back(p); }
+  std::vector<std::shared_ptr<Point>>& GetCandidates() { return candidates_; }
+  // depth_mean = frame->GetSceneDepth(); min_kf_id = last_kf_->GetKeyframeID() - 2 * Config::MaxSearchKeyframes()
+  void UpdateCandidates(const std::shared_ptr<Frame>& frame, double depth_mean, int min_kf_id);
+  const std::vector<sdvlb_seed>& LastSeeds() const { return seeds_; }   // per-candidate outcome of the last pass
  private:
   std::mutex mutex_map_;
   std::vector<std::shared_ptr<Point>> points_trash_;
+  std::vector<std::shared_ptr<Point>> candidates_;
+  std::vector<sdvlb_seed> seeds_;
 };
 
 // ------------------------------------------------------------------------------------------------ device context

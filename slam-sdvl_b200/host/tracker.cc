@@ -798,6 +798,62 @@ void sdvlh_config_set(const sdvlb_params* p, const sdvlb_camera* cam) { sdvl::Co
 // FeatureAlign::SelectInliers / OptimizePose of the class-API path on the device (1) or on the host (0, default).
 void sdvlh_device_pose_refinement(int on) { sdvl::FeatureAlign::SetDevicePoseRefinement(on != 0); }
 
+// Test hook for the class-level mapping pass: builds a keyframe with n candidate points (state taken from `seeds`),
+// runs Map::UpdateCandidates against each of the n_frames images (poses: n_frames x 7) and writes the candidates'
+// final state back into `seeds` (status = outcome of the last pass a candidate took part in).  *n_left = candidates
+// still in the list.  Config must have been set (sdvlh_config_set).
+int sdvlh_map_update_candidates(const uint8_t* ref_img, const double ref_T[7], const uint8_t* const* cur_imgs,
+                                const double* cur_poses, int n_frames, int w, int h, sdvlb_seed* seeds, int n,
+                                double depth_mean, int min_kf_id, int* n_left) {
+  try {
+    using namespace sdvl;
+    Camera cam;
+    cv::Mat rm(h, w, CV_8UC1, const_cast<uint8_t*>(ref_img));
+    shared_ptr<Frame> ref = std::make_shared<Frame>(&cam, static_cast<ORBDetector*>(nullptr), rm, false);
+    ref->SetPose(SE3(ref_T));
+    ref->SetKeyframe();
+    Map map;
+    vector<shared_ptr<Point>> pts(n);
+    for (int i = 0; i < n; i++) {
+      auto ft = std::make_shared<Feature>(ref, Eigen::Vector2d(seeds[i].ref_px[0], seeds[i].ref_px[1]), seeds[i].ref_level);
+      pts[i] = std::make_shared<Point>();
+      pts[i]->InitCandidate(ft, 1.0 / seeds[i].rho);
+      sdvlb_seed s0 = seeds[i];
+      s0.status = SDVLB_SEED_UPDATED;
+      pts[i]->FromSeed(s0);
+      pts[i]->SetLastKeyframeID(seeds[i].last_kf_id);
+      ft->SetPoint(pts[i]);
+      map.AddCandidate(pts[i]);
+      seeds[i].status = -1;
+    }
+    for (int k = 0; k < n_frames; k++) {
+      cv::Mat m(h, w, CV_8UC1, const_cast<uint8_t*>(cur_imgs[k]));
+      shared_ptr<Frame> cur = std::make_shared<Frame>(&cam, static_cast<ORBDetector*>(nullptr), m, true);
+      cur->SetPose(SE3(cur_poses + 7 * k));
+      vector<shared_ptr<Point>> before = map.GetCandidates();
+      map.UpdateCandidates(cur, depth_mean, min_kf_id);
+      const vector<sdvlb_seed>& out = map.LastSeeds();
+      size_t j = 0;
+      for (size_t c = 0; c < before.size(); c++) {
+        if (before[c]->ToDelete()) continue;
+        for (int i = 0; i < n; i++)
+          if (pts[i] == before[c]) {
+            const sdvlb_frame* keep = seeds[i].ref_frame;
+            seeds[i] = out[j];
+            seeds[i].ref_frame = keep;
+          }
+        j++;
+      }
+      map.EmptyTrash();
+    }
+    if (n_left) *n_left = int(map.GetCandidates().size());
+    return 0;
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return -1;
+  }
+}
+
 // resident != 0: the sequences live on the device (sdvlb_seq_*): the host neither marshals features nor replays matches.
 void* sdvlh_tracker_create2(const double plane[4], int max_points, int kf_every, int n_seq, int n_groups, int n_threads,
                             int device, int timing, int resident) {

@@ -131,3 +131,42 @@ def test_update_candidates_edge_cases(binding, sw, scenes, abi, O):
         ref.destroy(); cur.destroy()
     finally:
         ctx.close()
+
+
+def test_host_map_update_candidates_equals_c_abi(binding, sw, scenes, abi, O):
+    """sdvl::Map::UpdateCandidates (C++ host mirror: one device call per frame + the reference's list surgery) ends in
+    the same candidate states as driving sdvlb_update_candidates by hand."""
+    cfg, poses, imgs = sw.sequence("C2", 4, 19)
+    P, cam = cfg["params"], cfg["cam"]
+    xyl, _ = O.detect(P, imgs[0], P.num_features)
+    depth_mean = float(np.median(scenes.seed_points(cfg, xyl, poses[0])["depth"]))
+    ks = list(range(3, 19, 3))
+    ctx = binding.Context(P, cam)
+    try:
+        ref = ctx.frame(imgs[0], corners=False)
+        s0, _ = make_seeds(cfg, scenes, abi, xyl, poses[0], ref.h, depth_mean, 4)
+        s0 = s0[:300].copy()
+        s0["last_kf_id"][:5] = -100          # will be deleted as too old once they leave the image
+        s = s0.copy()
+        s["status"] = -1
+        live = np.ones(len(s), bool)
+        for k in ks:
+            cur = ctx.frame(imgs[k], corners=True)
+            s[live] = ctx.update_candidates(cur, poses[k], s[live], depth_mean, min_kf_id=-10)
+            live &= ~np.isin(s["status"], (abi.SEED_CONVERGED, abi.SEED_DELETE_OLD))
+            # map.cc:449-452: a candidate that failed too often is handed to DeletePoint; the trash is emptied after
+            # the pass and the next pass erases it
+            live &= s["status"] != abi.SEED_DELETE_FAILED
+            cur.destroy()
+        ref.destroy()
+    finally:
+        ctx.close()
+    hs, n_left = binding.host_map_update_candidates(P, cam, imgs[0], poses[0], [imgs[k] for k in ks],
+                                                    [poses[k] for k in ks], s0, depth_mean, min_kf_id=-10)
+    assert np.array_equal(hs["status"], s["status"])
+    assert n_left == int(live.sum())
+    for key in ("rho", "sigma2", "a", "b", "cos_alpha", "last_distance"):
+        np.testing.assert_allclose(hs[key], s[key], rtol=1e-9, atol=0)
+    assert np.array_equal(hs["n_failed"], s["n_failed"])
+    print(f"host Map::UpdateCandidates: {len(s)} candidates, {n_left} left after {len(ks)} frames, "
+          f"{(s['status'] == abi.SEED_CONVERGED).sum()} converged")
