@@ -212,3 +212,26 @@ def test_class_api_with_device_pose_refinement(binding, sw):
     print(f"class API, device vs host pose refinement: max {d.max():.2e} m, identical stats {same:.2%}")
     assert d.max() < 1e-9
     assert same == 1.0
+
+
+def test_c5_stress_1080p_2000_features(binding, sw, O):
+    """BASELINE.json configs[4]: 1920x1080, 5-level pyramid, 2000 features per frame -- resident chain and class API
+    against the CPU oracle (one sequence, a keyframe every 4 frames so that the map is re-seeded twice)."""
+    cfg = sw.config("C5")
+    poses = sw.trajectory(cfg, 1, 10)
+    imgs = sw.render(cfg, poses)
+    seqs = [(poses, imgs)]
+    est_r, st_r = _run_tracker(binding, sw, cfg, seqs, resident=True, kf_every=4)
+    est_c, st_c = _run_tracker(binding, sw, cfg, seqs, resident=False, classic=True, kf_every=4)
+    tr = O.Tracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], 4)
+    est_o, st_o, _ = tr.run(imgs, poses)
+    tr.close()
+    for tag, est, st in (("resident", est_r[0], st_r[0]), ("classic", est_c[0], st_c[0])):
+        d = np.array([np.linalg.norm(sw.cam_center(a) - sw.cam_center(b)) for a, b in zip(est, est_o)])
+        ate = float(np.sqrt((d ** 2).mean())) * 1e3
+        same = float((st[:, 1:6] == st_o[:, 1:6]).all(axis=1).mean())
+        print(f"C5 {tag} vs oracle: ATE {ate:.4f} mm (max {d.max()*1e3:.4f}), vs GT {sw.ate(est, poses)*1e3:.3f} mm, identical "
+              f"stats {same:.2%}, matches/frame {st[1:,1].mean():.0f}, features tracked {st[1:,0].mean():.0f}, "
+              f"keyframes {st[:,7].sum()}")
+        assert ate <= ATE_MM
+        assert st[1:, 1].mean() > 300 and same >= 0.8   # one match per 32-px cell that holds a seeded point
