@@ -406,6 +406,8 @@ typedef struct sdvlb_seed {
   int32_t n_failed;             /* Point::n_failed_ */
   int32_t last_kf_id;           /* point->GetLastFeature()->GetFrame()->GetKeyframeID() */
   int32_t status;               /* out: SDVLB_SEED_* */
+  int32_t level;                /* out: pyramid level the match was refined at (SearchPoint's *flevel, when found) */
+  int32_t pad_;
 } sdvlb_seed;
 
 enum {
@@ -426,8 +428,14 @@ typedef struct sdvlb_seed_params {
   double map_scale;        /* Config::MapScale()      1.0  */
   double scale_min_dist;   /* Config::ScaleMinDist()  0.25 */
   int32_t min_kf_id;       /* last_kf->GetKeyframeID() - 2 * Config::MaxSearchKeyframes() */
-  int32_t pad_;
+  int32_t mode;            /* SDVLB_SEEDS_UPDATE or SDVLB_SEEDS_INIT */
 } sdvlb_seed_params;
+/* SDVLB_SEEDS_INIT: the per-corner part of Map::InitCandidates (map.cc:262-395) -- a corner of the new keyframe
+ * (ref_frame; rho = 1/depth_mean, sigma2 = 1) is searched in a connected keyframe (`cur`), triangulated and screened
+ * (parallax, minimum distance) exactly as above, but there is no visibility test and no filter update: status
+ * SDVLB_SEED_UPDATED means "InitCandidate(feature, depth) may be called", with `depth` and `px` (imgpos) filled in.
+ * The 1-px link test against cframe's features (map.cc:325-343) and the list handling stay with the caller. */
+enum { SDVLB_SEEDS_UPDATE = 0, SDVLB_SEEDS_INIT = 1 };
 
 /* The loop body of Map::UpdateCandidates for n candidates against `cur` (with corners) at pose T_cur.  Seeds are
  * updated in place; the caller applies the list surgery (erase / DeletePoint) that the statuses call for. */

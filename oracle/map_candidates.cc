@@ -72,8 +72,9 @@ void UpdateCandidate(const sdvlb_params& P, const std::shared_ptr<Frame>& cur, c
   // map.cc:426-437: pos = point->GetPosition(); frame->IsPointVisible(pos)
   V3 pos = ref->GetWorldPose() * (ft->v * (1.0 / S->rho));
   const V3 rel = cur->pose * pos;
-  bool visible = !(rel.z < 0.0);
-  if (visible) {
+  const bool init = sp.mode == SDVLB_SEEDS_INIT;   // the per-corner part of Map::InitCandidates (map.cc:306-378)
+  bool visible = init || !(rel.z < 0.0);
+  if (visible && !init) {
     V2 ip;
     cam->Project(rel, &ip);
     visible = cam->IsInsideImage(int(ip.x), int(ip.y));
@@ -90,12 +91,13 @@ void UpdateCandidate(const sdvlb_params& P, const std::shared_ptr<Frame>& cur, c
   V2 imgpos;
   int level = 0;
   if (!matcher.SearchPoint(cur, ft, S->rho, std::sqrt(S->sigma2), false, &imgpos, &level)) {
+    if (init) { S->status = SDVLB_SEED_NOT_FOUND; return; }   // map.cc:320-321
     S->n_failed++;   // Point::Unpromote (point.cc:109-116)
     S->b++;
     S->status = S->n_failed > P.max_failed ? SDVLB_SEED_DELETE_FAILED : SDVLB_SEED_NOT_FOUND;
     return;
   }
-  S->px[0] = imgpos.x; S->px[1] = imgpos.y;
+  S->px[0] = imgpos.x; S->px[1] = imgpos.y; S->level = level;
   // map.cc:456-461
   const SE3 pose = cur->pose * ref->pose.Inverse();
   const V3 v3d = cam->Unproject(imgpos);
@@ -110,8 +112,9 @@ void UpdateCandidate(const sdvlb_params& P, const std::shared_ptr<Frame>& cur, c
     S->status = SDVLB_SEED_TOO_CLOSE;
     return;
   }
-  // Point::Update (point.cc:63-100)
   S->status = SDVLB_SEED_UPDATED;
+  if (init) return;   // map.cc:381-388: candidate->InitCandidate(feature, depth) is the caller's
+  // Point::Update (point.cc:63-100)
   const double px_error_angle = std::atan(1.0 / (2.0 * cam->fx)) * 2.0;   // camera.h:104-107
   const SE3 pose_u = ref->pose * cur->pose.Inverse();
   const double tau = ComputeTau(pose_u, ft->v, depth, px_error_angle);

@@ -119,7 +119,7 @@ def search_points(params, cam, cur_img, T_cur, ref_imgs, cands):
 
 
 def update_candidates(params, cam, cur_img, T_cur, ref_imgs, seeds, depth_mean, min_kf_id=-1000, map_scale=1.0,
-                      scale_min_dist=0.25):
+                      scale_min_dist=0.25, mode=0):
     """Oracle Map::UpdateCandidates loop body. seeds: abi.SEED_DT array whose ref_frame fields index ref_imgs."""
     cur_img = np.ascontiguousarray(cur_img)
     h, w = cur_img.shape
@@ -128,7 +128,7 @@ def update_candidates(params, cam, cur_img, T_cur, ref_imgs, seeds, depth_mean, 
     seeds = np.ascontiguousarray(seeds).copy()
     assert seeds.dtype == abi.SEED_DT
     T_cur = np.ascontiguousarray(T_cur, np.float64)
-    sp = abi.SeedParams(depth_mean, map_scale, scale_min_dist, min_kf_id, 0)
+    sp = abi.SeedParams(depth_mean, map_scale, scale_min_dist, min_kf_id, mode)
     rc = lib().orc_update_candidates(C.byref(params), C.byref(cam), ptr(cur_img), w, h, ptr(T_cur), arr, len(refs),
                                      ptr(seeds), seeds.shape[0], C.byref(sp))
     assert rc == 0

@@ -70,17 +70,18 @@ MATCH_DT = np.dtype([("px", "f8", 2), ("proj", "f8", 2), ("level", "i4"), ("stat
 SEED_DT = np.dtype([("ref_frame", "u8"), ("ref_T", "f8", 7), ("ref_px", "f8", 2), ("ref_v", "f8", 3), ("rho", "f8"),
                     ("sigma2", "f8"), ("a", "f8"), ("b", "f8"), ("z_range", "f8"), ("cos_alpha", "f8"),
                     ("last_distance", "f8"), ("p3d", "f8", 3), ("depth", "f8"), ("px", "f8", 2), ("ref_level", "i4"),
-                    ("n_failed", "i4"), ("last_kf_id", "i4"), ("status", "i4")])
+                    ("n_failed", "i4"), ("last_kf_id", "i4"), ("status", "i4"), ("level", "i4"), ("pad_", "i4")])
 (SEED_NOT_VISIBLE, SEED_DELETE_OLD, SEED_SHORT_BASELINE, SEED_NOT_FOUND, SEED_DELETE_FAILED, SEED_NO_DEPTH,
  SEED_NO_PARALLAX, SEED_TOO_CLOSE, SEED_UPDATED, SEED_CONVERGED) = range(10)
+SEEDS_UPDATE, SEEDS_INIT = 0, 1
 
 
 class SeedParams(C.Structure):
     _fields_ = [("depth_mean", C.c_double), ("map_scale", C.c_double), ("scale_min_dist", C.c_double),
-                ("min_kf_id", C.c_int32), ("pad_", C.c_int32)]
+                ("min_kf_id", C.c_int32), ("mode", C.c_int32)]
 
 
-assert SEED_DT.itemsize == 224   # sizeof(sdvlb_seed)
+assert SEED_DT.itemsize == 232   # sizeof(sdvlb_seed)
 assert ALIGN_FEAT_DT.itemsize == C.sizeof(AlignFeat)
 assert GN_ITER_DT.itemsize == C.sizeof(GnIter)
 assert CANDIDATE_DT.itemsize == C.sizeof(Candidate)

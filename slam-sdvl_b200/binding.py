@@ -175,13 +175,14 @@ class Context:
                                           ptr(out)))
         return out
 
-    def update_candidates(self, cur, T_cur, seeds, depth_mean, min_kf_id=-1000, map_scale=1.0, scale_min_dist=0.25):
+    def update_candidates(self, cur, T_cur, seeds, depth_mean, min_kf_id=-1000, map_scale=1.0, scale_min_dist=0.25,
+                          mode=0):
         """Map::UpdateCandidates loop body on the device. seeds: abi.SEED_DT array whose ref_frame fields hold Frame
         handles; returns the updated copy."""
         seeds = np.ascontiguousarray(seeds).copy()
         assert seeds.dtype == abi.SEED_DT
         T = np.ascontiguousarray(T_cur, np.float64)
-        sp = abi.SeedParams(depth_mean, map_scale, scale_min_dist, min_kf_id, 0)
+        sp = abi.SeedParams(depth_mean, map_scale, scale_min_dist, min_kf_id, mode)
         _check(load().sdvlb_update_candidates(C.c_void_p(self.h), C.c_void_p(cur.h), ptr(T), ptr(seeds), seeds.shape[0],
                                               C.byref(sp)))
         return seeds
@@ -215,7 +216,7 @@ HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", 
                 "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_phases",
                 "sdvlh_tracker_ctx", "sdvlh_tracker_groups", "sdvlh_tracker_threads", "sdvlh_tracker_run",
                 "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles", "sdvlh_tracker_set_prefetch", "sdvlh_device_pose_refinement",
-                "sdvlh_map_update_candidates"]
+                "sdvlh_map_update_candidates", "sdvlh_map_init_candidates"]
 
 
 def build_host(verbose=False):
@@ -261,6 +262,36 @@ def host_map_update_candidates(params, cam, ref_img, ref_T, cur_imgs, cur_poses,
     if rc:
         raise RuntimeError(lib.sdvlh_last_error().decode())
     return seeds, left.value
+
+
+def host_map_init_candidates(params, cam, img_new, T_new, img_old, T_old, upd_imgs, upd_T, img_last, T_last, depth_mean,
+                             cap=4096):
+    """sdvl::Map::InitCandidates + UpdateCandidates + AddConnectionsPoints of the C++ host mirror (test hook)."""
+    lib = load_host()
+    lib.sdvlh_config_set(C.byref(params), C.byref(cam))
+    img_new = np.ascontiguousarray(img_new, np.uint8)
+    img_old = np.ascontiguousarray(img_old, np.uint8)
+    img_last = np.ascontiguousarray(img_last, np.uint8)
+    h, w = img_new.shape
+    upd = [np.ascontiguousarray(i, np.uint8) for i in upd_imgs]
+    arr = (C.c_void_p * max(1, len(upd)))(*[u.ctypes.data for u in upd])
+    upd_T = np.ascontiguousarray(upd_T, np.float64).reshape(-1, 7)
+    T_new, T_old, T_last = (np.ascontiguousarray(t, np.float64) for t in (T_new, T_old, T_last))
+    out = np.zeros(5, np.int32)
+    px = np.zeros((cap, 2))
+    rho = np.zeros(cap)
+    fixed = np.zeros(cap, np.int32)
+    lib.sdvlh_map_init_candidates.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                               C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                               C.c_int]
+    rc = lib.sdvlh_map_init_candidates(ptr(img_new), ptr(T_new), ptr(img_old), ptr(T_old), arr, ptr(upd_T), len(upd),
+                                       ptr(img_last), ptr(T_last), w, h, depth_mean, ptr(out), ptr(px), ptr(rho),
+                                       ptr(fixed), cap)
+    if rc:
+        raise RuntimeError(lib.sdvlh_last_error().decode())
+    n = int(out[0])
+    return dict(created=n, listed=int(out[1]), left=int(out[2]), fixed=int(out[3]), linked=int(out[4]),
+                px=px[:n], rho=rho[:n], is_fixed=fixed[:n])
 
 
 class HostTracker:

@@ -417,8 +417,9 @@ __global__ void __launch_bounds__(SE_THREADS) seed_update_kernel(sdvlb_seed* __r
   double pos[3], rel[3];
   se3_apply(T_ref_w, v[0] / rho, v[1] / rho, v[2] / rho, pos[0], pos[1], pos[2]);
   se3_apply(T_cur, pos[0], pos[1], pos[2], rel[0], rel[1], rel[2]);
-  bool visible = !(rel[2] < 0.0);
-  if (visible) {
+  const bool init = A.sp.mode == SDVLB_SEEDS_INIT;   // Map::InitCandidates: no visibility test, no filter update
+  bool visible = init || !(rel[2] < 0.0);
+  if (visible && !init) {
     double pu, pv;
     cam_project(cam, rel[0], rel[1], rel[2], pu, pv);
     visible = finite2(pu, pv) && fabs(pu) < 1e9 && fabs(pv) < 1e9;
@@ -450,10 +451,14 @@ __global__ void __launch_bounds__(SE_THREADS) seed_update_kernel(sdvlb_seed* __r
     __syncwarp();
     const sdvlb_match m = s_match[warp];
     if (m.status != SDVLB_MATCH_FOUND) {
-      const int nf = S.n_failed + 1;          // Point::Unpromote (point.cc:109-116)
-      b += 1.0;
-      status = nf > A.dp.p.max_failed ? SDVLB_SEED_DELETE_FAILED : SDVLB_SEED_NOT_FOUND;
-      if (lane == 0) { S.n_failed = nf; S.b = b; }
+      if (init) {
+        status = SDVLB_SEED_NOT_FOUND;        // map.cc:320-321: next corner
+      } else {
+        const int nf = S.n_failed + 1;        // Point::Unpromote (point.cc:109-116)
+        b += 1.0;
+        status = nf > A.dp.p.max_failed ? SDVLB_SEED_DELETE_FAILED : SDVLB_SEED_NOT_FOUND;
+        if (lane == 0) { S.n_failed = nf; S.b = b; }
+      }
     } else {
       // GetDepthFromTriangulation(pose, feature->GetVector(), v3d, &depth) (utils.cc:193-205)
       const DSE3 pose = se3_mul(T_cur, T_ref_w);
@@ -466,7 +471,7 @@ __global__ void __launch_bounds__(SE_THREADS) seed_update_kernel(sdvlb_seed* __r
       const double a01 = rv[0] * vc[0] + rv[1] * vc[1] + rv[2] * vc[2];
       const double a11 = vc[0] * vc[0] + vc[1] * vc[1] + vc[2] * vc[2];
       const double det = a00 * a11 - a01 * a01;
-      if (lane == 0) { S.px[0] = m.px[0]; S.px[1] = m.px[1]; }
+      if (lane == 0) { S.px[0] = m.px[0]; S.px[1] = m.px[1]; S.level = m.level; }
       if (det < 0.000001) {
         status = SDVLB_SEED_NO_DEPTH;
       } else {
@@ -480,6 +485,8 @@ __global__ void __launch_bounds__(SE_THREADS) seed_update_kernel(sdvlb_seed* __r
           status = SDVLB_SEED_NO_PARALLAX;
         } else if (depth < A.sp.map_scale * A.sp.scale_min_dist || depth < A.sp.depth_mean * A.sp.scale_min_dist) {
           status = SDVLB_SEED_TOO_CLOSE;
+        } else if (init) {
+          status = SDVLB_SEED_UPDATED;   // the caller runs Point::InitCandidate(feature, depth)
         } else {
           // Point::Update(frame, depth, px_error_angle) (point.cc:63-100)
           status = SDVLB_SEED_UPDATED;

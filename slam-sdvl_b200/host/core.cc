@@ -2,6 +2,8 @@
 // The SE3 / LDLT arithmetic is the same __host__ __device__ code the kernels use (csrc/common.cuh), which follows
 // extra/se3.cc and Eigen's documented algorithms.
 #include <atomic>
+#include <cstring>
+#include <set>
 #include <cmath>
 #include <stdexcept>
 #include <string>
@@ -119,7 +121,7 @@ void Point::FromSeed(const sdvlb_seed& s) {
   rho_ = s.rho; sigma2_ = s.sigma2; a_ = s.a; b_ = s.b;
   cos_alpha_ = s.cos_alpha; last_distance_ = s.last_distance;
   n_failed_ = s.n_failed;
-  if (s.status == SDVLB_SEED_CONVERGED) {   // Point::HasConverged (point.cc:168-174)
+  if (s.status == SDVLB_SEED_CONVERGED && !fixed_) {   // Point::HasConverged (point.cc:162-174); a fixed point keeps p3d_
     p3d_ = Eigen::Vector3d(s.p3d[0], s.p3d[1], s.p3d[2]);
     fixed_ = true;
   }
@@ -137,44 +139,212 @@ void Map::DeletePoint(const std::shared_ptr<Point>& point) {
   std::unique_lock<std::mutex> lock(mutex_map_);
   points_trash_.push_back(point);
 }
-// map.cc:397-498.  The reference walks candidates_ and erases as it goes; every candidate's outcome depends only on
-// its own state and the frame, so all SearchPoint / triangulation / Point::Update calls go to the device in one batch
-// and the walk is replayed over the results (same erase / DeletePoint decisions, same order).  The reference's
+// map.cc:397-498.  The reference walks candidates_ and erases as it goes; a candidate's outcome depends only on its
+// own state and the frame, so the SearchPoint / triangulation / Point::Update calls of a pass go to the device as a
+// batch and the walk is replayed over the results (same erase / DeletePoint decisions).  InitCandidates lists every
+// non-fixed candidate twice (map.cc:386,393), so the reference applies each observation twice, the second time to the
+// state the first left behind: the k-th occurrences of the points form the k-th batch.  The reference's
 // candidates_updating_halt_ early return (map.cc:414-420) belongs to its two-thread protocol and is the caller's.
 void Map::UpdateCandidates(const std::shared_ptr<Frame>& frame, double depth_mean, int min_kf_id) {
-  std::vector<std::shared_ptr<Point>> kept;
-  std::vector<int> slot(candidates_.size(), -1);
-  seeds_.clear();
-  for (size_t i = 0; i < candidates_.size(); i++) {
-    const std::shared_ptr<Point>& p = candidates_[i];
-    if (p->ToDelete()) continue;   // map.cc:426-430: DeletePoint + erase below
-    slot[i] = int(seeds_.size());
-    seeds_.emplace_back();
-    p->ToSeed(&seeds_.back());
+  const size_t n = candidates_.size();
+  std::vector<int> rank(n, 0);
+  int rounds = 0;
+  for (size_t i = 0; i < n; i++) {
+    for (size_t j = 0; j < i; j++)
+      if (candidates_[j] == candidates_[i]) rank[i]++;
+    rounds = std::max(rounds, rank[i] + 1);
   }
   sdvlb_seed_params sp;
   sp.depth_mean = depth_mean;
   sp.map_scale = 1.0;          // Config::MapScale()      (config.cc:70)
   sp.scale_min_dist = 0.25;    // Config::ScaleMinDist()  (config.cc:75)
   sp.min_kf_id = min_kf_id;
-  sp.pad_ = 0;
+  sp.mode = SDVLB_SEEDS_UPDATE;
   double T[7];
   frame->GetPose().ToArray(T);
-  const int rc = sdvlb_update_candidates(frame->Context(), frame->Handle(), T, seeds_.data(), int(seeds_.size()), &sp);
-  if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_update_candidates failed: ") + sdvlb_last_error());
-  for (size_t i = 0; i < candidates_.size(); i++) {
-    const std::shared_ptr<Point>& p = candidates_[i];
-    if (slot[i] < 0) { DeletePoint(p); continue; }
-    const sdvlb_seed& s = seeds_[slot[i]];
-    p->FromSeed(s);
-    switch (s.status) {
-      case SDVLB_SEED_DELETE_OLD: DeletePoint(p); break;                 // map.cc:433-436: erased
-      case SDVLB_SEED_DELETE_FAILED: DeletePoint(p); kept.push_back(p); break;   // map.cc:449-452: deleted, `it++`
-      case SDVLB_SEED_CONVERGED: break;                                  // map.cc:486-489: erased, now a fixed point
-      default: kept.push_back(p);
+  seeds_.assign(n, sdvlb_seed());
+  for (auto& s : seeds_) s.status = -1;
+  std::vector<char> erase(n, 0);
+  std::vector<sdvlb_seed> batch;
+  std::vector<size_t> who;
+  for (int r = 0; r < rounds; r++) {
+    batch.clear();
+    who.clear();
+    for (size_t i = 0; i < n; i++) {
+      if (rank[i] != r) continue;
+      const std::shared_ptr<Point>& p = candidates_[i];
+      if (p->ToDelete()) { DeletePoint(p); erase[i] = 1; continue; }   // map.cc:426-430
+      batch.emplace_back();
+      p->ToSeed(&batch.back());
+      who.push_back(i);
+    }
+    const int rc = sdvlb_update_candidates(frame->Context(), frame->Handle(), T, batch.data(), int(batch.size()), &sp);
+    if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_update_candidates failed: ") + sdvlb_last_error());
+    for (size_t k = 0; k < who.size(); k++) {
+      const size_t i = who[k];
+      const std::shared_ptr<Point>& p = candidates_[i];
+      const sdvlb_seed& s = batch[k];
+      seeds_[i] = s;
+      const bool was_fixed = p->IsFixed();
+      p->FromSeed(s);
+      switch (s.status) {
+        case SDVLB_SEED_DELETE_OLD: DeletePoint(p); erase[i] = 1; break;   // map.cc:433-436
+        case SDVLB_SEED_DELETE_FAILED: DeletePoint(p); break;              // map.cc:449-452: deleted, stays listed
+        case SDVLB_SEED_CONVERGED: erase[i] = 1; break;                    // map.cc:486-489: now a fixed point
+        case SDVLB_SEED_UPDATED: if (was_fixed) erase[i] = 1; break;       // HasConverged() of a fixed point
+        default: break;
+      }
     }
   }
+  std::vector<std::shared_ptr<Point>> kept;
+  for (size_t i = 0; i < n; i++)
+    if (!erase[i]) kept.push_back(candidates_[i]);
   candidates_.swap(kept);
+}
+
+static double Distance2D(const Eigen::Vector2d& a, const Eigen::Vector2d& b) {   // extra/utils.cc:222-226
+  const double d1 = a(0) - b(0), d2 = a(1) - b(1);
+  return std::sqrt(d1 * d1 + d2 * d2);
+}
+
+int Map::InitCandidates(const std::shared_ptr<Frame>& frame, const std::vector<std::shared_ptr<Frame>>& best_kfs,
+                        double depth_mean) {
+  if (best_kfs.empty()) return 0;
+  frame->FilterCorners();
+  std::vector<Eigen::Vector3i>& corners = frame->GetCorners();
+  std::vector<int>& fcorners = frame->GetFilteredCorners();
+  std::vector<char> imatches(fcorners.size(), 0);
+  sdvlb_seed_params sp;
+  sp.depth_mean = depth_mean;
+  sp.map_scale = 1.0;
+  sp.scale_min_dist = 0.25;
+  sp.min_kf_id = 0;
+  sp.mode = SDVLB_SEEDS_INIT;
+  double T_frame[7];
+  frame->GetPose().ToArray(T_frame);
+  int created = 0;
+  std::vector<sdvlb_seed> batch;
+  std::vector<size_t> who;
+  std::vector<std::shared_ptr<Feature>> feats;
+  for (const std::shared_ptr<Frame>& cframe : best_kfs) {
+    // pure rotation leads to wrong triangulation (map.cc:301-304)
+    const double distance = (frame->GetWorldPosition() - cframe->GetWorldPosition()).norm();
+    if (distance / depth_mean < 0.01) continue;
+    batch.clear(); who.clear(); feats.clear();
+    for (size_t count = 0; count < fcorners.size(); count++) {
+      if (imatches[count]) continue;
+      const Eigen::Vector3i corner = corners[fcorners[count]];
+      const int scale = 1 << corner(2);
+      auto feature = std::make_shared<Feature>(frame, Eigen::Vector2d(corner(0) * scale, corner(1) * scale), corner(2));
+      sdvlb_seed s;
+      std::memset(&s, 0, sizeof(s));
+      s.ref_frame = frame->Handle();
+      std::memcpy(s.ref_T, T_frame, sizeof(T_frame));
+      s.ref_px[0] = feature->GetPosition()(0); s.ref_px[1] = feature->GetPosition()(1);
+      for (int i = 0; i < 3; i++) s.ref_v[i] = feature->GetVector()(i);
+      s.rho = 1.0 / depth_mean;   // SearchPoint(cframe, feature, 1.0/depth_mean, 1.0, false, ...) (map.cc:320)
+      s.sigma2 = 1.0;
+      s.a = s.b = 10; s.z_range = 6; s.cos_alpha = 1.0; s.last_distance = depth_mean;
+      s.ref_level = corner(2);
+      batch.push_back(s);
+      who.push_back(count);
+      feats.push_back(feature);
+    }
+    double T_c[7];
+    cframe->GetPose().ToArray(T_c);
+    const int rc = sdvlb_update_candidates(cframe->Context(), cframe->Handle(), T_c, batch.data(), int(batch.size()), &sp);
+    if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_update_candidates failed: ") + sdvlb_last_error());
+    for (size_t k = 0; k < batch.size(); k++) {
+      const sdvlb_seed& s = batch[k];
+      if (s.status < SDVLB_SEED_NO_DEPTH) continue;   // SearchPoint failed
+      const Eigen::Vector2d imgpos(s.px[0], s.px[1]);
+      const std::shared_ptr<Feature>& feature = feats[k];
+      // compare to the 3D points seen from the selected keyframe (map.cc:324-345)
+      bool mfound = false;
+      for (auto& f2 : cframe->GetFeatures()) {
+        if (mfound) break;
+        if (!f2) continue;
+        std::shared_ptr<Point> point = f2->GetPoint();
+        if (!point || point->ToDelete()) continue;
+        if (Distance2D(imgpos, f2->GetPosition()) < 1.0) {
+          std::unique_lock<std::mutex> lock(mutex_map_);
+          feature->SetPoint(point);
+          frame->AddFeature(feature);
+          mfound = true;
+        }
+      }
+      if (mfound) continue;
+      if (s.status != SDVLB_SEED_UPDATED) continue;   // triangulation, parallax, minimum distance (map.cc:348-366)
+      auto candidate = std::make_shared<Point>();
+      auto feature2 = std::make_shared<Feature>(cframe, imgpos, s.level);
+      {
+        std::unique_lock<std::mutex> lock(mutex_map_);
+        candidate->InitCandidate(feature, s.depth);
+        frame->AddFeature(feature);
+        feature->SetPoint(candidate);
+        cframe->AddFeature(feature2);
+        feature2->SetPoint(candidate);
+      }
+      imatches[who[k]] = 1;
+      candidates_.push_back(candidate);   // map.cc:386
+      candidates_.push_back(candidate);   // map.cc:393: `fixed` is false, the reference lists the candidate again
+      created++;
+    }
+  }
+  return created;
+}
+
+int Map::AddConnectionsPoints(const std::shared_ptr<Frame>& frame, const std::vector<std::shared_ptr<Frame>>& best_kfs) {
+  if (best_kfs.empty()) return 0;
+  // points seen from the connected keyframes and not from this frame, in std::set<shared_ptr<Point>> order (map.cc:570-588)
+  std::set<std::shared_ptr<Point>> points;
+  for (const auto& kf : best_kfs)
+    for (auto& f : kf->GetFeatures()) {
+      if (!f) continue;
+      std::shared_ptr<Point> point = f->GetPoint();
+      if (!point || point->ToDelete()) continue;
+      bool seen = false;   // Point::SeenFrom(frame) (point.cc:178-184) through the frame's feature list
+      for (auto& ff : frame->GetFeatures())
+        if (ff && ff->GetPoint() == point) { seen = true; break; }
+      if (!seen) points.insert(point);
+    }
+  std::vector<std::shared_ptr<Point>> list;
+  std::vector<sdvlb_candidate> cands;
+  for (const auto& pt : points) {
+    std::shared_ptr<Feature> feature = pt->GetInitFeature();
+    if (!feature) continue;
+    sdvlb_candidate c;
+    std::memset(&c, 0, sizeof(c));
+    const std::shared_ptr<Frame> rf = feature->GetFrame();
+    c.ref_frame = rf->Handle();
+    rf->GetPose().ToArray(c.ref_T);
+    c.ref_px[0] = feature->GetPosition()(0); c.ref_px[1] = feature->GetPosition()(1);
+    for (int i = 0; i < 3; i++) c.ref_v[i] = feature->GetVector()(i);
+    c.idepth = pt->GetInverseDepth();
+    c.idepth_std = pt->GetStd();
+    const Eigen::Vector3d pos = pt->GetPosition();
+    for (int i = 0; i < 3; i++) c.pos[i] = pos(i);
+    c.ref_level = feature->GetLevel();
+    // Project + IsInsideImage(pos, PatchSize) (map.cc:597-602) run on the device (SDVLB_CAND_PROJECT)
+    c.flags = SDVLB_CAND_PROJECT | (pt->IsFixed() ? SDVLB_CAND_FIXED : 0);
+    cands.push_back(c);
+    list.push_back(pt);
+  }
+  std::vector<sdvlb_match> matches(cands.size());
+  double T[7];
+  frame->GetPose().ToArray(T);
+  const int rc = sdvlb_search_points(frame->Context(), frame->Handle(), cands.data(), int(cands.size()), T, matches.data());
+  if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_search_points failed: ") + sdvlb_last_error());
+  int linked = 0;
+  for (size_t i = 0; i < list.size(); i++) {
+    if (matches[i].status != SDVLB_MATCH_FOUND) continue;
+    std::unique_lock<std::mutex> lock(mutex_map_);
+    auto feature = std::make_shared<Feature>(frame, Eigen::Vector2d(matches[i].px[0], matches[i].px[1]), matches[i].level);
+    feature->SetPoint(list[i]);
+    frame->AddFeature(feature);
+    linked++;
+  }
+  return linked;
 }
 
 void Map::EmptyTrash() {

@@ -169,7 +169,15 @@ class Map {
   std::vector<std::shared_ptr<Point>>& GetCandidates() { return candidates_; }
   // depth_mean = frame->GetSceneDepth(); min_kf_id = last_kf_->GetKeyframeID() - 2 * Config::MaxSearchKeyframes()
   void UpdateCandidates(const std::shared_ptr<Frame>& frame, double depth_mean, int min_kf_id);
-  const std::vector<sdvlb_seed>& LastSeeds() const { return seeds_; }   // per-candidate outcome of the last pass
+  // per list entry of the last pass (status -1: the entry was not evaluated)
+  const std::vector<sdvlb_seed>& LastSeeds() const { return seeds_; }
+  // map.cc:262-395.  best_kfs = frame->GetBestConnections(Config::MaxSearchKeyframes()) (the keyframe graph is the
+  // caller's); depth_mean = frame->GetSceneDepth().  Returns the number of candidates created.
+  int InitCandidates(const std::shared_ptr<Frame>& frame, const std::vector<std::shared_ptr<Frame>>& best_kfs,
+                     double depth_mean);
+  // map.cc:560-617: points seen from the connected keyframes but not from `frame` are searched in it (one
+  // sdvlb_search_points batch) and linked when found.  Returns the number of links made.
+  int AddConnectionsPoints(const std::shared_ptr<Frame>& frame, const std::vector<std::shared_ptr<Frame>>& best_kfs);
  private:
   std::mutex mutex_map_;
   std::vector<std::shared_ptr<Point>> points_trash_;

@@ -798,6 +798,20 @@ void sdvlh_config_set(const sdvlb_params* p, const sdvlb_camera* cam) { sdvl::Co
 // FeatureAlign::SelectInliers / OptimizePose of the class-API path on the device (1) or on the host (0, default).
 void sdvlh_device_pose_refinement(int on) { sdvl::FeatureAlign::SetDevicePoseRefinement(on != 0); }
 
+// A context of its own for the test hooks below (the process-wide default context keeps the camera it was made with).
+struct HookContext {
+  sdvlb_ctx* ctx = nullptr;
+  HookContext() {
+    if (sdvlb_ctx_create(0, &sdvl::Config::Params(), &sdvl::Config::CameraParams(), &ctx))
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_create failed: ") + sdvlb_last_error());
+    sdvl::Device::SetCurrent(ctx);
+  }
+  ~HookContext() {
+    sdvl::Device::SetCurrent(nullptr);
+    sdvlb_ctx_destroy(ctx);
+  }
+};
+
 // Test hook for the class-level mapping pass: builds a keyframe with n candidate points (state taken from `seeds`),
 // runs Map::UpdateCandidates against each of the n_frames images (poses: n_frames x 7) and writes the candidates'
 // final state back into `seeds` (status = outcome of the last pass a candidate took part in).  *n_left = candidates
@@ -807,6 +821,7 @@ int sdvlh_map_update_candidates(const uint8_t* ref_img, const double ref_T[7], c
                                 double depth_mean, int min_kf_id, int* n_left) {
   try {
     using namespace sdvl;
+    HookContext hook_ctx;   // declared first: destroyed after every frame below
     Camera cam;
     cv::Mat rm(h, w, CV_8UC1, const_cast<uint8_t*>(ref_img));
     shared_ptr<Frame> ref = std::make_shared<Frame>(&cam, static_cast<ORBDetector*>(nullptr), rm, false);
@@ -833,20 +848,74 @@ int sdvlh_map_update_candidates(const uint8_t* ref_img, const double ref_T[7], c
       vector<shared_ptr<Point>> before = map.GetCandidates();
       map.UpdateCandidates(cur, depth_mean, min_kf_id);
       const vector<sdvlb_seed>& out = map.LastSeeds();
-      size_t j = 0;
       for (size_t c = 0; c < before.size(); c++) {
-        if (before[c]->ToDelete()) continue;
+        if (out[c].status < 0) continue;
         for (int i = 0; i < n; i++)
           if (pts[i] == before[c]) {
             const sdvlb_frame* keep = seeds[i].ref_frame;
-            seeds[i] = out[j];
+            seeds[i] = out[c];
             seeds[i].ref_frame = keep;
           }
-        j++;
       }
       map.EmptyTrash();
     }
     if (n_left) *n_left = int(map.GetCandidates().size());
+    return 0;
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return -1;
+  }
+}
+
+// Test hook for Map::InitCandidates + UpdateCandidates + AddConnectionsPoints of the host mirror.  A new keyframe
+// (img_new, T_new) is matched against an older keyframe (img_old, T_old): InitCandidates creates candidates;
+// UpdateCandidates then runs on every image of upd_imgs (poses upd_T, n_upd x 7); finally the points that converged
+// are searched in a last frame (img_last, T_last) through AddConnectionsPoints.
+// out[0] = candidates created, out[1] = list entries after InitCandidates, out[2] = entries left after the updates,
+// out[3] = points that became fixed, out[4] = links made by AddConnectionsPoints.  cand_px / cand_rho (cap entries):
+// position in the new keyframe and inverse depth of every created candidate after the updates.
+int sdvlh_map_init_candidates(const uint8_t* img_new, const double T_new[7], const uint8_t* img_old, const double T_old[7],
+                              const uint8_t* const* upd_imgs, const double* upd_T, int n_upd, const uint8_t* img_last,
+                              const double T_last[7], int w, int h, double depth_mean, int32_t out[5], double* cand_px,
+                              double* cand_rho, int32_t* cand_fixed, int cap) {
+  try {
+    using namespace sdvl;
+    HookContext hook_ctx;   // declared first: destroyed after every frame below
+    Camera cam;
+    auto mk = [&](const uint8_t* img, const double* T, bool corners) {
+      cv::Mat m(h, w, CV_8UC1, const_cast<uint8_t*>(img));
+      shared_ptr<Frame> f = std::make_shared<Frame>(&cam, static_cast<ORBDetector*>(nullptr), m, corners);
+      f->SetPose(SE3(T));
+      return f;
+    };
+    shared_ptr<Frame> kf_new = mk(img_new, T_new, true), kf_old = mk(img_old, T_old, true);
+    kf_new->SetKeyframe();
+    kf_old->SetKeyframe();
+    Map map;
+    out[0] = map.InitCandidates(kf_new, {kf_old}, depth_mean);
+    out[1] = int(map.GetCandidates().size());
+    vector<shared_ptr<Point>> created;
+    for (auto& p : map.GetCandidates())
+      if (created.empty() || created.back() != p) created.push_back(p);
+    for (int k = 0; k < n_upd; k++) {
+      shared_ptr<Frame> cur = mk(upd_imgs[k], upd_T + 7 * k, true);
+      map.UpdateCandidates(cur, depth_mean, -1000);
+      map.EmptyTrash();
+    }
+    out[2] = int(map.GetCandidates().size());
+    out[3] = 0;
+    for (size_t i = 0; i < created.size(); i++) {
+      if (created[i]->IsFixed()) out[3]++;
+      if (int(i) < cap) {
+        cand_px[2 * i] = created[i]->GetInitFeature()->GetPosition()(0);
+        cand_px[2 * i + 1] = created[i]->GetInitFeature()->GetPosition()(1);
+        cand_rho[i] = created[i]->GetInverseDepth();
+        cand_fixed[i] = created[i]->IsFixed() ? 1 : 0;
+      }
+    }
+    // keep only the fixed points on the keyframes, then look for them in the last frame
+    shared_ptr<Frame> last = mk(img_last, T_last, true);
+    out[4] = map.AddConnectionsPoints(last, {kf_new});
     return 0;
   } catch (const std::exception& e) {
     g_host_error = e.what();

@@ -170,3 +170,92 @@ def test_host_map_update_candidates_equals_c_abi(binding, sw, scenes, abi, O):
     assert np.array_equal(hs["n_failed"], s["n_failed"])
     print(f"host Map::UpdateCandidates: {len(s)} candidates, {n_left} left after {len(ks)} frames, "
           f"{(s['status'] == abi.SEED_CONVERGED).sum()} converged")
+
+
+def _init_seeds(cfg, abi, xyl, idx, T_new, handle, depth_mean):
+    s = np.zeros(len(idx), abi.SEED_DT)
+    cam = cfg["cam"]
+    c = xyl[idx].astype(np.float64)
+    px = c[:, :2] * (1 << xyl[idx, 2])[:, None]
+    v = np.stack([(px[:, 0] - cam.u0) / cam.fx, (px[:, 1] - cam.v0) / cam.fy, np.ones(len(idx))], axis=1)
+    v /= np.sqrt((v * v).sum(1))[:, None]
+    s["ref_frame"] = handle
+    s["ref_T"] = np.asarray(T_new)
+    s["ref_px"] = px
+    s["ref_v"] = v
+    s["rho"] = 1.0 / depth_mean
+    s["sigma2"] = 1.0
+    s["a"] = 10; s["b"] = 10; s["z_range"] = 6; s["cos_alpha"] = 1; s["last_distance"] = depth_mean
+    s["ref_level"] = xyl[idx, 2]
+    return s
+
+
+@pytest.mark.parametrize("name,seed", [("C2", 2), ("C3", 1)])
+def test_init_candidates_vs_oracle_and_host_map(binding, sw, scenes, abi, O, name, seed):
+    """The per-corner part of Map::InitCandidates (SDVLB_SEEDS_INIT) against the oracle, and the host mirror's
+    InitCandidates -> UpdateCandidates (every candidate listed twice, as the reference does) -> AddConnectionsPoints."""
+    cfg, poses, imgs = sw.sequence(name, seed, 28)
+    P, cam = cfg["params"], cfg["cam"]
+    k_old, k_new = 0, 9
+    ctx = binding.Context(P, cam)
+    try:
+        kf_new = ctx.frame(imgs[k_new], corners=True)
+        kf_old = ctx.frame(imgs[k_old], corners=True)
+        xyl, _ = kf_new.corners()
+        depth_mean = float(np.median(scenes.seed_points(cfg, xyl, poses[k_new])["depth"]))
+        idx = kf_new.filter_corners(np.zeros((0, 2)))
+        assert len(idx) > 150
+        s0 = _init_seeds(cfg, abi, xyl, idx, poses[k_new], kf_new.h, depth_mean)
+        got = ctx.update_candidates(kf_old, poses[k_old], s0, depth_mean, mode=abi.SEEDS_INIT)
+        so = s0.copy(); so["ref_frame"] = 0
+        exp = O.update_candidates(P, cam, imgs[k_old], poses[k_old], [imgs[k_new]], so, depth_mean, mode=abi.SEEDS_INIT)
+        assert np.array_equal(got["status"], exp["status"])
+        ok = exp["status"] == abi.SEED_UPDATED
+        found = exp["status"] >= abi.SEED_NO_DEPTH
+        assert ok.sum() > 50
+        assert np.array_equal(got["level"][found], exp["level"][found])
+        assert np.abs(got["px"][found] - exp["px"][found]).max() <= 0.01
+        np.testing.assert_allclose(got["depth"][ok], exp["depth"][ok], rtol=1e-4)
+        # nothing but status / depth / px / level is touched in this mode
+        for key in ("rho", "sigma2", "a", "b", "n_failed"):
+            assert np.array_equal(got[key], s0[key])
+        # triangulated depths are the plane's
+        true_depth = scenes.seed_points(cfg, xyl[idx][ok], poses[k_new], one_per_cell=False, margin=0)
+        print(f"{name}: {len(idx)} filtered corners, {found.sum()} found in the old keyframe, {ok.sum()} initialisable")
+
+        # host mirror: same candidates, then the depth filter on the following frames
+        ks = list(range(k_new + 3, 27, 3))
+        res = binding.host_map_init_candidates(P, cam, imgs[k_new], poses[k_new], imgs[k_old], poses[k_old],
+                                               [imgs[k] for k in ks], [poses[k] for k in ks], imgs[27], poses[27], depth_mean)
+        assert res["created"] == int(ok.sum()) and res["listed"] == 2 * res["created"]
+        np.testing.assert_allclose(res["px"], got["ref_px"][ok], rtol=0, atol=1e-9)
+        # replay of the reference's walk: every candidate is listed twice, so each frame updates it twice in a row
+        st = got[ok].copy()
+        st["rho"] = 1.0 / st["depth"]
+        st["last_distance"] = st["depth"]
+        fixed = np.zeros(len(st), bool)
+        alive = np.ones((len(st), 2), bool)          # the two list entries of every candidate
+        for k in ks:
+            cur = ctx.frame(imgs[k], corners=True)
+            n_entries = alive.sum(1)
+            first = np.where(alive[:, 0], 0, 1)       # which entry comes first in the list
+            for occ in range(2):
+                m = n_entries > occ                   # k-th occurrences form the k-th batch
+                entry = first if occ == 0 else np.ones(len(st), int)
+                was_fixed = fixed.copy()
+                st[m] = ctx.update_candidates(cur, poses[k], st[m], depth_mean)
+                conv = m & (st["status"] == abi.SEED_CONVERGED)
+                gone = conv | (m & was_fixed & (st["status"] == abi.SEED_UPDATED)) | (m & (st["status"] == abi.SEED_DELETE_OLD))
+                fixed |= conv
+                alive[np.where(gone)[0], entry[gone]] = False
+            cur.destroy()
+        listed = alive.sum(1)
+        assert res["fixed"] == int(fixed.sum())
+        assert res["left"] == int(listed.sum())
+        np.testing.assert_allclose(res["rho"], st["rho"], rtol=1e-9)
+        assert res["linked"] > 0.5 * res["fixed"]
+        print(f"{name}: host Map created {res['created']} candidates, {res['fixed']} converged, {res['left']} entries left, "
+              f"{res['linked']} linked into the last frame")
+        kf_new.destroy(); kf_old.destroy()
+    finally:
+        ctx.close()
