@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
                                                                   const int32_t* __restrict__ cell_cnt,
                                                                   uint32_t* __restrict__ level_kp,
                                                                   int32_t* __restrict__ level_cnt,
-                                                                  int32_t* __restrict__ frame_ticket) {
-  extern __shared__ int s_dyn[];   // nleft[ncells], nsel[ncells], kept_off[ncells+1]
+                                                                  int32_t* __restrict__ frame_ticket, int pool_keys) {
+  extern __shared__ int s_dyn[];   // nleft[ncells], nsel[ncells], kept_off[ncells+1], then the per-cell selection pool
   __shared__ int s_tmp[SEL_THREADS / 32];
   __shared__ uint32_t s_keys[SEL_SMEM_KEYS];
   __shared__ int s_final, s_ticket;
@@ -310,12 +310,39 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   }
   __syncthreads();
 
-  // ---- per-cell retainBest (fast_detector.cc:138-140), in place in the cell scratch
-  for (int c = tid; c < ncells; c += SEL_THREADS) {
-    const int n = cell_cnt[cbase + c];
-    int kept = 0;
-    if (n > 0) kept = sdvlb_sel::retain_best<10>(cell_kp + size_t(cbase + c) * SDVLB_CELL_CAP, n, nsel[c]);
-    nleft[c] = kept;   // reuse as kept count
+  // ---- per-cell retainBest (fast_detector.cc:138-140).  The selection replays libstdc++'s nth_element / partition
+  // (the ORDER of the survivors is part of the contract), a chain of dependent accesses one thread long: each thread
+  // pulls its cell's keypoints into a shared-memory pool first, so the chain runs at shared-memory latency instead
+  // of L2 latency (cells that do not fit in the pool are processed in place).
+  uint32_t* const pool = reinterpret_cast<uint32_t*>(s_dyn + 3 * ncells + 4);
+  for (int c0 = 0; c0 < ncells; c0 += SEL_THREADS) {
+    const int c = c0 + tid;
+    const int n = c < ncells ? max(cell_cnt[cbase + c], 0) : 0;
+    // exclusive scan of n over the CTA
+    const int lane = tid & 31, warp = tid >> 5;
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    __syncthreads();   // s_tmp and the pool are free again
+    if (lane == 31) s_tmp[warp] = incl;
+    __syncthreads();
+    int off = incl - n;
+    for (int w = 0; w < warp; w++) off += s_tmp[w];
+    if (c < ncells) {
+      uint32_t* const g = cell_kp + size_t(cbase + c) * SDVLB_CELL_CAP;
+      const bool in_pool = off + n <= pool_keys;
+      uint32_t* const wk = in_pool ? pool + off : g;
+      if (in_pool)
+        for (int i = 0; i < n; i++) wk[i] = g[i];
+      int kept = 0;
+      if (n > 0) kept = sdvlb_sel::retain_best<10>(wk, n, nsel[c]);
+      if (in_pool)
+        for (int i = 0; i < kept; i++) g[i] = wk[i];
+      nleft[c] = kept;   // reuse as kept count
+    }
   }
   __syncthreads();
 
@@ -496,8 +523,17 @@ cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, 
                                      cudaStream_t stream) {
   const FastArgs& A = plan.args;
   dim3 g2(A.n_fast_levels, B.n);
-  const size_t dyn = size_t(3 * plan.max_cells_level + 1) * sizeof(int);
+  const int pool_keys = 12288;   // 48 KB: 256 cells x 48 keypoints on average after NMS
+  const size_t dyn = size_t(3 * plan.max_cells_level + 4 + pool_keys) * sizeof(int);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(fast_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (dyn > 160 * 1024) return cudaErrorInvalidValue;
   sdvlb_common_carveout(fast_select_kernel);
-  fast_select_kernel<<<g2, SEL_THREADS, dyn, stream>>>(B, A, cell_kp, cell_cnt, level_kp, level_cnt, frame_ticket);
+  fast_select_kernel<<<g2, SEL_THREADS, dyn, stream>>>(B, A, cell_kp, cell_cnt, level_kp, level_cnt, frame_ticket,
+                                                      pool_keys);
   return cudaGetLastError();
 }
