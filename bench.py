@@ -52,6 +52,37 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_h_ncu_full.txt")   # summary of the committed `ncu --set full` capture
+NCU_KERNELS = {"pyr_down_kernel": "pyramid", "pyr_tail_kernel": "pyramid", "fast_cells_kernel": "fast",
+               "fast_select_kernel": "select", "image_align_kernel": "align", "search_seq_kernel": "search",
+               "seq_prep_kernel": "prep", "seq_post_kernel": "pose"}
+NCU_SEQS_PER_LAUNCH = 64
+
+
+def ncu_traffic_per_launch(kernel, seqs):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` (bench key) from the ncu capture under
+    profiles/ (64 sequences per launch; scaled to `seqs`).  A key made of several launches per step (pyramid) is the
+    sum of their per-launch averages.  None when the summary is not there."""
+    if not os.path.exists(NCU_SUMMARY):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    cur = None
+    with open(NCU_SUMMARY) as f:
+        for line in f:
+            if line.startswith("## "):
+                name, grid = line[3:].split()[0], line[line.index("grid"):].strip()
+                cur = (name, grid) if NCU_KERNELS.get(name) == kernel else None
+                if cur:
+                    per.setdefault(cur, []).append(0.0)
+            elif cur and line.strip().startswith(("dram read", "dram write")):
+                parts = line.split()
+                per[cur][-1] += float(parts[2]) * unit.get(parts[3], 1.0)
+    if not per:
+        return None
+    return sum(sum(v) / len(v) for v in per.values()) * seqs / NCU_SEQS_PER_LAUNCH
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
 
@@ -399,7 +430,9 @@ def main():
     avg_ms = ktimes[dom][0] / n_launch
     achieved = (alg / n_launch) / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                "frac": achieved / peak, "traffic": ncu_traffic_per_launch(dom, S),
+                "traffic_source": "profiles/r01_h_ncu_full.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+                "peak_source": peak_kind,
                 "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes_per_launch": alg / n_launch,
                 "kernel_ms_share": {k: (v / tot_ms if tot_ms else 0.0) for k, v in kshare.items()},
                 "kernel_us_per_step": {k: v[0] * 1e3 / K for k, v in ktimes.items()}}
