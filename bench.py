@@ -52,7 +52,7 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_h_ncu_full.txt")   # summary of the committed `ncu --set full` capture
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_i_ncu_full.txt")   # summary of the committed `ncu --set full` capture
 NCU_KERNELS = {"pyr_down_kernel": "pyramid", "pyr_tail_kernel": "pyramid", "fast_cells_kernel": "fast",
                "fast_select_kernel": "select", "image_align_kernel": "align", "search_seq_kernel": "search",
                "seq_prep_kernel": "prep", "seq_post_kernel": "pose"}
@@ -290,9 +290,10 @@ def main():
     if args.host_replay:     # the host replays FeatureAlign: every core is needed
         threads = args.threads or max(1, min(S, cores))
         groups = args.groups or max(1, min(S, 2 * threads))
-    else:                    # resident sequences: the host only submits; a few threads keep 8 groups in flight
-        threads = args.threads or max(1, min(4, cores))
-        groups = args.groups or max(1, min(S, 8))
+    else:                    # resident sequences: the host only submits; 3 threads keep 6 groups in flight (measured on
+        # B200: 6x3 173 k frames/s, 8x4 172 k, 4x2 164 k; on the 8-GPU box, 4 cores per rank: 6x3 1.28 M, 8x3 1.14 M)
+        threads = args.threads or max(1, min(3, cores))
+        groups = args.groups or max(1, min(S, 6))
 
     # ---- synthetic frames, rendered once into pinned host memory
     host = torch.empty((S, F, h, w), dtype=torch.uint8).pin_memory()
@@ -431,7 +432,7 @@ def main():
     achieved = (alg / n_launch) / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic_per_launch(dom, S),
-                "traffic_source": "profiles/r01_h_ncu_full.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic_source": "profiles/r01_i_ncu_full.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
                 "peak_source": peak_kind,
                 "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes_per_launch": alg / n_launch,
                 "kernel_ms_share": {k: (v / tot_ms if tot_ms else 0.0) for k, v in kshare.items()},
