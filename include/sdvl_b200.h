@@ -120,6 +120,17 @@ int sdvlb_timing_read(sdvlb_ctx* ctx, double ms[SDVLB_K_COUNT], int64_t launches
 /* Counters since the last reset: kernels launched by this context, bytes copied host->device and device->host. */
 int sdvlb_ctx_counters(sdvlb_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes, int reset);
 
+/* ---- input pre-processing: Camera::UndistortImage ----
+ * Camera::SetDistortions (camera.cc:38-67): d = (k1, k2, p1, p2, k3), the five cv::undistort coefficients the
+ * reference reads from Camera.d1..d5; all zero switches distortion off (camera.cc:45-48).  When set, every level-0
+ * image handed to sdvlb_frame_create / sdvlb_frames_submit / sdvlb_track_batch is first undistorted on the device,
+ * as main.cc:133 does before SDVL::HandleFrame -- bit-exact with cv::undistort(in, out, K, D) (OpenCV 4.13:
+ * initUndistortRectifyMap CV_16SC2 + remap INTER_LINEAR, BORDER_CONSTANT). */
+int sdvlb_ctx_set_distortion(sdvlb_ctx* ctx, const double d[5]);
+/* Camera::UndistortImage(in, out) (camera.cc:100-105) on its own: w*h u8 host buffers of the context's camera size.
+ * With distortion off it copies, as the reference does. */
+int sdvlb_undistort(sdvlb_ctx* ctx, const uint8_t* in, uint8_t* out);
+
 /* ---- Frame -------------------------------------------------------------- */
 /* Frame::Frame(camera, detector, img, corners): uploads `img` (u8, `stride`
  * bytes per row), builds the pyramid on the device, optionally runs FAST with

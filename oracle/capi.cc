@@ -53,6 +53,16 @@ int orc_retain_best(float* xyr, int n, int keep) {
   return int(k.size());
 }
 
+// Camera::UndistortImage
+int orc_undistort(const sdvlb_camera* cam_, const double d[5], const uint8_t* img, int w, int h, uint8_t* out) {
+  const Camera cam = CamFrom(cam_);
+  Mat8 in(w, h), o;
+  std::memcpy(in.data.data(), img, size_t(w) * h);
+  UndistortImage(cam, d, in, &o);
+  std::memcpy(out, o.data.data(), size_t(w) * h);
+  return 0;
+}
+
 // Frame(img, corners=true) then GetCorners(): returns the number of corners.
 int orc_detect(const sdvlb_params* P, const uint8_t* img, int w, int h, int nfeatures, int32_t* xyl, int32_t* score,
                int cap) {

@@ -318,3 +318,41 @@ void FilterCorners(const sdvlb_params& P, const std::vector<Mat8>& pyr, const st
 }
 
 }  // namespace oracle
+
+namespace oracle {
+
+// cv::undistort as Camera::UndistortImage calls it (camera.cc:100-105; main.cc:133 is the call site).  OpenCV builds a
+// fixed-point map per destination pixel (initUndistortRectifyMap, m1type CV_16SC2: integer source pixel + 5-bit
+// fractions, INTER_TAB_SIZE 32) and resamples with cv::remap's fixed-point bilinear kernel: weights
+// (32-fx)(32-fy)*32 ... with 15 fractional bits (INTER_REMAP_COEF_SCALE 32768; exact products, so the table's
+// normalisation step never fires), result (sum + 2^14) >> 15, taps outside the image read the border value 0.
+void UndistortImage(const Camera& cam, const double d[5], const Mat8& in, Mat8* out) {
+  const int w = in.cols, h = in.rows;
+  *out = Mat8(w, h);
+  const double k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4];
+  const double ir0 = 1.0 / cam.fx, ir2 = -cam.u0 / cam.fx, ir4 = 1.0 / cam.fy, ir5 = -cam.v0 / cam.fy;   // (K)^-1
+  for (int i = 0; i < h; i++) {
+    const double y = i * ir4 + ir5;
+    uint8_t* dst = out->data.data() + size_t(i) * w;
+    for (int j = 0; j < w; j++) {
+      const double x = j * ir0 + ir2;
+      const double x2 = x * x, y2 = y * y;
+      const double r2 = x2 + y2, _2xy = 2 * x * y;
+      const double kr = (1 + ((k3 * r2 + k2) * r2 + k1) * r2) / (1 + ((0 * r2 + 0) * r2 + 0) * r2);
+      const double xd = (x * kr + p1 * _2xy + p2 * (r2 + 2 * x2));
+      const double yd = (y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy);
+      const double u = cam.fx * xd + cam.u0, v = cam.fy * yd + cam.v0;
+      const int iu = int(std::nearbyint(u * 32)), iv = int(std::nearbyint(v * 32));   // saturate_cast<int> = cvRound
+      const int sx = int16_t(iu >> 5), sy = int16_t(iv >> 5);                         // stored as short
+      const int fx = iu & 31, fy = iv & 31;
+      const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+      auto tap = [&](int yy, int xx) -> int {
+        return (xx >= 0 && xx < w && yy >= 0 && yy < h) ? int(in.ptr(yy)[xx]) : 0;
+      };
+      const int acc = tap(sy, sx) * w00 + tap(sy, sx + 1) * w01 + tap(sy + 1, sx) * w10 + tap(sy + 1, sx + 1) * w11;
+      dst[j] = uint8_t((acc + (1 << 14)) >> 15);
+    }
+  }
+}
+
+}  // namespace oracle

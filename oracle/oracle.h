@@ -113,6 +113,11 @@ double FindShiTomasiScoreAtPoint(const Mat8& img, int px, int py);
 void FilterCorners(const sdvlb_params& P, const std::vector<Mat8>& pyr, const std::vector<Corner>& corners,
                    const std::vector<V2>& locked, int min_feature_score, std::vector<int>* indices);
 
+// Camera::UndistortImage (camera.cc:100-105) = cv::undistort(in, out, K, D) with D = (k1, k2, p1, p2, k3)
+// (camera.cc:38-67), i.e. cv::initUndistortRectifyMap(K, D, I, K, size, CV_16SC2) + cv::remap(INTER_LINEAR,
+// BORDER_CONSTANT 0).  Pinned bit-exactly against OpenCV 4.13 (tests/golden, tests/test_oracle_cpu.py).
+void UndistortImage(const Camera& cam, const double d[5], const Mat8& in, Mat8* out);
+
 // ---------------------------------------------------------------- utils (extra/utils.cc)
 double AbsMax6(const Vec6 v);                              // utils.cc:28-42
 float Interpolate8U(const Mat8& m, float u, float v);      // utils.cc:44-59

@@ -135,6 +135,17 @@ def update_candidates(params, cam, cur_img, T_cur, ref_imgs, seeds, depth_mean, 
     return seeds
 
 
+def undistort(cam, dist, img):
+    """Oracle Camera::UndistortImage (cv::undistort with D = (k1, k2, p1, p2, k3))."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    d = np.ascontiguousarray(dist, np.float64)
+    assert d.shape == (5,)
+    out = np.zeros_like(img)
+    lib().orc_undistort(C.byref(cam), ptr(d), ptr(img), w, h, ptr(out))
+    return out
+
+
 def filter_corners(params, img, nfeatures, locked, min_feature_score=50):
     """Oracle Frame::FilterCorners: indices into the frame's corner list, one per free cell."""
     img = np.ascontiguousarray(img, np.uint8)

@@ -68,6 +68,7 @@ EXPORTS = [
     "sdvlb_rand_seed", "sdvlb_rand_next", "sdvlb_rand_shuffle", "sdvlb_select_inliers", "sdvlb_optimize_pose",
     "sdvlb_seq_create", "sdvlb_seq_destroy", "sdvlb_seq_reset", "sdvlb_seq_add_points", "sdvlb_seq_track_submit",
     "sdvlb_seq_track_poll", "sdvlb_seq_track_collect", "sdvlb_frame_filter_corners", "sdvlb_update_candidates",
+    "sdvlb_ctx_set_distortion", "sdvlb_undistort",
 ]
 
 
@@ -173,6 +174,20 @@ class Context:
             Tp = ptr(T_cur)
         _check(load().sdvlb_search_points(C.c_void_p(self.h), C.c_void_p(cur.h), ptr(cands), cands.shape[0], Tp,
                                           ptr(out)))
+        return out
+
+    def set_distortion(self, d):
+        """Camera::SetDistortions: d = (k1, k2, p1, p2, k3); zeros switch the undistortion of incoming images off."""
+        d = np.ascontiguousarray(d, np.float64)
+        assert d.shape == (5,)
+        _check(load().sdvlb_ctx_set_distortion(C.c_void_p(self.h), ptr(d)))
+
+    def undistort(self, img):
+        """Camera::UndistortImage on the device (host image in, host image out)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        assert img.shape == (self.hh, self.w)
+        out = np.zeros_like(img)
+        _check(load().sdvlb_undistort(C.c_void_p(self.h), ptr(img), ptr(out)))
         return out
 
     def update_candidates(self, cur, T_cur, seeds, depth_mean, min_kf_id=-1000, map_scale=1.0, scale_min_dist=0.25,

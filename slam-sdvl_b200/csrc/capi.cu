@@ -19,6 +19,7 @@
 
 // ---- kernel launchers (other translation units)
 cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, cudaStream_t stream);
+cudaError_t sdvlb_launch_undistort(const FrameBatch& B, const ImageBatch& raw, const UndistortArgs& U, cudaStream_t stream);
 cudaError_t sdvlb_launch_seed_update(sdvlb_seed* d_seeds, int n, const FrameDev& cur, const PyrGeom& g,
                                      const DevParams& dp, const sdvlb_seed_params& sp, cudaStream_t stream);
 cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStream_t stream);
@@ -81,8 +82,6 @@ int ensure_fast_scratch(sdvlb_ctx* c, int n_frames) {
   SDVLB_CUDA_TRY(cudaStreamSynchronize(c->bstream));
   SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
   const int nf = std::max(n_frames, c->fast_frames * 2);
-  if (c->d_seeds) cudaFree(c->d_seeds);
-  if (c->h_seeds) cudaFreeHost(c->h_seeds);
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt); cudaFree(c->frame_ticket);
   c->cell_kp = nullptr; c->cell_cnt = nullptr; c->level_kp = nullptr; c->level_cnt = nullptr; c->frame_ticket = nullptr;
   c->fast_frames = 0;
@@ -303,16 +302,44 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
       f->build_corners = want_corners;
       f->build_mirror = want_corners && mirror;
     }
+    // Camera::UndistortImage: the raw images go to a scratch set, the undistortion kernel fills level 0
+    FrameBatch Bup = B;
+    ImageBatch Iraw;
+    int raw_set = -1;
+    if (c->has_dist) {
+      if (!c->raw_scratch) {
+        c->raw_stride = (img_bytes + 255) & ~size_t(255);
+        SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->raw_scratch), c->raw_stride * SDVLB_BATCH_MAX * kBuildEvents));
+        for (int i = 0; i < kBuildEvents; i++)
+          SDVLB_CUDA_TRY(cudaEventCreateWithFlags(&c->raw_done[i], cudaEventDisableTiming));
+      }
+      raw_set = c->raw_next;
+      c->raw_next = (c->raw_next + 1) % kBuildEvents;
+      if (c->raw_used[raw_set]) SDVLB_CUDA_TRY(cudaStreamWaitEvent(ustream, c->raw_done[raw_set], 0));
+      for (int i = 0; i < m; i++) {
+        uint8_t* slot = c->raw_scratch + (size_t(raw_set) * SDVLB_BATCH_MAX + i) * c->raw_stride;
+        Bup.f[i].pyr = slot;
+        Iraw.src[i] = slot;
+      }
+    }
     // launch + event record are one unit on the shared upload stream
     std::unique_lock<std::mutex> ulock;
     if (ustream != stream && c->umutex) ulock = std::unique_lock<std::mutex>(*c->umutex);
     if (by_kernel) {
-      SDVLB_CUDA_TRY(sdvlb_launch_upload(B, I, int(img_bytes), ustream));
+      SDVLB_CUDA_TRY(sdvlb_launch_upload(Bup, I, int(img_bytes), ustream));
       c->n_launches += 1;
     } else {
+      // copy engine into level 0 of the frame slots; with distortion set the raw pixels then move on to the scratch
+      // set through the device-to-device path of the upload kernel (level 0 is rewritten by the undistortion)
       for (int i = 0; i < m; i++)
         SDVLB_CUDA_TRY(cudaMemcpyAsync(B.f[i].pyr, I.src[i], img_bytes,
                                        image_loc[base + i] == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ustream));
+      if (c->has_dist) {
+        ImageBatch I2;
+        for (int i = 0; i < m; i++) I2.src[i] = B.f[i].pyr;
+        SDVLB_CUDA_TRY(sdvlb_launch_upload(Bup, I2, int(img_bytes), ustream));
+        c->n_launches += 1;
+      }
     }
     if (ustream != stream) {
       cudaEvent_t ev = c->uevents[c->uevent_next];
@@ -323,6 +350,12 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
     }
     for (int i = 0; i < m; i++)
       if (image_loc[base + i] != 1) c->h2d_bytes += int64_t(img_bytes);
+    if (c->has_dist) {
+      SDVLB_CUDA_TRY(sdvlb_launch_undistort(B, Iraw, c->und, stream));
+      SDVLB_CUDA_TRY(cudaEventRecord(c->raw_done[raw_set], stream));
+      c->raw_used[raw_set] = true;
+      c->n_launches += 1;
+    }
     timer_begin(c, SDVLB_K_PYRAMID, stream);
     SDVLB_CUDA_TRY(sdvlb_launch_pyramid(B, c->geom, stream));
     timer_end(c);
@@ -693,6 +726,8 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   if (c->ustream) cudaStreamSynchronize(c->ustream);   // shared by the contexts of the device: never destroyed
   if (c->d_seeds) cudaFree(c->d_seeds);
   if (c->h_seeds) cudaFreeHost(c->h_seeds);
+  if (c->raw_scratch) cudaFree(c->raw_scratch);
+  for (int i = 0; i < kBuildEvents; i++) if (c->raw_done[i]) cudaEventDestroy(c->raw_done[i]);
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
   cudaFree(c->frame_ticket); cudaFree(c->scratch);
   if (c->h_overflow) cudaFreeHost(c->h_overflow);
@@ -1003,6 +1038,38 @@ int sdvlb_search_points(sdvlb_ctx* ctx, const sdvlb_frame* cur, const sdvlb_cand
     SDVLB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   }
   return run_batch(ctx, &j, 1, 0, nullptr, 0, nullptr, nullptr, false);
+}
+
+int sdvlb_ctx_set_distortion(sdvlb_ctx* c, const double d[5]) {
+  if (!c || !d) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  c->has_dist = !(d[0] == 0.0 && d[1] == 0.0 && d[2] == 0.0 && d[3] == 0.0 && d[4] == 0.0);
+  c->und.w = c->w; c->und.h = c->h;
+  c->und.fx = c->cam.fx; c->und.fy = c->cam.fy; c->und.u0 = c->cam.u0; c->und.v0 = c->cam.v0;
+  c->und.k1 = d[0]; c->und.k2 = d[1]; c->und.p1 = d[2]; c->und.p2 = d[3]; c->und.k3 = d[4];
+  return 0;
+}
+
+// Camera::UndistortImage(in, out) (camera.cc:100-105): a frame slot is borrowed for the result
+int sdvlb_undistort(sdvlb_ctx* c, const uint8_t* in, uint8_t* out) {
+  if (!c || !in || !out) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  const size_t bytes = size_t(c->w) * c->h;
+  if (!c->has_dist) { memmove(out, in, bytes); return 0; }
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  sdvlb_frame* f = nullptr;
+  int rc = frame_alloc(c, &f);
+  if (rc) return rc;
+  const int32_t loc = SDVLB_IMG_HOST;
+  const uint8_t* img = in;
+  // upload + undistortion only: no corners, and the pyramid levels built behind it are simply not read
+  rc = enqueue_build(c, &f, &img, &loc, 1, false, 0, false, c->stream);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(out, f->dev.pyr, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = sdvlb_set_cuda_error(e, "undistort", __FILE__, __LINE__);
+    c->d2h_bytes += int64_t(bytes);
+  }
+  frame_release(c, f);
+  return rc;
 }
 
 // Map::UpdateCandidates (map.cc:397-498) for n seeds against `cur`: one upload, one kernel, one read-back.

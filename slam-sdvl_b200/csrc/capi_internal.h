@@ -82,6 +82,15 @@ struct sdvlb_ctx {
   cudaStream_t ustream = nullptr;   // upload stream (shared by the contexts of the device): level 0 of asynchronous
                                     // frame batches (PCIe), ahead of bstream
   std::mutex* umutex = nullptr;     // serialises launch + event record on the shared stream
+  // Camera::UndistortImage: raw (distorted) level-0 images land in a ring of scratch sets, one per frame batch in
+  // flight, and the undistortion kernel writes level 0 of the frame slots
+  bool has_dist = false;
+  UndistortArgs und = {};
+  uint8_t* raw_scratch = nullptr;   // kBuildEvents sets x SDVLB_BATCH_MAX images
+  size_t raw_stride = 0;            // bytes per image slot
+  int raw_next = 0;
+  cudaEvent_t raw_done[kBuildEvents] = {};
+  bool raw_used[kBuildEvents] = {};
   sdvlb_seed* d_seeds = nullptr;    // sdvlb_update_candidates staging (device + pinned host), grown on demand
   sdvlb_seed* h_seeds = nullptr;
   int seeds_cap = 0;

@@ -57,6 +57,11 @@ struct ImageBatch {    // level-0 sources of a frame batch (device-visible pinne
   const uint8_t* src[SDVLB_BATCH_MAX];
 };
 
+struct UndistortArgs {   // cv::undistort with K = (fx, fy, u0, v0), D = (k1, k2, p1, p2, k3)
+  int w, h;
+  double fx, fy, u0, v0, k1, k2, p1, p2, k3;
+};
+
 struct DevParams {
   sdvlb_params p;
   sdvlb_camera cam;

@@ -265,6 +265,58 @@ __global__ void __launch_bounds__(32) upload_bulk_kernel(const __grid_constant__
   }
 }
 
+// Camera::UndistortImage = cv::undistort (camera.cc:100-105): per destination pixel the fixed-point map of
+// cv::initUndistortRectifyMap (m1type CV_16SC2: source pixel + 5-bit fractions) and cv::remap's fixed-point bilinear
+// kernel (weights with 15 fractional bits, taps outside the image are 0).  Four destination pixels per thread, one
+// 32-bit store; the taps are byte gathers from the raw image (L1/L2: neighbouring pixels share their sources).
+__global__ void __launch_bounds__(256) undistort_kernel(const __grid_constant__ FrameBatch B,
+                                                        const __grid_constant__ ImageBatch R,
+                                                        const __grid_constant__ UndistortArgs U) {
+  const uint8_t* __restrict__ src = R.src[blockIdx.y];
+  uint8_t* __restrict__ dst = B.f[blockIdx.y].pyr;
+  const int w = U.w, h = U.h;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;   // group of four pixels; rows are multiples of 4 wide or padded
+  const int gpr = (w + 3) >> 2;
+  if (q >= gpr * h) return;
+  const int i = q / gpr, j0 = (q - i * gpr) * 4;
+  const double ir0 = 1.0 / U.fx, ir2 = -U.u0 / U.fx, ir4 = 1.0 / U.fy, ir5 = -U.v0 / U.fy;
+  const double y = i * ir4 + ir5;
+  uint32_t packed = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int j = j0 + k;
+    const double x = j * ir0 + ir2;
+    const double x2 = x * x, y2 = y * y;
+    const double r2 = x2 + y2, _2xy = 2 * x * y;
+    const double kr = 1 + ((U.k3 * r2 + U.k2) * r2 + U.k1) * r2;   // the rational part k4..k6 is not used by SDVL
+    const double xd = x * kr + U.p1 * _2xy + U.p2 * (r2 + 2 * x2);
+    const double yd = y * kr + U.p1 * (r2 + 2 * y2) + U.p2 * _2xy;
+    const double u = U.fx * xd + U.u0, v = U.fy * yd + U.v0;
+    const int iu = __double2int_rn(u * 32), iv = __double2int_rn(v * 32);   // saturate_cast<int>(x) = cvRound(x)
+    const int sx = int(short(iu >> 5)), sy = int(short(iv >> 5));          // the map stores them as short
+    const int fx = iu & 31, fy = iv & 31;
+    int acc = 0;
+    if (sx >= 0 && sy >= 0 && sx + 1 < w && sy + 1 < h) {
+      const uint8_t* p = src + size_t(sy) * w + sx;
+      acc = int(__ldg(p)) * ((32 - fx) * (32 - fy)) + int(__ldg(p + 1)) * (fx * (32 - fy)) +
+            int(__ldg(p + w)) * ((32 - fx) * fy) + int(__ldg(p + w + 1)) * (fx * fy);
+    } else {
+      auto tap = [&](int yy, int xx) -> int {
+        return (xx >= 0 && xx < w && yy >= 0 && yy < h) ? int(__ldg(src + size_t(yy) * w + xx)) : 0;
+      };
+      acc = tap(sy, sx) * ((32 - fx) * (32 - fy)) + tap(sy, sx + 1) * (fx * (32 - fy)) +
+            tap(sy + 1, sx) * ((32 - fx) * fy) + tap(sy + 1, sx + 1) * (fx * fy);
+    }
+    // weights carry a factor 32 (2^15 scale): (acc * 32 + 2^14) >> 15 == (acc + 2^9) >> 10
+    const uint32_t px = uint32_t((acc + (1 << 9)) >> 10);
+    if (j < w) packed |= px << (8 * k);
+  }
+  uint8_t* o = dst + size_t(i) * w + j0;
+  if (j0 + 3 < w && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) *reinterpret_cast<uint32_t*>(o) = packed;
+  else
+    for (int k = 0; k < 4 && j0 + k < w; k++) o[k] = uint8_t(packed >> (8 * k));
+}
+
 // The level the tail kernel starts from: the first one that fits in shared memory together with its successor
 // (-1: none, every level is produced by pyr_down_kernel).
 int tail_source_level(const PyrGeom& g, size_t* smem_bytes) {
@@ -306,6 +358,14 @@ cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int by
     sdvlb_common_carveout(upload_kernel);
     upload_kernel<<<grid, 256, 0, stream>>>(B, I, bytes);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t sdvlb_launch_undistort(const FrameBatch& B, const ImageBatch& raw, const UndistortArgs& U, cudaStream_t stream) {
+  const int groups = ((U.w + 3) >> 2) * U.h;
+  dim3 grid((groups + 255) / 256, B.n);
+  sdvlb_common_carveout(undistort_kernel);
+  undistort_kernel<<<grid, 256, 0, stream>>>(B, raw, U);
   return cudaGetLastError();
 }
 

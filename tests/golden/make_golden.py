@@ -1,5 +1,6 @@
 """Generates tests/golden/cv2_golden.npz from OpenCV (cv2 4.13 in this image): the third-party arithmetic the
-reference calls on this path (cv::pyrDown at frame.cc:119, cv::FAST at extra/fast_detector.cc:95).
+reference calls on this path (cv::pyrDown at frame.cc:119, cv::FAST at extra/fast_detector.cc:95, cv::undistort at
+camera.cc:102).
 Run from the repo root:  python tests/golden/make_golden.py"""
 import os
 import sys
@@ -45,5 +46,18 @@ for k, (src, x0, y0, cw, ch) in enumerate(picked + [(blur, 0, 0, 32, 32), (blur,
     out[f"fast_roi_{k}"] = roi
     out[f"fast_kps_{k}"] = arr
 out["n_rois"] = np.array(6)
+# --- cv::undistort (Camera::UndistortImage, camera.cc:100-105): EuRoC cam0 coefficients on a crop-sized camera, and a
+# strongly distorted small camera whose corners map outside the source (BORDER_CONSTANT)
+und_cases = [("euroc", 188, 120, 114.66, 114.32, 91.8, 62.1, (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0)),
+             ("strong", 135, 67, 90.0, 85.0, 70.3, 31.9, (-0.45, 0.21, 0.004, -0.003, -0.05)),
+             ("barrel", 96, 96, 80.0, 80.0, 47.5, 47.5, (0.35, -0.2, -0.002, 0.001, 0.3))]
+for name, w, h, fx, fy, u0, v0, D in und_cases:
+    src = cv2.GaussianBlur(rng.integers(0, 256, (h, w), dtype=np.uint8), (0, 0), 1.2)
+    K = np.array([[fx, 0, u0], [0, fy, v0], [0, 0, 1.0]])
+    out[f"und_{name}_src"] = src
+    out[f"und_{name}_cam"] = np.array([w, h, fx, fy, u0, v0])
+    out[f"und_{name}_D"] = np.array(D)
+    out[f"und_{name}_dst"] = cv2.undistort(src, K, np.array(D))
+out["und_names"] = np.array([c[0] for c in und_cases])
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cv2_golden.npz"), **out)
 print("written", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})

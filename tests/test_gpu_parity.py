@@ -230,3 +230,68 @@ def test_filter_corners_bit_exact(binding, sw, O, name, seed, n_locked):
     assert np.array_equal(got, ref)
     f.destroy()
     ctx.close()
+
+
+# ------------------------------------------------------------------ Camera::UndistortImage
+EUROC_D = (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0)
+TUM1_D = (0.2624, -0.9531, -0.0054, 0.0026, 1.1633)
+
+
+@pytest.mark.parametrize("name,seed,D", [("C2", 0, EUROC_D), ("C1", 3, TUM1_D), ("C5", 1, (-0.2, 0.05, 0.001, -0.0005, 0.0))])
+def test_undistort_bit_exact_and_fused_frame_build(binding, sw, O, name, seed, D):
+    """Device Camera::UndistortImage == oracle (== cv2.undistort, tests/test_oracle_cpu.py), and a frame built from a
+    distorted image by a context that knows the distortion equals a frame built from the undistorted image."""
+    cfg, poses, imgs = sw.sequence(name, seed, 2)
+    P, cam = cfg["params"], cfg["cam"]
+    exp = [O.undistort(cam, D, im) for im in imgs]
+    assert (exp[0] != imgs[0]).mean() > 0.1           # the distortion does something
+    plain = _ctx(binding, cfg)
+    ctx = _ctx(binding, cfg)
+    try:
+        # off: a copy, as the reference does (camera.cc:103-104)
+        assert np.array_equal(ctx.undistort(imgs[0]), imgs[0])
+        ctx.set_distortion(D)
+        got = ctx.undistort(imgs[0])
+        assert np.array_equal(got, exp[0]), f"{(got != exp[0]).sum()} pixels differ"
+        # fused: upload -> undistort -> pyramid -> FAST
+        f_d = ctx.frame(imgs[1], corners=True)
+        f_u = plain.frame(exp[1], corners=True)
+        for l in range(P.pyramid_levels):
+            assert np.array_equal(f_d.level(l), f_u.level(l)), f"level {l}"
+        xa, sa = f_d.corners()
+        xb, sb = f_u.corners()
+        assert np.array_equal(xa, xb) and np.array_equal(sa, sb)
+        f_d.destroy(); f_u.destroy()
+        ctx.set_distortion((0, 0, 0, 0, 0))
+        assert np.array_equal(ctx.undistort(imgs[0]), imgs[0])
+    finally:
+        ctx.close(); plain.close()
+
+
+@pytest.mark.parametrize("loc", [1, 2])
+def test_undistort_in_async_frame_batches(binding, sw, O, loc):
+    """sdvlb_frames_submit with distortion set: images in device memory or pinned host memory go through the raw
+    scratch ring and the undistortion kernel before the pyramid (12 batches: the ring of 8 sets wraps)."""
+    import ctypes as C
+    import torch
+    cfg, poses, imgs = sw.sequence("C2", 6, 3)
+    ctx = _ctx(binding, cfg)
+    L = binding.load()
+    try:
+        ctx.set_distortion(EUROC_D)
+        exp = [O.undistort(cfg["cam"], EUROC_D, im) for im in imgs]
+        n = len(imgs)
+        t = torch.from_numpy(np.ascontiguousarray(imgs))
+        t = t.cuda() if loc == 1 else t.pin_memory()
+        stride = imgs.shape[1] * imgs.shape[2]
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() + i * stride for i in range(n)])
+        for rep in range(12):
+            out = (C.c_void_p * n)()
+            assert L.sdvlb_frames_submit(C.c_void_p(ctx.h), ptrs, n, loc, 1, cfg["params"].num_features, out) == 0
+            assert L.sdvlb_frames_wait(C.c_void_p(ctx.h), out, n) == 0
+            for i in range(n):
+                f = binding.Frame(ctx, out[i])
+                assert np.array_equal(f.level(0), exp[i]), f"batch {rep} frame {i}"
+                f.destroy()
+    finally:
+        ctx.close()

@@ -307,3 +307,28 @@ def test_depth_filter_converges_to_the_plane(O, sw, scenes, abi):
     assert (s["sigma2"][upd] < sig0[upd]).all()
     err = np.abs(1.0 / s["rho"][conv] - pts["depth"][conv]) / pts["depth"][conv]
     assert np.median(err) < 0.01
+
+
+# ------------------------------------------------------------------ Camera::UndistortImage = cv::undistort
+def test_undistort_golden(O, abi):
+    for name in GOLD["und_names"]:
+        w, h, fx, fy, u0, v0 = GOLD[f"und_{name}_cam"]
+        got = O.undistort(abi.Camera(w, h, fx, fy, u0, v0), GOLD[f"und_{name}_D"], GOLD[f"und_{name}_src"])
+        exp = GOLD[f"und_{name}_dst"]
+        assert np.array_equal(got, exp), f"{name}: {(got != exp).sum()} pixels differ from cv2.undistort"
+    # taps outside the source read 0 (BORDER_CONSTANT): the case with positive k1 maps its corners outside the source
+    assert (GOLD["und_barrel_dst"] == 0).sum() > 1000
+
+
+@pytest.mark.parametrize("w,h,fx,fy,u0,v0,D", [
+    (752, 480, 458.654, 457.296, 367.215, 248.375, (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0)),   # EuRoC cam0
+    (640, 480, 517.3, 516.5, 318.6, 255.3, (0.2624, -0.9531, -0.0054, 0.0026, 1.1633)),                            # TUM fr1
+    (333, 201, 300.0, 310.0, 160.2, 99.7, (-0.3, 0.1, 0.001, -0.002, 0.01))])
+def test_undistort_vs_cv2(O, abi, w, h, fx, fy, u0, v0, D):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(w)
+    src = cv2.GaussianBlur(rng.integers(0, 256, (h, w), dtype=np.uint8), (0, 0), 1.5)
+    K = np.array([[fx, 0, u0], [0, fy, v0], [0, 0, 1.0]])
+    exp = cv2.undistort(src, K, np.array(D))
+    got = O.undistort(abi.Camera(w, h, fx, fy, u0, v0), D, src)
+    assert np.array_equal(got, exp)
