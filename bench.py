@@ -444,7 +444,7 @@ def main():
     if rank == 0:
         from oracle import oracle_py as O
         O.lib()
-        ns = 2
+        ns = min(S, 8)     # bounded sample: 8 sequences x (steps + warmup) frames, about 2 s of CPU work per 65 frames
         t_cpu, frames_cpu, gn_cpu = 0.0, 0, 0
         for s in range(ns):
             tr = O.Tracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], args.kf_every)

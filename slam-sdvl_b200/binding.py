@@ -231,7 +231,7 @@ HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", 
                 "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_phases",
                 "sdvlh_tracker_ctx", "sdvlh_tracker_groups", "sdvlh_tracker_threads", "sdvlh_tracker_run",
                 "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles", "sdvlh_tracker_set_prefetch", "sdvlh_device_pose_refinement",
-                "sdvlh_map_update_candidates", "sdvlh_map_init_candidates"]
+                "sdvlh_map_update_candidates", "sdvlh_map_init_candidates", "sdvlh_camera_undistort"]
 
 
 def build_host(verbose=False):
@@ -277,6 +277,19 @@ def host_map_update_candidates(params, cam, ref_img, ref_T, cur_imgs, cur_poses,
     if rc:
         raise RuntimeError(lib.sdvlh_last_error().decode())
     return seeds, left.value
+
+
+def host_camera_undistort(params, cam, dist, img):
+    """sdvl::Camera::SetDistortions + UndistortImage of the C++ host mirror (test hook)."""
+    lib = load_host()
+    lib.sdvlh_config_set(C.byref(params), C.byref(cam))
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    d = np.ascontiguousarray(dist, np.float64)
+    out = np.zeros_like(img)
+    if lib.sdvlh_camera_undistort(ptr(d), ptr(img), w, h, ptr(out)):
+        raise RuntimeError(lib.sdvlh_last_error().decode())
+    return out
 
 
 def host_map_init_candidates(params, cam, img_new, T_new, img_old, T_old, upd_imgs, upd_T, img_last, T_last, depth_mean,

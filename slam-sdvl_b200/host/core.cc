@@ -67,6 +67,27 @@ Camera::Camera() {
   const sdvlb_camera& c = Config::CameraParams();
   width_ = c.width; height_ = c.height; fx_ = c.fx; fy_ = c.fy; u0_ = c.u0; v0_ = c.v0;
 }
+void Camera::SetDistortions(double d0, double d1, double d2, double d3, double d4) {   // camera.cc:38-67
+  d_[0] = d0; d_[1] = d1; d_[2] = d2; d_[3] = d3; d_[4] = d4;
+  // the reference tests d0 five times (camera.cc:45); the intent -- and cv::undistort's behaviour -- is "all zero"
+  has_distortion_ = !(d0 == 0.0 && d1 == 0.0 && d2 == 0.0 && d3 == 0.0 && d4 == 0.0);
+}
+
+void Camera::UndistortImage(const cv::Mat& in, cv::Mat* out) const {   // camera.cc:100-105
+  if (!has_distortion_) { *out = in.clone(); return; }
+  if (in.cols != int(width_) || in.rows != int(height_) || !in.isContinuous())
+    throw std::runtime_error("sdvl-b200: UndistortImage needs a continuous image of the camera's size");
+  sdvlb_ctx* ctx = Device::Current();
+  if (sdvlb_ctx_set_distortion(ctx, d_))
+    throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_set_distortion failed: ") + sdvlb_last_error());
+  cv::Mat dst(in.rows, in.cols, CV_8UC1);
+  const int rc = sdvlb_undistort(ctx, in.data, dst.data);
+  const double off[5] = {0, 0, 0, 0, 0};
+  sdvlb_ctx_set_distortion(ctx, off);   // the caller's Frame() calls get the undistorted image, as in main.cc:133-137
+  if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_undistort failed: ") + sdvlb_last_error());
+  *out = dst;
+}
+
 void Camera::Project(const Eigen::Vector3d& p, Eigen::Vector2d* o) const {
   (*o)(0) = u0_ + fx_ * p(0) / p(2);
   (*o)(1) = v0_ + fy_ * p(1) / p(2);

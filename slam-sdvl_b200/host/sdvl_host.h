@@ -92,8 +92,19 @@ class Camera {
     return p(0) >= m && p(0) < width_ - m && p(1) >= m && p(1) < height_ - m;
   }
   static Eigen::Vector2d SimpleProject(const Eigen::Vector3d& p) { return Eigen::Vector2d(p(0) / p(2), p(1) / p(2)); }
+  // camera.cc:38-67: (k1, k2, p1, p2, k3) of cv::undistort; all zero = no distortion
+  void SetDistortions(double d0, double d1, double d2, double d3, double d4);
+  bool HasDistortion() const { return has_distortion_; }
+  const double* GetDistortions() const { return d_; }
+  // camera.cc:100-105: cv::undistort on the device (sdvlb_undistort), a copy without distortion.  `in` must be
+  // continuous.  A tracker that wants the undistortion fused into Frame construction instead calls
+  // sdvlb_ctx_set_distortion(ctx, camera->GetDistortions()) once and hands the distorted image to Frame().
+  void UndistortImage(const cv::Mat& in, cv::Mat* out) const;
+  double GetPixelErrorAngle() const { return std::atan(1.0 / (2.0 * fx_)) * 2.0; }   // camera.h:104-107
  private:
   double width_, height_, fx_, fy_, u0_, v0_;
+  double d_[5] = {0, 0, 0, 0, 0};
+  bool has_distortion_ = false;
 };
 
 // ------------------------------------------------------------------------------------------------ Point (point.h)

@@ -812,6 +812,23 @@ struct HookContext {
   }
 };
 
+// Camera::SetDistortions + Camera::UndistortImage of the host mirror (test hook).  Config must have been set.
+int sdvlh_camera_undistort(const double d[5], const uint8_t* in, int w, int h, uint8_t* out) {
+  try {
+    using namespace sdvl;
+    HookContext hook_ctx;
+    Camera cam;
+    cam.SetDistortions(d[0], d[1], d[2], d[3], d[4]);
+    cv::Mat src(h, w, CV_8UC1, const_cast<uint8_t*>(in)), dst;
+    cam.UndistortImage(src, &dst);
+    std::memcpy(out, dst.data, size_t(w) * h);
+    return 0;
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return -1;
+  }
+}
+
 // Test hook for the class-level mapping pass: builds a keyframe with n candidate points (state taken from `seeds`),
 // runs Map::UpdateCandidates against each of the n_frames images (poses: n_frames x 7) and writes the candidates'
 // final state back into `seeds` (status = outcome of the last pass a candidate took part in).  *n_left = candidates

@@ -295,3 +295,11 @@ def test_undistort_in_async_frame_batches(binding, sw, O, loc):
                 f.destroy()
     finally:
         ctx.close()
+
+
+def test_host_camera_undistort_image(binding, sw, O):
+    """sdvl::Camera::UndistortImage (C++ host mirror) == oracle == cv2.undistort; without distortion it clones."""
+    cfg, poses, imgs = sw.sequence("C2", 2, 1)
+    got = binding.host_camera_undistort(cfg["params"], cfg["cam"], EUROC_D, imgs[0])
+    assert np.array_equal(got, O.undistort(cfg["cam"], EUROC_D, imgs[0]))
+    assert np.array_equal(binding.host_camera_undistort(cfg["params"], cfg["cam"], (0, 0, 0, 0, 0), imgs[0]), imgs[0])
