@@ -9,8 +9,9 @@ frame for every sequence of this GPU.  Sequences are sharded over ranks with no 
   e2e   : frames/s through the host-facing API with frames in pinned host memory (H2D of every frame and D2H of
           poses / matches / corner lists inside the timed region)
   roofline    : dominant kernel, algorithmic bytes per launch / CUDA-event duration, vs measured HBM copy peak
-  cpu_baseline: the CPU oracle (port of the reference path) on one host core, bounded sample
-  --impl reference : the same oracle on all host cores (one sequence per thread), no GPU
+  cpu_baseline: the reference's own CPU code (oracle/_ref, kind "reference": SDVL's sources compiled unmodified
+          against stand-in Eigen / OpenCV headers) on one host core, bounded sample; the oracle port if _ref is absent
+  --impl reference : the same on all host cores (one sequence per core, one process each), no GPU
 """
 import argparse
 import importlib
@@ -192,41 +193,87 @@ def algorithmic_bytes(cfg, kernel, stats_prev, stats_cur, n_corners=1000, kbar=3
     raise ValueError(kernel)
 
 
+def cpu_impl():
+    """The CPU arm's implementation: the reference's own sources (oracle/_ref/libsdvlref.so, compiled unmodified from
+    /root/reference against oracle/ref_shim, kind "reference") when that library was built, else the oracle port."""
+    from oracle import oracle_py, ref_py
+    if os.path.exists(ref_py.path()):
+        try:
+            ref_py.lib()
+            return ref_py, "reference", ("SDVL's own image_align.cc / matcher.cc / feature_align.cc / frame.cc / fast_detector.cc "
+                                         "(oracle/_ref: compiled unmodified, -O3; cv::pyrDown / cv::FAST served by the "
+                                         "cv2-pinned restatements)")
+        except Exception as e:   # a library built for another machine: fall back to the port, and say so
+            print(f"bench.py: oracle/_ref unusable ({e}); timing the oracle port", file=sys.stderr)
+    oracle_py.lib()
+    return oracle_py, "port", "CPU oracle (restatement of the reference path)"
+
+
+def _reference_worker(i, cfg_name, F, W, kf_every, start, q):
+    """One process per host core: the reference keeps process-wide state (rand(), Frame::counter_, Config singleton),
+    so sequences run in separate processes, as separate SDVL instances would."""
+    try:
+        load_pkg()
+        sw = importlib.import_module("slam_sdvl_b200.synthworld")
+        impl, _, _ = cpu_impl()
+        cfg = sw.config(cfg_name)
+        poses = sw.trajectory(cfg, 1000 + i, F)
+        imgs = sw.render(cfg, poses, threads=1)
+        tr = impl.Tracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], kf_every)
+        tr.run(imgs[:1 + W], poses[:1 + W])
+        start.wait()
+        est, st, sec = tr.run(imgs[1 + W:], poses[1 + W:])
+        t_end = time.perf_counter()
+        tr.close()
+        q.put((i, t_end, sec, float(sw.ate(est, poses[1 + W:])), int(np.clip(st[:, 6], 0, None).sum()), None))
+    except Exception as e:   # noqa: BLE001 -- reported by the parent
+        try:
+            start.abort()
+        except Exception:
+            pass
+        q.put((i, 0.0, 0.0, 0.0, 0, repr(e)))
+
+
 def run_reference(args, cfg, sw, rank, world):
-    """The reference path's CPU implementation (oracle port; the reference itself needs OpenCV/Eigen to build) on all
-    host cores, one sequence per thread."""
+    """The reference path's CPU implementation on all host cores, one sequence per core (one process each): the
+    reference's own code when oracle/_ref was built (see cpu_impl), else the oracle port.  No GPU, no CUDA."""
     if rank != 0:
         return
-    from oracle import oracle_py as O
-    O.lib()
+    import multiprocessing as mp
+    impl, kind, what = cpu_impl()
     T = os.cpu_count() or 1
     W, K = args.warmup, args.steps
     F = 1 + W + K
-    seqs = []
-    for t in range(T):
-        poses = sw.trajectory(cfg, 1000 + t, F)
-        seqs.append((poses, sw.render(cfg, poses, threads=T)))
-    trackers = [O.Tracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], args.kf_every) for _ in range(T)]
-    pool = ThreadPoolExecutor(T)
-    list(pool.map(lambda i: trackers[i].run(seqs[i][1][:1 + W], seqs[i][0][:1 + W]), range(T)))
+    ctx = mp.get_context("fork")
+    start = ctx.Barrier(T + 1)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_reference_worker, args=(i, args.config, F, W, args.kf_every, start, q)) for i in range(T)]
+    for p in procs:
+        p.start()
+    start.wait()                      # every worker has rendered its sequence and run its warm-up frames
     t0 = time.perf_counter()
-    res = list(pool.map(lambda i: trackers[i].run(seqs[i][1][1 + W:], seqs[i][0][1 + W:]), range(T)))
-    dt = time.perf_counter() - t0
-    gn = sum(int(r[1][:, 6].sum()) for r in res)
+    res = [q.get() for _ in range(T)]
+    for p in procs:
+        p.join()
+    bad = [r for r in res if r[5]]
+    if bad:
+        raise SystemExit(f"bench.py --impl reference: worker failed: {bad[0][5]}")
+    dt = max(r[1] for r in res) - t0  # CLOCK_MONOTONIC is system-wide: the slowest worker ends the step
+    gn = sum(r[4] for r in res)
     value = T * K / dt
-    ate = max(sw.ate(r[0], seqs[i][0][1 + W:]) for i, r in enumerate(res)) * 1e3
+    ate = max(r[3] for r in res) * 1e3
     out = {
         "impl": "reference", "metric": "tracked_frames_per_sec", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
         "config": {"workload": "C2: 752x480 EuRoC-shaped synthetic sequences, 5-level pyramid, 200 features, "
-                               "pyramid+FAST+ImageAlign+FeatureAlign", "sequences": T, "threads": T,
-                   "step": "one frame for each of the sequences (one per host thread)"},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": T, "kind": "port",
-                         "sample": f"{T} sequences x {K} frames, one sequence per thread, CPU oracle "
-                                   "(reference needs OpenCV/Eigen headers, not buildable here)"},
+                               "pyramid+FAST+ImageAlign+FeatureAlign", "sequences": T, "processes": T,
+                   "step": "one frame for each of the sequences (one per host core)"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": T, "kind": kind,
+                         "sample": f"{T} sequences x {K} frames, one sequence per core; {what}",
+                         "frames_per_s_per_core": K * T / sum(r[2] for r in res) if sum(r[2] for r in res) > 0 else None},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "us_per_gn_iter_cpu": None, "gn_iters": gn, "max_ate_mm_vs_gt": ate,
+        "us_per_gn_iter_cpu": None, "gn_iters": gn if kind == "port" else None, "max_ate_mm_vs_gt": ate,
     }
     print(json.dumps(out), flush=True)
 
@@ -442,8 +489,7 @@ def main():
     # ---- CPU baseline on one host core (rank 0, bounded sample)
     cpu_baseline = None
     if rank == 0:
-        from oracle import oracle_py as O
-        O.lib()
+        O, cpu_kind, cpu_what = cpu_impl()
         ns = min(S, 8)     # bounded sample: 8 sequences x (steps + warmup) frames, about 2 s of CPU work per 65 frames
         t_cpu, frames_cpu, gn_cpu = 0.0, 0, 0
         for s in range(ns):
@@ -452,10 +498,10 @@ def main():
             _, st, sec = tr.run(host_np[s, 1:], gt[s, 1:])
             t_cpu += sec
             frames_cpu += F - 1
-            gn_cpu += int(st[:, 6].sum())
+            gn_cpu += int(np.clip(st[:, 6], 0, None).sum())
             tr.close()
-        cpu_baseline = {"value": frames_cpu / t_cpu, "unit": "frames/s", "cores": 1, "kind": "port",
-                        "sample": f"{ns} sequences x {F - 1} frames of the same workload, CPU oracle, 1 thread",
+        cpu_baseline = {"value": frames_cpu / t_cpu, "unit": "frames/s", "cores": 1, "kind": cpu_kind,
+                        "sample": f"{ns} sequences x {F - 1} frames of the same workload, 1 thread; {cpu_what}",
                         "host_cores_available": ncpu}
 
     if rank == 0:

@@ -2,8 +2,10 @@
 // depth-filter candidates: the loop body of Map::UpdateCandidates (map.cc:397-498) with
 // Point::Update / ComputeTau / PDFNormal / HasConverged / Unpromote (point.cc:63-100,109-116,162-216),
 // GetDepthFromTriangulation and GetParallax (extra/utils.cc:193-213), Frame::IsPointVisible (frame.cc:104-112).
-// PARITY UNPINNED by the reference (it has no tests); checked by known-answer tests (tests/test_oracle_cpu.py:
-// the filter converges to the true depth of a synthetic plane).
+// PINNED against the reference's own Map::UpdateCandidates run from oracle/_ref (tests/test_oracle_vs_ref.py::
+// test_update_candidates_vs_reference: same converged / deleted / kept sets, filter state to 1e-10); the per-corner
+// part of Map::InitCandidates (SDVLB_SEEDS_INIT) shares every step but the list handling and is checked by the
+// known-answer tests of tests/test_oracle_cpu.py (the filter converges to the true depth of a synthetic plane).
 #include <algorithm>
 #include <cmath>
 

@@ -1,5 +1,6 @@
 """ctypes binding of the CPU oracle (TEST INFRASTRUCTURE: import only from tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs)."""
+import contextlib
 import ctypes as C
 import importlib.util
 import os
@@ -25,7 +26,8 @@ def _pkg():
 
 abi = importlib.import_module(_pkg().__name__ + ".abi")
 ptr = abi.ptr
-_LIB = None
+_LIBS = {}
+_SUF = ""   # "" = default build, "_strict" = -ffp-contract=off (oracle/Makefile)
 
 
 def build():
@@ -33,17 +35,35 @@ def build():
     return os.path.join(_HERE, "liboracle.so")
 
 
+def build_strict():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "-j8", "SUF=_strict",
+                           "CXXFLAGS=-O3 -march=x86-64-v3 -std=c++14 -fPIC -ffp-contract=off", "all"])
+    return os.path.join(_HERE, "liboracle_strict.so")
+
+
 def lib():
-    global _LIB
-    if _LIB is None:
-        path = os.path.join(_HERE, "liboracle.so")
+    if _SUF not in _LIBS:
+        path = os.path.join(_HERE, "liboracle%s.so" % _SUF)
         if not os.path.exists(path):
-            build()
-        _LIB = C.CDLL(path)
-        _LIB.orc_pyramid.restype = C.c_int64
-        _LIB.orc_tracker_create.restype = C.c_void_p
-        _LIB.orc_tracker_run.restype = C.c_double
-    return _LIB
+            build_strict() if _SUF else build()
+        l = C.CDLL(path)
+        l.orc_pyramid.restype = C.c_int64
+        l.orc_tracker_create.restype = C.c_void_p
+        l.orc_tracker_run.restype = C.c_double
+        _LIBS[_SUF] = l
+    return _LIBS[_SUF]
+
+
+@contextlib.contextmanager
+def strict():
+    """Within the block every call goes to liboracle_strict.so (no FMA contraction): bit-comparable with
+    ref_py.strict()."""
+    global _SUF
+    old, _SUF = _SUF, "_strict"
+    try:
+        yield
+    finally:
+        _SUF = old
 
 
 def pyramid(img, levels):
@@ -176,7 +196,8 @@ def pose_refine(params, cam, obs, T, rng=None, mode=0):
 class Tracker:
     def __init__(self, params, cam, plane, max_points, kf_every):
         plane = np.ascontiguousarray(plane, np.float64)
-        self.h = lib().orc_tracker_create(C.byref(params), C.byref(cam), ptr(plane), max_points, kf_every)
+        self.lib = lib()   # the variant this tracker lives in (default or strict)
+        self.h = self.lib.orc_tracker_create(C.byref(params), C.byref(cam), ptr(plane), max_points, kf_every)
 
     def run(self, imgs, gt_poses):
         imgs = np.ascontiguousarray(imgs)
@@ -184,12 +205,12 @@ class Tracker:
         gt = np.ascontiguousarray(gt_poses, np.float64)
         est = np.zeros((n, 7))
         stats = np.zeros((n, 8), np.int32)
-        sec = lib().orc_tracker_run(C.c_void_p(self.h), ptr(imgs), n, w, h, ptr(gt), ptr(est), ptr(stats))
+        sec = self.lib.orc_tracker_run(C.c_void_p(self.h), ptr(imgs), n, w, h, ptr(gt), ptr(est), ptr(stats))
         return est, stats, sec
 
     def close(self):
         if self.h:
-            lib().orc_tracker_destroy(C.c_void_p(self.h))
+            self.lib.orc_tracker_destroy(C.c_void_p(self.h))
             self.h = None
 
     def __del__(self):

@@ -1,0 +1,1 @@
+#include <opencv2/core/core.hpp>
