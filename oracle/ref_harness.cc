@@ -503,6 +503,65 @@ int ref_update_candidates(const sdvlb_params* P, const sdvlb_camera* cam_, const
   return rc;
 }
 
+// Map::InitCandidates (map.cc:262-400; private) on a new keyframe `new_img` connected to one older keyframe `old_img`:
+// the reference's own FilterCorners -> per-corner SearchPoint in the connected keyframe -> triangulation -> parallax /
+// minimum-distance screens -> Point::InitCandidate, and its candidates_ list (where every candidate is pushed twice,
+// map.cc:384,392).  The new keyframe carries one fixed point on its optical axis at depth_mean so that
+// Frame::GetSceneDepth() returns it (its cell is locked for FilterCorners, as any feature's is); the old keyframe has
+// no features, so the 1-px link test (map.cc:325-343) never fires.  Out, per unique candidate in list order: init
+// feature position / level, InitCandidate depth (1/rho), matched position / level in the old keyframe.
+int ref_init_candidates(const sdvlb_params* P, const sdvlb_camera* cam_, const uint8_t* new_img, const double T_new[7],
+                        const uint8_t* old_img, const double T_old[7], int w, int h, double depth_mean, double map_scale,
+                        double scale_min_dist, int min_feature_score, double* ref_px, int32_t* ref_level, double* depth,
+                        double* px2, int32_t* level2, int cap, int* n_listed) {
+  Quiet q;
+  Configure(P, cam_);
+  Config& c = Config::GetInstance();
+  c.kMapScale_ = map_scale;
+  c.kScaleMinDist_ = scale_min_dist;
+  c.kMinFeatureScore_ = min_feature_score;
+  sdvl::Camera cam;
+  sdvl::ORBDetector orb;
+  auto frame = MakeFrame(&cam, &orb, new_img, w, h, true, 1);
+  auto cframe = MakeFrame(&cam, &orb, old_img, w, h, true, 0);
+  frame->SetPose(ToSE3(T_new));
+  cframe->SetPose(ToSE3(T_old));
+  frame->SetKeyframe();
+  cframe->SetKeyframe();
+  auto anchor = std::make_shared<sdvl::Feature>(frame, Eigen::Vector2d(cam_->u0, cam_->v0), 0);
+  auto anchor_pt = FixedPoint(anchor, frame->GetWorldPose() * Eigen::Vector3d(0, 0, depth_mean));
+  anchor->SetPoint(anchor_pt);
+  frame->AddFeature(anchor);
+  frame->AddConnection(std::make_pair(cframe, 1));
+  sdvl::Map map;
+  map.InitCandidates(frame);
+  if (n_listed) *n_listed = int(map.candidates_.size());
+  std::vector<shared_ptr<sdvl::Point>> uniq;
+  for (auto& p : map.candidates_)
+    if (std::find(uniq.begin(), uniq.end(), p) == uniq.end()) uniq.push_back(p);
+  int rc = int(uniq.size());
+  for (int i = 0; i < int(uniq.size()) && i < cap; i++) {
+    const auto& p = uniq[i];
+    const auto& f1 = p->GetInitFeature();
+    const auto& f2 = p->GetFeatures().front();   // feature2 was pushed to the front last (map.cc:381)
+    if (f1->GetFrame() != frame || f2->GetFrame() != cframe || p->GetFeatures().size() != 2) rc = -8;
+    ref_px[2 * i] = f1->GetPosition()(0); ref_px[2 * i + 1] = f1->GetPosition()(1);
+    ref_level[i] = f1->GetLevel();
+    depth[i] = 1.0 / p->GetInverseDepth();
+    px2[2 * i] = f2->GetPosition()(0); px2[2 * i + 1] = f2->GetPosition()(1);
+    level2[i] = f2->GetLevel();
+  }
+  // break the shared_ptr cycles
+  for (auto& p : uniq) { for (auto& f : p->GetFeatures()) f->SetPoint(nullptr); p->GetFeatures().clear(); p->feature_ = nullptr; }
+  anchor->SetPoint(nullptr);
+  anchor_pt->feature_ = nullptr;
+  map.candidates_.clear();
+  frame->connections_.clear();
+  frame->RemoveFeatures();
+  cframe->RemoveFeatures();
+  return rc;
+}
+
 // ---- primitives -------------------------------------------------------------------------------------------------
 void ref_se3_exp(const double u[6], double T[7]) {
   Vec6 v;

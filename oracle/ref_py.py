@@ -147,6 +147,28 @@ def update_candidates(params, cam, cur_img, T_cur, ref_imgs, seeds, depth_mean, 
     return seeds
 
 
+def init_candidates(params, cam, new_img, T_new, old_img, T_old, depth_mean, map_scale=1.0, scale_min_dist=0.25,
+                    min_feature_score=50):
+    """The reference's Map::InitCandidates on keyframe `new_img` connected to keyframe `old_img`.  Returns a dict:
+    ref_px, ref_level (init features), depth (InitCandidate), px, level (match in the old keyframe), listed."""
+    new_img = np.ascontiguousarray(new_img)
+    old_img = np.ascontiguousarray(old_img)
+    h, w = new_img.shape
+    cap = 4096
+    ref_px, px2, depth = np.zeros((cap, 2)), np.zeros((cap, 2)), np.zeros(cap)
+    ref_level, level2 = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    listed = C.c_int(0)
+    T_new = np.ascontiguousarray(T_new, np.float64)
+    T_old = np.ascontiguousarray(T_old, np.float64)
+    n = lib().ref_init_candidates(C.byref(params), C.byref(cam), ptr(new_img), ptr(T_new), ptr(old_img), ptr(T_old), w, h,
+                                  C.c_double(depth_mean), C.c_double(map_scale), C.c_double(scale_min_dist),
+                                  min_feature_score, ptr(ref_px), ptr(ref_level), ptr(depth), ptr(px2), ptr(level2), cap,
+                                  C.byref(listed))
+    assert 0 <= n <= cap, n
+    return dict(ref_px=ref_px[:n], ref_level=ref_level[:n], depth=depth[:n], px=px2[:n], level=level2[:n],
+                listed=listed.value)
+
+
 def align_patch(params, img, border_patch, px):
     img = np.ascontiguousarray(img, np.uint8)
     bp = np.ascontiguousarray(border_patch, np.uint8)

@@ -338,6 +338,41 @@ def test_update_candidates_vs_reference(O, sw, scenes, abi):
         assert seen[st] > 0, st
 
 
+@needs_ref
+@pytest.mark.parametrize("name,seed", [("C2", 2), ("C3", 1), ("C1", 3)])
+def test_init_candidates_vs_reference(O, sw, scenes, abi, name, seed):
+    """Map::InitCandidates run by the reference on a new keyframe connected to an older one: which filtered corners
+    become candidates (SearchPoint along the whole epipolar range, triangulation, parallax and minimum-distance
+    screens), with which depth and which match, and the candidates_ list holding every one of them twice
+    (map.cc:384,392) -- against the oracle's per-corner pass (SDVLB_SEEDS_INIT), which is what the device runs."""
+    cfg, poses, imgs = sw.sequence(name, seed, 10)
+    P, cam = cfg["params"], cfg["cam"]
+    k_old, k_new = 0, 9
+    with _both(O, True):
+        xyl, _ = O.detect(P, imgs[k_new], P.num_features)
+        depth_mean = float(np.median(scenes.seed_points(cfg, xyl, poses[k_new])["depth"]))
+        # the frame's only feature (the depth anchor on the optical axis) locks its cell, as in the reference harness
+        idx = O.filter_corners(P, imgs[k_new], P.num_features, np.array([[cam.u0, cam.v0]]))
+        s = np.zeros(len(idx), abi.SEED_DT)
+        c = xyl[idx].astype(np.float64)
+        px = c[:, :2] * (1 << xyl[idx, 2])[:, None]
+        v = np.stack([(px[:, 0] - cam.u0) / cam.fx, (px[:, 1] - cam.v0) / cam.fy, np.ones(len(idx))], axis=1)
+        v /= np.sqrt((v * v).sum(1))[:, None]
+        s["ref_frame"] = 0
+        s["ref_T"] = poses[k_new]
+        s["ref_px"] = px; s["ref_v"] = v; s["ref_level"] = xyl[idx, 2]
+        s["rho"] = 1.0 / depth_mean
+        s["sigma2"] = 1.0; s["a"] = 10; s["b"] = 10; s["z_range"] = 6; s["cos_alpha"] = 1; s["last_distance"] = depth_mean
+        exp = O.update_candidates(P, cam, imgs[k_old], poses[k_old], [imgs[k_new]], s, depth_mean, mode=abi.SEEDS_INIT)
+        got = R.init_candidates(P, cam, imgs[k_new], poses[k_new], imgs[k_old], poses[k_old], depth_mean)
+    ok = exp["status"] == abi.SEED_UPDATED
+    assert ok.sum() > 40
+    assert got["listed"] == 2 * ok.sum() and len(got["depth"]) == ok.sum()
+    assert np.array_equal(got["ref_px"], exp["ref_px"][ok]) and np.array_equal(got["ref_level"], exp["ref_level"][ok])
+    assert np.array_equal(got["level"], exp["level"][ok]) and np.array_equal(got["px"], exp["px"][ok])
+    assert np.allclose(got["depth"], exp["depth"][ok], rtol=1e-12, atol=0)
+
+
 # ------------------------------------------------------------------------------------------------ whole trajectories
 @needs_ref
 @pytest.mark.parametrize("strict", [True, False])
