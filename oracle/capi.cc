@@ -137,6 +137,13 @@ int orc_search_points(const sdvlb_params* P, const sdvlb_camera* cam_, const uin
     ft->p2d.x = c.ref_px[0]; ft->p2d.y = c.ref_px[1];
     ft->v = V3(c.ref_v[0], c.ref_v[1], c.ref_v[2]);
     ft->level = c.ref_level;
+    if (UseOrb()) {   // the descriptor the feature got where it was created (frame.cc:148-161, map.cc:319-323)
+      static const OrbDetector det;
+      const int lx = int(c.ref_px[0] / (1 << c.ref_level)), ly = int(c.ref_px[1] / (1 << c.ref_level));
+      if (!det.IsInsideLimits(rf->pyramid[size_t(c.ref_level)], lx, ly)) return -3;
+      ft->descriptor.resize(32);
+      det.GetDescriptor(rf->pyramid[size_t(c.ref_level)], lx, ly, ft->descriptor.data());
+    }
     sdvlb_match& o = out[i];
     std::memset(&o, 0, sizeof(o));
     o.zmssd = -1;

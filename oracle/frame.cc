@@ -154,7 +154,7 @@ void RetainBest(std::vector<KeyPoint>* kps, int n) {  // KeyPointsFilter::retain
 void SelectPixels(const sdvlb_params& P, const Mat8& src, int level, int nfeatures, std::vector<Corner>* corners,
                   std::vector<int>* scores) {
   const int cell = P.cell_size;
-  const int margin = 1 + P.patch_size / 2;  // use_orb == 0 (fast_detector.cc:66)
+  const int margin = BorderMargin(P);  // fast_detector.cc:63-66
   const int wcells = int(std::ceil(double(src.cols) / double(cell)));
   const int hcells = int(std::ceil(double(src.rows) / double(cell)));
   std::vector<std::vector<KeyPoint>> cell_fts(size_t(hcells) * wcells);
@@ -303,7 +303,7 @@ void FilterCorners(const sdvlb_params& P, const std::vector<Mat8>& pyr, const st
   std::vector<std::pair<int, int>> cgrid(size_t(gw) * gh, std::make_pair(0, min_feature_score));
   std::vector<bool> mask(size_t(gw) * gh, false);
   for (const V2& p : locked) mask.at(size_t(int(p.y / cell) * gw + int(p.x / cell))) = true;
-  const int margin = 1 + P.patch_size / 2;
+  const int margin = BorderMargin(P);   // fast_detector.cc:183-186
   int index = 0;
   for (auto it = corners.begin(); it != corners.end(); it++, index++) {
     const int px = it->x, py = it->y, level = it->level, scale = 1 << level;

@@ -33,6 +33,11 @@ bool Matcher::SearchPoint(const std::shared_ptr<Frame>& frame, const std::shared
     if (!frame->Project(p3d_max, &pxb)) return false;
   }
 
+  if (UseOrb()) {   // matcher.cc:79-80: assert(feature->HasDescriptor())
+    assert(feature->descriptor.size() == 32);
+    desc_ = feature->descriptor.data();
+  }
+
   // feature->GetLevelPosition().cast<int>() (feature.h:93-95): truncation of p2d / 2^level
   const int lx = int(feature->p2d.x / (1 << level));
   const int ly = int(feature->p2d.y / (1 << level));
@@ -76,7 +81,7 @@ bool Matcher::SearchPoint(const std::shared_ptr<Frame>& frame, const std::shared
 void Matcher::GetCornersInRange(const std::shared_ptr<Frame>& frame, const V2& pxa, const V2& pxb, int level,
                                 double range, std::vector<int>* indices) {  // :123-192
   const double range2 = range * range;
-  const int margin = 1 + patch_size_ / 2;
+  const int margin = BorderMargin(P_);   // matcher.cc:131-134,199-202
   const std::vector<Corner>& cc = frame->corners;
 
   double ex = pxa.x - pxb.x, ey = pxa.y - pxb.y;
@@ -113,7 +118,7 @@ void Matcher::GetCornersInRange(const std::shared_ptr<Frame>& frame, const V2& p
 void Matcher::GetCornersInRange(const std::shared_ptr<Frame>& frame, const V2& cpos, int level, double range,
                                 std::vector<int>* indices) {  // :194-230
   const double range2 = range * range;
-  const int margin = 1 + patch_size_ / 2;
+  const int margin = BorderMargin(P_);   // matcher.cc:131-134,199-202
   const std::vector<Corner>& cc = frame->corners;
   int index = 0;
   for (auto it = cc.begin(); it != cc.end(); ++it, ++index) {
@@ -159,15 +164,21 @@ bool Matcher::SearchFeatures(const std::shared_ptr<Frame>& frame, const std::vec
   int sumA = 0, sumAA = 0;
   V2 best_px;
   const std::vector<Corner>& corners = frame->corners;
-  const int threshold = int(patch_size_ * patch_size_ * MAX_SSD_PER_PIXEL);
+  const bool orb = UseOrb();
+  const int threshold = orb ? 100 /* MIN_ORB_THRESHOLD, matcher.h:37 */ : int(patch_size_ * patch_size_ * MAX_SSD_PER_PIXEL);
   int best_score = threshold + 1;
-  GetZMSSDScore(patch, patch_size_ * patch_size_, &sumA, &sumAA);
+  if (!orb) GetZMSSDScore(patch, patch_size_ * patch_size_, &sumA, &sumAA);
   for (auto it = indices.begin(); it != indices.end(); ++it) {
     const Corner& corner = corners[*it];
     const int level = corner.level;
     const Mat8& cimg = frame->pyramid[level];
-    const uint8_t* cur_patch = cimg.data.data() + (corner.y - patch_size_ / 2) * cimg.cols + (corner.x - patch_size_ / 2);
-    const int score = int(CompareZMSSDScore(patch, cur_patch, patch_size_, sumA, sumAA, cimg.cols));
+    int score;
+    if (orb) {   // matcher.cc:264-273: lazily computed corner descriptor vs the feature's
+      score = OrbDetector::Distance(desc_, CornerDescriptor(frame.get(), *it).data());
+    } else {
+      const uint8_t* cur_patch = cimg.data.data() + (corner.y - patch_size_ / 2) * cimg.cols + (corner.x - patch_size_ / 2);
+      score = int(CompareZMSSDScore(patch, cur_patch, patch_size_, sumA, sumAA, cimg.cols));
+    }
     if (score < best_score) {
       best_score = score;
       best_px.x = corner.x * (1 << level);

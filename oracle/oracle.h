@@ -122,6 +122,25 @@ void FilterCorners(const sdvlb_params& P, const std::vector<Mat8>& pyr, const st
 // BORDER_CONSTANT 0).  Pinned bit-exactly against OpenCV 4.13 (tests/golden, tests/test_oracle_cpu.py).
 void UndistortImage(const Camera& cam, const double d[5], const Mat8& in, Mat8* out);
 
+// ---------------------------------------------------------------- ORB descriptor mode (extra/orb_detector.cc)
+const int kOrbSize = 31;               // Config::ORBSize(); the only size the learned pattern exists for
+void SetUseOrb(int on);                // Config::UseORB() for this process (the oracle is single-threaded test code)
+bool UseOrb();
+int BorderMargin(const sdvlb_params& P);   // 4 + orb_size/2 with ORB, 1 + patch_size/2 without
+float FastAtan2(float y, float x);     // cv::fastAtan2
+class OrbDetector {
+ public:
+  OrbDetector();
+  bool IsInsideLimits(const Mat8& src, int x, int y) const;
+  double GetOrientation(const Mat8& src, int x, int y) const;
+  void GetDescriptor(const Mat8& src, int x, int y, uint8_t desc[32]) const;
+  static int Distance(const uint8_t* a, const uint8_t* b);
+ private:
+  std::vector<int> umax_;
+};
+struct Frame;
+const std::vector<uint8_t>& CornerDescriptor(Frame* f, int index);
+
 // ---------------------------------------------------------------- utils (extra/utils.cc)
 double AbsMax6(const Vec6 v);                              // utils.cc:28-42
 float Interpolate8U(const Mat8& m, float u, float v);      // utils.cc:44-59
@@ -165,6 +184,7 @@ struct Feature {  // feature.h:97-104
   V2 p2d;
   V3 v;
   int level = 0;
+  std::vector<uint8_t> descriptor;   // descriptor_ (32 bytes once set; ORB mode only)
 };
 
 struct Frame {  // frame.h:148-172
@@ -173,6 +193,7 @@ struct Frame {  // frame.h:148-172
   std::vector<Mat8> pyramid;
   std::vector<Corner> corners;
   std::vector<int> corner_scores;
+  std::vector<std::vector<uint8_t>> descriptors;   // descriptors_: per corner, filled lazily (ORB mode only)
   std::vector<std::shared_ptr<Feature>> features;
   std::vector<V2> outliers;
   SE3 pose;  // world -> camera
@@ -235,6 +256,7 @@ class Matcher {
   int patch_size_;
   uint8_t patch_[64 * 4];
   uint8_t border_patch_[100 * 4];
+  const uint8_t* desc_ = nullptr;   // feature->GetDescriptor() of the current SearchPoint (ORB mode)
 };
 
 // ---------------------------------------------------------------- FeatureAlign (feature_align.cc)

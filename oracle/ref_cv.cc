@@ -4,7 +4,7 @@
 // not installed, so the four image operations they call are supplied here by the oracle's restatements, each of which
 // is pinned bit-exactly against OpenCV 4.13 (tests/test_oracle_cpu.py, tests/golden/):
 //   cv::pyrDown (frame.cc:119), cv::FAST (extra/fast_detector.cc:95), cv::KeyPointsFilter::retainBest
-//   (extra/fast_detector.cc:140,148), cv::undistort (camera.cc:102).
+//   (extra/fast_detector.cc:140,148), cv::undistort (camera.cc:102), cv::fastAtan2 (extra/orb_detector.cc:436).
 #include <opencv2/core/core.hpp>
 
 #include "oracle.h"
@@ -55,10 +55,8 @@ void undistort(const Mat& src, Mat& dst, const Mat& K, const Mat& D) {
   FromMat8(out, &dst);
 }
 
-float fastAtan2(float y, float x) {   // ORB orientation only (extra/orb_detector.cc:436), degrees in [0, 360)
-  float a = std::atan2(y, x) * float(180.0 / CV_PI);
-  if (a < 0) a += 360.f;
-  return a;
+float fastAtan2(float y, float x) {   // extra/orb_detector.cc:436; the oracle's restatement, pinned against cv2.fastAtan2
+  return oracle::FastAtan2(y, x);
 }
 
 }  // namespace cv

@@ -76,6 +76,8 @@ struct Quiet {
   ~Quiet() { std::cout.rdbuf(old); }
 };
 
+bool g_use_orb = false;   // Config::UseORB() for the calls that follow (ref_set_orb)
+
 void Configure(const sdvlb_params* P, const sdvlb_camera* cam) {
   Config& c = Config::GetInstance();
   c.kPyramidLevels_ = P->pyramid_levels; c.kCellSize_ = P->cell_size; c.kMaxMatches_ = P->max_matches;
@@ -86,7 +88,8 @@ void Configure(const sdvlb_params* P, const sdvlb_camera* cam) {
   c.kMaxOptimPoseIts_ = P->max_optim_pose_its; c.kMaxRansacPoints_ = P->max_ransac_points;
   c.kMaxRansacIts_ = P->max_ransac_its; c.kMinMatches_ = P->min_matches;
   c.kInlierErrorThreshold_ = P->inlier_error_threshold;
-  c.kUseORB_ = false;
+  c.kUseORB_ = g_use_orb;
+  c.kORBSize_ = 31;
   if (cam) {
     sdvl::CameraParameters& k = c.camera_params_;
     k.width = int(cam->width); k.height = int(cam->height);
@@ -324,6 +327,13 @@ int ref_search_points(const sdvlb_params* P, const sdvlb_camera* cam_, const uin
     rf->SetPose(ToSE3(c.ref_T));
     auto ft = std::make_shared<sdvl::Feature>(rf, nullptr, Eigen::Vector2d(c.ref_px[0], c.ref_px[1]),
                                               Eigen::Vector3d(c.ref_v[0], c.ref_v[1], c.ref_v[2]), c.ref_level);
+    if (g_use_orb) {   // the descriptor the feature got where it was created (frame.cc:148-161, map.cc:319-323)
+      std::vector<uchar> d(32);
+      const Eigen::Vector2i lp = ft->GetLevelPosition().cast<int>();
+      if (!orb.IsInsideLimits(rf->GetPyramid()[c.ref_level], lp)) return -3;
+      orb.GetDescriptor(rf->GetPyramid()[c.ref_level], lp, &d);
+      ft->SetDescriptor(d);
+    }
     sdvlb_match& o = out[i];
     std::memset(&o, 0, sizeof(o));
     o.zmssd = -1;
@@ -560,6 +570,32 @@ int ref_init_candidates(const sdvlb_params* P, const sdvlb_camera* cam_, const u
   frame->RemoveFeatures();
   cframe->RemoveFeatures();
   return rc;
+}
+
+// ---- ORB descriptor mode ------------------------------------------------------------------------------------------
+void ref_set_orb(int on) { g_use_orb = on != 0; }
+// ORBDetector::GetDescriptor / GetOrientation (extra/orb_detector.cc:350-437) at n positions (x, y, level).
+int ref_orb_descriptors(const sdvlb_params* P, const uint8_t* img, int w, int h, const int32_t* xyl, int n, uint8_t* desc,
+                        float* angle) {
+  sdvlb_camera k{double(w), double(h), 1, 1, 0, 0};
+  Configure(P, &k);
+  sdvl::Camera cam;
+  sdvl::ORBDetector orb;
+  auto f = MakeFrame(&cam, &orb, img, w, h, false, 0);
+  std::vector<uchar> d(32);
+  for (int i = 0; i < n; i++) {
+    const Eigen::Vector2i p(xyl[3 * i], xyl[3 * i + 1]);
+    const int l = xyl[3 * i + 2];
+    if (l < 0 || l >= int(f->GetPyramid().size()) || !orb.IsInsideLimits(f->GetPyramid()[l], p)) return -2;
+    orb.GetDescriptor(f->GetPyramid()[l], p, &d);
+    std::memcpy(desc + 32 * size_t(i), d.data(), 32);
+    if (angle) angle[i] = float(orb.GetOrientation(f->GetPyramid()[l], p));
+  }
+  return 0;
+}
+int ref_orb_distance(const uint8_t* a, const uint8_t* b) {   // ORBDetector::Distance (:399-410)
+  sdvl::ORBDetector orb;
+  return orb.Distance(std::vector<uchar>(a, a + 32), std::vector<uchar>(b, b + 32));
 }
 
 // ---- primitives -------------------------------------------------------------------------------------------------

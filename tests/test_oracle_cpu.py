@@ -332,3 +332,56 @@ def test_undistort_vs_cv2(O, abi, w, h, fx, fy, u0, v0, D):
     exp = cv2.undistort(src, K, np.array(D))
     got = O.undistort(abi.Camera(w, h, fx, fy, u0, v0), D, src)
     assert np.array_equal(got, exp)
+
+
+# ------------------------------------------------------------------ ORB descriptor mode: third-party pins
+def test_fast_atan2_vs_cv2(O):
+    """cv::fastAtan2 (the orientation of ORBDetector::GetOrientation, extra/orb_detector.cc:436): the oracle's
+    restatement of OpenCV's polynomial returns cv2.fastAtan2's bits."""
+    cv2 = pytest.importorskip("cv2")
+    L = O.lib()
+    L.orc_fast_atan2.restype = C.c_float
+    L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(0)
+    for i in range(20000):
+        y, x = (rng.normal(0, 10 ** rng.uniform(-3, 6), 2)).astype(np.float32)
+        if i % 50 == 0:
+            y = np.float32(0)
+        if i % 77 == 0:
+            x = np.float32(0)
+        assert L.orc_fast_atan2(float(y), float(x)) == cv2.fastAtan2(float(y), float(x)), (y, x)
+    for y, x in ((0, 0), (1, 0), (-1, 0), (0, -1), (5, 5), (-5, 5), (3e5, -2e-3)):
+        assert L.orc_fast_atan2(float(y), float(x)) == cv2.fastAtan2(float(y), float(x))
+
+
+def test_orb_pattern_against_cv2(O, sw):
+    """The 256 learned tests of csrc/orb_pattern.h are OpenCV's: cv2.ORB descriptors (computed by OpenCV on its own
+    7x7 sigma-2 blur, at the orientation handed to it) against the oracle's GetDescriptor on the same blurred image.
+    A wrong table would differ in ~128 of 256 bits; the residue (well under one bit per descriptor) is a sample that
+    rounds to the neighbouring pixel in OpenCV's build."""
+    cv2 = pytest.importorskip("cv2")
+    cfg, poses, imgs = sw.sequence("C2", 0, 1)
+    P, img = cfg["params"], imgs[0]
+    O.lib().orc_set_orb(1)
+    try:
+        xyl, _ = O.detect(P, img, 1000)
+    finally:
+        O.lib().orc_set_orb(0)
+    assert xyl[:, 0].min() >= 19 and xyl[:, 1].min() >= 19      # ORB mode: FAST margin 4 + 31/2
+    xyl = np.ascontiguousarray(xyl[(xyl[:, 2] == 0) & (xyl[:, 0] > 40) & (xyl[:, 0] < 712) & (xyl[:, 1] > 40) & (xyl[:, 1] < 440)])
+    assert len(xyl) > 200
+    blur = cv2.GaussianBlur(img, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+    P1 = type(P)()
+    C.memmove(C.byref(P1), C.byref(P), C.sizeof(P))
+    P1.pyramid_levels = 1
+    d = np.zeros((len(xyl), 32), np.uint8)
+    ang = np.zeros(len(xyl), np.float32)
+    assert O.lib().orc_orb_descriptors(C.byref(P1), O.ptr(blur), img.shape[1], img.shape[0], O.ptr(xyl), len(xyl), O.ptr(d), O.ptr(ang)) == 0
+    kps = [cv2.KeyPoint(float(x), float(y), 31.0, float(a), 1.0, 0) for (x, y, l), a in zip(xyl, ang)]
+    orb = cv2.ORB_create(nfeatures=5000, scaleFactor=1.2, nlevels=1, edgeThreshold=31, firstLevel=0, WTA_K=2, patchSize=31)
+    kps2, desc = orb.compute(img, kps)
+    idx = {(int(x), int(y)): i for i, (x, y, l) in enumerate(xyl)}
+    sel = [idx[(int(k.pt[0]), int(k.pt[1]))] for k in kps2]
+    assert len(sel) > 200
+    bits = np.unpackbits(d[sel] ^ desc, axis=1).sum(1)
+    assert bits.mean() < 0.5 and (bits == 0).mean() > 0.8, (bits.mean(), (bits == 0).mean())

@@ -293,6 +293,58 @@ def test_select_inliers_and_optimize_pose_vs_reference(O, sw, abi, n, n_bad, see
         assert (o2["flags"] == abi.OBS_INLIER).sum() >= n - n_bad - 3
 
 
+# ------------------------------------------------------------------------------------------------ ORB descriptor mode
+@needs_ref
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("name,seed", [("C2", 0), ("C1", 3), ("C5", 1)])
+def test_orb_mode_vs_reference(O, sw, scenes, abi, name, seed, strict):
+    """Config::UseORB(): FAST / FilterCorners / GetCornersInRange margins of 4 + orb_size/2, ORBDetector::GetOrientation
+    and GetDescriptor at every corner, ORBDetector::Distance, and Matcher::SearchPoint scoring by descriptor distance
+    (threshold 100) -- the reference's own extra/orb_detector.cc and matcher.cc against the oracle."""
+    cfg, poses, imgs = sw.sequence(name, seed, 5)
+    P, cam = cfg["params"], cfg["cam"]
+    h, w = imgs[0].shape
+    with _both(O, strict):
+        O.lib().orc_set_orb(1)
+        R.lib().ref_set_orb(1)
+        try:
+            xo, _ = O.detect(P, imgs[0], P.num_features)
+            xr, _ = R.detect(P, imgs[0], P.num_features)
+            assert len(xo) > 300 and np.array_equal(xo, xr) and xo[:, 0].min() >= 19 and xo[:, 1].min() >= 19
+            io, ir = O.filter_corners(P, imgs[0], P.num_features, np.zeros((0, 2))), R.filter_corners(P, imgs[0], P.num_features, np.zeros((0, 2)))
+            assert len(io) > 20 and np.array_equal(io, ir)
+            xyl = np.ascontiguousarray(xo)
+            do, dr = np.zeros((len(xyl), 32), np.uint8), np.zeros((len(xyl), 32), np.uint8)
+            ao, ar = np.zeros(len(xyl), np.float32), np.zeros(len(xyl), np.float32)
+            assert O.lib().orc_orb_descriptors(C.byref(P), O.ptr(imgs[0]), w, h, O.ptr(xyl), len(xyl), O.ptr(do), O.ptr(ao)) == 0
+            assert R.lib().ref_orb_descriptors(C.byref(P), O.ptr(imgs[0]), w, h, O.ptr(xyl), len(xyl), O.ptr(dr), O.ptr(ar)) == 0
+            assert np.array_equal(ao, ar)
+            if strict:
+                assert np.array_equal(do, dr)
+            else:   # FMA contraction in the reference's build can move a sample to the neighbouring pixel
+                assert (do == dr).all(1).mean() > 0.98
+            for i in range(0, len(xyl) - 1, 7):
+                d = int(np.unpackbits(do[i] ^ do[i + 1]).sum())
+                assert R.lib().ref_orb_distance(O.ptr(do[i]), O.ptr(do[i + 1])) == d
+            pts = scenes.seed_points(cfg, xo, poses[0], max_points=400, one_per_cell=False, margin=20)
+            n_found = 0
+            for gap in (1, 4):
+                for fixed, std_frac in ((True, 0.05), (False, 0.5)):
+                    c = scenes.candidates(pts, poses[0], 0, fixed=fixed, project=True, std_frac=std_frac)
+                    mo = O.search_points(P, cam, imgs[gap], poses[gap], [imgs[0]], c)
+                    mr = R.search_points(P, cam, imgs[gap], poses[gap], [imgs[0]], c)
+                    assert np.array_equal(mo["status"], mr["status"]) and np.array_equal(mo["level"], mr["level"])
+                    n_found += int((mo["status"] == abi.MATCH_FOUND).sum())
+                    if strict:
+                        assert np.array_equal(mo["px"], mr["px"])
+                    else:
+                        assert np.abs(mo["px"] - mr["px"]).max() < 1e-4
+            assert n_found > 400
+        finally:
+            O.lib().orc_set_orb(0)
+            R.lib().ref_set_orb(0)
+
+
 # ------------------------------------------------------------------------------------------------ Map (mapping thread)
 @needs_ref
 def test_update_candidates_vs_reference(O, sw, scenes, abi):
