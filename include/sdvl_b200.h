@@ -131,6 +131,21 @@ int sdvlb_ctx_set_distortion(sdvlb_ctx* ctx, const double d[5]);
  * With distortion off it copies, as the reference does. */
 int sdvlb_undistort(sdvlb_ctx* ctx, const uint8_t* in, uint8_t* out);
 
+/* ---- ORB descriptor mode ----------------------------------------------------------
+ * Config::UseORB() (config.h:139, `SDVL.use_orb`), orb_size 31 (the size the learned pattern exists for).
+ * sdvlb_ctx_set_orb(ctx, 1) switches the context to the reference's ORB mode: FAST cells and Frame::FilterCorners use the
+ * border margin 4 + orb_size/2 = 19 (extra/fast_detector.cc:63-64,183-184) for every frame built from then on; call it
+ * before creating frames.  It synchronises the context. */
+int sdvlb_ctx_set_orb(sdvlb_ctx* ctx, int on);
+/* ORBDetector::GetDescriptor / GetOrientation (extra/orb_detector.cc:350-437) at n positions xyl = n x (x, y, level),
+ * level coordinates, of frame f: what Frame::FilterCorners stores in Frame::descriptors_ for the filtered corners
+ * (frame.cc:148-161), Map::InitCandidates copies into Feature::descriptor_ (map.cc:319-323) and Matcher::SearchFeatures
+ * fills in lazily (matcher.cc:265-269).  desc receives n x 32 bytes; angle (optional) the orientation in degrees
+ * (cv::fastAtan2).  Positions must satisfy ORBDetector::IsInsideLimits (19 px from the border of their level), else
+ * SDVLB_ERR_ARG is returned and their descriptor is zero (the reference asserts). */
+int sdvlb_frame_orb_descriptors(sdvlb_ctx* ctx, const sdvlb_frame* f, const int32_t* xyl, int n, uint8_t* desc,
+                                float* angle);
+
 /* ---- Frame -------------------------------------------------------------- */
 /* Frame::Frame(camera, detector, img, corners): uploads `img` (u8, `stride`
  * bytes per row), builds the pyramid on the device, optionally runs FAST with
@@ -233,6 +248,13 @@ typedef struct sdvlb_match {
  * on `cur` in device memory. */
 int sdvlb_search_points(sdvlb_ctx* ctx, const sdvlb_frame* cur, const sdvlb_candidate* cands,
                         int n, const double T_cur[7], sdvlb_match* out);
+/* The same with Config::UseORB() (matcher.cc:79-80,131-134,243-277): corners are gated with the ORB margin and scored
+ * by ORBDetector::Distance between cand_desc[i] (n x 32 bytes: feature->GetDescriptor() of candidate i) and the
+ * corner's descriptor, accepted below MIN_ORB_THRESHOLD = 100 (matcher.h:37); sdvlb_match.zmssd then carries that
+ * distance.  Warp, search level, patch and the Lucas-Kanade refinement are unchanged.  Needs sdvlb_ctx_set_orb(ctx, 1)
+ * and T_cur. */
+int sdvlb_search_points_orb(sdvlb_ctx* ctx, const sdvlb_frame* cur, const sdvlb_candidate* cands, int n,
+                            const double T_cur[7], const uint8_t* cand_desc, sdvlb_match* out);
 
 /* ---- batched front half of ProcessFrame -------------------------------- */
 /* Where a level-0 image lives.  HOST: any host memory (one cudaMemcpyAsync per

@@ -69,6 +69,7 @@ EXPORTS = [
     "sdvlb_seq_create", "sdvlb_seq_destroy", "sdvlb_seq_reset", "sdvlb_seq_add_points", "sdvlb_seq_track_submit",
     "sdvlb_seq_track_poll", "sdvlb_seq_track_collect", "sdvlb_frame_filter_corners", "sdvlb_update_candidates",
     "sdvlb_ctx_set_distortion", "sdvlb_undistort",
+    "sdvlb_ctx_set_orb", "sdvlb_frame_orb_descriptors", "sdvlb_search_points_orb",
 ]
 
 
@@ -98,6 +99,15 @@ class Frame:
         _check(load().sdvlb_frame_filter_corners(C.c_void_p(self.ctx.h), C.c_void_p(self.h), ptr(locked), locked.shape[0],
                                                  min_feature_score, ptr(out), out.shape[0], C.byref(n)))
         return out[:n.value].copy()
+
+    def orb_descriptors(self, xyl):
+        """ORBDetector::GetDescriptor / GetOrientation at positions xyl = n x (x, y, level): (n x 32 bytes, degrees)."""
+        xyl = np.ascontiguousarray(xyl, np.int32).reshape(-1, 3)
+        desc = np.zeros((xyl.shape[0], 32), np.uint8)
+        ang = np.zeros(xyl.shape[0], np.float32)
+        _check(load().sdvlb_frame_orb_descriptors(C.c_void_p(self.ctx.h), C.c_void_p(self.h), ptr(xyl), xyl.shape[0],
+                                                  ptr(desc), ptr(ang)))
+        return desc, ang
 
     def detect(self, nfeatures):
         _check(load().sdvlb_frame_detect(C.c_void_p(self.ctx.h), C.c_void_p(self.h), nfeatures))
@@ -174,6 +184,22 @@ class Context:
             Tp = ptr(T_cur)
         _check(load().sdvlb_search_points(C.c_void_p(self.h), C.c_void_p(cur.h), ptr(cands), cands.shape[0], Tp,
                                           ptr(out)))
+        return out
+
+    def set_orb(self, on=True):
+        """Config::UseORB(): ORB border margins for FAST / FilterCorners of the frames built from now on."""
+        _check(load().sdvlb_ctx_set_orb(C.c_void_p(self.h), int(on)))
+
+    def search_points_orb(self, cur, cands, T_cur, cand_desc):
+        """Matcher::SearchPoint with Config::UseORB(): cand_desc = n x 32 bytes (the candidates' feature descriptors)."""
+        cands = np.ascontiguousarray(cands)
+        assert cands.dtype == abi.CANDIDATE_DT
+        cand_desc = np.ascontiguousarray(cand_desc, np.uint8).reshape(-1, 32)
+        assert cand_desc.shape[0] == cands.shape[0]
+        out = np.zeros(cands.shape[0], abi.MATCH_DT)
+        T_cur = np.ascontiguousarray(T_cur, np.float64)
+        _check(load().sdvlb_search_points_orb(C.c_void_p(self.h), C.c_void_p(cur.h), ptr(cands), cands.shape[0], ptr(T_cur),
+                                              ptr(cand_desc), ptr(out)))
         return out
 
     def set_distortion(self, d):

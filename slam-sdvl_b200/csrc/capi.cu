@@ -25,6 +25,13 @@ cudaError_t sdvlb_launch_seed_update(sdvlb_seed* d_seeds, int n, const FrameDev&
 cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStream_t stream);
 int sdvlb_pyramid_launches(const PyrGeom& g);
 void sdvlb_fast_plan(const PyrGeom& g, const sdvlb_params& p, int nfeatures, int corner_cap, FastPlan* plan);
+cudaError_t sdvlb_launch_orb_positions(const uint8_t* pyr, const PyrGeom& g, int levels, const int32_t* d_xyl, int n,
+                                       uint8_t* d_desc, float* d_angle, cudaStream_t stream);
+cudaError_t sdvlb_launch_orb_corners(const FrameDev& f, const PyrGeom& g, int levels, int cap, uint8_t* d_desc,
+                                     cudaStream_t stream);
+cudaError_t sdvlb_launch_search_orb(const SearchCandDev* d_cands, int n, const FrameDev& cur, sdvlb_match* d_out,
+                                    const PyrGeom& g, const DevParams& dp, const uint32_t* d_qdesc,
+                                    const uint32_t* d_curdesc, cudaStream_t stream);
 cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
                                     cudaStream_t stream);
 cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
@@ -209,6 +216,7 @@ const FastPlan* get_plan(sdvlb_ctx* c, int nfeatures) {
   c->plans.reserve(16);
   FastPlan p;
   sdvlb_fast_plan(c->geom, c->params, nfeatures, c->corner_cap, &p);
+  if (c->use_orb) p.args.margin = 4 + 31 / 2;   // Config::UseORB(): fast_detector.cc:63-64
   p.args.overflow_flag = c->h_overflow;
   c->plans.push_back(p);
   return &c->plans.back();
@@ -724,6 +732,7 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   for (int i = 0; i < kBuildEvents; i++) if (c->bevents[i]) cudaEventDestroy(c->bevents[i]);
   for (int i = 0; i < kBuildEvents; i++) if (c->uevents[i]) cudaEventDestroy(c->uevents[i]);
   if (c->ustream) cudaStreamSynchronize(c->ustream);   // shared by the contexts of the device: never destroyed
+  if (c->orb_buf) cudaFree(c->orb_buf);
   if (c->d_seeds) cudaFree(c->d_seeds);
   if (c->h_seeds) cudaFreeHost(c->h_seeds);
   if (c->raw_scratch) cudaFree(c->raw_scratch);
@@ -1116,6 +1125,111 @@ int sdvlb_update_candidates(sdvlb_ctx* c, const sdvlb_frame* cur, const double T
     seeds[i].ref_frame = ref;
   }
   return check_overflow(c);
+}
+
+// ---- ORB descriptor mode (Config::UseORB()) ------------------------------------------
+static int orb_scratch(sdvlb_ctx* c, size_t bytes) {
+  if (bytes <= c->orb_cap) return 0;
+  const size_t cap = std::max(bytes, 2 * c->orb_cap);
+  if (c->orb_buf) cudaFree(c->orb_buf);
+  c->orb_buf = nullptr; c->orb_cap = 0;
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->orb_buf), cap));
+  c->orb_cap = cap;
+  return 0;
+}
+
+int sdvlb_ctx_set_orb(sdvlb_ctx* c, int on) {
+  if (!c) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  if (on && (c->params.patch_size != 8)) return sdvlb_set_error(SDVLB_ERR_ARG, "ORB mode needs patch_size 8");
+  const int rc = sdvlb_ctx_sync(c);
+  if (rc) return rc;
+  c->use_orb = on != 0;
+  c->plans.clear();          // FAST plans carry the border margin
+  return 0;
+}
+
+int sdvlb_frame_orb_descriptors(sdvlb_ctx* c, const sdvlb_frame* f, const int32_t* xyl, int n, uint8_t* desc, float* angle) {
+  if (!c || !f || n < 0 || (n > 0 && (!xyl || !desc))) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  int rc = ensure_built(const_cast<sdvlb_frame*>(f));
+  if (rc) return rc;
+  if (n == 0) return 0;
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  const size_t o_xyl = 0, o_desc = align_up(size_t(n) * 12, 256), o_ang = o_desc + align_up(size_t(n) * 32, 256);
+  rc = orb_scratch(c, o_ang + size_t(n) * 4);
+  if (rc) return rc;
+  int32_t* d_xyl = reinterpret_cast<int32_t*>(c->orb_buf + o_xyl);
+  uint8_t* d_desc = c->orb_buf + o_desc;
+  float* d_ang = reinterpret_cast<float*>(c->orb_buf + o_ang);
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(d_xyl, xyl, size_t(n) * 12, cudaMemcpyHostToDevice, c->stream));
+  SDVLB_CUDA_TRY(sdvlb_launch_orb_positions(f->dev.pyr, c->geom, c->params.pyramid_levels, d_xyl, n, d_desc, d_ang, c->stream));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(desc, d_desc, size_t(n) * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (angle) SDVLB_CUDA_TRY(cudaMemcpyAsync(angle, d_ang, size_t(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->n_launches += 1;
+  c->h2d_bytes += int64_t(n) * 12;
+  c->d2h_bytes += int64_t(n) * (angle ? 36 : 32);
+  for (int i = 0; i < n; i++) {   // ORBDetector::GetDescriptor asserts IsInsideLimits (extra/orb_detector.cc:357)
+    const int l = xyl[3 * i + 2];
+    if (l < 0 || l >= c->params.pyramid_levels || xyl[3 * i] < 19 || xyl[3 * i] >= c->geom.w[l] - 19 || xyl[3 * i + 1] < 19 ||
+        xyl[3 * i + 1] >= c->geom.h[l] - 19)
+      return sdvlb_set_error(SDVLB_ERR_ARG, "position outside the ORB limits (descriptor zeroed)");
+  }
+  return 0;
+}
+
+int sdvlb_search_points_orb(sdvlb_ctx* c, const sdvlb_frame* cur, const sdvlb_candidate* cands, int n, const double T_cur[7],
+                            const uint8_t* cand_desc, sdvlb_match* out) {
+  if (!c || !cur || !T_cur || n < 0 || (n > 0 && (!cands || !out || !cand_desc)))
+    return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  if (!c->use_orb) return sdvlb_set_error(SDVLB_ERR_STATE, "sdvlb_ctx_set_orb(ctx, 1) first");
+  int rc = ensure_built(const_cast<sdvlb_frame*>(cur));
+  if (rc) return rc;
+  if (!cur->has_corners) return sdvlb_set_error(SDVLB_ERR_STATE, "current frame has no corners");
+  if (n == 0) return 0;
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  std::vector<SearchCandDev> hc(static_cast<size_t>(n));
+  for (int k = 0; k < n; k++) {
+    const sdvlb_candidate& s = cands[k];
+    SearchCandDev& d = hc[size_t(k)];
+    if (!s.ref_frame) return sdvlb_set_error(SDVLB_ERR_ARG, "candidate without reference frame");
+    if (s.ref_level < 0 || s.ref_level >= c->params.pyramid_levels)
+      return sdvlb_set_error(SDVLB_ERR_ARG, "candidate level out of range");
+    rc = ensure_built(const_cast<sdvlb_frame*>(s.ref_frame));
+    if (rc) return rc;
+    d.ref_pyr = s.ref_frame->dev.pyr;
+    memcpy(d.ref_T, s.ref_T, sizeof(d.ref_T));
+    d.ref_px[0] = s.ref_px[0]; d.ref_px[1] = s.ref_px[1];
+    d.ref_v[0] = s.ref_v[0]; d.ref_v[1] = s.ref_v[1]; d.ref_v[2] = s.ref_v[2];
+    d.idepth = s.idepth; d.idepth_std = s.idepth_std;
+    d.px[0] = s.px[0]; d.px[1] = s.px[1];
+    d.pos[0] = s.pos[0]; d.pos[1] = s.pos[1]; d.pos[2] = s.pos[2];
+    d.ref_level = s.ref_level;
+    d.flags = s.flags;
+    d.cur_index = 0;
+    d.pad_ = 0;
+  }
+  const size_t b_cand = sizeof(SearchCandDev) * size_t(n), b_q = size_t(n) * 32, b_cd = size_t(c->corner_cap) * 32;
+  const size_t b_m = sizeof(sdvlb_match) * size_t(n);
+  const size_t o_cand = 0, o_q = align_up(b_cand, 256), o_cd = o_q + align_up(b_q, 256), o_m = o_cd + align_up(b_cd, 256);
+  rc = orb_scratch(c, o_m + b_m);
+  if (rc) return rc;
+  SearchCandDev* d_cand = reinterpret_cast<SearchCandDev*>(c->orb_buf + o_cand);
+  uint32_t* d_q = reinterpret_cast<uint32_t*>(c->orb_buf + o_q);
+  uint8_t* d_cd = c->orb_buf + o_cd;
+  sdvlb_match* d_m = reinterpret_cast<sdvlb_match*>(c->orb_buf + o_m);
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(cur->dev.pose, T_cur, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(d_cand, hc.data(), b_cand, cudaMemcpyHostToDevice, c->stream));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(d_q, cand_desc, b_q, cudaMemcpyHostToDevice, c->stream));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));   // hc is pageable host memory about to go out of use
+  SDVLB_CUDA_TRY(sdvlb_launch_orb_corners(cur->dev, c->geom, c->params.pyramid_levels, c->corner_cap, d_cd, c->stream));
+  SDVLB_CUDA_TRY(sdvlb_launch_search_orb(d_cand, n, cur->dev, d_m, c->geom, c->dp, d_q, reinterpret_cast<const uint32_t*>(d_cd),
+                                         c->stream));
+  SDVLB_CUDA_TRY(cudaMemcpyAsync(out, d_m, b_m, cudaMemcpyDeviceToHost, c->stream));
+  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->n_launches += 2;
+  c->h2d_bytes += int64_t(b_cand + b_q) + 56;
+  c->d2h_bytes += int64_t(b_m);
+  return 0;
 }
 
 }  // extern "C"

@@ -91,6 +91,9 @@ struct sdvlb_ctx {
   int raw_next = 0;
   cudaEvent_t raw_done[kBuildEvents] = {};
   bool raw_used[kBuildEvents] = {};
+  bool use_orb = false;             // Config::UseORB(): ORB margins for FAST / FilterCorners, sdvlb_search_points_orb
+  uint8_t* orb_buf = nullptr;       // device scratch of the ORB entry points (positions / descriptors / candidates)
+  size_t orb_cap = 0;
   sdvlb_seed* d_seeds = nullptr;    // sdvlb_update_candidates staging (device + pinned host), grown on demand
   sdvlb_seed* h_seeds = nullptr;
   int seeds_cap = 0;

@@ -22,7 +22,7 @@ constexpr int FC_THREADS = 512;
 struct FilterArgs {
   FrameDev f;
   PyrGeom g;
-  int margin;              // 1 + patch_size / 2 (use_orb == 0)
+  int margin;              // 1 + patch_size / 2, or 4 + orb_size / 2 with Config::UseORB()
   int min_score;           // Config::MinFeatureScore()
   int n_cells, gw;
   const uint8_t* locked;   // n_cells bytes: FastDetector::grid_mask_
@@ -134,7 +134,7 @@ extern "C" int sdvlb_frame_filter_corners(sdvlb_ctx* c, const sdvlb_frame* f, co
   FilterArgs A;
   A.f = f->dev;
   A.g = c->geom;
-  A.margin = 1 + c->params.patch_size / 2;
+  A.margin = c->use_orb ? 4 + 31 / 2 : 1 + c->params.patch_size / 2;   // fast_detector.cc:183-186
   A.min_score = min_feature_score;
   A.n_cells = n_cells;
   A.gw = gw;

@@ -55,8 +55,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // One Matcher::SearchPoint by one warp.  s_bp / s_patch: this warp's 10x10 border patch and 8x8 patch in shared memory.
+// kOrb = Config::UseORB() (matcher.cc:79,131-134,243-277): corners are gated with the ORB margin and scored by the
+// Hamming distance between the feature's descriptor (q_desc, 8 words) and the corner's (cur_desc, 8 words per corner
+// of `cur`, orb.cu) with threshold MIN_ORB_THRESHOLD = 100; everything else is the same code.
+template <bool kOrb = false>
 __device__ __forceinline__ void search_one(const SearchCandDev& C, const FrameDev& cur, sdvlb_match* __restrict__ out_m,
-                                           const PyrGeom& G, const DevParams& dp, uint8_t* s_bp_w, uint8_t* s_patch_w) {
+                                           const PyrGeom& G, const DevParams& dp, uint8_t* s_bp_w, uint8_t* s_patch_w,
+                                           const uint32_t* __restrict__ q_desc = nullptr,
+                                           const uint32_t* __restrict__ cur_desc = nullptr) {
   const int lane = threadIdx.x & 31;
   const sdvlb_params& P = dp.p;
   const sdvlb_camera& cam = dp.cam;
@@ -165,12 +171,12 @@ __device__ __forceinline__ void search_one(const SearchCandDev& C, const FrameDe
   // ---- GetCornersInRange + SearchFeatures (matcher.cc:123-291)
   unsigned long long best_key = ~0ull;
   int n_in_range = 0;
-  const int threshold = ps * ps * 500;   // MAX_SSD_PER_PIXEL (matcher.h:36)
+  const int threshold = kOrb ? 100 : ps * ps * 500;   // MIN_ORB_THRESHOLD / MAX_SSD_PER_PIXEL (matcher.h:36-37)
   if (alive) {
     double range = double(P.search_size);
     for (int i = 1; i <= slevel; i++) range *= 1.2;
     const double range2 = range * range;
-    const int margin = 1 + ps / 2;
+    const int margin = kOrb ? 4 + 31 / 2 : 1 + ps / 2;   // matcher.cc:131-134
     // epipolar-capsule constants (matcher.cc:140-150)
     double nx = 0, ny = 0, normdist = 0, xdiff = 0, ydiff = 0, vline = 1;
     if (!fixed) {
@@ -183,9 +189,15 @@ __device__ __forceinline__ void search_one(const SearchCandDev& C, const FrameDe
       vline = xdiff * xdiff + ydiff * ydiff;
     }
     // GetZMSSDScore (matcher.cc:447-457): template sums, two pixels per lane
-    const int ta0 = s_patch_w[lane], ta1 = s_patch_w[lane + 32];
-    const int sumA = int(__reduce_add_sync(0xffffffffu, unsigned(ta0 + ta1)));
-    const int sumAA = int(__reduce_add_sync(0xffffffffu, unsigned(ta0 * ta0 + ta1 * ta1)));
+    int sumA = 0, sumAA = 0;
+    uint32_t qword = 0;
+    if constexpr (kOrb) {
+      qword = __ldg(q_desc + (lane & 7));
+    } else {
+      const int ta0 = s_patch_w[lane], ta1 = s_patch_w[lane + 32];
+      sumA = int(__reduce_add_sync(0xffffffffu, unsigned(ta0 + ta1)));
+      sumAA = int(__reduce_add_sync(0xffffffffu, unsigned(ta0 * ta0 + ta1 * ta1)));
+    }
     const int nc = *cur.n_corners;
     // GetCornersInRange scans every corner of the frame (matcher.cc:123-230); only corners within `range` of the
     // predicted position (fixed points) or of the epipolar segment can pass, so only the 32-px index cells that
@@ -244,15 +256,22 @@ __device__ __forceinline__ void search_one(const SearchCandDev& C, const FrameDe
           todo &= todo - 1;
           const int bcx = __shfl_sync(0xffffffffu, cx, src), bcy = __shfl_sync(0xffffffffu, cy, src);
           const int bcl = __shfl_sync(0xffffffffu, cl, src), bidx = __shfl_sync(0xffffffffu, idx, src);
-          const int Wc = G.w[bcl];
-          const int py = lane >> 2, pxx = (lane & 3) * 2;
-          const uint8_t* __restrict__ cp = cur.pyr + G.off[bcl] + size_t(bcy - half + py) * Wc + (bcx - half + pxx);
-          const int b0 = __ldg(cp), b1 = __ldg(cp + 1);
-          const int a0 = s_patch_w[py * 8 + pxx], a1 = s_patch_w[py * 8 + pxx + 1];
-          const int sB = int(__reduce_add_sync(0xffffffffu, unsigned(b0 + b1)));
-          const int sBB = int(__reduce_add_sync(0xffffffffu, unsigned(b0 * b0 + b1 * b1)));
-          const int sAB = int(__reduce_add_sync(0xffffffffu, unsigned(a0 * b0 + a1 * b1)));
-          const int score = sumAA - 2 * sAB + sBB - (sumA * sumA - 2 * sumA * sB + sB * sB) / 64;
+          int score;
+          if constexpr (kOrb) {   // ORBDetector::Distance (extra/orb_detector.cc:399-410): 8 words, one per lane
+            const unsigned bits = lane < 8 ? unsigned(__popc(qword ^ __ldg(cur_desc + size_t(bidx) * 8 + lane))) : 0u;
+            score = int(__reduce_add_sync(0xffffffffu, bits));
+            (void)bcx; (void)bcy; (void)bcl;
+          } else {
+            const int Wc = G.w[bcl];
+            const int py = lane >> 2, pxx = (lane & 3) * 2;
+            const uint8_t* __restrict__ cp = cur.pyr + G.off[bcl] + size_t(bcy - half + py) * Wc + (bcx - half + pxx);
+            const int b0 = __ldg(cp), b1 = __ldg(cp + 1);
+            const int a0 = s_patch_w[py * 8 + pxx], a1 = s_patch_w[py * 8 + pxx + 1];
+            const int sB = int(__reduce_add_sync(0xffffffffu, unsigned(b0 + b1)));
+            const int sBB = int(__reduce_add_sync(0xffffffffu, unsigned(b0 * b0 + b1 * b1)));
+            const int sAB = int(__reduce_add_sync(0xffffffffu, unsigned(a0 * b0 + a1 * b1)));
+            score = sumAA - 2 * sAB + sBB - (sumA * sumA - 2 * sumA * sB + sB * sB) / 64;
+          }
           const unsigned long long key = (static_cast<unsigned long long>(uint32_t(score)) << 32) | uint32_t(bidx);
           if (key < best_key) best_key = key;
         }
@@ -363,6 +382,21 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
   const SearchCandDev& C = cands[ci];
   const FrameDev cur = frames[C.cur_index];
   search_one(C, cur, out + ci, A.g, A.dp, s_bp[warp], s_patch[warp]);
+}
+
+// Matcher::SearchPoint with Config::UseORB(): one current frame, its corner descriptors in cur_desc (8 words per corner),
+// the candidates' feature descriptors in q_desc (8 words per candidate).
+__global__ void __launch_bounds__(SE_THREADS) search_points_orb_kernel(const SearchCandDev* __restrict__ cands,
+                                                                       const FrameDev cur, sdvlb_match* __restrict__ out,
+                                                                       const __grid_constant__ SearchArgs A,
+                                                                       const uint32_t* __restrict__ q_desc,
+                                                                       const uint32_t* __restrict__ cur_desc) {
+  __shared__ uint8_t s_bp[SE_WARPS][104];
+  __shared__ uint8_t s_patch[SE_WARPS][64];
+  const int warp = threadIdx.x >> 5;
+  const int ci = blockIdx.x * SE_WARPS + warp;
+  if (ci >= A.n) return;
+  search_one<true>(cands[ci], cur, out + ci, A.g, A.dp, s_bp[warp], s_patch[warp], q_desc + size_t(ci) * 8, cur_desc);
 }
 
 // Resident sequences: blockIdx.y = sequence of the step; candidates, their count and the matches live in the
@@ -576,6 +610,19 @@ cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const Frame
   A.n = n;
   sdvlb_common_carveout(search_points_kernel);
   search_points_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, d_frames, d_out, A);
+  return cudaGetLastError();
+}
+
+cudaError_t sdvlb_launch_search_orb(const SearchCandDev* d_cands, int n, const FrameDev& cur, sdvlb_match* d_out,
+                                    const PyrGeom& g, const DevParams& dp, const uint32_t* d_qdesc,
+                                    const uint32_t* d_curdesc, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  SearchArgs A;
+  A.g = g;
+  A.dp = dp;
+  A.n = n;
+  sdvlb_common_carveout(search_points_orb_kernel);
+  search_points_orb_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, cur, d_out, A, d_qdesc, d_curdesc);
   return cudaGetLastError();
 }
 
