@@ -169,6 +169,57 @@ int orc_search_points(const sdvlb_params* P, const sdvlb_camera* cam_, const uin
   return 0;
 }
 
+// SDVL::Relocalize's body for one keyframe (sdvl.cc:209-237): ComputePose(kf, cur, fast = true) from the keyframe's
+// pose, the GetError() gate, FeatureAlign::Reproject(cur, kf, kf, reloc = true).  feats / pos3 / levels: the keyframe's
+// features with their fixed points.  out[0] = matches (-1 when the error gate rejected the keyframe), out[1] =
+// attempts, out[2] = features the current frame gained, out[3] = sum of the points' Score() afterwards.
+int orc_relocalize(const sdvlb_params* P, const sdvlb_camera* cam_, const uint8_t* kf_img, const uint8_t* cur_img, int w,
+                   int h, const sdvlb_align_feat* feats, const double* pos3, const int32_t* levels, int n,
+                   const double T_kf[7], double T_out[7], double* error, int32_t out[4]) {
+  Camera cam = CamFrom(cam_);
+  auto kf = MakeFrame(*P, &cam, kf_img, w, h, false, 0);
+  auto cur = MakeFrame(*P, &cam, cur_img, w, h, true, 1);
+  kf->pose = SE3::FromArray(T_kf);
+  cur->pose = kf->pose;
+  const V3 C = kf->GetWorldPosition();
+  std::vector<std::shared_ptr<Point>> pts;
+  for (int i = 0; i < n; i++) {
+    auto ft = std::make_shared<Feature>();
+    ft->frame = kf;
+    ft->p2d.x = feats[i].px[0]; ft->p2d.y = feats[i].px[1];
+    ft->v = V3(feats[i].v[0], feats[i].v[1], feats[i].v[2]);
+    ft->level = levels[i];
+    auto pt = std::make_shared<Point>();
+    pt->id = i;
+    pt->fixed = true;
+    pt->p3d = V3(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2]);
+    pt->rho = 1.0 / (pt->p3d - C).norm();
+    pt->sigma2 = (0.05 * pt->rho) * (0.05 * pt->rho);
+    pt->feature = ft;
+    ft->point = pt;
+    kf->features.push_back(ft);
+    pts.push_back(pt);
+  }
+  ImageAlign ia(*P);
+  ia.ComputePose(kf, cur, true);
+  *error = ia.GetError();
+  cur->pose.ToArray(T_out);
+  out[0] = -1; out[1] = 0; out[2] = 0; out[3] = 0;
+  if (!(ia.GetError() >= 0.001)) {
+    GlibcRand rng;
+    std::vector<std::shared_ptr<Point>> trash;
+    FeatureAlign fa(*P, &cam, P->max_matches, &rng, &trash);
+    fa.Reproject(cur, kf, true);
+    out[0] = fa.GetMatches();
+    out[1] = fa.GetAttempts();
+  }
+  out[2] = int(cur->features.size());
+  for (auto& p : pts) { out[3] += p->n_successful; p->feature = nullptr; }
+  kf->features.clear();
+  cur->features.clear();
+  return 0;
+}
+
 // ---- primitives exposed for known-answer tests -------------------------------------------------
 void orc_se3_exp(const double u[6], double T[7]) { SE3::Exp(u).ToArray(T); }
 void orc_se3_log(const double T[7], double u[6]) { SE3::Log(SE3::FromArray(T), u); }

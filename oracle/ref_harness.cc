@@ -572,6 +572,53 @@ int ref_init_candidates(const sdvlb_params* P, const sdvlb_camera* cam_, const u
   return rc;
 }
 
+// SDVL::Relocalize's body for one keyframe (sdvl.cc:209-237) with the reference's own ImageAlign (fast = true) and
+// FeatureAlign::Reproject (reloc = true); contract of orc_relocalize.
+int ref_relocalize(const sdvlb_params* P, const sdvlb_camera* cam_, const uint8_t* kf_img, const uint8_t* cur_img, int w,
+                   int h, const sdvlb_align_feat* feats, const double* pos3, const int32_t* levels, int n,
+                   const double T_kf[7], double T_out[7], double* error, int32_t out[4]) {
+  Quiet q;
+  Configure(P, cam_);
+  sdvl::Camera cam;
+  sdvl::ORBDetector orb;
+  auto kf = MakeFrame(&cam, &orb, kf_img, w, h, false, 0);
+  auto cur = MakeFrame(&cam, &orb, cur_img, w, h, true, 1);
+  kf->SetPose(ToSE3(T_kf));
+  cur->SetPose(kf->GetPose());                                   // sdvl.cc:211
+  const Eigen::Vector3d C = kf->GetWorldPosition();
+  std::vector<shared_ptr<sdvl::Point>> pts;
+  for (int i = 0; i < n; i++) {
+    auto ft = std::make_shared<sdvl::Feature>(kf, nullptr, Eigen::Vector2d(feats[i].px[0], feats[i].px[1]),
+                                              Eigen::Vector3d(feats[i].v[0], feats[i].v[1], feats[i].v[2]), levels[i]);
+    auto pt = FixedPoint(ft, Eigen::Vector3d(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2]));
+    pt->id_ = i;
+    pt->rho_ = 1.0 / (pt->p3d_ - C).norm();
+    pt->sigma2_ = (0.05 * pt->rho_) * (0.05 * pt->rho_);
+    ft->SetPoint(pt);
+    kf->AddFeature(ft);
+    pts.push_back(pt);
+  }
+  sdvl::ImageAlign ia;
+  ia.ComputePose(kf, cur, true);                                 // sdvl.cc:217
+  *error = ia.GetError();
+  FromSE3(cur->GetPose(), T_out);
+  out[0] = -1; out[1] = 0; out[2] = 0; out[3] = 0;
+  if (!(ia.GetError() >= 0.001)) {                               // sdvl.cc:221-222
+    srand(1);
+    sdvl::Map map;
+    sdvl::FeatureAlign fa(&map, &cam, Config::MaxMatches());
+    fa.Reproject(cur, kf, kf, true);                             // sdvl.cc:225
+    out[0] = fa.GetMatches();
+    out[1] = fa.GetAttempts();
+  }
+  out[2] = cur->GetNumFeatures();
+  for (auto& p : pts) { out[3] += p->Score(); p->feature_ = nullptr; }
+  for (auto& f : kf->GetFeatures()) f->SetPoint(nullptr);
+  kf->RemoveFeatures();
+  cur->RemoveFeatures();
+  return 0;
+}
+
 // ---- ORB descriptor mode ------------------------------------------------------------------------------------------
 void ref_set_orb(int on) { g_use_orb = on != 0; }
 // ORBDetector::GetDescriptor / GetOrientation (extra/orb_detector.cc:350-437) at n positions (x, y, level).

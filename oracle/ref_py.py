@@ -208,6 +208,23 @@ def pose_refine(params, cam, obs, T, seed=1, mode=0):
     return obs, T
 
 
+def relocalize(params, cam, kf_img, cur_img, feats, pos3, levels, T_kf):
+    """SDVL::Relocalize's body for one keyframe: (pose after the fast ImageAlign, GetError(), [matches (-1 = rejected by
+    the error gate), attempts, features gained by the current frame, sum of the points' scores])."""
+    kf_img = np.ascontiguousarray(kf_img)
+    cur_img = np.ascontiguousarray(cur_img)
+    h, w = kf_img.shape
+    feats = np.ascontiguousarray(feats)
+    pos3 = np.ascontiguousarray(pos3, np.float64)
+    levels = np.ascontiguousarray(levels, np.int32)
+    T_kf = np.ascontiguousarray(T_kf, np.float64)
+    T_out, err, out = np.zeros(7), C.c_double(0), np.zeros(4, np.int32)
+    rc = lib().ref_relocalize(C.byref(params), C.byref(cam), ptr(kf_img), ptr(cur_img), w, h, ptr(feats), ptr(pos3),
+                             ptr(levels), feats.shape[0], ptr(T_kf), ptr(T_out), C.byref(err), ptr(out))
+    assert rc == 0
+    return T_out, err.value, out
+
+
 class Tracker:
     def __init__(self, params, cam, plane, max_points, kf_every):
         plane = np.ascontiguousarray(plane, np.float64)

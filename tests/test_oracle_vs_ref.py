@@ -425,10 +425,31 @@ def test_init_candidates_vs_reference(O, sw, scenes, abi, name, seed):
     assert np.allclose(got["depth"], exp["depth"][ok], rtol=1e-12, atol=0)
 
 
+# ------------------------------------------------------------------------------------------------ relocalisation
+@needs_ref
+@pytest.mark.parametrize("name,seed,gap", [("C2", 0, 1), ("C2", 0, 12), ("C3", 5, 2), ("C3", 5, 25)])
+def test_relocalize_vs_reference(O, sw, scenes, name, seed, gap):
+    """SDVL::Relocalize's body for one keyframe: ImageAlign::ComputePose(fast = true) from the keyframe's pose (the
+    early exit after the coarsest level when its error is large), the GetError() gate, and
+    FeatureAlign::Reproject(reloc = true), which must neither promote points nor add features to the frame."""
+    with _both(O, True):
+        cfg, poses, imgs, pts = _scene(O, sw, scenes, name, seed, gap + 1, cfg_feats(name))
+        P, cam = cfg["params"], cfg["cam"]
+        feats = scenes.align_feats(pts, poses[0])
+        a = O.relocalize(P, cam, imgs[0], imgs[gap], feats, pts["pos"], pts["level"], poses[0])
+        b = R.relocalize(P, cam, imgs[0], imgs[gap], feats, pts["pos"], pts["level"], poses[0])
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2])
+    assert a[2][2] == 0 and a[2][3] == 0                     # reloc: no features created, no point promoted
+    if gap <= 2:
+        assert a[2][0] > 50 and a[1] < 0.001                 # a nearby frame relocalises against the keyframe
+    else:
+        assert a[2][0] == -1 or a[2][0] < a[2][1]            # a far one is rejected by the error gate or matches poorly
+
+
 # ------------------------------------------------------------------------------------------------ whole trajectories
 @needs_ref
 @pytest.mark.parametrize("strict", [True, False])
-@pytest.mark.parametrize("name,seed,n", [("C2", 9, 45), ("C1", 3, 30), ("C3", 5, 45)])
+@pytest.mark.parametrize("name,seed,n", [("C2", 9, 45), ("C1", 3, 30), ("C3", 5, 45), ("C5", 1, 12)])
 def test_trajectory_vs_reference(O, sw, name, seed, n, strict):
     """The reference's ImageAlign + FeatureAlign::Reproject + OptimizePose + motion model + Map::NeedKeyframe /
     EmptyTrash driven frame after frame (oracle/ref_harness.cc) against oracle/tracker.cc, same seeded map: per-frame
@@ -444,7 +465,7 @@ def test_trajectory_vs_reference(O, sw, name, seed, n, strict):
         er, sr, _ = t.run(imgs, poses)
         t.close()
     assert np.array_equal(so[:, STAT_COLS], sr[:, STAT_COLS])
-    assert so[:, 7].sum() >= 2 and so[1:, 1].mean() > 60       # keyframes were inserted, points were matched
+    assert so[:, 7].sum() >= (2 if n >= 30 else 1) and so[1:, 1].mean() > 60   # keyframes were inserted, points were matched
     if strict:
         assert np.array_equal(eo, er)
     else:
