@@ -209,6 +209,53 @@ def cpu_impl():
     return oracle_py, "port", "CPU oracle (restatement of the reference path)"
 
 
+def opencv_sanity(cfg, sw):
+    """the two third-party image operations of the CPU arm are the oracle's restatements of
+    cv::pyrDown / cv::FAST (OpenCV's C++ library is not installed); this times them next to the real OpenCV (python
+    cv2, one thread) on one frame of the workload, so the reader can see how much of the CPU arm's time per frame could
+    be owed to the restatement rather than to OpenCV.  cv2's FAST is timed on whole levels (one call per level): a
+    lower bound of the reference's 480 per-cell calls."""
+    try:
+        import cv2
+        from oracle import oracle_py as O
+        cv2.setNumThreads(1)
+        P = cfg["params"]
+        img = sw.render(cfg, sw.trajectory(cfg, 4242, 1), threads=1)[0]
+
+        def ms(fn, reps=5):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t0) / reps * 1e3
+
+        def cv_pyr():
+            pyr = [img]
+            for _ in range(1, P.pyramid_levels):
+                pyr.append(cv2.pyrDown(pyr[-1], dstsize=(pyr[-1].shape[1] // 2, pyr[-1].shape[0] // 2)))
+            return pyr
+
+        fd = cv2.FastFeatureDetector_create(threshold=P.fast_threshold, nonmaxSuppression=True)
+        levels = cv_pyr()[:P.max_fast_levels]
+        t_pyr_o = ms(lambda: O.pyramid(img, P.pyramid_levels))
+        return {"cv2_version": cv2.__version__, "cv2_pyrdown_ms_per_frame": ms(cv_pyr),
+                "cv2_fast_whole_levels_ms_per_frame": ms(lambda: [fd.detect(x) for x in levels]),
+                "restated_pyrdown_ms_per_frame": t_pyr_o,
+                "restated_fast_and_selection_ms_per_frame": ms(lambda: O.detect(P, img, P.num_features)) - t_pyr_o}
+    except Exception as e:   # noqa: BLE001 -- informational only
+        return {"unavailable": repr(e)}
+
+
+def opencv_sanity_subprocess(config):
+    """opencv_sanity in a fresh interpreter: cv2 is never imported into the process that holds the CUDA context."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--opencv-sanity", "--config", config],
+                           capture_output=True, text=True, timeout=120)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:   # noqa: BLE001 -- informational only
+        return {"unavailable": repr(e)}
+
+
 def _reference_worker(i, cfg_name, F, W, kf_every, start, q):
     """One process per host core: the reference keeps process-wide state (rand(), Frame::counter_, Config singleton),
     so sequences run in separate processes, as separate SDVL instances would."""
@@ -271,7 +318,8 @@ def run_reference(args, cfg, sw, rank, world):
                    "step": "one frame for each of the sequences (one per host core)"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": T, "kind": kind,
                          "sample": f"{T} sequences x {K} frames, one sequence per core; {what}",
-                         "frames_per_s_per_core": K * T / sum(r[2] for r in res) if sum(r[2] for r in res) > 0 else None},
+                         "frames_per_s_per_core": K * T / sum(r[2] for r in res) if sum(r[2] for r in res) > 0 else None,
+                         "opencv_sanity": opencv_sanity(cfg, sw)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "us_per_gn_iter_cpu": None, "gn_iters": gn if kind == "port" else None, "max_ate_mm_vs_gt": ate,
     }
@@ -289,6 +337,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host threads per GPU (0 = cores / ranks)")
     ap.add_argument("--kf-every", type=int, default=20)
     ap.add_argument("--config", default="C2")
+    ap.add_argument("--opencv-sanity", action="store_true", help="print the cv2-vs-restatement timings as JSON and exit")
     ap.add_argument("--sweep", default="", help="comma list of GROUPSxTHREADS to time (e2e only), e.g. 8x4,16x8")
     ap.add_argument("--prefetch", type=int, default=2, help="frame batches are built this many steps ahead")
     ap.add_argument("--sweep-cycles", action="store_true", help="print the in-kernel latency breakdown per sweep entry")
@@ -311,6 +360,9 @@ def main():
     sharding = importlib.import_module("slam_sdvl_b200.sharding")
     cfg = sw.config(args.config)
 
+    if args.opencv_sanity:
+        print(json.dumps(opencv_sanity(cfg, sw)), flush=True)
+        return
     if args.impl == "reference":
         run_reference(args, cfg, sw, rank, world)
         return
@@ -502,7 +554,7 @@ def main():
             tr.close()
         cpu_baseline = {"value": frames_cpu / t_cpu, "unit": "frames/s", "cores": 1, "kind": cpu_kind,
                         "sample": f"{ns} sequences x {F - 1} frames of the same workload, 1 thread; {cpu_what}",
-                        "host_cores_available": ncpu}
+                        "host_cores_available": ncpu, "opencv_sanity": opencv_sanity_subprocess(args.config)}
 
     if rank == 0:
         out = {
