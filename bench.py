@@ -540,7 +540,7 @@ def main():
 
     # ---- CPU baseline on one host core (rank 0, bounded sample)
     cpu_baseline = None
-    if rank == 0:
+    if rank == 0 and world == 1:   # N = 1 only: at N > 1 the host cores belong to the ranks' submission threads
         O, cpu_kind, cpu_what = cpu_impl()
         ns = min(S, 8)     # bounded sample: 8 sequences x (steps + warmup) frames, about 2 s of CPU work per 65 frames
         t_cpu, frames_cpu, gn_cpu = 0.0, 0, 0
