@@ -81,7 +81,11 @@ def test_corners_and_image_align_vs_reference(binding, sw, scenes, G, name, seed
 
 def test_search_point_vs_reference(binding, sw, scenes, abi, G):
     """Matcher::SearchPoint, fixed (circle) and epipolar (capsule) candidates: the reference's found / not-found /
-    unseen decisions and search levels, refined positions within 0.01 px."""
+    unseen decisions and search levels, refined positions within 0.01 px.  The fixture comes from the strict
+    (-ffp-contract=off) build; the reference's own code built with its default flags differs from that build by up to
+    0.0098 px on these candidates (the float LK stops on |update|^2 < 9e-4, so one more or one fewer iteration moves the
+    result by a few thousandths of a pixel), and the device agrees with the default-flag builds to 2e-5 px
+    (tests/test_gpu_parity.py): the 0.0098 px measured here is that compiler-flag spread of the reference itself."""
     cfg, poses, imgs = sw.sequence("C2", 0, 5)
     P = cfg["params"]
     ctx = binding.Context(P, cfg["cam"])
