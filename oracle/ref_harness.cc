@@ -619,6 +619,65 @@ int ref_relocalize(const sdvlb_params* P, const sdvlb_camera* cam_, const uint8_
   return 0;
 }
 
+// Map::AddConnectionsPoints (map.cc:560-617; private): the points seen from a connected keyframe are projected into the
+// new keyframe `cur_img`, searched with Matcher::SearchPoint and linked when found.  cands describe the points (init
+// feature in the connected keyframe, inverse depth or fixed position); out[i].status = SDVLB_MATCH_FOUND with the linked
+// feature's position / level when point i gained a feature in the new keyframe, SDVLB_MATCH_NOT_FOUND otherwise.
+int ref_add_connections_points(const sdvlb_params* P, const sdvlb_camera* cam_, const uint8_t* cur_img, const double T_cur[7],
+                               const uint8_t* kf_img, const double T_kf[7], int w, int h, const sdvlb_candidate* cands,
+                               int n, sdvlb_match* out) {
+  Quiet q;
+  Configure(P, cam_);
+  sdvl::Camera cam;
+  sdvl::ORBDetector orb;
+  auto kf = MakeFrame(&cam, &orb, kf_img, w, h, false, 0);
+  auto frame = MakeFrame(&cam, &orb, cur_img, w, h, true, 1);
+  kf->SetPose(ToSE3(T_kf));
+  frame->SetPose(ToSE3(T_cur));
+  kf->SetKeyframe();
+  frame->SetKeyframe();
+  std::vector<shared_ptr<sdvl::Point>> pts;
+  for (int i = 0; i < n; i++) {
+    const sdvlb_candidate& c = cands[i];
+    auto ft = std::make_shared<sdvl::Feature>(kf, nullptr, Eigen::Vector2d(c.ref_px[0], c.ref_px[1]),
+                                              Eigen::Vector3d(c.ref_v[0], c.ref_v[1], c.ref_v[2]), c.ref_level);
+    auto pt = std::make_shared<sdvl::Point>();
+    pt->id_ = i;
+    pt->feature_ = ft;
+    pt->a_ = 10; pt->b_ = 10; pt->z_range_ = 6; pt->cos_alpha_ = 1; pt->last_distance_ = 1.0 / c.idepth;
+    pt->rho_ = c.idepth;
+    pt->sigma2_ = c.idepth_std * c.idepth_std;
+    if (c.flags & SDVLB_CAND_FIXED) { pt->fixed_ = true; pt->p3d_ = Eigen::Vector3d(c.pos[0], c.pos[1], c.pos[2]); }
+    pt->AddFeature(ft);
+    ft->SetPoint(pt);
+    kf->AddFeature(ft);
+    pts.push_back(pt);
+    std::memset(&out[i], 0, sizeof(out[i]));
+    out[i].status = SDVLB_MATCH_NOT_FOUND;
+    out[i].zmssd = -1;
+  }
+  frame->AddConnection(std::make_pair(kf, n));
+  sdvl::Map map;
+  map.AddConnectionsPoints(frame);
+  int linked = 0;
+  for (auto& f : frame->GetFeatures()) {
+    const auto pt = f->GetPoint();
+    if (!pt || pt->GetID() < 0 || pt->GetID() >= n || pts[pt->GetID()] != pt) return -9;
+    sdvlb_match& o = out[pt->GetID()];
+    if (o.status == SDVLB_MATCH_FOUND) return -10;            // a point linked twice
+    o.status = SDVLB_MATCH_FOUND;
+    o.px[0] = f->GetPosition()(0); o.px[1] = f->GetPosition()(1);
+    o.level = f->GetLevel();
+    if (pt->GetFeatures().front() != f) return -11;           // Point::AddFeature pushes to the front (point.h:100-102)
+    linked++;
+  }
+  for (auto& p : pts) { for (auto& f : p->GetFeatures()) f->SetPoint(nullptr); p->GetFeatures().clear(); p->feature_ = nullptr; }
+  frame->connections_.clear();
+  frame->RemoveFeatures();
+  kf->RemoveFeatures();
+  return linked;
+}
+
 // ---- ORB descriptor mode ------------------------------------------------------------------------------------------
 void ref_set_orb(int on) { g_use_orb = on != 0; }
 // ORBDetector::GetDescriptor / GetOrientation (extra/orb_detector.cc:350-437) at n positions (x, y, level).

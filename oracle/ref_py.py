@@ -169,6 +169,22 @@ def init_candidates(params, cam, new_img, T_new, old_img, T_old, depth_mean, map
                 listed=listed.value)
 
 
+def add_connections_points(params, cam, cur_img, T_cur, kf_img, T_kf, cands):
+    """The reference's Map::AddConnectionsPoints: new keyframe `cur_img`, one connected keyframe `kf_img` whose points
+    `cands` (abi.CANDIDATE_DT) describe.  Returns abi.MATCH_DT records: FOUND + px + level for the points it linked."""
+    cur_img = np.ascontiguousarray(cur_img)
+    kf_img = np.ascontiguousarray(kf_img)
+    h, w = cur_img.shape
+    cands = np.ascontiguousarray(cands)
+    out = np.zeros(cands.shape[0], abi.MATCH_DT)
+    T_cur = np.ascontiguousarray(T_cur, np.float64)
+    T_kf = np.ascontiguousarray(T_kf, np.float64)
+    rc = lib().ref_add_connections_points(C.byref(params), C.byref(cam), ptr(cur_img), ptr(T_cur), ptr(kf_img), ptr(T_kf),
+                                          w, h, ptr(cands), cands.shape[0], ptr(out))
+    assert rc >= 0, rc
+    return out
+
+
 def align_patch(params, img, border_patch, px):
     img = np.ascontiguousarray(img, np.uint8)
     bp = np.ascontiguousarray(border_patch, np.uint8)

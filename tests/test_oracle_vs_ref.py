@@ -425,6 +425,30 @@ def test_init_candidates_vs_reference(O, sw, scenes, abi, name, seed):
     assert np.allclose(got["depth"], exp["depth"][ok], rtol=1e-12, atol=0)
 
 
+@needs_ref
+@pytest.mark.parametrize("name,seed,fixed", [("C2", 2, True), ("C2", 2, False), ("C3", 1, True)])
+def test_add_connections_points_vs_reference(O, sw, scenes, abi, name, seed, fixed):
+    """Map::AddConnectionsPoints run by the reference (projection into the new keyframe, the patch_size margin,
+    SearchPoint, one new Feature per found point pushed to the front of the point's list) against the oracle's
+    SearchPoint with SDVLB_CAND_PROJECT, which is how the device serves that loop."""
+    cfg, poses, imgs = sw.sequence(name, seed, 10)
+    P, cam = cfg["params"], cfg["cam"]
+    with _both(O, True):
+        xyl, _ = O.detect(P, imgs[0], P.num_features)
+        pts = scenes.seed_points(cfg, xyl, poses[0], max_points=300, one_per_cell=False)
+        c = scenes.candidates(pts, poses[0], 0, fixed=fixed, project=True, std_frac=0.05 if fixed else 0.02)
+        exp = O.search_points(P, cam, imgs[9], poses[9], [imgs[0]], c)
+        got = R.add_connections_points(P, cam, imgs[9], poses[9], imgs[0], poses[0], c)
+    f = exp["status"] == abi.MATCH_FOUND
+    assert f.sum() > 60 and (~f).sum() > 10
+    assert np.array_equal(got["status"] == abi.MATCH_FOUND, f)
+    assert np.array_equal(got["level"][f], exp["level"][f])
+    if fixed:
+        assert np.array_equal(got["px"][f], exp["px"][f])
+    else:   # the reference recomputes the position from the inverse depth: the projection differs in the last bits
+        assert np.abs(got["px"][f] - exp["px"][f]).max() < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ relocalisation
 @needs_ref
 @pytest.mark.parametrize("name,seed,gap", [("C2", 0, 1), ("C2", 0, 12), ("C3", 5, 2), ("C3", 5, 25)])
