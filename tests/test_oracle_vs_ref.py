@@ -221,6 +221,44 @@ def test_search_point_vs_reference(O, sw, scenes, abi, name, seed, strict):
 
 
 @needs_ref
+def test_search_point_degenerate_candidates_vs_reference(O, sw, scenes, abi):
+    """Edge cases of Matcher::SearchPoint where a restatement could drift from the code: zero depth uncertainty on an
+    epipolar candidate (zero-length segment: Eigen's guarded normalize, u = 0/0), a depth range reaching behind the
+    camera, the 1e-8 inverse-depth clamp, reference patches that fail the margin test at their level, points projected
+    outside the image, and a camera looking away from the points."""
+    cfg, poses, imgs = sw.sequence("C2", 0, 4)
+    P, cam = cfg["params"], cfg["cam"]
+    with _both(O, True):
+        xyl, _ = O.detect(P, imgs[0], P.num_features)
+        pts = scenes.seed_points(cfg, xyl, poses[0], max_points=240, one_per_cell=False, margin=0)
+        n = len(pts["px"])
+        c = scenes.candidates(pts, poses[0], 0, fixed=False, project=False, std_frac=0.05)
+        k = np.arange(n) % 6
+        c["idepth_std"][k == 0] = 0.0                        # pxa == pxb
+        c["idepth_std"][k == 1] = 10.0 * c["idepth"][k == 1]  # idepth - 2 std < 0: clamp to 1e-8, far point
+        c["idepth"][k == 2] *= 40.0                          # 2.5 % of the true depth: projects far from the feature
+        c["flags"][k == 3] |= abi.CAND_FIXED                 # fixed, searched around a prediction that is off
+        c["px"] = pts["px"] + np.where((k == 3)[:, None], 4.0, 0.0)
+        c["flags"][k == 4] |= abi.CAND_PROJECT
+        c["pos"][k == 4] *= np.array([1.0, 1.0, -1.0])       # mirrored through the plane: other side of the camera? no, below it
+        c["pos"][k == 5] += np.array([30.0, 0.0, 0.0])       # far outside the image
+        c["flags"][k == 5] |= abi.CAND_PROJECT
+        res = []
+        for T in (poses[3], poses[0]):
+            res.append((O.search_points(P, cam, imgs[3], T, [imgs[0]], c), R.search_points(P, cam, imgs[3], T, [imgs[0]], c)))
+        # a camera turned away from the scene: every projection is behind it
+        Tb = poses[3].copy()
+        Tb[:4] = [0.0, 1.0, 0.0, 0.0]   # half a turn about x on top of nothing: looks along -z
+        res.append((O.search_points(P, cam, imgs[3], Tb, [imgs[0]], c), R.search_points(P, cam, imgs[3], Tb, [imgs[0]], c)))
+    seen = np.zeros(3, int)
+    for mo, mr in res:
+        assert np.array_equal(mo["status"], mr["status"])
+        assert np.array_equal(mo["level"], mr["level"]) and np.array_equal(mo["px"], mr["px"])
+        seen += np.bincount(mo["status"], minlength=3)[:3]
+    assert (seen > 0).all(), seen      # unseen, not found and found all occurred
+
+
+@needs_ref
 def test_align_patch_identical(O, abi, seq_c2):
     """Matcher::AlignPatch alone (private in the reference, reached through the harness): convergence flag and position,
     including starts that run out of the image (the `break` of matcher.cc:402-403)."""
