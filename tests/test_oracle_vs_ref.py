@@ -189,6 +189,41 @@ def test_image_align_iteration_budgets_and_empty(O, sw, scenes):
         assert nto == ntr == 0 and np.array_equal(To, Tr) and np.array_equal(To, poses[1])
 
 
+@needs_ref
+def test_image_align_degenerate_inputs_vs_reference(O, sw, scenes):
+    """Edge cases of ImageAlign: a textureless current image (H singular: Eigen's LDLT with its pseudo-inverse of D),
+    a single feature (rank-deficient H), every feature without a point, a prior so far off that nothing projects into
+    the image (n_meas = 0 sets the sticky stop_ flag, image_align.cc:98-99), and features on the image border."""
+    with _both(O, True):
+        cfg, poses, imgs, pts = _scene(O, sw, scenes, "C2", 3, 3, 200)
+        P, cam = cfg["params"], cfg["cam"]
+        feats = scenes.align_feats(pts, poses[0])
+        flat = np.full_like(imgs[0], 127)
+        far = poses[0].copy()
+        far[4:] += [5.0, -3.0, 0.5]
+        none = feats.copy()
+        none["valid"] = 0
+        edge = feats.copy()
+        edge["px"][::3] = [2.0, 3.0]
+        cases = [("flat current image", imgs[0], flat, feats, poses[0]),
+                 ("flat reference image", flat, imgs[1], feats, poses[0]),
+                 ("single feature", imgs[0], imgs[1], feats[:1], poses[0]),
+                 ("two features", imgs[0], imgs[1], feats[:2], poses[0]),
+                 ("no feature has a point", imgs[0], imgs[1], none, poses[0]),
+                 ("prior far away", imgs[0], imgs[2], feats, far),
+                 ("features on the border", imgs[0], imgs[1], edge, poses[0])]
+        for what, ref_img, cur_img, f, prior in cases:
+            pos = pts["pos"][:len(f)]
+            To, nto, eo, tro = O.image_align(P, cam, ref_img, cur_img, f, pos, poses[0], prior)
+            Tr, ntr, er, trr = R.image_align(P, cam, ref_img, cur_img, f, pos, poses[0], prior)
+            assert len(tro) == len(trr) and nto == ntr, what
+            for k in ("level", "iter", "n_meas", "flags"):
+                assert np.array_equal(tro[k], trr[k]), (what, k)
+            for k in ("T_in", "H", "b", "x", "chi2"):
+                assert np.array_equal(tro[k], trr[k], equal_nan=True), (what, k)
+            assert np.array_equal(To, Tr, equal_nan=True) and (eo == er or (np.isnan(eo) and np.isnan(er))), what
+
+
 # ------------------------------------------------------------------------------------------------ Matcher
 @needs_ref
 @pytest.mark.parametrize("strict", [True, False])
@@ -307,7 +342,8 @@ def _pose_obs(sw, abi, n, n_bad, seed):
 
 
 @needs_ref
-@pytest.mark.parametrize("n,n_bad,seed", [(80, 9, 1), (200, 40, 2), (30, 12, 3), (6, 1, 4), (4, 0, 5)])
+@pytest.mark.parametrize("n,n_bad,seed", [(80, 9, 1), (200, 40, 2), (30, 12, 3), (6, 1, 4), (4, 0, 5), (1, 0, 6), (2, 1, 7),
+                                            (3, 0, 8), (12, 11, 9)])
 def test_select_inliers_and_optimize_pose_vs_reference(O, sw, abi, n, n_bad, seed):
     """FeatureAlign::SelectInliers (RANSAC on glibc rand(): same draws, same hypotheses, same supporters) and
     OptimizePose (MAD-scaled Tukey IRLS, RescueOutliers, RemoveOutliers) on noisy observations with gross outliers,
