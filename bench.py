@@ -297,7 +297,10 @@ def run_reference(args, cfg, sw, rank, world):
     procs = [ctx.Process(target=_reference_worker, args=(i, args.config, F, W, args.kf_every, start, q)) for i in range(T)]
     for p in procs:
         p.start()
-    start.wait()                      # every worker has rendered its sequence and run its warm-up frames
+    try:
+        start.wait()                  # every worker has rendered its sequence and run its warm-up frames
+    except Exception:                 # a worker failed before the barrier (it aborts it): its message is in the queue
+        pass
     t0 = time.perf_counter()
     res = [q.get() for _ in range(T)]
     for p in procs:
