@@ -776,6 +776,13 @@ static void SeedKeyframe(RefTracker* t, const shared_ptr<sdvl::Frame>& f, const 
     const int cx = int(px(0) / cell), cy = int(px(1) / cell);
     if (occupied[size_t(cy) * gw + cx]) continue;
     auto ft = std::make_shared<sdvl::Feature>(f, px, c(2));
+    if (g_use_orb) {   // the descriptor an init feature gets at its keyframe (frame.cc:148-161, map.cc:319-323)
+      const Eigen::Vector2i lp(c(0), c(1));
+      if (!t->orb.IsInsideLimits(lvl, lp)) continue;
+      std::vector<uchar> d(32);
+      t->orb.GetDescriptor(lvl, lp, &d);
+      ft->SetDescriptor(d);
+    }
     const Eigen::Vector3d dir = Rwc * ft->GetVector();
     const double denom = nrm.dot(dir);
     if (std::fabs(denom) < 1e-9) continue;

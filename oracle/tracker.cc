@@ -43,6 +43,12 @@ void Tracker::SeedKeyframe(const std::shared_ptr<Frame>& f, const SE3& gt_pose) 
     const int cx = int(px.x / P_.cell_size), cy = int(px.y / P_.cell_size);
     if (occupied[size_t(cy) * gw + cx]) continue;
     std::shared_ptr<Feature> ft = MakeFeature(f, px, c.level);
+    if (UseOrb()) {   // the descriptor an init feature gets at its keyframe (frame.cc:148-161, map.cc:319-323)
+      static const OrbDetector det;
+      if (!det.IsInsideLimits(lvl, c.x, c.y)) continue;
+      ft->descriptor.resize(32);
+      det.GetDescriptor(lvl, c.x, c.y, ft->descriptor.data());
+    }
     const V3 dir(Rwc.m[0][0] * ft->v.x + Rwc.m[0][1] * ft->v.y + Rwc.m[0][2] * ft->v.z,
                  Rwc.m[1][0] * ft->v.x + Rwc.m[1][1] * ft->v.y + Rwc.m[1][2] * ft->v.z,
                  Rwc.m[2][0] * ft->v.x + Rwc.m[2][1] * ft->v.y + Rwc.m[2][2] * ft->v.z);

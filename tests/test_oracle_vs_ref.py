@@ -419,6 +419,29 @@ def test_orb_mode_vs_reference(O, sw, scenes, abi, name, seed, strict):
             R.lib().ref_set_orb(0)
 
 
+@needs_ref
+@pytest.mark.parametrize("name,seed,n", [("C2", 9, 30), ("C3", 5, 30)])
+def test_orb_mode_trajectory_vs_reference(O, sw, name, seed, n):
+    """Whole sequences with Config::UseORB(): FAST with the ORB margin, init features carrying descriptors, every
+    SearchPoint of FeatureAlign::Reproject scored by descriptor distance -- reference code vs oracle, bit for bit."""
+    cfg, poses, imgs = sw.sequence(name, seed, n)
+    with _both(O, True):
+        O.lib().orc_set_orb(1)
+        R.lib().ref_set_orb(1)
+        try:
+            t = O.Tracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], 20)
+            eo, so, _ = t.run(imgs, poses)
+            t.close()
+            t = R.Tracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], 20)
+            er, sr, _ = t.run(imgs, poses)
+            t.close()
+        finally:
+            O.lib().orc_set_orb(0)
+            R.lib().ref_set_orb(0)
+    assert np.array_equal(so[:, STAT_COLS], sr[:, STAT_COLS]) and np.array_equal(eo, er)
+    assert so[1:, 1].mean() > 60 and sw.ate(er, poses) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ Map (mapping thread)
 @needs_ref
 def test_update_candidates_vs_reference(O, sw, scenes, abi):
