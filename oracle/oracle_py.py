@@ -69,9 +69,9 @@ def strict():
 def pyramid(img, levels):
     h, w = img.shape
     img = np.ascontiguousarray(img)
-    n = lib().orc_pyramid(ptr(img), w, h, levels, None)
-    out = np.zeros(n, np.uint8)
-    lib().orc_pyramid(ptr(img), w, h, levels, ptr(out))
+    n = sum((w >> l) * (h >> l) for l in range(levels))
+    out = np.empty(n, np.uint8)
+    assert lib().orc_pyramid(ptr(img), w, h, levels, ptr(out)) == n
     res, off = [], 0
     for _ in range(levels):
         res.append(out[off:off + w * h].reshape(h, w))

@@ -77,9 +77,9 @@ def read_config(filename=None):
 def pyramid(img, levels):
     h, w = img.shape
     img = np.ascontiguousarray(img)
-    n = lib().ref_pyramid(ptr(img), w, h, levels, None)
-    out = np.zeros(n, np.uint8)
-    lib().ref_pyramid(ptr(img), w, h, levels, ptr(out))
+    n = sum((w >> l) * (h >> l) for l in range(levels))
+    out = np.empty(n, np.uint8)
+    assert lib().ref_pyramid(ptr(img), w, h, levels, ptr(out)) == n
     res, off = [], 0
     for _ in range(levels):
         res.append(out[off:off + w * h].reshape(h, w))
