@@ -545,7 +545,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1:   # N = 1 only: at N > 1 the host cores belong to the ranks' submission threads
         O, cpu_kind, cpu_what = cpu_impl()
-        ns = min(S, 8)     # bounded sample: 8 sequences x (steps + warmup) frames, about 2 s of CPU work per 65 frames
+        ns = min(S, 32)    # bounded sample: 32 sequences x (steps + warmup) frames, about 5-10 s of CPU work
         t_cpu, frames_cpu, gn_cpu = 0.0, 0, 0
         for s in range(ns):
             tr = O.Tracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], args.kf_every)
