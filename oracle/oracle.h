@@ -324,6 +324,7 @@ struct TrackStats { int n_tracked = 0, matches = 0, attempts = 0, inliers = 0, o
 class Tracker {
  public:
   Tracker(const sdvlb_params& P, const Camera& cam, const SeedPlane& plane, int max_points, int kf_every);
+  ~Tracker();   // breaks the Point <-> init Feature -> keyframe cycles of every point it created
   // First frame: pose given (ground truth), becomes keyframe and seeds the map.
   // Later frames: motion model prior -> ImageAlign -> FeatureAlign -> motion model update.
   // gt_pose is used only to place seeded points when this frame becomes a keyframe.
@@ -342,6 +343,7 @@ class Tracker {
   std::shared_ptr<Frame> last_frame_, last_kf_;
   Vec6 vel_;
   int frame_counter_ = 0, point_counter_ = 0, last_matches_ = 0;
+  std::vector<std::weak_ptr<Point>> all_points_;
 };
 
 }  // namespace oracle

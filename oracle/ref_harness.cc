@@ -746,6 +746,7 @@ struct RefTracker {
   double sec_total = 0;
   sdvlb_params P;
   sdvlb_camera K;
+  std::vector<std::weak_ptr<sdvl::Point>> all_points;   // to break the Point <-> init Feature cycles at destruction
 };
 
 static void SeedKeyframe(RefTracker* t, const shared_ptr<sdvl::Frame>& f, const sdvl::SE3& gt_pose) {
@@ -794,6 +795,7 @@ static void SeedKeyframe(RefTracker* t, const shared_ptr<sdvl::Frame>& f, const 
     pt->rho_ = 1.0 / depth;
     pt->sigma2_ = (0.05 * pt->rho_) * (0.05 * pt->rho_);
     ft->SetPoint(pt);
+    t->all_points.push_back(pt);
     f->AddFeature(ft);
     occupied[size_t(cy) * gw + cx] = 1;
     n_points++;
@@ -819,12 +821,13 @@ void* ref_tracker_create(const sdvlb_params* P, const sdvlb_camera* cam, const d
 }
 void ref_tracker_destroy(void* h) {
   RefTracker* t = static_cast<RefTracker*>(h);
-  // break the Frame <-> Feature <-> Point shared_ptr cycles of whatever is still alive
-  if (t->last_frame) {
-    for (auto& ft : t->last_frame->GetFeatures())
-      if (ft && ft->GetPoint()) { if (ft->GetPoint()->feature_) ft->GetPoint()->feature_->frame_ = nullptr; }
-    t->last_frame->RemoveFeatures();
-  }
+  // break the Point <-> init Feature -> keyframe shared_ptr cycles of every point this tracker created
+  for (auto& w : t->all_points)
+    if (auto p = w.lock()) p->feature_ = nullptr;
+  if (t->last_frame) t->last_frame->RemoveFeatures();
+  t->last_frame = nullptr;
+  t->last_kf = nullptr;
+  t->map.last_kf_ = nullptr;
   delete t;
 }
 int ref_tracker_step(void* h, const uint8_t* img, int w, int h_, const double gt_pose[7], double est_pose[7],

@@ -17,6 +17,12 @@ Tracker::Tracker(const sdvlb_params& P, const Camera& cam, const SeedPlane& plan
   for (int i = 0; i < 6; i++) vel_[i] = 0;
 }
 
+Tracker::~Tracker() {
+  for (auto& w : all_points_)
+    if (auto p = w.lock()) p->feature = nullptr;
+  if (last_frame_) last_frame_->features.clear();
+}
+
 void Tracker::SeedKeyframe(const std::shared_ptr<Frame>& f, const SE3& gt_pose) {
   f->is_keyframe = true;
   const int gw = int(std::ceil(cam_.width / P_.cell_size));
@@ -66,6 +72,7 @@ void Tracker::SeedKeyframe(const std::shared_ptr<Frame>& f, const SE3& gt_pose) 
     pt->sigma2 = (0.05 * pt->rho) * (0.05 * pt->rho);
     pt->feature = ft;
     ft->point = pt;
+    all_points_.push_back(pt);
     f->features.push_back(ft);
     occupied[size_t(cy) * gw + cx] = 1;
     n_points++;
