@@ -174,3 +174,33 @@ def test_product_rand_matches_glibc_and_libstdcxx(binding, abi):
         L.sdvlb_rand_seed(C.byref(r), 1)
         L.sdvlb_rand_shuffle(C.byref(r), abi.ptr(v), n)
         assert np.array_equal(v, expect)
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` (no GPU): one JSON line with the keys the driver reads, `impl: reference`, a
+    `cpu_baseline` describing the run and the e2e object with zero transfer bytes; non-zero ranks print nothing."""
+    import json
+    import subprocess
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    env.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "4", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "tracked_frames_per_sec" and d["unit"] == "frames/s"
+    assert d["steps"] == 4 and d["warmup"] == 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["value"] > 0 and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # under torchrun only rank 0 runs the arm
+    env["RANK"], env["WORLD_SIZE"] = "1", "2"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "4", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0 and r.stdout.strip() == ""
