@@ -238,8 +238,24 @@ def opencv_sanity(cfg, sw):
         fd = cv2.FastFeatureDetector_create(threshold=P.fast_threshold, nonmaxSuppression=True)
         levels = cv_pyr()[:P.max_fast_levels]
         t_pyr_o = ms(lambda: O.pyramid(img, P.pyramid_levels))
+        # the reference's own call pattern: one cv::FAST per 32 x 32 cell ROI (fast_detector.cc:81-95); the same number
+        # of calls on 7 x 7 ROIs (nothing to test) measures the per-call overhead, most of which is the python binding
+        m = 1 + P.patch_size // 2
+        rois, tiny = [], []
+        for im in levels:
+            H, W = im.shape
+            for i in range((H + P.cell_size - 1) // P.cell_size):
+                y0, y1 = max(m, P.cell_size * i), min(H - m, P.cell_size * (i + 1))
+                for j in range((W + P.cell_size - 1) // P.cell_size):
+                    x0, x1 = max(m, P.cell_size * j), min(W - m, P.cell_size * (j + 1))
+                    if y1 > y0 and x1 > x0:
+                        rois.append(im[y0:y1, x0:x1])
+                        tiny.append(im[y0:y0 + 7, x0:x0 + 7])
         return {"cv2_version": cv2.__version__, "cv2_pyrdown_ms_per_frame": ms(cv_pyr),
                 "cv2_fast_whole_levels_ms_per_frame": ms(lambda: [fd.detect(x) for x in levels]),
+                "cv2_fast_per_cell_ms_per_frame": ms(lambda: [fd.detect(r) for r in rois]),
+                "cv2_fast_per_cell_call_overhead_ms_per_frame": ms(lambda: [fd.detect(r) for r in tiny]),
+                "cells": len(rois),
                 "restated_pyrdown_ms_per_frame": t_pyr_o,
                 "restated_fast_and_selection_ms_per_frame": ms(lambda: O.detect(P, img, P.num_features)) - t_pyr_o}
     except Exception as e:   # noqa: BLE001 -- informational only
