@@ -354,6 +354,25 @@ int sdvlb_optimize_pose(sdvlb_ctx* ctx, sdvlb_pose_obs* obs, int n, double T_fra
  * plays the mapping thread's role (sdvlb_seq_add_points). */
 typedef struct sdvlb_seq sdvlb_seq;
 #define SDVLB_SEQ_KF_CAP 64   /* keyframes that may be referenced by live points of one sequence */
+#define SDVLB_SEQ_DEPTH 4     /* tracking submissions that may be in flight on one context (results are kept in a ring) */
+
+/* What the tracking thread decides by itself after a frame (SDVL::HandleFrame, sdvl.cc:93-120), evaluated by the
+ * FeatureAlign kernel so that the next frames can be queued without waiting for the host.  All zero (the default):
+ * every frame is adopted and nothing is ever held. */
+typedef struct sdvlb_seq_policy {
+  int32_t keyframe_rule;     /* 1: Map::NeedKeyframe (map.cc:170-188).  When it fires the result carries need_keyframe
+                                and the sequence is HELD: tracking steps already queued behind it skip the sequence
+                                (status SDVLB_SEQ_HELD, its frame is not consumed) until sdvlb_seq_add_points or
+                                sdvlb_seq_release answers. */
+  int32_t min_keyframe_its;  /* Config::MinKeyframeIts() */
+  double lost_ratio;         /* Config::LostRatio() */
+  int32_t tracking_quality;  /* 1: SDVL::CalcTrackingQuality (sdvl.cc:240-264, Config::MinMatches() = params.min_matches):
+                                a TRACKING_BAD frame is not adopted as the next alignment reference (sdvl.cc:99,119);
+                                after 3 lost frames the sequence is held for relocalisation (sdvl.cc:74-91). */
+  int32_t pad_;
+} sdvlb_seq_policy;
+enum { SDVLB_SEQ_TRACKED = 0, SDVLB_SEQ_HELD = 1, SDVLB_SEQ_IDLE = 2 };
+enum { SDVLB_TRACKING_GOOD = 0, SDVLB_TRACKING_INSUFFICIENT = 1, SDVLB_TRACKING_BAD = 2 };
 
 typedef struct sdvlb_seq_point {   /* a map point handed to the tracker with its observation in the current frame */
   double pos[3];       /* Point::GetPosition() */
@@ -387,7 +406,13 @@ typedef struct sdvlb_seq_result {
   int32_t n_points;    /* Frame::GetNumPoints() */
   int32_t gn_iters;    /* ImageAlign Gauss-Newton iterations */
   int32_t n_feats;     /* entries in feats */
-  const sdvlb_seq_feat* feats;             /* pinned host memory, valid until the sequence is submitted again */
+  const sdvlb_seq_feat* feats;             /* pinned host memory, valid until SDVLB_SEQ_DEPTH later submissions of
+                                              the context have been made */
+  int32_t status;      /* SDVLB_SEQ_TRACKED; _HELD: the sequence was on hold, the frame was not consumed (submit it
+                          again once the hold is answered); _IDLE: no track yet (no sdvlb_seq_reset) */
+  int32_t quality;     /* SDVLB_TRACKING_* (GOOD unless policy.tracking_quality) */
+  int32_t need_keyframe;   /* policy.keyframe_rule fired on this frame: the sequence is now held */
+  int32_t lost_frames; /* SDVL::lost_frames_ */
   int32_t kf_live[SDVLB_SEQ_KF_CAP];       /* live points per keyframe slot (see sdvlb_seq_add_points) */
   int32_t phase_cycles[8];                 /* latency breakdown of the FeatureAlign kernel for this sequence, SM cycles:
                                               cell ranks, SelectPoints, RANSAC hypotheses, RANSAC supporters, RANSAC
@@ -408,12 +433,21 @@ int sdvlb_seq_reset(sdvlb_ctx* ctx, sdvlb_seq* seq, const sdvlb_frame* frame, co
  * `kf` must stay alive until a result reports kf_live[slot] == 0.  Takes effect before the next tracked frame. */
 int sdvlb_seq_add_points(sdvlb_ctx* ctx, sdvlb_seq* seq, const sdvlb_frame* kf, const double T_kf[7],
                          const sdvlb_seq_point* pts, int n, int* kf_slot);
-/* One new frame for each of n sequences (frames built by sdvlb_frames_submit / sdvlb_frame_create with corners).
- * Asynchronous: _poll returns 1 when finished, _collect waits and fills n results in submission order.  One
- * submission in flight per context; a frame must stay alive until the sequence has tracked the next one. */
+/* Sets the sequence's policy; takes effect before the next tracked frame (queued like sdvlb_seq_add_points). */
+int sdvlb_seq_set_policy(sdvlb_ctx* ctx, sdvlb_seq* seq, const sdvlb_seq_policy* policy);
+/* Answers a hold without adding points (sdvlb_seq_add_points releases it too). */
+int sdvlb_seq_release(sdvlb_ctx* ctx, sdvlb_seq* seq);
+/* One new frame for each of n sequences (frames built by sdvlb_frames_submit / sdvlb_frame_create with corners): three
+ * launches on the context's tracking stream, chained with programmatic dependent launch.  Asynchronous, and up to
+ * SDVLB_SEQ_DEPTH submissions may be in flight: the frames of one sequence are serially dependent (sdvl.cc:93,119,
+ * 278-281), but that dependency lives in the sequence's device state, so frame k+1 can be queued while frame k is
+ * being tracked and the host's turnaround leaves the critical path.  _poll returns 1 when the OLDEST submission in
+ * flight has finished, _collect waits for it and fills its n results in submission order; _inflight returns how many
+ * are outstanding.  A frame must stay alive until the sequence has tracked (not skipped) the next one. */
 int sdvlb_seq_track_submit(sdvlb_ctx* ctx, sdvlb_seq* const* seqs, sdvlb_frame* const* frames, int n);
 int sdvlb_seq_track_poll(sdvlb_ctx* ctx);
 int sdvlb_seq_track_collect(sdvlb_ctx* ctx, sdvlb_seq_result* results);
+int sdvlb_seq_track_inflight(sdvlb_ctx* ctx);
 
 /* ---- depth-filter seeds: Map::UpdateCandidates (map.cc:397-498) -------------
  * The mapping thread's per-frame pass over its candidate points (SURVEY.md

@@ -67,7 +67,8 @@ EXPORTS = [
     "sdvlb_track_collect", "sdvlb_ctx_reserve_frames",
     "sdvlb_rand_seed", "sdvlb_rand_next", "sdvlb_rand_shuffle", "sdvlb_select_inliers", "sdvlb_optimize_pose",
     "sdvlb_seq_create", "sdvlb_seq_destroy", "sdvlb_seq_reset", "sdvlb_seq_add_points", "sdvlb_seq_track_submit",
-    "sdvlb_seq_track_poll", "sdvlb_seq_track_collect", "sdvlb_frame_filter_corners", "sdvlb_update_candidates",
+    "sdvlb_seq_track_poll", "sdvlb_seq_track_collect", "sdvlb_seq_track_inflight", "sdvlb_seq_set_policy",
+    "sdvlb_seq_release", "sdvlb_frame_filter_corners", "sdvlb_update_candidates",
     "sdvlb_ctx_set_distortion", "sdvlb_undistort",
     "sdvlb_ctx_set_orb", "sdvlb_frame_orb_descriptors", "sdvlb_search_points_orb",
 ]
@@ -256,7 +257,7 @@ _HLIB = None
 HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", "sdvlh_tracker_destroy",
                 "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_phases",
                 "sdvlh_tracker_ctx", "sdvlh_tracker_groups", "sdvlh_tracker_threads", "sdvlh_tracker_run",
-                "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles", "sdvlh_tracker_set_prefetch", "sdvlh_device_pose_refinement",
+                "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles", "sdvlh_tracker_set_prefetch", "sdvlh_tracker_set_depth",
                 "sdvlh_map_update_candidates", "sdvlh_map_init_candidates", "sdvlh_camera_undistort"]
 
 
@@ -434,6 +435,10 @@ class HostTracker:
 
     def set_prefetch(self, depth):
         load_host().sdvlh_tracker_set_prefetch(C.c_void_p(self.h), int(depth))
+
+    def set_depth(self, depth):
+        """Tracking submissions kept in flight per group (resident sequences), 1..SDVLB_SEQ_DEPTH."""
+        load_host().sdvlh_tracker_set_depth(C.c_void_p(self.h), int(depth))
 
     def post_cycles(self, reset=True):
         """Average SM cycles per tracked frame in the phases of the device-side FeatureAlign kernel."""

@@ -1,20 +1,39 @@
 // align.cu — K3: ImageAlign::ComputePose (image_align.cc:46-267) as ONE persistent kernel per call: all pyramid
-// levels and all Gauss-Newton iterations run on the device (one CTA per alignment job = per sequence), including the
+// levels and all Gauss-Newton iterations run on the device (one CTA per alignment = per sequence), including the
 // 6x6 LDLT solve, the SE3 update T <- T*Exp(-x) and the reference's accept/rollback logic.  No host round trip, no
-// atomics: per-feature partials go through shared memory and a fixed-order tree.
+// atomics: partial sums go through warp shuffles and one fixed-order pass over the warps' totals.
+//
+// Two entry kernels share the body (align_core): image_align_kernel (class API: features marshalled by the host,
+// AlignJobDev) and seq_align_kernel (resident sequences: the CTA first applies the mapping thread's commands, sets the
+// motion-model prior -- SDVL::SetMotionModel, sdvl.cc:278-281 -- and reads its features straight from the sequence's
+// feature list; what used to be a separate "prep" launch).
 //
 // Arithmetic mirrors the reference's type ledger: fp32 pixel weights / patch / gradients / residual,
 // fp64 geometry, Jacobian, H, b, pose.  The reference's per-pixel J = (dx*Jp0 + dy*Jp1)*fx/2^l is linear in (dx,dy),
 // so per feature b_f = -s*(Jp0*sum(dx*res) + Jp1*sum(dy*res)) and H_f = s^2*(A Jp0Jp0' + B(Jp0Jp1'+Jp1Jp0') + C Jp1Jp1')
 // with A,B,C = sum(dx^2, dx*dy, dy^2): identical in exact arithmetic, and within 1e-15 relative in fp64.
+//
+// Inverse compositional: H_f does not change inside a level, and H only depends on WHICH features project into the
+// current image.  So PrecomputePatches also forms H_all = sum_f H_f once per level; an iteration reduces b, chi2 and
+// three counters only (8 values instead of 29) and H is H_all, corrected by the few features that fell outside the
+// image (rare; a fixed-order pass of 21 lanes over the per-feature H_f kept in global memory).  With H unchanged its
+// LDL^T factor is reused too: most iterations are two triangular substitutions.
+//
+// Per-feature caches (xyz, Jacobian rows, reference patch and its gradients) live in SHARED memory for the first
+// `cap` features (256 or 512, chosen by the launcher); features beyond that use the same layout in global scratch.
 // Quirks kept: sticky visible_fts_/patch_cache_ across levels with J zeroed per level, stop_/chi2_ never reset,
 // fx used for both Jacobian rows, chi2 compared as float(chi2)/float(n_meas).
-#include "common.cuh"
+#include "seq.cuh"
 
 namespace {
 
 constexpr int AL_THREADS = 256;
-constexpr int NV = 30;   // reduced values: H(21) b(6) chi2 n_meas + pad
+constexpr int AL_WARPS = AL_THREADS / 32;
+constexpr int ND = 17;                        // cached doubles per feature: xyz[3], j0[6], j1[6] (times fx / 2^level), px[2]
+constexpr int PF = SDVLB_ALIGN_SC_FLOATS;     // cached floats per feature: patch[16], dx[16], dy[16], 4 pad.  A row
+                                              // stride of 52 words spreads the 16-byte loads of 8 neighbouring
+                                              // threads over all 32 banks (48 would make them collide 4-way)
+constexpr int NRED = 7;                       // b[6], chi2
 
 // Eight consecutive pixels starting at p, from aligned 32-bit words: a row of the 5x5 / 7x7 footprints costs two or
 // three loads instead of five or seven byte loads (the load/store unit is what the residual phase waits for).
@@ -29,34 +48,320 @@ __device__ __forceinline__ uint64_t load_pixels8(const uint8_t* __restrict__ p, 
   return (uint64_t(hi) << 32) | lo;
 }
 
-struct AlignArgs {
-  PyrGeom g;
-  DevParams dp;
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void store_Rt12(const DSE3& T, double* __restrict__ Rt) {
+  double R[9];
+  se3_rot(T, R);
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rt[i] = R[i];
+  Rt[9] = T.tx; Rt[10] = T.ty; Rt[11] = T.tz;
+}
+
+// Unpivoted LDL^T of a symmetric 6x6 matrix given by its upper triangle (row-major, 21 values), in registers.
+// fac[0..14] = L (strictly lower, row-major: L10, L20, L21, L30 ...), fac[15..20] = 1 / D.  Returns false when a pivot
+// is not safely positive (the caller then uses Eigen's pivoted algorithm, ldlt_solve6).  Same operations as
+// ldlt_solve6_spd (common.cuh).
+__device__ __forceinline__ bool ldlt_factor6(const double* __restrict__ up, double* __restrict__ fac) {
+  double A[6][6];
+  {
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int q = r; q < 6; q++) { A[r][q] = up[k]; A[q][r] = up[k]; k++; }
+  }
+  double L[6][6], W[6][6], Dinv[6];
+  double dmax = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) dmax = fmax(dmax, A[i][i]);
+  const double tiny = dmax * 1e-13;
+  bool ok = dmax > 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    double d = A[k][k];
+#pragma unroll
+    for (int j = 0; j < k; j++) d -= L[k][j] * W[k][j];
+    ok = ok && (d > tiny);
+    const double inv = pivot_rcp(d);
+    Dinv[k] = inv;
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) {
+      double s = A[i][k];
+#pragma unroll
+      for (int j = 0; j < k; j++) s -= L[i][j] * W[k][j];
+      W[i][k] = s;
+      L[i][k] = s * inv;
+    }
+  }
+  int k = 0;
+#pragma unroll
+  for (int i = 1; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < i; j++) fac[k++] = L[i][j];
+#pragma unroll
+  for (int i = 0; i < 6; i++) fac[15 + i] = Dinv[i];
+  return ok;
+}
+
+__device__ __forceinline__ void ldlt_apply6(const double* __restrict__ fac, const double b[6], double x[6]) {
+  double L[6][6];
+  {
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j < i; j++) L[i][j] = fac[k++];
+  }
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    double s = b[i];
+#pragma unroll
+    for (int j = 0; j < i; j++) s -= L[i][j] * y[j];
+    y[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) y[i] = y[i] * fac[15 + i];
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    double s = y[i];
+#pragma unroll
+    for (int j = i + 1; j < 6; j++) s -= L[j][i] * x[j];
+    x[i] = s;
+  }
+}
+
+// What align_core needs to know about one alignment.
+struct AlignView {
+  const uint8_t* ref_pyr;
+  const uint8_t* cur_pyr;
+  int n;
+  int fast;
+  double* out_pose;        // 7 doubles
+  double* cur_pose;        // 7 doubles: the current frame's pose slot (FrameDev::pose)
+  int32_t* out_info;       // [0] n_meas of the last ComputeResiduals, [1] iterations run
+  double* out_error;       // GetError()
+  int32_t* out_cycles;     // optional: [4] SM cycles in PrecomputePatches / residuals / reduction / solve + update
+  sdvlb_gn_iter* trace;    // optional
+  int trace_cap;
+  const double* forced_T;  // teacher forcing (parity tests)
+  const int32_t* forced_iters;
+  double* g_H;             // [21][n] per-feature J J^T sum of the level
+  double* g_d;             // [ND][n - cap] overflow cache
+  float* g_f;              // [n - cap][PF]
+  int32_t* g_flags;        // [n] flags of the overflow features (indexed by feature)
 };
 
-__global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobDev* __restrict__ jobs,
-                                                                 const __grid_constant__ AlignArgs A) {
-  extern __shared__ double s_dyn_part[];                 // NV x AL_THREADS partials (60 KB, opt-in dynamic)
-  double (*s_part)[AL_THREADS] = reinterpret_cast<double (*)[AL_THREADS]>(s_dyn_part);
-  __shared__ double s_red[NV];
-  __shared__ double s_T[7];        // current relative pose
-  __shared__ double s_Rt[12];      // rotation + translation of s_T
-  __shared__ int s_ctrl[4];        // [0] continue flag
+// Shared-memory plan of the kernel (dynamic): caches of the first `cap` features, then the small reduction areas.
+struct AlignSmem {
+  double* d;               // [ND][cap]
+  float* f;                // [cap][PF]
+  uint8_t* flag;           // [cap]  bit0 visible (sticky), bit1 has a Jacobian at this level, bit2 inside the current
+                           //        image in the iteration being evaluated, bit3 the feature observes a live point
+  double* wred;            // [AL_WARPS][8] per-warp partials of an iteration
+  double* hred;            // [AL_WARPS][21] per-warp partials of H_all
+  int* wredi;              // [AL_WARPS][4]
+  double* Hall;            // [21] sum of H_f over the features that have a Jacobian at this level
+  double* Hcur;            // [21] H of the iteration being solved
+  double* fac;             // [21] LDL^T factor
+  double* red;             // [8]  b[6], chi2
+  double* T;               // [7]  current relative pose
+  double* Rt;              // [12] its rotation + translation
+  int* ctrl;               // [0] continue, [1] level break, [2] n_meas, [3] n_inv, [4] n_vis_j
+};
+__host__ __device__ inline size_t align_smem_bytes(int cap) {
+  return size_t(cap) * (ND * 8 + PF * 4 + 1) + 16 + (AL_WARPS * (8 + 21) + 21 * 3 + 8 + 7 + 12) * 8 + (AL_WARPS * 4 + 8) * 4;
+}
+__device__ __forceinline__ void align_carve(unsigned char* mem, int cap, AlignSmem& s) {
+  s.d = reinterpret_cast<double*>(mem);
+  s.f = reinterpret_cast<float*>(s.d + size_t(ND) * cap);
+  s.flag = reinterpret_cast<uint8_t*>(s.f + size_t(cap) * PF);
+  uintptr_t p = (reinterpret_cast<uintptr_t>(s.flag + cap) + 15) & ~uintptr_t(15);
+  s.wred = reinterpret_cast<double*>(p);
+  s.hred = s.wred + AL_WARPS * 8;
+  s.Hall = s.hred + AL_WARPS * 21;
+  s.Hcur = s.Hall + 21;
+  s.fac = s.Hcur + 21;
+  s.red = s.fac + 21;
+  s.T = s.red + 8;
+  s.Rt = s.T + 7;
+  s.wredi = reinterpret_cast<int*>(s.Rt + 12);
+  s.ctrl = s.wredi + AL_WARPS * 4;
+}
 
-  const AlignJobDev& J = jobs[blockIdx.x];
+// Features marshalled by the host (class API, AlignJobDev::feats).
+struct JobFeatures {
+  const sdvlb_align_feat* __restrict__ feats;
+  __device__ __forceinline__ void load(int f, double& px0, double& px1, double& X, double& Y, double& Z, bool& valid) const {
+    const sdvlb_align_feat ft = feats[f];
+    px0 = ft.px[0]; px1 = ft.px[1];
+    X = ft.v[0] * ft.depth; Y = ft.v[1] * ft.depth; Z = ft.v[2] * ft.depth;   // xyz_ref = v * depth (image_align.cc:160,235)
+    valid = ft.valid != 0;
+  }
+};
+// Features of a resident sequence's last frame; depth = |point - camera centre of that frame| (image_align.cc:159,234).
+struct SeqFeatures {
+  const SeqFeat* __restrict__ list;
+  double C[3];
+  __device__ __forceinline__ void load(int f, double& px0, double& px1, double& X, double& Y, double& Z, bool& valid) const {
+    const SeqFeat& ft = list[f];
+    px0 = ft.px[0]; px1 = ft.px[1];
+    valid = (ft.flags & SEQF_HAS_POINT) != 0;
+    const double dx = ft.pos[0] - C[0], dy = ft.pos[1] - C[1], dz = ft.pos[2] - C[2];
+    const double depth = valid ? sqrt(dx * dx + dy * dy + dz * dz) : 1.0;
+    X = ft.v[0] * depth; Y = ft.v[1] * depth; Z = ft.v[2] * depth;
+  }
+};
+
+// PrecomputePatches for one feature (image_align.cc:208-267).  d / ds: the feature's double cache and its stride,
+// fl: its float row.  Returns the new flags; adds the feature's H_f to Hacc and stores it at gH[k * n].
+__device__ __forceinline__ int precompute_feature(int old_flags, const uint8_t* __restrict__ img1, int W, int Hh, float scale,
+                                                  int border, double fs, double* __restrict__ d, int ds,
+                                                  float* __restrict__ fl, double* __restrict__ gH, int n, double Hacc[21]) {
+  int flags = old_flags & 9;   // J zeroed per level (image_align.cc:69), visibility sticky
+  const bool valid = (old_flags & 8) != 0;
+  const float u_ref = float(d[15 * ds] * double(scale));
+  const float v_ref = float(d[16 * ds] * double(scale));
+  const bool in_img = u_ref >= 0.f && v_ref >= 0.f && u_ref < float(W) && v_ref < float(Hh);   // guards the int cast
+  const int ui = in_img ? int(floorf(u_ref)) : -1, vi = in_img ? int(floorf(v_ref)) : -1;
+  if (!(valid && !(ui - border < 0 || vi - border < 0 || ui + border >= W || vi + border >= Hh))) return flags;
+  flags = 11;
+  const float su = u_ref - float(ui), sv = v_ref - float(vi);
+  const float wtl = float((1.0 - su) * (1.0 - sv));
+  const float wtr = float(su * (1.0 - sv));
+  const float wbl = float((1.0 - su) * sv);
+  const float wbr = float(su * sv);
+  // 7x7 footprint: rows vi-3..vi+3, cols ui-3..ui+3
+  float px[7][7];
+#pragma unroll
+  for (int r = 0; r < 7; r++) {
+    const uint64_t v = load_pixels8(img1 + size_t(vi - 3 + r) * W + (ui - 3), true);
+#pragma unroll
+    for (int c = 0; c < 7; c++) px[r][c] = float(unsigned(v >> (8 * c)) & 0xffu);
+  }
+  double sa = 0, sb = 0, sc = 0;
+#pragma unroll
+  for (int y = 0; y < 4; y++) {
+    float pv[4], gx[4], gy[4];
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+      // p = &img[(vi+y-2)][ui-2+x]  -> px[y+1][x+1]
+      const int r = y + 1, c = x + 1;
+      const float val = wtl * px[r][c] + wtr * px[r][c + 1] + wbl * px[r + 1][c] + wbr * px[r + 1][c + 1];
+      const float dx = 0.5f * ((wtl * px[r][c + 1] + wtr * px[r][c + 2] + wbl * px[r + 1][c + 1] + wbr * px[r + 1][c + 2]) -
+                               (wtl * px[r][c - 1] + wtr * px[r][c] + wbl * px[r + 1][c - 1] + wbr * px[r + 1][c]));
+      const float dy = 0.5f * ((wtl * px[r + 1][c] + wtr * px[r + 1][c + 1] + wbl * px[r + 2][c] + wbr * px[r + 2][c + 1]) -
+                               (wtl * px[r - 1][c] + wtr * px[r - 1][c + 1] + wbl * px[r][c] + wbr * px[r][c + 1]));
+      pv[x] = val; gx[x] = dx; gy[x] = dy;
+      sa += double(dx) * double(dx);
+      sb += double(dx) * double(dy);
+      sc += double(dy) * double(dy);
+    }
+    reinterpret_cast<float4*>(fl)[y] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    reinterpret_cast<float4*>(fl)[4 + y] = make_float4(gx[0], gx[1], gx[2], gx[3]);
+    reinterpret_cast<float4*>(fl)[8 + y] = make_float4(gy[0], gy[1], gy[2], gy[3]);
+  }
+  double j0[6], j1[6];
+  jacobian3d_to_plane(d[0], d[ds], d[2 * ds], j0, j1);
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    j0[r] *= fs; j1[r] *= fs;
+    d[(3 + r) * ds] = j0[r];
+    d[(9 + r) * ds] = j1[r];
+  }
+  // sum over the 16 pixels of J J^T: constant for the whole level (inverse compositional)
+  int k = 0;
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int q = r; q < 6; q++) {
+      const double h = sa * j0[r] * j0[q] + sb * (j0[r] * j1[q] + j1[r] * j0[q]) + sc * j1[r] * j1[q];
+      gH[size_t(k) * n] = h;
+      Hacc[k] += h;
+      k++;
+    }
+  return flags;
+}
+
+// ComputeResiduals for one feature that is marked visible (image_align.cc:127-206).  Returns the new flags (bit2 = the
+// projection fell inside the current image); adds to b / chi2 / the counters.
+__device__ __forceinline__ int residual_feature(int flags, const double* __restrict__ Rt, const sdvlb_camera& cam,
+                                                const uint8_t* __restrict__ img2, int W, int Hh, float scale, int border,
+                                                const double* __restrict__ d, int ds, const float* __restrict__ fl,
+                                                double b[6], float& chi2_f, int& n_meas, int& n_inv, int& n_visj) {
+  flags &= 11;
+  const double X = d[0], Y = d[ds], Z = d[2 * ds];
+  const double xc = Rt[0] * X + Rt[1] * Y + Rt[2] * Z + Rt[9];
+  const double yc = Rt[3] * X + Rt[4] * Y + Rt[5] * Z + Rt[10];
+  const double zc = Rt[6] * X + Rt[7] * Y + Rt[8] * Z + Rt[11];
+  const double pu = cam.u0 + cam.fx * xc / zc;   // Camera::Project (camera.cc:69-72)
+  const double pv = cam.v0 + cam.fy * yc / zc;
+  const float u_cur = float(pu * double(scale));
+  const float v_cur = float(pv * double(scale));
+  bool inside = u_cur >= 0.f && v_cur >= 0.f && u_cur < float(W) && v_cur < float(Hh);   // NaN / inf / out of range
+  int ui = 0, vi = 0;
+  if (inside) {
+    ui = int(floorf(u_cur)); vi = int(floorf(v_cur));
+    inside = !(ui < 0 || vi < 0 || ui - border < 0 || vi - border < 0 || ui + border >= W || vi + border >= Hh);
+  }
+  if (!inside) {
+    if (flags & 2) n_inv++;
+    return flags;
+  }
+  const float su = u_cur - float(ui), sv = v_cur - float(vi);
+  const float wtl = float((1.0 - su) * (1.0 - sv));
+  const float wtr = float(su * (1.0 - sv));
+  const float wbl = float((1.0 - su) * sv);
+  const float wbr = float(su * sv);
+  float px[5][5];
+#pragma unroll
+  for (int r = 0; r < 5; r++) {
+    const uint64_t v = load_pixels8(img2 + size_t(vi - 2 + r) * W + (ui - 2), false);
+#pragma unroll
+    for (int c = 0; c < 5; c++) px[r][c] = float(unsigned(v >> (8 * c)) & 0xffu);
+  }
+  double sdx = 0, sdy = 0;
+  float chi = 0.0f;
+  const float4* __restrict__ row = reinterpret_cast<const float4*>(fl);
+#pragma unroll
+  for (int y = 0; y < 4; y++) {
+    const float4 pt = row[y], gx = row[4 + y], gy = row[8 + y];
+    const float ptv[4] = {pt.x, pt.y, pt.z, pt.w};
+    const float gxv[4] = {gx.x, gx.y, gx.z, gx.w};
+    const float gyv[4] = {gy.x, gy.y, gy.z, gy.w};
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+      const float ic = wtl * px[y][x] + wtr * px[y][x + 1] + wbl * px[y + 1][x] + wbr * px[y + 1][x + 1];
+      const float res = ic - ptv[x];
+      chi += res * res;
+      sdx += double(res) * double(gxv[x]);
+      sdy += double(res) * double(gyv[x]);
+    }
+  }
+  chi2_f += chi;
+  n_meas += 16;
+  if (flags & 2) {
+#pragma unroll
+    for (int r = 0; r < 6; r++) b[r] -= d[(3 + r) * ds] * sdx + d[(9 + r) * ds] * sdy;
+    n_visj++;
+    flags |= 4;
+  }
+  return flags;
+}
+
+template <typename Src>
+__device__ void align_core(const AlignView& J, const Src& src, const PyrGeom& G, const DevParams& dp, int cap,
+                           const AlignSmem& S, const double* T_ref, const double* T_cur) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = J.n;
-  const sdvlb_params& P = A.dp.p;
-  const sdvlb_camera& cam = A.dp.cam;
-
-  float* __restrict__ c_patch = J.sc_f;
-  float* __restrict__ c_dx = J.sc_f + size_t(n) * 16;
-  float* __restrict__ c_dy = J.sc_f + size_t(n) * 32;
-  double* __restrict__ c_xyz = J.sc_d;
-  double* __restrict__ c_j0 = J.sc_d + size_t(n) * 3;
-  double* __restrict__ c_j1 = J.sc_d + size_t(n) * 9;
-  double* __restrict__ c_H = J.sc_d + size_t(n) * 15;   // per-feature J J^T sum of the level, [k * n + f], k < 21
-  int32_t* __restrict__ c_flags = J.sc_flags;
+  const int n_over = n > cap ? n - cap : 0;
+  const sdvlb_params& P = dp.p;
+  const sdvlb_camera& cam = dp.cam;
 
   // thread-0 state (image_align.cc:35-41)
   double chi2_ = 1e10, error_ = 1e10;
@@ -66,26 +371,35 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
   int forced_k = 0;
   DSE3 T, T_bk;
 
-  if (n < 0) return;   // resident sequence without a reference frame yet: nothing to align
   if (n == 0) {   // image_align.cc:55-58: nothing to track, frame2 keeps its pose
     if (tid == 0) {
-      for (int i = 0; i < 7; i++) { J.out_pose[i] = J.T_cur[i]; J.cur.pose[i] = J.T_cur[i]; }
+      for (int i = 0; i < 7; i++) { J.out_pose[i] = T_cur[i]; J.cur_pose[i] = T_cur[i]; }
       J.out_info[0] = 0; J.out_info[1] = 0;
       *J.out_error = 1e10;
     }
     return;
   }
   if (tid == 0) {
-    const DSE3 T1 = se3_load(J.T_ref), T2 = se3_load(J.T_cur);
+    const DSE3 T1 = se3_load(T_ref), T2 = se3_load(T_cur);
     T = se3_mul(T2, se3_inverse(T1));   // image_align.cc:66
-    se3_store(T, s_T);
+    se3_store(T, S.T);
+    store_Rt12(T, S.Rt);
   }
+  // A feature is always handled by the same thread (f = tid, tid + 256, ...), in every phase: its caches are private
+  // to that thread and need no barrier; only the totals and the H correction cross threads.
   for (int f = tid; f < n; f += AL_THREADS) {
-    c_flags[f] = 0;
-    const sdvlb_align_feat ft = J.feats[f];
-    c_xyz[3 * f + 0] = ft.v[0] * ft.depth;   // xyz_ref = v * depth (image_align.cc:160,235)
-    c_xyz[3 * f + 1] = ft.v[1] * ft.depth;
-    c_xyz[3 * f + 2] = ft.v[2] * ft.depth;
+    double px0, px1, X, Y, Z;
+    bool valid;
+    src.load(f, px0, px1, X, Y, Z, valid);
+    if (f < cap) {
+      S.flag[f] = valid ? 8 : 0;
+      double* d = S.d + f;
+      d[0] = X; d[cap] = Y; d[2 * cap] = Z; d[15 * cap] = px0; d[16 * cap] = px1;
+    } else {
+      J.g_flags[f] = valid ? 8 : 0;
+      double* d = J.g_d + (f - cap);
+      d[0] = X; d[n_over] = Y; d[2 * n_over] = Z; d[15 * n_over] = px0; d[16 * n_over] = px1;
+    }
   }
   __syncthreads();
 
@@ -93,250 +407,213 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
   long long t_mark = clock64();
   bool level_break = false;   // uniform (derived from shared state)
   for (int level = P.max_align_level; level >= P.min_align_level && !level_break; level--) {
-    const int W = A.g.w[level], Hh = A.g.h[level];
-    const uint8_t* __restrict__ img1 = J.ref.pyr + A.g.off[level];
-    const uint8_t* __restrict__ img2 = J.cur.pyr + A.g.off[level];
+    const int W = G.w[level], Hh = G.h[level];
+    const uint8_t* __restrict__ img1 = J.ref_pyr + G.off[level];
+    const uint8_t* __restrict__ img2 = J.cur_pyr + G.off[level];
     const float scale = 1.0f / float(1 << level);
     const int border = P.align_patch_size / 2 + 1;   // 3
     const int n_forced = J.forced_T ? J.forced_iters[level] : -1;
     if (n_forced == 0) continue;
     if (tid == 0) T_bk = T;
+    int fac_state = 0;   // thread 0: 0 no factor, 1 S.fac = LDL^T of H_all of this level
 
     const int max_its = J.forced_T ? n_forced : P.max_img_align_its;
     for (int it = 0; it < max_its; it++) {
-      if (J.forced_T) {
-        if (tid == 0) { T = se3_load(J.forced_T + 7 * forced_k); se3_store(T, s_T); forced_k++; }
+      if (J.forced_T) {   // parity tests only: the schedule dictates the pose of every iteration
+        if (tid == 0) { T = se3_load(J.forced_T + 7 * forced_k); se3_store(T, S.T); store_Rt12(T, S.Rt); forced_k++; }
+        __syncthreads();
       }
-      if (tid == 0) {
-        double R[9];
-        se3_rot(T, R);
-        for (int i = 0; i < 9; i++) s_Rt[i] = R[i];
-        s_Rt[9] = T.tx; s_Rt[10] = T.ty; s_Rt[11] = T.tz;
-      }
-      // ---- PrecomputePatches(level) on the first iteration (image_align.cc:208-267)
+      // ---- PrecomputePatches(level) on the first iteration (image_align.cc:208-267) + partials of H_all
       if (it == 0) {
         const double fs = cam.fx / double(1 << level);
+        double Hacc[21];
+#pragma unroll
+        for (int k = 0; k < 21; k++) Hacc[k] = 0.0;
         for (int f = tid; f < n; f += AL_THREADS) {
-          const sdvlb_align_feat ft = J.feats[f];
-          int flags = c_flags[f] & 1;   // J zeroed per level (image_align.cc:69), visibility sticky
-          const float u_ref = float(ft.px[0] * double(scale));
-          const float v_ref = float(ft.px[1] * double(scale));
-          const bool in_img = u_ref >= 0.f && v_ref >= 0.f && u_ref < float(W) && v_ref < float(Hh);   // guards the int cast
-          const int ui = in_img ? int(floorf(u_ref)) : -1, vi = in_img ? int(floorf(v_ref)) : -1;
-          if (ft.valid && !(ui - border < 0 || vi - border < 0 || ui + border >= W || vi + border >= Hh)) {
-            flags = 3;
-            double j0[6], j1[6];
-            jacobian3d_to_plane(c_xyz[3 * f], c_xyz[3 * f + 1], c_xyz[3 * f + 2], j0, j1);
-            const float su = u_ref - float(ui), sv = v_ref - float(vi);
-            const float wtl = float((1.0 - su) * (1.0 - sv));
-            const float wtr = float(su * (1.0 - sv));
-            const float wbl = float((1.0 - su) * sv);
-            const float wbr = float(su * sv);
-            // 7x7 footprint: rows vi-3..vi+3, cols ui-3..ui+3
-            float px[7][7];
-#pragma unroll
-            for (int r = 0; r < 7; r++) {
-              const uint64_t v = load_pixels8(img1 + size_t(vi - 3 + r) * W + (ui - 3), true);
-#pragma unroll
-              for (int c = 0; c < 7; c++) px[r][c] = float(unsigned(v >> (8 * c)) & 0xffu);
-            }
-            double sa = 0, sb = 0, sc = 0;
-#pragma unroll
-            for (int y = 0; y < 4; y++)
-#pragma unroll
-              for (int x = 0; x < 4; x++) {
-                // p = &img[(vi+y-2)][ui-2+x]  -> px[y+1][x+1]
-                const int r = y + 1, c = x + 1;
-                const float val = wtl * px[r][c] + wtr * px[r][c + 1] + wbl * px[r + 1][c] + wbr * px[r + 1][c + 1];
-                const float dx = 0.5f * ((wtl * px[r][c + 1] + wtr * px[r][c + 2] + wbl * px[r + 1][c + 1] + wbr * px[r + 1][c + 2]) -
-                                         (wtl * px[r][c - 1] + wtr * px[r][c] + wbl * px[r + 1][c - 1] + wbr * px[r + 1][c]));
-                const float dy = 0.5f * ((wtl * px[r + 1][c] + wtr * px[r + 1][c + 1] + wbl * px[r + 2][c] + wbr * px[r + 2][c + 1]) -
-                                         (wtl * px[r - 1][c] + wtr * px[r - 1][c + 1] + wbl * px[r][c] + wbr * px[r][c + 1]));
-                c_patch[f * 16 + y * 4 + x] = val;
-                c_dx[f * 16 + y * 4 + x] = dx;
-                c_dy[f * 16 + y * 4 + x] = dy;
-                sa += double(dx) * double(dx);
-                sb += double(dx) * double(dy);
-                sc += double(dy) * double(dy);
-              }
-#pragma unroll
-            for (int r = 0; r < 6; r++) { j0[r] *= fs; j1[r] *= fs; c_j0[6 * f + r] = j0[r]; c_j1[6 * f + r] = j1[r]; }
-            // sum over the 16 pixels of J J^T: constant for the whole level (inverse compositional), so it is formed
-            // once here instead of in every Gauss-Newton iteration
-            int k = 0;
-#pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-              for (int q = r; q < 6; q++) {
-                c_H[size_t(k) * n + f] = sa * j0[r] * j0[q] + sb * (j0[r] * j1[q] + j1[r] * j0[q]) + sc * j1[r] * j1[q];
-                k++;
-              }
+          if (f < cap) {
+            S.flag[f] = uint8_t(precompute_feature(S.flag[f], img1, W, Hh, scale, border, fs, S.d + f, cap,
+                                                   S.f + size_t(f) * PF, J.g_H + f, n, Hacc));
+          } else {
+            J.g_flags[f] = precompute_feature(J.g_flags[f], img1, W, Hh, scale, border, fs, J.g_d + (f - cap), n_over,
+                                              J.g_f + size_t(f - cap) * PF, J.g_H + f, n, Hacc);
           }
-          c_flags[f] = flags;
         }
+#pragma unroll
+        for (int k = 0; k < 21; k++) {
+          const double s = warp_sum_d(Hacc[k]);
+          if (lane == 0) S.hred[warp * 21 + k] = s;
+        }
+        if (tid == 0) { const long long t = clock64(); cyc[0] += t - t_mark; t_mark = t; }
       }
-      __syncthreads();
-      if (tid == 0) { const long long t = clock64(); cyc[0] += t - t_mark; t_mark = t; }
 
       // ---- ComputeResiduals (image_align.cc:127-206)
-      double acc[NV];
-#pragma unroll
-      for (int i = 0; i < NV; i++) acc[i] = 0.0;
+      double b[6] = {0, 0, 0, 0, 0, 0};
       float chi2_f = 0.0f;
-      int n_meas = 0;
+      int n_meas = 0, n_inv = 0, n_visj = 0;
       for (int f = tid; f < n; f += AL_THREADS) {
-        const int flags = c_flags[f];
-        if (!(flags & 1)) continue;
-        const double X = c_xyz[3 * f], Y = c_xyz[3 * f + 1], Z = c_xyz[3 * f + 2];
-        const double xc = s_Rt[0] * X + s_Rt[1] * Y + s_Rt[2] * Z + s_Rt[9];
-        const double yc = s_Rt[3] * X + s_Rt[4] * Y + s_Rt[5] * Z + s_Rt[10];
-        const double zc = s_Rt[6] * X + s_Rt[7] * Y + s_Rt[8] * Z + s_Rt[11];
-        const double pu = cam.u0 + cam.fx * xc / zc;   // Camera::Project (camera.cc:69-72)
-        const double pv = cam.v0 + cam.fy * yc / zc;
-        const float u_cur = float(pu * double(scale));
-        const float v_cur = float(pv * double(scale));
-        if (!(u_cur >= 0.f && v_cur >= 0.f && u_cur < float(W) && v_cur < float(Hh))) continue;   // NaN/inf/out of range
-        const int ui = int(floorf(u_cur)), vi = int(floorf(v_cur));
-        if (ui < 0 || vi < 0 || ui - border < 0 || vi - border < 0 || ui + border >= W || vi + border >= Hh) continue;
-        const float su = u_cur - float(ui), sv = v_cur - float(vi);
-        const float wtl = float((1.0 - su) * (1.0 - sv));
-        const float wtr = float(su * (1.0 - sv));
-        const float wbl = float((1.0 - su) * sv);
-        const float wbr = float(su * sv);
-        float px[5][5];
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          const uint64_t v = load_pixels8(img2 + size_t(vi - 2 + r) * W + (ui - 2), false);
-#pragma unroll
-          for (int c = 0; c < 5; c++) px[r][c] = float(unsigned(v >> (8 * c)) & 0xffu);
-        }
-        double sdx = 0, sdy = 0;
-        float chi = 0.0f;
-        const float4* pp = reinterpret_cast<const float4*>(c_patch + f * 16);
-        const float4* pdx = reinterpret_cast<const float4*>(c_dx + f * 16);
-        const float4* pdy = reinterpret_cast<const float4*>(c_dy + f * 16);
-#pragma unroll
-        for (int y = 0; y < 4; y++) {
-          const float4 pt = pp[y], gx = pdx[y], gy = pdy[y];
-          const float ptv[4] = {pt.x, pt.y, pt.z, pt.w};
-          const float gxv[4] = {gx.x, gx.y, gx.z, gx.w};
-          const float gyv[4] = {gy.x, gy.y, gy.z, gy.w};
-#pragma unroll
-          for (int x = 0; x < 4; x++) {
-            const float ic = wtl * px[y][x] + wtr * px[y][x + 1] + wbl * px[y + 1][x] + wbr * px[y + 1][x + 1];
-            const float res = ic - ptv[x];
-            chi += res * res;
-            sdx += double(res) * double(gxv[x]);
-            sdy += double(res) * double(gyv[x]);
-          }
-        }
-        chi2_f += chi;
-        n_meas += 16;
-        if (flags & 2) {
-          double j0[6], j1[6];
-#pragma unroll
-          for (int r = 0; r < 6; r++) { j0[r] = c_j0[6 * f + r]; j1[r] = c_j1[6 * f + r]; }
-#pragma unroll
-          for (int k = 0; k < 21; k++) acc[k] += c_H[size_t(k) * n + f];
-#pragma unroll
-          for (int r = 0; r < 6; r++) acc[21 + r] -= j0[r] * sdx + j1[r] * sdy;
+        if (f < cap) {
+          const int flags = S.flag[f];
+          if (!(flags & 1)) continue;
+          S.flag[f] = uint8_t(residual_feature(flags, S.Rt, cam, img2, W, Hh, scale, border, S.d + f, cap,
+                                               S.f + size_t(f) * PF, b, chi2_f, n_meas, n_inv, n_visj));
+        } else {
+          const int flags = J.g_flags[f];
+          if (!(flags & 1)) continue;
+          J.g_flags[f] = residual_feature(flags, S.Rt, cam, img2, W, Hh, scale, border, J.g_d + (f - cap), n_over,
+                                          J.g_f + size_t(f - cap) * PF, b, chi2_f, n_meas, n_inv, n_visj);
         }
       }
-      acc[27] = double(chi2_f);
-      acc[28] = double(n_meas);
+      {
+        double v[NRED];
 #pragma unroll
-      for (int i = 0; i < NV; i++) s_part[i][tid] = acc[i];
+        for (int r = 0; r < 6; r++) v[r] = b[r];
+        v[6] = double(chi2_f);
+#pragma unroll
+        for (int k = 0; k < NRED; k++) {
+          const double s = warp_sum_d(v[k]);
+          if (lane == 0) S.wred[warp * 8 + k] = s;
+        }
+        const int m = int(__reduce_add_sync(0xffffffffu, unsigned(n_meas)));
+        const int ni = int(__reduce_add_sync(0xffffffffu, unsigned(n_inv)));
+        const int nv = int(__reduce_add_sync(0xffffffffu, unsigned(n_visj)));
+        if (lane == 0) { S.wredi[warp * 4] = m; S.wredi[warp * 4 + 1] = ni; S.wredi[warp * 4 + 2] = nv; }
+      }
       __syncthreads();
       if (tid == 0) { const long long t = clock64(); cyc[1] += t - t_mark; t_mark = t; }
-      // fixed-order tree: warp w reduces rows w, w+8, ...
-      for (int v = warp; v < 29; v += AL_THREADS / 32) {
-        double s = 0;
-#pragma unroll
-        for (int k = 0; k < AL_THREADS / 32; k++) s += s_part[v][lane + 32 * k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) s_red[v] = s;
-      }
-      __syncthreads();
 
-      // ---- Optimize step on thread 0 (image_align.cc:91-124)
-      if (tid == 0) {
-        { const long long t = clock64(); cyc[2] += t - t_mark; t_mark = t; }
-        double Hm[6][6], b[6], x[6];
-        {
-          int k = 0;
+      // ---- warp 0: totals in fixed order, H of this iteration, then the Optimize step on thread 0
+      if (warp == 0) {
+        if (it == 0 && lane < 21) {
+          double s = 0;
 #pragma unroll
-          for (int r = 0; r < 6; r++)
+          for (int w = 0; w < AL_WARPS; w++) s += S.hred[w * 21 + lane];
+          S.Hall[lane] = s;
+        }
+        if (lane < NRED) {
+          double tot = 0;
 #pragma unroll
-            for (int q = r; q < 6; q++) { Hm[r][q] = s_red[k]; Hm[q][r] = s_red[k]; k++; }
+          for (int w = 0; w < AL_WARPS; w++) tot += S.wred[w * 8 + lane];
+          S.red[lane] = tot;
         }
+        int ti = 0;
+        if (lane < 3) {
 #pragma unroll
-        for (int r = 0; r < 6; r++) b[r] = s_red[21 + r];
-        const int nm = int(s_red[28]);
-        n_meas_last = nm;
-        const double new_chi2 = double(float(s_red[27]) / float(nm));   // float / size_t -> float (image_align.cc:205)
-        if (nm == 0) stop_ = true;
-        // H.ldlt().solve(Jres) (image_align.cc:102): register-only LDL^T when H is safely positive definite (the normal
-        // case), Eigen's pivoted algorithm otherwise (singular / empty systems, NaN propagation)
-        if (!ldlt_solve6_spd(Hm, b, x)) {
-          double H[36];
-          for (int r = 0; r < 6; r++)
-            for (int q = 0; q < 6; q++) H[r * 6 + q] = Hm[r][q];
-          ldlt_solve6(H, b, x);
+          for (int w = 0; w < AL_WARPS; w++) ti += S.wredi[w * 4 + lane];
         }
-        bool nan = false;
-        if (isnan(x[0])) { stop_ = true; nan = true; }
-        int flags = (nan ? 2 : 0) | (nm == 0 ? 4 : 0);
-        int cont = 1;
-        const bool reject = (it > 0 && new_chi2 > chi2_) || stop_;
-        if (J.forced_T) {
-          if (reject) flags |= 1;     // what the reference would have decided; control stays with the schedule
-        } else if (reject) {
-          T = T_bk;
-          flags |= 1;
-          cont = 0;
-        } else {
-          T_bk = T;
-          double mx[6];
-          for (int r = 0; r < 6; r++) mx[r] = -x[r];
-          T = se3_mul(T, se3_exp(mx));   // image_align.cc:116
-          chi2_ = new_chi2;
-          double e = -1;
-          for (int r = 0; r < 6; r++) e = fmax(e, fabs(x[r]));   // AbsMax (utils.cc:28-42)
-          error_ = e;
-          if (error_ <= 1e-10) cont = 0;
+        const int nm = __shfl_sync(0xffffffffu, ti, 0);
+        const int ninv = __shfl_sync(0xffffffffu, ti, 1);
+        const int nvisj = __shfl_sync(0xffffffffu, ti, 2);
+        // H: every feature with a Jacobian projects inside the image -> H_all; none does -> 0; otherwise H_all minus
+        // the ones outside, or the sum of the ones inside when those are fewer (fixed feature order, lane k owns H[k])
+        if (ninv > 0 && lane < 21) {
+          double h = 0.0;
+          if (nvisj > 0) {
+            const bool sum_inside = nvisj < ninv;
+            const int want = sum_inside ? 6 : 2;     // has J & inside  /  has J & not inside
+            double acc = 0.0;
+            for (int f = 0; f < n; f++) {
+              const int fl = f < cap ? int(S.flag[f]) : J.g_flags[f];
+              if ((fl & 6) == want) acc += J.g_H[size_t(lane) * n + f];
+            }
+            h = sum_inside ? acc : S.Hall[lane] - acc;
+          }
+          S.Hcur[lane] = h;
         }
-        if (J.trace && trace_n < J.trace_cap) {
-          sdvlb_gn_iter& rec = J.trace[trace_n];
-          rec.level = level; rec.iter = it; rec.n_meas = nm; rec.flags = flags;
-          for (int i = 0; i < 7; i++) rec.T_in[i] = s_T[i];
-          for (int r = 0; r < 6; r++)
-            for (int q = 0; q < 6; q++) rec.H[r * 6 + q] = Hm[r][q];
-          for (int i = 0; i < 6; i++) { rec.b[i] = b[i]; rec.x[i] = x[i]; }
-          rec.chi2 = new_chi2;
+        __syncwarp();
+
+        if (lane == 0) {
+          { const long long t = clock64(); cyc[2] += t - t_mark; t_mark = t; }
+          const double* __restrict__ Hup = ninv > 0 ? S.Hcur : S.Hall;
+          double bb[6], x[6];
+#pragma unroll
+          for (int r = 0; r < 6; r++) bb[r] = S.red[r];
+          n_meas_last = nm;
+          const double new_chi2 = double(float(S.red[6]) / float(nm));   // float / size_t -> float (image_align.cc:205)
+          if (nm == 0) stop_ = true;
+          // H.ldlt().solve(Jres) (image_align.cc:102): register-only LDL^T when H is safely positive definite (the
+          // normal case; the factor of H_all serves every iteration of the level), Eigen's pivoted algorithm otherwise
+          // (singular / empty systems, NaN propagation)
+          bool solved = false;
+          if (ninv == 0 && fac_state == 1) {
+            ldlt_apply6(S.fac, bb, x);
+            solved = true;
+          } else {
+            double fac[21];
+            if (ldlt_factor6(Hup, fac)) {
+              ldlt_apply6(fac, bb, x);
+              solved = true;
+              if (ninv == 0) {
+#pragma unroll
+                for (int k = 0; k < 21; k++) S.fac[k] = fac[k];
+                fac_state = 1;
+              }
+            }
+          }
+          if (!solved) {
+            double H[36];
+            int k = 0;
+            for (int r = 0; r < 6; r++)
+              for (int q = r; q < 6; q++) { H[r * 6 + q] = Hup[k]; H[q * 6 + r] = Hup[k]; k++; }
+            ldlt_solve6(H, bb, x);
+          }
+          bool nan = false;
+          if (isnan(x[0])) { stop_ = true; nan = true; }
+          int flags = (nan ? 2 : 0) | (nm == 0 ? 4 : 0);
+          int cont = 1;
+          const bool reject = (it > 0 && new_chi2 > chi2_) || stop_;
+          const DSE3 T_in = T;
+          if (J.forced_T) {
+            if (reject) flags |= 1;     // what the reference would have decided; control stays with the schedule
+          } else if (reject) {
+            T = T_bk;
+            flags |= 1;
+            cont = 0;
+          } else {
+            T_bk = T;
+            double mx[6];
+            for (int r = 0; r < 6; r++) mx[r] = -x[r];
+            T = se3_mul(T, se3_exp(mx));   // image_align.cc:116
+            chi2_ = new_chi2;
+            double e = -1;
+            for (int r = 0; r < 6; r++) e = fmax(e, fabs(x[r]));   // AbsMax (utils.cc:28-42)
+            error_ = e;
+            if (error_ <= 1e-10) cont = 0;
+          }
+          se3_store(T, S.T);
+          store_Rt12(T, S.Rt);           // the pose the next iteration (or level) evaluates its residuals at
+          S.ctrl[0] = cont;
+          if (J.trace && trace_n < J.trace_cap) {
+            sdvlb_gn_iter& rec = J.trace[trace_n];
+            rec.level = level; rec.iter = it; rec.n_meas = nm; rec.flags = flags;
+            se3_store(T_in, rec.T_in);
+            int k = 0;
+            for (int r = 0; r < 6; r++)
+              for (int q = r; q < 6; q++) { rec.H[r * 6 + q] = Hup[k]; rec.H[q * 6 + r] = Hup[k]; k++; }
+            for (int i = 0; i < 6; i++) { rec.b[i] = bb[i]; rec.x[i] = x[i]; }
+            rec.chi2 = new_chi2;
+          }
+          trace_n++;
+          { const long long t = clock64(); cyc[3] += t - t_mark; t_mark = t; }
         }
-        trace_n++;
-        se3_store(T, s_T);
-        s_ctrl[0] = cont;
-        { const long long t = clock64(); cyc[3] += t - t_mark; t_mark = t; }
       }
       __syncthreads();
-      if (!s_ctrl[0]) break;
+      if (!S.ctrl[0]) break;
     }
     // image_align.cc:73-76 (relocalisation only)
     if (tid == 0) {
       int lb = 0;
       if (!J.forced_T && J.fast && error_ > 0.01) { error_ = 1e10; lb = 1; }
-      s_ctrl[1] = lb;
+      S.ctrl[1] = lb;
     }
     __syncthreads();
-    level_break = s_ctrl[1] != 0;
+    level_break = S.ctrl[1] != 0;
   }
 
+  sdvlb_launch_dependents();   // the next kernel of the chain may be brought in; it waits for this grid to complete
   if (tid == 0) {
-    const DSE3 out = se3_mul(T, se3_load(J.T_ref));   // frame2_->SetPose(current_se3 * frame1_->GetPose())
+    const DSE3 out = se3_mul(T, se3_load(T_ref));   // frame2_->SetPose(current_se3 * frame1_->GetPose())
     se3_store(out, J.out_pose);
-    se3_store(out, J.cur.pose);
+    se3_store(out, J.cur_pose);
     J.out_info[0] = n_meas_last;
     J.out_info[1] = trace_n;
     *J.out_error = error_;
@@ -345,26 +622,114 @@ __global__ void __launch_bounds__(AL_THREADS) image_align_kernel(const AlignJobD
   }
 }
 
+struct AlignArgs {
+  PyrGeom g;
+  DevParams dp;
+  int cap;
+};
+
+__global__ void __launch_bounds__(AL_THREADS, 1) image_align_kernel(const AlignJobDev* __restrict__ jobs,
+                                                                    const __grid_constant__ AlignArgs A) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ double s_Tref[7], s_Tcur[7];
+  AlignSmem S;
+  align_carve(s_dyn, A.cap, S);
+  const AlignJobDev& Jd = jobs[blockIdx.x];
+  if (Jd.n < 0) return;
+  if (threadIdx.x < 7) { s_Tref[threadIdx.x] = Jd.T_ref[threadIdx.x]; s_Tcur[threadIdx.x] = Jd.T_cur[threadIdx.x]; }
+  __syncthreads();
+  AlignView J;
+  J.ref_pyr = Jd.ref.pyr; J.cur_pyr = Jd.cur.pyr;
+  J.n = Jd.n; J.fast = Jd.fast;
+  J.out_pose = Jd.out_pose; J.cur_pose = Jd.cur.pose; J.out_info = Jd.out_info; J.out_error = Jd.out_error;
+  J.out_cycles = Jd.out_cycles;
+  J.trace = Jd.trace; J.trace_cap = Jd.trace_cap; J.forced_T = Jd.forced_T; J.forced_iters = Jd.forced_iters;
+  J.g_H = Jd.sc_d;
+  J.g_d = Jd.sc_d + size_t(21) * Jd.n;
+  J.g_f = Jd.sc_f;
+  J.g_flags = Jd.sc_flags;
+  JobFeatures src{Jd.feats};
+  align_core(J, src, A.g, A.dp, A.cap, S, s_Tref, s_Tcur);
+}
+
 }  // namespace
 
-size_t sdvlb_align_scratch_floats(int n) { return size_t(n) * 48; }
-size_t sdvlb_align_scratch_doubles(int n) { return size_t(n) * SDVLB_ALIGN_SC_DOUBLES; }
+// ------------------------------------------------------------------------------------------------ resident sequences
+// One CTA per sequence of the step: the mapping thread's commands, the motion-model prior and ImageAlign.
+namespace {
 
-cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, const PyrGeom& g, const DevParams& dp,
+__global__ void __launch_bounds__(AL_THREADS, 1) seq_align_kernel(const __grid_constant__ SeqStepArgs A, int cap) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ double s_Tref[7], s_Tcur[7], s_C[3];
+  __shared__ int s_base;
+  AlignSmem Sm;
+  align_carve(s_dyn, cap, Sm);
+  SeqState* S = A.seq[blockIdx.x];
+  const int tid = threadIdx.x;
+  sdvlb_grid_dependency_wait();   // queued behind the previous step's post kernel: the sequence state is its output
+  if (A.cmd_range[blockIdx.x].y > 0) {   // the mapping thread's commands for this sequence (keyframes), in order
+    seq_apply_commands(A.cmds, A.cmd_range[blockIdx.x], A.dp, &s_base);
+    __threadfence_block();
+    __syncthreads();
+  }
+  const int has_last = S->has_last;
+  const int n = has_last ? S->n_list : 0;
+  if (tid == 0) {
+    const DSE3 T_last = se3_load(S->T_last);
+    const DSE3 Twc = se3_inverse(T_last);   // Frame::GetWorldPosition (frame.h)
+    s_C[0] = Twc.tx; s_C[1] = Twc.ty; s_C[2] = Twc.tz;
+    const DSE3 prior = se3_mul(se3_exp(S->vel), T_last);   // SDVL::SetMotionModel (sdvl.cc:278-281)
+    se3_store(T_last, s_Tref);
+    se3_store(prior, s_Tcur);
+    S->align_info[0] = 0; S->align_info[1] = 0;
+  }
+  __syncthreads();
+  if (!has_last || S->hold) return;   // no track yet (no reset) / on hold: the post kernel reports which
+  AlignView J;
+  J.ref_pyr = S->last.pyr; J.cur_pyr = A.cur[blockIdx.x].pyr;
+  J.n = n; J.fast = 0;
+  J.out_pose = S->align_pose; J.cur_pose = A.cur[blockIdx.x].pose; J.out_info = S->align_info;
+  J.out_error = &S->align_error; J.out_cycles = S->align_cycles;
+  J.trace = nullptr; J.trace_cap = 0; J.forced_T = nullptr; J.forced_iters = nullptr;
+  // the sequence's own scratch, carved by ITS capacity (sequences of one submission may differ)
+  const size_t nn = size_t(S->max_feats);
+  double* sc_d = reinterpret_cast<double*>(S->align_scratch);
+  J.g_H = sc_d;
+  J.g_d = sc_d + size_t(21) * n;
+  J.g_f = reinterpret_cast<float*>(S->align_scratch + nn * SDVLB_ALIGN_SC_DOUBLES * 8);
+  J.g_flags = reinterpret_cast<int32_t*>(S->align_scratch + nn * (SDVLB_ALIGN_SC_DOUBLES * 8 + SDVLB_ALIGN_SC_FLOATS * 4));
+  SeqFeatures src;
+  src.list = S->list[S->cur];
+  src.C[0] = s_C[0]; src.C[1] = s_C[1]; src.C[2] = s_C[2];
+  align_core(J, src, A.g, A.dp, cap, Sm, s_Tref, s_Tcur);
+}
+
+// Features cached in shared memory: 256 (85 KB) covers the tracking configurations of the reference (at most
+// max(max_matches, points per keyframe) features per frame); 512 (170 KB) is used when the caller's bound is larger.
+// More features than that still work (global scratch), more slowly.
+int align_cap_for(int n_bound) { return n_bound <= 256 ? 256 : 512; }
+
+}  // namespace
+
+size_t sdvlb_align_scratch_bytes(int n) { return SDVLB_ALIGN_SC_BYTES(n) + 256; }
+
+cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, int n_bound, const PyrGeom& g, const DevParams& dp,
                                cudaStream_t stream) {
   AlignArgs A;
   A.g = g;
   A.dp = dp;
-  const size_t dyn = sizeof(double) * NV * AL_THREADS;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(image_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn));
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  sdvlb_common_carveout(image_align_kernel);
+  A.cap = align_cap_for(n_bound);
+  const size_t dyn = align_smem_bytes(A.cap);
+  SDVLB_PREPARE(image_align_kernel, dyn);
   image_align_kernel<<<n_jobs, AL_THREADS, dyn, stream>>>(static_cast<const AlignJobDev*>(d_jobs), A);
   return cudaGetLastError();
+}
+
+cudaError_t sdvlb_launch_seq_align(const SeqStepArgs& A, int n_bound, cudaStream_t stream) {
+  const int cap = align_cap_for(n_bound);
+  const size_t dyn = align_smem_bytes(cap);
+  SDVLB_PREPARE(seq_align_kernel, dyn);
+  return sdvlb_launch_dependent(seq_align_kernel, dim3(A.n), dim3(AL_THREADS), dyn, stream, A, cap);
 }
 
 size_t sdvlb_align_job_size() { return sizeof(AlignJobDev); }

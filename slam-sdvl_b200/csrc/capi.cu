@@ -37,7 +37,7 @@ cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, u
 cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
                                      uint32_t* level_kp, int32_t* level_cnt, int32_t* frame_ticket,
                                      cudaStream_t stream);
-cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, const PyrGeom& g, const DevParams& dp,
+cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, int n_bound, const PyrGeom& g, const DevParams& dp,
                                cudaStream_t stream);
 cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const FrameDev* d_frames, sdvlb_match* d_out,
                                 const PyrGeom& g, const DevParams& dp, cudaStream_t stream);
@@ -57,6 +57,47 @@ int sdvlb_set_error(int code, const char* msg) {
 }
 
 #include "capi_internal.h"
+
+// Per (device, kernel) launch preparation (declared in common.cuh).  A thread-local record answers the steady state
+// without a lock; the first call per thread / a larger request goes through the process-wide table.
+cudaError_t sdvlb_kernel_prepare_ptr(const void* kernel, int dyn_smem_bytes) {
+  struct Rec { const void* kernel; int device; int dyn; };
+  static std::mutex mu;
+  static std::vector<Rec> table;
+  static int carveout = -2;
+  thread_local std::vector<Rec> seen;
+  int device = 0;
+  cudaError_t e = cudaGetDevice(&device);
+  if (e != cudaSuccess) return e;
+  for (const Rec& r : seen)
+    if (r.kernel == kernel && r.device == device && r.dyn >= dyn_smem_bytes) return cudaSuccess;
+  std::lock_guard<std::mutex> lk(mu);
+  if (carveout == -2) {
+    const char* env = getenv("SDVLB_CARVEOUT");
+    carveout = env ? atoi(env) : 100;
+  }
+  Rec* rec = nullptr;
+  for (Rec& r : table)
+    if (r.kernel == kernel && r.device == device) rec = &r;
+  if (!rec) {
+    if (carveout >= 0) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+      if (e != cudaSuccess) return e;
+    }
+    table.push_back(Rec{kernel, device, 0});
+    rec = &table.back();
+  }
+  if (dyn_smem_bytes > 48 * 1024 && dyn_smem_bytes > rec->dyn) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem_bytes);
+    if (e != cudaSuccess) return e;
+  }
+  if (dyn_smem_bytes > rec->dyn) rec->dyn = dyn_smem_bytes;
+  bool found = false;
+  for (Rec& r : seen)
+    if (r.kernel == kernel && r.device == device) { r.dyn = rec->dyn; found = true; }
+  if (!found) seen.push_back(*rec);
+  return cudaSuccess;
+}
 
 
 namespace sdvlb_detail {
@@ -387,11 +428,12 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
 int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_gn_iter* trace, int trace_cap,
                  int* trace_n, const sdvlb_gn_forced* forced, bool build_frames, int fast = 0) {
   SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-  if (c->pending.active || c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
+  if (c->pending.active || !c->seq_queue.empty()) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
   const PyrGeom& g = c->geom;
 
-  int n_detect = 0, n_align = 0, n_cands = 0, n_feats = 0, nfeatures = -1;
+  int n_detect = 0, n_align = 0, n_cands = 0, n_feats = 0, nfeatures = -1, max_feats_job = 0;
   for (int i = 0; i < n; i++) {
+    if (jobs[i].ref) max_feats_job = std::max(max_feats_job, jobs[i].n_feats);
     if (build_frames && jobs[i].want_corners) {
       n_detect++;
       if (nfeatures < 0) nfeatures = jobs[i].nfeatures;
@@ -433,7 +475,7 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
   if (rc) return rc;
   size_t scratch_need = 0;
   for (int i = 0; i < n; i++)
-    if (jobs[i].ref) scratch_need += align_up(size_t(jobs[i].n_feats) * (48 * 4 + SDVLB_ALIGN_SC_DOUBLES * 8 + 4) + 1024, 256);
+    if (jobs[i].ref) scratch_need += align_up(SDVLB_ALIGN_SC_BYTES(jobs[i].n_feats) + 1024, 256);
   rc = ensure_scratch(c, scratch_need);
   if (rc) return rc;
 
@@ -491,8 +533,8 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
       a.sc_d = reinterpret_cast<double*>(sc);
       a.sc_f = reinterpret_cast<float*>(sc + align_up(size_t(j.n_feats) * SDVLB_ALIGN_SC_DOUBLES * 8, 256));
       a.sc_flags = reinterpret_cast<int32_t*>(sc + align_up(size_t(j.n_feats) * SDVLB_ALIGN_SC_DOUBLES * 8, 256) +
-                                              align_up(size_t(j.n_feats) * 48 * 4, 256));
-      sc_off += align_up(size_t(j.n_feats) * (48 * 4 + SDVLB_ALIGN_SC_DOUBLES * 8 + 4) + 1024, 256);
+                                              align_up(size_t(j.n_feats) * SDVLB_ALIGN_SC_FLOATS * 4, 256));
+      sc_off += align_up(SDVLB_ALIGN_SC_BYTES(j.n_feats) + 1024, 256);
       if (j.n_feats > 0) memcpy(hfe + fi, j.feats, size_t(j.n_feats) * sizeof(sdvlb_align_feat));
       fi += j.n_feats;
       ai++;
@@ -554,7 +596,7 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
   }
   if (n_align > 0) {
     timer_begin(c, SDVLB_K_ALIGN);
-    SDVLB_CUDA_TRY(sdvlb_launch_align(in.d + o_align, n_align, g, c->dp, c->stream));
+    SDVLB_CUDA_TRY(sdvlb_launch_align(in.d + o_align, n_align, max_feats_job, g, c->dp, c->stream));
     timer_end(c);
     c->n_launches += 1;
   }
@@ -579,16 +621,17 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
   return 0;
 }
 
-// Spins on the pinned completion word; falls back to the driver now and then so that device errors surface.
-int wait_signal(sdvlb_ctx* c) {
+// Spins on the pinned completion word until submission `seq_no` of the tracking stream has finished (submissions
+// complete in order); falls back to the driver now and then so that device errors surface.
+int wait_signal(sdvlb_ctx* c, uint32_t seq_no) {
   volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(c->h_overflow) + 16;
   uint64_t spins = 0;
-  while (*done != c->track_seq) {
+  while (int32_t(*done - seq_no) < 0) {
     if ((++spins & 0xFFFFF) == 0) {
       SDVLB_CUDA_TRY(cudaSetDevice(c->device));
       const cudaError_t e = cudaStreamQuery(c->stream);
       if (e != cudaSuccess && e != cudaErrorNotReady) return sdvlb_set_cuda_error(e, "cudaStreamQuery", __FILE__, __LINE__);
-      if (e == cudaSuccess && *done != c->track_seq)
+      if (e == cudaSuccess && int32_t(*done - seq_no) < 0)
         return sdvlb_set_error(SDVLB_ERR_CUDA, "tracking stream drained without publishing its completion word");
     }
 #if defined(__x86_64__)
@@ -603,7 +646,7 @@ int collect_batch(sdvlb_ctx* c) {
   if (!P.active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
   P.active = false;
   {
-    const int rcw = wait_signal(c);
+    const int rcw = wait_signal(c, c->track_seq);
     if (rcw) return rcw;
   }
   Arena& out = c->out;
@@ -741,9 +784,11 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   cudaFree(c->frame_ticket); cudaFree(c->scratch);
   if (c->h_overflow) cudaFreeHost(c->h_overflow);
   while (!c->seqs.empty()) sdvlb_seq_destroy(c, c->seqs.back());
-  if (c->seq_in.h) cudaFreeHost(c->seq_in.h);
-  if (c->seq_in.d) cudaFree(c->seq_in.d);
-  cudaFree(c->d_seq_jobs); cudaFree(c->d_seq_frames); cudaFree(c->d_seq_done);
+  for (Arena& a : c->seq_in) {
+    if (a.h) cudaFreeHost(a.h);
+    if (a.d) cudaFree(a.d);
+  }
+  cudaFree(c->d_seq_done);
   if (c->in.h) cudaFreeHost(c->in.h);
   if (c->in.d) cudaFree(c->in.d);
   if (c->out.h) cudaFreeHost(c->out.h);

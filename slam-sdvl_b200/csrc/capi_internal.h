@@ -3,6 +3,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <deque>
 #include <mutex>
 #include <vector>
 
@@ -68,9 +69,20 @@ struct PendingTrack {
 struct sdvlb_seq {   // host handle of a resident sequence
   sdvlb_ctx* ctx = nullptr;
   uint8_t* d_block = nullptr;        // SeqState followed by its arrays
-  SeqResultHost* h_result = nullptr; // pinned, device-visible
+  uint8_t* h_result = nullptr;       // pinned, device-visible: SDVLB_SEQ_DEPTH blocks of result_stride bytes
+  size_t result_stride = 0;          // SeqResultHost + max_feats feature records, 256-byte aligned
   int max_feats = 0, n_cells = 0;
+  int n_bound = 0;                   // upper bound of the device-side feature count at the next submission
+  sdvlb_seq_policy policy = {};
   int kf_state[SDVLB_SEQ_KF_CAP] = {};   // 0 free, 1 points queued, 2 queued points submitted, 3 live
+  uint32_t kf_seq[SDVLB_SEQ_KF_CAP] = {};   // submission that carried the slot's points to the device
+};
+
+struct SeqSubmission {   // one sdvlb_seq_track_submit in flight
+  uint32_t seq_no = 0;
+  int slot = 0;
+  std::vector<sdvlb_seq*> seqs;
+  std::vector<sdvlb_frame*> frames;
 };
 
 struct sdvlb_ctx {
@@ -131,16 +143,12 @@ struct sdvlb_ctx {
   uint8_t* scratch = nullptr;    // device-only scratch for ImageAlign caches
   size_t scratch_cap = 0;
   // resident sequences (seq_api.cu)
-  Arena seq_in;                  // commands + new points (pinned + device copy)
+  Arena seq_in[SDVLB_SEQ_DEPTH];   // commands + new points (pinned + device copy), one staging per submission slot
   std::vector<SeqCmd> seq_cmds;  // queued by sdvlb_seq_reset / _add_points until the next submission
   std::vector<sdvlb_seq_point> seq_pts;
   std::vector<const sdvlb_frame*> seq_cmd_frames;
-  AlignJobDev* d_seq_jobs = nullptr;
-  FrameDev* d_seq_frames = nullptr;
   uint32_t* d_seq_done = nullptr;
-  bool seq_active = false;
-  std::vector<sdvlb_seq*> seq_inflight;
-  std::vector<sdvlb_frame*> seq_inflight_frames;
+  std::deque<SeqSubmission> seq_queue;   // submissions in flight, oldest first (at most SDVLB_SEQ_DEPTH)
   std::vector<sdvlb_seq*> seqs;  // every sequence created on this context
   // counters
   int64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -161,5 +169,5 @@ void timer_end(sdvlb_ctx* c);
 int wait_frame_built(sdvlb_ctx* c, const sdvlb_frame* f, cudaStream_t stream);   // orders `stream` after f's batch
 void finalize_build(sdvlb_ctx* c, sdvlb_frame* f);
 int check_overflow(sdvlb_ctx* c);
-int wait_signal(sdvlb_ctx* c);   // spins on the pinned completion word of the last submission
+int wait_signal(sdvlb_ctx* c, uint32_t seq_no);   // spins on the pinned completion word until submission seq_no is done
 }  // namespace sdvlb_detail

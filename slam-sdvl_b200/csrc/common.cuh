@@ -67,8 +67,12 @@ struct DevParams {
   sdvlb_camera cam;
 };
 
-// doubles of ImageAlign scratch per feature: xyz[3], j0[6], j1[6], per-level J J^T sum [21]
-#define SDVLB_ALIGN_SC_DOUBLES 36
+// ImageAlign scratch in global memory per feature: 38 doubles (the level's per-feature J J^T sum [21]; xyz[3], j0[6],
+// j1[6], px[2] for the features that do not fit the kernel's shared-memory cache), 52 floats (patch[16], dx[16], dy[16]
+// + 4 pad of the same overflow features) and one flag word.
+#define SDVLB_ALIGN_SC_DOUBLES 38
+#define SDVLB_ALIGN_SC_FLOATS 52
+#define SDVLB_ALIGN_SC_BYTES(n) (size_t(n) * (SDVLB_ALIGN_SC_DOUBLES * 8 + SDVLB_ALIGN_SC_FLOATS * 4 + 4))
 // One ImageAlign::ComputePose call (device descriptor).
 struct AlignJobDev {
   FrameDev ref, cur;
@@ -442,24 +446,53 @@ __host__ __device__ inline void jacobian3d_to_plane(double x, double y, double z
   J1[5] = -x * z_inv;
 }
 
-// Every kernel of the library asks for the SAME shared-memory carve-out.  An SM runs CTAs of different kernels side by
-// side only if they agree on the L1 / shared-memory split; with per-kernel defaults the big-smem kernels (ImageAlign,
-// FeatureAlign) and the small-smem ones (FAST, pyramid, SearchPoint) of different streams could not share SMs and the
-// build stream serialised against the tracking stream.
+// One-time per (device, kernel) launch preparation, safe to call from any host thread before every launch: the common
+// shared-memory carve-out and the opt-in to `dyn_smem_bytes` of dynamic shared memory (raised when a later call asks for
+// more).  cudaFuncSetAttribute applies to the CURRENT device only, so the record is kept per device.
+//
+// Every kernel of the library asks for the SAME carve-out: an SM runs CTAs of different kernels side by side only if
+// they agree on the L1 / shared-memory split; with per-kernel defaults the big-smem kernels (ImageAlign, FeatureAlign)
+// and the small-smem ones (FAST, pyramid, SearchPoint) of different streams could not share SMs and the build stream
+// serialised against the tracking stream.
 #if defined(__CUDACC__)
-#include <cstdlib>
+cudaError_t sdvlb_kernel_prepare_ptr(const void* kernel, int dyn_smem_bytes);
 template <typename K>
-inline void sdvlb_common_carveout(K kernel) {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  static int pct = -2;
-  if (pct == -2) {
-    const char* e = getenv("SDVLB_CARVEOUT");
-    pct = e ? atoi(e) : 100;
-  }
-  if (pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+inline cudaError_t sdvlb_kernel_prepare(K kernel, size_t dyn_smem_bytes = 0) {
+  return sdvlb_kernel_prepare_ptr(reinterpret_cast<const void*>(kernel), int(dyn_smem_bytes));
 }
+// Programmatic dependent launch: a kernel launched with sdvlb_launch_dependent may start while the previous kernel of
+// its stream is still running, once every CTA of that kernel has called sdvlb_launch_dependents() (or exited); it must
+// call sdvlb_grid_dependency_wait() before it touches anything the previous kernel writes (the wait returns when that
+// grid has completed and its memory operations are visible).  The tracking chain of a sequence is three short
+// kernels per frame, so the launch latency between them is a visible part of a frame's latency.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void sdvlb_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void sdvlb_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+inline void sdvlb_grid_dependency_wait() {}
+inline void sdvlb_launch_dependents() {}
+#endif
+template <typename... KArgs, typename... Args>
+inline cudaError_t sdvlb_launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t dyn_smem,
+                                          cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = dyn_smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// inside a launcher that returns cudaError_t
+#define SDVLB_PREPARE(kernel, dyn)                                             \
+  do {                                                                         \
+    const cudaError_t pe_ = sdvlb_kernel_prepare(kernel, dyn);                 \
+    if (pe_ != cudaSuccess) return pe_;                                        \
+  } while (0)
 #endif
 
 // error handling shared by the host side

@@ -513,7 +513,7 @@ cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, u
                                     cudaStream_t stream) {
   const FastArgs& A = plan.args;
   dim3 g1((A.g.total_cells + DET_WARPS - 1) / DET_WARPS, B.n);
-  sdvlb_common_carveout(fast_cells_kernel);
+  SDVLB_PREPARE(fast_cells_kernel, 0);
   fast_cells_kernel<<<g1, DET_THREADS, 0, stream>>>(B, A, cell_kp, cell_cnt);
   return cudaGetLastError();
 }
@@ -525,14 +525,8 @@ cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, 
   dim3 g2(A.n_fast_levels, B.n);
   const int pool_keys = 12288;   // 48 KB: 256 cells x 48 keypoints on average after NMS
   const size_t dyn = size_t(3 * plan.max_cells_level + 4 + pool_keys) * sizeof(int);
-  static bool attr_set = false;
-  if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(fast_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
   if (dyn > 160 * 1024) return cudaErrorInvalidValue;
-  sdvlb_common_carveout(fast_select_kernel);
+  SDVLB_PREPARE(fast_select_kernel, dyn);
   fast_select_kernel<<<g2, SEL_THREADS, dyn, stream>>>(B, A, cell_kp, cell_cnt, level_kp, level_cnt, frame_ticket,
                                                       pool_keys);
   return cudaGetLastError();

@@ -104,7 +104,7 @@ extern "C" int sdvlb_frame_filter_corners(sdvlb_ctx* c, const sdvlb_frame* f, co
                                           int min_feature_score, int32_t* indices, int cap, int* n_out) {
   if (!c || !f || n_locked < 0 || (n_locked > 0 && !locked_px) || !indices || !n_out)
     return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
-  if (c->pending.active || c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
+  if (c->pending.active || !c->seq_queue.empty()) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
   SDVLB_CUDA_TRY(cudaSetDevice(c->device));
   sdvlb_frame* mf = const_cast<sdvlb_frame*>(f);
   if (mf->build_pending) {
@@ -142,7 +142,7 @@ extern "C" int sdvlb_frame_filter_corners(sdvlb_ctx* c, const sdvlb_frame* f, co
   A.score = reinterpret_cast<double*>(in.d + o_score);
   A.cell = reinterpret_cast<int32_t*>(in.d + o_cell);
   A.out = reinterpret_cast<int32_t*>(in.d + o_out);
-  sdvlb_common_carveout(filter_corners_kernel);
+  SDVLB_PREPARE(filter_corners_kernel, 0);
   filter_corners_kernel<<<1, FC_THREADS, 0, c->stream>>>(A);
   SDVLB_CUDA_TRY(cudaGetLastError());
   c->n_launches += 1;

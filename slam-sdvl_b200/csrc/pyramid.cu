@@ -355,7 +355,7 @@ cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int by
     upload_bulk_kernel<<<ctas, 32, 0, stream>>>(B, I, bytes, (unsigned long long)(min_ns * B.n));
   } else {
     dim3 grid(bulk ? 1 : ctas, B.n);
-    sdvlb_common_carveout(upload_kernel);
+    SDVLB_PREPARE(upload_kernel, 0);
     upload_kernel<<<grid, 256, 0, stream>>>(B, I, bytes);
   }
   return cudaGetLastError();
@@ -364,7 +364,7 @@ cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int by
 cudaError_t sdvlb_launch_undistort(const FrameBatch& B, const ImageBatch& raw, const UndistortArgs& U, cudaStream_t stream) {
   const int groups = ((U.w + 3) >> 2) * U.h;
   dim3 grid((groups + 255) / 256, B.n);
-  sdvlb_common_carveout(undistort_kernel);
+  SDVLB_PREPARE(undistort_kernel, 0);
   undistort_kernel<<<grid, 256, 0, stream>>>(B, raw, U);
   return cudaGetLastError();
 }
@@ -382,18 +382,11 @@ cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStre
   for (int l = 1; l <= direct_to; l++) {
     const int tasks = ((g.w[l] + 7) >> 3) * g.h[l];
     dim3 grid((tasks + PD_THREADS - 1) / PD_THREADS, B.n);
-    sdvlb_common_carveout(pyr_down_kernel);
+    SDVLB_PREPARE(pyr_down_kernel, 0);
     pyr_down_kernel<<<grid, PD_THREADS, 0, stream>>>(B, g.off[l - 1], g.w[l - 1], g.h[l - 1], g.off[l], g.w[l], g.h[l]);
   }
   if (tail_src > 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      const cudaError_t e = cudaFuncSetAttribute(pyr_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 int(kTailSmemMax));
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
-    sdvlb_common_carveout(pyr_tail_kernel);
+    SDVLB_PREPARE(pyr_tail_kernel, smem);
     pyr_tail_kernel<<<B.n, PT_THREADS, smem, stream>>>(B, g, tail_src);
   }
   return cudaGetLastError();

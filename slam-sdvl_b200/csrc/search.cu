@@ -399,16 +399,40 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_orb_kernel(const Sea
   search_one<true>(cands[ci], cur, out + ci, A.g, A.dp, s_bp[warp], s_patch[warp], q_desc + size_t(ci) * 8, cur_desc);
 }
 
-// Resident sequences: blockIdx.y = sequence of the step; candidates, their count and the matches live in the
-// sequence's own device state (written by seq_prep_kernel).
+// Resident sequences: blockIdx.y = sequence of the step, one warp per feature of the sequence's last frame.  A feature
+// that observes a point is a candidate (FeatureAlign::ProjectPoints, feature_align.cc:296-321): lane 0 assembles the
+// SearchPoint arguments from the feature and its keyframe slot in shared memory, the match goes to the sequence's own
+// device state at the feature's index.
 __global__ void __launch_bounds__(SE_THREADS) search_seq_kernel(const __grid_constant__ SeqStepArgs A) {
   __shared__ uint8_t s_bp[SE_WARPS][104];
   __shared__ uint8_t s_patch[SE_WARPS][64];
-  const int warp = threadIdx.x >> 5;
+  __shared__ SearchCandDev s_cand[SE_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SeqState* S = A.seq[blockIdx.y];
-  const int ci = blockIdx.x * SE_WARPS + warp;
-  if (ci >= S->n_cands) return;
-  search_one(S->cands[ci], A.cur[blockIdx.y], S->matches + ci, A.g, A.dp, s_bp[warp], s_patch[warp]);
+  const int fi = blockIdx.x * SE_WARPS + warp;
+  sdvlb_grid_dependency_wait();   // the align kernel's commands decide which features exist
+  sdvlb_launch_dependents();      // the post kernel's CTAs (one per sequence) may take their places and wait
+  if (!S->has_last || S->hold || fi >= S->n_list) return;
+  const SeqFeat& ft = S->list[S->cur][fi];
+  if (!(ft.flags & SEQF_HAS_POINT)) return;
+  if (lane == 0) {
+    SearchCandDev& c = s_cand[warp];
+    const SeqKf& K = S->kf[ft.kf];
+    c.ref_pyr = K.pyr;
+#pragma unroll
+    for (int i = 0; i < 7; i++) c.ref_T[i] = K.T[i];
+    c.ref_px[0] = ft.ref_px[0]; c.ref_px[1] = ft.ref_px[1];
+    c.ref_v[0] = ft.ref_v[0]; c.ref_v[1] = ft.ref_v[1]; c.ref_v[2] = ft.ref_v[2];
+    c.idepth = ft.idepth; c.idepth_std = ft.idepth_std;
+    c.px[0] = 0.0; c.px[1] = 0.0;
+    c.pos[0] = ft.pos[0]; c.pos[1] = ft.pos[1]; c.pos[2] = ft.pos[2];
+    c.ref_level = ft.ref_level;
+    c.flags = SDVLB_CAND_PROJECT | ((ft.flags & SEQF_FIXED) ? SDVLB_CAND_FIXED : 0);
+    c.cur_index = blockIdx.y;
+    c.pad_ = 0;
+  }
+  __syncwarp();
+  search_one(s_cand[warp], A.cur[blockIdx.y], S->matches + fi, A.g, A.dp, s_bp[warp], s_patch[warp]);
 }
 
 // ---- Map::UpdateCandidates (map.cc:397-498): one warp per depth-filter seed.  The geometry is a few dozen fp64
@@ -596,7 +620,7 @@ __global__ void signal_kernel(volatile uint32_t* flag, uint32_t seq) {
 }  // namespace
 
 cudaError_t sdvlb_launch_signal(uint32_t* h_flag, uint32_t seq, cudaStream_t stream) {
-  sdvlb_common_carveout(signal_kernel);
+  SDVLB_PREPARE(signal_kernel, 0);
   signal_kernel<<<1, 1, 0, stream>>>(h_flag, seq);
   return cudaGetLastError();
 }
@@ -608,7 +632,7 @@ cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const Frame
   A.g = g;
   A.dp = dp;
   A.n = n;
-  sdvlb_common_carveout(search_points_kernel);
+  SDVLB_PREPARE(search_points_kernel, 0);
   search_points_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, d_frames, d_out, A);
   return cudaGetLastError();
 }
@@ -621,7 +645,7 @@ cudaError_t sdvlb_launch_search_orb(const SearchCandDev* d_cands, int n, const F
   A.g = g;
   A.dp = dp;
   A.n = n;
-  sdvlb_common_carveout(search_points_orb_kernel);
+  SDVLB_PREPARE(search_points_orb_kernel, 0);
   search_points_orb_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, cur, d_out, A, d_qdesc, d_curdesc);
   return cudaGetLastError();
 }
@@ -634,14 +658,13 @@ cudaError_t sdvlb_launch_seed_update(sdvlb_seed* d_seeds, int n, const FrameDev&
   A.dp = dp;
   A.sp = sp;
   A.n = n;
-  sdvlb_common_carveout(seed_update_kernel);
+  SDVLB_PREPARE(seed_update_kernel, 0);
   seed_update_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_seeds, cur, A);
   return cudaGetLastError();
 }
 
 cudaError_t sdvlb_launch_search_seq(const SeqStepArgs& A, cudaStream_t stream) {
-  const dim3 grid((A.max_feats + SE_WARPS - 1) / SE_WARPS, A.n);
-  sdvlb_common_carveout(search_seq_kernel);
-  search_seq_kernel<<<grid, SE_THREADS, 0, stream>>>(A);
-  return cudaGetLastError();
+  const dim3 grid((A.max_feats + SE_WARPS - 1) / SE_WARPS, A.n);   // max_feats: the caller's bound on features per sequence
+  SDVLB_PREPARE(search_seq_kernel, 0);
+  return sdvlb_launch_dependent(search_seq_kernel, grid, dim3(SE_THREADS), 0, stream, A);
 }

@@ -1,24 +1,27 @@
-// seq.cu — resident sequences: everything SDVL::ProcessFrame does around ImageAlign and SearchPoint, on the device.
+// seq.cu — resident sequences: everything SDVL::ProcessFrame does after ImageAlign and SearchPoint, on the device.
 //
-//   seq_apply_kernel : host commands (restart a track, append the mapping thread's new points to the current frame)
-//   seq_prep_kernel  : SetMotionModel (sdvl.cc:278-281), ImageAlign feature marshalling (image_align.cc:154-160,
-//                      229-235), FeatureAlign::ProjectPoints candidate list (feature_align.cc:296-321)
-//   [image_align_kernel, search_points_kernel: align.cu / search.cu]
+//   seq_apply_kernel : host commands for sequences that are not part of the step being submitted (the others get
+//                      theirs applied by their own seq_align_kernel CTA, align.cu)
+//   [seq_align_kernel, search_seq_kernel: align.cu / search.cu]
 //   seq_post_kernel  : FeatureAlign::ProjectPoint binning + SelectPoints (feature_align.cc:88-150,323-339),
 //                      SelectInliers (RANSAC, :152-216), OptimizePose / RescueOutliers / RemoveOutliers (:73-82,
-//                      :218-256), ConvergePose (:341-421), GetMotionModel (sdvl.cc:266-276); writes the sequence's
-//                      next feature list and its pinned host result
+//                      :218-256), ConvergePose (:341-421), GetMotionModel (sdvl.cc:266-276), CalcTrackingQuality
+//                      (sdvl.cc:240-264) and Map::NeedKeyframe (map.cc:170-188); writes the sequence's next feature list
+//                      and its pinned host result
 //   pose_call_kernel : SelectInliers / OptimizePose alone (sdvlb_select_inliers, sdvlb_optimize_pose)
 //
 // One CTA per sequence.  SelectPoints is order-exact without walking the reference's per-cell std::list: the reference
 // visits the 32-px cells in cell_order_ order, inside a cell the points by descending Point::Score() (stable), stops a
 // cell at its first match and everything at max_matches matches.  Here every candidate gets its rank inside its cell
-// (score desc, candidate index asc), a cell's match is its lowest-ranked found candidate, a prefix sum over the cells in
-// cell_order_ gives both the max_matches cut-off and each match's index in fs_found.  RANSAC evaluates all
-// max_ransac_its hypotheses at once (one thread each, 5-point Gauss-Newton in registers), then one thread replays the
-// reference's adaptive iteration count over the results, so the same hypothesis wins and rand() advances by exactly the
-// number of draws the reference makes.  The next frame's random_shuffle of cell_order_ (the only other rand() consumer)
-// runs on a ninth warp while the other eight refine the pose.
+// (score desc, candidate index asc; candidates of a cell are chained through a shared-memory list, so a rank costs a
+// walk over the handful of candidates of that cell), a cell's match is its lowest-ranked found candidate, a prefix sum
+// over the cells in cell_order_ gives both the max_matches cut-off and each match's index in fs_found.  RANSAC
+// evaluates hypotheses in batches (8, 24, then the rest of max_ransac_its), one thread per hypothesis (5-point
+// Gauss-Newton in registers) with the supporter counts taken by all threads, and after each batch one thread replays
+// the reference's adaptive iteration count over the results: the same hypothesis wins and rand() advances by exactly
+// the number of draws the reference makes (with mostly-inlier matches the loop ends inside the first batch).  The next
+// frame's random_shuffle of cell_order_ (the only other rand() consumer) runs on a fifth warp while the other four
+// refine the pose.
 #include <climits>
 
 #include "seq.cuh"
@@ -321,7 +324,7 @@ struct RansacShared {
   int* hsup;                 // [R] supporters                                            } memory by ransac_carve()
   int* hconv;                // [R] ConvergePose returned true
   int* rnd;                  // [R] speculative draws
-  int best, draws;
+  int best, it, nits, best_supporters, more;
 };
 __host__ __device__ inline size_t ransac_bytes(int R) { return size_t(R) * (12 * sizeof(double) + 3 * sizeof(int)); }
 __device__ inline void ransac_carve(RansacShared& rs, unsigned char* mem, int R) {   // mem 8-byte aligned
@@ -333,62 +336,84 @@ __device__ inline void ransac_carve(RansacShared& rs, unsigned char* mem, int R)
 
 // FeatureAlign::SelectInliers (feature_align.cc:152-216) over P (= fs_found): flags every observation INLIER/OUTLIER.
 // T_frame: frame->GetPose().  *rng advances by the reference's number of rand() calls.  Main threads only.
+//
+// Hypotheses h0..h1 of a batch are spread over the four warps (hypothesis h0 + k on warp k % 4): a warp waits for its
+// slowest Gauss-Newton loop, so the first, small batch -- the one that usually settles the loop -- has two per warp.
 __device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, const DevParams& dp, sdvlb_rand* rng,
                                    RansacShared& rs, long long* stamps = nullptr) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int size = P.n;
   if (size == 0) return;
   const int R = min(dp.p.max_ransac_its, HYP_MAX);
   const int np = min(min(dp.p.max_ransac_points, size), RANSAC_MAX_PTS);
   const double thr = dp.p.inlier_error_threshold / dp.cam.fx;
   if (tid < 34) rs.backup.r[tid] = rng->r[tid];
-  if (tid == 0) rs.backup.n = rng->n;
+  if (tid == 0) {
+    rs.backup.n = rng->n;
+    rs.best = -1; rs.it = 0; rs.nits = dp.p.max_ransac_its; rs.best_supporters = 0; rs.more = 1;
+  }
   main_sync();
-  if (tid == 0)   // speculative draws for every hypothesis; the stream is rewound to the reference's count below
-    for (int h = 0; h < R; h++) rs.rnd[h] = rand_next(rng);
-  main_sync();
-  for (int h = tid; h < R; h += PO_MAIN) {
-    DSE3 T;
-    const bool ok = np == 5 ? converge_pose_small<5>(P, rs.rnd[h] % size, np, size, se3_load(T_frame), dp, &T)
-                            : converge_pose_small<0>(P, rs.rnd[h] % size, np, size, se3_load(T_frame), dp, &T);
-    rs.hconv[h] = ok ? 1 : 0;
-    double Rt[12];
-    store_Rt(T, Rt);
+  int h0 = 0;
+  while (h0 < R) {
+    const int h1 = min(R, h0 == 0 ? 8 : (h0 == 8 ? 32 : R));
+    if (tid == 0)   // speculative draws of the batch; the stream is rewound to the reference's count below
+      for (int h = h0; h < h1; h++) rs.rnd[h] = rand_next(rng);
+    main_sync();
+    for (int k = lane * (PO_MAIN / 32) + warp; h0 + k < h1; k += PO_MAIN) {   // consecutive hypotheses on different warps
+      const int h = h0 + k;
+      {
+        DSE3 T;
+        const bool ok = np == 5 ? converge_pose_small<5>(P, rs.rnd[h] % size, np, size, se3_load(T_frame), dp, &T)
+                                : converge_pose_small<0>(P, rs.rnd[h] % size, np, size, se3_load(T_frame), dp, &T);
+        rs.hconv[h] = ok ? 1 : 0;
+        rs.hsup[h] = 0;
+        double Rt[12];
+        store_Rt(T, Rt);
 #pragma unroll
-    for (int k = 0; k < 12; k++) rs.hRt[h][k] = Rt[k];
-    // CheckReprojectionError of this hypothesis against every match (feature_align.cc:258-283); the observation
-    // loads are warp-uniform
-    int sup = 0;
-    for (int i = 0; i < size; i++) sup += within_threshold(Rt, P, i, thr) ? 1 : 0;
-    rs.hsup[h] = sup;
-  }
-  main_sync();
-  if (stamps) stamps[0] = clock64();
-  if (stamps) stamps[1] = clock64();
-  if (tid == 0) {   // the reference's loop, replayed over the precomputed hypotheses
-    const double sprob = 0.99;
-    int nits = dp.p.max_ransac_its, it = 0, best_supporters = 0, best = -1;
-    while (it < nits && it < R) {
-      if (rs.hconv[it] && rs.hsup[it] > best_supporters) {
-        best = it;
-        best_supporters = rs.hsup[it];
-        const double epsilon = 1.0 - (double(best_supporters) / double(size));
-        double tmp = 1.0 - epsilon;
-        for (int k = 1; k < np; k++) tmp *= tmp;
-        if (tmp < 1e-5) nits = dp.p.max_ransac_its;
-        else nits = min(dp.p.max_ransac_its, int(log(1.0 - sprob) / log(1.0 - tmp)));
+        for (int q = 0; q < 12; q++) rs.hRt[h][q] = Rt[q];
       }
-      it++;
     }
-    rs.best = best;
-    rs.draws = it;
-    if (it < R) {   // rewind: the reference drew `it` numbers only
-      for (int k = 0; k < 34; k++) rng->r[k] = rs.backup.r[k];
-      rng->n = rs.backup.n;
-      for (int k = 0; k < it; k++) rand_next(rng);
+    main_sync();
+    if (stamps && h0 == 0) stamps[0] = clock64();
+    // CheckReprojectionError of every hypothesis of the batch against every match (feature_align.cc:258-283): thread t
+    // tests matches t, t + 128, ... against all of them; counts by ballot, one shared-memory add per warp and hypothesis
+    for (int i0 = 0; i0 < size; i0 += PO_MAIN) {
+      const int i = i0 + tid;
+      for (int h = h0; h < h1; h++) {
+        const bool in = i < size && within_threshold(rs.hRt[h], P, i, thr);
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0 && bal) atomicAdd(&rs.hsup[h], __popc(bal));   // integer adds: order does not matter
+      }
     }
+    main_sync();
+    if (tid == 0) {   // the reference's loop, replayed over the hypotheses computed so far
+      const double sprob = 0.99;
+      int nits = rs.nits, it = rs.it, best_supporters = rs.best_supporters, best = rs.best;
+      while (it < nits && it < h1) {
+        if (rs.hconv[it] && rs.hsup[it] > best_supporters) {
+          best = it;
+          best_supporters = rs.hsup[it];
+          const double epsilon = 1.0 - (double(best_supporters) / double(size));
+          double tmp = 1.0 - epsilon;
+          for (int k = 1; k < np; k++) tmp *= tmp;
+          if (tmp < 1e-5) nits = dp.p.max_ransac_its;
+          else nits = min(dp.p.max_ransac_its, int(log(1.0 - sprob) / log(1.0 - tmp)));
+        }
+        it++;
+      }
+      rs.nits = nits; rs.it = it; rs.best_supporters = best_supporters; rs.best = best;
+      rs.more = (it < nits && h1 < R) ? 1 : 0;
+    }
+    main_sync();
+    h0 = h1;
+    if (!rs.more) break;
   }
-  main_sync();
+  if (stamps) stamps[1] = clock64();
+  if (tid == 0) {   // rewind: the reference drew rs.it numbers only
+    for (int k = 0; k < 34; k++) rng->r[k] = rs.backup.r[k];
+    rng->n = rs.backup.n;
+    for (int k = 0; k < rs.it; k++) rand_next(rng);
+  }
   // "Get low innovation inliers" with best_se3 (identity when no hypothesis ever had a supporter)
   double Rt[12];
   if (rs.best >= 0) {
@@ -449,159 +474,11 @@ __device__ void optimize_pose_cta(const PoseProblem& P, double* T_frame, const D
 }
 
 // ------------------------------------------------------------------------------------------------ commands
-// The commands of one sequence (contiguous, applied in order) by the threads of one CTA.
-__device__ void apply_commands(const SeqCmd* __restrict__ cmds, int2 range, const DevParams& dp, int* s_base) {
-  const int tid = threadIdx.x;
-  for (int ci = range.x; ci < range.x + range.y; ci++) {
-    const SeqCmd& C = cmds[ci];
-    SeqState* S = C.seq;
-    if (C.kind == 0) {
-      if (tid == 0) {
-        for (int i = 0; i < 7; i++) S->T_last[i] = C.T[i];
-        for (int i = 0; i < 6; i++) S->vel[i] = 0.0;
-        S->last = C.frame;
-        S->has_last = 1;
-        S->n_list = 0;
-        S->n_cands = 0;
-        for (int i = 0; i < 7; i++) C.frame.pose[i] = C.T[i];
-      }
-      __syncthreads();
-      continue;
-    }
-    // append points to the current list (keyframe seeding / mapping thread output)
-    if (tid == 0) {
-      *s_base = S->n_list;
-      SeqKf& K = S->kf[C.kf_slot];
-      K.pyr = C.kf_pyr;
-      for (int i = 0; i < 7; i++) K.T[i] = C.T[i];
-    }
-    __syncthreads();
-    const int base = *s_base;
-    SeqFeat* L = S->list[S->cur];
-    for (int k = tid; k < C.n; k += blockDim.x) {
-      if (base + k >= S->max_feats) break;
-      const sdvlb_seq_point p = C.pts[k];
-      SeqFeat f;
-      f.px[0] = p.cur_px[0]; f.px[1] = p.cur_px[1];
-      cam_unproject_unit(dp.cam, p.cur_px[0], p.cur_px[1], f.v);
-      f.pos[0] = p.pos[0]; f.pos[1] = p.pos[1]; f.pos[2] = p.pos[2];
-      f.ref_px[0] = p.ref_px[0]; f.ref_px[1] = p.ref_px[1];
-      cam_unproject_unit(dp.cam, p.ref_px[0], p.ref_px[1], f.ref_v);
-      f.idepth = p.idepth; f.idepth_std = p.idepth_std;
-      f.user_id = p.user_id;
-      f.level = p.cur_level; f.ref_level = p.ref_level;
-      f.kf = C.kf_slot;
-      f.flags = SEQF_HAS_POINT | ((p.flags & SDVLB_CAND_FIXED) ? SEQF_FIXED : 0);
-      f.n_successful = p.n_successful; f.n_failed = p.n_failed;
-      f.status = SEQP_FOUND;
-      f.n_unpromoted = 0;
-      L[base + k] = f;
-    }
-    __syncthreads();
-    if (tid == 0) S->n_list = min(base + C.n, S->max_feats);
-    __syncthreads();
-  }
-}
-
 // One CTA per sequence that has commands (sequences that are not part of the step being submitted).
 __global__ void __launch_bounds__(128) seq_apply_kernel(const SeqCmd* __restrict__ cmds, const int2* __restrict__ ranges,
                                                         const __grid_constant__ DevParams dp) {
   __shared__ int s_base;
-  apply_commands(cmds, ranges[blockIdx.x], dp, &s_base);
-}
-
-// ------------------------------------------------------------------------------------------------ prep
-__global__ void __launch_bounds__(128) seq_prep_kernel(const __grid_constant__ SeqStepArgs A) {
-  SeqState* S = A.seq[blockIdx.x];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ double s_C[3];
-  __shared__ int s_warp_cnt[4];
-  __shared__ int s_base;
-  if (A.cmd_range[blockIdx.x].y > 0) {   // the mapping thread's commands for this sequence (keyframes), in order
-    apply_commands(A.cmds, A.cmd_range[blockIdx.x], A.dp, &s_base);
-    __threadfence_block();
-    __syncthreads();
-  }
-  AlignJobDev& J = A.jobs[blockIdx.x];
-  const int n = S->has_last ? S->n_list : 0;
-  if (tid == 0) {
-    A.frames[blockIdx.x] = A.cur[blockIdx.x];
-    s_base = 0;
-    const DSE3 T_last = se3_load(S->T_last);
-    const DSE3 Twc = se3_inverse(T_last);   // Frame::GetWorldPosition (frame.h)
-    s_C[0] = Twc.tx; s_C[1] = Twc.ty; s_C[2] = Twc.tz;
-    const DSE3 prior = se3_mul(se3_exp(S->vel), T_last);   // SDVL::SetMotionModel (sdvl.cc:278-281)
-    J.ref = S->last;
-    J.cur = A.cur[blockIdx.x];
-    J.feats = S->afeat;
-    J.n = S->has_last ? n : -1;
-    J.fast = 0;
-    for (int i = 0; i < 7; i++) J.T_ref[i] = S->T_last[i];
-    se3_store(prior, J.T_cur);
-    J.out_pose = S->align_pose;
-    J.out_info = S->align_info;
-    J.out_error = &S->align_error;
-    J.out_cycles = S->align_cycles;
-    J.trace = nullptr; J.trace_cap = 0; J.forced_n = 0; J.forced_T = nullptr; J.forced_iters = nullptr;
-    const size_t nn = size_t(A.max_feats);
-    uint8_t* sc = S->align_scratch;
-    J.sc_d = reinterpret_cast<double*>(sc);
-    J.sc_f = reinterpret_cast<float*>(sc + nn * SDVLB_ALIGN_SC_DOUBLES * 8);
-    J.sc_flags = reinterpret_cast<int32_t*>(sc + nn * SDVLB_ALIGN_SC_DOUBLES * 8 + nn * 48 * 4);
-    S->align_info[0] = 0; S->align_info[1] = 0;
-    if (n == 0) {   // ImageAlign::ComputePose returns at once (image_align.cc:55-58); frame2 keeps the prior
-      se3_store(prior, S->align_pose);
-      se3_store(prior, A.cur[blockIdx.x].pose);
-    }
-  }
-  __syncthreads();
-  const SeqFeat* __restrict__ L = S->list[S->cur];
-  // ImageAlign features: every feature of the last frame; candidates: the ones that still observe a point
-  for (int b = 0; b < n; b += blockDim.x) {
-    const int f = b + tid;
-    bool valid = false;
-    SeqFeat ft;
-    if (f < n) {
-      ft = L[f];
-      valid = (ft.flags & SEQF_HAS_POINT) != 0;
-      sdvlb_align_feat a;
-      a.px[0] = ft.px[0]; a.px[1] = ft.px[1];
-      a.v[0] = ft.v[0]; a.v[1] = ft.v[1]; a.v[2] = ft.v[2];
-      const double dx = ft.pos[0] - s_C[0], dy = ft.pos[1] - s_C[1], dz = ft.pos[2] - s_C[2];
-      a.depth = valid ? sqrt(dx * dx + dy * dy + dz * dz) : 1.0;   // image_align.cc:159,234
-      a.valid = valid ? 1 : 0;
-      a.pad_ = 0;
-      S->afeat[f] = a;
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, valid);
-    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    int off = s_base;
-    for (int w = 0; w < warp; w++) off += s_warp_cnt[w];
-    if (valid) {
-      const int ci = off + __popc(bal & ((1u << lane) - 1));
-      SearchCandDev c;
-      const SeqKf& K = S->kf[ft.kf];
-      c.ref_pyr = K.pyr;
-#pragma unroll
-      for (int i = 0; i < 7; i++) c.ref_T[i] = K.T[i];
-      c.ref_px[0] = ft.ref_px[0]; c.ref_px[1] = ft.ref_px[1];
-      c.ref_v[0] = ft.ref_v[0]; c.ref_v[1] = ft.ref_v[1]; c.ref_v[2] = ft.ref_v[2];
-      c.idepth = ft.idepth; c.idepth_std = ft.idepth_std;
-      c.px[0] = 0.0; c.px[1] = 0.0;
-      c.pos[0] = ft.pos[0]; c.pos[1] = ft.pos[1]; c.pos[2] = ft.pos[2];
-      c.ref_level = ft.ref_level;
-      c.flags = SDVLB_CAND_PROJECT | ((ft.flags & SEQF_FIXED) ? SDVLB_CAND_FIXED : 0);
-      c.cur_index = blockIdx.x;
-      c.pad_ = 0;
-      S->cands[ci] = c;
-      S->cand_feat[ci] = f;
-    }
-    __syncthreads();
-    if (tid == 0) { for (int w = 0; w < 4; w++) s_base += s_warp_cnt[w]; }
-    __syncthreads();
-  }
-  if (tid == 0) S->n_cands = s_base;
+  seq_apply_commands(cmds, ranges[blockIdx.x], dp, &s_base);
 }
 
 // ------------------------------------------------------------------------------------------------ post
@@ -626,8 +503,10 @@ struct PostShared {
   int* win;                    // [n_cells] per cell: rank of its match (INT_MAX: none)          } dynamic shared
   int* slot;                   // [n_cells] index of its match in fs_found, -1: not visited     } memory
   int* order;                  // [n_cells] cell_order_
+  int* head;                   // [n_cells] first candidate of the cell's chain, -1: empty
   int scan[PO_MAIN];
   int attempts, n_found, n_inl, n_outl;
+  int adopt;
   int kf_live[SDVLB_SEQ_KF_CAP];
 };
 
@@ -640,8 +519,16 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   const int tid = threadIdx.x;
   const int n_cells = A.g.wcells[0] * A.g.hcells[0];
   const int gw = A.g.wcells[0];
-  if (!S->has_last) {         // uniform: nothing was tracked (no reset yet)
-    if (tid == 0) signal_done(A);
+  sdvlb_grid_dependency_wait();   // programmatic dependent launch: everything above overlaps the search kernel's tail
+  SeqResultHost* Rz = S->result[A.slot];
+  if (!S->has_last || S->hold) {   // uniform: no track yet (no reset) / waiting for the caller: the frame is not consumed
+    if (tid == 0) {
+      Rz->status = S->has_last ? SDVLB_SEQ_HELD : SDVLB_SEQ_IDLE;
+      Rz->error = S->overflow;
+      Rz->need_keyframe = 0;
+      Rz->lost_frames = S->lost_frames;
+      signal_done(A);
+    }
     return;
   }
   if (tid == 0) {             // small shared memory on purpose: this CTA must fit beside the build stream's kernels
@@ -651,11 +538,14 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     sh.win = reinterpret_cast<int*>(mem);
     sh.slot = sh.win + n_cells;
     sh.order = sh.slot + n_cells;
+    sh.head = sh.order + n_cells;
   }
   __syncthreads();
 
   // ---- load the persistent FeatureAlign state (all PO_THREADS threads)
-  for (int i = tid; i < n_cells; i += PO_THREADS) { sh.order[i] = S->cell_order[i]; sh.win[i] = INT_MAX; sh.slot[i] = -1; }
+  for (int i = tid; i < n_cells; i += PO_THREADS) {
+    sh.order[i] = S->cell_order[i]; sh.win[i] = INT_MAX; sh.slot[i] = -1; sh.head[i] = -1;
+  }
   if (tid < 34) sh.rng.r[tid] = S->rng.r[tid];
   if (tid == 0) {
     sh.rng.n = S->rng.n;
@@ -706,7 +596,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
       }
       __syncwarp();
       for (int i = lane; i < n_cells; i += 32) S->cell_order[i] = sh.order[i];
-      if (lane == 0) S->result->phase_cycles[7] = int(clock64() - t_entry);
+      if (lane == 0) Rz->phase_cycles[7] = int(clock64() - t_entry);
       return;
     }
     if (tid == PO_MAIN) {
@@ -719,31 +609,40 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     __syncwarp();
     for (int i = lane; i < n_cells; i += 32) S->cell_order[i] = sh.order[i];
     for (int i = lane; i < 34; i += 32) S->rng.r[i] = sh.rng.r[i];
-    if (lane == 0) { S->rng.n = sh.rng.n; S->result->phase_cycles[7] = int(clock64() - t_entry); }
+    if (lane == 0) { S->rng.n = sh.rng.n; Rz->phase_cycles[7] = int(clock64() - t_entry); }
     return;
   }
 
   // =============================== main threads (barrier 1) ===============================
   long long t_phase[8];
   t_phase[0] = clock64();
-  const SeqFeat* __restrict__ L = S->list[S->cur];
+  SeqFeat* __restrict__ L = S->list[S->cur];
   SeqFeat* __restrict__ NL = S->list[S->cur ^ 1];
-  const int nc = S->n_cands;
+  // Candidates = the features of the last frame that observe a point, in list order (FeatureAlign::ProjectPoints,
+  // feature_align.cc:296-321); a candidate's index is its feature index.
+  const int nc = S->n_list;
   const sdvlb_match* __restrict__ M = S->matches;
-  // cell / score of every candidate: in shared memory (the GN partials area is idle here) unless there are too many
-  constexpr int kSmemCands = NVP * PO_MAIN;   // two int arrays in NVP * PO_MAIN doubles
-  int32_t* __restrict__ c_cell = nc <= kSmemCands ? reinterpret_cast<int32_t*>(&part[0][0]) : S->c_cell;
-  int32_t* __restrict__ c_score = nc <= kSmemCands ? reinterpret_cast<int32_t*>(&part[0][0]) + kSmemCands : S->c_score;
+  // cell / score / chain link of every candidate: in shared memory (the GN partials area is idle here) unless there
+  // are too many
+  constexpr int kSmemCands = NVP * PO_MAIN * 2 / 3;   // three int arrays in NVP * PO_MAIN doubles
+  const bool in_smem = nc <= kSmemCands;
+  int32_t* __restrict__ c_cell = in_smem ? reinterpret_cast<int32_t*>(&part[0][0]) : S->c_cell;
+  int32_t* __restrict__ c_score = in_smem ? reinterpret_cast<int32_t*>(&part[0][0]) + kSmemCands : S->c_score;
+  int32_t* __restrict__ c_next = in_smem ? reinterpret_cast<int32_t*>(&part[0][0]) + 2 * kSmemCands : S->c_next;
   int32_t* __restrict__ c_rank = S->c_rank;
 
-  // ---- ProjectPoint bookkeeping (feature_align.cc:323-339): cell of every seen point
+  // ---- ProjectPoint bookkeeping (feature_align.cc:323-339): cell of every seen point, chained per cell
   for (int i = tid; i < nc; i += PO_MAIN) {
-    const sdvlb_match m = M[i];
+    const SeqFeat& ft = L[i];
     int cell = -1;
-    if (m.status != SDVLB_MATCH_UNSEEN) cell = int(m.proj[1] / SDVLB_CELL) * gw + int(m.proj[0] / SDVLB_CELL);
-    if (cell >= n_cells) cell = -1;
+    if (ft.flags & SEQF_HAS_POINT) {
+      const sdvlb_match m = M[i];
+      if (m.status != SDVLB_MATCH_UNSEEN) cell = int(m.proj[1] / SDVLB_CELL) * gw + int(m.proj[0] / SDVLB_CELL);
+      if (cell >= n_cells) cell = -1;
+    }
     c_cell[i] = cell;
-    c_score[i] = L[S->cand_feat[i]].n_successful;
+    c_score[i] = ft.n_successful;
+    if (cell >= 0) c_next[i] = atomicExch(&sh.head[cell], i);   // chain order is arbitrary; ranks do not depend on it
   }
   main_sync();
   // ---- rank inside the cell: Score() descending, stable (std::list::sort, feature_align.cc:111)
@@ -752,9 +651,9 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     if (cell < 0) { c_rank[i] = -1; continue; }
     const int sc = c_score[i];
     int rank = 0;
-    for (int j = 0; j < nc; j++) {
-      const int cj = c_cell[j], sj = c_score[j];
-      rank += (cj == cell && (sj > sc || (sj == sc && j < i))) ? 1 : 0;
+    for (int j = sh.head[cell]; j >= 0; j = c_next[j]) {
+      const int sj = c_score[j];
+      rank += (sj > sc || (sj == sc && j < i)) ? 1 : 0;
     }
     c_rank[i] = rank;
     if (M[i].status == SDVLB_MATCH_FOUND) atomicMin(&sh.win[cell], rank);
@@ -813,7 +712,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
       my_attempts++;
       if (rank == win && slot >= 0) {                 // found: Promote, new Feature(frame, px, level)
         const sdvlb_match m = M[i];
-        SeqFeat f = L[S->cand_feat[i]];
+        SeqFeat f = L[i];
         f.px[0] = m.px[0]; f.px[1] = m.px[1];
         cam_unproject_unit(A.dp.cam, m.px[0], m.px[1], f.v);
         f.level = m.level;
@@ -833,6 +732,37 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   }
   main_sync();
 
+  // ---- SDVL::CalcTrackingQuality (sdvl.cc:240-264), when the policy asks for it
+  const sdvlb_seq_policy pol = S->policy;
+  int quality = SDVLB_TRACKING_GOOD;
+  int lost_frames = S->lost_frames;
+  if (pol.tracking_quality) {
+    const int attempts = sh.attempts;
+    const double ratio = attempts == 0 ? 0.0 : double(n_found) / double(attempts);
+    if (ratio > 0.2) { quality = SDVLB_TRACKING_GOOD; lost_frames = 0; }
+    else if (n_found < A.dp.p.min_matches) { quality = SDVLB_TRACKING_BAD; lost_frames += 1; }
+    else { quality = SDVLB_TRACKING_INSUFFICIENT; lost_frames = 0; }
+  }
+  const bool adopt = quality != SDVLB_TRACKING_BAD;   // sdvl.cc:99,119: last_frame_ advances unless tracking is bad
+  if (!adopt) {
+    // The frame is dropped but the points were visited: Promote / Unpromote stay with them (they live in the list of
+    // the frame that remains the reference); a point that failed too often is deleted (point.cc:102-115, Map::DeletePoint)
+    for (int i = tid; i < nc; i += PO_MAIN) {
+      const int cell = c_cell[i];
+      if (cell < 0) continue;
+      const int slot = sh.slot[cell];
+      if (slot == -1) continue;
+      const int rank = c_rank[i], win = sh.win[cell];
+      if (rank > win) continue;
+      SeqFeat& f = L[i];
+      if (rank == win && slot >= 0) { f.n_successful += 1; f.n_failed = 0; }
+      else {
+        f.n_failed += 1; f.n_unpromoted += 1;
+        if (f.n_failed > A.dp.p.max_failed) f.flags &= ~SEQF_HAS_POINT;
+      }
+    }
+  }
+
   // ---- SelectInliers (RANSAC)
   t_phase[2] = clock64();
   t_phase[6] = t_phase[7] = t_phase[2];
@@ -846,7 +776,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   t_phase[4] = clock64();
 
   // ---- RemoveOutliers (feature_align.cc:245-256), result, GetMotionModel, state update
-  SeqResultHost* Rz = S->result;
+  sdvlb_launch_dependents();   // a queued next step may bring its align CTAs in; they wait for this grid to finish
   sdvlb_seq_feat* hfe = reinterpret_cast<sdvlb_seq_feat*>(reinterpret_cast<unsigned char*>(Rz) + sizeof(SeqResultHost));
   {
     int inl = 0, outl = 0;
@@ -866,18 +796,40 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     if (outl) atomicAdd(&sh.n_outl, outl);
   }
   main_sync();
+  if (!adopt) {   // the reference frame stays: its keyframes are the live ones
+    if (tid < SDVLB_SEQ_KF_CAP) sh.kf_live[tid] = 0;
+    main_sync();
+    for (int i = tid; i < nc; i += PO_MAIN)
+      if (L[i].flags & SEQF_HAS_POINT) atomicAdd(&sh.kf_live[L[i].kf], 1);
+    main_sync();
+  }
   if (tid < SDVLB_SEQ_KF_CAP) Rz->kf_live[tid] = sh.kf_live[tid];
   if (tid == 0) {
     const DSE3 T_new = se3_load(sh.T_frame);
-    const DSE3 mov = se3_mul(T_new, se3_inverse(se3_load(S->T_last)));   // sdvl.cc:266-276
+    const DSE3 mov = se3_mul(T_new, se3_inverse(se3_load(S->T_last)));   // SDVL::GetMotionModel, sdvl.cc:266-276
     double vel[6];
     se3_log(mov, vel);
     for (int i = 0; i < 6; i++) S->vel[i] = 0.9 * (0.5 * vel[i] + 0.5 * S->vel[i]);
-    for (int i = 0; i < 7; i++) { S->T_last[i] = sh.T_frame[i]; Rz->pose[i] = sh.T_frame[i]; A.cur[blockIdx.x].pose[i] = sh.T_frame[i]; }
-    S->last = A.cur[blockIdx.x];
-    S->n_list = n_found;
-    S->cur ^= 1;
-    S->frame_id += 1;
+    for (int i = 0; i < 7; i++) { Rz->pose[i] = sh.T_frame[i]; A.cur[blockIdx.x].pose[i] = sh.T_frame[i]; }
+    int need_kf = 0;
+    if (adopt) {
+      for (int i = 0; i < 7; i++) S->T_last[i] = sh.T_frame[i];
+      S->last = A.cur[blockIdx.x];
+      S->n_list = n_found;
+      S->cur ^= 1;
+      S->frame_id += 1;
+      // Map::NeedKeyframe (map.cc:170-188), asked only when tracking is good (sdvl.cc:100)
+      if (pol.keyframe_rule && quality == SDVLB_TRACKING_GOOD) {
+        const int npoints = sh.n_inl;   // frame->GetNumPoints()
+        const bool enough_its = (S->frame_id - S->last_kf_frame) >= pol.min_keyframe_its;
+        const bool lost_many = double(npoints) < double(S->last_matches) * pol.lost_ratio;
+        const bool lost_some = double(npoints) < double(S->last_matches) * 0.9;
+        S->last_matches = max(S->last_matches, npoints);
+        if ((enough_its && lost_some) || lost_many) { S->last_matches = npoints; need_kf = 1; }
+      }
+    }
+    S->lost_frames = lost_frames;
+    if (need_kf || (pol.tracking_quality && lost_frames >= 3)) S->hold = 1;   // sdvl.cc:74-91: relocalisation is the caller's
     Rz->stats[0] = S->align_info[0];
     Rz->stats[1] = n_found;
     Rz->stats[2] = sh.attempts;
@@ -886,14 +838,18 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     Rz->stats[5] = sh.n_inl;        // Frame::GetNumPoints(): features that still have a point
     Rz->stats[6] = S->align_info[1];
     Rz->stats[7] = n_found;
-    Rz->error = 0;
+    Rz->error = S->overflow;
+    Rz->status = SDVLB_SEQ_TRACKED;
+    Rz->quality = quality;
+    Rz->need_keyframe = need_kf;
+    Rz->lost_frames = lost_frames;
     // latency breakdown of this kernel in SM cycles
     t_phase[5] = clock64();
     Rz->phase_cycles[0] = int(t_phase[1] - t_phase[0]);
     Rz->phase_cycles[1] = int(t_phase[2] - t_phase[1]);
-    Rz->phase_cycles[2] = int(t_phase[6] - t_phase[2]);   // RANSAC: draws + hypotheses
+    Rz->phase_cycles[2] = int(t_phase[6] - t_phase[2]);   // RANSAC: draws + hypotheses of the first batch
     Rz->phase_cycles[3] = int(t_phase[0] - t_entry);      // kernel entry -> state loaded
-    Rz->phase_cycles[4] = int(t_phase[3] - t_phase[6]);   //         supporters, replay + final inlier flags
+    Rz->phase_cycles[4] = int(t_phase[3] - t_phase[6]);   //         supporters, replay, further batches, inlier flags
     Rz->phase_cycles[5] = int(t_phase[4] - t_phase[3]);
     Rz->phase_cycles[6] = int(t_phase[5] - t_phase[4]);
     for (int i = 0; i < 4; i++) Rz->align_cycles[i] = S->align_cycles[i];
@@ -950,52 +906,28 @@ __global__ void __launch_bounds__(PO_MAIN, 1) pose_call_kernel(const __grid_cons
   for (int i = tid; i < A.n; i += PO_MAIN) A.obs[i].flags = P.o_flag[i];
 }
 
-template <typename K>
-cudaError_t opt_in_smem(K kernel, size_t bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-}
-
 }  // namespace
 
 cudaError_t sdvlb_launch_seq_apply(const SeqCmd* d_cmds, const int2* d_ranges, int n_ranges, const DevParams& dp,
                                    cudaStream_t stream) {
   if (n_ranges <= 0) return cudaSuccess;
-  sdvlb_common_carveout(seq_apply_kernel);
+  SDVLB_PREPARE(seq_apply_kernel, 0);
   seq_apply_kernel<<<n_ranges, 128, 0, stream>>>(d_cmds, d_ranges, dp);
-  return cudaGetLastError();
-}
-
-cudaError_t sdvlb_launch_seq_prep(const SeqStepArgs& A, cudaStream_t stream) {
-  sdvlb_common_carveout(seq_prep_kernel);
-  seq_prep_kernel<<<A.n, 128, 0, stream>>>(A);
   return cudaGetLastError();
 }
 
 cudaError_t sdvlb_launch_seq_post(const SeqStepArgs& A, cudaStream_t stream) {
   const int n_cells = A.g.wcells[0] * A.g.hcells[0];
   const size_t dyn = ((sizeof(PostShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN +
-                     (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16 + size_t(3 * n_cells) * sizeof(int);
-  static bool attr_set = false;
-  if (!attr_set) {
-    const cudaError_t e = opt_in_smem(seq_post_kernel, 160 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  sdvlb_common_carveout(seq_post_kernel);
-  seq_post_kernel<<<A.n, PO_THREADS, dyn, stream>>>(A);
-  return cudaGetLastError();
+                     (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16 + size_t(4 * n_cells) * sizeof(int);
+  SDVLB_PREPARE(seq_post_kernel, dyn);
+  return sdvlb_launch_dependent(seq_post_kernel, dim3(A.n), dim3(PO_THREADS), dyn, stream, A);
 }
 
 cudaError_t sdvlb_launch_pose_call(const PoseCallArgs& A, cudaStream_t stream) {
   const size_t dyn = ((sizeof(PoseCallShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN +
                      (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    const cudaError_t e = opt_in_smem(pose_call_kernel, dyn);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  sdvlb_common_carveout(pose_call_kernel);
+  SDVLB_PREPARE(pose_call_kernel, dyn);
   pose_call_kernel<<<1, PO_MAIN, dyn, stream>>>(A);
   return cudaGetLastError();
 }

@@ -1,9 +1,15 @@
-// seq.cuh — device-side state of a resident sequence and the launch descriptors of its kernels (seq.cu), shared with the
-// host side of the C-ABI (seq_api.cu).
+// seq.cuh — device-side state of a resident sequence and the launch descriptors of its kernels (align.cu, search.cu,
+// seq.cu), shared with the host side of the C-ABI (seq_api.cu).
 //
 // A sequence's tracked state is the feature list of its last frame, every feature carrying the map point it observes
 // inline (the reference keeps Frame::features_ -> Feature -> Point objects on the heap, frame.h:148-172,
 // feature.h:97-104, point.h:121-146).  Two lists ping-pong: tracking frame k+1 reads list k and writes list k+1.
+//
+// A tracked frame is three launches: seq_align_kernel (commands of the mapping thread, motion-model prior,
+// ImageAlign), search_seq_kernel (one warp per feature that observes a point: ProjectPoint + SearchPoint) and
+// seq_post_kernel (SelectPoints, RANSAC, OptimizePose, motion model, tracking quality / keyframe decision, result).
+// Several steps may be queued behind each other: a sequence that needs its mapping thread (new keyframe) raises `hold`
+// and the steps already queued behind it leave it untouched until the caller has answered.
 #pragma once
 #include "common.cuh"
 
@@ -32,14 +38,18 @@ struct SeqKf {
   double T[7];         // its pose
 };
 
-// Pinned, device-visible result block of one sequence (written by seq_post_kernel).
+// Pinned, device-visible result block of one sequence and one submission slot (written by seq_post_kernel).
 struct SeqResultHost {
   double pose[7];
   int32_t stats[8];    // n_tracked(n_meas), matches, attempts, inliers, outliers, n_points, gn_iters, n_feats
   int32_t kf_live[SDVLB_SEQ_KF_CAP];
   int32_t error;       // != 0: a capacity was exceeded
+  int32_t status;      // SDVLB_SEQ_TRACKED / _HELD / _IDLE
+  int32_t quality;     // SDVL::CalcTrackingQuality: SDVLB_TRACKING_*
+  int32_t need_keyframe;   // Map::NeedKeyframe said yes (the sequence is on hold until the caller answers)
+  int32_t lost_frames;
   int32_t phase_cycles[8];   // seq_post_kernel latency breakdown (SM cycles of the sequence's CTA)
-  int32_t align_cycles[4];   // image_align_kernel: PrecomputePatches, residuals, reduction, solve + update
+  int32_t align_cycles[4];   // ImageAlign kernel: PrecomputePatches, residuals, reduction, solve + update
   int32_t pad_[3];
   // sdvlb_seq_feat feats[max_feats] follows
 };
@@ -51,11 +61,17 @@ struct SeqState {
   double vel[6];       // SDVL::vel_ (sdvl.cc:266-276)
   FrameDev last;       // that frame
   int32_t has_last;
-  int32_t frame_id;
+  int32_t frame_id;    // frames tracked since the last reset (the frame the current list belongs to)
   int32_t n_list;      // features in list[cur]
   int32_t cur;
-  int32_t n_cands;     // candidates of the step in flight
+  int32_t overflow;    // a command tried to append beyond max_feats (sticky until the next reset)
+  int32_t hold;        // != 0: waiting for the caller (keyframe / relocalisation); queued steps skip the sequence
+  // Map::NeedKeyframe (map.cc:170-188) / SDVL::CalcTrackingQuality (sdvl.cc:240-264) state
+  int32_t last_matches;
+  int32_t last_kf_frame;   // frame_id at which points were last appended (last_kf_->GetID())
+  int32_t lost_frames;
   int32_t pad0_;
+  sdvlb_seq_policy policy;
   sdvlb_rand rng;
   SeqKf kf[SDVLB_SEQ_KF_CAP];
   // ImageAlign outputs of the step in flight
@@ -67,15 +83,12 @@ struct SeqState {
   int32_t max_feats, n_cells;
   SeqFeat* list[2];
   int32_t* cell_order;             // FeatureAlign::cell_order_ (already shuffled for the next frame)
-  sdvlb_align_feat* afeat;         // ImageAlign features of the step in flight
-  SearchCandDev* cands;            // SearchPoint candidates
-  int32_t* cand_feat;              // candidate -> index in list[cur]
-  sdvlb_match* matches;
-  uint8_t* align_scratch;          // patch / Jacobian caches of image_align_kernel
-  // FeatureAlign scratch, one entry per candidate / found feature
-  int32_t* c_cell; int32_t* c_score; int32_t* c_rank;
+  sdvlb_match* matches;            // SearchPoint result per feature of list[cur]
+  uint8_t* align_scratch;          // per-feature H_f and cache overflow of the ImageAlign kernel
+  // FeatureAlign scratch, one entry per feature / found feature
+  int32_t* c_cell; int32_t* c_score; int32_t* c_rank; int32_t* c_next;
   double* o_a; double* o_pos; double* o_scale; double* o_err; int32_t* o_flag;
-  SeqResultHost* result;           // pinned host memory
+  SeqResultHost* result[SDVLB_SEQ_DEPTH];   // pinned host memory, one block per submission slot
 };
 
 // Pose-refinement problem (FeatureAlign lists as arrays): obs i is (a = SimpleProject(v), pos, scale = 2^-level).
@@ -90,22 +103,21 @@ struct SeqStepArgs {
   int max_feats;
   SeqState* seq[SDVLB_SEQ_BATCH];
   FrameDev cur[SDVLB_SEQ_BATCH];
-  AlignJobDev* jobs;     // n entries, written by the prep kernel
-  FrameDev* frames;      // n entries (SearchCandDev::cur_index)
-  const struct SeqCmd* cmds;            // commands of this step's sequences, applied by the prep kernel
+  const struct SeqCmd* cmds;            // commands of this step's sequences, applied by the align kernel
   int2 cmd_range[SDVLB_SEQ_BATCH];      // (first, count) per sequence of the step
   uint32_t* d_done;      // device counter of CTAs that finished the post kernel
-  uint32_t* h_flag;      // pinned completion word (nullptr: the caller launches signal_kernel itself)
+  uint32_t* h_flag;      // pinned completion word
   uint32_t seq_no;       // value to publish
-  uint32_t pad_;
+  int32_t slot;          // result slot of this submission (seq_no % SDVLB_SEQ_DEPTH)
   DevParams dp;
   PyrGeom g;
 };
 
-// Host -> device commands applied before a step (seq_apply_kernel): restart a track / append points.
+// Host -> device commands applied before a step: restart a track / append points / release a hold / set the policy.
+enum { SEQC_RESET = 0, SEQC_ADD_POINTS = 1, SEQC_RELEASE = 2, SEQC_POLICY = 3 };
 struct SeqCmd {
   SeqState* seq;
-  int32_t kind;          // 0 reset, 1 add points
+  int32_t kind;          // SEQC_*
   int32_t n;             // points
   int32_t kf_slot;
   int32_t pad_;
@@ -113,6 +125,7 @@ struct SeqCmd {
   const uint8_t* kf_pyr;
   double T[7];           // reset: pose; add: keyframe pose
   const sdvlb_seq_point* pts;   // device copy
+  sdvlb_seq_policy policy;
 };
 
 // One standalone FeatureAlign pose-refinement call (sdvlb_select_inliers / sdvlb_optimize_pose).
@@ -127,9 +140,81 @@ struct PoseCallArgs {
   DevParams dp;
 };
 
+#if defined(__CUDACC__)
+// The commands of one sequence (contiguous, applied in order) by the threads of one CTA (any block size).
+__device__ inline void seq_apply_commands(const SeqCmd* __restrict__ cmds, int2 range, const DevParams& dp, int* s_base) {
+  const int tid = threadIdx.x;
+  for (int ci = range.x; ci < range.x + range.y; ci++) {
+    const SeqCmd& C = cmds[ci];
+    SeqState* S = C.seq;
+    if (C.kind != SEQC_ADD_POINTS) {
+      if (tid == 0) {
+        if (C.kind == SEQC_RESET) {
+          for (int i = 0; i < 7; i++) S->T_last[i] = C.T[i];
+          for (int i = 0; i < 6; i++) S->vel[i] = 0.0;
+          S->last = C.frame;
+          S->has_last = 1;
+          S->n_list = 0;
+          S->frame_id = 0;
+          S->overflow = 0;
+          S->hold = 0;
+          S->last_matches = 0;
+          S->last_kf_frame = 0;
+          S->lost_frames = 0;
+          for (int i = 0; i < 7; i++) C.frame.pose[i] = C.T[i];
+        } else if (C.kind == SEQC_RELEASE) {
+          S->hold = 0;
+        } else if (C.kind == SEQC_POLICY) {
+          S->policy = C.policy;
+        }
+      }
+      __syncthreads();
+      continue;
+    }
+    // append points to the current list (keyframe seeding / mapping thread output); answers a keyframe hold
+    if (tid == 0) {
+      *s_base = S->n_list;
+      SeqKf& K = S->kf[C.kf_slot];
+      K.pyr = C.kf_pyr;
+      for (int i = 0; i < 7; i++) K.T[i] = C.T[i];
+    }
+    __syncthreads();
+    const int base = *s_base;
+    SeqFeat* L = S->list[S->cur];
+    for (int k = tid; k < C.n; k += blockDim.x) {
+      if (base + k >= S->max_feats) break;
+      const sdvlb_seq_point p = C.pts[k];
+      SeqFeat f;
+      f.px[0] = p.cur_px[0]; f.px[1] = p.cur_px[1];
+      cam_unproject_unit(dp.cam, p.cur_px[0], p.cur_px[1], f.v);
+      f.pos[0] = p.pos[0]; f.pos[1] = p.pos[1]; f.pos[2] = p.pos[2];
+      f.ref_px[0] = p.ref_px[0]; f.ref_px[1] = p.ref_px[1];
+      cam_unproject_unit(dp.cam, p.ref_px[0], p.ref_px[1], f.ref_v);
+      f.idepth = p.idepth; f.idepth_std = p.idepth_std;
+      f.user_id = p.user_id;
+      f.level = p.cur_level; f.ref_level = p.ref_level;
+      f.kf = C.kf_slot;
+      f.flags = SEQF_HAS_POINT | ((p.flags & SDVLB_CAND_FIXED) ? SEQF_FIXED : 0);
+      f.n_successful = p.n_successful; f.n_failed = p.n_failed;
+      f.status = SEQP_FOUND;
+      f.n_unpromoted = 0;
+      L[base + k] = f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (base + C.n > S->max_feats) S->overflow = 1;   // reported with every later result until the next reset
+      S->n_list = min(base + C.n, S->max_feats);
+      S->last_kf_frame = S->frame_id;
+      S->hold = 0;
+    }
+    __syncthreads();
+  }
+}
+#endif
+
 cudaError_t sdvlb_launch_seq_apply(const SeqCmd* d_cmds, const int2* d_ranges, int n_ranges, const DevParams& dp,
                                    cudaStream_t stream);
-cudaError_t sdvlb_launch_seq_prep(const SeqStepArgs& A, cudaStream_t stream);
+cudaError_t sdvlb_launch_seq_align(const SeqStepArgs& A, int n_bound, cudaStream_t stream);
+cudaError_t sdvlb_launch_search_seq(const SeqStepArgs& A, cudaStream_t stream);
 cudaError_t sdvlb_launch_seq_post(const SeqStepArgs& A, cudaStream_t stream);
 cudaError_t sdvlb_launch_pose_call(const PoseCallArgs& A, cudaStream_t stream);
-cudaError_t sdvlb_launch_search_seq(const SeqStepArgs& A, cudaStream_t stream);

@@ -12,14 +12,10 @@
 
 using namespace sdvlb_detail;
 
-cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, const PyrGeom& g, const DevParams& dp, cudaStream_t stream);
-cudaError_t sdvlb_launch_signal(uint32_t* h_flag, uint32_t seq, cudaStream_t stream);
-
 namespace {
 
 struct SeqLayout {
-  size_t list[2], cell_order, afeat, cands, cand_feat, matches, align_scratch, c_cell, c_score, c_rank, o_a, o_pos, o_scale,
-      o_err, o_flag, total;
+  size_t list[2], cell_order, matches, align_scratch, c_cell, c_score, c_rank, c_next, o_a, o_pos, o_scale, o_err, o_flag, total;
 };
 
 SeqLayout seq_layout(int max_feats, int n_cells) {
@@ -30,14 +26,12 @@ SeqLayout seq_layout(int max_feats, int n_cells) {
   L.list[0] = take(n * sizeof(SeqFeat));
   L.list[1] = take(n * sizeof(SeqFeat));
   L.cell_order = take(size_t(n_cells) * sizeof(int32_t));
-  L.afeat = take(n * sizeof(sdvlb_align_feat));
-  L.cands = take(n * sizeof(SearchCandDev));
-  L.cand_feat = take(n * sizeof(int32_t));
   L.matches = take(n * sizeof(sdvlb_match));
-  L.align_scratch = take(n * (SDVLB_ALIGN_SC_DOUBLES * 8 + 48 * 4 + 4) + 256);
+  L.align_scratch = take(SDVLB_ALIGN_SC_BYTES(n) + 256);
   L.c_cell = take(n * sizeof(int32_t));
   L.c_score = take(n * sizeof(int32_t));
   L.c_rank = take(n * sizeof(int32_t));
+  L.c_next = take(n * sizeof(int32_t));
   L.o_a = take(n * 2 * sizeof(double));
   L.o_pos = take(n * 3 * sizeof(double));
   L.o_scale = take(n * sizeof(double));
@@ -47,14 +41,16 @@ SeqLayout seq_layout(int max_feats, int n_cells) {
   return L;
 }
 
+size_t result_stride(int max_feats) { return align_up(sizeof(SeqResultHost) + size_t(max_feats) * sizeof(sdvlb_seq_feat), 256); }
+
 int ensure_step_buffers(sdvlb_ctx* c) {
-  if (c->d_seq_jobs) return 0;
-  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_seq_jobs), SDVLB_SEQ_BATCH * sizeof(AlignJobDev)));
-  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_seq_frames), SDVLB_SEQ_BATCH * sizeof(FrameDev)));
+  if (c->d_seq_done) return 0;
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_seq_done), 256));
   SDVLB_CUDA_TRY(cudaMemsetAsync(c->d_seq_done, 0, 256, c->stream));
   return 0;
 }
+
+bool seq_busy(const sdvlb_ctx* c) { return !c->seq_queue.empty(); }
 
 }  // namespace
 
@@ -73,7 +69,7 @@ void sdvlb_rand_shuffle(sdvlb_rand* s, int32_t* v, int n) {   // libstdc++ std::
 // ---------------------------------------------------------------------------------------------- pose refinement
 static int pose_call(sdvlb_ctx* c, sdvlb_pose_obs* obs, int n, double T[7], sdvlb_rand* rng, int mode) {
   if (!c || n < 0 || (n > 0 && !obs) || !T) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
-  if (c->pending.active || c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
+  if (c->pending.active || seq_busy(c)) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
   if (n == 0) return 0;   // SelectInliers returns at once (feature_align.cc:163-164); ConvergePose has no errors (:373-374)
   SDVLB_CUDA_TRY(cudaSetDevice(c->device));
   Arena& in = c->in;
@@ -143,16 +139,16 @@ int sdvlb_seq_create(sdvlb_ctx* c, int max_feats, sdvlb_seq** out) {
   s->ctx = c;
   s->max_feats = max_feats;
   s->n_cells = n_cells;
+  s->result_stride = result_stride(max_feats);
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->d_block), L.total);
   if (e == cudaSuccess)
-    e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_result), sizeof(SeqResultHost) + size_t(max_feats) * sizeof(sdvlb_seq_feat),
-                      cudaHostAllocDefault);
+    e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_result), s->result_stride * SDVLB_SEQ_DEPTH, cudaHostAllocDefault);
   if (e != cudaSuccess) {
     if (s->d_block) cudaFree(s->d_block);
     delete s;
     return sdvlb_set_cuda_error(e, "sequence storage", __FILE__, __LINE__);
   }
-  memset(s->h_result, 0, sizeof(SeqResultHost));
+  for (int k = 0; k < SDVLB_SEQ_DEPTH; k++) memset(s->h_result + size_t(k) * s->result_stride, 0, sizeof(SeqResultHost));
   // initial state: FeatureAlign constructor (cell order shuffled once, feature_align.cc:47-53) + the shuffle that
   // opens the first tracked frame's SelectPoints (:103), which the device always holds one frame ahead
   std::vector<uint8_t> init(L.cell_order + size_t(n_cells) * sizeof(int32_t), 0);
@@ -169,20 +165,19 @@ int sdvlb_seq_create(sdvlb_ctx* c, int max_feats, sdvlb_seq** out) {
   st->list[0] = reinterpret_cast<SeqFeat*>(d + L.list[0]);
   st->list[1] = reinterpret_cast<SeqFeat*>(d + L.list[1]);
   st->cell_order = reinterpret_cast<int32_t*>(d + L.cell_order);
-  st->afeat = reinterpret_cast<sdvlb_align_feat*>(d + L.afeat);
-  st->cands = reinterpret_cast<SearchCandDev*>(d + L.cands);
-  st->cand_feat = reinterpret_cast<int32_t*>(d + L.cand_feat);
   st->matches = reinterpret_cast<sdvlb_match*>(d + L.matches);
   st->align_scratch = d + L.align_scratch;
   st->c_cell = reinterpret_cast<int32_t*>(d + L.c_cell);
   st->c_score = reinterpret_cast<int32_t*>(d + L.c_score);
   st->c_rank = reinterpret_cast<int32_t*>(d + L.c_rank);
+  st->c_next = reinterpret_cast<int32_t*>(d + L.c_next);
   st->o_a = reinterpret_cast<double*>(d + L.o_a);
   st->o_pos = reinterpret_cast<double*>(d + L.o_pos);
   st->o_scale = reinterpret_cast<double*>(d + L.o_scale);
   st->o_err = reinterpret_cast<double*>(d + L.o_err);
   st->o_flag = reinterpret_cast<int32_t*>(d + L.o_flag);
-  st->result = s->h_result;
+  for (int k = 0; k < SDVLB_SEQ_DEPTH; k++)
+    st->result[k] = reinterpret_cast<SeqResultHost*>(s->h_result + size_t(k) * s->result_stride);
   e = cudaMemcpyAsync(d, init.data(), init.size(), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {
@@ -217,18 +212,45 @@ int sdvlb_seq_destroy(sdvlb_ctx* c, sdvlb_seq* s) {
   return 0;
 }
 
+static void push_cmd(sdvlb_ctx* c, const SeqCmd& cmd, const sdvlb_frame* frame) {
+  c->seq_cmds.push_back(cmd);
+  c->seq_cmd_frames.push_back(frame);
+}
+
 int sdvlb_seq_reset(sdvlb_ctx* c, sdvlb_seq* s, const sdvlb_frame* frame, const double T[7]) {
   if (!c || !s || !frame || !T) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
   SeqCmd cmd;
   memset(&cmd, 0, sizeof(cmd));
   cmd.seq = reinterpret_cast<SeqState*>(s->d_block);
-  cmd.kind = 0;
+  cmd.kind = SEQC_RESET;
   cmd.frame = frame->dev;
   cmd.frame.host_mirror = nullptr;
   memcpy(cmd.T, T, sizeof(cmd.T));
-  c->seq_cmds.push_back(cmd);
-  c->seq_cmd_frames.push_back(frame);
+  push_cmd(c, cmd, frame);
   for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++) s->kf_state[k] = 0;
+  s->n_bound = 0;
+  return 0;
+}
+
+int sdvlb_seq_set_policy(sdvlb_ctx* c, sdvlb_seq* s, const sdvlb_seq_policy* policy) {
+  if (!c || !s || !policy) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  SeqCmd cmd;
+  memset(&cmd, 0, sizeof(cmd));
+  cmd.seq = reinterpret_cast<SeqState*>(s->d_block);
+  cmd.kind = SEQC_POLICY;
+  cmd.policy = *policy;
+  push_cmd(c, cmd, nullptr);
+  s->policy = *policy;
+  return 0;
+}
+
+int sdvlb_seq_release(sdvlb_ctx* c, sdvlb_seq* s) {
+  if (!c || !s) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  SeqCmd cmd;
+  memset(&cmd, 0, sizeof(cmd));
+  cmd.seq = reinterpret_cast<SeqState*>(s->d_block);
+  cmd.kind = SEQC_RELEASE;
+  push_cmd(c, cmd, nullptr);
   return 0;
 }
 
@@ -248,39 +270,45 @@ int sdvlb_seq_add_points(sdvlb_ctx* c, sdvlb_seq* s, const sdvlb_frame* kf, cons
   SeqCmd cmd;
   memset(&cmd, 0, sizeof(cmd));
   cmd.seq = reinterpret_cast<SeqState*>(s->d_block);
-  cmd.kind = 1;
+  cmd.kind = SEQC_ADD_POINTS;
   cmd.n = n;
   cmd.kf_slot = slot;
   cmd.kf_pyr = kf->dev.pyr;
   memcpy(cmd.T, T_kf, sizeof(cmd.T));
   cmd.pts = reinterpret_cast<const sdvlb_seq_point*>(c->seq_pts.size());   // index for now, device pointer at submission
-  c->seq_cmds.push_back(cmd);
-  c->seq_cmd_frames.push_back(kf);
+  push_cmd(c, cmd, kf);
   c->seq_pts.insert(c->seq_pts.end(), pts, pts + n);
+  s->n_bound = std::min(s->max_feats, s->n_bound + n);   // the device truncates at max_feats (and reports it)
   if (kf_slot) *kf_slot = slot;
   return 0;
 }
 
+int sdvlb_seq_track_inflight(sdvlb_ctx* c) { return c ? int(c->seq_queue.size()) : 0; }
+
 int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* const* frames, int n) {
   if (!c || !seqs || !frames || n <= 0 || n > SDVLB_SEQ_BATCH)
     return sdvlb_set_error(SDVLB_ERR_ARG, "a sequence submission takes 1..64 sequences");
-  if (c->pending.active || c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "a submission is still in flight on this context");
+  if (c->pending.active) return sdvlb_set_error(SDVLB_ERR_STATE, "a tracking batch is still in flight on this context");
+  if (int(c->seq_queue.size()) >= SDVLB_SEQ_DEPTH)
+    return sdvlb_set_error(SDVLB_ERR_STATE, "SDVLB_SEQ_DEPTH sequence submissions are already in flight: collect one first");
   SDVLB_CUDA_TRY(cudaSetDevice(c->device));
   int rc = ensure_step_buffers(c);
   if (rc) return rc;
-  int max_feats = 0;
+  int n_bound = 0;
   for (int i = 0; i < n; i++) {
     if (!seqs[i] || !frames[i] || seqs[i]->ctx != c) return sdvlb_set_error(SDVLB_ERR_ARG, "null / foreign sequence or frame");
+    for (int k = 0; k < i; k++)
+      if (seqs[k] == seqs[i]) return sdvlb_set_error(SDVLB_ERR_ARG, "a sequence appears twice in one submission");
     if (!(frames[i]->has_corners || (frames[i]->build_pending && frames[i]->build_corners)))
       return sdvlb_set_error(SDVLB_ERR_STATE, "a tracked frame needs corners");
-    max_feats = std::max(max_feats, seqs[i]->max_feats);
+    n_bound = std::max(n_bound, seqs[i]->n_bound);
   }
   // ---- order the tracking stream after the builds of every frame it touches
   {
     cudaEvent_t waited[8];
     int nw = 0;
     auto wait_once = [&](const sdvlb_frame* f) -> int {
-      if (!f->build_pending) return 0;
+      if (!f || !f->build_pending) return 0;
       for (int k = 0; k < nw; k++) if (waited[k] == f->built) return 0;
       if (nw < 8) waited[nw++] = f->built;
       return wait_frame_built(c, f, c->stream);
@@ -289,22 +317,27 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
     for (const sdvlb_frame* f : c->seq_cmd_frames) { rc = wait_once(f); if (rc) return rc; }
   }
 
-  // ---- queued commands: one upload; applied by the prep kernel
+  c->track_seq++;
+  const int slot = int(c->track_seq % SDVLB_SEQ_DEPTH);
+
+  // ---- queued commands: one upload (the slot's own staging: an earlier submission's copy may still be in flight);
+  // applied by the align kernel
   int2 cmd_range[SDVLB_SEQ_BATCH];
   for (int i = 0; i < SDVLB_SEQ_BATCH; i++) { cmd_range[i].x = 0; cmd_range[i].y = 0; }
   const SeqCmd* d_cmds = nullptr;
   const int n_cmds = int(c->seq_cmds.size());
   if (n_cmds > 0) {
-    Arena& in = c->seq_in;
+    Arena& in = c->seq_in[slot];
     in.used = 0;
     const size_t need = 2048 + size_t(n_cmds) * (sizeof(SeqCmd) + sizeof(int2)) + c->seq_pts.size() * sizeof(sdvlb_seq_point);
+    if (need > in.cap) SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));   // growing frees the old buffers
     rc = ensure_arena(&in, need, true);
     if (rc) return rc;
     const size_t o_cmds = in.take(size_t(n_cmds) * sizeof(SeqCmd));
     const size_t o_ranges = in.take(size_t(n_cmds) * sizeof(int2));
     const size_t o_pts = in.take(std::max<size_t>(1, c->seq_pts.size()) * sizeof(sdvlb_seq_point));
     // commands grouped by sequence, order kept inside a sequence.  Sequences of this step get theirs applied by their
-    // own prep CTA; the others (not tracked now) by one extra launch.
+    // own align CTA; the others (not tracked now) by one extra launch.
     std::vector<int> idx(n_cmds);
     for (int k = 0; k < n_cmds; k++) idx[k] = k;
     std::stable_sort(idx.begin(), idx.end(), [c](int a, int b) { return c->seq_cmds[a].seq < c->seq_cmds[b].seq; });
@@ -314,7 +347,8 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
     for (int k = 0; k < n_cmds; k++) {
       const SeqCmd& src = c->seq_cmds[idx[k]];
       hc[k] = src;
-      if (src.kind == 1) hc[k].pts = reinterpret_cast<const sdvlb_seq_point*>(in.d + o_pts) + reinterpret_cast<size_t>(src.pts);
+      if (src.kind == SEQC_ADD_POINTS)
+        hc[k].pts = reinterpret_cast<const sdvlb_seq_point*>(in.d + o_pts) + reinterpret_cast<size_t>(src.pts);
       if (k > 0 && src.seq == c->seq_cmds[idx[k - 1]].seq) continue;   // same run as the previous command
       int cnt = 1;
       while (k + cnt < n_cmds && c->seq_cmds[idx[k + cnt]].seq == src.seq) cnt++;
@@ -334,37 +368,31 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
     }
     for (sdvlb_seq* s : c->seqs)
       for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++)
-        if (s->kf_state[k] == 1) s->kf_state[k] = 2;
+        if (s->kf_state[k] == 1) { s->kf_state[k] = 2; s->kf_seq[k] = c->track_seq; }
     c->seq_cmds.clear();
     c->seq_pts.clear();
     c->seq_cmd_frames.clear();
   }
 
-  // ---- the step
+  // ---- the step: align (+ commands, prior) -> search -> post, each a programmatic dependent of the one before
   SeqStepArgs A;
   A.n = n;
-  A.max_feats = max_feats;
+  A.max_feats = std::max(4, n_bound);
   for (int i = 0; i < n; i++) {
     A.seq[i] = reinterpret_cast<SeqState*>(seqs[i]->d_block);
     A.cur[i] = frames[i]->dev;
     A.cur[i].host_mirror = nullptr;
   }
-  A.jobs = c->d_seq_jobs;
-  A.frames = c->d_seq_frames;
   A.cmds = d_cmds;
   memcpy(A.cmd_range, cmd_range, sizeof(cmd_range));
-  c->track_seq++;
   A.d_done = c->d_seq_done;
   A.h_flag = reinterpret_cast<uint32_t*>(c->h_overflow) + 16;
   A.seq_no = c->track_seq;
-  A.pad_ = 0;
+  A.slot = slot;
   A.dp = c->dp;
   A.g = c->geom;
-  timer_begin(c, SDVLB_K_PREP);
-  SDVLB_CUDA_TRY(sdvlb_launch_seq_prep(A, c->stream));
-  timer_end(c);
   timer_begin(c, SDVLB_K_ALIGN);
-  SDVLB_CUDA_TRY(sdvlb_launch_align(c->d_seq_jobs, n, c->geom, c->dp, c->stream));
+  SDVLB_CUDA_TRY(sdvlb_launch_seq_align(A, n_bound, c->stream));
   timer_end(c);
   timer_begin(c, SDVLB_K_SEARCH);
   SDVLB_CUDA_TRY(sdvlb_launch_search_seq(A, c->stream));
@@ -372,35 +400,47 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
   timer_begin(c, SDVLB_K_POSE);
   SDVLB_CUDA_TRY(sdvlb_launch_seq_post(A, c->stream));
   timer_end(c);
-  c->n_launches += 4;   // the post kernel publishes the completion word itself
-  c->seq_active = true;
-  c->seq_inflight.assign(seqs, seqs + n);
-  c->seq_inflight_frames.assign(frames, frames + n);
+  c->n_launches += 3;   // the post kernel publishes the completion word itself
+  // a tracked frame leaves at most max_matches features behind (feature_align.cc:108); a frame that tracking quality
+  // rejects leaves the list as it was
+  for (int i = 0; i < n; i++)
+    if (!seqs[i]->policy.tracking_quality) seqs[i]->n_bound = std::min(seqs[i]->n_bound, c->params.max_matches);
+  c->seq_queue.emplace_back();
+  SeqSubmission& sub = c->seq_queue.back();
+  sub.seq_no = c->track_seq;
+  sub.slot = slot;
+  sub.seqs.assign(seqs, seqs + n);
+  sub.frames.assign(frames, frames + n);
   return 0;
 }
 
 int sdvlb_seq_track_poll(sdvlb_ctx* c) {
-  if (!c || !c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
+  if (!c || c->seq_queue.empty()) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
   const volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(c->h_overflow) + 16;
-  return *done == c->track_seq ? 1 : 0;
+  return int32_t(*done - c->seq_queue.front().seq_no) >= 0 ? 1 : 0;
 }
 
 int sdvlb_seq_track_collect(sdvlb_ctx* c, sdvlb_seq_result* results) {
   if (!c || !results) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
-  if (!c->seq_active) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
-  c->seq_active = false;
-  int rc = wait_signal(c);
+  if (c->seq_queue.empty()) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
+  const SeqSubmission sub = std::move(c->seq_queue.front());
+  c->seq_queue.pop_front();
+  int rc = wait_signal(c, sub.seq_no);
   if (rc) return rc;
   rc = check_overflow(c);
   if (rc) return rc;
   const int pa = c->params.align_patch_size * c->params.align_patch_size;
-  for (size_t i = 0; i < c->seq_inflight.size(); i++) {
-    sdvlb_seq* s = c->seq_inflight[i];
-    sdvlb_frame* f = c->seq_inflight_frames[i];
+  for (size_t i = 0; i < sub.seqs.size(); i++) {
+    sdvlb_seq* s = sub.seqs[i];
+    sdvlb_frame* f = sub.frames[i];
     if (f->build_pending) finalize_build(c, f);   // the tracking stream ran after this frame's build
-    const SeqResultHost* R = s->h_result;
-    if (R->error) return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "a sequence exceeded its feature capacity");
+    const SeqResultHost* R = reinterpret_cast<const SeqResultHost*>(s->h_result + size_t(sub.slot) * s->result_stride);
+    if (R->error) return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "a sequence exceeded its feature capacity (points were dropped)");
     sdvlb_seq_result& o = results[i];
+    memset(&o, 0, sizeof(o));
+    o.status = R->status;
+    o.lost_frames = R->lost_frames;
+    if (R->status != SDVLB_SEQ_TRACKED) continue;   // held / idle: the frame was not consumed, nothing else is valid
     memcpy(o.pose, R->pose, sizeof(o.pose));
     o.n_tracked = R->stats[0] / pa;
     o.matches = R->stats[1];
@@ -410,13 +450,16 @@ int sdvlb_seq_track_collect(sdvlb_ctx* c, sdvlb_seq_result* results) {
     o.n_points = R->stats[5];
     o.gn_iters = R->stats[6];
     o.n_feats = R->stats[7];
+    o.quality = R->quality;
+    o.need_keyframe = R->need_keyframe;
     o.feats = reinterpret_cast<const sdvlb_seq_feat*>(reinterpret_cast<const uint8_t*>(R) + sizeof(SeqResultHost));
     memcpy(o.kf_live, R->kf_live, sizeof(o.kf_live));
     memcpy(o.phase_cycles, R->phase_cycles, sizeof(o.phase_cycles));
     memcpy(o.align_cycles, R->align_cycles, sizeof(o.align_cycles));
+    // keyframe slots: a result only speaks for the slots whose points had reached the device when its step ran
     for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++) {
-      if (R->kf_live[k] > 0) { if (s->kf_state[k] != 1) s->kf_state[k] = 3; }
-      else if (s->kf_state[k] == 2 || s->kf_state[k] == 3) s->kf_state[k] = 0;
+      if (s->kf_state[k] < 2 || int32_t(sub.seq_no - s->kf_seq[k]) < 0) continue;
+      s->kf_state[k] = R->kf_live[k] > 0 ? 3 : 0;
     }
     c->d2h_bytes += int64_t(sizeof(SeqResultHost)) + int64_t(o.n_feats) * int64_t(sizeof(sdvlb_seq_feat));
   }

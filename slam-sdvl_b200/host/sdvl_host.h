@@ -325,26 +325,16 @@ class FeatureAlign {
                          std::vector<sdvlb_candidate>* cands, std::vector<std::shared_ptr<Point>>* points);
   void ApplyMatches(const std::shared_ptr<Frame>& frame, const std::vector<std::shared_ptr<Point>>& points,
                     const sdvlb_match* matches);
-  // SelectInliers / OptimizePose on the device (sdvlb_select_inliers, sdvlb_optimize_pose) instead of the CPU bodies
-  // below; same lists, same rand() consumption.  Process-wide, like Config.
-  static void SetDevicePoseRefinement(bool on) { device_pose_refinement_ = on; }
   int GetInliers() const { return int(inliers_.size()); }
   int GetOutliers() const { return int(outliers_.size()); }
   double ransac_seconds = 0;   // time spent in SelectInliers (host phase accounting)
  private:
+  // RANSAC (feature_align.cc:152-216) and OptimizePose's Gauss-Newton rounds are device calls
+  // (sdvlb_select_inliers / sdvlb_optimize_pose); the host only keeps the inlier / outlier lists.
   void SelectInliers(const std::shared_ptr<Frame>& frame, std::vector<std::shared_ptr<Feature>>& fs_found,
                      std::vector<std::shared_ptr<Feature>>* inliers, std::vector<std::shared_ptr<Feature>>* outliers);
-  void OptimizePose(const std::shared_ptr<Frame>& frame, std::vector<std::shared_ptr<Feature>>* features,
-                    std::vector<std::shared_ptr<Feature>>* outliers);
-  bool RescueOutliers(const std::shared_ptr<Frame>& frame, std::vector<std::shared_ptr<Feature>>* inliers,
-                      std::vector<std::shared_ptr<Feature>>* outliers);
   void RemoveOutliers(const std::shared_ptr<Frame>& frame, std::vector<std::shared_ptr<Feature>>* outliers);
-  int CheckReprojectionError(const std::vector<std::shared_ptr<Feature>>& features, const SE3& se3, double threshold,
-                             std::vector<std::shared_ptr<Feature>>* inliers = NULL,
-                             std::vector<std::shared_ptr<Feature>>* outliers = NULL);
   void ResetGrid();
-  bool ConvergePose(const std::shared_ptr<Frame>& frame, const std::vector<std::shared_ptr<Feature>>& features, SE3* se3);
-  double GetTukeyValue(double x);
 
   Map* map_;
   int cell_size_, max_matches_, grid_width_, grid_height_;
@@ -354,9 +344,6 @@ class FeatureAlign {
   bool relocalizing_;
   std::vector<std::shared_ptr<Feature>> inliers_, outliers_;
   HostRand rng_;
-  static bool device_pose_refinement_;
-  static constexpr double KMADNorm = 1.4826;
-  static constexpr double KTukeyC = 4.6851 * 4.6851;
 };
 
 void RandomShuffle(std::vector<int>* v, HostRand* rng);   // libstdc++ std::random_shuffle with rand()

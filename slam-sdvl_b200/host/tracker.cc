@@ -55,14 +55,21 @@ struct Sequence {
 };
 
 // Host side of a resident sequence (sdvlb_seq): the tracked state lives on the device; the host keeps the frame handles
-// the device still references and plays the mapping thread (keyframe decision + seeding).
+// the device still references and plays the mapping thread (seeding when the device's Map::NeedKeyframe fires).
+constexpr int kFrameRing = 16;   // frames of a sequence between "result seen" and "build submitted" (prefetch + depth + 2)
 struct ResidentSeq {
   sdvlb_seq* h = nullptr;
   sdvlb_frame* last_frame = nullptr;
   sdvlb_frame* kf_frames[SDVLB_SEQ_KF_CAP] = {};
-  int frame_counter = 0, last_kf_id = 0, last_matches = 0;
+  int kf_added_at[SDVLB_SEQ_KF_CAP] = {};   // frame_counter of the keyframe that filled the slot
+  int frame_counter = 0, last_kf_id = 0;
   int64_t next_point_id = 0;
   vector<sdvlb_seq_point> seeds;
+  // pipelined run (indices are steps of the current run)
+  sdvlb_frame* ring[kFrameRing] = {};   // built (or being built) frames not yet consumed, by step % kFrameRing
+  int next_build = 0;    // next step to submit for frame construction
+  int next_track = 0;    // next step to submit for tracking
+  int n_done = 0;        // steps whose result the host has processed
 };
 
 class SequenceDriver {
@@ -244,6 +251,7 @@ class SequenceDriver {
     if (sdvlb_seq_add_points(ctx, s->h, f, T, s->seeds.data(), int(s->seeds.size()), &slot))
       throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_add_points failed: ") + sdvlb_last_error());
     s->kf_frames[slot] = f;
+    s->kf_added_at[slot] = s->frame_counter;
     s->last_kf_id = s->frame_counter;
     return n_points - before;
   }
@@ -272,6 +280,15 @@ class Group {
       if (sdvlb_seq_create(ctx_, std::max(256, 2 * std::max(max_points, Config::MaxMatches())), &r.h))
         throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_create failed: ") + sdvlb_last_error());
       seq_handles_.push_back(r.h);
+      // SDVL::HandleFrame's own decision after a frame (Map::NeedKeyframe, map.cc:170-188, MinKeyframeIts = kf_every,
+      // LostRatio = 0.7) runs on the device, so that later frames can be queued before the host has seen the result
+      sdvlb_seq_policy pol;
+      std::memset(&pol, 0, sizeof(pol));
+      pol.keyframe_rule = 1;
+      pol.min_keyframe_its = kf_every;
+      pol.lost_ratio = 0.7;
+      if (sdvlb_seq_set_policy(ctx_, r.h, &pol))
+        throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_set_policy failed: ") + sdvlb_last_error());
     }
     results_.resize(rseqs_.size());
   }
@@ -286,14 +303,26 @@ class Group {
   void StepResident(const uint8_t* const* images, int on_device, const double* gt, double* est, int32_t* stats) {
     Device::SetCurrent(ctx_);
     const int n = size();
-    built_.assign(n, nullptr);
+    vector<sdvlb_frame*> built(n, nullptr);
     const auto tA = std::chrono::steady_clock::now();
-    if (sdvlb_frames_submit(ctx_, images, n, on_device, 1, Config::NumFeatures(), built_.data()))
+    if (sdvlb_frames_submit(ctx_, images, n, on_device, 1, Config::NumFeatures(), built.data()))
       throw std::runtime_error(std::string("sdvl-b200: sdvlb_frames_submit failed: ") + sdvlb_last_error());
     const auto tB = std::chrono::steady_clock::now();
-    const bool tracked = SubmitResident();
-    const auto tC = std::chrono::steady_clock::now();
-    FinishResident(tracked, gt, 1, 0, est, stats);
+    const bool first = rseqs_[0].last_frame == nullptr;   // the sequences of a group start together
+    auto tC = tB;
+    if (first) {
+      InitResident(built, gt, 1, est, stats);
+    } else {
+      if (sdvlb_seq_track_submit(ctx_, seq_handles_.data(), built.data(), n))
+        throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_track_submit failed: ") + sdvlb_last_error());
+      tC = std::chrono::steady_clock::now();
+      if (sdvlb_seq_track_collect(ctx_, results_.data()))
+        throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_track_collect failed: ") + sdvlb_last_error());
+      for (int i = 0; i < n; i++) {
+        if (results_[i].status != SDVLB_SEQ_TRACKED) throw std::runtime_error("sdvl-b200: a sequence was not tracked in a lock-step step");
+        FinishTracked(i, built[i], results_[i], gt + 7 * size_t(i), est + 7 * size_t(i), stats + 8 * size_t(i));
+      }
+    }
     const auto tD = std::chrono::steady_clock::now();
     phase_s_[0] += std::chrono::duration<double>(tB - tA).count();
     phase_s_[1] += std::chrono::duration<double>(tC - tB).count();
@@ -346,6 +375,14 @@ class Group {
     images_ = images; on_device_ = on_device; n_steps_ = n_steps; stride_ = table_stride; gt_ = gt; est_ = est;
     stats_ = stats;
     step_ = 0; in_flight_ = false;
+    if (resident_) {
+      for (auto& r : rseqs_) {
+        r.next_build = r.next_track = r.n_done = 0;
+        for (auto& f : r.ring) f = nullptr;
+      }
+      subs_.clear();
+      return;
+    }
     built_.assign(size(), nullptr);
     next_built_.assign(size(), nullptr);
     ahead_.clear();
@@ -357,25 +394,26 @@ class Group {
       SubmitBuild(k, &ahead_.back());
     }
   }
-  bool RunDone() const { return step_ >= n_steps_; }
+  bool RunDone() const {
+    if (!resident_) return step_ >= n_steps_;
+    if (!subs_.empty()) return false;
+    for (const auto& r : rseqs_) if (r.n_done < n_steps_) return false;
+    return true;
+  }
+  // One scheduling round of the pipelined run; returns whether anything happened.  `block`: nothing else to do on this
+  // thread, so waiting inside a collect is fine.
+  bool Pump(bool block) {
+    if (resident_) return PumpResident(block);
+    if (!InFlight()) { SubmitStep(); return true; }
+    if (block || Poll()) { FinishStep(); return true; }
+    return false;
+  }
   void AddIdle(double s) { phase_s_[7] += s; }
   bool InFlight() const { return in_flight_; }
 
   void SubmitStep() {   // build(step+1) then track(step)
     Device::SetCurrent(ctx_);
     const auto tA = std::chrono::steady_clock::now();
-    if (resident_) {   // the tracking chain is the critical path: submit it first, then the prefetch work
-      tracked_ = SubmitResident();
-      in_flight_ = true;
-      const auto tB = std::chrono::steady_clock::now();
-      if (step_ + prefetch_ < n_steps_) {
-        ahead_.emplace_back(size(), nullptr);
-        SubmitBuild(step_ + prefetch_, &ahead_.back());
-      }
-      phase_s_[1] += std::chrono::duration<double>(tB - tA).count();
-      phase_s_[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tB).count();
-      return;
-    }
     if (step_ + prefetch_ < n_steps_) {
       ahead_.emplace_back(size(), nullptr);
       SubmitBuild(step_ + prefetch_, &ahead_.back());
@@ -395,26 +433,13 @@ class Group {
     phase_s_[1] += std::chrono::duration<double>(tC - tB).count();
   }
   bool Poll() {
-    if (resident_ && !tracked_) return true;
-    const int rc = resident_ ? sdvlb_seq_track_poll(ctx_) : sdvlb_track_poll(ctx_);
+    const int rc = sdvlb_track_poll(ctx_);
     if (rc < 0) throw std::runtime_error(std::string("sdvl-b200: sdvlb_track_poll failed: ") + sdvlb_last_error());
     return rc == 1;
   }
   void FinishStep() {   // waits if the device is not done yet
     Device::SetCurrent(ctx_);
     const auto tA = std::chrono::steady_clock::now();
-    if (resident_) {
-      const double waited = FinishResident(tracked_, gt_ + 7 * size_t(step_), stride_, step_, est_ + 7 * size_t(step_),
-                                           stats_ + 8 * size_t(step_));
-      in_flight_ = false;
-      AdvanceBuilt();
-      step_++;
-      const double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - tA).count();
-      phase_s_[1] += waited;
-      phase_s_[6] += waited;
-      phase_s_[2] += total - waited;
-      return;
-    }
     const int rc = sdvlb_track_collect(ctx_);
     if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_track_collect failed: ") + sdvlb_last_error());
     in_flight_ = false;
@@ -477,80 +502,167 @@ class Group {
     phase_s_[3] += std::chrono::duration<double>(t1 - t0).count();
     phase_s_[5] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
   }
-  // Submits the tracking of built_ for every sequence; sequences without a track yet are started instead (host only).
-  // Returns whether a device submission is in flight.
-  bool SubmitResident() {
-    if (rseqs_[0].last_frame == nullptr) return false;   // the sequences of a group run in lock-step
-    if (sdvlb_seq_track_submit(ctx_, seq_handles_.data(), built_.data(), size()))
-      throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_track_submit failed: ") + sdvlb_last_error());
-    return true;
-  }
-  // Host half of a resident step: results, keyframe decision (Map::NeedKeyframe, map.cc:170-188) and seeding, frame
-  // lifetimes.  Tables are indexed [i * stride + offset].  Returns the seconds spent waiting for the device.
-  double FinishResident(bool tracked, const double* gt, int stride, int /*step*/, double* est, int32_t* stats) {
+  // ---------------------------------------------------------------------------------------------- resident sequences
+  // First frame of every sequence of `built` (one per sequence, in order): ground-truth pose + map seeding (stand-in
+  // for SDVL's initialisation).  Tables are indexed [i * stride].
+  void InitResident(const vector<sdvlb_frame*>& built, const double* gt, int stride, double* est, int32_t* stats) {
     const int n = size();
-    double waited = 0;
-    if (tracked) {
-      const auto t0 = std::chrono::steady_clock::now();
-      if (sdvlb_seq_track_collect(ctx_, results_.data()))
-        throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_track_collect failed: ") + sdvlb_last_error());
-      waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    } else {
-      if (sdvlb_frames_wait(ctx_, built_.data(), n))
-        throw std::runtime_error(std::string("sdvl-b200: sdvlb_frames_wait failed: ") + sdvlb_last_error());
+    if (sdvlb_frames_wait(ctx_, built.data(), n))
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_frames_wait failed: ") + sdvlb_last_error());
+    for (int i = 0; i < n; i++) InitOne(i, built[i], gt + 7 * size_t(i) * stride, est + 7 * size_t(i) * stride, stats + 8 * size_t(i) * stride);
+  }
+  void InitOne(int i, sdvlb_frame* frame, const double* gt7, double* est7, int32_t* st) {
+    ResidentSeq& s = rseqs_[i];
+    std::memset(st, 0, 8 * sizeof(int32_t));
+    const SE3 gt_pose(gt7);
+    if (sdvlb_seq_reset(ctx_, s.h, frame, gt7))
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_reset failed: ") + sdvlb_last_error());
+    for (auto& k : s.kf_frames) k = nullptr;
+    s.frame_counter = 0;
+    st[5] = driver_.SeedResident(ctx_, &s, frame, gt_pose, gt_pose, nullptr, 0);
+    st[7] = 1;
+    gt_pose.ToArray(est7);
+    if (s.last_frame) sdvlb_frame_destroy(ctx_, s.last_frame);
+    s.last_frame = frame;
+    s.frame_counter++;
+  }
+  // Host half of a tracked frame: results, seeding when the device's keyframe rule fired (the sequence is on hold until
+  // the new points -- or an empty list -- reach it), frame lifetimes.
+  void FinishTracked(int i, sdvlb_frame* frame, const sdvlb_seq_result& r, const double* gt7, double* est7, int32_t* st) {
+    ResidentSeq& s = rseqs_[i];
+    std::memset(st, 0, 8 * sizeof(int32_t));
+    for (int k = 0; k < 8; k++) post_cycles_[k] += r.phase_cycles[k];
+    post_cycles_[8] += 1;
+    for (int k = 0; k < 4; k++) align_cycles_[k] += r.align_cycles[k];
+    st[0] = r.n_tracked; st[1] = r.matches; st[2] = r.attempts; st[3] = r.inliers; st[4] = r.outliers;
+    st[6] = r.gn_iters;
+    std::memcpy(est7, r.pose, 7 * sizeof(double));
+    // keyframe slots nothing references any more give their frames back (a result only speaks for the slots that
+    // were filled before its frame)
+    for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++)
+      if (s.kf_frames[k] && s.frame_counter > s.kf_added_at[k] && r.kf_live[k] == 0) {
+        if (s.kf_frames[k] != s.last_frame) sdvlb_frame_destroy(ctx_, s.kf_frames[k]);
+        s.kf_frames[k] = nullptr;
+      }
+    int seeded = 0;
+    if (r.need_keyframe) {
+      seeded = driver_.SeedResident(ctx_, &s, frame, SE3(r.pose), SE3(gt7), r.feats, r.n_feats);
+      st[7] = 1;
     }
+    st[5] = r.n_points + seeded;
+    if (s.last_frame) {
+      bool held = false;
+      for (int k = 0; k < SDVLB_SEQ_KF_CAP && !held; k++) held = s.kf_frames[k] == s.last_frame;
+      if (!held) sdvlb_frame_destroy(ctx_, s.last_frame);
+    }
+    s.last_frame = frame;
+    s.frame_counter++;
+  }
+
+  struct TrackEntry { int seq; int step; };
+  void FinishOldest() {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (sdvlb_seq_track_collect(ctx_, results_.data()))
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_track_collect failed: ") + sdvlb_last_error());
     const auto t1 = std::chrono::steady_clock::now();
+    const vector<TrackEntry> entries = std::move(subs_.front());
+    subs_.pop_front();
+    for (size_t j = 0; j < entries.size(); j++) {
+      const int i = entries[j].seq, k = entries[j].step;
+      ResidentSeq& s = rseqs_[i];
+      const sdvlb_seq_result& r = results_[j];
+      if (r.status == SDVLB_SEQ_HELD) continue;   // queued behind a keyframe decision: the frame is submitted again
+      if (r.status != SDVLB_SEQ_TRACKED || k != s.n_done)
+        throw std::runtime_error("sdvl-b200: resident sequence result out of order");
+      const size_t o = size_t(i) * stride_ + k;
+      sdvlb_frame* frame = s.ring[k % kFrameRing];
+      s.ring[k % kFrameRing] = nullptr;
+      FinishTracked(i, frame, r, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
+      s.n_done = k + 1;
+      if (r.need_keyframe) s.next_track = k + 1;   // whatever was queued behind this frame has been skipped
+    }
+    const auto t2 = std::chrono::steady_clock::now();
+    phase_s_[1] += std::chrono::duration<double>(t1 - t0).count();
+    phase_s_[6] += std::chrono::duration<double>(t1 - t0).count();
+    phase_s_[2] += std::chrono::duration<double>(t2 - t1).count();
+    phase_s_[5] += std::chrono::duration<double>(t2 - t1).count();
+  }
+
+  bool PumpResident(bool block) {
+    Device::SetCurrent(ctx_);
+    bool progressed = false;
+    const int n = size();
+    // 1. finished submissions, oldest first
+    while (!subs_.empty()) {
+      const int rc = sdvlb_seq_track_poll(ctx_);
+      if (rc < 0) throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_track_poll failed: ") + sdvlb_last_error());
+      if (rc != 1) break;
+      FinishOldest();
+      progressed = true;
+    }
+    const auto tA = std::chrono::steady_clock::now();
+    // 2. tracking: every sequence whose next frame has been handed to the build stream, up to depth_ submissions in
+    //    flight.  The critical path of a sequence is this chain, so it is queued before any prefetch work.
+    while (int(subs_.size()) < depth_) {
+      track_seqs_.clear(); track_frames_.clear();
+      vector<TrackEntry> entries;
+      for (int i = 0; i < n; i++) {
+        ResidentSeq& s = rseqs_[i];
+        if (!s.last_frame || s.next_track >= n_steps_ || s.next_track >= s.next_build) continue;
+        track_seqs_.push_back(s.h);
+        track_frames_.push_back(s.ring[s.next_track % kFrameRing]);
+        entries.push_back(TrackEntry{i, s.next_track});
+      }
+      if (entries.empty()) break;
+      if (sdvlb_seq_track_submit(ctx_, track_seqs_.data(), track_frames_.data(), int(entries.size())))
+        throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_track_submit failed: ") + sdvlb_last_error());
+      for (const TrackEntry& e : entries) rseqs_[e.seq].next_track++;
+      subs_.push_back(std::move(entries));
+      progressed = true;
+    }
+    const auto tB = std::chrono::steady_clock::now();
+    // 3. frame construction, prefetch_ steps ahead of each sequence's tracking
+    {
+      build_imgs_.clear(); build_entries_.clear();
+      for (int pass = 0; pass < prefetch_; pass++)
+        for (int i = 0; i < n; i++) {
+          ResidentSeq& s = rseqs_[i];
+          if (s.next_build >= n_steps_ || s.next_build >= s.next_track + prefetch_) continue;
+          build_imgs_.push_back(images_[size_t(i) * stride_ + s.next_build]);
+          build_entries_.push_back(TrackEntry{i, s.next_build});
+          s.next_build++;
+        }
+      if (!build_entries_.empty()) {
+        build_out_.assign(build_entries_.size(), nullptr);
+        if (sdvlb_frames_submit(ctx_, build_imgs_.data(), int(build_imgs_.size()), on_device_, 1, Config::NumFeatures(), build_out_.data()))
+          throw std::runtime_error(std::string("sdvl-b200: sdvlb_frames_submit failed: ") + sdvlb_last_error());
+        for (size_t j = 0; j < build_entries_.size(); j++)
+          rseqs_[build_entries_[j].seq].ring[build_entries_[j].step % kFrameRing] = build_out_[j];
+        progressed = true;
+      }
+    }
+    // 4. sequences without a track yet: their first frame initialises them on the host (needs the built frame)
     for (int i = 0; i < n; i++) {
       ResidentSeq& s = rseqs_[i];
-      const size_t o = size_t(i) * stride;
-      int32_t* st = stats + 8 * o;
-      std::memset(st, 0, 8 * sizeof(int32_t));
-      const SE3 gt_pose(gt + 7 * o);
-      sdvlb_frame* frame = built_[i];
-      if (!tracked) {   // first frame of the sequence: ground-truth pose + seeding (stand-in for the initialisation)
-        if (sdvlb_seq_reset(ctx_, s.h, frame, gt + 7 * o))
-          throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_reset failed: ") + sdvlb_last_error());
-        for (auto& k : s.kf_frames) k = nullptr;
-        st[5] = driver_.SeedResident(ctx_, &s, frame, gt_pose, gt_pose, nullptr, 0);
-        st[7] = 1;
-        gt_pose.ToArray(est + 7 * o);
-      } else {
-        const sdvlb_seq_result& r = results_[i];
-        for (int k = 0; k < 8; k++) post_cycles_[k] += r.phase_cycles[k];
-        post_cycles_[8] += 1;
-        for (int k = 0; k < 4; k++) align_cycles_[k] += r.align_cycles[k];
-        st[0] = r.n_tracked; st[1] = r.matches; st[2] = r.attempts; st[3] = r.inliers; st[4] = r.outliers;
-        st[6] = r.gn_iters;
-        std::memcpy(est + 7 * o, r.pose, 7 * sizeof(double));
-        // keyframe slots nothing references any more give their frames back
-        for (int k = 0; k < SDVLB_SEQ_KF_CAP; k++)
-          if (s.kf_frames[k] && r.kf_live[k] == 0) {
-            if (s.kf_frames[k] != s.last_frame) sdvlb_frame_destroy(ctx_, s.kf_frames[k]);
-            s.kf_frames[k] = nullptr;
-          }
-        const int npoints = r.n_points;
-        const bool enough_its = (s.frame_counter - s.last_kf_id) >= kf_every_;
-        const bool lost_many = npoints < s.last_matches * 0.7;
-        const bool lost_some = npoints < s.last_matches * 0.9;
-        s.last_matches = std::max(s.last_matches, npoints);
-        int seeded = 0;
-        if ((enough_its && lost_some) || lost_many) {
-          s.last_matches = npoints;
-          seeded = driver_.SeedResident(ctx_, &s, frame, SE3(r.pose), gt_pose, r.feats, r.n_feats);
-          st[7] = 1;
-        }
-        st[5] = npoints + seeded;
-      }
-      if (s.last_frame) {
-        bool held = false;
-        for (int k = 0; k < SDVLB_SEQ_KF_CAP && !held; k++) held = s.kf_frames[k] == s.last_frame;
-        if (!held) sdvlb_frame_destroy(ctx_, s.last_frame);
-      }
-      s.last_frame = frame;
-      s.frame_counter++;
+      if (s.n_done != 0 || s.next_track != 0 || s.next_build == 0 || s.last_frame) continue;
+      sdvlb_frame* f = s.ring[0];
+      if (sdvlb_frames_wait(ctx_, &f, 1))
+        throw std::runtime_error(std::string("sdvl-b200: sdvlb_frames_wait failed: ") + sdvlb_last_error());
+      const size_t o = size_t(i) * stride_;
+      s.ring[0] = nullptr;
+      InitOne(i, f, gt_ + 7 * o, est_ + 7 * o, stats_ + 8 * o);
+      s.n_done = 1;
+      s.next_track = 1;
+      progressed = true;
     }
-    phase_s_[5] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
-    return waited;
+    const auto tC = std::chrono::steady_clock::now();
+    phase_s_[1] += std::chrono::duration<double>(tB - tA).count();
+    phase_s_[0] += std::chrono::duration<double>(tC - tB).count();
+    if (!progressed && block && !subs_.empty()) {   // nothing else to do on this thread: wait inside the collect
+      FinishOldest();
+      progressed = true;
+    }
+    return progressed;
   }
   void AdvanceBuilt() {
     if (!ahead_.empty()) {
@@ -572,7 +684,13 @@ class Group {
   vector<Sequence> seqs_;
   vector<sdvlb_track_job> jobs_;
   int kf_every_ = 0;
-  bool resident_ = false, tracked_ = false;
+  bool resident_ = false;
+  // resident pipelined run: tracking submissions in flight (oldest first) and per-call staging
+  std::deque<vector<TrackEntry>> subs_;
+  vector<sdvlb_seq*> track_seqs_;
+  vector<sdvlb_frame*> track_frames_, build_out_;
+  vector<const uint8_t*> build_imgs_;
+  vector<TrackEntry> build_entries_;
  public:
   double align_cycles_[4] = {0, 0, 0, 0};
   double post_cycles_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // seq_post_kernel phase cycles summed over frames, [8] = frames
@@ -595,6 +713,7 @@ class Group {
   std::deque<vector<sdvlb_frame*>> ahead_;   // frame batches of the steps after the current one, oldest first
  public:
   int prefetch_ = 2;
+  int depth_ = 2;    // tracking submissions in flight per group (resident sequences)
  private:
   vector<const uint8_t*> img_ptrs_;
 };
@@ -673,6 +792,7 @@ class BatchTracker {
     }
   }
   void SetPrefetch(int depth) { for (auto& g : groups_) g->prefetch_ = std::max(1, std::min(depth, 6)); }
+  void SetDepth(int depth) { for (auto& g : groups_) g->depth_ = std::max(1, std::min(depth, SDVLB_SEQ_DEPTH)); }
   void PostCycles(double out[13], int reset) {
     for (int i = 0; i < 13; i++) out[i] = 0;
     for (auto& g : groups_) {
@@ -728,14 +848,8 @@ class BatchTracker {
         for (int g : mine) {
           Group& G = *groups_[g];
           if (G.RunDone()) continue;
-          if (!G.InFlight()) {
-            G.SubmitStep();
-            progressed = true;
-          } else if (active == 1 || G.Poll()) {   // the only unfinished group: block in collect
-            G.FinishStep();
-            if (G.RunDone()) active--;
-            progressed = true;
-          }
+          if (G.Pump(active == 1)) progressed = true;   // the only unfinished group may block in its collect
+          if (G.RunDone()) active--;
         }
         if (!progressed) {   // everything in flight: nothing to do but wait (plain memory polls, no driver calls)
           const auto t0 = std::chrono::steady_clock::now();
@@ -796,7 +910,6 @@ const char* sdvlh_last_error(void) { return g_host_error.c_str(); }
 // Config is process-wide in the reference (singleton, config.h:56); set it before creating trackers.
 void sdvlh_config_set(const sdvlb_params* p, const sdvlb_camera* cam) { sdvl::Config::Set(*p, *cam); }
 // FeatureAlign::SelectInliers / OptimizePose of the class-API path on the device (1) or on the host (0, default).
-void sdvlh_device_pose_refinement(int on) { sdvl::FeatureAlign::SetDevicePoseRefinement(on != 0); }
 
 // A context of its own for the test hooks below (the process-wide default context keeps the camera it was made with).
 struct HookContext {
@@ -1013,6 +1126,7 @@ int sdvlh_tracker_post_cycles(void* t, double out[13], int reset) {
 
 // How many steps ahead of the tracking the frame batches (upload + pyramid + FAST) are submitted in sdvlh_tracker_run.
 void sdvlh_tracker_set_prefetch(void* t, int depth) { static_cast<sdvl::BatchTracker*>(t)->SetPrefetch(depth); }
+void sdvlh_tracker_set_depth(void* t, int depth) { static_cast<sdvl::BatchTracker*>(t)->SetDepth(depth); }
 
 void* sdvlh_tracker_ctx(void* t) { return static_cast<sdvl::BatchTracker*>(t)->ctx0(); }
 int sdvlh_tracker_groups(void* t) { return static_cast<sdvl::BatchTracker*>(t)->n_groups(); }
