@@ -22,7 +22,7 @@ for s, L in sorted(by.items()):
     if kind == "track":
         start = None
         for a, b in zip(L, L[1:] + [None]):
-            if "seq_prep" in a["name"]:
+            if "seq_align" in a["name"] or "seq_prep" in a["name"]:
                 start = a["ts"]
             if "seq_post" in a["name"]:
                 if start is not None:
@@ -30,7 +30,7 @@ for s, L in sorted(by.items()):
                 if b is not None:
                     gaps.append(b["ts"] - (a["ts"] + a["dur"]))
 med = lambda v: sorted(v)[len(v) // 2] if v else float("nan")
-print(f"tracking chain prep..post: median {med(chains):.0f} us; host turnaround (post end -> next prep start): median {med(gaps):.0f} us, max {max(gaps):.0f} us")
+print(f"tracking chain align..post: median {med(chains):.0f} us; gap (post end -> next chain start; negative = overlapped by programmatic dependent launch): median {med(gaps):.0f} us, max {max(gaps):.0f} us")
 d = defaultdict(list)
 for e in ev:
     d[short(e["name"])].append(e["dur"])

@@ -15,9 +15,11 @@
 //
 // Inverse compositional: H_f does not change inside a level, and H only depends on WHICH features project into the
 // current image.  So PrecomputePatches also forms H_all = sum_f H_f once per level; an iteration reduces b, chi2 and
-// three counters only (8 values instead of 29) and H is H_all, corrected by the few features that fell outside the
-// image (rare; a fixed-order pass of 21 lanes over the per-feature H_f kept in global memory).  With H unchanged its
-// LDL^T factor is reused too: most iterations are two triangular substitutions.
+// three counters only (8 values instead of 29) and H is H_all minus the H_f of the features that fell outside the
+// current image (a handful near the borders): the warp that owns such a feature re-forms its H_f from the cached
+// Jacobian rows and gradient moments, lane k computing entry k, so the correction needs no shuffle and no extra pass.
+// As long as the SET of outside features does not change, H does not either and its LDL^T factor is reused: most
+// iterations are two triangular substitutions.
 //
 // Per-feature caches (xyz, Jacobian rows, reference patch and its gradients) live in SHARED memory for the first
 // `cap` features (256 or 512, chosen by the launcher); features beyond that use the same layout in global scratch.
@@ -29,11 +31,13 @@ namespace {
 
 constexpr int AL_THREADS = 256;
 constexpr int AL_WARPS = AL_THREADS / 32;
-constexpr int ND = 17;                        // cached doubles per feature: xyz[3], j0[6], j1[6] (times fx / 2^level), px[2]
+constexpr int ND = 20;                        // cached doubles per feature: xyz[3], j0[6], j1[6] (times fx / 2^level), px[2],
+                                              // gradient moments sum(dx^2, dx dy, dy^2) of the level
 constexpr int PF = SDVLB_ALIGN_SC_FLOATS;     // cached floats per feature: patch[16], dx[16], dy[16], 4 pad.  A row
                                               // stride of 52 words spreads the 16-byte loads of 8 neighbouring
                                               // threads over all 32 banks (48 would make them collide 4-way)
 constexpr int NRED = 7;                       // b[6], chi2
+constexpr int AL_PASSES_MAX = 16;             // features per alignment <= 16 * 256 for the factor-reuse bookkeeping
 
 // Eight consecutive pixels starting at p, from aligned 32-bit words: a row of the 5x5 / 7x7 footprints costs two or
 // three loads instead of five or seven byte loads (the load/store unit is what the residual phase waits for).
@@ -151,7 +155,6 @@ struct AlignView {
   int trace_cap;
   const double* forced_T;  // teacher forcing (parity tests)
   const int32_t* forced_iters;
-  double* g_H;             // [21][n] per-feature J J^T sum of the level
   double* g_d;             // [ND][n - cap] overflow cache
   float* g_f;              // [n - cap][PF]
   int32_t* g_flags;        // [n] flags of the overflow features (indexed by feature)
@@ -165,6 +168,8 @@ struct AlignSmem {
                            //        image in the iteration being evaluated, bit3 the feature observes a live point
   double* wred;            // [AL_WARPS][8] per-warp partials of an iteration
   double* hred;            // [AL_WARPS][21] per-warp partials of H_all
+  double* hcor;            // [AL_WARPS][21] per-warp sums of the H_f of the features outside the current image
+  unsigned* outside;       // [AL_PASSES_MAX][AL_WARPS] ballots of those features at the last factorisation
   int* wredi;              // [AL_WARPS][4]
   double* Hall;            // [21] sum of H_f over the features that have a Jacobian at this level
   double* Hcur;            // [21] H of the iteration being solved
@@ -175,7 +180,8 @@ struct AlignSmem {
   int* ctrl;               // [0] continue, [1] level break, [2] n_meas, [3] n_inv, [4] n_vis_j
 };
 __host__ __device__ inline size_t align_smem_bytes(int cap) {
-  return size_t(cap) * (ND * 8 + PF * 4 + 1) + 16 + (AL_WARPS * (8 + 21) + 21 * 3 + 8 + 7 + 12) * 8 + (AL_WARPS * 4 + 8) * 4;
+  return size_t(cap) * (ND * 8 + PF * 4 + 1) + 16 + (AL_WARPS * (8 + 21 + 21) + 21 * 3 + 8 + 7 + 12) * 8 +
+         (AL_WARPS * 4 + 8 + AL_PASSES_MAX * AL_WARPS) * 4;
 }
 __device__ __forceinline__ void align_carve(unsigned char* mem, int cap, AlignSmem& s) {
   s.d = reinterpret_cast<double*>(mem);
@@ -184,7 +190,8 @@ __device__ __forceinline__ void align_carve(unsigned char* mem, int cap, AlignSm
   uintptr_t p = (reinterpret_cast<uintptr_t>(s.flag + cap) + 15) & ~uintptr_t(15);
   s.wred = reinterpret_cast<double*>(p);
   s.hred = s.wred + AL_WARPS * 8;
-  s.Hall = s.hred + AL_WARPS * 21;
+  s.hcor = s.hred + AL_WARPS * 21;
+  s.Hall = s.hcor + AL_WARPS * 21;
   s.Hcur = s.Hall + 21;
   s.fac = s.Hcur + 21;
   s.red = s.fac + 21;
@@ -192,6 +199,7 @@ __device__ __forceinline__ void align_carve(unsigned char* mem, int cap, AlignSm
   s.Rt = s.T + 7;
   s.wredi = reinterpret_cast<int*>(s.Rt + 12);
   s.ctrl = s.wredi + AL_WARPS * 4;
+  s.outside = reinterpret_cast<unsigned*>(s.ctrl + 8);
 }
 
 // Features marshalled by the host (class API, AlignJobDev::feats).
@@ -220,9 +228,23 @@ struct SeqFeatures {
 
 // PrecomputePatches for one feature (image_align.cc:208-267).  d / ds: the feature's double cache and its stride,
 // fl: its float row.  Returns the new flags; adds the feature's H_f to Hacc and stores it at gH[k * n].
+// Entry (r, q) of a feature's H_f = sum over its 16 pixels of J J^T, from the gradient moments (sa, sb, sc) and the
+// scaled Jacobian rows.  One definition with explicit roundings: PrecomputePatches (H_all) and the correction for
+// features outside the image must produce the same bits.
+__device__ __forceinline__ double hf_entry(double sa, double sb, double sc, double j0r, double j0q, double j1r, double j1q) {
+  const double aa = __dmul_rn(j0r, j0q);
+  const double ab = __fma_rn(j0r, j1q, __dmul_rn(j1r, j0q));
+  const double bb = __dmul_rn(j1r, j1q);
+  return __fma_rn(sa, aa, __fma_rn(sb, ab, __dmul_rn(sc, bb)));
+}
+__constant__ int c_hr[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
+__constant__ int c_hq[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+
+// PrecomputePatches for one feature (image_align.cc:208-267).  d / ds: the feature's double cache and its stride,
+// fl: its float row.  Returns the new flags; adds the feature's H_f to Hacc.
 __device__ __forceinline__ int precompute_feature(int old_flags, const uint8_t* __restrict__ img1, int W, int Hh, float scale,
                                                   int border, double fs, double* __restrict__ d, int ds,
-                                                  float* __restrict__ fl, double* __restrict__ gH, int n, double Hacc[21]) {
+                                                  float* __restrict__ fl, double Hacc[21]) {
   int flags = old_flags & 9;   // J zeroed per level (image_align.cc:69), visibility sticky
   const bool valid = (old_flags & 8) != 0;
   const float u_ref = float(d[15 * ds] * double(scale));
@@ -274,15 +296,14 @@ __device__ __forceinline__ int precompute_feature(int old_flags, const uint8_t* 
     d[(3 + r) * ds] = j0[r];
     d[(9 + r) * ds] = j1[r];
   }
+  d[17 * ds] = sa; d[18 * ds] = sb; d[19 * ds] = sc;
   // sum over the 16 pixels of J J^T: constant for the whole level (inverse compositional)
   int k = 0;
 #pragma unroll
   for (int r = 0; r < 6; r++)
 #pragma unroll
     for (int q = r; q < 6; q++) {
-      const double h = sa * j0[r] * j0[q] + sb * (j0[r] * j1[q] + j1[r] * j0[q]) + sc * j1[r] * j1[q];
-      gH[size_t(k) * n] = h;
-      Hacc[k] += h;
+      Hacc[k] += hf_entry(sa, sb, sc, j0[r], j0[q], j1[r], j1[q]);
       k++;
     }
   return flags;
@@ -415,7 +436,9 @@ __device__ void align_core(const AlignView& J, const Src& src, const PyrGeom& G,
     const int n_forced = J.forced_T ? J.forced_iters[level] : -1;
     if (n_forced == 0) continue;
     if (tid == 0) T_bk = T;
-    int fac_state = 0;   // thread 0: 0 no factor, 1 S.fac = LDL^T of H_all of this level
+    int fac_state = 0;   // thread 0: 1 = S.fac is the LDL^T factor of H for the set of outside features in S.outside
+    if (lane == 0)   // every warp keeps its own entries: no barrier needed
+      for (int k = 0; k < AL_PASSES_MAX; k++) S.outside[k * AL_WARPS + warp] = 0u;
 
     const int max_its = J.forced_T ? n_forced : P.max_img_align_its;
     for (int it = 0; it < max_its; it++) {
@@ -432,10 +455,10 @@ __device__ void align_core(const AlignView& J, const Src& src, const PyrGeom& G,
         for (int f = tid; f < n; f += AL_THREADS) {
           if (f < cap) {
             S.flag[f] = uint8_t(precompute_feature(S.flag[f], img1, W, Hh, scale, border, fs, S.d + f, cap,
-                                                   S.f + size_t(f) * PF, J.g_H + f, n, Hacc));
+                                                   S.f + size_t(f) * PF, Hacc));
           } else {
             J.g_flags[f] = precompute_feature(J.g_flags[f], img1, W, Hh, scale, border, fs, J.g_d + (f - cap), n_over,
-                                              J.g_f + size_t(f - cap) * PF, J.g_H + f, n, Hacc);
+                                              J.g_f + size_t(f - cap) * PF, Hacc);
           }
         }
 #pragma unroll
@@ -450,17 +473,45 @@ __device__ void align_core(const AlignView& J, const Src& src, const PyrGeom& G,
       double b[6] = {0, 0, 0, 0, 0, 0};
       float chi2_f = 0.0f;
       int n_meas = 0, n_inv = 0, n_visj = 0;
-      for (int f = tid; f < n; f += AL_THREADS) {
-        if (f < cap) {
-          const int flags = S.flag[f];
-          if (!(flags & 1)) continue;
-          S.flag[f] = uint8_t(residual_feature(flags, S.Rt, cam, img2, W, Hh, scale, border, S.d + f, cap,
-                                               S.f + size_t(f) * PF, b, chi2_f, n_meas, n_inv, n_visj));
-        } else {
-          const int flags = J.g_flags[f];
-          if (!(flags & 1)) continue;
-          J.g_flags[f] = residual_feature(flags, S.Rt, cam, img2, W, Hh, scale, border, J.g_d + (f - cap), n_over,
-                                          J.g_f + size_t(f - cap) * PF, b, chi2_f, n_meas, n_inv, n_visj);
+      double hc = 0.0;          // lane k < 21: entry k of the sum of H_f over this warp's features outside the image
+      int set_changed = 0;      // lane 0: the set of those features differs from the one H was last factorised for
+      for (int f0 = 0, pass = 0; f0 < n; f0 += AL_THREADS, pass++) {   // uniform trip count: every warp votes
+        const int f = f0 + tid;
+        bool outside = false;
+        if (f < n) {
+          const int flags = f < cap ? int(S.flag[f]) : J.g_flags[f];
+          if (flags & 1) {
+            const int inv_before = n_inv;
+            int nf;
+            if (f < cap) {
+              nf = residual_feature(flags, S.Rt, cam, img2, W, Hh, scale, border, S.d + f, cap, S.f + size_t(f) * PF, b,
+                                    chi2_f, n_meas, n_inv, n_visj);
+              S.flag[f] = uint8_t(nf);
+            } else {
+              nf = residual_feature(flags, S.Rt, cam, img2, W, Hh, scale, border, J.g_d + (f - cap), n_over,
+                                    J.g_f + size_t(f - cap) * PF, b, chi2_f, n_meas, n_inv, n_visj);
+              J.g_flags[f] = nf;
+            }
+            outside = n_inv != inv_before;   // has a Jacobian at this level but projects outside the current image
+          }
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, outside);
+        if (lane == 0 && pass < AL_PASSES_MAX) {
+          if (S.outside[pass * AL_WARPS + warp] != bal) { S.outside[pass * AL_WARPS + warp] = bal; set_changed = 1; }
+        }
+        if (pass >= AL_PASSES_MAX && bal) set_changed = 1;   // beyond the bookkeeping: never reuse a factor
+        // the owning warp re-forms H_f of each such feature, lane k computing entry k (fixed order: ascending feature)
+        __syncwarp();   // the caches of a feature were written by its own lane
+        while (bal) {
+          const int src = __ffs(bal) - 1;
+          bal &= bal - 1;
+          const int fo = f0 + warp * 32 + src;
+          if (lane < 21) {
+            const double* __restrict__ d = fo < cap ? S.d + fo : J.g_d + (fo - cap);
+            const int ds = fo < cap ? cap : n_over;
+            const int r = c_hr[lane], q = c_hq[lane];
+            hc += hf_entry(d[17 * ds], d[18 * ds], d[19 * ds], d[(3 + r) * ds], d[(3 + q) * ds], d[(9 + r) * ds], d[(9 + q) * ds]);
+          }
         }
       }
       {
@@ -476,7 +527,10 @@ __device__ void align_core(const AlignView& J, const Src& src, const PyrGeom& G,
         const int m = int(__reduce_add_sync(0xffffffffu, unsigned(n_meas)));
         const int ni = int(__reduce_add_sync(0xffffffffu, unsigned(n_inv)));
         const int nv = int(__reduce_add_sync(0xffffffffu, unsigned(n_visj)));
-        if (lane == 0) { S.wredi[warp * 4] = m; S.wredi[warp * 4 + 1] = ni; S.wredi[warp * 4 + 2] = nv; }
+        if (lane == 0) {
+          S.wredi[warp * 4] = m; S.wredi[warp * 4 + 1] = ni; S.wredi[warp * 4 + 2] = nv; S.wredi[warp * 4 + 3] = set_changed;
+        }
+        if (lane < 21) S.hcor[warp * 21 + lane] = hc;
       }
       __syncthreads();
       if (tid == 0) { const long long t = clock64(); cyc[1] += t - t_mark; t_mark = t; }
@@ -496,26 +550,23 @@ __device__ void align_core(const AlignView& J, const Src& src, const PyrGeom& G,
           S.red[lane] = tot;
         }
         int ti = 0;
-        if (lane < 3) {
+        if (lane < 4) {
 #pragma unroll
           for (int w = 0; w < AL_WARPS; w++) ti += S.wredi[w * 4 + lane];
         }
         const int nm = __shfl_sync(0xffffffffu, ti, 0);
         const int ninv = __shfl_sync(0xffffffffu, ti, 1);
         const int nvisj = __shfl_sync(0xffffffffu, ti, 2);
-        // H: every feature with a Jacobian projects inside the image -> H_all; none does -> 0; otherwise H_all minus
-        // the ones outside, or the sum of the ones inside when those are fewer (fixed feature order, lane k owns H[k])
+        const bool set_changed_any = __shfl_sync(0xffffffffu, ti, 3) != 0;
+        // H: every feature with a Jacobian projects inside the image -> H_all; none does -> exactly 0 (as the
+        // reference's empty sum); otherwise H_all minus the H_f of the ones outside
         if (ninv > 0 && lane < 21) {
           double h = 0.0;
           if (nvisj > 0) {
-            const bool sum_inside = nvisj < ninv;
-            const int want = sum_inside ? 6 : 2;     // has J & inside  /  has J & not inside
-            double acc = 0.0;
-            for (int f = 0; f < n; f++) {
-              const int fl = f < cap ? int(S.flag[f]) : J.g_flags[f];
-              if ((fl & 6) == want) acc += J.g_H[size_t(lane) * n + f];
-            }
-            h = sum_inside ? acc : S.Hall[lane] - acc;
+            double c = 0.0;
+#pragma unroll
+            for (int w = 0; w < AL_WARPS; w++) c += S.hcor[w * 21 + lane];
+            h = S.Hall[lane] - c;
           }
           S.Hcur[lane] = h;
         }
@@ -534,19 +585,18 @@ __device__ void align_core(const AlignView& J, const Src& src, const PyrGeom& G,
           // normal case; the factor of H_all serves every iteration of the level), Eigen's pivoted algorithm otherwise
           // (singular / empty systems, NaN propagation)
           bool solved = false;
-          if (ninv == 0 && fac_state == 1) {
+          if (fac_state == 1 && !set_changed_any) {   // same H as the last factorisation: substitutions only
             ldlt_apply6(S.fac, bb, x);
             solved = true;
           } else {
             double fac[21];
+            fac_state = 0;
             if (ldlt_factor6(Hup, fac)) {
               ldlt_apply6(fac, bb, x);
               solved = true;
-              if (ninv == 0) {
 #pragma unroll
-                for (int k = 0; k < 21; k++) S.fac[k] = fac[k];
-                fac_state = 1;
-              }
+              for (int k = 0; k < 21; k++) S.fac[k] = fac[k];
+              fac_state = 1;
             }
           }
           if (!solved) {
@@ -644,8 +694,7 @@ __global__ void __launch_bounds__(AL_THREADS, 1) image_align_kernel(const AlignJ
   J.out_pose = Jd.out_pose; J.cur_pose = Jd.cur.pose; J.out_info = Jd.out_info; J.out_error = Jd.out_error;
   J.out_cycles = Jd.out_cycles;
   J.trace = Jd.trace; J.trace_cap = Jd.trace_cap; J.forced_T = Jd.forced_T; J.forced_iters = Jd.forced_iters;
-  J.g_H = Jd.sc_d;
-  J.g_d = Jd.sc_d + size_t(21) * Jd.n;
+  J.g_d = Jd.sc_d;
   J.g_f = Jd.sc_f;
   J.g_flags = Jd.sc_flags;
   JobFeatures src{Jd.feats};
@@ -694,8 +743,7 @@ __global__ void __launch_bounds__(AL_THREADS, 1) seq_align_kernel(const __grid_c
   // the sequence's own scratch, carved by ITS capacity (sequences of one submission may differ)
   const size_t nn = size_t(S->max_feats);
   double* sc_d = reinterpret_cast<double*>(S->align_scratch);
-  J.g_H = sc_d;
-  J.g_d = sc_d + size_t(21) * n;
+  J.g_d = sc_d;
   J.g_f = reinterpret_cast<float*>(S->align_scratch + nn * SDVLB_ALIGN_SC_DOUBLES * 8);
   J.g_flags = reinterpret_cast<int32_t*>(S->align_scratch + nn * (SDVLB_ALIGN_SC_DOUBLES * 8 + SDVLB_ALIGN_SC_FLOATS * 4));
   SeqFeatures src;

@@ -18,7 +18,7 @@
 #include "common.cuh"
 
 // ---- kernel launchers (other translation units)
-cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, cudaStream_t stream);
+cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, bool src_on_device, cudaStream_t stream);
 cudaError_t sdvlb_launch_undistort(const FrameBatch& B, const ImageBatch& raw, const UndistortArgs& U, cudaStream_t stream);
 cudaError_t sdvlb_launch_seed_update(sdvlb_seed* d_seeds, int n, const FrameDev& cur, const PyrGeom& g,
                                      const DevParams& dp, const sdvlb_seed_params& sp, cudaStream_t stream);
@@ -341,8 +341,9 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
     ImageBatch I;
     B.n = m;
     B.scratch_base = base;
-    bool by_kernel = true;
+    bool by_kernel = true, all_device = true;
     for (int i = 0; i < m; i++) {
+      if (image_loc[base + i] != 1) all_device = false;
       sdvlb_frame* f = frames[base + i];
       B.f[i] = f->dev;
       B.f[i].host_mirror = (want_corners && mirror) ? reinterpret_cast<int32_t*>(f->h_corners) : nullptr;
@@ -375,7 +376,7 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
     std::unique_lock<std::mutex> ulock;
     if (ustream != stream && c->umutex) ulock = std::unique_lock<std::mutex>(*c->umutex);
     if (by_kernel) {
-      SDVLB_CUDA_TRY(sdvlb_launch_upload(Bup, I, int(img_bytes), ustream));
+      SDVLB_CUDA_TRY(sdvlb_launch_upload(Bup, I, int(img_bytes), all_device, ustream));
       c->n_launches += 1;
     } else {
       // copy engine into level 0 of the frame slots; with distortion set the raw pixels then move on to the scratch
@@ -386,7 +387,7 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
       if (c->has_dist) {
         ImageBatch I2;
         for (int i = 0; i < m; i++) I2.src[i] = B.f[i].pyr;
-        SDVLB_CUDA_TRY(sdvlb_launch_upload(Bup, I2, int(img_bytes), ustream));
+        SDVLB_CUDA_TRY(sdvlb_launch_upload(Bup, I2, int(img_bytes), true, ustream));
         c->n_launches += 1;
       }
     }

@@ -67,10 +67,10 @@ struct DevParams {
   sdvlb_camera cam;
 };
 
-// ImageAlign scratch in global memory per feature: 38 doubles (the level's per-feature J J^T sum [21]; xyz[3], j0[6],
-// j1[6], px[2] for the features that do not fit the kernel's shared-memory cache), 52 floats (patch[16], dx[16], dy[16]
-// + 4 pad of the same overflow features) and one flag word.
-#define SDVLB_ALIGN_SC_DOUBLES 38
+// ImageAlign scratch in global memory per feature, used by the features that do not fit the kernel's shared-memory
+// cache: 20 doubles (xyz[3], j0[6], j1[6], px[2], gradient moments[3]), 52 floats (patch[16], dx[16], dy[16] + 4 pad)
+// and one flag word.
+#define SDVLB_ALIGN_SC_DOUBLES 20
 #define SDVLB_ALIGN_SC_FLOATS 52
 #define SDVLB_ALIGN_SC_BYTES(n) (size_t(n) * (SDVLB_ALIGN_SC_DOUBLES * 8 + SDVLB_ALIGN_SC_FLOATS * 4 + 4))
 // One ImageAlign::ComputePose call (device descriptor).

@@ -332,7 +332,13 @@ int tail_source_level(const PyrGeom& g, size_t* smem_bytes) {
 
 }  // namespace
 
-cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, cudaStream_t stream) {
+cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, bool src_on_device, cudaStream_t stream) {
+  static const bool emulate_pcie = getenv("SDVLB_UPLOAD_MIN_NS_PER_FRAME") != nullptr;   // experiment knob, see below
+  if (src_on_device && !emulate_pcie) {   // HBM -> HBM: no PCIe depth to manage, a plain wide copy (8 CTAs per frame)
+    SDVLB_PREPARE(upload_kernel, 0);
+    upload_kernel<<<dim3(8, B.n), 256, 0, stream>>>(B, I, bytes);
+    return cudaGetLastError();
+  }
   // PCIe wants its bandwidth-delay product in flight (~100 KB) and not much more: every other PCIe read -- above all
   // the GPU front end fetching the launch commands of the compute kernels -- queues behind what the upload has
   // outstanding.  The bulk kernel keeps SDVLB_UPLOAD_CTAS (default 2) x 32 KB in flight whatever the batch size

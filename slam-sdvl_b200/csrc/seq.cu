@@ -495,6 +495,17 @@ __device__ __forceinline__ void signal_done(const SeqStepArgs& A) {
   }
 }
 
+// The observation arrays of the pose refinement (a, pos, scale, err: 7 doubles, and a flag per observation) live in
+// shared memory when the problem is small enough (always, for FeatureAlign's max_matches <= 256): every Gauss-Newton
+// iteration of every RANSAC hypothesis re-reads them.
+constexpr int OBS_SMEM_MAX = 256;
+__host__ __device__ inline size_t obs_smem_bytes(int cap) { return size_t(cap) * (7 * sizeof(double) + sizeof(int32_t)); }
+__device__ inline void obs_carve(unsigned char* mem, int cap, PoseProblem& P) {   // mem 8-byte aligned
+  double* d = reinterpret_cast<double*>(mem);
+  P.o_a = d; P.o_pos = d + 2 * size_t(cap); P.o_scale = d + 5 * size_t(cap); P.o_err = d + 6 * size_t(cap);
+  P.o_flag = reinterpret_cast<int32_t*>(d + 7 * size_t(cap));
+}
+
 struct PostShared {
   PoseShared ps;
   RansacShared rs;
@@ -697,7 +708,14 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   main_sync();
   const int n_found = sh.n_found;
   PoseProblem P;
-  P.o_a = S->o_a; P.o_pos = S->o_pos; P.o_scale = S->o_scale; P.o_err = S->o_err; P.o_flag = S->o_flag;
+  const int obs_cap = min(OBS_SMEM_MAX, (A.dp.p.max_matches + 7) & ~7);
+  if (A.dp.p.max_matches <= OBS_SMEM_MAX) {
+    obs_carve(reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN +
+                  (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16 + ((size_t(4 * n_cells) * sizeof(int) + 15) / 16) * 16,
+              obs_cap, P);
+  } else {
+    P.o_a = S->o_a; P.o_pos = S->o_pos; P.o_scale = S->o_scale; P.o_err = S->o_err; P.o_flag = S->o_flag;
+  }
   P.n = n_found;
   // ---- SelectPoints side effects (feature_align.cc:112-147): attempts, Promote / Unpromote, new features
   {
@@ -838,7 +856,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     Rz->stats[5] = sh.n_inl;        // Frame::GetNumPoints(): features that still have a point
     Rz->stats[6] = S->align_info[1];
     Rz->stats[7] = n_found;
-    Rz->error = S->overflow;
+    Rz->error = S->overflow | (nc > A.max_feats ? 2 : 0);   // 2: more features than the submission was sized for
     Rz->status = SDVLB_SEQ_TRACKED;
     Rz->quality = quality;
     Rz->need_keyframe = need_kf;
@@ -877,9 +895,15 @@ __global__ void __launch_bounds__(PO_MAIN, 1) pose_call_kernel(const __grid_cons
     ransac_carve(sh.rs, reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN, A.dp.p.max_ransac_its);
   PoseProblem P;
   P.n = A.n;
-  P.o_a = A.scratch; P.o_pos = A.scratch + 2 * size_t(A.n); P.o_scale = A.scratch + 5 * size_t(A.n);
-  P.o_err = A.scratch + 6 * size_t(A.n);
-  P.o_flag = A.iscratch;
+  if (A.n <= OBS_SMEM_MAX) {
+    obs_carve(reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN +
+                  (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16,
+              (A.n + 7) & ~7, P);
+  } else {
+    P.o_a = A.scratch; P.o_pos = A.scratch + 2 * size_t(A.n); P.o_scale = A.scratch + 5 * size_t(A.n);
+    P.o_err = A.scratch + 6 * size_t(A.n);
+    P.o_flag = A.iscratch;
+  }
   for (int i = tid; i < A.n; i += PO_MAIN) {
     const sdvlb_pose_obs o = A.obs[i];
     P.o_a[2 * i] = o.v[0] / o.v[2]; P.o_a[2 * i + 1] = o.v[1] / o.v[2];
@@ -918,15 +942,18 @@ cudaError_t sdvlb_launch_seq_apply(const SeqCmd* d_cmds, const int2* d_ranges, i
 
 cudaError_t sdvlb_launch_seq_post(const SeqStepArgs& A, cudaStream_t stream) {
   const int n_cells = A.g.wcells[0] * A.g.hcells[0];
+  const int obs_cap = A.dp.p.max_matches <= OBS_SMEM_MAX ? ((A.dp.p.max_matches + 7) & ~7) : 0;
   const size_t dyn = ((sizeof(PostShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN +
-                     (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16 + size_t(4 * n_cells) * sizeof(int);
+                     (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16 + ((size_t(4 * n_cells) * sizeof(int) + 15) / 16) * 16 +
+                     obs_smem_bytes(obs_cap);
   SDVLB_PREPARE(seq_post_kernel, dyn);
   return sdvlb_launch_dependent(seq_post_kernel, dim3(A.n), dim3(PO_THREADS), dyn, stream, A);
 }
 
 cudaError_t sdvlb_launch_pose_call(const PoseCallArgs& A, cudaStream_t stream) {
   const size_t dyn = ((sizeof(PoseCallShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN +
-                     (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16;
+                     (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16 +
+                     (A.n <= OBS_SMEM_MAX ? obs_smem_bytes((A.n + 7) & ~7) : 0);
   SDVLB_PREPARE(pose_call_kernel, dyn);
   pose_call_kernel<<<1, PO_MAIN, dyn, stream>>>(A);
   return cudaGetLastError();

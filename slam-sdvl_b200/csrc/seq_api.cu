@@ -47,6 +47,12 @@ int ensure_step_buffers(sdvlb_ctx* c) {
   if (c->d_seq_done) return 0;
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_seq_done), 256));
   SDVLB_CUDA_TRY(cudaMemsetAsync(c->d_seq_done, 0, 256, c->stream));
+  // the command staging of every submission slot up front: an allocation (pinned host + device) synchronises the
+  // device and costs milliseconds, and which slot carries the next keyframe's points is a matter of timing
+  for (Arena& a : c->seq_in) {
+    const int rc = ensure_arena(&a, 1 << 20, true);
+    if (rc) return rc;
+  }
   return 0;
 }
 
@@ -188,7 +194,7 @@ int sdvlb_seq_create(sdvlb_ctx* c, int max_feats, sdvlb_seq** out) {
   }
   c->seqs.push_back(s);
   *out = s;
-  return 0;
+  return ensure_step_buffers(c);
 }
 
 int sdvlb_seq_destroy(sdvlb_ctx* c, sdvlb_seq* s) {
