@@ -35,7 +35,7 @@ cudaError_t sdvlb_launch_search_orb(const SearchCandDev* d_cands, int n, const F
 cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
                                     cudaStream_t stream);
 cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
-                                     uint32_t* level_kp, int32_t* level_cnt, int32_t* frame_ticket,
+                                     int32_t* cell_kept, uint32_t* level_kp, int32_t* level_cnt, int32_t* tickets,
                                      cudaStream_t stream);
 cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, int n_bound, const PyrGeom& g, const DevParams& dp,
                                cudaStream_t stream);
@@ -130,16 +130,19 @@ int ensure_fast_scratch(sdvlb_ctx* c, int n_frames) {
   SDVLB_CUDA_TRY(cudaStreamSynchronize(c->bstream));
   SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
   const int nf = std::max(n_frames, c->fast_frames * 2);
-  cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt); cudaFree(c->frame_ticket);
-  c->cell_kp = nullptr; c->cell_cnt = nullptr; c->level_kp = nullptr; c->level_cnt = nullptr; c->frame_ticket = nullptr;
+  cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->cell_kept); cudaFree(c->level_kp); cudaFree(c->level_cnt);
+  cudaFree(c->frame_ticket);
+  c->cell_kp = nullptr; c->cell_cnt = nullptr; c->cell_kept = nullptr; c->level_kp = nullptr; c->level_cnt = nullptr;
+  c->frame_ticket = nullptr;
   c->fast_frames = 0;
   const size_t cells = size_t(c->geom.total_cells) * nf;
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->cell_kp), cells * SDVLB_CELL_CAP * sizeof(uint32_t)));
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->cell_cnt), cells * sizeof(int32_t)));
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->cell_kept), cells * sizeof(int32_t)));
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->level_kp), c->level_kp_total * nf * sizeof(uint32_t)));
   SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->level_cnt), size_t(nf) * SDVLB_MAX_LEVELS * sizeof(int32_t)));
-  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->frame_ticket), size_t(nf) * sizeof(int32_t)));
-  SDVLB_CUDA_TRY(cudaMemset(c->frame_ticket, 0, size_t(nf) * sizeof(int32_t)));
+  SDVLB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->frame_ticket), size_t(nf) * SDVLB_TICKET_STRIDE * sizeof(int32_t)));
+  SDVLB_CUDA_TRY(cudaMemset(c->frame_ticket, 0, size_t(nf) * SDVLB_TICKET_STRIDE * sizeof(int32_t)));
   c->fast_frames = nf;
   return 0;
 }
@@ -415,7 +418,7 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
       SDVLB_CUDA_TRY(sdvlb_launch_fast_cells(B, *plan, c->cell_kp, c->cell_cnt, stream));
       timer_end(c);
       timer_begin(c, SDVLB_K_SELECT, stream);
-      SDVLB_CUDA_TRY(sdvlb_launch_fast_select(B, *plan, c->cell_kp, c->cell_cnt, c->level_kp, c->level_cnt,
+      SDVLB_CUDA_TRY(sdvlb_launch_fast_select(B, *plan, c->cell_kp, c->cell_cnt, c->cell_kept, c->level_kp, c->level_cnt,
                                               c->frame_ticket, stream));
       timer_end(c);
       c->n_launches += 2;
@@ -781,7 +784,7 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   if (c->h_seeds) cudaFreeHost(c->h_seeds);
   if (c->raw_scratch) cudaFree(c->raw_scratch);
   for (int i = 0; i < kBuildEvents; i++) if (c->raw_done[i]) cudaEventDestroy(c->raw_done[i]);
-  cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->level_kp); cudaFree(c->level_cnt);
+  cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->cell_kept); cudaFree(c->level_kp); cudaFree(c->level_cnt);
   cudaFree(c->frame_ticket); cudaFree(c->scratch);
   if (c->h_overflow) cudaFreeHost(c->h_overflow);
   while (!c->seqs.empty()) sdvlb_seq_destroy(c, c->seqs.back());
@@ -965,8 +968,8 @@ int sdvlb_frame_detect(sdvlb_ctx* ctx, sdvlb_frame* f, int nfeatures) {
   SDVLB_CUDA_TRY(sdvlb_launch_fast_cells(B, *plan, ctx->cell_kp, ctx->cell_cnt, ctx->stream));
   timer_end(ctx);
   timer_begin(ctx, SDVLB_K_SELECT);
-  SDVLB_CUDA_TRY(sdvlb_launch_fast_select(B, *plan, ctx->cell_kp, ctx->cell_cnt, ctx->level_kp, ctx->level_cnt,
-                                          ctx->frame_ticket, ctx->stream));
+  SDVLB_CUDA_TRY(sdvlb_launch_fast_select(B, *plan, ctx->cell_kp, ctx->cell_cnt, ctx->cell_kept, ctx->level_kp,
+                                          ctx->level_cnt, ctx->frame_ticket, ctx->stream));
   timer_end(ctx);
   ctx->n_launches += 2;
   SDVLB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -133,6 +133,7 @@ struct sdvlb_ctx {
   int fast_frames = 0;
   uint32_t* cell_kp = nullptr;
   int32_t* cell_cnt = nullptr;
+  int32_t* cell_kept = nullptr;   // survivors of the per-cell retainBest
   uint32_t* level_kp = nullptr;
   int32_t* level_cnt = nullptr;
   int32_t* frame_ticket = nullptr;

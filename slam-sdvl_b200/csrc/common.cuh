@@ -125,7 +125,9 @@ struct FastArgs {
   int level_kp_off[SDVLB_MAX_LEVELS];
   int level_kp_total;
   int32_t* overflow_flag;   // pinned, device-visible: set when a fixed capacity was exceeded
+  int part_off[SDVLB_MAX_LEVELS + 1];   // selection kernel: first CTA (part) of each level, [n_fast_levels] = total
 };
+#define SDVLB_TICKET_STRIDE 16   // ints of selection tickets per frame: [0] levels done, [1 + l] parts of level l done
 struct FastPlan {
   FastArgs args;
   int max_cells_level;

@@ -9,8 +9,10 @@
 //  fast_select_kernel: one CTA per (level, frame): water-filling quota (fast_detector.cc:114-135), per-cell
 //                      retainBest, level-wide retainBest, and — by the last CTA of a frame — concatenation of the
 //                      levels into Frame::corners_ order.
+#include <algorithm>
+
 #include "common.cuh"
-#include "select_impl.h"
+#include "select_warp.cuh"
 
 namespace {
 
@@ -18,6 +20,7 @@ constexpr int DET_WARPS = 4;          // one warp per 32x32 cell, no block-level
 constexpr int DET_THREADS = DET_WARPS * 32;
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_SMEM_KEYS = 4096;   // level-wide retainBest runs in shared memory up to this many keypoints
+constexpr int SEL_PART_CELLS = 64;    // cells of one level per CTA of the selection kernel (8 per warp)
 constexpr int TSE = 40;               // score tile row stride in 16-bit elements
 constexpr int TSW = TSE / 2;          // ... in 32-bit words (one word = one horizontally adjacent pixel pair)
 // Pixel tile row stride in words: 45 = 13 (mod 32), so the 13 + 13 + 6 pairs of three consecutive tile rows that one warp
@@ -261,24 +264,59 @@ __device__ __forceinline__ T block_sum(T v, T* s_tmp) {   // all threads get the
   return r;
 }
 
+// Exclusive scan of vals[0..n) in place (n <= a few thousand) by the CTA; vals[n] receives the total.
+__device__ __forceinline__ void block_exclusive_scan(int* vals, int n, int* s_tmp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + SEL_THREADS - 1) / SEL_THREADS;
+  const int c0 = min(n, tid * per), c1 = min(n, c0 + per);
+  int local = 0;
+  for (int c = c0; c < c1; c++) local += vals[c];
+  int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  __syncthreads();
+  if (lane == 31) s_tmp[warp] = incl;
+  __syncthreads();
+  int run = incl - local;
+  for (int w = 0; w < warp; w++) run += s_tmp[w];
+  for (int c = c0; c < c1; c++) { const int v = vals[c]; vals[c] = run; run += v; }
+  if (tid == SEL_THREADS - 1) vals[n] = run;
+  __syncthreads();
+}
+
+// fast_select_kernel: grid (parts, frames); a part is SEL_PART_CELLS consecutive cells of one level.
+//   1. every CTA runs the level's water-filling quota (fast_detector.cc:108-135) -- a few block-wide sums over the
+//      level's cell counts -- and keeps the quotas of its own cells;
+//   2. per-cell retainBest (fast_detector.cc:138-140), one WARP per cell (select_warp.cuh), in shared memory;
+//   3. the last CTA of a (level, frame) gathers the survivors into the level list and runs the level-wide retainBest
+//      (fast_detector.cc:146-148) on warp 0;
+//   4. the last CTA of a frame concatenates the levels into Frame::corners_ order (fast_detector.cc:150-151,170-173),
+//      mirrors the list to the host and builds the matcher's grid index.
 __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_constant__ FrameBatch B,
                                                                   const __grid_constant__ FastArgs A,
                                                                   uint32_t* __restrict__ cell_kp,
                                                                   const int32_t* __restrict__ cell_cnt,
+                                                                  int32_t* __restrict__ cell_kept,
                                                                   uint32_t* __restrict__ level_kp,
                                                                   int32_t* __restrict__ level_cnt,
-                                                                  int32_t* __restrict__ frame_ticket, int pool_keys) {
-  extern __shared__ int s_dyn[];   // nleft[ncells], nsel[ncells], kept_off[ncells+1], then the per-cell selection pool
+                                                                  int32_t* __restrict__ tickets, int max_cells) {
+  extern __shared__ __align__(16) int s_dyn[];   // nleft[max_cells + 1], nsel[max_cells + 1], then the work area
   __shared__ int s_tmp[SEL_THREADS / 32];
-  __shared__ uint32_t s_keys[SEL_SMEM_KEYS];
   __shared__ int s_final, s_ticket;
 
-  const int tid = threadIdx.x;
-  const int level = blockIdx.x, frame = B.scratch_base + blockIdx.y;   // `frame` indexes the scratch arrays
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = B.scratch_base + blockIdx.y;   // index into the scratch arrays
+  int level = 0;
+  while (level + 1 < A.n_fast_levels && int(blockIdx.x) >= A.part_off[level + 1]) level++;
+  const int part = int(blockIdx.x) - A.part_off[level];
+  const int n_parts = A.part_off[level + 1] - A.part_off[level];
   const int ncells = A.g.wcells[level] * A.g.hcells[level];
   int* nleft = s_dyn;
-  int* nsel = s_dyn + ncells;
-  int* koff = s_dyn + 2 * ncells;
+  int* nsel = s_dyn + (max_cells + 1);
+  unsigned char* work = reinterpret_cast<unsigned char*>(s_dyn + 2 * (max_cells + 1));
   const int cbase = frame * A.g.total_cells + A.g.cell_off[level];
   const int nfeatures = A.nfeat[level];
 
@@ -310,67 +348,65 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   }
   __syncthreads();
 
-  // ---- per-cell retainBest (fast_detector.cc:138-140).  The selection replays libstdc++'s nth_element / partition
-  // (the ORDER of the survivors is part of the contract), a chain of dependent accesses one thread long: each thread
-  // pulls its cell's keypoints into a shared-memory pool first, so the chain runs at shared-memory latency instead
-  // of L2 latency (cells that do not fit in the pool are processed in place).
-  uint32_t* const pool = reinterpret_cast<uint32_t*>(s_dyn + 3 * ncells + 4);
-  for (int c0 = 0; c0 < ncells; c0 += SEL_THREADS) {
-    const int c = c0 + tid;
-    const int n = c < ncells ? max(cell_cnt[cbase + c], 0) : 0;
-    // exclusive scan of n over the CTA
-    const int lane = tid & 31, warp = tid >> 5;
-    int incl = n;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    __syncthreads();   // s_tmp and the pool are free again
-    if (lane == 31) s_tmp[warp] = incl;
-    __syncthreads();
-    int off = incl - n;
-    for (int w = 0; w < warp; w++) off += s_tmp[w];
-    if (c < ncells) {
-      uint32_t* const g = cell_kp + size_t(cbase + c) * SDVLB_CELL_CAP;
-      const bool in_pool = off + n <= pool_keys;
-      uint32_t* const wk = in_pool ? pool + off : g;
-      if (in_pool)
-        for (int i = 0; i < n; i++) wk[i] = g[i];
-      int kept = 0;
-      if (n > 0) kept = sdvlb_sel::retain_best<10>(wk, n, nsel[c]);
-      if (in_pool)
-        for (int i = 0; i < kept; i++) g[i] = wk[i];
-      nleft[c] = kept;   // reuse as kept count
-    }
-  }
-  __syncthreads();
-
-  // ---- exclusive scan of kept counts in cell order
+  // ---- per-cell retainBest (fast_detector.cc:138-140): warp w takes cells c0 + w, c0 + w + 8, ... of this part.  The
+  // keypoints of the warp's NEXT cell are fetched (into registers) while the current one is being selected.
   {
-    const int per = (ncells + SEL_THREADS - 1) / SEL_THREADS;
-    const int c0 = tid * per, c1 = min(ncells, c0 + per);
-    int local = 0;
-    for (int c = c0; c < c1; c++) local += nleft[c];
-    // block exclusive scan of `local`
-    const int lane = tid & 31, warp = tid >> 5;
-    int incl = local;
+    uint32_t* const kbuf = reinterpret_cast<uint32_t*>(work) + warp * SDVLB_CELL_CAP;
+    uint8_t* const pbuf = work + (SEL_THREADS / 32) * SDVLB_CELL_CAP * sizeof(uint32_t) + warp * 2 * SDVLB_CELL_CAP;
+    constexpr int KPL = (SDVLB_CELL_CAP + 31) / 32;   // keypoints per lane
+    const int c0 = part * SEL_PART_CELLS, c1 = min(ncells, c0 + SEL_PART_CELLS);
+    uint32_t nxt[KPL];
+    int n_nxt = 0;
+    auto fetch = [&](int c) {
+      n_nxt = 0;
+      if (c < c1) {
+        n_nxt = max(cell_cnt[cbase + c], 0);
+        if (n_nxt <= nsel[c]) return;   // nothing to select: the list stays as it is
+        const uint32_t* g = cell_kp + size_t(cbase + c) * SDVLB_CELL_CAP;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+        for (int k = 0; k < KPL; k++) nxt[k] = (lane + 32 * k < n_nxt) ? g[lane + 32 * k] : 0u;
+      }
+    };
+    fetch(c0 + warp);
+    for (int c = c0 + warp; c < c1; c += SEL_THREADS / 32) {
+      const int n = n_nxt;
+      const int quota = nsel[c];
+      int kept = n;
+      if (n > quota) {
+#pragma unroll
+        for (int k = 0; k < KPL; k++)
+          if (lane + 32 * k < n) kbuf[lane + 32 * k] = nxt[k];
+      }
+      __syncwarp();
+      fetch(c + SEL_THREADS / 32);
+      if (n > quota) {
+        uint32_t* const g = cell_kp + size_t(cbase + c) * SDVLB_CELL_CAP;
+        kept = sdvlb_sel::warp_retain_best<10, uint8_t>(kbuf, n, quota, pbuf);
+        for (int i = lane; i < kept; i += 32) g[i] = kbuf[i];
+        __syncwarp();
+      }
+      if (lane == 0) cell_kept[cbase + c] = kept;
     }
-    if (lane == 31) s_tmp[warp] = incl;
-    __syncthreads();
-    int wbase = 0;
-    for (int w = 0; w < warp; w++) wbase += s_tmp[w];
-    int run = wbase + incl - local;
-    for (int c = c0; c < c1; c++) { koff[c] = run; run += nleft[c]; }
-    if (tid == SEL_THREADS - 1) koff[ncells] = run;
-    __syncthreads();
   }
-  const int total = koff[ncells];
+
+  // ---- last CTA of this (level, frame): level list + level-wide retainBest
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(&tickets[frame * SDVLB_TICKET_STRIDE + 1 + level], 1);
+  __syncthreads();
+  if (s_ticket != n_parts - 1) return;
+  __threadfence();
+  if (tid == 0) tickets[frame * SDVLB_TICKET_STRIDE + 1 + level] = 0;
+  int* kept_of = nleft;   // kept count, then its exclusive scan (the water-filling state is no longer needed)
+  for (int c = tid; c < ncells; c += SEL_THREADS) kept_of[c] = __ldcg(&cell_kept[cbase + c]);
+  __syncthreads();
+  for (int c = tid; c < ncells; c += SEL_THREADS) nsel[c] = kept_of[c];   // counts, kept beside their offsets
+  __syncthreads();
+  block_exclusive_scan(kept_of, ncells, s_tmp);
+  const int total = kept_of[ncells];
   uint32_t* __restrict__ lk = level_kp + size_t(frame) * A.level_kp_total + A.level_kp_off[level];
+  uint32_t* const s_keys = reinterpret_cast<uint32_t*>(work);
+  uint16_t* const s_pos = reinterpret_cast<uint16_t*>(work + SEL_SMEM_KEYS * sizeof(uint32_t));
   const bool use_smem = total <= SEL_SMEM_KEYS;
   const bool fits = total <= A.level_cap[level];
   if (!fits && tid == 0) *reinterpret_cast<volatile int32_t*>(A.overflow_flag) = 1;
@@ -378,29 +414,36 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   // ---- gather to the level list (fast_detector.cc:141-142): key = score<<22 | y<<11 | x (level coordinates)
   const int wc = A.g.wcells[level];
   if (fits) {
-    for (int c = tid; c < ncells; c += SEL_THREADS) {
-      const int k = nleft[c];
+    for (int c = tid; c < ncells; c += SEL_THREADS) {   // a thread per cell: its (few) loads are all in flight at once
+      const int k = nsel[c];
       const uint32_t* src = cell_kp + size_t(cbase + c) * SDVLB_CELL_CAP;
       const int ci = c / wc, cj = c - ci * wc;
       for (int i = 0; i < k; i++) {
-        const uint32_t v = src[i];
+        const uint32_t v = __ldcg(src + i);
         const uint32_t key = ((v >> 10) << 22) | (uint32_t(ci * SDVLB_CELL + ((v >> 5) & 31)) << 11) |
                              uint32_t(cj * SDVLB_CELL + (v & 31));
-        if (use_smem) s_keys[koff[c] + i] = key;
-        else lk[koff[c] + i] = key;
+        if (use_smem) s_keys[kept_of[c] + i] = key;
+        else lk[kept_of[c] + i] = key;
       }
     }
   }
   __syncthreads();
 
-  // ---- level-wide retainBest (fast_detector.cc:146-148)
-  if (tid == 0) {
-    int fin = fits ? total : 0;
-    if (fits && total > nfeatures) fin = sdvlb_sel::retain_best<22>(use_smem ? s_keys : lk, total, nfeatures);
-    s_final = fin;
+  // ---- level-wide retainBest (fast_detector.cc:146-148): warp 0 in shared memory; one thread on the global list when
+  // the level holds more than SEL_SMEM_KEYS candidates
+  int fin = fits ? total : 0;
+  if (fits && total > nfeatures) {
+    if (use_smem) {
+      if (warp == 0) {
+        const int f2 = sdvlb_sel::warp_retain_best<22, uint16_t>(s_keys, total, nfeatures, s_pos);
+        if (lane == 0) s_final = f2;
+      }
+    } else if (tid == 0) {
+      s_final = sdvlb_sel::retain_best<22>(lk, total, nfeatures);
+    }
+    __syncthreads();
+    fin = s_final;
   }
-  __syncthreads();
-  const int fin = s_final;
   if (use_smem)
     for (int i = tid; i < fin; i += SEL_THREADS) lk[i] = s_keys[i];
   if (tid == 0) level_cnt[frame * SDVLB_MAX_LEVELS + level] = fin;
@@ -408,7 +451,7 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   // ---- last CTA of this frame concatenates the levels (fast_detector.cc:150-151,170-173)
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(&frame_ticket[frame], 1);
+  if (tid == 0) s_ticket = atomicAdd(&tickets[frame * SDVLB_TICKET_STRIDE], 1);
   __syncthreads();
   if (s_ticket != A.n_fast_levels - 1) return;
   __threadfence();
@@ -433,49 +476,35 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   if (tid == 0) {
     *fr.n_corners = base;
     if (mirror) mirror[0] = make_int4(base, 0, 0, 0);
-    frame_ticket[frame] = 0;
+    tickets[frame * SDVLB_TICKET_STRIDE] = 0;
   }
 
-  // ---- spatial index for the matcher: counting sort of the corner indices by 32-px cell of their level-0 position
+  // ---- spatial index for the matcher: counting sort of the corner indices by 32-px cell of their level-0 position,
+  // counted and scanned in shared memory (the level-0 FAST grid has at most max_cells cells: nleft / nsel are free)
   const int gw = A.g.wcells[0], gcells = gw * A.g.hcells[0];
   int32_t* const start = fr.grid;
   int32_t* const cursor = fr.grid + gcells + 1;
   int32_t* const item = cursor + gcells;
-  for (int i = tid; i < gcells; i += SEL_THREADS) cursor[i] = 0;
+  int* const s_cnt = nleft;    // count, then running cursor
+  __syncthreads();
+  for (int i = tid; i <= gcells; i += SEL_THREADS) s_cnt[i] = 0;
   __syncthreads();
   for (int i = tid; i < base; i += SEL_THREADS) {
     const int4 c = fr.corners[i];
-    atomicAdd(&cursor[((c.y << c.z) >> 5) * gw + ((c.x << c.z) >> 5)], 1);
+    atomicAdd(&s_cnt[((c.y << c.z) >> 5) * gw + ((c.x << c.z) >> 5)], 1);
   }
   __syncthreads();
-  {   // exclusive scan of the counts (block-wide, contiguous chunk per thread)
-    const int per = (gcells + SEL_THREADS - 1) / SEL_THREADS;
-    const int c0 = min(gcells, tid * per), c1 = min(gcells, c0 + per);
-    int local = 0;
-    for (int c = c0; c < c1; c++) local += cursor[c];
-    const int lane = tid & 31, warp = tid >> 5;
-    int incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_tmp[warp] = incl;
-    __syncthreads();
-    int run = incl - local;
-    for (int w = 0; w < warp; w++) run += s_tmp[w];
-    for (int c = c0; c < c1; c++) {
-      const int n = cursor[c];
-      start[c] = run;
-      cursor[c] = run;
-      run += n;
-    }
-    if (tid == SEL_THREADS - 1) start[gcells] = run;
+  block_exclusive_scan(s_cnt, gcells, s_tmp);
+  for (int i = tid; i <= gcells; i += SEL_THREADS) {
+    start[i] = s_cnt[i];
+    if (i < gcells) cursor[i] = s_cnt[i];   // kept for the layout's sake (readers use start[] and item[])
   }
   __syncthreads();
+  // (the order of a cell's items is arbitrary: SearchPoint keeps the minimum of (score, corner index), which is what
+  // the reference's in-order scan yields)
   for (int i = tid; i < base; i += SEL_THREADS) {
     const int4 c = fr.corners[i];
-    item[atomicAdd(&cursor[((c.y << c.z) >> 5) * gw + ((c.x << c.z) >> 5)], 1)] = i;
+    item[atomicAdd(&s_cnt[((c.y << c.z) >> 5) * gw + ((c.x << c.z) >> 5)], 1)] = i;
   }
 }
 
@@ -506,6 +535,11 @@ void sdvlb_fast_plan(const PyrGeom& g, const sdvlb_params& p, int nfeatures, int
     if (nc > plan->max_cells_level) plan->max_cells_level = nc;
   }
   A.level_kp_total = off;
+  int parts = 0;
+  for (int l = 0; l < SDVLB_MAX_LEVELS + 1; l++) {
+    A.part_off[l] = parts;
+    if (l < p.max_fast_levels) parts += (g.wcells[l] * g.hcells[l] + SEL_PART_CELLS - 1) / SEL_PART_CELLS;
+  }
   plan->nfeatures = nfeatures;
 }
 
@@ -519,15 +553,17 @@ cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, u
 }
 
 cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
-                                     uint32_t* level_kp, int32_t* level_cnt, int32_t* frame_ticket,
+                                     int32_t* cell_kept, uint32_t* level_kp, int32_t* level_cnt, int32_t* tickets,
                                      cudaStream_t stream) {
   const FastArgs& A = plan.args;
-  dim3 g2(A.n_fast_levels, B.n);
-  const int pool_keys = 12288;   // 48 KB: 256 cells x 48 keypoints on average after NMS
-  const size_t dyn = size_t(3 * plan.max_cells_level + 4 + pool_keys) * sizeof(int);
-  if (dyn > 160 * 1024) return cudaErrorInvalidValue;
+  dim3 g2(A.part_off[A.n_fast_levels], B.n);
+  // work area: the per-warp cell buffers (keys + positions) or, in the last CTA of a level, the level list + positions
+  const size_t work = std::max(size_t(SEL_THREADS / 32) * SDVLB_CELL_CAP * (sizeof(uint32_t) + 2),
+                               size_t(SEL_SMEM_KEYS) * (sizeof(uint32_t) + 2 * sizeof(uint16_t)));
+  const size_t dyn = size_t(2 * (plan.max_cells_level + 1)) * sizeof(int) + work;
+  if (dyn > 200 * 1024) return cudaErrorInvalidValue;
   SDVLB_PREPARE(fast_select_kernel, dyn);
-  fast_select_kernel<<<g2, SEL_THREADS, dyn, stream>>>(B, A, cell_kp, cell_cnt, level_kp, level_cnt, frame_ticket,
-                                                      pool_keys);
+  fast_select_kernel<<<g2, SEL_THREADS, dyn, stream>>>(B, A, cell_kp, cell_cnt, cell_kept, level_kp, level_cnt, tickets,
+                                                      plan.max_cells_level);
   return cudaGetLastError();
 }
