@@ -359,6 +359,7 @@ def main():
     ap.add_argument("--opencv-sanity", action="store_true", help="print the cv2-vs-restatement timings as JSON and exit")
     ap.add_argument("--sweep", default="", help="comma list of GROUPSxTHREADS to time (e2e only), e.g. 8x4,16x8")
     ap.add_argument("--prefetch", type=int, default=2, help="frame batches are built this many steps ahead")
+    ap.add_argument("--depth", type=int, default=1, help="tracking submissions in flight per group (resident sequences)")
     ap.add_argument("--sweep-cycles", action="store_true", help="print the in-kernel latency breakdown per sweep entry")
     ap.add_argument("--sweep-device", action="store_true", help="sweep with the frames resident in HBM")
     ap.add_argument("--e2e-upload", default="kernel", choices=["dma", "kernel"],
@@ -458,6 +459,8 @@ def main():
                                   device=local_rank, timing=timing, n_threads=min(n_groups, threads),
                                   resident=not args.host_replay)
         trk.set_prefetch(args.prefetch)
+        if not args.host_replay:
+            trk.set_depth(args.depth)
         est = np.zeros((S, F, 7))
         stats = np.zeros((F, S, 8), np.int32)
 
@@ -494,6 +497,7 @@ def main():
         ktimes = trk.timing_read(reset=True) if timing else None
         if not args.host_replay:
             extras["post_cycles_timing" if timing else "post_cycles_run"] = trk.post_cycles(reset=True)
+            extras["slowest_timing" if timing else "slowest_run"] = trk.slowest_cycles(reset=True)
             if timing:
                 extras["post_cycles"] = extras["post_cycles_timing"]
         ngroups = trk.groups()
@@ -600,6 +604,8 @@ def main():
             "us_per_gn_iter": us_per_gn_iter,
             "align_and_feature_align_kernel_us_per_frame": {k: v / (clock_info.get("sm_mhz") or 1965.0) for k, v in
                                                   extras.get("post_cycles", {}).items()},
+            "slowest_sequence_of_a_group_step_us": {k: v / (clock_info.get("sm_mhz") or 1965.0) for k, v in
+                                                    extras.get("slowest_run", {}).items()},
             "gn_iters_per_frame": gn_iters / (S * K),
             "max_ate_mm_vs_gt": ate_mm,
             "matches_per_frame": float(stats_v[1 + W:, :, 1].mean()),

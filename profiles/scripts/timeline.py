@@ -22,7 +22,8 @@ S = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 LOC = int(sys.argv[4]) if len(sys.argv) > 4 else 1   # 1 frames in HBM, 2 pinned host memory (upload kernel), 0 DMA
 cfg = sw.config("C2")
 w, h = cfg["w"], cfg["h"]
-F = 1 + 5 + 8
+NSTEPS = int(sys.argv[5]) if len(sys.argv) > 5 else 8
+F = 1 + 5 + NSTEPS
 host = torch.empty((S, F, h, w), dtype=torch.uint8).pin_memory()
 gt = np.zeros((S, F, 7))
 for s in range(S):

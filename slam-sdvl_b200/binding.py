@@ -257,7 +257,7 @@ _HLIB = None
 HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", "sdvlh_tracker_destroy",
                 "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_phases",
                 "sdvlh_tracker_ctx", "sdvlh_tracker_groups", "sdvlh_tracker_threads", "sdvlh_tracker_run",
-                "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles", "sdvlh_tracker_set_prefetch", "sdvlh_tracker_set_depth",
+                "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles", "sdvlh_tracker_set_prefetch", "sdvlh_tracker_set_depth", "sdvlh_tracker_slowest_cycles",
                 "sdvlh_map_update_candidates", "sdvlh_map_init_candidates", "sdvlh_camera_undistort"]
 
 
@@ -444,6 +444,16 @@ class HostTracker:
         """Average SM cycles per tracked frame in the phases of the device-side FeatureAlign kernel."""
         a = (C.c_double * 13)()
         load_host().sdvlh_tracker_post_cycles(C.c_void_p(self.h), a, int(reset))
+        n = max(1.0, a[8])
+        return {"align_precompute": a[9] / n, "align_residuals": a[10] / n, "align_reduce": a[11] / n,
+                "align_solve": a[12] / n, "cell_ranks": a[0] / n, "select_points": a[1] / n, "ransac_hypotheses": a[2] / n,
+                "startup": a[3] / n, "ransac_replay": a[4] / n, "optimize_pose": a[5] / n, "finish": a[6] / n,
+                "shuffle_warp_done_since_entry": a[7] / n}
+
+    def slowest_cycles(self, reset=True):
+        """The same phases for the slowest sequence of each submission (a step lasts as long as its slowest CTA)."""
+        a = (C.c_double * 13)()
+        load_host().sdvlh_tracker_slowest_cycles(C.c_void_p(self.h), a, int(reset))
         n = max(1.0, a[8])
         return {"align_precompute": a[9] / n, "align_residuals": a[10] / n, "align_reduce": a[11] / n,
                 "align_solve": a[12] / n, "cell_ranks": a[0] / n, "select_points": a[1] / n, "ransac_hypotheses": a[2] / n,

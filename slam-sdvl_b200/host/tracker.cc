@@ -318,6 +318,7 @@ class Group {
       tC = std::chrono::steady_clock::now();
       if (sdvlb_seq_track_collect(ctx_, results_.data()))
         throw std::runtime_error(std::string("sdvl-b200: sdvlb_seq_track_collect failed: ") + sdvlb_last_error());
+      AccumulateSlowest(n);
       for (int i = 0; i < n; i++) {
         if (results_[i].status != SDVLB_SEQ_TRACKED) throw std::runtime_error("sdvl-b200: a sequence was not tracked in a lock-step step");
         FinishTracked(i, built[i], results_[i], gt + 7 * size_t(i), est + 7 * size_t(i), stats + 8 * size_t(i));
@@ -559,6 +560,26 @@ class Group {
     s.frame_counter++;
   }
 
+  // Latency breakdown of the SLOWEST sequence of a submission (the kernels are one CTA per sequence: a step lasts as
+  // long as its slowest CTA), separately for the FeatureAlign and the ImageAlign kernel.
+  void AccumulateSlowest(int n) {
+    int bp = -1, ba = -1;
+    long long tp = -1, ta = -1;
+    for (int j = 0; j < n; j++) {
+      const sdvlb_seq_result& r = results_[j];
+      if (r.status != SDVLB_SEQ_TRACKED) continue;
+      long long p = 0, a = 0;
+      for (int k = 0; k < 7; k++) p += r.phase_cycles[k];
+      for (int k = 0; k < 4; k++) a += r.align_cycles[k];
+      if (p > tp) { tp = p; bp = j; }
+      if (a > ta) { ta = a; ba = j; }
+    }
+    if (bp < 0) return;
+    for (int k = 0; k < 8; k++) slowest_[k] += results_[bp].phase_cycles[k];
+    for (int k = 0; k < 4; k++) slowest_[9 + k] += results_[ba].align_cycles[k];
+    slowest_[8] += 1;
+  }
+
   struct TrackEntry { int seq; int step; };
   void FinishOldest() {
     const auto t0 = std::chrono::steady_clock::now();
@@ -567,6 +588,7 @@ class Group {
     const auto t1 = std::chrono::steady_clock::now();
     const vector<TrackEntry> entries = std::move(subs_.front());
     subs_.pop_front();
+    AccumulateSlowest(int(entries.size()));
     for (size_t j = 0; j < entries.size(); j++) {
       const int i = entries[j].seq, k = entries[j].step;
       ResidentSeq& s = rseqs_[i];
@@ -692,6 +714,7 @@ class Group {
   vector<const uint8_t*> build_imgs_;
   vector<TrackEntry> build_entries_;
  public:
+  double slowest_[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // as post_cycles_ + align_cycles_, [8] = submissions
   double align_cycles_[4] = {0, 0, 0, 0};
   double post_cycles_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // seq_post_kernel phase cycles summed over frames, [8] = frames
  private:
@@ -799,6 +822,11 @@ class BatchTracker {
       for (int i = 0; i < 9; i++) { out[i] += g->post_cycles_[i]; if (reset) g->post_cycles_[i] = 0; }
       for (int i = 0; i < 4; i++) { out[9 + i] += g->align_cycles_[i]; if (reset) g->align_cycles_[i] = 0; }
     }
+  }
+  void SlowestCycles(double out[13], int reset) {
+    for (int i = 0; i < 13; i++) out[i] = 0;
+    for (auto& g : groups_)
+      for (int i = 0; i < 13; i++) { out[i] += g->slowest_[i]; if (reset) g->slowest_[i] = 0; }
   }
   sdvlb_ctx* ctx0() { return groups_[0]->ctx(); }
   int n_seq() const { return n_seq_; }
@@ -1121,6 +1149,12 @@ int sdvlh_tracker_phases(void* t, double out[8], int reset) {
 // out[9..12]: the ImageAlign kernel (PrecomputePatches, residuals, reduction, solve + update).
 int sdvlh_tracker_post_cycles(void* t, double out[13], int reset) {
   static_cast<sdvl::BatchTracker*>(t)->PostCycles(out, reset);
+  return 0;
+}
+
+// The same breakdown for the slowest sequence of every submission (out[8] = number of submissions).
+int sdvlh_tracker_slowest_cycles(void* t, double out[13], int reset) {
+  static_cast<sdvl::BatchTracker*>(t)->SlowestCycles(out, reset);
   return 0;
 }
 
