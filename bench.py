@@ -53,10 +53,29 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_i_ncu_full.txt")   # summary of the committed `ncu --set full` capture
+WORKLOADS = {
+    "C1": "C1: 640x480 TUM-shaped synthetic textured-plane sequences, 4-level pyramid, ~100 features",
+    "C2": "C2: 752x480 EuRoC-shaped synthetic sequences, 5-level pyramid, 200 features",
+    "C3": "C3: 640x480 TUM-shaped synthetic sequences with fast camera motion, 5-level pyramid, 200 features",
+    "C5": "C5: 1920x1080 synthetic sequences, 5-level pyramid, 2000 features per frame",
+}
+
+
+def workload(name):
+    return WORKLOADS[name] + ", pyramid+FAST+ImageAlign+FeatureAlign"
+
+
+def ncu_summary_path():
+    """The newest committed `ncu --set full` summary (profiles/rNN_*_ncu_full.txt)."""
+    d = os.path.join(ROOT, "profiles")
+    c = sorted(f for f in os.listdir(d) if f.endswith("_ncu_full.txt") and "seed" not in f) if os.path.isdir(d) else []
+    return os.path.join(d, c[-1]) if c else os.path.join(d, "missing")
+
+
+NCU_SUMMARY = ncu_summary_path()
 NCU_KERNELS = {"pyr_down_kernel": "pyramid", "pyr_tail_kernel": "pyramid", "fast_cells_kernel": "fast",
-               "fast_select_kernel": "select", "image_align_kernel": "align", "search_seq_kernel": "search",
-               "seq_prep_kernel": "prep", "seq_post_kernel": "pose"}
+               "fast_select_kernel": "select", "seq_align_kernel": "align", "image_align_kernel": "align",
+               "search_seq_kernel": "search", "seq_post_kernel": "pose"}
 NCU_SEQS_PER_LAUNCH = 64
 
 
@@ -332,8 +351,7 @@ def run_reference(args, cfg, sw, rank, world):
         "impl": "reference", "metric": "tracked_frames_per_sec", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-        "config": {"workload": "C2: 752x480 EuRoC-shaped synthetic sequences, 5-level pyramid, 200 features, "
-                               "pyramid+FAST+ImageAlign+FeatureAlign", "sequences": T, "processes": T,
+        "config": {"workload": workload(args.config), "sequences": T, "processes": T,
                    "step": "one frame for each of the sequences (one per host core)"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": T, "kind": kind,
                          "sample": f"{T} sequences x {K} frames, one sequence per core; {what}",
@@ -351,7 +369,11 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU")
+    ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU (weak scaling) / in total (strong scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --seqs sequences per GPU; strong: --seqs sequences in total, split over the ranks "
+                         "(BASELINE.json configs[3] as written: 64 sequences over 1/2/4/8 GPUs)")
+    ap.add_argument("--repeats", type=int, default=5, help="timed blocks per leg; the median is reported")
     ap.add_argument("--groups", type=int, default=0, help="contexts (stream pairs) per GPU (0 = 2 per host thread)")
     ap.add_argument("--threads", type=int, default=0, help="host threads per GPU (0 = cores / ranks)")
     ap.add_argument("--kf-every", type=int, default=20)
@@ -367,6 +389,7 @@ def main():
                          "one-kernel upload reading pinned host memory")
     ap.add_argument("--host-replay", action="store_true",
                     help="previous design: FeatureAlign bookkeeping + pose refinement on the host (for comparison)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the pageable / single-sequence / CPU legs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -399,7 +422,16 @@ def main():
     binding.load()
     binding.load_host()
 
-    S, W, K = args.seqs, args.warmup, args.steps
+    # sequences of this rank: a fixed number per GPU (weak) or an equal share of a fixed total (strong)
+    if args.scaling == "strong":
+        S = (args.seqs + world - 1 - rank) // world
+        S_total = args.seqs
+        first_seq = sum((args.seqs + world - 1 - r) // world for r in range(rank))
+    else:
+        S, S_total, first_seq = args.seqs, args.seqs * world, rank * args.seqs
+    if S <= 0:
+        raise SystemExit("bench.py: fewer sequences than ranks")
+    W, K, R = args.warmup, args.steps, max(1, args.repeats)
     F = 1 + W + K                       # frame 0 initialises every sequence (ground-truth pose + map seeding)
     w, h = cfg["w"], cfg["h"]
     ncpu = os.cpu_count() or 1
@@ -409,18 +441,16 @@ def main():
     if args.host_replay:     # the host replays FeatureAlign: every core is needed
         threads = args.threads or max(1, min(S, cores))
         groups = args.groups or max(1, min(S, 2 * threads))
-    else:                    # resident sequences: the host only submits; 3 threads keep 6 groups in flight (measured on
-        # B200: 6x3 173 k frames/s, 8x4 172 k, 4x2 164 k; on the 8-GPU box, 4 cores per rank: 6x3 1.28 M, 8x3 1.14 M)
-        threads = args.threads or max(1, min(3, cores))
+    else:                    # resident sequences: the host only submits and plays the mapping thread
+        threads = args.threads or max(1, min(6, cores))
         groups = args.groups or max(1, min(S, 6))
 
     # ---- synthetic frames, rendered once into pinned host memory
     host = torch.empty((S, F, h, w), dtype=torch.uint8).pin_memory()
     host_np = host.numpy()
     gt = np.zeros((S, F, 7))
-    seeds = sharding.shard_seeds(rank, world, S)
     for s in range(S):
-        gt[s] = sw.trajectory(cfg, seeds[s], F)
+        gt[s] = sw.trajectory(cfg, first_seq + s, F)
         sw.render(cfg, gt[s], threads=max(1, ncpu // max(1, world)), out=host_np[s])
     frame_bytes = w * h
 
@@ -451,29 +481,32 @@ def main():
 
     pcie_gbs = pcie_h2d_gbs()
 
-    def timed_run(base_ptr, on_device, n_groups, timing=False, pipelined=True):
+    def timed_run(base_ptr, on_device, n_groups, timing=False, pipelined=True, seqs=None, n_threads=None):
         """Fresh tracker; init + warm-up untimed; K timed steps. Returns seconds (max over ranks), est, stats, extras.
-        pipelined: sdvlh_tracker_run (frame batches one step ahead, groups free-running); otherwise every step is one
-        synchronous lock-step submission (used for the per-kernel timing pass, where launches must not overlap)."""
-        trk = binding.HostTracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], args.kf_every, S, n_groups,
-                                  device=local_rank, timing=timing, n_threads=min(n_groups, threads),
+        pipelined: sdvlh_tracker_run (frame batches ahead of the tracking they feed, groups free-running); otherwise
+        every step is one synchronous lock-step submission (used for the per-kernel timing pass, where launches must
+        not overlap).  seqs: only the first `seqs` sequences (single-sequence latency leg)."""
+        n = S if seqs is None else seqs
+        n_groups = min(n_groups, n)
+        trk = binding.HostTracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], args.kf_every, n, n_groups,
+                                  device=local_rank, timing=timing, n_threads=min(n_groups, n_threads or threads),
                                   resident=not args.host_replay)
         trk.set_prefetch(args.prefetch)
         if not args.host_replay:
             trk.set_depth(args.depth)
-        est = np.zeros((S, F, 7))
-        stats = np.zeros((F, S, 8), np.int32)
+        est = np.zeros((n, F, 7))
+        stats = np.zeros((F, n, 8), np.int32)
 
-        ptr_tab = (base_ptr + (np.arange(S, dtype=np.uint64)[:, None] * F + np.arange(F, dtype=np.uint64)[None, :])
+        ptr_tab = (base_ptr + (np.arange(n, dtype=np.uint64)[:, None] * F + np.arange(F, dtype=np.uint64)[None, :])
                    * np.uint64(frame_bytes))
         def go(k0, k1):
             if pipelined:
-                e, st = trk.run_ptrs(ptr_tab[:, k0:k1], gt[:, k0:k1], on_device=on_device)
+                e, st = trk.run_ptrs(ptr_tab[:, k0:k1], gt[:n, k0:k1], on_device=on_device)
                 est[:, k0:k1] = e
                 stats[k0:k1] = st.transpose(1, 0, 2)
             else:
                 for k in range(k0, k1):
-                    e, st = trk.step_ptrs([int(p) for p in ptr_tab[:, k]], gt[:, k], on_device=on_device)
+                    e, st = trk.step_ptrs([int(p) for p in ptr_tab[:, k]], gt[:n, k], on_device=on_device)
                     est[:, k] = e
                     stats[k] = st
 
@@ -504,6 +537,15 @@ def main():
         trk.close()
         return sec, wall, est, stats, counters, ktimes, ngroups
 
+    def repeated(base_ptr, on_device, n_groups, **kw):
+        """R timed blocks, each a fresh tracker over the same frames (init + warm-up untimed).  Returns the block with
+        the median time, plus every block's seconds."""
+        runs = [timed_run(base_ptr, on_device, n_groups, **kw) for _ in range(R)]
+        for r in runs[1:]:
+            assert np.array_equal(r[2], runs[0][2]), "repeated blocks must be the same computation"
+        order = sorted(range(R), key=lambda i: runs[i][0])
+        return runs[order[R // 2]], [r[0] for r in runs]
+
     e2e_loc = IMG_HOST if args.e2e_upload == "dma" else IMG_PINNED
     if args.sweep:   # host-side configuration sweep (groups x threads), e2e placement; prints a table and exits
         for spec in args.sweep.split(","):
@@ -515,7 +557,7 @@ def main():
                 sec, wall, *_ = timed_run(extras["dev"].data_ptr(), IMG_DEVICE, g_)
             else:
                 sec, wall, *_ = timed_run(host.data_ptr(), e2e_loc, g_)
-            print(f"sweep groups={g_:3d} threads={t_:3d}: {S * K * world / sec:10.0f} frames/s  ({sec / K * 1e3:.3f} ms/step)",
+            print(f"sweep groups={g_:3d} threads={t_:3d}: {S_total * K / sec:10.0f} frames/s  ({sec / K * 1e3:.3f} ms/step)",
                   file=sys.stderr, flush=True)
             if args.sweep_cycles:
                 print("   in-kernel us/frame:", {k: round(v / 1965.0, 1) for k, v in extras["post_cycles_run"].items()},
@@ -525,47 +567,81 @@ def main():
     clocks = ClockSampler(local_rank if rank == 0 else None)   # rank 0 samples its GPU; 8 samplers only add noise
     clocks.start()
     # ---- e2e: frames in pinned host memory
-    e2e_sec, e2e_wall, est_e, stats_e, cnt_e, _, ngroups = timed_run(host.data_ptr(), e2e_loc, groups)
+    (e2e_sec, e2e_wall, est_e, stats_e, cnt_e, _, ngroups), e2e_all = repeated(host.data_ptr(), e2e_loc, groups)
     # ---- value: frames resident in HBM
     dev = host.cuda(non_blocking=False)
-    val_sec, val_wall, est_v, stats_v, cnt_v, _, _ = timed_run(dev.data_ptr(), IMG_DEVICE, groups)
+    (val_sec, val_wall, est_v, stats_v, cnt_v, _, _), val_all = repeated(dev.data_ptr(), IMG_DEVICE, groups)
     clock_info = clocks.stop()
     # ---- kernel pass: one context so launches do not overlap, per-kernel CUDA events on the launching stream
     k_sec, _, est_k, stats_k, _, ktimes, _ = timed_run(dev.data_ptr(), IMG_DEVICE, 1, timing=True, pipelined=False)
     assert np.array_equal(est_k, est_v), "pipelined and lock-step runs must be the same computation"
-
     assert np.array_equal(est_e, est_v), "host-resident and HBM-resident runs must be the same computation"
-    total_frames = S * K * world
+    total_frames = S_total * K
     value = total_frames / val_sec
     e2e = total_frames / e2e_sec
     ate_mm = max(sw.ate(est_v[s, 1 + W:], gt[s, 1 + W:]) for s in range(S)) * 1e3
     gn_iters = int(stats_k[1 + W:, :, 6].sum())
 
-    # ---- roofline of the dominant kernel
+    # ---- further legs (N = 1 and weak scaling only: they describe one GPU)
+    e2e_pageable = None
+    latency = None
+    if not args.no_extras and world == 1:
+        # the reference hands cv::Mat (pageable memory) to HandleFrame: the same e2e leg from pageable host memory,
+        # one cudaMemcpyAsync per frame (SDVLB_IMG_HOST)
+        pageable = np.array(host_np, copy=True)
+        p_sec, _, est_p, _, cnt_p, _, _ = timed_run(pageable.ctypes.data, IMG_HOST, groups)
+        assert np.array_equal(est_p, est_v), "pageable and pinned inputs must be the same computation"
+        e2e_pageable = {"value": total_frames / p_sec, "unit": "frames/s", "ms_per_step": p_sec / K * 1e3,
+                        "h2d_bytes_per_step": cnt_p[1] / K,
+                        "source": "pageable host memory (numpy), one cudaMemcpyAsync per frame inside sdvlb_frames_submit"}
+        del pageable
+        # the reference's real deployment is ONE camera (main.cc:126-159): latency of a single sequence through the same
+        # API (frames in pinned host memory, one group, results read back), and with the frames already in HBM
+        l_sec, *_ = timed_run(host.data_ptr(), e2e_loc, 1, seqs=1, n_threads=1)
+        ld_sec, *_ = timed_run(dev.data_ptr(), IMG_DEVICE, 1, seqs=1, n_threads=1)
+        latency = {"sequences": 1, "ms_per_frame_e2e": l_sec / K * 1e3, "ms_per_frame_hbm": ld_sec / K * 1e3,
+                   "frames_per_s_e2e": K / l_sec, "note": "one camera, frames pipelined one step ahead of the tracking"}
+
+    # ---- roofline: every kernel of the kernel pass against the measured HBM peak, the dominant one first
     peak, peak_kind = measured_peaks()
-    kshare = {k: v[0] for k, v in ktimes.items()}
+    kshare = {k: v[0] for k, v in ktimes.items() if v[1] > 0}
     tot_ms = sum(kshare.values())
     dom = max(kshare, key=kshare.get)
-    alg = 0
-    for k in range(1 + W, F):
-        alg += algorithmic_bytes(cfg, dom, stats_k[k - 1], stats_k[k])
-    n_launch = max(1, ktimes[dom][1])
-    avg_ms = ktimes[dom][0] / n_launch
-    achieved = (alg / n_launch) / (avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic_per_launch(dom, S),
-                "traffic_source": "profiles/r01_i_ncu_full.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+    per_kernel = {}
+    for name in kshare:
+        alg = 0
+        for k in range(1 + W, F):
+            alg += algorithmic_bytes(cfg, name, stats_k[k - 1], stats_k[k])
+        n_launch = max(1, ktimes[name][1])
+        avg_ms = ktimes[name][0] / n_launch
+        per_kernel[name] = {"us_per_launch": avg_ms * 1e3, "algorithmic_bytes_per_launch": alg / n_launch,
+                            "gbs": (alg / n_launch) / (avg_ms * 1e-3) / 1e9,
+                            "frac": (alg / n_launch) / (avg_ms * 1e-3) / 1e9 / peak,
+                            "launches_per_step": ktimes[name][1] / K,
+                            "traffic": ncu_traffic_per_launch(name, S)}
+    alg_all = sum(v["algorithmic_bytes_per_launch"] * v["launches_per_step"] for v in per_kernel.values())
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": per_kernel[dom]["frac"], "traffic": per_kernel[dom]["traffic"],
+                "traffic_source": os.path.relpath(NCU_SUMMARY, ROOT) + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
                 "peak_source": peak_kind,
-                "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes_per_launch": alg / n_launch,
+                "avg_launch_us": per_kernel[dom]["us_per_launch"],
+                "algorithmic_bytes_per_launch": per_kernel[dom]["algorithmic_bytes_per_launch"],
                 "kernel_ms_share": {k: (v / tot_ms if tot_ms else 0.0) for k, v in kshare.items()},
-                "kernel_us_per_step": {k: v[0] * 1e3 / K for k, v in ktimes.items()}}
+                "kernel_us_per_step": {k: v[0] * 1e3 / K for k, v in ktimes.items() if v[1] > 0},
+                "per_kernel": per_kernel,
+                "whole_step": {"algorithmic_bytes": alg_all, "gbs_at_value": alg_all / (val_sec / K) / 1e9,
+                               "frac_at_value": alg_all / (val_sec / K) / 1e9 / peak},
+                "pcie": {"h2d_gbs_per_gpu_achieved": cnt_e[1] / e2e_sec / 1e9, "h2d_gbs_per_gpu_peak": pcie_gbs,
+                         "frac": cnt_e[1] / e2e_sec / 1e9 / pcie_gbs,
+                         "peak_source": "pinned cudaMemcpyAsync 4 x 256 MB, all ranks at once, slowest rank",
+                         "frames_per_s_at_peak": pcie_gbs * 1e9 / frame_bytes * world}}
     us_per_gn_iter = ktimes["align"][0] * 1e3 / max(1, gn_iters) * S   # one CTA per sequence runs its own GN loop
 
     # ---- CPU baseline on one host core (rank 0, bounded sample)
     cpu_baseline = None
-    if rank == 0 and world == 1:   # N = 1 only: at N > 1 the host cores belong to the ranks' submission threads
+    if rank == 0 and world == 1 and not args.no_extras:   # N = 1 only: at N > 1 the host cores belong to the ranks
         O, cpu_kind, cpu_what = cpu_impl()
-        ns = min(S, 32)    # bounded sample: 32 sequences x (steps + warmup) frames, about 5-10 s of CPU work
+        ns = min(S, 32 if w * h < 1000000 else 4)    # bounded sample, about 5-20 s of CPU work
         t_cpu, frames_cpu, gn_cpu = 0.0, 0, 0
         for s in range(ns):
             tr = O.Tracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], args.kf_every)
@@ -577,26 +653,37 @@ def main():
             tr.close()
         cpu_baseline = {"value": frames_cpu / t_cpu, "unit": "frames/s", "cores": 1, "kind": cpu_kind,
                         "sample": f"{ns} sequences x {F - 1} frames of the same workload, 1 thread; {cpu_what}",
+                        "ms_per_frame": t_cpu / frames_cpu * 1e3,
                         "host_cores_available": ncpu, "opencv_sanity": opencv_sanity_subprocess(args.config)}
+        if latency is not None:
+            latency["ms_per_frame_cpu_reference_1_thread"] = t_cpu / frames_cpu * 1e3
+
+    def spread(all_sec):
+        v = sorted(total_frames / x for x in all_sec)
+        return {"median": v[len(v) // 2], "min": v[0], "max": v[-1], "runs": len(v)}
 
     if rank == 0:
         out = {
             "metric": "tracked_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": val_sec / K * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": val_sec / K * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-            "config": {"workload": "C2: 752x480 EuRoC-shaped synthetic sequences, 5-level pyramid, 200 features, "
-                                   "pyramid+FAST+ImageAlign+FeatureAlign", "sequences_per_gpu": S,
-                       "step": "one new frame for every sequence of the GPU", "host_groups_per_gpu": ngroups, "host_threads_per_gpu": min(ngroups, threads),
-                       "cache": "every step consumes frames never seen before (inputs 0.36 MB x sequences per step, "
-                                f"{S * F * frame_bytes / 1e6:.0f} MB total, larger than L2); no L2 flush needed",
+            "value_runs": spread(val_all),
+            "config": {"workload": workload(args.config), "sequences_per_gpu": S, "sequences_total": S_total,
+                       "step": "one new frame for every sequence of the GPU", "host_groups_per_gpu": ngroups,
+                       "host_threads_per_gpu": min(ngroups, threads), "submissions_in_flight_per_group": args.depth,
+                       "timed_blocks": f"{R} blocks of {K} steps per leg, each a fresh tracker (init + {W} warm-up "
+                                       "steps untimed); value / e2e are the median block",
+                       "cache": "every step consumes frames never seen before (inputs "
+                                f"{frame_bytes / 1e6:.2f} MB x sequences per step, "
+                                f"{S * F * frame_bytes / 1e6:.0f} MB per block, larger than L2); no L2 flush needed",
                        "kf_every": args.kf_every, "numa": numa,
                        "sequence_state": "host replay" if args.host_replay else "resident in HBM (sdvlb_seq_*)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": cnt_e[1] / K, "d2h_bytes_per_step": cnt_e[2] / K,
-                    "ms_per_step": e2e_sec / K * 1e3,
-                    "pcie": {"h2d_gbs_per_gpu_achieved": cnt_e[1] / e2e_sec / 1e9,
-                             "h2d_gbs_per_gpu_peak": pcie_gbs, "frac": cnt_e[1] / e2e_sec / 1e9 / pcie_gbs,
-                             "peak_source": "pinned cudaMemcpyAsync 4 x 256 MB, all ranks at once, slowest rank",
-                             "frames_per_s_at_peak": pcie_gbs * 1e9 / frame_bytes * world}},
+                    "ms_per_step": e2e_sec / K * 1e3, "runs": spread(e2e_all),
+                    "source": "pinned host memory, read over PCIe by the upload kernel",
+                    "pcie": roofline["pcie"]},
+            "e2e_pageable": e2e_pageable,
+            "latency_single_sequence": latency,
             "gpu_launches": cnt_v[0],
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
@@ -609,6 +696,7 @@ def main():
             "gn_iters_per_frame": gn_iters / (S * K),
             "max_ate_mm_vs_gt": ate_mm,
             "matches_per_frame": float(stats_v[1 + W:, :, 1].mean()),
+            "keyframes_per_frame": float(stats_v[1 + W:, :, 7].mean()),
             "wall_check_s": {"value": val_wall, "e2e": e2e_wall},
             "host_phase_thread_seconds": {"value": cnt_v[3], "e2e": cnt_e[3]},
         }

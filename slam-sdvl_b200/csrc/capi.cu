@@ -597,6 +597,13 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
     for (int i = 0; i < n; i++) { fr[i] = jobs[i].cur; img[i] = jobs[i].image; loc[i] = jobs[i].image_on_device; }
     rc = enqueue_build(c, fr.data(), img.data(), loc.data(), n, n_detect > 0, nfeatures, mirror != 0, c->stream);
     if (rc) return rc;
+    // the FAST scratch is shared with the build stream: a frame batch submitted later must not start before this one
+    // has read its cell lists
+    if (n_detect > 0) {
+      if (!c->track_build_done) SDVLB_CUDA_TRY(cudaEventCreateWithFlags(&c->track_build_done, cudaEventDisableTiming));
+      SDVLB_CUDA_TRY(cudaEventRecord(c->track_build_done, c->stream));
+      c->track_build_pending = true;
+    }
   }
   if (n_align > 0) {
     timer_begin(c, SDVLB_K_ALIGN);
@@ -787,6 +794,7 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   cudaFree(c->cell_kp); cudaFree(c->cell_cnt); cudaFree(c->cell_kept); cudaFree(c->level_kp); cudaFree(c->level_cnt);
   cudaFree(c->frame_ticket); cudaFree(c->scratch);
   if (c->h_overflow) cudaFreeHost(c->h_overflow);
+  if (c->track_build_done) cudaEventDestroy(c->track_build_done);
   while (!c->seqs.empty()) sdvlb_seq_destroy(c, c->seqs.back());
   for (Arena& a : c->seq_in) {
     if (a.h) cudaFreeHost(a.h);
@@ -905,6 +913,10 @@ int sdvlb_frames_submit(sdvlb_ctx* c, const uint8_t* const* images, int n, int i
     rc = frame_alloc(c, &f);
     if (rc) { for (int k = 0; k < i; k++) frame_release(c, out[k]); return rc; }
     out[i] = f;
+  }
+  if (c->track_build_pending) {   // a tracking batch that built its own frames used the FAST scratch on the other stream
+    SDVLB_CUDA_TRY(cudaStreamWaitEvent(c->bstream, c->track_build_done, 0));
+    c->track_build_pending = false;
   }
   std::vector<int32_t> loc(n, images_on_device);
   rc = enqueue_build(c, out, images, loc.data(), n, want_corners != 0, nfeatures, true, c->bstream,

@@ -112,6 +112,8 @@ struct sdvlb_ctx {
   cudaEvent_t uevents[kBuildEvents] = {};
   int uevent_next = 0;
   cudaEvent_t last_build = nullptr; // event of the most recent asynchronous build (null: none yet)
+  cudaEvent_t track_build_done = nullptr;   // recorded after a tracking batch built its own frames (shared FAST scratch)
+  bool track_build_pending = false;
   int32_t* h_overflow = nullptr;    // pinned, device-visible: [0] overflow flag written by the selector,
                                     // [16] sequence number of the last finished tracking submission (signal kernel)
   uint32_t track_seq = 0;
