@@ -81,7 +81,32 @@ class SeedParams(C.Structure):
                 ("min_kf_id", C.c_int32), ("mode", C.c_int32)]
 
 
+# resident sequences (sdvlb_seq_*)
+SEQ_KF_CAP, SEQ_DEPTH = 64, 4
+SEQ_POINT_DT = np.dtype([("pos", "f8", 3), ("ref_px", "f8", 2), ("cur_px", "f8", 2), ("idepth", "f8"), ("idepth_std", "f8"),
+                         ("user_id", "i8"), ("ref_level", "i4"), ("cur_level", "i4"), ("flags", "i4"),
+                         ("n_successful", "i4"), ("n_failed", "i4"), ("pad_", "i4")])
+SEQ_FEAT_DT = np.dtype([("px", "f8", 2), ("user_id", "i8"), ("level", "i4"), ("flags", "i4")])
+SEQ_TRACKED, SEQ_HELD, SEQ_IDLE = 0, 1, 2
+TRACKING_GOOD, TRACKING_INSUFFICIENT, TRACKING_BAD = 0, 1, 2
+FEAT_HAS_POINT = 1
+
+
+class SeqPolicy(C.Structure):
+    _fields_ = [("keyframe_rule", C.c_int32), ("min_keyframe_its", C.c_int32), ("lost_ratio", C.c_double),
+                ("tracking_quality", C.c_int32), ("pad_", C.c_int32)]
+
+
+class SeqResult(C.Structure):
+    _fields_ = [("pose", C.c_double * 7), ("n_tracked", C.c_int32), ("matches", C.c_int32), ("attempts", C.c_int32),
+                ("inliers", C.c_int32), ("outliers", C.c_int32), ("n_points", C.c_int32), ("gn_iters", C.c_int32),
+                ("n_feats", C.c_int32), ("feats", C.c_void_p), ("status", C.c_int32), ("quality", C.c_int32),
+                ("need_keyframe", C.c_int32), ("lost_frames", C.c_int32), ("kf_live", C.c_int32 * SEQ_KF_CAP),
+                ("phase_cycles", C.c_int32 * 8), ("align_cycles", C.c_int32 * 4)]
+
+
 assert SEED_DT.itemsize == 232   # sizeof(sdvlb_seed)
+assert SEQ_POINT_DT.itemsize == 104 and SEQ_FEAT_DT.itemsize == 32
 assert ALIGN_FEAT_DT.itemsize == C.sizeof(AlignFeat)
 assert GN_ITER_DT.itemsize == C.sizeof(GnIter)
 assert CANDIDATE_DT.itemsize == C.sizeof(Candidate)

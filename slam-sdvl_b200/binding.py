@@ -119,6 +119,43 @@ class Frame:
             self.h = None
 
 
+class Sequence:
+    """A resident sequence (sdvlb_seq_*): the tracked state lives on the device."""
+
+    def __init__(self, ctx, max_feats=0):
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(load().sdvlb_seq_create(C.c_void_p(ctx.h), int(max_feats), C.byref(h)))
+        self.h = h.value
+
+    def reset(self, frame, T):
+        T = np.ascontiguousarray(T, np.float64)
+        _check(load().sdvlb_seq_reset(C.c_void_p(self.ctx.h), C.c_void_p(self.h), C.c_void_p(frame.h), ptr(T)))
+
+    def add_points(self, kf_frame, T_kf, pts):
+        """pts: array of abi.SEQ_POINT_DT.  Returns the keyframe slot."""
+        from .abi import SEQ_POINT_DT
+        pts = np.ascontiguousarray(pts, SEQ_POINT_DT)
+        T_kf = np.ascontiguousarray(T_kf, np.float64)
+        slot = C.c_int(-1)
+        _check(load().sdvlb_seq_add_points(C.c_void_p(self.ctx.h), C.c_void_p(self.h), C.c_void_p(kf_frame.h), ptr(T_kf),
+                                           ptr(pts) if len(pts) else None, len(pts), C.byref(slot)))
+        return slot.value
+
+    def set_policy(self, keyframe_rule=0, min_keyframe_its=0, lost_ratio=0.7, tracking_quality=0):
+        from .abi import SeqPolicy
+        pol = SeqPolicy(int(keyframe_rule), int(min_keyframe_its), float(lost_ratio), int(tracking_quality), 0)
+        _check(load().sdvlb_seq_set_policy(C.c_void_p(self.ctx.h), C.c_void_p(self.h), C.byref(pol)))
+
+    def release(self):
+        _check(load().sdvlb_seq_release(C.c_void_p(self.ctx.h), C.c_void_p(self.h)))
+
+    def destroy(self):
+        if self.h:
+            load().sdvlb_seq_destroy(C.c_void_p(self.ctx.h), C.c_void_p(self.h))
+            self.h = None
+
+
 class Context:
     def __init__(self, params, cam, device=0):
         self.params, self.cam = params, cam
@@ -134,6 +171,40 @@ class Context:
 
     def stream(self):
         return load().sdvlb_ctx_stream(C.c_void_p(self.h))
+
+    # ---- resident sequences
+    def seq_submit(self, seqs, frames):
+        n = len(seqs)
+        sa = (C.c_void_p * n)(*[s.h for s in seqs])
+        fa = (C.c_void_p * n)(*[f.h for f in frames])
+        self._seq_n = getattr(self, "_seq_n", []) + [n]
+        rc = load().sdvlb_seq_track_submit(C.c_void_p(self.h), sa, fa, n)
+        if rc:
+            self._seq_n.pop()
+        _check(rc)
+
+    def seq_inflight(self):
+        return load().sdvlb_seq_track_inflight(C.c_void_p(self.h))
+
+    def seq_collect(self):
+        """Results of the oldest submission in flight: a list of dicts (the feature list copied out of pinned memory)."""
+        from .abi import SeqResult, SEQ_FEAT_DT
+        n = self._seq_n.pop(0)
+        res = (SeqResult * n)()
+        _check(load().sdvlb_seq_track_collect(C.c_void_p(self.h), res))
+        out = []
+        for r in res:
+            d = {k: getattr(r, k) for k in ("n_tracked", "matches", "attempts", "inliers", "outliers", "n_points", "gn_iters",
+                                            "n_feats", "status", "quality", "need_keyframe", "lost_frames")}
+            d["pose"] = np.array(r.pose)
+            d["kf_live"] = np.array(r.kf_live)
+            if r.status == 0 and r.n_feats > 0:
+                buf = (C.c_uint8 * (r.n_feats * SEQ_FEAT_DT.itemsize)).from_address(r.feats)
+                d["feats"] = np.frombuffer(buf, SEQ_FEAT_DT).copy()
+            else:
+                d["feats"] = np.zeros(0, SEQ_FEAT_DT)
+            out.append(d)
+        return out
 
     def sync(self):
         _check(load().sdvlb_ctx_sync(C.c_void_p(self.h)))

@@ -101,11 +101,13 @@ def test_pose_refine_degenerate_inputs(binding, abi, sw, O):
     ctx.close()
 
 
-def _run_tracker(binding, sw, cfg, seqs, resident, classic=False, n_groups=1, kf_every=20, pipelined=False):
+def _run_tracker(binding, sw, cfg, seqs, resident, classic=False, n_groups=1, kf_every=20, pipelined=False, depth=None):
     n_seq = len(seqs)
     n = seqs[0][1].shape[0]
     t = binding.HostTracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], kf_every, n_seq, n_groups,
                             resident=resident)
+    if depth is not None:
+        t.set_depth(depth)
     if pipelined:
         imgs = np.stack([s[1] for s in seqs])
         gt = np.stack([s[0] for s in seqs])
@@ -157,16 +159,20 @@ def test_resident_sequences_vs_classic_and_oracle(binding, sw, O, name, n_frames
         assert st_r[i][1:, 1].mean() > 0.4 * cfg["n_feat"]
 
 
-@pytest.mark.parametrize("n_groups", [1, 3])
-def test_resident_pipelined_equals_lockstep(binding, sw, n_groups):
-    """Free-running groups with frame batches one step ahead == stepping all sequences synchronously (bit-exact)."""
+@pytest.mark.parametrize("n_groups,depth", [(1, 1), (3, 1), (1, 2), (3, 2), (2, 4)])
+def test_resident_pipelined_equals_lockstep(binding, sw, n_groups, depth):
+    """Free-running groups with frame batches ahead of the tracking and `depth` tracking submissions queued behind each
+    other == stepping all sequences synchronously (bit-exact).  With depth > 1 a frame is submitted before the result
+    of the previous one is known: when that result asks for a keyframe (every 2-3 frames in this scene) the queued step
+    comes back HELD and the frame is submitted again after the new points."""
     cfg = sw.config("C2")
     seqs = []
     for seed in range(5):
         poses = sw.trajectory(cfg, 20 + seed, 14)
         seqs.append((poses, sw.render(cfg, poses)))
     est_s, st_s = _run_tracker(binding, sw, cfg, seqs, resident=True, n_groups=2)
-    est_p, st_p = _run_tracker(binding, sw, cfg, seqs, resident=True, n_groups=n_groups, pipelined=True)
+    est_p, st_p = _run_tracker(binding, sw, cfg, seqs, resident=True, n_groups=n_groups, pipelined=True, depth=depth)
+    assert st_s[:, :, 7].sum() >= 5, "the scene is expected to need keyframes"
     assert np.array_equal(est_s, est_p)
     assert np.array_equal(st_s, st_p)
 
