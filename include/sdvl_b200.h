@@ -133,10 +133,29 @@ int sdvlb_undistort(sdvlb_ctx* ctx, const uint8_t* in, uint8_t* out);
 
 /* ---- ORB descriptor mode ----------------------------------------------------------
  * Config::UseORB() (config.h:139, `SDVL.use_orb`), orb_size 31 (the size the learned pattern exists for).
- * sdvlb_ctx_set_orb(ctx, 1) switches the context to the reference's ORB mode: FAST cells and Frame::FilterCorners use the
- * border margin 4 + orb_size/2 = 19 (extra/fast_detector.cc:63-64,183-184) for every frame built from then on; call it
- * before creating frames.  It synchronises the context. */
+ * sdvlb_ctx_set_orb(ctx, 1) switches the context to the reference's ORB mode, end to end:
+ *   - FAST cells and Frame::FilterCorners use the border margin 4 + orb_size/2 = 19
+ *     (extra/fast_detector.cc:63-64,183-184) for every frame built from then on;
+ *   - every frame built with corners also gets Frame::descriptors_ -- the reference fills them lazily
+ *     (matcher.cc:265-269, frame.cc:148-161), here one kernel per frame batch computes all of them when the frame is
+ *     built (sdvlb_frame_descriptors reads them);
+ *   - Matcher::SearchPoint scores corners by ORBDetector::Distance against the descriptor of the point's init feature
+ *     (matcher.cc:243-277): sdvlb_search_points_orb / sdvlb_track_job.cand_desc for the class API and the batched
+ *     tracker, and inside the resident-sequence chain (sdvlb_seq_*), where the descriptor of every map point's init
+ *     feature is computed on the device from its keyframe when the point is handed over (sdvlb_seq_add_points) and
+ *     travels with the point from frame to frame;
+ *   - sdvlb_update_candidates (Map::UpdateCandidates / InitCandidates) scores by descriptor distance too; the
+ *     descriptor of a candidate's init feature is recomputed from its keyframe (ref_frame, ref_px, ref_level).
+ * A feature's descriptor is ORBDetector::GetDescriptor(keyframe pyramid[level], int(position / 2^level)) wherever the
+ * reference creates one (frame.cc:159 + map.cc:322; homography_init.cc:141-149), so it is a function of the keyframe
+ * and the feature; a feature outside ORBDetector::IsInsideLimits keeps the zero descriptor of the Feature constructor.
+ * Call it before creating frames (frame slots allocated outside ORB mode have no room for descriptors: switching it on
+ * regrows the pool, which fails with SDVLB_ERR_STATE while frames are alive) and before sdvlb_seq_create.  It
+ * synchronises the context. */
 int sdvlb_ctx_set_orb(sdvlb_ctx* ctx, int on);
+/* Frame::GetDescriptors(): 32 bytes per corner in Frame::GetCorners() order, at most cap corners; *n = corners the frame
+ * has.  The frame must have been built with corners in ORB mode. */
+int sdvlb_frame_descriptors(sdvlb_ctx* ctx, const sdvlb_frame* f, uint8_t* desc, int cap, int* n);
 /* ORBDetector::GetDescriptor / GetOrientation (extra/orb_detector.cc:350-437) at n positions xyl = n x (x, y, level),
  * level coordinates, of frame f: what Frame::FilterCorners stores in Frame::descriptors_ for the filtered corners
  * (frame.cc:148-161), Map::InitCandidates copies into Feature::descriptor_ (map.cc:319-323) and Matcher::SearchFeatures
@@ -281,6 +300,8 @@ typedef struct sdvlb_track_job {
   double T_ref[7];
   double T_cur[7];          /* in: prior, out: ImageAlign result */
   double error;             /* out */
+  const uint8_t* cand_desc; /* Config::UseORB() (sdvlb_ctx_set_orb): n_cands x 32 bytes, feature->GetDescriptor() of
+                               every candidate's init feature (matcher.cc:109); NULL outside ORB mode */
 } sdvlb_track_job;
 
 /* For every job: upload image, pyramid, FAST, ImageAlign(ref,cur), then
@@ -430,7 +451,8 @@ int sdvlb_seq_destroy(sdvlb_ctx* ctx, sdvlb_seq* seq);
 int sdvlb_seq_reset(sdvlb_ctx* ctx, sdvlb_seq* seq, const sdvlb_frame* frame, const double T[7]);
 /* Mapping thread -> tracker: n points whose init features live in keyframe `kf` (pose T_kf) are appended, in order,
  * to the feature list of the sequence's current frame.  *kf_slot receives the keyframe slot the points reference;
- * `kf` must stay alive until a result reports kf_live[slot] == 0.  Takes effect before the next tracked frame. */
+ * `kf` must stay alive until a result reports kf_live[slot] == 0.  Takes effect before the next tracked frame.
+ * ORB mode: Feature::descriptor_ of every init feature is computed on the device from `kf` at (ref_px, ref_level). */
 int sdvlb_seq_add_points(sdvlb_ctx* ctx, sdvlb_seq* seq, const sdvlb_frame* kf, const double T_kf[7],
                          const sdvlb_seq_point* pts, int n, int* kf_slot);
 /* Sets the sequence's policy; takes effect before the next tracked frame (queued like sdvlb_seq_add_points). */

@@ -28,7 +28,8 @@ class TrackJob(C.Structure):
     _fields_ = [("image", C.c_void_p), ("image_on_device", C.c_int32), ("want_corners", C.c_int32),
                 ("nfeatures", C.c_int32), ("n_feats", C.c_int32), ("n_cands", C.c_int32), ("n_tracked", C.c_int32),
                 ("gn_iters", C.c_int32), ("pad_", C.c_int32), ("ref", C.c_void_p), ("cur", C.c_void_p), ("feats", C.c_void_p), ("cands", C.c_void_p),
-                ("matches", C.c_void_p), ("T_ref", C.c_double * 7), ("T_cur", C.c_double * 7), ("error", C.c_double)]
+                ("matches", C.c_void_p), ("T_ref", C.c_double * 7), ("T_cur", C.c_double * 7), ("error", C.c_double),
+                ("cand_desc", C.c_void_p)]
 
 
 def build(verbose=False):
@@ -70,7 +71,7 @@ EXPORTS = [
     "sdvlb_seq_track_poll", "sdvlb_seq_track_collect", "sdvlb_seq_track_inflight", "sdvlb_seq_set_policy",
     "sdvlb_seq_release", "sdvlb_frame_filter_corners", "sdvlb_update_candidates",
     "sdvlb_ctx_set_distortion", "sdvlb_undistort",
-    "sdvlb_ctx_set_orb", "sdvlb_frame_orb_descriptors", "sdvlb_search_points_orb",
+    "sdvlb_ctx_set_orb", "sdvlb_frame_orb_descriptors", "sdvlb_search_points_orb", "sdvlb_frame_descriptors",
 ]
 
 
@@ -109,6 +110,15 @@ class Frame:
         _check(load().sdvlb_frame_orb_descriptors(C.c_void_p(self.ctx.h), C.c_void_p(self.h), ptr(xyl), xyl.shape[0],
                                                   ptr(desc), ptr(ang)))
         return desc, ang
+
+    def descriptors(self):
+        """Frame::GetDescriptors(): (n_corners x 32) bytes, corners() order (ORB mode)."""
+        n = C.c_int()
+        _check(load().sdvlb_frame_descriptors(C.c_void_p(self.ctx.h), C.c_void_p(self.h), None, 0, C.byref(n)))
+        d = np.zeros((n.value, 32), np.uint8)
+        if n.value:
+            _check(load().sdvlb_frame_descriptors(C.c_void_p(self.ctx.h), C.c_void_p(self.h), ptr(d), n.value, C.byref(n)))
+        return d
 
     def detect(self, nfeatures):
         _check(load().sdvlb_frame_detect(C.c_void_p(self.ctx.h), C.c_void_p(self.h), nfeatures))
@@ -329,7 +339,8 @@ HOST_EXPORTS = ["sdvlh_last_error", "sdvlh_config_set", "sdvlh_tracker_create", 
                 "sdvlh_tracker_step", "sdvlh_tracker_timing_read", "sdvlh_tracker_counters", "sdvlh_tracker_phases",
                 "sdvlh_tracker_ctx", "sdvlh_tracker_groups", "sdvlh_tracker_threads", "sdvlh_tracker_run",
                 "sdvlh_tracker_create2", "sdvlh_tracker_post_cycles", "sdvlh_tracker_set_prefetch", "sdvlh_tracker_set_depth", "sdvlh_tracker_slowest_cycles",
-                "sdvlh_map_update_candidates", "sdvlh_map_init_candidates", "sdvlh_camera_undistort"]
+                "sdvlh_map_update_candidates", "sdvlh_map_init_candidates", "sdvlh_camera_undistort",
+                "sdvlh_config_set_orb"]
 
 
 def build_host(verbose=False):
@@ -427,10 +438,12 @@ class HostTracker:
     the batched submission."""
 
     def __init__(self, params, cam, plane, max_points, kf_every, n_seq, n_groups=1, device=0, timing=False,
-                 n_threads=0, resident=False):
-        """resident=True keeps the sequences on the device (sdvlb_seq_*): no host marshalling / match replay."""
+                 n_threads=0, resident=False, use_orb=False):
+        """resident=True keeps the sequences on the device (sdvlb_seq_*): no host marshalling / match replay.
+        use_orb=True: Config::UseORB() for this tracker's contexts (the flag is process-wide, as in the reference)."""
         H = load_host()
         H.sdvlh_config_set(C.byref(params), C.byref(cam))
+        H.sdvlh_config_set_orb(int(use_orb))
         plane = np.ascontiguousarray(plane, np.float64)
         self.h = H.sdvlh_tracker_create2(ptr(plane), max_points, kf_every, n_seq, n_groups, n_threads, device,
                                          int(timing), int(resident))

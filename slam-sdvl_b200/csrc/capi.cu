@@ -21,17 +21,13 @@
 cudaError_t sdvlb_launch_upload(const FrameBatch& B, const ImageBatch& I, int bytes, bool src_on_device, cudaStream_t stream);
 cudaError_t sdvlb_launch_undistort(const FrameBatch& B, const ImageBatch& raw, const UndistortArgs& U, cudaStream_t stream);
 cudaError_t sdvlb_launch_seed_update(sdvlb_seed* d_seeds, int n, const FrameDev& cur, const PyrGeom& g,
-                                     const DevParams& dp, const sdvlb_seed_params& sp, cudaStream_t stream);
+                                     const DevParams& dp, const sdvlb_seed_params& sp, cudaStream_t stream, bool orb);
 cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStream_t stream);
 int sdvlb_pyramid_launches(const PyrGeom& g);
 void sdvlb_fast_plan(const PyrGeom& g, const sdvlb_params& p, int nfeatures, int corner_cap, FastPlan* plan);
 cudaError_t sdvlb_launch_orb_positions(const uint8_t* pyr, const PyrGeom& g, int levels, const int32_t* d_xyl, int n,
                                        uint8_t* d_desc, float* d_angle, cudaStream_t stream);
-cudaError_t sdvlb_launch_orb_corners(const FrameDev& f, const PyrGeom& g, int levels, int cap, uint8_t* d_desc,
-                                     cudaStream_t stream);
-cudaError_t sdvlb_launch_search_orb(const SearchCandDev* d_cands, int n, const FrameDev& cur, sdvlb_match* d_out,
-                                    const PyrGeom& g, const DevParams& dp, const uint32_t* d_qdesc,
-                                    const uint32_t* d_curdesc, cudaStream_t stream);
+cudaError_t sdvlb_launch_orb_frames(const FrameBatch& B, const PyrGeom& g, int levels, int cap, cudaStream_t stream);
 cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
                                     cudaStream_t stream);
 cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, uint32_t* cell_kp, int32_t* cell_cnt,
@@ -40,7 +36,7 @@ cudaError_t sdvlb_launch_fast_select(const FrameBatch& B, const FastPlan& plan, 
 cudaError_t sdvlb_launch_align(const void* d_jobs, int n_jobs, int n_bound, const PyrGeom& g, const DevParams& dp,
                                cudaStream_t stream);
 cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const FrameDev* d_frames, sdvlb_match* d_out,
-                                const PyrGeom& g, const DevParams& dp, cudaStream_t stream);
+                                const PyrGeom& g, const DevParams& dp, cudaStream_t stream, const uint32_t* d_qdesc);
 cudaError_t sdvlb_launch_signal(uint32_t* h_flag, uint32_t seq, cudaStream_t stream);
 
 // ---- error reporting
@@ -156,6 +152,11 @@ int grow_pool(sdvlb_ctx* c) {
   const size_t off_pose = off;  off = align_up(off + 7 * sizeof(double), 256);
   const size_t gcells = size_t(c->geom.wcells[0]) * c->geom.hcells[0];
   const size_t off_grid = off;  off = align_up(off + (2 * gcells + 1 + size_t(c->corner_cap)) * sizeof(int32_t), 256);
+  // Config::UseORB(): Frame::descriptors_, 32 bytes per corner.  Slots carry the region when the context was in ORB mode
+  // when the slab was allocated (sdvlb_ctx_set_orb regrows the pool, which is why it wants no live frames).
+  const bool with_desc = c->use_orb;
+  const size_t off_desc = off;
+  if (with_desc) off = align_up(off + size_t(c->corner_cap) * 32, 256);
   c->block_bytes = off;
   uint8_t* slab = nullptr;
   uint8_t* mslab = nullptr;
@@ -174,6 +175,7 @@ int grow_pool(sdvlb_ctx* c) {
     f->dev.corners = reinterpret_cast<int4*>(f->d_block + off_hdr + 16);
     f->dev.pose = reinterpret_cast<double*>(f->d_block + off_pose);
     f->dev.grid = reinterpret_cast<int32_t*>(f->d_block + off_grid);
+    f->dev.desc = with_desc ? reinterpret_cast<uint32_t*>(f->d_block + off_desc) : nullptr;
     f->dev.host_mirror = nullptr;
     f->dev.mirror_cap = c->corner_copy;
     c->pool.push_back(f);
@@ -193,6 +195,7 @@ int frame_alloc(sdvlb_ctx* c, sdvlb_frame** out) {
   c->pool.pop_back();
   f->has_corners = false; f->pyr_mirrored = false; f->corners_mirrored = -1; f->n_corners = 0;
   f->build_pending = false; f->build_corners = false; f->build_mirror = false;
+  f->build_desc = false; f->has_desc = false;
   f->built = nullptr;
   f->h_more.clear();
   *out = f;
@@ -278,6 +281,7 @@ int check_overflow(sdvlb_ctx* c) {   // the stream that ran the selector must ha
 // Host bookkeeping once a frame's build commands are known to have completed.
 void finalize_build(sdvlb_ctx* c, sdvlb_frame* f) {
   f->has_corners = f->build_corners;
+  f->has_desc = f->build_corners && f->build_desc;
   f->corners_mirrored = -1;
   if (f->build_corners && f->build_mirror) {
     memcpy(&f->n_corners, f->h_corners, sizeof(int32_t));
@@ -354,6 +358,7 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
       if (image_loc[base + i] == 0) by_kernel = false;
       f->build_corners = want_corners;
       f->build_mirror = want_corners && mirror;
+      f->build_desc = want_corners && c->use_orb && f->dev.desc != nullptr;
     }
     // Camera::UndistortImage: the raw images go to a scratch set, the undistortion kernel fills level 0
     FrameBatch Bup = B;
@@ -422,6 +427,10 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
                                               c->frame_ticket, stream));
       timer_end(c);
       c->n_launches += 2;
+      if (c->use_orb) {   // Frame::descriptors_ for every corner, once (the reference fills them lazily)
+        SDVLB_CUDA_TRY(sdvlb_launch_orb_frames(B, c->geom, c->params.pyramid_levels, c->corner_cap, stream));
+        c->n_launches += 1;
+      }
     }
   }
   return 0;
@@ -436,7 +445,9 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
   const PyrGeom& g = c->geom;
 
   int n_detect = 0, n_align = 0, n_cands = 0, n_feats = 0, nfeatures = -1, max_feats_job = 0;
+  int n_with_desc = 0, n_with_cands = 0;
   for (int i = 0; i < n; i++) {
+    if (jobs[i].n_cands > 0) { n_with_cands++; if (jobs[i].cand_desc) n_with_desc++; }
     if (jobs[i].ref) max_feats_job = std::max(max_feats_job, jobs[i].n_feats);
     if (build_frames && jobs[i].want_corners) {
       n_detect++;
@@ -449,6 +460,18 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
   }
   if (build_frames && n_detect != 0 && n_detect != n)
     return sdvlb_set_error(SDVLB_ERR_ARG, "mixed want_corners in one batch");
+  // Config::UseORB(): candidates come with the descriptors of their init features and are scored against the corner
+  // descriptors of the current frames (matcher.cc:243-277)
+  const bool orb_search = n_with_desc > 0;
+  if (orb_search) {
+    if (n_with_desc != n_with_cands) return sdvlb_set_error(SDVLB_ERR_ARG, "cand_desc on some jobs of a batch only");
+    if (!c->use_orb) return sdvlb_set_error(SDVLB_ERR_STATE, "candidate descriptors need sdvlb_ctx_set_orb(ctx, 1)");
+    for (int i = 0; i < n; i++)
+      if (jobs[i].n_cands > 0 && !build_frames && !(jobs[i].cur && (jobs[i].cur->has_desc || (jobs[i].cur->build_pending && jobs[i].cur->build_desc))))
+        return sdvlb_set_error(SDVLB_ERR_STATE, "the current frame was built outside ORB mode: it has no corner descriptors");
+  } else if (c->use_orb && n_with_cands > 0) {
+    return sdvlb_set_error(SDVLB_ERR_ARG, "ORB mode: candidates need cand_desc (feature->GetDescriptor())");
+  }
 
   // ---- frames
   if (build_frames) {
@@ -470,7 +493,7 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
   in.used = 0; out.used = 0;
   const size_t need_in = 4096 + size_t(n) * (sizeof(FrameDev) + sizeof(AlignJobDev) + 512) +
                          size_t(n_feats) * sizeof(sdvlb_align_feat) + size_t(n_cands) * sizeof(SearchCandDev) +
-                         (forced ? size_t(forced->n_total) * 56 + 512 : 0) + 32 * 256;
+                         (forced ? size_t(forced->n_total) * 56 + 512 : 0) + 32 * 256 + (orb_search ? size_t(n_cands) * 32 + 256 : 0);
   const size_t need_out = 4096 + size_t(n) * sizeof(BatchOut) + size_t(n_cands) * sizeof(sdvlb_match) +
                           size_t(trace ? trace_cap : 0) * sizeof(sdvlb_gn_iter) + 16 * 256;
   int rc = ensure_arena(&in, need_in, true);
@@ -487,6 +510,7 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
   const size_t o_align = in.take(size_t(std::max(n_align, 1)) * sizeof(AlignJobDev));
   const size_t o_feats = in.take(size_t(std::max(n_feats, 1)) * sizeof(sdvlb_align_feat));
   const size_t o_cands = in.take(size_t(std::max(n_cands, 1)) * sizeof(SearchCandDev));
+  const size_t o_qdesc = orb_search ? in.take(size_t(std::max(n_cands, 1)) * 32) : 0;
   size_t o_forced_T = 0, o_forced_it = 0;
   if (forced) {
     o_forced_T = in.take(size_t(forced->n_total) * 7 * sizeof(double));
@@ -543,6 +567,7 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
       fi += j.n_feats;
       ai++;
     }
+    if (orb_search && j.n_cands > 0) memcpy(in.h + o_qdesc + size_t(cidx) * 32, j.cand_desc, size_t(j.n_cands) * 32);
     for (int k = 0; k < j.n_cands; k++) {
       const sdvlb_candidate& s = j.cands[k];
       SearchCandDev& d = hc[cidx++];
@@ -615,7 +640,8 @@ int submit_batch(sdvlb_ctx* c, sdvlb_track_job* jobs, int n, int mirror, sdvlb_g
     timer_begin(c, SDVLB_K_SEARCH);
     SDVLB_CUDA_TRY(sdvlb_launch_search(reinterpret_cast<const SearchCandDev*>(in.d + o_cands), n_cands,
                                        reinterpret_cast<const FrameDev*>(in.d + o_frames),
-                                       reinterpret_cast<sdvlb_match*>(out.h + o_match), g, c->dp, c->stream));
+                                       reinterpret_cast<sdvlb_match*>(out.h + o_match), g, c->dp, c->stream,
+                                       orb_search ? reinterpret_cast<const uint32_t*>(in.d + o_qdesc) : nullptr));
     timer_end(c);
     c->n_launches += 1;
   }
@@ -984,6 +1010,11 @@ int sdvlb_frame_detect(sdvlb_ctx* ctx, sdvlb_frame* f, int nfeatures) {
                                           ctx->level_cnt, ctx->frame_ticket, ctx->stream));
   timer_end(ctx);
   ctx->n_launches += 2;
+  f->build_desc = ctx->use_orb && f->dev.desc != nullptr;
+  if (ctx->use_orb) {
+    SDVLB_CUDA_TRY(sdvlb_launch_orb_frames(B, ctx->geom, ctx->params.pyramid_levels, ctx->corner_cap, ctx->stream));
+    ctx->n_launches += 1;
+  }
   SDVLB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   rc = check_overflow(ctx);
   if (rc) return rc;
@@ -1174,7 +1205,7 @@ int sdvlb_update_candidates(sdvlb_ctx* c, const sdvlb_frame* cur, const double T
   const size_t bytes = sizeof(sdvlb_seed) * size_t(n);
   SDVLB_CUDA_TRY(cudaMemcpyAsync(cur->dev.pose, T_cur, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   SDVLB_CUDA_TRY(cudaMemcpyAsync(c->d_seeds, c->h_seeds, bytes, cudaMemcpyHostToDevice, c->stream));
-  SDVLB_CUDA_TRY(sdvlb_launch_seed_update(c->d_seeds, n, cur->dev, c->geom, c->dp, *sp, c->stream));
+  SDVLB_CUDA_TRY(sdvlb_launch_seed_update(c->d_seeds, n, cur->dev, c->geom, c->dp, *sp, c->stream, c->use_orb));
   SDVLB_CUDA_TRY(cudaMemcpyAsync(c->h_seeds, c->d_seeds, bytes, cudaMemcpyDeviceToHost, c->stream));
   SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->n_launches += 1;
@@ -1204,6 +1235,21 @@ int sdvlb_ctx_set_orb(sdvlb_ctx* c, int on) {
   if (on && (c->params.patch_size != 8)) return sdvlb_set_error(SDVLB_ERR_ARG, "ORB mode needs patch_size 8");
   const int rc = sdvlb_ctx_sync(c);
   if (rc) return rc;
+  if (on && !c->use_orb && !c->slabs.empty()) {
+    // frame slots allocated so far have no room for Frame::descriptors_: regrow the pool (no frame may be alive)
+    if (c->pool.size() != c->all_frames.size())
+      return sdvlb_set_error(SDVLB_ERR_STATE, "sdvlb_ctx_set_orb(ctx, 1) with frames alive: switch the mode before creating frames");
+    SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n_frames = c->all_frames.size();
+    for (sdvlb_frame* f : c->all_frames) { if (f->h_pyr) cudaFreeHost(f->h_pyr); delete f; }
+    c->all_frames.clear(); c->pool.clear();
+    for (uint8_t* p : c->slabs) cudaFree(p);
+    for (uint8_t* p : c->mirror_slabs) cudaFreeHost(p);
+    c->slabs.clear(); c->mirror_slabs.clear();
+    c->use_orb = true;
+    c->plans.clear();
+    return sdvlb_ctx_reserve_frames(c, int(n_frames));
+  }
   c->use_orb = on != 0;
   c->plans.clear();          // FAST plans carry the border margin
   return 0;
@@ -1243,53 +1289,41 @@ int sdvlb_search_points_orb(sdvlb_ctx* c, const sdvlb_frame* cur, const sdvlb_ca
   if (!c || !cur || !T_cur || n < 0 || (n > 0 && (!cands || !out || !cand_desc)))
     return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
   if (!c->use_orb) return sdvlb_set_error(SDVLB_ERR_STATE, "sdvlb_ctx_set_orb(ctx, 1) first");
-  int rc = ensure_built(const_cast<sdvlb_frame*>(cur));
+  const int rc = ensure_built(const_cast<sdvlb_frame*>(cur));
   if (rc) return rc;
   if (!cur->has_corners) return sdvlb_set_error(SDVLB_ERR_STATE, "current frame has no corners");
   if (n == 0) return 0;
-  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
-  std::vector<SearchCandDev> hc(static_cast<size_t>(n));
-  for (int k = 0; k < n; k++) {
-    const sdvlb_candidate& s = cands[k];
-    SearchCandDev& d = hc[size_t(k)];
-    if (!s.ref_frame) return sdvlb_set_error(SDVLB_ERR_ARG, "candidate without reference frame");
-    if (s.ref_level < 0 || s.ref_level >= c->params.pyramid_levels)
-      return sdvlb_set_error(SDVLB_ERR_ARG, "candidate level out of range");
-    rc = ensure_built(const_cast<sdvlb_frame*>(s.ref_frame));
-    if (rc) return rc;
-    d.ref_pyr = s.ref_frame->dev.pyr;
-    memcpy(d.ref_T, s.ref_T, sizeof(d.ref_T));
-    d.ref_px[0] = s.ref_px[0]; d.ref_px[1] = s.ref_px[1];
-    d.ref_v[0] = s.ref_v[0]; d.ref_v[1] = s.ref_v[1]; d.ref_v[2] = s.ref_v[2];
-    d.idepth = s.idepth; d.idepth_std = s.idepth_std;
-    d.px[0] = s.px[0]; d.px[1] = s.px[1];
-    d.pos[0] = s.pos[0]; d.pos[1] = s.pos[1]; d.pos[2] = s.pos[2];
-    d.ref_level = s.ref_level;
-    d.flags = s.flags;
-    d.cur_index = 0;
-    d.pad_ = 0;
-  }
-  const size_t b_cand = sizeof(SearchCandDev) * size_t(n), b_q = size_t(n) * 32, b_cd = size_t(c->corner_cap) * 32;
-  const size_t b_m = sizeof(sdvlb_match) * size_t(n);
-  const size_t o_cand = 0, o_q = align_up(b_cand, 256), o_cd = o_q + align_up(b_q, 256), o_m = o_cd + align_up(b_cd, 256);
-  rc = orb_scratch(c, o_m + b_m);
+  sdvlb_track_job j;
+  memset(&j, 0, sizeof(j));
+  j.cur = const_cast<sdvlb_frame*>(cur);
+  j.cands = cands;
+  j.n_cands = n;
+  j.matches = out;
+  j.cand_desc = cand_desc;
+  memcpy(j.T_cur, T_cur, sizeof(j.T_cur));
+  return run_batch(c, &j, 1, 0, nullptr, 0, nullptr, nullptr, false);
+}
+
+// Frame::GetDescriptors() (frame.h): the 32-byte descriptor of every corner, in Frame::GetCorners() order.
+int sdvlb_frame_descriptors(sdvlb_ctx* c, const sdvlb_frame* f, uint8_t* desc, int cap, int* n) {
+  if (!c || !f || (cap > 0 && !desc)) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
+  const int rc = ensure_built(const_cast<sdvlb_frame*>(f));
   if (rc) return rc;
-  SearchCandDev* d_cand = reinterpret_cast<SearchCandDev*>(c->orb_buf + o_cand);
-  uint32_t* d_q = reinterpret_cast<uint32_t*>(c->orb_buf + o_q);
-  uint8_t* d_cd = c->orb_buf + o_cd;
-  sdvlb_match* d_m = reinterpret_cast<sdvlb_match*>(c->orb_buf + o_m);
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(cur->dev.pose, T_cur, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(d_cand, hc.data(), b_cand, cudaMemcpyHostToDevice, c->stream));
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(d_q, cand_desc, b_q, cudaMemcpyHostToDevice, c->stream));
-  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));   // hc is pageable host memory about to go out of use
-  SDVLB_CUDA_TRY(sdvlb_launch_orb_corners(cur->dev, c->geom, c->params.pyramid_levels, c->corner_cap, d_cd, c->stream));
-  SDVLB_CUDA_TRY(sdvlb_launch_search_orb(d_cand, n, cur->dev, d_m, c->geom, c->dp, d_q, reinterpret_cast<const uint32_t*>(d_cd),
-                                         c->stream));
-  SDVLB_CUDA_TRY(cudaMemcpyAsync(out, d_m, b_m, cudaMemcpyDeviceToHost, c->stream));
-  SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-  c->n_launches += 2;
-  c->h2d_bytes += int64_t(b_cand + b_q) + 56;
-  c->d2h_bytes += int64_t(b_m);
+  if (!f->has_corners || !f->has_desc)
+    return sdvlb_set_error(SDVLB_ERR_STATE, "the frame has no corner descriptors (built without corners or outside ORB mode)");
+  SDVLB_CUDA_TRY(cudaSetDevice(c->device));
+  int nc = f->n_corners;
+  if (f->corners_mirrored < 0) {   // built without a mirror: the count is still on the device
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(&nc, f->dev.n_corners, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  if (n) *n = nc;
+  const int m = std::min(nc, cap);
+  if (m > 0) {
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(desc, f->dev.desc, size_t(m) * 32, cudaMemcpyDeviceToHost, c->stream));
+    SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += int64_t(m) * 32;
+  }
   return 0;
 }
 

@@ -49,7 +49,9 @@ struct sdvlb_frame {
   cudaEvent_t built = nullptr;   // borrowed from the context's ring: recorded after the frame's batch was enqueued
   bool build_pending = false;    // submitted with sdvlb_frames_submit, completion not yet observed by the host
   bool build_corners = false, build_mirror = false;
+  bool build_desc = false;       // ORB mode: the build also writes the corner descriptors (FrameDev::desc)
   bool has_corners = false;
+  bool has_desc = false;
   int corners_mirrored = -1;     // number of corners valid in the host mirror, -1 = not mirrored
   int n_corners = 0;
 };
@@ -73,6 +75,7 @@ struct sdvlb_seq {   // host handle of a resident sequence
   size_t result_stride = 0;          // SeqResultHost + max_feats feature records, 256-byte aligned
   int max_feats = 0, n_cells = 0;
   int n_bound = 0;                   // upper bound of the device-side feature count at the next submission
+  bool has_desc = false;             // created in ORB mode: the feature lists carry init-feature descriptors
   sdvlb_seq_policy policy = {};
   int kf_state[SDVLB_SEQ_KF_CAP] = {};   // 0 free, 1 points queued, 2 queued points submitted, 3 live
   uint32_t kf_seq[SDVLB_SEQ_KF_CAP] = {};   // submission that carried the slot's points to the device

@@ -43,6 +43,9 @@ struct FrameDev {
   // Spatial index of the corners for Matcher::GetCornersInRange: 32-px cells of the level-0 image (the level-0 FAST
   // grid), corners binned by their level-0 position.  Layout: start[cells + 1], cursor[cells], item[corner_cap].
   int32_t* grid;
+  // Config::UseORB(): Frame::descriptors_, 8 words per corner (same order as `corners`), written when the frame is
+  // built; nullptr for frames of a context that was not in ORB mode when their slot was allocated.
+  uint32_t* desc;
 };
 
 // Frames of one build submission, passed to the build kernels BY VALUE (kernel parameter space), so a frame batch

@@ -1,92 +1,13 @@
 // orb.cu — ORB descriptor mode on the device: ORBDetector::GetOrientation and
-// GetDescriptor (extra/orb_detector.cc:350-437) for a list of positions or for every corner of a frame.
-//
-// One warp per position.  Orientation: the intensity-centroid moments m_10, m_01 over the circular patch of radius
-// 15 are integer sums (lane r owns row r - 15), so any summation order is exact; cv::fastAtan2 is OpenCV's degree-7
-// polynomial, evaluated here with explicitly rounded float operations (no FMA contraction) so that it returns
-// OpenCV's bits.  Descriptor: lane i computes byte i, i.e. the 8 learned tests 8i..8i+7 of csrc/orb_pattern.h
-// rotated by the orientation, sample coordinates rounded half-to-even as cvRound does.  cos / sin of the float angle
-// are taken in double and rounded to float (the correctly rounded value; glibc's cosf / sinf, which the reference
-// calls, return the same float except in rare last-place cases).
-#include <cfloat>
+// GetDescriptor (extra/orb_detector.cc:350-437) for a list of positions, for every corner of the frames of a build
+// batch (Frame::descriptors_, filled lazily by the reference, matcher.cc:265-269; here once, when the frame is built),
+// and for the init features of the map points a sequence receives (Feature::descriptor_).  Device functions: orb.cuh.
+#include "orb.cuh"
+#include "seq.cuh"
 
-#include "common.cuh"
-#include "orb_pattern.h"
+using namespace sdvlb_orb;
 
 namespace {
-
-constexpr int kOrbHalf = 15;                 // Config::ORBSize() / 2, orb_size = 31
-constexpr int kOrbLimit = kOrbHalf + 4;      // ORBDetector::IsInsideLimits (extra/orb_detector.cc:439-446)
-// umax_ of ORBDetector::InitParameters (extra/orb_detector.cc:326-348) for a half patch of 15
-__constant__ int8_t c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-
-__device__ __forceinline__ float fast_atan2_deg(float y, float x) {   // cv::fastAtan2 (atan_f32)
-  const float scale = float(180.0 / 3.1415926535897932384626433832795);
-  const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
-  const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
-  const float ax = fabsf(x), ay = fabsf(y);
-  float a;
-  if (ax >= ay) {
-    const float c = __fdiv_rn(ay, __fadd_rn(ax, float(DBL_EPSILON)));
-    const float c2 = __fmul_rn(c, c);
-    float t = __fadd_rn(__fmul_rn(p7, c2), p5);
-    t = __fadd_rn(__fmul_rn(t, c2), p3);
-    t = __fadd_rn(__fmul_rn(t, c2), p1);
-    a = __fmul_rn(t, c);
-  } else {
-    const float c = __fdiv_rn(ax, __fadd_rn(ay, float(DBL_EPSILON)));
-    const float c2 = __fmul_rn(c, c);
-    float t = __fadd_rn(__fmul_rn(p7, c2), p5);
-    t = __fadd_rn(__fmul_rn(t, c2), p3);
-    t = __fadd_rn(__fmul_rn(t, c2), p1);
-    a = __fsub_rn(90.f, __fmul_rn(t, c));
-  }
-  if (x < 0) a = __fsub_rn(180.f, a);
-  if (y < 0) a = __fsub_rn(360.f, a);
-  return a;
-}
-
-// img: one pyramid level (stride = W); (x, y) inside the limits.  Every lane returns the orientation in degrees; lane
-// i returns descriptor byte i in *byte_out.
-__device__ __forceinline__ float orb_describe(const uint8_t* __restrict__ img, int W, int x, int y, uint32_t* byte_out) {
-  const int lane = threadIdx.x & 31;
-  const uint8_t* __restrict__ center = img + size_t(y) * W + x;
-  int m10 = 0, m01 = 0;
-  if (lane < 2 * kOrbHalf + 1) {
-    const int v = lane - kOrbHalf;
-    const int d = c_umax[v < 0 ? -v : v];
-    const uint8_t* __restrict__ row = center + v * W;
-    int s = 0;
-    for (int u = -d; u <= d; ++u) {
-      const int val = __ldg(row + u);
-      m10 += u * val;
-      s += val;
-    }
-    m01 = v * s;
-  }
-  m10 = int(__reduce_add_sync(0xffffffffu, unsigned(m10)));
-  m01 = int(__reduce_add_sync(0xffffffffu, unsigned(m01)));
-  const float deg = fast_atan2_deg(float(m01), float(m10));
-  const float factorPI = float(3.1415926535897932384626433832795 / 180.f);
-  const float angle = float(double(deg) * double(factorPI));
-  const float a = float(cos(double(angle))), b = float(sin(double(angle)));
-  const signed char* pat = kOrbPattern31 + lane * 32;
-  uint32_t val = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    int t[2];
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const float px = float(pat[4 * k + 2 * j]), py = float(pat[4 * k + 2 * j + 1]);
-      const float r = __fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a));
-      const float c = __fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b));
-      t[j] = __ldg(center + __float2int_rn(r) * W + __float2int_rn(c));
-    }
-    val |= uint32_t(t[0] < t[1]) << k;
-  }
-  *byte_out = val;
-  return deg;
-}
 
 constexpr int ORB_WARPS = 8;
 
@@ -107,19 +28,40 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_positions_kernel(const uin
   if (angle && lane == 0) angle[i] = deg;
 }
 
-// every corner of a frame (the lazily filled Frame::descriptors_ of matcher.cc:265-269, all at once)
-__global__ void __launch_bounds__(ORB_WARPS * 32) orb_corners_kernel(const FrameDev f, const __grid_constant__ PyrGeom G,
-                                                                      int levels, int cap, uint8_t* __restrict__ desc) {
+// Every corner of every frame of a build batch: Frame::descriptors_ (filled lazily by the reference, matcher.cc:265-269,
+// frame.cc:148-161; a descriptor is a function of the frame and the corner, so computing all of them when the frame is
+// built gives the same bytes).  grid (ORB_FRAME_CTAS, frames); the warps of a frame's CTAs stride over its corners.
+constexpr int ORB_FRAME_CTAS = 32;
+__global__ void __launch_bounds__(ORB_WARPS * 32) orb_frames_kernel(const __grid_constant__ FrameBatch B,
+                                                                     const __grid_constant__ PyrGeom G, int levels, int cap) {
+  const FrameDev& f = B.f[blockIdx.y];
+  if (!f.desc) return;
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * ORB_WARPS + (threadIdx.x >> 5);
   const int n = min(*f.n_corners, cap);
-  if (i >= n) return;
-  const int4 c = __ldg(f.corners + i);
-  uint32_t byte = 0;
-  if (c.z >= 0 && c.z < levels && c.x >= kOrbLimit && c.x < G.w[c.z] - kOrbLimit && c.y >= kOrbLimit &&
-      c.y < G.h[c.z] - kOrbLimit)
-    orb_describe(f.pyr + G.off[c.z], G.w[c.z], c.x, c.y, &byte);
-  desc[size_t(i) * 32 + lane] = uint8_t(byte);
+  for (int i = blockIdx.x * ORB_WARPS + (threadIdx.x >> 5); i < n; i += gridDim.x * ORB_WARPS) {
+    const int4 c = __ldg(f.corners + i);
+    uint32_t byte = 0;
+    if (c.z >= 0 && c.z < levels && c.x >= kOrbLimit && c.x < G.w[c.z] - kOrbLimit && c.y >= kOrbLimit &&
+        c.y < G.h[c.z] - kOrbLimit)
+      orb_describe(f.pyr + G.off[c.z], G.w[c.z], c.x, c.y, &byte);
+    reinterpret_cast<uint8_t*>(f.desc)[size_t(i) * 32 + lane] = uint8_t(byte);
+  }
+}
+
+// Feature::descriptor_ of the init features of the map points carried by the SEQC_ADD_POINTS commands of a
+// submission (blockIdx.y = command): computed from the keyframe the points come from, before the align kernel appends
+// the points -- and their descriptors -- to the sequence's feature list.
+__global__ void __launch_bounds__(ORB_WARPS * 32) seq_orb_points_kernel(const SeqCmd* __restrict__ cmds,
+                                                                         const __grid_constant__ PyrGeom G) {
+  const SeqCmd& C = cmds[blockIdx.y];
+  if (C.kind != SEQC_ADD_POINTS || !C.desc) return;
+  const int lane = threadIdx.x & 31;
+  for (int k = blockIdx.x * ORB_WARPS + (threadIdx.x >> 5); k < C.n; k += gridDim.x * ORB_WARPS) {
+    const double px0 = C.pts[k].ref_px[0], px1 = C.pts[k].ref_px[1];
+    const int level = C.pts[k].ref_level;
+    const uint32_t w = orb_feature_word(C.kf_pyr, G, level, px0, px1);
+    if (lane < 8) C.desc[size_t(k) * 8 + lane] = w;
+  }
 }
 
 }  // namespace
@@ -127,13 +69,22 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_corners_kernel(const Frame
 cudaError_t sdvlb_launch_orb_positions(const uint8_t* pyr, const PyrGeom& g, int levels, const int32_t* d_xyl, int n,
                                        uint8_t* d_desc, float* d_angle, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
+  SDVLB_PREPARE(orb_positions_kernel, 0);
   orb_positions_kernel<<<(n + ORB_WARPS - 1) / ORB_WARPS, ORB_WARPS * 32, 0, stream>>>(pyr, g, levels, d_xyl, n, d_desc, d_angle);
   return cudaGetLastError();
 }
 
-cudaError_t sdvlb_launch_orb_corners(const FrameDev& f, const PyrGeom& g, int levels, int cap, uint8_t* d_desc,
-                                     cudaStream_t stream) {
-  if (cap <= 0) return cudaSuccess;
-  orb_corners_kernel<<<(cap + ORB_WARPS - 1) / ORB_WARPS, ORB_WARPS * 32, 0, stream>>>(f, g, levels, cap, d_desc);
+cudaError_t sdvlb_launch_orb_frames(const FrameBatch& B, const PyrGeom& g, int levels, int cap, cudaStream_t stream) {
+  if (B.n <= 0 || cap <= 0) return cudaSuccess;
+  SDVLB_PREPARE(orb_frames_kernel, 0);
+  orb_frames_kernel<<<dim3(ORB_FRAME_CTAS, B.n), ORB_WARPS * 32, 0, stream>>>(B, g, levels, cap);
+  return cudaGetLastError();
+}
+
+cudaError_t sdvlb_launch_seq_orb_points(const SeqCmd* d_cmds, int n_cmds, int max_points, const PyrGeom& g, cudaStream_t stream) {
+  if (n_cmds <= 0 || max_points <= 0) return cudaSuccess;
+  SDVLB_PREPARE(seq_orb_points_kernel, 0);
+  const int ctas = (max_points + ORB_WARPS - 1) / ORB_WARPS;
+  seq_orb_points_kernel<<<dim3(ctas < 16 ? ctas : 16, n_cmds), ORB_WARPS * 32, 0, stream>>>(d_cmds, g);
   return cudaGetLastError();
 }

@@ -7,6 +7,7 @@
 // pixels are spread over the lanes; the LK normal equations are reduced with xor-butterfly shuffles (every lane ends
 // with the same bits).  Ties in ZMSSD resolve to the lowest corner index, as the reference's in-order scan does.
 #include "common.cuh"
+#include "orb.cuh"
 #include "seq.cuh"
 
 namespace {
@@ -56,13 +57,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // One Matcher::SearchPoint by one warp.  s_bp / s_patch: this warp's 10x10 border patch and 8x8 patch in shared memory.
 // kOrb = Config::UseORB() (matcher.cc:79,131-134,243-277): corners are gated with the ORB margin and scored by the
-// Hamming distance between the feature's descriptor (q_desc, 8 words) and the corner's (cur_desc, 8 words per corner
-// of `cur`, orb.cu) with threshold MIN_ORB_THRESHOLD = 100; everything else is the same code.
+// Hamming distance between the feature's descriptor (qword: word (lane & 7) of its 8 words, in every lane) and the
+// corner's (cur.desc, 8 words per corner, written when the frame was built, orb.cu) with threshold
+// MIN_ORB_THRESHOLD = 100; everything else is the same code.
 template <bool kOrb = false>
 __device__ __forceinline__ void search_one(const SearchCandDev& C, const FrameDev& cur, sdvlb_match* __restrict__ out_m,
                                            const PyrGeom& G, const DevParams& dp, uint8_t* s_bp_w, uint8_t* s_patch_w,
-                                           const uint32_t* __restrict__ q_desc = nullptr,
-                                           const uint32_t* __restrict__ cur_desc = nullptr) {
+                                           uint32_t qword = 0u) {
+  const uint32_t* __restrict__ cur_desc = cur.desc;
   const int lane = threadIdx.x & 31;
   const sdvlb_params& P = dp.p;
   const sdvlb_camera& cam = dp.cam;
@@ -190,10 +192,7 @@ __device__ __forceinline__ void search_one(const SearchCandDev& C, const FrameDe
     }
     // GetZMSSDScore (matcher.cc:447-457): template sums, two pixels per lane
     int sumA = 0, sumAA = 0;
-    uint32_t qword = 0;
-    if constexpr (kOrb) {
-      qword = __ldg(q_desc + (lane & 7));
-    } else {
+    if constexpr (!kOrb) {
       const int ta0 = s_patch_w[lane], ta1 = s_patch_w[lane + 32];
       sumA = int(__reduce_add_sync(0xffffffffu, unsigned(ta0 + ta1)));
       sumAA = int(__reduce_add_sync(0xffffffffu, unsigned(ta0 * ta0 + ta1 * ta1)));
@@ -370,10 +369,13 @@ __device__ __forceinline__ void search_one(const SearchCandDev& C, const FrameDe
   if (lane == 0) *out_m = m;
 }
 
+// q_desc (kOrb): 8 words per candidate, feature->GetDescriptor() of the candidate's init feature.
+template <bool kOrb>
 __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchCandDev* __restrict__ cands,
                                                                    const FrameDev* __restrict__ frames,
                                                                    sdvlb_match* __restrict__ out,
-                                                                   const __grid_constant__ SearchArgs A) {
+                                                                   const __grid_constant__ SearchArgs A,
+                                                                   const uint32_t* __restrict__ q_desc) {
   __shared__ uint8_t s_bp[SE_WARPS][104];
   __shared__ uint8_t s_patch[SE_WARPS][64];
   const int warp = threadIdx.x >> 5;
@@ -381,28 +383,16 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
   if (ci >= A.n) return;
   const SearchCandDev& C = cands[ci];
   const FrameDev cur = frames[C.cur_index];
-  search_one(C, cur, out + ci, A.g, A.dp, s_bp[warp], s_patch[warp]);
-}
-
-// Matcher::SearchPoint with Config::UseORB(): one current frame, its corner descriptors in cur_desc (8 words per corner),
-// the candidates' feature descriptors in q_desc (8 words per candidate).
-__global__ void __launch_bounds__(SE_THREADS) search_points_orb_kernel(const SearchCandDev* __restrict__ cands,
-                                                                       const FrameDev cur, sdvlb_match* __restrict__ out,
-                                                                       const __grid_constant__ SearchArgs A,
-                                                                       const uint32_t* __restrict__ q_desc,
-                                                                       const uint32_t* __restrict__ cur_desc) {
-  __shared__ uint8_t s_bp[SE_WARPS][104];
-  __shared__ uint8_t s_patch[SE_WARPS][64];
-  const int warp = threadIdx.x >> 5;
-  const int ci = blockIdx.x * SE_WARPS + warp;
-  if (ci >= A.n) return;
-  search_one<true>(cands[ci], cur, out + ci, A.g, A.dp, s_bp[warp], s_patch[warp], q_desc + size_t(ci) * 8, cur_desc);
+  uint32_t qword = 0u;
+  if constexpr (kOrb) qword = __ldg(q_desc + size_t(ci) * 8 + (threadIdx.x & 7));
+  search_one<kOrb>(C, cur, out + ci, A.g, A.dp, s_bp[warp], s_patch[warp], qword);
 }
 
 // Resident sequences: blockIdx.y = sequence of the step, one warp per feature of the sequence's last frame.  A feature
 // that observes a point is a candidate (FeatureAlign::ProjectPoints, feature_align.cc:296-321): lane 0 assembles the
 // SearchPoint arguments from the feature and its keyframe slot in shared memory, the match goes to the sequence's own
 // device state at the feature's index.
+template <bool kOrb>
 __global__ void __launch_bounds__(SE_THREADS) search_seq_kernel(const __grid_constant__ SeqStepArgs A) {
   __shared__ uint8_t s_bp[SE_WARPS][104];
   __shared__ uint8_t s_patch[SE_WARPS][64];
@@ -432,7 +422,12 @@ __global__ void __launch_bounds__(SE_THREADS) search_seq_kernel(const __grid_con
     c.pad_ = 0;
   }
   __syncwarp();
-  search_one(s_cand[warp], A.cur[blockIdx.y], S->matches + fi, A.g, A.dp, s_bp[warp], s_patch[warp]);
+  uint32_t qword = 0u;
+  if constexpr (kOrb) {   // Feature::descriptor_ of the point's init feature, kept beside the feature list
+    const uint32_t* fd = S->fdesc[S->cur];
+    if (fd) qword = fd[size_t(fi) * 8 + (lane & 7)];
+  }
+  search_one<kOrb>(s_cand[warp], A.cur[blockIdx.y], S->matches + fi, A.g, A.dp, s_bp[warp], s_patch[warp], qword);
 }
 
 // ---- Map::UpdateCandidates (map.cc:397-498): one warp per depth-filter seed.  The geometry is a few dozen fp64
@@ -452,6 +447,7 @@ __device__ __forceinline__ double parallax_cos(const double a[3], const double b
   return v1[0] * v2[0] + v1[1] * v2[1] + v1[2] * v2[2];
 }
 
+template <bool kOrb>
 __global__ void __launch_bounds__(SE_THREADS) seed_update_kernel(sdvlb_seed* __restrict__ seeds, const FrameDev cur,
                                                                  const __grid_constant__ SeedArgs A) {
   __shared__ uint8_t s_bp[SE_WARPS][104];
@@ -505,7 +501,11 @@ __global__ void __launch_bounds__(SE_THREADS) seed_update_kernel(sdvlb_seed* __r
       C.ref_level = S.ref_level; C.flags = 0; C.cur_index = 0; C.pad_ = 0;
     }
     __syncwarp();
-    search_one(s_cand[warp], cur, &s_match[warp], A.g, A.dp, s_bp[warp], s_patch[warp]);
+    uint32_t qword = 0u;
+    // ORB mode: the candidate's init-feature descriptor, recomputed from its keyframe (the seed record has no room for it)
+    if constexpr (kOrb)
+      qword = sdvlb_orb::orb_feature_word(reinterpret_cast<const uint8_t*>(S.ref_frame), A.g, S.ref_level, S.ref_px[0], S.ref_px[1]);
+    search_one<kOrb>(s_cand[warp], cur, &s_match[warp], A.g, A.dp, s_bp[warp], s_patch[warp], qword);
     __syncwarp();
     const sdvlb_match m = s_match[warp];
     if (m.status != SDVLB_MATCH_FOUND) {
@@ -625,46 +625,48 @@ cudaError_t sdvlb_launch_signal(uint32_t* h_flag, uint32_t seq, cudaStream_t str
   return cudaGetLastError();
 }
 
+// d_qdesc != nullptr: Config::UseORB(), 8 descriptor words per candidate; the frames must carry descriptors
 cudaError_t sdvlb_launch_search(const SearchCandDev* d_cands, int n, const FrameDev* d_frames, sdvlb_match* d_out,
-                                const PyrGeom& g, const DevParams& dp, cudaStream_t stream) {
+                                const PyrGeom& g, const DevParams& dp, cudaStream_t stream, const uint32_t* d_qdesc) {
   if (n <= 0) return cudaSuccess;
   SearchArgs A;
   A.g = g;
   A.dp = dp;
   A.n = n;
-  SDVLB_PREPARE(search_points_kernel, 0);
-  search_points_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, d_frames, d_out, A);
-  return cudaGetLastError();
-}
-
-cudaError_t sdvlb_launch_search_orb(const SearchCandDev* d_cands, int n, const FrameDev& cur, sdvlb_match* d_out,
-                                    const PyrGeom& g, const DevParams& dp, const uint32_t* d_qdesc,
-                                    const uint32_t* d_curdesc, cudaStream_t stream) {
-  if (n <= 0) return cudaSuccess;
-  SearchArgs A;
-  A.g = g;
-  A.dp = dp;
-  A.n = n;
-  SDVLB_PREPARE(search_points_orb_kernel, 0);
-  search_points_orb_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, cur, d_out, A, d_qdesc, d_curdesc);
+  if (d_qdesc) {
+    SDVLB_PREPARE(search_points_kernel<true>, 0);
+    search_points_kernel<true><<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, d_frames, d_out, A, d_qdesc);
+  } else {
+    SDVLB_PREPARE(search_points_kernel<false>, 0);
+    search_points_kernel<false><<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_cands, d_frames, d_out, A, nullptr);
+  }
   return cudaGetLastError();
 }
 
 cudaError_t sdvlb_launch_seed_update(sdvlb_seed* d_seeds, int n, const FrameDev& cur, const PyrGeom& g,
-                                     const DevParams& dp, const sdvlb_seed_params& sp, cudaStream_t stream) {
+                                     const DevParams& dp, const sdvlb_seed_params& sp, cudaStream_t stream, bool orb) {
   if (n <= 0) return cudaSuccess;
   SeedArgs A;
   A.g = g;
   A.dp = dp;
   A.sp = sp;
   A.n = n;
-  SDVLB_PREPARE(seed_update_kernel, 0);
-  seed_update_kernel<<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_seeds, cur, A);
+  if (orb) {
+    SDVLB_PREPARE(seed_update_kernel<true>, 0);
+    seed_update_kernel<true><<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_seeds, cur, A);
+  } else {
+    SDVLB_PREPARE(seed_update_kernel<false>, 0);
+    seed_update_kernel<false><<<(n + SE_WARPS - 1) / SE_WARPS, SE_THREADS, 0, stream>>>(d_seeds, cur, A);
+  }
   return cudaGetLastError();
 }
 
 cudaError_t sdvlb_launch_search_seq(const SeqStepArgs& A, cudaStream_t stream) {
   const dim3 grid((A.max_feats + SE_WARPS - 1) / SE_WARPS, A.n);   // max_feats: the caller's bound on features per sequence
-  SDVLB_PREPARE(search_seq_kernel, 0);
-  return sdvlb_launch_dependent(search_seq_kernel, grid, dim3(SE_THREADS), 0, stream, A);
+  if (A.use_orb) {
+    SDVLB_PREPARE(search_seq_kernel<true>, 0);
+    return sdvlb_launch_dependent(search_seq_kernel<true>, grid, dim3(SE_THREADS), 0, stream, A);
+  }
+  SDVLB_PREPARE(search_seq_kernel<false>, 0);
+  return sdvlb_launch_dependent(search_seq_kernel<false>, grid, dim3(SE_THREADS), 0, stream, A);
 }

@@ -737,6 +737,11 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
         f.n_successful += 1; f.n_failed = 0;          // Point::Promote (point.cc:102-106)
         f.status = SEQP_FOUND;
         NL[slot] = f;
+        if (S->fdesc[0]) {   // ORB mode: the point keeps its init feature, hence that feature's descriptor
+          const uint4* src = reinterpret_cast<const uint4*>(S->fdesc[S->cur] + size_t(i) * 8);
+          uint4* dst = reinterpret_cast<uint4*>(S->fdesc[S->cur ^ 1] + size_t(slot) * 8);
+          dst[0] = src[0]; dst[1] = src[1];
+        }
         P.o_a[2 * slot] = f.v[0] / f.v[2];            // Camera::SimpleProject(feature->GetVector())
         P.o_a[2 * slot + 1] = f.v[1] / f.v[2];
         P.o_pos[3 * slot] = f.pos[0]; P.o_pos[3 * slot + 1] = f.pos[1]; P.o_pos[3 * slot + 2] = f.pos[2];

@@ -89,6 +89,9 @@ struct SeqState {
   int32_t* c_cell; int32_t* c_score; int32_t* c_rank; int32_t* c_next;
   double* o_a; double* o_pos; double* o_scale; double* o_err; int32_t* o_flag;
   SeqResultHost* result[SDVLB_SEQ_DEPTH];   // pinned host memory, one block per submission slot
+  // Config::UseORB(): Feature::descriptor_ of the init feature of every feature's point (8 words each), parallel to
+  // list[0] / list[1]; nullptr when the sequence was created outside ORB mode
+  uint32_t* fdesc[2];
 };
 
 // Pose-refinement problem (FeatureAlign lists as arrays): obs i is (a = SimpleProject(v), pos, scale = 2^-level).
@@ -109,6 +112,8 @@ struct SeqStepArgs {
   uint32_t* h_flag;      // pinned completion word
   uint32_t seq_no;       // value to publish
   int32_t slot;          // result slot of this submission (seq_no % SDVLB_SEQ_DEPTH)
+  int32_t use_orb;       // Config::UseORB(): SearchPoint scored by descriptor distance
+  int32_t pad_;
   DevParams dp;
   PyrGeom g;
 };
@@ -125,6 +130,7 @@ struct SeqCmd {
   const uint8_t* kf_pyr;
   double T[7];           // reset: pose; add: keyframe pose
   const sdvlb_seq_point* pts;   // device copy
+  uint32_t* desc;        // ORB mode: 8 words per point, filled by seq_orb_points_kernel before the commands are applied
   sdvlb_seq_policy policy;
 };
 
@@ -199,6 +205,11 @@ __device__ inline void seq_apply_commands(const SeqCmd* __restrict__ cmds, int2 
       f.status = SEQP_FOUND;
       f.n_unpromoted = 0;
       L[base + k] = f;
+      if (C.desc && S->fdesc[0]) {   // Feature::descriptor_ of the init feature (ORB mode)
+        const uint4* src = reinterpret_cast<const uint4*>(C.desc + size_t(k) * 8);
+        uint4* dst = reinterpret_cast<uint4*>(S->fdesc[S->cur] + size_t(base + k) * 8);
+        dst[0] = src[0]; dst[1] = src[1];
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -216,5 +227,6 @@ cudaError_t sdvlb_launch_seq_apply(const SeqCmd* d_cmds, const int2* d_ranges, i
                                    cudaStream_t stream);
 cudaError_t sdvlb_launch_seq_align(const SeqStepArgs& A, int n_bound, cudaStream_t stream);
 cudaError_t sdvlb_launch_search_seq(const SeqStepArgs& A, cudaStream_t stream);
+cudaError_t sdvlb_launch_seq_orb_points(const SeqCmd* d_cmds, int n_cmds, int max_points, const PyrGeom& g, cudaStream_t stream);
 cudaError_t sdvlb_launch_seq_post(const SeqStepArgs& A, cudaStream_t stream);
 cudaError_t sdvlb_launch_pose_call(const PoseCallArgs& A, cudaStream_t stream);

@@ -16,9 +16,10 @@ namespace {
 
 struct SeqLayout {
   size_t list[2], cell_order, matches, align_scratch, c_cell, c_score, c_rank, c_next, o_a, o_pos, o_scale, o_err, o_flag, total;
+  size_t fdesc[2];
 };
 
-SeqLayout seq_layout(int max_feats, int n_cells) {
+SeqLayout seq_layout(int max_feats, int n_cells, bool orb) {
   SeqLayout L;
   size_t off = align_up(sizeof(SeqState), 256);
   auto take = [&off](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -37,6 +38,8 @@ SeqLayout seq_layout(int max_feats, int n_cells) {
   L.o_scale = take(n * sizeof(double));
   L.o_err = take(n * sizeof(double));
   L.o_flag = take(n * sizeof(int32_t));
+  L.fdesc[0] = L.fdesc[1] = 0;
+  if (orb) { L.fdesc[0] = take(n * 32); L.fdesc[1] = take(n * 32); }
   L.total = off;
   return L;
 }
@@ -140,12 +143,13 @@ int sdvlb_seq_create(sdvlb_ctx* c, int max_feats, sdvlb_seq** out) {
   // FeatureAlign's grid (feature_align.cc:44-46) is the level-0 FAST grid
   const int n_cells = c->geom.wcells[0] * c->geom.hcells[0];
   if (n_cells > 4096) return sdvlb_set_error(SDVLB_ERR_ARG, "image too large for the FeatureAlign grid");
-  const SeqLayout L = seq_layout(max_feats, n_cells);
+  const SeqLayout L = seq_layout(max_feats, n_cells, c->use_orb);
   sdvlb_seq* s = new sdvlb_seq;
   s->ctx = c;
   s->max_feats = max_feats;
   s->n_cells = n_cells;
   s->result_stride = result_stride(max_feats);
+  s->has_desc = c->use_orb;
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->d_block), L.total);
   if (e == cudaSuccess)
     e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_result), s->result_stride * SDVLB_SEQ_DEPTH, cudaHostAllocDefault);
@@ -182,6 +186,8 @@ int sdvlb_seq_create(sdvlb_ctx* c, int max_feats, sdvlb_seq** out) {
   st->o_scale = reinterpret_cast<double*>(d + L.o_scale);
   st->o_err = reinterpret_cast<double*>(d + L.o_err);
   st->o_flag = reinterpret_cast<int32_t*>(d + L.o_flag);
+  st->fdesc[0] = c->use_orb ? reinterpret_cast<uint32_t*>(d + L.fdesc[0]) : nullptr;
+  st->fdesc[1] = c->use_orb ? reinterpret_cast<uint32_t*>(d + L.fdesc[1]) : nullptr;
   for (int k = 0; k < SDVLB_SEQ_DEPTH; k++)
     st->result[k] = reinterpret_cast<SeqResultHost*>(s->h_result + size_t(k) * s->result_stride);
   e = cudaMemcpyAsync(d, init.data(), init.size(), cudaMemcpyHostToDevice, c->stream);
@@ -307,6 +313,10 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
       if (seqs[k] == seqs[i]) return sdvlb_set_error(SDVLB_ERR_ARG, "a sequence appears twice in one submission");
     if (!(frames[i]->has_corners || (frames[i]->build_pending && frames[i]->build_corners)))
       return sdvlb_set_error(SDVLB_ERR_STATE, "a tracked frame needs corners");
+    if (c->use_orb && !(frames[i]->has_desc || (frames[i]->build_pending && frames[i]->build_desc)))
+      return sdvlb_set_error(SDVLB_ERR_STATE, "ORB mode: the frame was built without corner descriptors");
+    if (c->use_orb && !seqs[i]->has_desc)
+      return sdvlb_set_error(SDVLB_ERR_STATE, "ORB mode: the sequence was created before sdvlb_ctx_set_orb(ctx, 1)");
     n_bound = std::max(n_bound, seqs[i]->n_bound);
   }
   // ---- order the tracking stream after the builds of every frame it touches
@@ -335,13 +345,18 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
   if (n_cmds > 0) {
     Arena& in = c->seq_in[slot];
     in.used = 0;
-    const size_t need = 2048 + size_t(n_cmds) * (sizeof(SeqCmd) + sizeof(int2)) + c->seq_pts.size() * sizeof(sdvlb_seq_point);
+    const size_t need = 2560 + size_t(n_cmds) * (sizeof(SeqCmd) + sizeof(int2)) +
+                        c->seq_pts.size() * (sizeof(sdvlb_seq_point) + (c->use_orb ? 32 : 0));
     if (need > in.cap) SDVLB_CUDA_TRY(cudaStreamSynchronize(c->stream));   // growing frees the old buffers
     rc = ensure_arena(&in, need, true);
     if (rc) return rc;
     const size_t o_cmds = in.take(size_t(n_cmds) * sizeof(SeqCmd));
     const size_t o_ranges = in.take(size_t(n_cmds) * sizeof(int2));
     const size_t o_pts = in.take(std::max<size_t>(1, c->seq_pts.size()) * sizeof(sdvlb_seq_point));
+    const size_t up_bytes = in.used;   // what follows is device-only scratch
+    // ORB mode: Feature::descriptor_ of the new points' init features, written by seq_orb_points_kernel
+    const size_t o_pdesc = c->use_orb ? in.take(std::max<size_t>(1, c->seq_pts.size()) * 32) : 0;
+    int max_points = 0;
     // commands grouped by sequence, order kept inside a sequence.  Sequences of this step get theirs applied by their
     // own align CTA; the others (not tracked now) by one extra launch.
     std::vector<int> idx(n_cmds);
@@ -353,8 +368,11 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
     for (int k = 0; k < n_cmds; k++) {
       const SeqCmd& src = c->seq_cmds[idx[k]];
       hc[k] = src;
-      if (src.kind == SEQC_ADD_POINTS)
+      if (src.kind == SEQC_ADD_POINTS) {
         hc[k].pts = reinterpret_cast<const sdvlb_seq_point*>(in.d + o_pts) + reinterpret_cast<size_t>(src.pts);
+        hc[k].desc = c->use_orb ? reinterpret_cast<uint32_t*>(in.d + o_pdesc) + reinterpret_cast<size_t>(src.pts) * 8 : nullptr;
+        max_points = std::max(max_points, src.n);
+      }
       if (k > 0 && src.seq == c->seq_cmds[idx[k - 1]].seq) continue;   // same run as the previous command
       int cnt = 1;
       while (k + cnt < n_cmds && c->seq_cmds[idx[k + cnt]].seq == src.seq) cnt++;
@@ -365,9 +383,13 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
       else { hr[n_foreign].x = k; hr[n_foreign].y = cnt; n_foreign++; }
     }
     if (!c->seq_pts.empty()) memcpy(in.h + o_pts, c->seq_pts.data(), c->seq_pts.size() * sizeof(sdvlb_seq_point));
-    SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, in.used, cudaMemcpyHostToDevice, c->stream));
-    c->h2d_bytes += int64_t(in.used);
+    SDVLB_CUDA_TRY(cudaMemcpyAsync(in.d, in.h, up_bytes, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += int64_t(up_bytes);
     d_cmds = reinterpret_cast<const SeqCmd*>(in.d + o_cmds);
+    if (c->use_orb && max_points > 0) {
+      SDVLB_CUDA_TRY(sdvlb_launch_seq_orb_points(d_cmds, n_cmds, max_points, c->geom, c->stream));
+      c->n_launches += 1;
+    }
     if (n_foreign > 0) {
       SDVLB_CUDA_TRY(sdvlb_launch_seq_apply(d_cmds, reinterpret_cast<const int2*>(in.d + o_ranges), n_foreign, c->dp, c->stream));
       c->n_launches += 1;
@@ -395,6 +417,8 @@ int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* co
   A.h_flag = reinterpret_cast<uint32_t*>(c->h_overflow) + 16;
   A.seq_no = c->track_seq;
   A.slot = slot;
+  A.use_orb = c->use_orb ? 1 : 0;
+  A.pad_ = 0;
   A.dp = c->dp;
   A.g = c->geom;
   timer_begin(c, SDVLB_K_ALIGN);

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstring>
 #include <set>
+#include <cassert>
 #include <cmath>
 #include <stdexcept>
 #include <string>
@@ -61,6 +62,10 @@ sdvlb_params& Config::params_() {
 sdvlb_camera& Config::camera_() {
   static sdvlb_camera c = {640, 480, 300.0, 300.0, 320.0, 240.0};   // config.cc:35-40
   return c;
+}
+bool& Config::use_orb_() {
+  static bool on = false;   // kUseORB_ (config.cc:79)
+  return on;
 }
 
 Camera::Camera() {
@@ -257,6 +262,11 @@ int Map::InitCandidates(const std::shared_ptr<Frame>& frame, const std::vector<s
       const Eigen::Vector3i corner = corners[fcorners[count]];
       const int scale = 1 << corner(2);
       auto feature = std::make_shared<Feature>(frame, Eigen::Vector2d(corner(0) * scale, corner(1) * scale), corner(2));
+      if (Config::UseORB()) {   // map.cc:319-323: save the descriptor
+        std::vector<std::vector<unsigned char>>& descriptors = frame->GetDescriptors();
+        assert(!descriptors[size_t(fcorners[count])].empty());
+        feature->SetDescriptor(descriptors[size_t(fcorners[count])]);
+      }
       sdvlb_seed s;
       std::memset(&s, 0, sizeof(s));
       s.ref_frame = frame->Handle();
@@ -354,7 +364,15 @@ int Map::AddConnectionsPoints(const std::shared_ptr<Frame>& frame, const std::ve
   std::vector<sdvlb_match> matches(cands.size());
   double T[7];
   frame->GetPose().ToArray(T);
-  const int rc = sdvlb_search_points(frame->Context(), frame->Handle(), cands.data(), int(cands.size()), T, matches.data());
+  std::vector<unsigned char> descs;
+  if (Config::UseORB())
+    for (const auto& pt : list) {
+      const std::vector<unsigned char>& d = pt->GetInitFeature()->GetDescriptor();
+      descs.insert(descs.end(), d.begin(), d.end());
+    }
+  const int rc = Config::UseORB()
+      ? sdvlb_search_points_orb(frame->Context(), frame->Handle(), cands.data(), int(cands.size()), T, descs.data(), matches.data())
+      : sdvlb_search_points(frame->Context(), frame->Handle(), cands.data(), int(cands.size()), T, matches.data());
   if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_search_points failed: ") + sdvlb_last_error());
   int linked = 0;
   for (size_t i = 0; i < list.size(); i++) {
@@ -388,6 +406,8 @@ sdvlb_ctx* Device::Current() {
   if (!g_default_ctx) {
     const int rc = sdvlb_ctx_create(0, &Config::Params(), &Config::CameraParams(), &g_default_ctx);
     if (rc) throw std::runtime_error(std::string("sdvl-b200: cannot create CUDA context (no CPU fallback): ") + sdvlb_last_error());
+    if (Config::UseORB() && sdvlb_ctx_set_orb(g_default_ctx, 1))
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_set_orb failed: ") + sdvlb_last_error());
   }
   return g_default_ctx;
 }

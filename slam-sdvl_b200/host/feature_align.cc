@@ -44,9 +44,11 @@ void FeatureAlign::ResetGrid() {   // :285-294
 
 // ProjectPoints' iteration and filters (:296-321); the projection itself runs on the device.
 void FeatureAlign::CollectCandidates(int frame_id, const shared_ptr<Frame>& last_frame, bool reloc,
-                                     vector<sdvlb_candidate>* cands, vector<shared_ptr<Point>>* points) {
+                                     vector<sdvlb_candidate>* cands, vector<shared_ptr<Point>>* points,
+                                     vector<unsigned char>* descs) {
   cands->clear();
   points->clear();
+  if (descs) descs->clear();
   relocalizing_ = reloc;
   vector<shared_ptr<Feature>>& features = last_frame->GetFeatures();
   for (auto it_fts = features.begin(); it_fts != features.end(); it_fts++) {
@@ -66,6 +68,10 @@ void FeatureAlign::CollectCandidates(int frame_id, const shared_ptr<Frame>& last
     c.flags |= SDVLB_CAND_PROJECT;
     cands->push_back(c);
     points->push_back(point);
+    if (descs) {
+      const vector<unsigned char>& d = (feature ? feature : *it_fts)->GetDescriptor();
+      descs->insert(descs->end(), d.begin(), d.end());
+    }
     if (!reloc) point->SetLastFrame(frame_id);
   }
 }
@@ -144,12 +150,15 @@ void FeatureAlign::Reproject(const shared_ptr<Frame>& frame, const shared_ptr<Fr
   relocalizing_ = reloc;
   vector<sdvlb_candidate> cands;
   vector<shared_ptr<Point>> points;
-  CollectCandidates(frame->GetID(), last_frame, reloc, &cands, &points);
+  vector<unsigned char> descs;
+  CollectCandidates(frame->GetID(), last_frame, reloc, &cands, &points, Config::UseORB() ? &descs : nullptr);
   vector<sdvlb_match> res(cands.size());
   if (!cands.empty()) {
     double T_cur[7];
     frame->GetPose().ToArray(T_cur);
-    const int rc = sdvlb_search_points(frame->Context(), frame->Handle(), cands.data(), int(cands.size()), T_cur, res.data());
+    const int rc = Config::UseORB()
+        ? sdvlb_search_points_orb(frame->Context(), frame->Handle(), cands.data(), int(cands.size()), T_cur, descs.data(), res.data())
+        : sdvlb_search_points(frame->Context(), frame->Handle(), cands.data(), int(cands.size()), T_cur, res.data());
     if (rc) throw std::runtime_error(std::string("sdvl-b200: FeatureAlign::Reproject failed: ") + sdvlb_last_error());
   }
   ApplyMatches(frame, points, res.data());

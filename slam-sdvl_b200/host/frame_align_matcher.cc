@@ -87,6 +87,23 @@ const std::vector<int>& Frame::GetCornerScores() { GetCorners(); return corner_s
 void Frame::CreateCorners(int /*levels*/, int nfeatures) {   // `levels` is ignored by the reference too (frame.cc:122-126)
   Check(sdvlb_frame_detect(ctx_, handle_, nfeatures), "CreateCorners");
   corners_fetched_ = false;
+  descriptors_fetched_ = false;
+}
+
+std::vector<std::vector<unsigned char>>& Frame::GetDescriptors() {
+  if (!descriptors_fetched_) {
+    descriptors_.clear();
+    if (Config::UseORB()) {
+      const int n = int(GetCorners().size());
+      std::vector<unsigned char> flat(size_t(n) * 32);
+      int got = 0;
+      if (n > 0) Check(sdvlb_frame_descriptors(ctx_, handle_, flat.data(), n, &got), "GetDescriptors");
+      descriptors_.resize(size_t(n));
+      for (int i = 0; i < n; i++) descriptors_[size_t(i)].assign(flat.begin() + size_t(i) * 32, flat.begin() + size_t(i + 1) * 32);
+    }
+    descriptors_fetched_ = true;
+  }
+  return descriptors_;
 }
 
 int Frame::GetNumPoints() const {
@@ -205,7 +222,13 @@ bool Matcher::SearchPoint(const std::shared_ptr<Frame>& frame, const std::shared
   double T_cur[7];
   frame->GetPose().ToArray(T_cur);
   sdvlb_match m;
-  Check(sdvlb_search_points(frame->Context(), frame->Handle(), &c, 1, T_cur, &m), "Matcher::SearchPoint");
+  if (Config::UseORB()) {   // matcher.cc:79-80,109: scored against feature->GetDescriptor()
+    assert(feature->HasDescriptor());
+    Check(sdvlb_search_points_orb(frame->Context(), frame->Handle(), &c, 1, T_cur, feature->GetDescriptor().data(), &m),
+          "Matcher::SearchPoint");
+  } else {
+    Check(sdvlb_search_points(frame->Context(), frame->Handle(), &c, 1, T_cur, &m), "Matcher::SearchPoint");
+  }
   if (m.status != SDVLB_MATCH_FOUND) return false;
   (*px)(0) = m.px[0]; (*px)(1) = m.px[1];
   *flevel = m.level;

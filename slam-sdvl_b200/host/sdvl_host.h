@@ -8,6 +8,7 @@
 // build; the reduced versions below carry exactly the members the hot path touches so that this library and its
 // tests are self-contained (no OpenCV / Eigen in this image).
 #pragma once
+#include <algorithm>
 #include <list>
 #include <memory>
 #include <mutex>
@@ -19,7 +20,7 @@
 
 namespace sdvl {
 
-class ORBDetector;   // out of scope (use_orb = 0); pointer kept for signature compatibility
+class ORBDetector;   // the descriptors are computed on the device (csrc/orb.cu); pointer kept for signature compatibility
 class Frame;
 class Feature;
 class Point;
@@ -69,10 +70,15 @@ class Config {
   static int MinMatches() { return params_().min_matches; }
   static double InlierErrorThreshold() { return params_().inlier_error_threshold; }
   static int MinFeatureScore() { return 50; }   // kMinFeatureScore_ (config.cc:84)
-  static bool UseORB() { return false; }
+  // Config::UseORB() / ORBSize() (config.h:139-140).  Set before the first Frame / tracker exists: contexts switch to
+  // the ORB mode (sdvlb_ctx_set_orb) when they are created.
+  static bool UseORB() { return use_orb_(); }
+  static void SetUseORB(bool on) { use_orb_() = on; }
+  static int ORBSize() { return 31; }
  private:
   static sdvlb_params& params_();
   static sdvlb_camera& camera_();
+  static bool& use_orb_();
 };
 
 // ------------------------------------------------------------------------------------------------ Camera (camera.h)
@@ -159,7 +165,13 @@ class Feature {
   const Eigen::Vector3d& GetVector() const { return v_; }
   int GetLevel() const { return level_; }
   Eigen::Vector2d GetLevelPosition() { return p2d_ / double(1 << level_); }           // feature.h:93-95
+  // feature.h:78-89: the ORB descriptor of the feature (32 zero bytes until one is set)
+  const std::vector<unsigned char>& GetDescriptor() const { return descriptor_; }
+  void SetDescriptor(const std::vector<unsigned char>& d) { std::copy(d.begin(), d.end(), descriptor_.begin()); has_descriptor_ = true; }
+  bool HasDescriptor() const { return has_descriptor_; }
  private:
+  std::vector<unsigned char> descriptor_ = std::vector<unsigned char>(32, 0);
+  bool has_descriptor_ = false;
   std::shared_ptr<Frame> frame_;
   std::shared_ptr<Point> point_;
   Eigen::Vector2d p2d_;
@@ -237,6 +249,9 @@ class Frame {
   void RemoveFeatures();                                       // frame.cc:214-219
   void FilterCorners();                                        // frame.cc:133-163 (use_orb == 0)
   std::vector<int>& GetFilteredCorners() { return filtered_corners_; }
+  // frame.h: per-corner ORB descriptors.  The reference fills them lazily (frame.cc:148-161, matcher.cc:265-269); the
+  // device computes all of them when the frame is built, this fetches the host copy on first use (ORB mode only).
+  std::vector<std::vector<unsigned char>>& GetDescriptors();
   // device side
   sdvlb_frame* Handle() const { return handle_; }
   sdvlb_ctx* Context() const { return ctx_; }
@@ -256,6 +271,8 @@ class Frame {
   std::vector<int> corner_scores_;
   std::vector<Eigen::Vector2d> outliers_;
   std::vector<int> filtered_corners_;
+  std::vector<std::vector<unsigned char>> descriptors_;
+  bool descriptors_fetched_ = false;
   static int counter_;
 };
 
@@ -321,8 +338,10 @@ class FeatureAlign {
   // Batched form used by the multi-sequence tracker: the GPU evaluates ProjectPoint + SearchPoint for every point
   // ProjectPoints would visit (CollectCandidates), then ApplyMatches replays ProjectPoint's bookkeeping and the
   // SelectPoints / SelectInliers logic on the results, with identical side effects.
+  // descs (ORB mode): 32 bytes per candidate, feature->GetDescriptor() of its init feature (matcher.cc:109)
   void CollectCandidates(int frame_id, const std::shared_ptr<Frame>& last_frame, bool reloc,
-                         std::vector<sdvlb_candidate>* cands, std::vector<std::shared_ptr<Point>>* points);
+                         std::vector<sdvlb_candidate>* cands, std::vector<std::shared_ptr<Point>>* points,
+                         std::vector<unsigned char>* descs = nullptr);
   void ApplyMatches(const std::shared_ptr<Frame>& frame, const std::vector<std::shared_ptr<Point>>& points,
                     const sdvlb_match* matches);
   int GetInliers() const { return int(inliers_.size()); }

@@ -51,6 +51,7 @@ struct Sequence {
   vector<sdvlb_align_feat> feats;
   vector<sdvlb_candidate> cands;
   vector<shared_ptr<Point>> cand_points;
+  vector<unsigned char> cand_descs;   // ORB mode: 32 bytes per candidate
   vector<sdvlb_match> matches;
 };
 
@@ -107,6 +108,10 @@ class SequenceDriver {
       const int cx = int(px(0) / cell), cy = int(px(1) / cell);
       if (occupied[size_t(cy) * gw + cx]) continue;
       shared_ptr<Feature> ft = std::make_shared<Feature>(f, px, c(2));
+      if (Config::UseORB()) {   // the descriptor an init feature gets at its keyframe (frame.cc:148-161, map.cc:319-323)
+        if (c(0) < 19 || c(1) < 19 || c(0) >= lw - 19 || c(1) >= lh - 19) continue;   // ORBDetector::IsInsideLimits
+        ft->SetDescriptor(f->GetDescriptors()[size_t((long long)i * 7919 % n)]);
+      }
       const Eigen::Vector3d& v = ft->GetVector();
       const Eigen::Vector3d dir(Rwc[0] * v(0) + Rwc[1] * v(1) + Rwc[2] * v(2), Rwc[3] * v(0) + Rwc[4] * v(1) + Rwc[5] * v(2),
                                 Rwc[6] * v(0) + Rwc[7] * v(1) + Rwc[8] * v(2));
@@ -221,6 +226,8 @@ class SequenceDriver {
       const Eigen::Vector2d px(double(c[0] * (1 << c[2])), double(c[1] * (1 << c[2])));
       const int cx = int(px(0) / cell), cy = int(px(1) / cell);
       if (occupied[size_t(cy) * gw + cx]) continue;
+      // ORB mode: the init feature gets its descriptor at the keyframe (on the device, sdvlb_seq_add_points)
+      if (Config::UseORB() && (c[0] < 19 || c[1] < 19 || c[0] >= lw - 19 || c[1] >= lh - 19)) continue;
       const Eigen::Vector3d v = cam_->Unproject(px);
       const Eigen::Vector3d dir(Rwc[0] * v(0) + Rwc[1] * v(1) + Rwc[2] * v(2), Rwc[3] * v(0) + Rwc[4] * v(1) + Rwc[5] * v(2),
                                 Rwc[6] * v(0) + Rwc[7] * v(1) + Rwc[8] * v(2));
@@ -271,6 +278,8 @@ class Group {
         resident_(resident), rseqs_(resident ? n_seq : 0) {
     const int rc = sdvlb_ctx_create(device, &Config::Params(), &Config::CameraParams(), &ctx_);
     if (rc) throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_create failed: ") + sdvlb_last_error());
+    if (Config::UseORB() && sdvlb_ctx_set_orb(ctx_, 1))   // before any frame slot or sequence exists
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_set_orb failed: ") + sdvlb_last_error());
     if (timing) sdvlb_timing_enable(ctx_, 1);
     // current + prefetched + reference frame and a handful of live keyframes per sequence: no allocation while tracking
     if (sdvlb_ctx_reserve_frames(ctx_, 20 * n_seq))
@@ -474,8 +483,10 @@ class Group {
       (SE3::Exp(s.vel) * s.last_frame->GetPose()).ToArray(j.T_cur);   // sdvl.cc:278-281
       s.last_frame->GetPose().ToArray(j.T_ref);
       ImageAlign::CollectFeatures(s.last_frame, &s.feats);
-      s.fa->CollectCandidates(s.frame_counter, s.last_frame, false, &s.cands, &s.cand_points);
+      s.fa->CollectCandidates(s.frame_counter, s.last_frame, false, &s.cands, &s.cand_points,
+                              Config::UseORB() ? &s.cand_descs : nullptr);
       s.matches.resize(s.cands.size());
+      j.cand_desc = Config::UseORB() ? s.cand_descs.data() : nullptr;
       j.ref = s.last_frame->Handle();
       j.feats = s.feats.data();
       j.n_feats = int(s.feats.size());
@@ -937,7 +948,8 @@ const char* sdvlh_last_error(void) { return g_host_error.c_str(); }
 
 // Config is process-wide in the reference (singleton, config.h:56); set it before creating trackers.
 void sdvlh_config_set(const sdvlb_params* p, const sdvlb_camera* cam) { sdvl::Config::Set(*p, *cam); }
-// FeatureAlign::SelectInliers / OptimizePose of the class-API path on the device (1) or on the host (0, default).
+// Config::UseORB() for the trackers / frames created from now on (contexts pick it up when they are created)
+void sdvlh_config_set_orb(int on) { sdvl::Config::SetUseORB(on != 0); }
 
 // A context of its own for the test hooks below (the process-wide default context keeps the camera it was made with).
 struct HookContext {
@@ -945,6 +957,8 @@ struct HookContext {
   HookContext() {
     if (sdvlb_ctx_create(0, &sdvl::Config::Params(), &sdvl::Config::CameraParams(), &ctx))
       throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_create failed: ") + sdvlb_last_error());
+    if (sdvl::Config::UseORB() && sdvlb_ctx_set_orb(ctx, 1))
+      throw std::runtime_error(std::string("sdvl-b200: sdvlb_ctx_set_orb failed: ") + sdvlb_last_error());
     sdvl::Device::SetCurrent(ctx);
   }
   ~HookContext() {

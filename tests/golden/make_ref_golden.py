@@ -82,6 +82,32 @@ def compute(impl, sw, scenes, abi):
         t.close()
         out["traj_%s_poses" % name] = est
         out["traj_%s_stats" % name] = np.ascontiguousarray(stats[:, STAT_COLS])
+    # ---- ORB descriptor mode (Config::UseORB()): corners with the ORB margin, the descriptor of every corner of a
+    # frame (Frame::descriptors_), whole trajectories with SearchPoint scored by descriptor distance
+    set_orb = impl.lib().ref_set_orb if is_ref else impl.lib().orc_set_orb
+    orb_desc = impl.lib().ref_orb_descriptors if is_ref else impl.lib().orc_orb_descriptors
+    set_orb(1)
+    try:
+        cfg, poses, imgs = sw.sequence("C2", 0, 1)
+        P = cfg["params"]
+        h, w = imgs[0].shape
+        xyl, _ = impl.detect(P, imgs[0], P.num_features)
+        xc = np.ascontiguousarray(xyl, np.int32)
+        d = np.zeros((len(xc), 32), np.uint8)
+        ang = np.zeros(len(xc), np.float32)
+        assert orb_desc(C.byref(P), abi.ptr(imgs[0]), w, h, abi.ptr(xc), len(xc), abi.ptr(d), abi.ptr(ang)) == 0
+        out["orb_C2_corners"] = xc
+        out["orb_C2_desc"] = d
+        out["orb_C2_angle"] = ang
+        for name, seed, n in (("C2", 9, 30), ("C3", 5, 30)):
+            cfg, poses, imgs = sw.sequence(name, seed, n)
+            t = impl.Tracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], 20)
+            est, stats, _ = t.run(imgs, poses)
+            t.close()
+            out["orbtraj_%s_poses" % name] = est
+            out["orbtraj_%s_stats" % name] = np.ascontiguousarray(stats[:, STAT_COLS])
+    finally:
+        set_orb(0)
     return out
 
 
