@@ -11,6 +11,7 @@
 //                      levels into Frame::corners_ order.
 #include <algorithm>
 
+#include <cstdio>
 #include "common.cuh"
 #include "select_warp.cuh"
 
@@ -19,8 +20,8 @@ namespace {
 constexpr int DET_WARPS = 4;          // one warp per 32x32 cell, no block-level synchronisation at all
 constexpr int DET_THREADS = DET_WARPS * 32;
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_SMEM_KEYS = 4096;   // level-wide retainBest runs in shared memory up to this many keypoints
-constexpr int SEL_PART_CELLS = 64;    // cells of one level per CTA of the selection kernel (8 per warp)
+constexpr int SEL_SMEM_KEYS = 2048;   // level-wide retainBest runs in shared memory up to this many keypoints
+constexpr int SEL_PART_CELLS = 32;    // cells of one level per CTA of the selection kernel (4 per warp)
 constexpr int TSE = 40;               // score tile row stride in 16-bit elements
 constexpr int TSW = TSE / 2;          // ... in 32-bit words (one word = one horizontally adjacent pixel pair)
 // Pixel tile row stride in words: 45 = 13 (mod 32), so the 13 + 13 + 6 pairs of three consecutive tile rows that one warp
@@ -309,6 +310,13 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = B.scratch_base + blockIdx.y;   // index into the scratch arrays
+#ifdef SDVLB_SELECT_DEBUG
+  unsigned long long t_dbg[12];
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_dbg[0]));
+#define SEL_MARK(k) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_dbg[k]))
+#else
+#define SEL_MARK(k)
+#endif
   int level = 0;
   while (level + 1 < A.n_fast_levels && int(blockIdx.x) >= A.part_off[level + 1]) level++;
   const int part = int(blockIdx.x) - A.part_off[level];
@@ -347,6 +355,7 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
     cells_left = block_sum<int>(cl, s_tmp);
   }
   __syncthreads();
+  SEL_MARK(1);
 
   // ---- per-cell retainBest (fast_detector.cc:138-140): warp w takes cells c0 + w, c0 + w + 8, ... of this part.  The
   // keypoints of the warp's NEXT cell are fetched (into registers) while the current one is being selected.
@@ -390,11 +399,21 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   }
 
   // ---- last CTA of this (level, frame): level list + level-wide retainBest
+  SEL_MARK(2);
   __threadfence();
   __syncthreads();
+  SEL_MARK(3);
   if (tid == 0) s_ticket = atomicAdd(&tickets[frame * SDVLB_TICKET_STRIDE + 1 + level], 1);
   __syncthreads();
+#ifdef SDVLB_SELECT_DEBUG
+  if (s_ticket != n_parts - 1) {
+    if (false)
+      printf("sel part %d lvl %d: waterfill %llu cells(+barrier) %llu ns (start %llu)\n", int(blockIdx.x), level,
+             t_dbg[1] - t_dbg[0], t_dbg[3] - t_dbg[1], t_dbg[0] % 1000000ull);
+  }
+#endif
   if (s_ticket != n_parts - 1) return;
+  SEL_MARK(7);
   __threadfence();
   if (tid == 0) tickets[frame * SDVLB_TICKET_STRIDE + 1 + level] = 0;
   int* kept_of = nleft;   // kept count, then its exclusive scan (the water-filling state is no longer needed)
@@ -402,7 +421,9 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   __syncthreads();
   for (int c = tid; c < ncells; c += SEL_THREADS) nsel[c] = kept_of[c];   // counts, kept beside their offsets
   __syncthreads();
+  SEL_MARK(8);
   block_exclusive_scan(kept_of, ncells, s_tmp);
+  SEL_MARK(9);
   const int total = kept_of[ncells];
   uint32_t* __restrict__ lk = level_kp + size_t(frame) * A.level_kp_total + A.level_kp_off[level];
   uint32_t* const s_keys = reinterpret_cast<uint32_t*>(work);
@@ -414,49 +435,77 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   // ---- gather to the level list (fast_detector.cc:141-142): key = score<<22 | y<<11 | x (level coordinates)
   const int wc = A.g.wcells[level];
   if (fits) {
-    for (int c = tid; c < ncells; c += SEL_THREADS) {   // a thread per cell: its (few) loads are all in flight at once
-      const int k = nsel[c];
-      const uint32_t* src = cell_kp + size_t(cbase + c) * SDVLB_CELL_CAP;
-      const int ci = c / wc, cj = c - ci * wc;
-      for (int i = 0; i < k; i++) {
-        const uint32_t v = __ldcg(src + i);
-        const uint32_t key = ((v >> 10) << 22) | (uint32_t(ci * SDVLB_CELL + ((v >> 5) & 31)) << 11) |
-                             uint32_t(cj * SDVLB_CELL + (v & 31));
-        if (use_smem) s_keys[kept_of[c] + i] = key;
-        else lk[kept_of[c] + i] = key;
+    // a thread per survivor: its cell is found by bisection of the scanned offsets (shared memory), so every global
+    // load of the level is in flight at once (a thread per cell walked its survivors one L2 round trip at a time)
+    for (int j = tid; j < total; j += SEL_THREADS) {
+      int lo = 0, hi = ncells;   // largest c with kept_of[c] <= j; cells without survivors share an offset with the
+      while (hi - lo > 1) {      // next one and lose the bisection to it
+        const int mid = (lo + hi) >> 1;
+        if (kept_of[mid] <= j) lo = mid; else hi = mid;
       }
+      const int c = lo, i = j - kept_of[c];
+      const uint32_t v = __ldcg(cell_kp + size_t(cbase + c) * SDVLB_CELL_CAP + i);
+      const int ci = c / wc, cj = c - ci * wc;
+      const uint32_t key = ((v >> 10) << 22) | (uint32_t(ci * SDVLB_CELL + ((v >> 5) & 31)) << 11) |
+                           uint32_t(cj * SDVLB_CELL + (v & 31));
+      if (use_smem) s_keys[j] = key;
+      else lk[j] = key;
     }
   }
   __syncthreads();
 
   // ---- level-wide retainBest (fast_detector.cc:146-148): warp 0 in shared memory; one thread on the global list when
   // the level holds more than SEL_SMEM_KEYS candidates
+  SEL_MARK(4);
   int fin = fits ? total : 0;
   if (fits && total > nfeatures) {
     if (use_smem) {
+      // one warp, in shared memory (a CTA-wide variant of the two-sided passes, select_warp.cuh, measured slower: 11.7
+      // instead of 8.9 us on 440 keypoints -- two block barriers per 256 elements cost more than walking 32 at a time)
       if (warp == 0) {
         const int f2 = sdvlb_sel::warp_retain_best<22, uint16_t>(s_keys, total, nfeatures, s_pos);
         if (lane == 0) s_final = f2;
       }
-    } else if (tid == 0) {
-      s_final = sdvlb_sel::retain_best<22>(lk, total, nfeatures);
+      __syncthreads();
+      fin = s_final;
+    } else {
+      if (tid == 0) s_final = sdvlb_sel::retain_best<22>(lk, total, nfeatures);
+      __syncthreads();
+      fin = s_final;
     }
-    __syncthreads();
-    fin = s_final;
   }
   if (use_smem)
     for (int i = tid; i < fin; i += SEL_THREADS) lk[i] = s_keys[i];
   if (tid == 0) level_cnt[frame * SDVLB_MAX_LEVELS + level] = fin;
 
   // ---- last CTA of this frame concatenates the levels (fast_detector.cc:150-151,170-173)
+  SEL_MARK(5);
   __threadfence();
   __syncthreads();
   if (tid == 0) s_ticket = atomicAdd(&tickets[frame * SDVLB_TICKET_STRIDE], 1);
   __syncthreads();
+#ifdef SDVLB_SELECT_DEBUG
+  if (false)
+    printf("sel LAST of lvl %d (part %d): waterfill %llu cells %llu wait %llu gather %llu retain %llu ns, total %d nfeat %d (start %llu end %llu)\n",
+           level, int(blockIdx.x), t_dbg[1] - t_dbg[0], t_dbg[2] - t_dbg[1], t_dbg[3] - t_dbg[2], t_dbg[4] - t_dbg[3],
+           t_dbg[5] - t_dbg[4], total, nfeatures, t_dbg[0] % 1000000ull, t_dbg[5] % 1000000ull);
+#endif
   if (s_ticket != A.n_fast_levels - 1) return;
   __threadfence();
   const FrameDev& fr = B.f[blockIdx.y];
   int4* const mirror = reinterpret_cast<int4*>(fr.host_mirror);   // header at [0], records from [1]
+  // The same pass feeds the spatial index of the matcher (a counting sort of the corner indices by 32-px cell of their
+  // level-0 position; the level-0 FAST grid has at most max_cells cells, so nleft / nsel are free to hold the counts):
+  // a corner's cell is counted while its record is written and kept in shared memory for the scatter.
+  const int gw = A.g.wcells[0], gcells = gw * A.g.hcells[0];
+  int32_t* const start = fr.grid;
+  int32_t* const cursor = fr.grid + gcells + 1;
+  int32_t* const item = cursor + gcells;
+  int* const s_cnt = nleft;    // count, then running cursor
+  uint16_t* const s_cell = reinterpret_cast<uint16_t*>(work);
+  constexpr int kCellSmem = SEL_SMEM_KEYS * 4;   // corners whose cell fits in the work area
+  for (int i = tid; i <= gcells; i += SEL_THREADS) s_cnt[i] = 0;
+  __syncthreads();
   int base = 0;
   for (int l = 0; l < A.n_fast_levels; l++) {
     const int n = *reinterpret_cast<volatile int32_t*>(&level_cnt[frame * SDVLB_MAX_LEVELS + l]);
@@ -467,9 +516,13 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
     }
     for (int i = tid; i < n; i += SEL_THREADS) {
       const uint32_t key = __ldcg(src + i);
-      const int4 rec = make_int4(int32_t(key & 2047), int32_t((key >> 11) & 2047), l, int32_t(key >> 22));
+      const int x = int(key & 2047), y = int((key >> 11) & 2047);
+      const int4 rec = make_int4(x, y, l, int32_t(key >> 22));
       fr.corners[base + i] = rec;
       if (mirror && base + i < fr.mirror_cap) mirror[1 + base + i] = rec;
+      const int cell = ((y << l) >> 5) * gw + ((x << l) >> 5);
+      if (base + i < kCellSmem) s_cell[base + i] = uint16_t(cell);
+      atomicAdd(&s_cnt[cell], 1);
     }
     base += n;
   }
@@ -477,21 +530,6 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
     *fr.n_corners = base;
     if (mirror) mirror[0] = make_int4(base, 0, 0, 0);
     tickets[frame * SDVLB_TICKET_STRIDE] = 0;
-  }
-
-  // ---- spatial index for the matcher: counting sort of the corner indices by 32-px cell of their level-0 position,
-  // counted and scanned in shared memory (the level-0 FAST grid has at most max_cells cells: nleft / nsel are free)
-  const int gw = A.g.wcells[0], gcells = gw * A.g.hcells[0];
-  int32_t* const start = fr.grid;
-  int32_t* const cursor = fr.grid + gcells + 1;
-  int32_t* const item = cursor + gcells;
-  int* const s_cnt = nleft;    // count, then running cursor
-  __syncthreads();
-  for (int i = tid; i <= gcells; i += SEL_THREADS) s_cnt[i] = 0;
-  __syncthreads();
-  for (int i = tid; i < base; i += SEL_THREADS) {
-    const int4 c = fr.corners[i];
-    atomicAdd(&s_cnt[((c.y << c.z) >> 5) * gw + ((c.x << c.z) >> 5)], 1);
   }
   __syncthreads();
   block_exclusive_scan(s_cnt, gcells, s_tmp);
@@ -503,9 +541,19 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   // (the order of a cell's items is arbitrary: SearchPoint keeps the minimum of (score, corner index), which is what
   // the reference's in-order scan yields)
   for (int i = tid; i < base; i += SEL_THREADS) {
-    const int4 c = fr.corners[i];
-    item[atomicAdd(&s_cnt[((c.y << c.z) >> 5) * gw + ((c.x << c.z) >> 5)], 1)] = i;
+    int cell;
+    if (i < kCellSmem) cell = s_cell[i];
+    else { const int4 c = fr.corners[i]; cell = ((c.y << c.z) >> 5) * gw + ((c.x << c.z) >> 5); }
+    item[atomicAdd(&s_cnt[cell], 1)] = i;
   }
+#ifdef SDVLB_SELECT_DEBUG
+  SEL_MARK(6);
+  if (tid == 0)
+    printf("sel LAST of frame %d (lvl %d, part %d): waterfill %llu cells %llu wait %llu gather %llu retain %llu concat+index %llu ns, span of this CTA %llu ns (start %llu end %llu) [ticket %llu loads %llu scan %llu gather %llu]\n",
+           int(blockIdx.y), level, int(blockIdx.x), t_dbg[1] - t_dbg[0], t_dbg[2] - t_dbg[1], t_dbg[3] - t_dbg[2], t_dbg[4] - t_dbg[3], t_dbg[5] - t_dbg[4],
+           t_dbg[6] - t_dbg[5], t_dbg[6] - t_dbg[0], t_dbg[0] % 1000000ull, t_dbg[6] % 1000000ull, t_dbg[7] - t_dbg[3],
+           t_dbg[8] - t_dbg[7], t_dbg[9] - t_dbg[8], t_dbg[4] - t_dbg[9]);
+#endif
 }
 
 }  // namespace

@@ -492,6 +492,18 @@ int sdvlb_seq_track_collect(sdvlb_ctx* c, sdvlb_seq_result* results) {
       s->kf_state[k] = R->kf_live[k] > 0 ? 3 : 0;
     }
     c->d2h_bytes += int64_t(sizeof(SeqResultHost)) + int64_t(o.n_feats) * int64_t(sizeof(sdvlb_seq_feat));
+    // With nothing else in flight the host now knows the sequence's feature count exactly (the list of an adopted
+    // frame is its found features) instead of the conservative max_matches: the next launch is sized for it (the
+    // ImageAlign kernel's shared-memory cache is 256 or 512 features, the search grid follows the bound).
+    if (c->seq_queue.empty() && R->quality != SDVLB_TRACKING_BAD) {
+      int nb = R->stats[7];
+      for (const SeqCmd& cmd : c->seq_cmds) {   // queued, not yet submitted
+        if (cmd.seq != reinterpret_cast<SeqState*>(s->d_block)) continue;
+        if (cmd.kind == SEQC_RESET) nb = 0;
+        else if (cmd.kind == SEQC_ADD_POINTS) nb += cmd.n;
+      }
+      s->n_bound = std::min(s->max_feats, nb);
+    }
   }
   return 0;
 }
