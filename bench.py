@@ -593,7 +593,7 @@ def main():
         assert np.array_equal(est_p, est_v), "pageable and pinned inputs must be the same computation"
         e2e_pageable = {"value": total_frames / p_sec, "unit": "frames/s", "ms_per_step": p_sec / K * 1e3,
                         "h2d_bytes_per_step": cnt_p[1] / K,
-                        "source": "pageable host memory (numpy), one cudaMemcpyAsync per frame inside sdvlb_frames_submit"}
+                        "source": "pageable host memory (numpy): sdvlb_frames_submit copies it into the context's pinned staging sets (calling threads, non-temporal stores) and uploads from there"}
         del pageable
         # the reference's real deployment is ONE camera (main.cc:126-159): latency of a single sequence through the same
         # API (frames in pinned host memory, one group, results read back), and with the frames already in HBM

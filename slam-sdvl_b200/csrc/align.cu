@@ -25,6 +25,8 @@
 // `cap` features (256 or 512, chosen by the launcher); features beyond that use the same layout in global scratch.
 // Quirks kept: sticky visible_fts_/patch_cache_ across levels with J zeroed per level, stop_/chi2_ never reset,
 // fx used for both Jacobian rows, chi2 compared as float(chi2)/float(n_meas).
+#include <cstdlib>
+
 #include "seq.cuh"
 
 namespace {
@@ -755,7 +757,11 @@ __global__ void __launch_bounds__(AL_THREADS, 1) seq_align_kernel(const __grid_c
 // Features cached in shared memory: 256 (85 KB) covers the tracking configurations of the reference (at most
 // max(max_matches, points per keyframe) features per frame); 512 (170 KB) is used when the caller's bound is larger.
 // More features than that still work (global scratch), more slowly.
-int align_cap_for(int n_bound) { return n_bound <= 256 ? 256 : 512; }
+int align_cap_for(int n_bound) {
+  static const int forced = [] { const char* e = getenv("SDVLB_ALIGN_CAP"); return e ? atoi(e) : 0; }();   // experiment knob
+  if (forced == 256 || forced == 512) return forced;
+  return n_bound <= 256 ? 256 : 512;
+}
 
 }  // namespace
 

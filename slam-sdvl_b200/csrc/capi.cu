@@ -15,6 +15,9 @@
 #include <string>
 #include <vector>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include "common.cuh"
 
 // ---- kernel launchers (other translation units)
@@ -331,6 +334,28 @@ cudaError_t shared_upload_stream(int device, int prio, cudaStream_t* out, std::m
   return cudaSuccess;
 }
 
+// Copy into a pinned staging slot (256-byte aligned) with non-temporal stores: the destination is read next by the GPU
+// over PCIe, never by this core, so it should neither be fetched for ownership nor displace the cache.
+static void stream_copy(uint8_t* dst, const uint8_t* src, size_t bytes) {
+#if defined(__SSE2__)
+  size_t i = 0;
+  for (; i + 64 <= bytes; i += 64) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+    const __m128i b2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+    const __m128i c2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+    const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b2);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c2);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+  }
+  if (i < bytes) memcpy(dst + i, src + i, bytes - i);
+  _mm_sfence();
+#else
+  memcpy(dst, src, bytes);
+#endif
+}
+
 // Enqueues level-0 upload + pyramid (+ FAST + selection) for n frames on `stream`, in chunks of SDVLB_BATCH_MAX.
 // image_loc: 0 host memory of any kind (one cudaMemcpyAsync per frame), 1 device memory, 2 pinned device-visible host
 // memory (both uploaded by one kernel per chunk).
@@ -380,12 +405,44 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
         Iraw.src[i] = slot;
       }
     }
+    // Pageable host images (the reference hands cv::Mat data to Frame::Frame): copied by the calling thread into a
+    // pinned, device-visible staging set of the context and then uploaded like pinned images, by the same kernel.
+    // (cudaMemcpyAsync from pageable memory is staged by the driver one frame at a time, synchronously: 9.6 GB/s for
+    // the whole process however many threads submit, profiles/r02_a_bench_C2.json e2e_pageable.)
+    int stage_set = -1;
+    if (!by_kernel && !getenv("SDVLB_PAGEABLE_MEMCPY")) {
+      stage_set = c->stage_next;
+      c->stage_next = (c->stage_next + 1) % kStageSets;
+      const size_t slot_bytes = (img_bytes + 255) & ~size_t(255);
+      if (c->stage_cap[stage_set] < size_t(m) * slot_bytes) {
+        if (c->stage_used[stage_set]) SDVLB_CUDA_TRY(cudaEventSynchronize(c->stage_done[stage_set]));
+        if (c->stage[stage_set]) cudaFreeHost(c->stage[stage_set]);
+        c->stage[stage_set] = nullptr; c->stage_cap[stage_set] = 0;
+        SDVLB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->stage[stage_set]), size_t(m) * slot_bytes, cudaHostAllocDefault));
+        c->stage_cap[stage_set] = size_t(m) * slot_bytes;
+        if (!c->stage_done[stage_set]) SDVLB_CUDA_TRY(cudaEventCreateWithFlags(&c->stage_done[stage_set], cudaEventDisableTiming));
+        c->stage_used[stage_set] = false;
+      }
+      if (c->stage_used[stage_set]) SDVLB_CUDA_TRY(cudaEventSynchronize(c->stage_done[stage_set]));   // its last upload has read it
+      for (int i = 0; i < m; i++) {
+        if (image_loc[base + i] != 0) continue;
+        uint8_t* dst = c->stage[stage_set] + size_t(i) * slot_bytes;
+        stream_copy(dst, I.src[i], img_bytes);
+        I.src[i] = dst;
+      }
+      by_kernel = true;
+      all_device = false;
+    }
     // launch + event record are one unit on the shared upload stream
     std::unique_lock<std::mutex> ulock;
     if (ustream != stream && c->umutex) ulock = std::unique_lock<std::mutex>(*c->umutex);
     if (by_kernel) {
       SDVLB_CUDA_TRY(sdvlb_launch_upload(Bup, I, int(img_bytes), all_device, ustream));
       c->n_launches += 1;
+      if (stage_set >= 0) {
+        SDVLB_CUDA_TRY(cudaEventRecord(c->stage_done[stage_set], ustream));
+        c->stage_used[stage_set] = true;
+      }
     } else {
       // copy engine into level 0 of the frame slots; with distortion set the raw pixels then move on to the scratch
       // set through the device-to-device path of the upload kernel (level 0 is rewritten by the undistortion)
@@ -813,6 +870,10 @@ int sdvlb_ctx_destroy(sdvlb_ctx* c) {
   for (int i = 0; i < kBuildEvents; i++) if (c->uevents[i]) cudaEventDestroy(c->uevents[i]);
   if (c->ustream) cudaStreamSynchronize(c->ustream);   // shared by the contexts of the device: never destroyed
   if (c->orb_buf) cudaFree(c->orb_buf);
+  for (int i = 0; i < kStageSets; i++) {
+    if (c->stage[i]) cudaFreeHost(c->stage[i]);
+    if (c->stage_done[i]) cudaEventDestroy(c->stage_done[i]);
+  }
   if (c->d_seeds) cudaFree(c->d_seeds);
   if (c->h_seeds) cudaFreeHost(c->h_seeds);
   if (c->raw_scratch) cudaFree(c->raw_scratch);
@@ -898,6 +959,7 @@ int sdvlb_timing_read(sdvlb_ctx* c, double ms[SDVLB_K_COUNT], int64_t launches[S
 
 // ---------------------------------------------------------------------------------------------- tracking batches
 int sdvlb_track_batch(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, int mirror) {
+  SDVLB_RANGE("sdvlb.track_batch");
   bool build = false;
   const int rc = check_track_args(ctx, jobs, n_jobs, w, h, &build);
   if (rc) return rc;
@@ -905,6 +967,7 @@ int sdvlb_track_batch(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, 
 }
 
 int sdvlb_track_submit(sdvlb_ctx* ctx, sdvlb_track_job* jobs, int n_jobs, int w, int h, int mirror) {
+  SDVLB_RANGE("sdvlb.track_submit");
   bool build = false;
   int rc = check_track_args(ctx, jobs, n_jobs, w, h, &build);
   if (rc) return rc;
@@ -920,6 +983,7 @@ int sdvlb_track_poll(sdvlb_ctx* ctx) {
 }
 
 int sdvlb_track_collect(sdvlb_ctx* ctx) {
+  SDVLB_RANGE("sdvlb.track_collect");
   if (!ctx) return sdvlb_set_error(SDVLB_ERR_ARG, "null context");
   return collect_batch(ctx);
 }
@@ -927,6 +991,7 @@ int sdvlb_track_collect(sdvlb_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------- frame batches
 int sdvlb_frames_submit(sdvlb_ctx* c, const uint8_t* const* images, int n, int images_on_device, int want_corners,
                         int nfeatures, sdvlb_frame** out) {
+  SDVLB_RANGE("sdvlb.frames_submit");
   if (!c || !images || !out || n <= 0) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
   if (images_on_device < 0 || images_on_device > 2) return sdvlb_set_error(SDVLB_ERR_ARG, "bad image location");
   for (int i = 0; i < n; i++)
@@ -957,6 +1022,7 @@ int sdvlb_frames_submit(sdvlb_ctx* c, const uint8_t* const* images, int n, int i
 }
 
 int sdvlb_frames_wait(sdvlb_ctx* c, sdvlb_frame* const* frames, int n) {
+  SDVLB_RANGE("sdvlb.frames_wait");
   if (!c || (n > 0 && !frames)) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
   for (int i = 0; i < n; i++) {
     const int rc = ensure_built(frames[i]);
@@ -968,6 +1034,7 @@ int sdvlb_frames_wait(sdvlb_ctx* c, sdvlb_frame* const* frames, int n) {
 // ---------------------------------------------------------------------------------------------- Frame
 int sdvlb_frame_create(sdvlb_ctx* ctx, const uint8_t* img, int w, int h, int stride, int want_corners, int nfeatures,
                        sdvlb_frame** out) {
+  SDVLB_RANGE("sdvlb.frame_create");
   if (!ctx || !img || !out) return sdvlb_set_error(SDVLB_ERR_ARG, "null argument");
   if (w != ctx->w || h != ctx->h) return sdvlb_set_error(SDVLB_ERR_ARG, "image size differs from the context camera");
   std::vector<uint8_t> packed;
@@ -1094,6 +1161,7 @@ int sdvlb_frame_destroy(sdvlb_ctx* ctx, sdvlb_frame* f) {
 int sdvlb_image_align(sdvlb_ctx* ctx, const sdvlb_frame* ref, sdvlb_frame* cur, const sdvlb_align_feat* feats, int n,
                       const double T_ref[7], double T_cur[7], int fast, int* n_tracked, double* error,
                       sdvlb_gn_iter* trace, int trace_cap, int* trace_n, const sdvlb_gn_forced* forced) {
+  SDVLB_RANGE("sdvlb.image_align");
   if (!ctx || !ref || !cur || !T_ref || !T_cur || n < 0 || (n > 0 && !feats))
     return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
   if (trace_n) *trace_n = 0;
@@ -1120,6 +1188,7 @@ int sdvlb_image_align(sdvlb_ctx* ctx, const sdvlb_frame* ref, sdvlb_frame* cur, 
 
 int sdvlb_search_points(sdvlb_ctx* ctx, const sdvlb_frame* cur, const sdvlb_candidate* cands, int n,
                         const double T_cur[7], sdvlb_match* out) {
+  SDVLB_RANGE("sdvlb.search_points");
   if (!ctx || !cur || n < 0 || (n > 0 && (!cands || !out))) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
   const int rcb = ensure_built(const_cast<sdvlb_frame*>(cur));
   if (rcb) return rcb;
@@ -1176,6 +1245,7 @@ int sdvlb_undistort(sdvlb_ctx* c, const uint8_t* in, uint8_t* out) {
 // Map::UpdateCandidates (map.cc:397-498) for n seeds against `cur`: one upload, one kernel, one read-back.
 int sdvlb_update_candidates(sdvlb_ctx* c, const sdvlb_frame* cur, const double T_cur[7], sdvlb_seed* seeds, int n,
                             const sdvlb_seed_params* sp) {
+  SDVLB_RANGE("sdvlb.update_candidates");
   if (!c || !cur || !T_cur || !sp || n < 0 || (n > 0 && !seeds)) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
   int rc = ensure_built(const_cast<sdvlb_frame*>(cur));
   if (rc) return rc;

@@ -13,6 +13,18 @@
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// NVTX ranges around the entry points of the path (tracing): header-only NVTX v3, a couple of
+// loads per call unless a tool (Nsight Systems / Compute) is attached, in which case the ranges appear on the calling
+// thread's timeline: sdvlb.frames_submit, sdvlb.track_submit, sdvlb.track_collect, sdvlb.seq_track_submit, ...
+#include <nvtx3/nvToolsExt.h>
+struct SdvlbRange {
+  explicit SdvlbRange(const char* name) { nvtxRangePushA(name); }
+  ~SdvlbRange() { nvtxRangePop(); }
+  SdvlbRange(const SdvlbRange&) = delete;
+  SdvlbRange& operator=(const SdvlbRange&) = delete;
+};
+#define SDVLB_RANGE(name) SdvlbRange sdvlb_range_(name)
+
 struct Arena {   // bump allocator over a pinned host buffer and (optionally) a device buffer with identical layout
   uint8_t* h = nullptr;
   uint8_t* d = nullptr;
@@ -28,6 +40,7 @@ struct TimerSlot { cudaEvent_t a, b; int kind; };
 
 constexpr int kBuildEvents = 8;   // ring of "frame batch enqueued" events; a frame borrows the one of its batch
 constexpr int kSlabFrames = 32;
+constexpr int kStageSets = 4;     // staging sets for pageable host images
 
 struct BatchOut {   // per-job results in the `out` arena
   double pose[7];
@@ -106,6 +119,13 @@ struct sdvlb_ctx {
   int raw_next = 0;
   cudaEvent_t raw_done[kBuildEvents] = {};
   bool raw_used[kBuildEvents] = {};
+  // pageable host images: pinned, device-visible staging sets the calling thread copies into (one set per frame
+  // batch in flight; a set is reused once the event of its last upload has fired)
+  uint8_t* stage[4] = {};
+  size_t stage_cap[4] = {};
+  cudaEvent_t stage_done[4] = {};
+  bool stage_used[4] = {};
+  int stage_next = 0;
   bool use_orb = false;             // Config::UseORB(): ORB margins for FAST / FilterCorners, sdvlb_search_points_orb
   uint8_t* orb_buf = nullptr;       // device scratch of the ORB entry points (positions / descriptors / candidates)
   size_t orb_cap = 0;

@@ -120,6 +120,7 @@ static int pose_call(sdvlb_ctx* c, sdvlb_pose_obs* obs, int n, double T[7], sdvl
 }
 
 int sdvlb_select_inliers(sdvlb_ctx* ctx, sdvlb_pose_obs* obs, int n, const double T_frame[7], sdvlb_rand* rng) {
+  SDVLB_RANGE("sdvlb.select_inliers");
   if (!rng || !T_frame) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
   if (ctx && (ctx->params.max_ransac_its > 256 || ctx->params.max_ransac_points > 8))
     return sdvlb_set_error(SDVLB_ERR_ARG, "max_ransac_its <= 256 and max_ransac_points <= 8 are supported");
@@ -129,6 +130,7 @@ int sdvlb_select_inliers(sdvlb_ctx* ctx, sdvlb_pose_obs* obs, int n, const doubl
 }
 
 int sdvlb_optimize_pose(sdvlb_ctx* ctx, sdvlb_pose_obs* obs, int n, double T_frame[7]) {
+  SDVLB_RANGE("sdvlb.optimize_pose");
   return pose_call(ctx, obs, n, T_frame, nullptr, 1);
 }
 
@@ -268,6 +270,7 @@ int sdvlb_seq_release(sdvlb_ctx* c, sdvlb_seq* s) {
 
 int sdvlb_seq_add_points(sdvlb_ctx* c, sdvlb_seq* s, const sdvlb_frame* kf, const double T_kf[7],
                          const sdvlb_seq_point* pts, int n, int* kf_slot) {
+  SDVLB_RANGE("sdvlb.seq_add_points");
   if (!c || !s || !kf || !T_kf || n < 0 || (n > 0 && !pts)) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
   if (n > s->max_feats) return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "more points than the sequence's feature capacity");
   for (int k = 0; k < n; k++)
@@ -298,6 +301,7 @@ int sdvlb_seq_add_points(sdvlb_ctx* c, sdvlb_seq* s, const sdvlb_frame* kf, cons
 int sdvlb_seq_track_inflight(sdvlb_ctx* c) { return c ? int(c->seq_queue.size()) : 0; }
 
 int sdvlb_seq_track_submit(sdvlb_ctx* c, sdvlb_seq* const* seqs, sdvlb_frame* const* frames, int n) {
+  SDVLB_RANGE("sdvlb.seq_track_submit");
   if (!c || !seqs || !frames || n <= 0 || n > SDVLB_SEQ_BATCH)
     return sdvlb_set_error(SDVLB_ERR_ARG, "a sequence submission takes 1..64 sequences");
   if (c->pending.active) return sdvlb_set_error(SDVLB_ERR_STATE, "a tracking batch is still in flight on this context");
@@ -451,6 +455,7 @@ int sdvlb_seq_track_poll(sdvlb_ctx* c) {
 }
 
 int sdvlb_seq_track_collect(sdvlb_ctx* c, sdvlb_seq_result* results) {
+  SDVLB_RANGE("sdvlb.seq_track_collect");
   if (!c || !results) return sdvlb_set_error(SDVLB_ERR_ARG, "bad argument");
   if (c->seq_queue.empty()) return sdvlb_set_error(SDVLB_ERR_STATE, "nothing was submitted on this context");
   const SeqSubmission sub = std::move(c->seq_queue.front());
