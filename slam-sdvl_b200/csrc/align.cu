@@ -661,7 +661,12 @@ __device__ void align_core(const AlignView& J, const Src& src, const PyrGeom& G,
     level_break = S.ctrl[1] != 0;
   }
 
-  sdvlb_launch_dependents();   // the next kernel of the chain may be brought in; it waits for this grid to complete
+  // Programmatic dependent launch: the next kernel of the chain may be brought in; it waits for this grid to complete.
+  // The trigger stays at the END on purpose: raised when the last pyramid level starts (to hide the ~9 us between this
+  // kernel's end and the first SearchPoint CTA) it costs throughput -- 197 k instead of 223 k frames/s, A/B on one box
+  // -- because the ~850 SearchPoint CTAs of a group then sit in griddepcontrol.wait on SM slots that the frame-build
+  // kernels of the other groups need.
+  sdvlb_launch_dependents();
   if (tid == 0) {
     const DSE3 out = se3_mul(T, se3_load(T_ref));   // frame2_->SetPose(current_se3 * frame1_->GetPose())
     se3_store(out, J.out_pose);
