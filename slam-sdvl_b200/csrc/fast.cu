@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "select_warp.cuh"
 
@@ -595,6 +596,8 @@ cudaError_t sdvlb_launch_fast_cells(const FrameBatch& B, const FastPlan& plan, u
                                     cudaStream_t stream) {
   const FastArgs& A = plan.args;
   dim3 g1((A.g.total_cells + DET_WARPS - 1) / DET_WARPS, B.n);
+  // (Fewer FAST CTAs per SM, to leave room for the tracking kernels' CTAs, was tried with dynamic-memory padding: 5 -> 4
+  // -> 3 CTAs per SM makes this kernel 76 -> 84 -> 99 us and the whole step slower, 225 k -> 220 k -> 212 k frames/s.)
   SDVLB_PREPARE(fast_cells_kernel, 0);
   fast_cells_kernel<<<g1, DET_THREADS, 0, stream>>>(B, A, cell_kp, cell_cnt);
   return cudaGetLastError();
