@@ -219,8 +219,11 @@ class SequenceDriver {
     const int margin = Config::PatchSize() / 2 + 2;
     s->seeds.clear();
     const int before = n_points;
-    for (int i = 0; i < n && n_points < max_points_; i++) {
-      const int32_t* c = xyls + 4 * size_t((long long)i * 7919 % n);
+    // visiting order i * 7919 mod n, kept incrementally (this loop is on the critical path of the sequence's next frame)
+    const int stride = n > 0 ? 7919 % n : 0;
+    int at = 0;
+    for (int i = 0; i < n && n_points < max_points_; i++, at = (at + stride >= n ? at + stride - n : at + stride)) {
+      const int32_t* c = xyls + 4 * size_t(at);
       const int lw = int(cam_->GetWidth()) >> c[2], lh = int(cam_->GetHeight()) >> c[2];
       if (c[0] < margin || c[1] < margin || c[0] >= lw - margin || c[1] >= lh - margin) continue;
       const Eigen::Vector2d px(double(c[0] * (1 << c[2])), double(c[1] * (1 << c[2])));
