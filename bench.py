@@ -75,7 +75,7 @@ def ncu_summary_path():
 NCU_SUMMARY = ncu_summary_path()
 NCU_KERNELS = {"pyr_down_kernel": "pyramid", "pyr_tail_kernel": "pyramid", "fast_cells_kernel": "fast",
                "fast_select_kernel": "select", "seq_align_kernel": "align", "image_align_kernel": "align",
-               "search_seq_kernel": "search", "seq_post_kernel": "pose"}
+               "search_seq_kernel": "search", "seq_post_kernel": "pose", "orb_frames_kernel": "orb"}
 NCU_SEQS_PER_LAUNCH = 64
 
 
@@ -204,8 +204,8 @@ def algorithmic_bytes(cfg, kernel, stats_prev, stats_cur, n_corners=1000, kbar=3
         return int((levels * n_feat * 49 + iters * n_feat * 25 + 64 * n_feat).sum())
     if kernel == "search":
         return int((n_feat * (121 + 64 * kbar + 810)).sum())
-    if kernel == "prep":     # read the last frame's feature list (160 B each), write align features + candidates
-        return int((n_feat * (160 + 56 + 168)).sum())
+    if kernel == "orb":      # per corner: the radius-15 circular patch (709 bytes) + 32 descriptor bytes
+        return (709 + 32) * n_corners * len(stats_cur)
     if kernel == "pose":     # read matches (40 B) + features, write the new list, its host mirror and the obs arrays
         found = stats_cur[:, 1].astype(np.int64)
         return int((n_feat * (40 + 160)).sum() + (found * (160 + 32 + 7 * 8)).sum())
@@ -390,6 +390,9 @@ def main():
     ap.add_argument("--host-replay", action="store_true",
                     help="previous design: FeatureAlign bookkeeping + pose refinement on the host (for comparison)")
     ap.add_argument("--no-extras", action="store_true", help="skip the pageable / single-sequence / CPU legs")
+    ap.add_argument("--orb", action="store_true",
+                    help="Config::UseORB() (the mode every shipped cfg of the reference sets): FAST with the ORB margin, "
+                         "corner descriptors at frame construction, SearchPoint scored by descriptor distance; GPU arm only")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -490,7 +493,7 @@ def main():
         n_groups = min(n_groups, n)
         trk = binding.HostTracker(cfg["params"], cfg["cam"], sw.PLANE, cfg["n_feat"], args.kf_every, n, n_groups,
                                   device=local_rank, timing=timing, n_threads=min(n_groups, n_threads or threads),
-                                  resident=not args.host_replay)
+                                  resident=not args.host_replay, use_orb=args.orb)
         trk.set_prefetch(args.prefetch)
         if not args.host_replay:
             trk.set_depth(args.depth)
@@ -668,7 +671,8 @@ def main():
             "warmup": W, "ms_per_step": val_sec / K * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
             "value_runs": spread(val_all),
-            "config": {"workload": workload(args.config), "sequences_per_gpu": S, "sequences_total": S_total,
+            "config": {"workload": workload(args.config) + (" [ORB descriptor mode, use_orb: 1]" if args.orb else ""),
+                       "sequences_per_gpu": S, "sequences_total": S_total,
                        "step": "one new frame for every sequence of the GPU", "host_groups_per_gpu": ngroups,
                        "host_threads_per_gpu": min(ngroups, threads), "submissions_in_flight_per_group": args.depth,
                        "timed_blocks": f"{R} blocks of {K} steps per leg, each a fresh tracker (init + {W} warm-up "

@@ -109,7 +109,8 @@ int sdvlb_dev_upload(sdvlb_ctx* ctx, void* dst, const void* src, uint64_t bytes)
 /* ---- per-kernel timing (CUDA events on the context stream) -------------- */
 enum {
   SDVLB_K_PYRAMID = 0, SDVLB_K_FAST = 1, SDVLB_K_SELECT = 2, SDVLB_K_ALIGN = 3,
-  SDVLB_K_SEARCH = 4, SDVLB_K_PREP = 5, SDVLB_K_POSE = 6, SDVLB_K_COUNT = 7
+  SDVLB_K_SEARCH = 4, SDVLB_K_ORB = 5 /* corner descriptors of a frame batch (ORB mode) */, SDVLB_K_POSE = 6,
+  SDVLB_K_COUNT = 7
 };
 int sdvlb_timing_enable(sdvlb_ctx* ctx, int on);
 /* Accumulated milliseconds and launch counts per kernel since the last reset.

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdvl_b200.so")
 _LIB = None
 
-K_NAMES = ("pyramid", "fast", "select", "align", "search", "prep", "pose")
+K_NAMES = ("pyramid", "fast", "select", "align", "search", "orb", "pose")
 
 
 class SdvlbError(RuntimeError):

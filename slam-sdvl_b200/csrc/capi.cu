@@ -485,7 +485,9 @@ int enqueue_build(sdvlb_ctx* c, sdvlb_frame* const* frames, const uint8_t* const
       timer_end(c);
       c->n_launches += 2;
       if (c->use_orb) {   // Frame::descriptors_ for every corner, once (the reference fills them lazily)
+        timer_begin(c, SDVLB_K_ORB, stream);
         SDVLB_CUDA_TRY(sdvlb_launch_orb_frames(B, c->geom, c->params.pyramid_levels, c->corner_cap, stream));
+        timer_end(c);
         c->n_launches += 1;
       }
     }

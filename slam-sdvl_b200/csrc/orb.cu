@@ -22,29 +22,58 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_positions_kernel(const uin
   const int x = __ldg(xyl + 3 * i), y = __ldg(xyl + 3 * i + 1), l = __ldg(xyl + 3 * i + 2);
   uint32_t byte = 0;
   float deg = -1.f;
+  uint32_t pw[8];
+  orb_load_pattern(pw);
   if (l >= 0 && l < levels && x >= kOrbLimit && x < G.w[l] - kOrbLimit && y >= kOrbLimit && y < G.h[l] - kOrbLimit)
-    deg = orb_describe(pyr + G.off[l], G.w[l], x, y, &byte);
+    deg = orb_describe(pyr + G.off[l], G.w[l], x, y, &byte, pw);
   desc[size_t(i) * 32 + lane] = uint8_t(byte);
   if (angle && lane == 0) angle[i] = deg;
 }
 
 // Every corner of every frame of a build batch: Frame::descriptors_ (filled lazily by the reference, matcher.cc:265-269,
 // frame.cc:148-161; a descriptor is a function of the frame and the corner, so computing all of them when the frame is
-// built gives the same bytes).  grid (ORB_FRAME_CTAS, frames); the warps of a frame's CTAs stride over its corners.
+// built gives the same bytes).  grid (ORB_FRAME_CTAS, frames); a CTA takes chunks of ORB_CHUNK corners of its frame
+// through three phases: moments (a warp per corner), orientation + rotation (a THREAD per corner: the double-precision
+// cos / sin dominate the instruction count and are the same for all 32 lanes of a warp-per-corner design), rotated
+// tests (a warp per corner).
 constexpr int ORB_FRAME_CTAS = 32;
+constexpr int ORB_CHUNK = 32;
 __global__ void __launch_bounds__(ORB_WARPS * 32) orb_frames_kernel(const __grid_constant__ FrameBatch B,
                                                                      const __grid_constant__ PyrGeom G, int levels, int cap) {
+  __shared__ int s_m10[ORB_CHUNK], s_m01[ORB_CHUNK];
+  __shared__ float s_a[ORB_CHUNK], s_b[ORB_CHUNK];
   const FrameDev& f = B.f[blockIdx.y];
   if (!f.desc) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = min(*f.n_corners, cap);
-  for (int i = blockIdx.x * ORB_WARPS + (threadIdx.x >> 5); i < n; i += gridDim.x * ORB_WARPS) {
-    const int4 c = __ldg(f.corners + i);
-    uint32_t byte = 0;
-    if (c.z >= 0 && c.z < levels && c.x >= kOrbLimit && c.x < G.w[c.z] - kOrbLimit && c.y >= kOrbLimit &&
-        c.y < G.h[c.z] - kOrbLimit)
-      orb_describe(f.pyr + G.off[c.z], G.w[c.z], c.x, c.y, &byte);
-    reinterpret_cast<uint8_t*>(f.desc)[size_t(i) * 32 + lane] = uint8_t(byte);
+  uint32_t pw[8];
+  orb_load_pattern(pw);
+  for (int c0 = blockIdx.x * ORB_CHUNK; c0 < n; c0 += gridDim.x * ORB_CHUNK) {
+    const int m = min(ORB_CHUNK, n - c0);
+    for (int k = warp; k < m; k += ORB_WARPS) {
+      const int4 c = __ldg(f.corners + c0 + k);
+      int m10 = 0, m01 = 0;
+      const bool ok = c.z >= 0 && c.z < levels && c.x >= kOrbLimit && c.x < G.w[c.z] - kOrbLimit && c.y >= kOrbLimit &&
+                      c.y < G.h[c.z] - kOrbLimit;
+      if (ok) orb_moments(f.pyr + G.off[c.z] + size_t(c.y) * G.w[c.z] + c.x, G.w[c.z], m10, m01);
+      if (lane == 0) { s_m10[k] = m10; s_m01[k] = m01; }
+    }
+    __syncthreads();
+    if (int(threadIdx.x) < m) {
+      float a, b;
+      orb_angle(s_m10[threadIdx.x], s_m01[threadIdx.x], a, b);
+      s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+    }
+    __syncthreads();
+    for (int k = warp; k < m; k += ORB_WARPS) {
+      const int4 c = __ldg(f.corners + c0 + k);
+      const bool ok = c.z >= 0 && c.z < levels && c.x >= kOrbLimit && c.x < G.w[c.z] - kOrbLimit && c.y >= kOrbLimit &&
+                      c.y < G.h[c.z] - kOrbLimit;
+      uint32_t byte = 0;
+      if (ok) byte = orb_sample(f.pyr + G.off[c.z] + size_t(c.y) * G.w[c.z] + c.x, G.w[c.z], s_a[k], s_b[k], pw);
+      reinterpret_cast<uint8_t*>(f.desc)[size_t(c0 + k) * 32 + lane] = uint8_t(byte);
+    }
+    __syncthreads();
   }
 }
 

@@ -20,7 +20,22 @@ namespace sdvlb_orb {
 constexpr int kOrbHalf = 15;                 // Config::ORBSize() / 2, orb_size = 31
 constexpr int kOrbLimit = kOrbHalf + 4;      // ORBDetector::IsInsideLimits (extra/orb_detector.cc:439-446)
 // umax_ of ORBDetector::InitParameters (extra/orb_detector.cc:326-348) for a half patch of 15
-static __constant__ int8_t c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+// umax_ as 16 nibbles (entry v in bits 4v..4v+3): a table in constant memory would be read at a different address by every
+// lane, which the constant cache serialises
+constexpr unsigned long long kUmaxNibbles = 0x3689ABCDDEEEFFFFull;
+static_assert(((kUmaxNibbles >> 0) & 15) == 15 && ((kUmaxNibbles >> 16) & 15) == 14 && ((kUmaxNibbles >> 28) & 15) == 13 &&
+              ((kUmaxNibbles >> 36) & 15) == 12 && ((kUmaxNibbles >> 40) & 15) == 11 && ((kUmaxNibbles >> 44) & 15) == 10 &&
+              ((kUmaxNibbles >> 48) & 15) == 9 && ((kUmaxNibbles >> 52) & 15) == 8 && ((kUmaxNibbles >> 56) & 15) == 6 &&
+              ((kUmaxNibbles >> 60) & 15) == 3, "umax_ = {15,15,15,15,14,14,14,13,13,12,11,10,9,8,6,3}");
+
+// The 8 learned tests of descriptor byte `lane` (32 bytes of the pattern table) as 8 words, one test per word:
+// (x0, y0, x1, y1) signed bytes.  Two 16-byte loads per lane, a contiguous kilobyte per warp.  (The table used to live
+// in constant memory: 32 different addresses per load, serialised -- 486 us per 64 frames for orb_frames_kernel.)
+__device__ __forceinline__ void orb_load_pattern(uint32_t pw[8]) {
+  const uint4* __restrict__ pp = reinterpret_cast<const uint4*>(kOrbPattern31) + (threadIdx.x & 31) * 2;
+  const uint4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+  pw[0] = p0.x; pw[1] = p0.y; pw[2] = p0.z; pw[3] = p0.w; pw[4] = p1.x; pw[5] = p1.y; pw[6] = p1.z; pw[7] = p1.w;
+}
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {   // cv::fastAtan2 (atan_f32)
   const float scale = float(180.0 / 3.1415926535897932384626433832795);
@@ -50,43 +65,72 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {   // cv::fas
 
 // img: one pyramid level (stride = W); (x, y) inside the limits.  Every lane returns the orientation in degrees; lane
 // i returns descriptor byte i in *byte_out.
-__device__ __forceinline__ float orb_describe(const uint8_t* __restrict__ img, int W, int x, int y, uint32_t* byte_out) {
+// The three steps of a descriptor.  (1) intensity-centroid moments of the circular patch, by a warp; every lane
+// returns both sums.
+__device__ __forceinline__ void orb_moments(const uint8_t* __restrict__ center, int W, int& m10_out, int& m01_out) {
+  // lane u owns COLUMN u - 15: a warp-wide load reads one row of the patch (31 consecutive bytes, one or two sectors).
+  // With a lane per row every load touched 31 different rows -- 31 L1 wavefronts per instruction, ~960 per descriptor,
+  // which is what bounded the kernel.  The sums are integer, so any order gives the reference's value.
   const int lane = threadIdx.x & 31;
-  const uint8_t* __restrict__ center = img + size_t(y) * W + x;
-  int m10 = 0, m01 = 0;
-  if (lane < 2 * kOrbHalf + 1) {
-    const int v = lane - kOrbHalf;
-    const int d = c_umax[v < 0 ? -v : v];
-    const uint8_t* __restrict__ row = center + v * W;
-    int s = 0;
-    for (int u = -d; u <= d; ++u) {
-      const int val = __ldg(row + u);
-      m10 += u * val;
-      s += val;
-    }
-    m01 = v * s;
+  const int u = lane - kOrbHalf;
+  const int au = u < 0 ? -u : u;
+  // All 31 row loads are issued before the first one is used (they are independent; issued four at a time behind
+  // their own consumers they cost eight L2 round trips per descriptor).  Every address is inside the image: the corner
+  // is at least kOrbLimit = 19 pixels from the border, the loads reach 16.
+  int vals[2 * kOrbHalf + 1];
+#pragma unroll
+  for (int v = -kOrbHalf; v <= kOrbHalf; ++v) vals[v + kOrbHalf] = __ldg(center + v * W + u);
+  int col = 0, colv = 0;   // sum of the column's pixels inside the circle, and of v * pixel
+#pragma unroll
+  for (int v = -kOrbHalf; v <= kOrbHalf; ++v) {
+    const int d = int((kUmaxNibbles >> (4 * (v < 0 ? -v : v))) & 15ull);
+    const int val = au <= d ? vals[v + kOrbHalf] : 0;
+    col += val;
+    colv += v * val;
   }
-  m10 = int(__reduce_add_sync(0xffffffffu, unsigned(m10)));
-  m01 = int(__reduce_add_sync(0xffffffffu, unsigned(m01)));
+  m10_out = int(__reduce_add_sync(0xffffffffu, unsigned(u * col)));
+  m01_out = int(__reduce_add_sync(0xffffffffu, unsigned(colv)));
+}
+// (2) orientation in degrees (cv::fastAtan2) and the rotation (a, b) = (cos, sin) of it, by one thread: the double-
+// precision cos / sin are a few hundred fp64 instructions, which a warp should spend on 32 corners, not on one.
+__device__ __forceinline__ float orb_angle(int m10, int m01, float& a, float& b) {
   const float deg = fast_atan2_deg(float(m01), float(m10));
   const float factorPI = float(3.1415926535897932384626433832795 / 180.f);
   const float angle = float(double(deg) * double(factorPI));
-  const float a = float(cos(double(angle))), b = float(sin(double(angle)));
-  const signed char* pat = kOrbPattern31 + lane * 32;
-  uint32_t val = 0;
+  double sn, cs;
+  sincos(double(angle), &sn, &cs);
+  a = float(cs); b = float(sn);
+  return deg;
+}
+// (3) the 8 rotated tests of descriptor byte `lane`, by a warp.
+__device__ __forceinline__ uint32_t orb_sample(const uint8_t* __restrict__ center, int W, float a, float b, const uint32_t pw[8]) {
+  int t[16];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    int t[2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-      const float px = float(pat[4 * k + 2 * j]), py = float(pat[4 * k + 2 * j + 1]);
+      const float px = float(int(int8_t(pw[k] >> (16 * j)))), py = float(int(int8_t(pw[k] >> (16 * j + 8))));
       const float r = __fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a));
       const float c = __fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b));
-      t[j] = __ldg(center + __float2int_rn(r) * W + __float2int_rn(c));
+      t[2 * k + j] = __ldg(center + __float2int_rn(r) * W + __float2int_rn(c));
     }
-    val |= uint32_t(t[0] < t[1]) << k;
   }
-  *byte_out = val;
+  uint32_t val = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) val |= uint32_t(t[2 * k] < t[2 * k + 1]) << k;
+  return val;
+}
+
+// img: one pyramid level (stride = W); (x, y) inside the limits.  Every lane returns the orientation in degrees; lane
+// i returns descriptor byte i in *byte_out.  (All three steps by one warp: positions lists, single features.)
+__device__ __forceinline__ float orb_describe(const uint8_t* __restrict__ img, int W, int x, int y, uint32_t* byte_out,
+                                              const uint32_t pw[8]) {
+  const uint8_t* __restrict__ center = img + size_t(y) * W + x;
+  int m10, m01;
+  orb_moments(center, W, m10, m01);
+  float a, b;
+  const float deg = orb_angle(m10, m01, a, b);
+  *byte_out = orb_sample(center, W, a, b, pw);
   return deg;
 }
 
@@ -110,8 +154,11 @@ __device__ __forceinline__ uint32_t orb_feature_word(const uint8_t* __restrict__
   const int x = int(px0 / double(1 << level)), y = int(px1 / double(1 << level));
   uint32_t byte = 0;
   if (level >= 0 && level < G.levels && x >= kOrbLimit && x < G.w[level] - kOrbLimit && y >= kOrbLimit &&
-      y < G.h[level] - kOrbLimit)
-    orb_describe(pyr + G.off[level], G.w[level], x, y, &byte);
+      y < G.h[level] - kOrbLimit) {
+    uint32_t pw[8];
+    orb_load_pattern(pw);
+    orb_describe(pyr + G.off[level], G.w[level], x, y, &byte, pw);
+  }
   return orb_word_of_bytes(byte);
 }
 
