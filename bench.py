@@ -473,14 +473,17 @@ def main():
         dst = torch.empty(n, dtype=torch.uint8, device="cuda")
         dst.copy_(src, non_blocking=True)
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(4):
-            dst.copy_(src, non_blocking=True)
-        ev1.record()
-        torch.cuda.synchronize()
-        sec = sharding.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
-        return 4 * n / sec / 1e9
+        best = 0.0
+        for _ in range(5):   # the best of five passes: single passes of this measurement spread from 41 to 55 GB/s
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            sec = sharding.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+            best = max(best, 4 * n / sec / 1e9)
+        return best
 
     pcie_gbs = pcie_h2d_gbs()
 
@@ -636,7 +639,7 @@ def main():
                                "frac_at_value": alg_all / (val_sec / K) / 1e9 / peak},
                 "pcie": {"h2d_gbs_per_gpu_achieved": cnt_e[1] / e2e_sec / 1e9, "h2d_gbs_per_gpu_peak": pcie_gbs,
                          "frac": cnt_e[1] / e2e_sec / 1e9 / pcie_gbs,
-                         "peak_source": "pinned cudaMemcpyAsync 4 x 256 MB, all ranks at once, slowest rank",
+                         "peak_source": "pinned cudaMemcpyAsync 4 x 256 MB, all ranks at once, slowest rank, best of 5 passes",
                          "frames_per_s_at_peak": pcie_gbs * 1e9 / frame_bytes * world}}
     us_per_gn_iter = ktimes["align"][0] * 1e3 / max(1, gn_iters) * S   # one CTA per sequence runs its own GN loop
 

@@ -141,130 +141,4 @@ __device__ __forceinline__ int warp_retain_best(uint32_t* __restrict__ a, int si
   return n_points + nr;
 }
 
-// ---- the same algorithms by a whole CTA (blockDim.x threads, a multiple of 32, at most 1024): the level-wide
-// retainBest runs over a few hundred to a few thousand keypoints, where one warp spends its time walking the range 32
-// elements at a time.  s_w: shared scratch of 64 ints.  Every thread must call; results are uniform.
-template <int SHIFT, typename P, typename FL, typename FR>
-__device__ __forceinline__ int cta_two_sided(uint32_t* __restrict__ a, int lo, int hi, FL stopL, FR stopR,
-                                             P* __restrict__ pos, int& nl, int& nr, int* __restrict__ s_w) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
-  const unsigned lt = (1u << lane) - 1u;
-  const int m = hi - lo;
-  P* const Lp = pos;
-  P* const Ra = pos + m;
-  nl = 0; nr = 0;
-  for (int base = lo; base < hi; base += nt) {
-    const int i = base + tid;
-    const bool valid = i < hi;
-    const uint32_t r = valid ? (a[i] >> SHIFT) : 0u;
-    const bool isL = valid && stopL(r), isR = valid && stopR(r);
-    const unsigned bl = __ballot_sync(0xffffffffu, isL), br = __ballot_sync(0xffffffffu, isR);
-    if (lane == 0) { s_w[warp] = __popc(bl); s_w[32 + warp] = __popc(br); }
-    __syncthreads();
-    int offL = nl, offR = nr, totL = 0, totR = 0;
-    for (int w = 0; w < nw; w++) {
-      const int cl = s_w[w], cr = s_w[32 + w];
-      if (w < warp) { offL += cl; offR += cr; }
-      totL += cl; totR += cr;
-    }
-    if (isL) Lp[offL + __popc(bl & lt)] = P(i);
-    if (isR) Ra[offR + __popc(br & lt)] = P(i);
-    nl += totL; nr += totR;
-    __syncthreads();
-  }
-  const int m2 = min(nl, nr);
-  int K = 0;
-  for (int k0 = 0; k0 < m2; k0 += nt) {
-    const int k = k0 + tid;
-    const bool pred = k < m2 && int(Lp[k]) < int(Ra[nr - 1 - k]);
-    const unsigned b = __ballot_sync(0xffffffffu, pred);
-    if (lane == 0) s_w[warp] = __popc(b);
-    __syncthreads();
-    int c = 0;
-    for (int w = 0; w < nw; w++) c += s_w[w];
-    K += c;
-    __syncthreads();
-    if (c != nt) break;   // monotone: the first chunk that is not full ends it (uniform)
-  }
-  for (int k = tid; k < K; k += nt) {
-    const int i = Lp[k], j = Ra[nr - 1 - k];
-    const uint32_t t = a[i]; a[i] = a[j]; a[j] = t;
-  }
-  __syncthreads();
-  return K;
-}
-
-template <int SHIFT, typename P>
-__device__ __forceinline__ void cta_nth_element_desc(uint32_t* __restrict__ a, int nth, int n, P* __restrict__ pos,
-                                                     int* __restrict__ s_w) {
-  const int tid = threadIdx.x;
-  if (n == 0 || nth == n) return;
-  int first = 0, last = n;
-  int depth_limit = lg2(n) * 2;
-  while (last - first > 3) {
-    if (depth_limit == 0) {
-      if (tid == 0) {
-        heap_select<SHIFT>(a + first, nth + 1 - first, last - first);
-        swap_u32(a[first], a[nth]);
-      }
-      __syncthreads();
-      return;
-    }
-    --depth_limit;
-    const int mid = first + (last - first) / 2;
-    if (tid == 0) {   // __move_median_to_first(first, first + 1, mid, last - 1)
-      const int x = first + 1, y = mid, z = last - 1;
-      const uint32_t ax = a[x], ay = a[y], az = a[z];
-      int with;
-      if (greater<SHIFT>(ax, ay)) {
-        if (greater<SHIFT>(ay, az)) with = y;
-        else if (greater<SHIFT>(ax, az)) with = z;
-        else with = x;
-      } else if (greater<SHIFT>(ax, az)) with = x;
-      else if (greater<SHIFT>(ay, az)) with = z;
-      else with = y;
-      swap_u32(a[first], a[with]);
-    }
-    __syncthreads();
-    const uint32_t p = a[first] >> SHIFT;
-    int nl, nr;
-    const int lo = first + 1, m = last - lo;
-    const int K = cta_two_sided<SHIFT, P>(
-        a, lo, last, [p](uint32_t r) { return !(r > p); }, [p](uint32_t r) { return !(p > r); }, pos, nl, nr, s_w);
-    int cut = 0x7fffffff;
-    if (K < nl) cut = min(cut, int(pos[K]));
-    if (K > 0) cut = min(cut, int(pos[m + nr - K]));   // R[K - 1]
-    __syncthreads();   // pos is rewritten by the next pass
-    if (cut <= nth) first = cut;
-    else last = cut;
-  }
-  if (tid == 0) {   // __insertion_sort(first, last) on at most three elements
-    for (int i = first + 1; i < last; ++i) {
-      const uint32_t val = a[i];
-      if (greater<SHIFT>(val, a[first])) {
-        for (int k = i; k > first; --k) a[k] = a[k - 1];
-        a[first] = val;
-      } else {
-        int l = i, next = i - 1;
-        while (greater<SHIFT>(val, a[next])) { a[l] = a[next]; l = next; --next; }
-        a[l] = val;
-      }
-    }
-  }
-  __syncthreads();
-}
-
-template <int SHIFT, typename P>
-__device__ __forceinline__ int cta_retain_best(uint32_t* __restrict__ a, int size, int n_points, P* __restrict__ pos,
-                                               int* __restrict__ s_w) {
-  if (!(n_points >= 0 && size > n_points)) return size;
-  if (n_points == 0) return 0;
-  cta_nth_element_desc<SHIFT, P>(a, n_points - 1, size, pos, s_w);
-  const uint32_t amb = a[n_points - 1] >> SHIFT;
-  int nl, nr;
-  cta_two_sided<SHIFT, P>(
-      a, n_points, size, [amb](uint32_t r) { return !(r >= amb); }, [amb](uint32_t r) { return r >= amb; }, pos, nl, nr, s_w);
-  return n_points + nr;
-}
-
 }  // namespace sdvlb_sel
