@@ -1,9 +1,10 @@
 // seq_api.cu — host side of the resident-sequence entry points and of the standalone FeatureAlign pose refinement
 // (include/sdvl_b200.h: sdvlb_seq_*, sdvlb_select_inliers, sdvlb_optimize_pose, sdvlb_rand_*).
 //
-// A tracked frame of n sequences is one submission of five kernels on the context's tracking stream
-// (apply-commands, prep, image_align, search, post) followed by the completion signal; nothing is copied to the device
-// except the mapping thread's commands (new points), and every result lands in pinned host memory by itself.
+// A tracked frame of n sequences is one submission of three kernels on the context's tracking stream (align -- which
+// first applies the mapping thread's queued commands --, search, post; each a programmatic dependent launch of the one
+// before; in ORB mode a small kernel first computes the descriptors of new map points); nothing is copied to the device
+// except those commands (new points), and every result lands in pinned host memory by itself.
 #include <algorithm>
 #include <cstring>
 #include <vector>
