@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 cp slam-sdvl_b200/libsdvl_b200.so /tmp/orig.so
 for v in "$@"; do
   cp slam-sdvl_b200/_variants/$v.so slam-sdvl_b200/libsdvl_b200.so
-  timeout 300 python bench.py --steps 40 --warmup 5 --no-extras > gpurun_out/r02_var_$v.json 2> gpurun_out/r02_var_$v.err
+  timeout 300 python bench.py --steps 40 --warmup 5 --no-extras $VARARGS > gpurun_out/r02_var_$v.json 2> gpurun_out/r02_var_$v.err
   python - <<PY
 import json
 d=json.load(open("gpurun_out/r02_var_$v.json"))

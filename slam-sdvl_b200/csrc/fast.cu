@@ -23,8 +23,9 @@ constexpr int DET_THREADS = DET_WARPS * 32;
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_SMEM_KEYS = 2048;   // level-wide retainBest runs in shared memory up to this many keypoints
 constexpr int SEL_PART_CELLS = 32;    // cells of one level per CTA of the selection kernel (4 per warp)
-constexpr int TSE = 40;               // score tile row stride in 16-bit elements
-constexpr int TSW = TSE / 2;          // ... in 32-bit words (one word = one horizontally adjacent pixel pair)
+constexpr int TSE = 40;               // score tile row stride in elements: one BYTE per pixel (a score is at most 254), so
+                                      // that a CTA needs 36.6 instead of 41.7 KB and six instead of five share an SM
+constexpr int TSH = TSE / 2;          // ... in 16-bit halves (one half = one horizontally adjacent pixel pair)
 // Pixel tile row stride in words: 45 = 13 (mod 32), so the 13 + 13 + 6 pairs of three consecutive tile rows that one warp
 // pass of a full cell touches fall into 32 distinct banks (a stride of 20 makes 6 of them collide).
 constexpr int PSW = 45;
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
                                                                  uint32_t* __restrict__ cell_kp,
                                                                  int32_t* __restrict__ cell_cnt) {
   __shared__ __align__(16) uint32_t s_tile[DET_WARPS][32 * PSW];
-  __shared__ __align__(16) uint32_t s_score[DET_WARPS][32 * TSW];
+  __shared__ __align__(16) uint16_t s_score[DET_WARPS][32 * TSH];
   __shared__ uint16_t s_list[DET_WARPS][LIST_CAP];
   __shared__ uint16_t s_cand[DET_WARPS][13 * 26 + 14];   // pixel pairs that pass the quick test, raster order
 
@@ -78,13 +79,13 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
   }
   const uint8_t* __restrict__ img = B.f[frame].pyr + A.g.off[level];
   uint32_t* const tile = s_tile[warp];
-  uint32_t* const score = s_score[warp];
+  uint16_t* const score = s_score[warp];
   uint16_t* const list = s_list[warp];
   uint16_t* const tile16 = reinterpret_cast<uint16_t*>(tile);
 
   // ---- stage the ROI as 16-bit pixels (element x + 1 of row y); scores start at zero
 #pragma unroll
-  for (int i = 0; i < (32 * TSW / 4) / 32; i++) reinterpret_cast<uint4*>(score)[i * 32 + lane] = make_uint4(0, 0, 0, 0);
+  for (int i = lane; i < 32 * TSH * 2 / 16; i += 32) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
   if (((initx & 3) == 0) && ((W & 3) == 0)) {
     const int wpr = (cols + 3) >> 2;                      // <= 8 words per row
     const int lr = lane >> 3, c4 = (lane & 7) * 4;        // 4 rows x 8 words per pass
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
     const int qp = active ? cand[t0 + lane] : 0;
     const int qq = qp >> 4, pp = qp & 15;
     const int y = 3 + qq, x = 3 + 2 * pp;
-    const int wi = y * TSW + 2 + pp;       // score word of the pair (elements x + 1, x + 2)
+    const int wi = y * TSH + 2 + pp;       // score half-word of the pair (elements x + 1, x + 2)
     const uint32_t* T = tile + y * PSW + 2 + pp;
     uint32_t r[16];
     {
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
     uint32_t sc = __vsub2(S, 0x00010001u) & __vcmpgts2(S, t2);
     if (x + 1 >= cols - 3) sc &= 0x0000FFFFu;   // second pixel of the pair is outside the tested columns
     if (!active) sc = 0;
-    if (active) score[wi] = sc;
+    if (active) score[wi] = uint16_t((sc & 0xFFu) | ((sc >> 16) << 8));
     // raster-ordered list of corners (score > 0)
     const bool c0 = (sc & 0xFFFFu) != 0, c1 = (sc >> 16) != 0;
     const uint32_t b0 = __ballot_sync(0xffffffffu, c0), b1 = __ballot_sync(0xffffffffu, c1);
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
   // ---- strict NMS against the 8 neighbours (non-corners are 0) for listed corners, raster-ordered compaction
   uint32_t* __restrict__ out = cell_kp + size_t(out_idx) * SDVLB_CELL_CAP;
   const int ox = initx - cj * SDVLB_CELL, oy = inity - ci * SDVLB_CELL;   // ROI origin relative to the cell origin
-  const uint16_t* sc16 = reinterpret_cast<const uint16_t*>(score);
+  const uint8_t* sc8 = reinterpret_cast<const uint8_t*>(score);
   int nout = 0;
   for (int i0 = 0; i0 < nlist; i0 += 32) {
     const int i = i0 + lane;
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
     if (i < nlist) {
       const int yx = list[i];
       y = yx >> 5; x = yx & 31;
-      const uint16_t* c = sc16 + y * TSE + x + 1;
+      const uint8_t* c = sc8 + y * TSE + x + 1;
       s = c[0];
       keep = s > c[-1] && s > c[1] && s > c[-TSE - 1] && s > c[-TSE] && s > c[-TSE + 1] && s > c[TSE - 1] &&
              s > c[TSE] && s > c[TSE + 1];

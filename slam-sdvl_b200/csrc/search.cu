@@ -14,6 +14,10 @@ namespace {
 
 constexpr int SE_WARPS = 4;
 constexpr int SE_THREADS = SE_WARPS * 32;
+// CTAs per SM the batch kernels are compiled for.  The kernels are latency-bound (30 % issue-active at 118 registers = 4
+// CTAs per SM); capping the registers at 85 costs ~230 bytes of spills per thread and still wins: 64 -> 59 (5 CTAs) ->
+// 55 (6) -> 57 us (8) per 64 sequences, +3 % frames/s for the whole step (A/B on one box, round 2).
+constexpr int SE_MIN_CTAS = 6;
 
 struct SearchArgs {
   PyrGeom g;
@@ -371,7 +375,7 @@ __device__ __forceinline__ void search_one(const SearchCandDev& C, const FrameDe
 
 // q_desc (kOrb): 8 words per candidate, feature->GetDescriptor() of the candidate's init feature.
 template <bool kOrb>
-__global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchCandDev* __restrict__ cands,
+__global__ void __launch_bounds__(SE_THREADS, SE_MIN_CTAS) search_points_kernel(const SearchCandDev* __restrict__ cands,
                                                                    const FrameDev* __restrict__ frames,
                                                                    sdvlb_match* __restrict__ out,
                                                                    const __grid_constant__ SearchArgs A,
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(SE_THREADS) search_points_kernel(const SearchC
 // SearchPoint arguments from the feature and its keyframe slot in shared memory, the match goes to the sequence's own
 // device state at the feature's index.
 template <bool kOrb>
-__global__ void __launch_bounds__(SE_THREADS) search_seq_kernel(const __grid_constant__ SeqStepArgs A) {
+__global__ void __launch_bounds__(SE_THREADS, SE_MIN_CTAS) search_seq_kernel(const __grid_constant__ SeqStepArgs A) {
   __shared__ uint8_t s_bp[SE_WARPS][104];
   __shared__ uint8_t s_patch[SE_WARPS][64];
   __shared__ SearchCandDev s_cand[SE_WARPS];
