@@ -69,6 +69,14 @@ void UpdateCandidate(const sdvlb_params& P, const std::shared_ptr<Frame>& cur, c
   ft->p2d.x = S->ref_px[0]; ft->p2d.y = S->ref_px[1];
   ft->v = V3(S->ref_v[0], S->ref_v[1], S->ref_v[2]);
   ft->level = S->ref_level;
+  if (UseOrb()) {   // the descriptor the candidate's init feature got at its keyframe (frame.cc:148-161, map.cc:319-323);
+                    // a feature outside ORBDetector::IsInsideLimits never gets one: the constructor's 32 zero bytes
+    static const OrbDetector det;
+    ft->descriptor.assign(32, 0);
+    const int lx = int(S->ref_px[0] / (1 << S->ref_level)), ly = int(S->ref_px[1] / (1 << S->ref_level));
+    if (det.IsInsideLimits(ref->pyramid[size_t(S->ref_level)], lx, ly))
+      det.GetDescriptor(ref->pyramid[size_t(S->ref_level)], lx, ly, ft->descriptor.data());
+  }
   S->depth = 0.0;
 
   // map.cc:426-437: pos = point->GetPosition(); frame->IsPointVisible(pos)

@@ -473,6 +473,14 @@ int ref_update_candidates(const sdvlb_params* P, const sdvlb_camera* cam_, const
     ref_set[ri] = 1;
     auto ft = std::make_shared<sdvl::Feature>(refs[ri], nullptr, Eigen::Vector2d(S.ref_px[0], S.ref_px[1]),
                                               Eigen::Vector3d(S.ref_v[0], S.ref_v[1], S.ref_v[2]), S.ref_level);
+    if (g_use_orb) {   // the descriptor the init feature got at its keyframe (frame.cc:148-161, map.cc:319-323)
+      const Eigen::Vector2i lp(int(S.ref_px[0] / (1 << S.ref_level)), int(S.ref_px[1] / (1 << S.ref_level)));
+      if (orb.IsInsideLimits(refs[ri]->GetPyramid()[S.ref_level], lp)) {
+        std::vector<uchar> d(32);
+        orb.GetDescriptor(refs[ri]->GetPyramid()[S.ref_level], lp, &d);
+        ft->SetDescriptor(d);
+      }
+    }
     auto pt = std::make_shared<sdvl::Point>();
     pt->feature_ = ft;
     pt->a_ = S.a; pt->b_ = S.b; pt->rho_ = S.rho; pt->sigma2_ = S.sigma2; pt->z_range_ = S.z_range;

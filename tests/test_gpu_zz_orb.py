@@ -203,3 +203,55 @@ def test_orb_trajectory_vs_reference(binding, sw, G, orb_oracle, name, seed, n, 
     assert do < 1e-4 and np.array_equal(so[:, 7], ref_stats[:, 6]), "oracle and golden disagree: regenerate tests/golden/ref_golden.npz"
     # the ORB mode really ran: its trajectory differs from the ZMSSD-mode one
     assert not np.array_equal(G["traj_%s_stats" % name], ref_stats)
+
+
+def test_orb_update_candidates_vs_oracle(binding, sw, scenes, abi, orb_oracle):
+    """Map::UpdateCandidates with Config::UseORB(): seed_update_kernel<true> recomputes every candidate's init-feature
+    descriptor from its keyframe and scores the epipolar SearchPoint by descriptor distance; statuses, depth-filter state
+    and matched positions against the oracle (pinned against the reference's own Map::UpdateCandidates in ORB mode,
+    tests/test_oracle_vs_ref.py::test_update_candidates_vs_reference[True])."""
+    O = orb_oracle
+    cfg, poses, imgs = sw.sequence("C2", 0, 13)
+    P, cam = cfg["params"], cfg["cam"]
+    xyl, _ = O.detect(P, imgs[0], P.num_features)
+    pts = scenes.seed_points(cfg, xyl, poses[0], one_per_cell=False, margin=0)
+    n = len(pts["px"])
+    assert n > 400
+    rng = np.random.default_rng(5)
+    s = np.zeros(n, abi.SEED_DT)
+    s["ref_T"] = np.asarray(poses[0])
+    s["ref_px"] = pts["px"]; s["ref_v"] = pts["v"]; s["ref_level"] = pts["level"]
+    s["rho"] = 1.0 / (pts["depth"] * (1.0 + rng.uniform(-0.1, 0.1, n)))
+    s["sigma2"] = 1.0; s["a"] = 10.0; s["b"] = 10.0; s["z_range"] = 6.0; s["cos_alpha"] = 1.0
+    s["last_distance"] = 1.0 / s["rho"]
+    depth_mean = float(np.median(pts["depth"]))
+    ctx = binding.Context(P, cam)
+    try:
+        ctx.set_orb(True)
+        ref = ctx.frame(imgs[0], corners=False)
+        so = s.copy()
+        so["ref_frame"] = 0
+        n_diff = n_cmp = n_upd = 0
+        worst_rho = worst_px = 0.0
+        for k in range(3, 13, 3):
+            cur = ctx.frame(imgs[k], corners=True)
+            sg = so.copy()
+            sg["ref_frame"] = ref.h
+            got = ctx.update_candidates(cur, poses[k], sg, depth_mean)
+            so = O.update_candidates(P, cam, imgs[k], poses[k], [imgs[0]], so, depth_mean)
+            same = got["status"] == so["status"]
+            n_diff += int((~same).sum()); n_cmp += n
+            upd = same & (so["status"] >= abi.SEED_UPDATED)
+            n_upd += int(upd.sum())
+            if upd.any():
+                worst_rho = max(worst_rho, float(np.max(np.abs(got["rho"][upd] - so["rho"][upd]) / np.abs(so["rho"][upd]))))
+            found = same & (so["status"] >= abi.SEED_NO_DEPTH)
+            if found.any():
+                worst_px = max(worst_px, float(np.abs(got["px"][found] - so["px"][found]).max()))
+            cur.destroy()
+        print(f"ORB UpdateCandidates: {n_diff} of {n_cmp} statuses differ, {n_upd} filter updates, rho {worst_rho:.2e}, px {worst_px:.2e}")
+        assert n_upd > 300
+        assert n_diff <= 0.002 * n_cmp and worst_rho < 1e-4 and worst_px <= 0.01
+        ref.destroy()
+    finally:
+        ctx.close()

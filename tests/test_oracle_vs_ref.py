@@ -444,46 +444,54 @@ def test_orb_mode_trajectory_vs_reference(O, sw, name, seed, n):
 
 # ------------------------------------------------------------------------------------------------ Map (mapping thread)
 @needs_ref
-def test_update_candidates_vs_reference(O, sw, scenes, abi):
+@pytest.mark.parametrize("orb", [False, True])
+def test_update_candidates_vs_reference(O, sw, scenes, abi, orb):
     """Map::UpdateCandidates run by the reference on its own candidates_ list: which candidates converge, which are
-    handed to DeletePoint (too old and out of view / too many failures), and the depth-filter state of every other."""
+    handed to DeletePoint (too old and out of view / too many failures), and the depth-filter state of every other.
+    orb: Config::UseORB() -- the epipolar SearchPoint is scored by the distance to the init feature's descriptor."""
     cfg, poses, imgs = sw.sequence("C2", 0, 25)
     P, cam = cfg["params"], cfg["cam"]
     with _both(O, True):
-        xyl, _ = O.detect(P, imgs[0], P.num_features)
-        pts = scenes.seed_points(cfg, xyl, poses[0], one_per_cell=True, margin=12)
-        n = len(pts["px"])
-        rng = np.random.default_rng(0)
-        s = np.zeros(n, abi.SEED_DT)
-        s["ref_frame"] = 0
-        s["ref_T"] = poses[0]
-        s["ref_px"] = pts["px"]; s["ref_v"] = pts["v"]; s["ref_level"] = pts["level"]
-        s["rho"] = 1.0 / (pts["depth"] * (1.0 + rng.uniform(-0.1, 0.1, n)))
-        s["sigma2"] = 1.0; s["a"] = 10.0; s["b"] = 10.0; s["z_range"] = 6.0; s["cos_alpha"] = 1.0
-        s["last_distance"] = 1.0 / s["rho"]
-        s["n_failed"] = rng.integers(0, 16, n)
-        s["last_kf_id"] = rng.integers(0, 10, n)
-        depth_mean = float(np.median(pts["depth"]))
-        so, sr = s.copy(), s.copy()
-        live = np.ones(n, bool)
-        seen = np.zeros(10, int)
-        for k in range(1, 25, 3):
-            so[live] = O.update_candidates(P, cam, imgs[k], poses[k], [imgs[0]], so[live], depth_mean, min_kf_id=5)
-            sr[live] = R.update_candidates(P, cam, imgs[k], poses[k], [imgs[0]], sr[live], depth_mean, min_kf_id=5)
-            seen += np.bincount(so["status"][live], minlength=10)
-            conv_o, conv_r = so["status"] == abi.SEED_CONVERGED, sr["status"] == abi.SEED_CONVERGED
-            del_o = np.isin(so["status"], (abi.SEED_DELETE_OLD, abi.SEED_DELETE_FAILED))
-            del_r = sr["status"] == abi.SEED_DELETE_OLD
-            assert np.array_equal(conv_o, conv_r) and np.array_equal(del_o, del_r)
-            assert np.array_equal(so["n_failed"][live], sr["n_failed"][live])
-            for f in ("rho", "sigma2", "a", "b", "cos_alpha", "last_distance"):
-                assert np.allclose(so[f][live], sr[f][live], rtol=1e-10, atol=0), f
-            if conv_o.any():
-                assert np.abs(so["p3d"][conv_o] - sr["p3d"][conv_o]).max() < 1e-12
-            live &= ~(conv_o | del_o)
+        O.lib().orc_set_orb(int(orb))
+        R.lib().ref_set_orb(int(orb))
+        try:
+            xyl, _ = O.detect(P, imgs[0], P.num_features)
+            pts = scenes.seed_points(cfg, xyl, poses[0], one_per_cell=True, margin=12)
+            n = len(pts["px"])
+            rng = np.random.default_rng(0)
+            s = np.zeros(n, abi.SEED_DT)
+            s["ref_frame"] = 0
+            s["ref_T"] = poses[0]
+            s["ref_px"] = pts["px"]; s["ref_v"] = pts["v"]; s["ref_level"] = pts["level"]
+            s["rho"] = 1.0 / (pts["depth"] * (1.0 + rng.uniform(-0.1, 0.1, n)))
+            s["sigma2"] = 1.0; s["a"] = 10.0; s["b"] = 10.0; s["z_range"] = 6.0; s["cos_alpha"] = 1.0
+            s["last_distance"] = 1.0 / s["rho"]
+            s["n_failed"] = rng.integers(0, 16, n)
+            s["last_kf_id"] = rng.integers(0, 10, n)
+            depth_mean = float(np.median(pts["depth"]))
+            so, sr = s.copy(), s.copy()
+            live = np.ones(n, bool)
+            seen = np.zeros(10, int)
+            for k in range(1, 25, 3):
+                so[live] = O.update_candidates(P, cam, imgs[k], poses[k], [imgs[0]], so[live], depth_mean, min_kf_id=5)
+                sr[live] = R.update_candidates(P, cam, imgs[k], poses[k], [imgs[0]], sr[live], depth_mean, min_kf_id=5)
+                seen += np.bincount(so["status"][live], minlength=10)
+                conv_o, conv_r = so["status"] == abi.SEED_CONVERGED, sr["status"] == abi.SEED_CONVERGED
+                del_o = np.isin(so["status"], (abi.SEED_DELETE_OLD, abi.SEED_DELETE_FAILED))
+                del_r = sr["status"] == abi.SEED_DELETE_OLD
+                assert np.array_equal(conv_o, conv_r) and np.array_equal(del_o, del_r)
+                assert np.array_equal(so["n_failed"][live], sr["n_failed"][live])
+                for f in ("rho", "sigma2", "a", "b", "cos_alpha", "last_distance"):
+                    assert np.allclose(so[f][live], sr[f][live], rtol=1e-10, atol=0), f
+                if conv_o.any():
+                    assert np.abs(so["p3d"][conv_o] - sr["p3d"][conv_o]).max() < 1e-12
+                live &= ~(conv_o | del_o)
+        finally:
+            O.lib().orc_set_orb(0)
+            R.lib().ref_set_orb(0)
     # the run exercised every branch the two lists can show
     for st in (abi.SEED_NOT_VISIBLE, abi.SEED_DELETE_OLD, abi.SEED_SHORT_BASELINE, abi.SEED_NOT_FOUND,
-               abi.SEED_DELETE_FAILED, abi.SEED_UPDATED, abi.SEED_CONVERGED):
+               abi.SEED_DELETE_FAILED, abi.SEED_UPDATED) + (() if orb else (abi.SEED_CONVERGED,)):
         assert seen[st] > 0, st
 
 
