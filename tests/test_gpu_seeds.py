@@ -190,15 +190,21 @@ def _init_seeds(cfg, abi, xyl, idx, T_new, handle, depth_mean):
     return s
 
 
-@pytest.mark.parametrize("name,seed", [("C2", 2), ("C3", 1)])
-def test_init_candidates_vs_oracle_and_host_map(binding, sw, scenes, abi, O, name, seed):
+@pytest.mark.parametrize("name,seed,orb", [("C2", 2, False), ("C3", 1, False), ("C2", 2, True)])
+def test_init_candidates_vs_oracle_and_host_map(binding, sw, scenes, abi, O, name, seed, orb):
     """The per-corner part of Map::InitCandidates (SDVLB_SEEDS_INIT) against the oracle, and the host mirror's
-    InitCandidates -> UpdateCandidates (every candidate listed twice, as the reference does) -> AddConnectionsPoints."""
+    InitCandidates -> UpdateCandidates (every candidate listed twice, as the reference does) -> AddConnectionsPoints.
+    orb: the same with Config::UseORB() (descriptors of the filtered corners saved into the new features, map.cc:319-323;
+    every SearchPoint scored by descriptor distance)."""
     cfg, poses, imgs = sw.sequence(name, seed, 28)
     P, cam = cfg["params"], cfg["cam"]
     k_old, k_new = 0, 9
     ctx = binding.Context(P, cam)
+    O.lib().orc_set_orb(int(orb))
+    binding.load_host().sdvlh_config_set_orb(int(orb))
     try:
+        if orb:
+            ctx.set_orb(True)
         kf_new = ctx.frame(imgs[k_new], corners=True)
         kf_old = ctx.frame(imgs[k_old], corners=True)
         xyl, _ = kf_new.corners()
@@ -259,3 +265,5 @@ def test_init_candidates_vs_oracle_and_host_map(binding, sw, scenes, abi, O, nam
         kf_new.destroy(); kf_old.destroy()
     finally:
         ctx.close()
+        O.lib().orc_set_orb(0)
+        binding.load_host().sdvlh_config_set_orb(0)
