@@ -198,7 +198,7 @@ int frame_alloc(sdvlb_ctx* c, sdvlb_frame** out) {
   c->pool.pop_back();
   f->has_corners = false; f->pyr_mirrored = false; f->corners_mirrored = -1; f->n_corners = 0;
   f->build_pending = false; f->build_corners = false; f->build_mirror = false;
-  f->build_desc = false; f->has_desc = false;
+  f->build_desc = false; f->has_desc = false; f->overflowed = false;
   f->built = nullptr;
   f->h_more.clear();
   *out = f;
@@ -288,6 +288,9 @@ void finalize_build(sdvlb_ctx* c, sdvlb_frame* f) {
   f->corners_mirrored = -1;
   if (f->build_corners && f->build_mirror) {
     memcpy(&f->n_corners, f->h_corners, sizeof(int32_t));
+    int32_t ovf = 0;
+    memcpy(&ovf, f->h_corners + sizeof(int32_t), sizeof(int32_t));   // header word 1: the frame's own overflow flag
+    f->overflowed = ovf != 0;
     f->corners_mirrored = std::min(f->n_corners, c->corner_copy);
     c->d2h_bytes += 16 + int64_t(f->corners_mirrored) * 16;
   }
@@ -304,6 +307,7 @@ int ensure_built(sdvlb_frame* f) {
   SDVLB_CUDA_TRY(cudaSetDevice(f->ctx->device));
   SDVLB_CUDA_TRY(cudaEventSynchronize(f->built));
   finalize_build(f->ctx, f);
+  if (f->overflowed) return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in this frame's FAST selection");
   return check_overflow(f->ctx);
 }
 
@@ -751,11 +755,12 @@ int collect_batch(sdvlb_ctx* c) {
   const BatchOut* res = reinterpret_cast<const BatchOut*>(out.h + P.o_res);
   const sdvlb_match* hm = reinterpret_cast<const sdvlb_match*>(out.h + P.o_match);
   int mo = 0;
-  bool first_align = true;
+  bool first_align = true, any_overflow = false;
   for (int i = 0; i < P.n; i++) {
     sdvlb_track_job& j = P.jobs[i];
     // the tracking stream ran after this frame's build (same stream, or ordered by its `built` event)
     if (P.build_frames || j.cur->build_pending) finalize_build(c, j.cur);
+    if (j.cur->overflowed) any_overflow = true;
     if (j.ref) {
       memcpy(j.T_cur, res[i].pose, sizeof(j.T_cur));
       j.n_tracked = res[i].info[0] / (c->params.align_patch_size * c->params.align_patch_size);
@@ -770,6 +775,7 @@ int collect_batch(sdvlb_ctx* c) {
     if (j.n_cands > 0) memcpy(j.matches, hm + mo, size_t(j.n_cands) * sizeof(sdvlb_match));
     mo += j.n_cands;
   }
+  if (any_overflow) return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in a frame's FAST selection");
   return 0;
 }
 

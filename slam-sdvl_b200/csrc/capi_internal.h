@@ -65,6 +65,7 @@ struct sdvlb_frame {
   bool build_desc = false;       // ORB mode: the build also writes the corner descriptors (FrameDev::desc)
   bool has_corners = false;
   bool has_desc = false;
+  bool overflowed = false;       // the frame's corner selection exceeded a capacity (its list is truncated)
   int corners_mirrored = -1;     // number of corners valid in the host mirror, -1 = not mirrored
   int n_corners = 0;
 };

@@ -130,7 +130,8 @@ struct FastArgs {
   int32_t* overflow_flag;   // pinned, device-visible: set when a fixed capacity was exceeded
   int part_off[SDVLB_MAX_LEVELS + 1];   // selection kernel: first CTA (part) of each level, [n_fast_levels] = total
 };
-#define SDVLB_TICKET_STRIDE 16   // ints of selection tickets per frame: [0] levels done, [1 + l] parts of level l done
+#define SDVLB_TICKET_STRIDE 16   // ints of selection tickets per frame: [0] levels done, [1 + l] parts of level l done,
+#define SDVLB_TICKET_OVERFLOW 12 //   [12] a capacity of the frame's selection was exceeded
 struct FastPlan {
   FastArgs args;
   int max_cells_level;

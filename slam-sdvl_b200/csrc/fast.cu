@@ -432,7 +432,12 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   uint16_t* const s_pos = reinterpret_cast<uint16_t*>(work + SEL_SMEM_KEYS * sizeof(uint32_t));
   const bool use_smem = total <= SEL_SMEM_KEYS;
   const bool fits = total <= A.level_cap[level];
-  if (!fits && tid == 0) *reinterpret_cast<volatile int32_t*>(A.overflow_flag) = 1;
+  // a capacity was exceeded: recorded per frame (it reaches the frame's pinned header, so the overflow is reported for
+  // THIS frame whichever call observes it first); frames built without a host mirror fall back to the context's flag
+  if (!fits && tid == 0) {
+    atomicExch(&tickets[frame * SDVLB_TICKET_STRIDE + SDVLB_TICKET_OVERFLOW], 1);
+    if (!B.f[blockIdx.y].host_mirror) *reinterpret_cast<volatile int32_t*>(A.overflow_flag) = 1;
+  }
 
   // ---- gather to the level list (fast_detector.cc:141-142): key = score<<22 | y<<11 | x (level coordinates)
   const int wc = A.g.wcells[level];
@@ -513,7 +518,10 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
     const int n = *reinterpret_cast<volatile int32_t*>(&level_cnt[frame * SDVLB_MAX_LEVELS + l]);
     const uint32_t* src = level_kp + size_t(frame) * A.level_kp_total + A.level_kp_off[l];
     if (base + n > A.corner_cap) {
-      if (tid == 0) *reinterpret_cast<volatile int32_t*>(A.overflow_flag) = 1;
+      if (tid == 0) {
+        atomicExch(&tickets[frame * SDVLB_TICKET_STRIDE + SDVLB_TICKET_OVERFLOW], 1);
+        if (!mirror) *reinterpret_cast<volatile int32_t*>(A.overflow_flag) = 1;
+      }
       break;
     }
     for (int i = tid; i < n; i += SEL_THREADS) {
@@ -530,7 +538,8 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(const __grid_c
   }
   if (tid == 0) {
     *fr.n_corners = base;
-    if (mirror) mirror[0] = make_int4(base, 0, 0, 0);
+    const int ovf = atomicExch(&tickets[frame * SDVLB_TICKET_STRIDE + SDVLB_TICKET_OVERFLOW], 0);   // also re-arms it
+    if (mirror) mirror[0] = make_int4(base, ovf, 0, 0);
     tickets[frame * SDVLB_TICKET_STRIDE] = 0;
   }
   __syncthreads();

@@ -470,6 +470,7 @@ int sdvlb_seq_track_collect(sdvlb_ctx* c, sdvlb_seq_result* results) {
     sdvlb_seq* s = sub.seqs[i];
     sdvlb_frame* f = sub.frames[i];
     if (f->build_pending) finalize_build(c, f);   // the tracking stream ran after this frame's build
+    if (f->overflowed) return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "corner capacity exceeded in a tracked frame's FAST selection");
     const SeqResultHost* R = reinterpret_cast<const SeqResultHost*>(s->h_result + size_t(sub.slot) * s->result_stride);
     if (R->error) return sdvlb_set_error(SDVLB_ERR_OVERFLOW, "a sequence exceeded its feature capacity (points were dropped)");
     sdvlb_seq_result& o = results[i];
