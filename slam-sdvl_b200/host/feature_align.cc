@@ -19,26 +19,20 @@ using std::vector;
 
 namespace sdvl {
 
-FeatureAlign::FeatureAlign(Map* map, Camera* camera, int max_matches) {   // :33-54
-  map_ = map;
-  cell_size_ = Config::CellSize();
-  max_matches_ = max_matches;
-  matches_ = 0;
-  num_attempts_ = 0;
-  relocalizing_ = false;
+FeatureAlign::FeatureAlign(Map* map, Camera* camera, int max_matches)   // :33-54
+    : map_(map), cell_size_(Config::CellSize()), max_matches_(max_matches), matches_(0), num_attempts_(0), relocalizing_(false) {
   grid_width_ = int(std::ceil(double(camera->GetWidth()) / cell_size_));
   grid_height_ = int(std::ceil(double(camera->GetHeight()) / cell_size_));
-  const int size = grid_width_ * grid_height_;
-  grid_.resize(size);
-  for (int i = 0; i < size; ++i) cell_order_.push_back(i);
+  grid_.resize(size_t(grid_width_) * grid_height_);
+  cell_order_.resize(grid_.size());
+  for (size_t i = 0; i < cell_order_.size(); ++i) cell_order_[i] = int(i);
   RandomShuffle(&cell_order_, &rng_);
 }
 
 FeatureAlign::~FeatureAlign() {}
 
 void FeatureAlign::ResetGrid() {   // :285-294
-  matches_ = 0;
-  num_attempts_ = 0;
+  matches_ = num_attempts_ = 0;
   for (auto& c : grid_) c.clear();
 }
 
@@ -50,26 +44,22 @@ void FeatureAlign::CollectCandidates(int frame_id, const shared_ptr<Frame>& last
   points->clear();
   if (descs) descs->clear();
   relocalizing_ = reloc;
-  vector<shared_ptr<Feature>>& features = last_frame->GetFeatures();
-  for (auto it_fts = features.begin(); it_fts != features.end(); it_fts++) {
-    if (*it_fts == nullptr) continue;
-    shared_ptr<Point> point = (*it_fts)->GetPoint();
-    if (!point || point->ToDelete()) continue;
-    if (frame_id == point->GetLastFrame()) continue;
-    shared_ptr<Feature> feature = point->GetInitFeature();
+  for (const shared_ptr<Feature>& seen : last_frame->GetFeatures()) {
+    if (!seen) continue;
+    const shared_ptr<Point> point = seen->GetPoint();
+    if (!point || point->ToDelete() || frame_id == point->GetLastFrame()) continue;
+    const shared_ptr<Feature> feature = point->GetInitFeature();
     sdvlb_candidate c;
-    if (feature) {
-      Matcher::FillCandidate(feature, point->GetInverseDepth(), point->GetStd(), point->IsFixed(), &c);
-    } else {   // never searched (feature_align.cc:120-122) but still binned by ProjectPoint: project only
-      Matcher::FillCandidate((*it_fts), point->GetInverseDepth(), point->GetStd(), point->IsFixed(), &c);
-    }
+    // without an init feature the point is never searched (feature_align.cc:120-122) but still binned by ProjectPoint:
+    // it goes to the device for the projection only, described by the feature that sees it
+    Matcher::FillCandidate(feature ? feature : seen, point->GetInverseDepth(), point->GetStd(), point->IsFixed(), &c);
     const Eigen::Vector3d pos = point->GetPosition();
     c.pos[0] = pos(0); c.pos[1] = pos(1); c.pos[2] = pos(2);
     c.flags |= SDVLB_CAND_PROJECT;
     cands->push_back(c);
     points->push_back(point);
     if (descs) {
-      const vector<unsigned char>& d = (feature ? feature : *it_fts)->GetDescriptor();
+      const vector<unsigned char>& d = (feature ? feature : seen)->GetDescriptor();
       descs->insert(descs->end(), d.begin(), d.end());
     }
     if (!reloc) point->SetLastFrame(frame_id);
@@ -79,8 +69,7 @@ void FeatureAlign::CollectCandidates(int frame_id, const shared_ptr<Frame>& last
 void FeatureAlign::ApplyMatches(const shared_ptr<Frame>& frame, const vector<shared_ptr<Point>>& points,
                                 const sdvlb_match* matches) {
   vector<shared_ptr<Feature>> fs_found;
-  inliers_.clear();
-  outliers_.clear();
+  inliers_.clear(); outliers_.clear();
 
   // ---- ProjectPoint bookkeeping (:323-339), in ProjectPoints order
   ResetGrid();
@@ -106,8 +95,7 @@ void FeatureAlign::ApplyMatches(const shared_ptr<Frame>& frame, const vector<sha
   };
 
   // ---- SelectPoints loop (:98-149)
-  matches_ = 0;
-  num_attempts_ = 0;
+  matches_ = num_attempts_ = 0;
   RandomShuffle(&cell_order_, &rng_);
   const int size = int(grid_.size());
   for (int i = 0; i < size && matches_ < max_matches_; i++) {
@@ -190,8 +178,7 @@ void AppendObservations(const vector<shared_ptr<Feature>>& fs, int flag, vector<
 // Splits `kept` by the flags the device wrote back.
 void SplitByFlag(const vector<shared_ptr<Feature>>& kept, const vector<sdvlb_pose_obs>& obs,
                  vector<shared_ptr<Feature>>* inliers, vector<shared_ptr<Feature>>* outliers) {
-  inliers->clear();
-  outliers->clear();
+  inliers->clear(); outliers->clear();
   for (size_t i = 0; i < kept.size(); i++)
     (obs[i].flags == SDVLB_OBS_INLIER ? inliers : outliers)->push_back(kept[i]);
 }
@@ -215,8 +202,7 @@ bool FeatureAlign::OptimizePose(const shared_ptr<Frame>& frame) {   // :73-82, o
 
 void FeatureAlign::SelectInliers(const shared_ptr<Frame>& frame, vector<shared_ptr<Feature>>& fs_found,
                                  vector<shared_ptr<Feature>>* inliers, vector<shared_ptr<Feature>>* outliers) {   // :152-216
-  inliers->clear();
-  outliers->clear();
+  inliers->clear(); outliers->clear();
   if (fs_found.empty()) return;
   vector<shared_ptr<Feature>> kept;
   vector<sdvlb_pose_obs> obs;
