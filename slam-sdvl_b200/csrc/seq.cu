@@ -28,8 +28,15 @@
 
 namespace {
 
-constexpr int PO_MAIN = 128;      // threads doing the FeatureAlign work (named barrier 1)
-constexpr int PO_THREADS = 160;   // + the shuffle warp
+// Main threads of the FeatureAlign kernel.  192 instead of the original 128: a frame has up to max_matches = 150
+// observations, which 128 threads took in two passes in every Gauss-Newton iteration of OptimizePose (and the rank /
+// SelectPoints loops over ~200 candidates in two); A/B on one box, three alternating runs each: kernel 95.8 -> 85.1 us
+// per 64 sequences, tracked frames/s 225 k -> 237 k (160 threads 88 us, 256 threads 89 us).
+#ifndef SDVLB_PO_MAIN
+#define SDVLB_PO_MAIN 192
+#endif
+constexpr int PO_MAIN = SDVLB_PO_MAIN;        // threads doing the FeatureAlign work (named barrier 1)
+constexpr int PO_THREADS = PO_MAIN + 32;      // + the shuffle warp
 constexpr int NVP = 28;           // A (21, upper triangle) + b (6) + chi2
 constexpr int RANSAC_MAX_PTS = 8;
 constexpr int HYP_MAX = 256;      // max_ransac_its supported
@@ -37,7 +44,7 @@ constexpr int HYP_MAX = 256;      // max_ransac_its supported
 constexpr double KMADNorm = 1.4826;            // feature_align.h
 constexpr double KTukeyC = 4.6851 * 4.6851;
 
-__device__ __forceinline__ void main_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void main_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PO_MAIN) : "memory"); }
 
 __device__ __forceinline__ void store_Rt(const DSE3& T, double* Rt) {
   double R[9];
@@ -359,7 +366,9 @@ __device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, 
     if (tid == 0)   // speculative draws of the batch; the stream is rewound to the reference's count below
       for (int h = h0; h < h1; h++) rs.rnd[h] = rand_next(rng);
     main_sync();
-    for (int k = lane * (PO_MAIN / 32) + warp; h0 + k < h1; k += PO_MAIN) {   // consecutive hypotheses on different warps
+    // consecutive hypotheses on different warps -- of the first four only, one per SM sub-partition: a hypothesis is a
+    // serial fp64 chain, and two warps of them on one scheduler take turns (14.3 -> 17.7 us with six warps)
+    for (int k = lane * 4 + warp; warp < 4 && h0 + k < h1; k += 128) {
       const int h = h0 + k;
       {
         DSE3 T;
@@ -569,7 +578,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   if (tid >= PO_MAIN) {
     // ---- shuffle warp: std::random_shuffle(cell_order_) for the NEXT frame (feature_align.cc:103), once SelectInliers
     // has taken its draws.  Waits on barrier 2 (all PO_THREADS threads).
-    asm volatile("bar.sync 2, 160;" ::: "memory");
+    asm volatile("bar.sync 2, %0;" ::"n"(PO_THREADS) : "memory");
     const int lane = tid - PO_MAIN;
     if (n_cells >= 64) {
       // The n_cells - 1 draws in one go.  rand() is r[n] = r[n-3] + r[n-31] (mod 2^32): the 30 values of a round only
@@ -791,7 +800,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   t_phase[6] = t_phase[7] = t_phase[2];
   select_inliers_cta(P, sh.T_frame, A.dp, &sh.rng, sh.rs, t_phase + 6);
   t_phase[3] = clock64();
-  asm volatile("bar.sync 2, 160;" ::: "memory");   // releases the shuffle warp: rand() is its from here on
+  asm volatile("bar.sync 2, %0;" ::"n"(PO_THREADS) : "memory");   // releases the shuffle warp: rand() is its from here on
 
   // ---- OptimizePose + RescueOutliers + OptimizePose (feature_align.cc:73-82)
   optimize_pose_cta(P, sh.T_frame, A.dp, sh.ps, part);
