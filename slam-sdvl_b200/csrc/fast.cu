@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
   // ---- scores: task t = (q, p) is the pixel pair x = 3 + 2p, x + 1 of row y = 3 + q
   const int np = (cols - 6 + 1) >> 1;     // pairs per row
   const int nq = rows - 6;                // tested rows
-  const int ntask = np * nq;
   const uint32_t t2 = uint32_t(A.threshold) * 0x00010001u;
   const uint32_t lt = (1u << lane) - 1u;
   // ---- quick test (cv::FAST's own early rejection, fast.cpp: opposite ring pixels): an arc of 9 contains ring pixel
@@ -139,32 +138,41 @@ __global__ void __launch_bounds__(DET_THREADS) fast_cells_kernel(const __grid_co
   // pass (15 % at level 0, 28 % at level 1 of the synthetic scenes) are compacted, in raster order, for full scoring.
   uint16_t* const cand = s_cand[warp];
   int ncand = 0;
-  const uint32_t rcp = (65536u + uint32_t(np) - 1u) / uint32_t(np);   // t / np == (t * rcp) >> 16 for t < 352, np <= 13
-  for (int t0 = 0; t0 < ntask; t0 += 64) {   // two pairs per lane and pass: their loads are in flight together
+  // Task = two horizontally adjacent pairs (a QUAD, pixels x .. x + 3) per lane: the six row words T[-2..3] serve the
+  // centre and the left / right ring pixels of both pairs (10 shared loads per quad instead of 14 for two separate
+  // pairs).  __vcmpgts2 / __vsub2 are 5- / 3-instruction emulations on sm_100a, hence the biased 32-bit form below.
+  const int nq4 = (np + 1) >> 1;          // quads per row (<= 7); the last one may hold a single pair
+  const int ntask4 = nq4 * nq;
+  const uint32_t rcp4 = (65536u + uint32_t(nq4) - 1u) / uint32_t(nq4);   // t / nq4 == (t * rcp4) >> 16 for t < 182
+  const uint32_t kq = 0x80008000u - (uint32_t(A.threshold) + 1u) * 0x00010001u;
+  for (int t0 = 0; t0 < ntask4; t0 += 32) {
+    const int t = t0 + lane;
+    const bool active = t < ntask4;
+    const uint32_t tt = active ? uint32_t(t) : 0u;
+    const int qq = int((tt * rcp4) >> 16), pp = 2 * (int(tt) - qq * nq4);
+    const uint32_t* T = tile + (3 + qq) * PSW + 2 + pp;
+    const uint32_t u0 = T[3 * PSW], u1 = T[3 * PSW + 1], d0 = T[-3 * PSW], d1 = T[-3 * PSW + 1];
+    const uint32_t m2 = T[-2], m1 = T[-1], c0 = T[0], c1 = T[1], p2 = T[2], p3 = T[3];
     bool pass[2];
-    int code[2];
 #pragma unroll
     for (int hh = 0; hh < 2; hh++) {
-      const int t = t0 + 32 * hh + lane;
-      const bool active = t < ntask;
-      const uint32_t tt = active ? uint32_t(t) : 0u;
-      const int qq = int((tt * rcp) >> 16), pp = int(tt) - qq * np;
-      const uint32_t* T = tile + (3 + qq) * PSW + 2 + pp;
-      const uint32_t r0 = T[3 * PSW], r8 = T[-3 * PSW];
-      const uint32_t r4 = mid_pair(T[1], T[2]), r12 = mid_pair(T[-2], T[-1]);
-      const uint32_t v2 = T[0];
+      const uint32_t r0 = hh ? u1 : u0, r8 = hh ? d1 : d0, v2 = hh ? c1 : c0;
+      const uint32_t r4 = hh ? mid_pair(p2, p3) : mid_pair(c1, p2), r12 = hh ? mid_pair(m1, c0) : mid_pair(m2, m1);
       const uint32_t br = __vmins2(__vmaxs2(r0, r8), __vmaxs2(r4, r12));
       const uint32_t dk = __vmaxs2(__vmins2(r0, r8), __vmins2(r4, r12));
-      const uint32_t hit = __vcmpgts2(br, __vadd2(v2, t2)) | __vcmpgts2(__vsub2(v2, t2), dk);
-      pass[hh] = active && hit != 0;
-      code[hh] = (qq << 4) | pp;
+      // br > v + t  <=>  br - v - (t + 1) >= 0;   v - t > dk  <=>  v - dk - (t + 1) >= 0.  Both lanes of a register at
+      // once with ONE plain 32-bit add each: biased by 0x8000 a lane stays within 0x8000 +- 600, so no borrow crosses
+      // into the upper lane and bit 15 of a lane is the outcome.
+      const uint32_t ge = (br + kq - v2) | (v2 + kq - dk);
+      pass[hh] = active && (ge & 0x80008000u) != 0;
     }
-#pragma unroll
-    for (int hh = 0; hh < 2; hh++) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, pass[hh]);
-      if (pass[hh]) cand[ncand + __popc(bal & lt)] = uint16_t(code[hh]);
-      ncand += __popc(bal);
-    }
+    pass[1] = pass[1] && pp + 1 < np;
+    const uint32_t b0 = __ballot_sync(0xffffffffu, pass[0]), b1 = __ballot_sync(0xffffffffu, pass[1]);
+    int pos = ncand + __popc(b0 & lt) + __popc(b1 & lt);
+    const int code = (qq << 4) | pp;
+    if (pass[0]) cand[pos++] = uint16_t(code);
+    if (pass[1]) cand[pos] = uint16_t(code + 1);
+    ncand += __popc(b0) + __popc(b1);
   }
   __syncwarp();
   int nlist = 0;
