@@ -579,7 +579,9 @@ def main():
     (val_sec, val_wall, est_v, stats_v, cnt_v, _, _), val_all = repeated(dev.data_ptr(), IMG_DEVICE, groups)
     clock_info = clocks.stop()
     # ---- kernel pass: one context so launches do not overlap, per-kernel CUDA events on the launching stream
-    k_sec, _, est_k, stats_k, _, ktimes, _ = timed_run(dev.data_ptr(), IMG_DEVICE, 1, timing=True, pipelined=False)
+    # (a submission takes at most 64 sequences: more than that are split over contexts that run one after the other)
+    k_sec, _, est_k, stats_k, _, ktimes, _ = timed_run(dev.data_ptr(), IMG_DEVICE, (S + 63) // 64, timing=True, pipelined=False,
+                                                       n_threads=1)
     assert np.array_equal(est_k, est_v), "pipelined and lock-step runs must be the same computation"
     assert np.array_equal(est_e, est_v), "host-resident and HBM-resident runs must be the same computation"
     total_frames = S_total * K

@@ -10,8 +10,10 @@
 //
 //   upload_kernel   : level 0 of a whole frame batch from device-visible memory (pinned host memory over PCIe, or
 //                     device memory) in one launch.
-//   pyr_down_kernel : one level -> next level for a frame batch, 8 outputs per thread straight from global memory
-//                     (the 5 source rows of neighbouring outputs overlap in L1).
+//   pyr_down_roll_kernel : one level -> next level for a frame batch in separable form with a rolling window of
+//                     horizontal sums (round 2): a thread owns 8 output columns and walks down 4 or 8 output rows.
+//   pyr_down_kernel : the direct form (10 IDP.4A per output, 8 outputs of one row per thread); rows that are not
+//                     word-aligned, shared-memory sources (pyr_tail_kernel) and the SDVLB_PYR_DIRECT comparison knob.
 //   pyr_tail_kernel : all remaining levels once a level and its successor fit in shared memory, one CTA per frame
 //                     (levels 2..4 of a 752x480 frame from level 1: one launch instead of three).
 #include <cstdlib>
@@ -98,6 +100,9 @@ __device__ __forceinline__ uint8_t down1(const uint8_t* __restrict__ src, int st
 }
 
 constexpr int PD_THREADS = 256;
+#ifndef SDVLB_PYR_ROWS_DEFAULT
+#define SDVLB_PYR_ROWS_DEFAULT 0   // 0: by level size; 4 / 8: forced (experiments)
+#endif
 
 __global__ void __launch_bounds__(PD_THREADS) pyr_down_kernel(const __grid_constant__ FrameBatch B, int src_off, int sw,
                                                               int sh, int dst_off, int dw, int dh) {
@@ -114,6 +119,102 @@ __global__ void __launch_bounds__(PD_THREADS) pyr_down_kernel(const __grid_const
   } else {
     for (int k = 0; k < 8; k++)
       if (x0 + k < dw) dst[size_t(y) * dw + x0 + k] = down1(src, sw, sw, sh, y, x0 + k);
+  }
+}
+
+// ---- separable form with a rolling window (round 2) -------------------------------------------------------------------
+// The 25-tap sum is separable in exact integer arithmetic: h(s, x) = sum_j k_j src(s, 2x+j-2) <= 16 * 255 per source row
+// s, dst(y, x) = (h(2y-2) + 4 h(2y-1) + 6 h(2y) + 4 h(2y+1) + h(2y+2) + 128) >> 8 <= 65408 >> 8.  A thread owns 8
+// adjacent output columns and walks down PR output rows: every step loads TWO new source rows (one 16-byte load plus
+// the word on either side), forms their 8 horizontal sums with IDP.4A (2 per sum) packed as 16-bit pairs, and combines
+// the five live rows with plain 32-bit adds on the pairs (a lane never exceeds 16 bits, so no carry crosses) -- ~10
+// instead of ~70 instructions per output of the direct form, which recomputes every horizontal sum 2.5 times and
+// clamps the address of each of its 30 loads.
+// Borders cost nothing per row: a word outside the row is not loaded (it reads as 0) and the reflected taps are folded
+// into the IDP.4A coefficients of the one thread they concern -- columns -2, -1 <- 2, 1 turn (6,4,1,0) on the first
+// word of the row into (6,8,2,0) (coef_e0), column sw <- sw - 2 turns (1,4,6,4) on the last word into (1,4,7,4) for the
+// last output of the row (coef_o[j]).
+template <int ALIGN>
+struct RawRow { uint32_t w[6]; };   // w[k] = columns cm - 4 + 4k .. + 3
+
+template <int ALIGN>
+__device__ __forceinline__ RawRow<ALIGN> load_row8(const uint8_t* __restrict__ p, int cm, int sw) {
+  RawRow<ALIGN> r;
+  r.w[0] = cm > 0 ? __ldg(reinterpret_cast<const uint32_t*>(p + cm - 4)) : 0u;
+  if (ALIGN == 16) {   // sw % 16 == 0: the four middle words always lie inside the row
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + cm));
+    r.w[1] = v.x; r.w[2] = v.y; r.w[3] = v.z; r.w[4] = v.w;
+  } else if (ALIGN == 8) {
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(p + cm));
+    uint2 b = make_uint2(0u, 0u);
+    if (cm + 16 <= sw) b = __ldg(reinterpret_cast<const uint2*>(p + cm + 8));
+    r.w[1] = a.x; r.w[2] = a.y; r.w[3] = b.x; r.w[4] = b.y;
+  } else {
+#pragma unroll
+    for (int k = 1; k < 5; k++)
+      r.w[k] = cm + 4 * k <= sw ? __ldg(reinterpret_cast<const uint32_t*>(p + cm + 4 * k - 4)) : 0u;
+  }
+  r.w[5] = cm + 20 <= sw ? __ldg(reinterpret_cast<const uint32_t*>(p + cm + 16)) : 0u;
+  return r;
+}
+
+template <int ALIGN>
+__device__ __forceinline__ void hsum8(const RawRow<ALIGN>& r, uint32_t coef_e0, const uint32_t coef_o[4], uint32_t h[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint32_t e = __dp4a(r.w[j + 1], j == 0 ? coef_e0 : 0x00010406u, __dp4a(r.w[j], 0x04010000u, 0u));
+    const uint32_t o = __dp4a(r.w[j + 2], 0x00000001u, __dp4a(r.w[j + 1], coef_o[j], 0u));
+    h[j] = e + (o << 16);
+  }
+}
+
+template <int ALIGN, int PR>   // PR output rows per thread: 2 * PR + 3 source rows are summed for them
+__global__ void __launch_bounds__(PD_THREADS) pyr_down_roll_kernel(const __grid_constant__ FrameBatch B, int src_off, int sw,
+                                                                   int sh, int dst_off, int dw, int dh) {
+  uint8_t* const pyr = B.f[blockIdx.y].pyr;
+  const uint8_t* __restrict__ src = pyr + src_off;
+  uint8_t* __restrict__ dst = pyr + dst_off;
+  const int gpr = (dw + 7) >> 3;                       // groups of 8 outputs per row
+  const int task = blockIdx.x * PD_THREADS + threadIdx.x;
+  const int rb = task / gpr;
+  const int y0 = rb * PR, x0 = (task - rb * gpr) * 8;
+  if (y0 >= dh) return;
+  const int cm = 2 * x0;                               // column of the first middle word
+  const bool words_ok = (dw & 3) == 0;
+  const uint32_t coef_e0 = cm == 0 ? 0x00020806u : 0x00010406u;
+  uint32_t coef_o[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) coef_o[j] = x0 + 2 * j + 1 == dw - 1 ? 0x04070401u : 0x04060401u;
+  // rows beyond the image (a last, partial block of rows) are clamped: loaded, summed, not stored
+  auto row = [&](int s) { return src + size_t(reflect101(min(s, sh), sh)) * sw; };
+  uint32_t ha[4], hb[4], hc[4], hd[4], he[4];
+  {
+    const RawRow<ALIGN> ra = load_row8<ALIGN>(row(2 * y0 - 2), cm, sw), rb_ = load_row8<ALIGN>(row(2 * y0 - 1), cm, sw),
+                        rc = load_row8<ALIGN>(row(2 * y0), cm, sw);
+    hsum8<ALIGN>(ra, coef_e0, coef_o, ha);
+    hsum8<ALIGN>(rb_, coef_e0, coef_o, hb);
+    hsum8<ALIGN>(rc, coef_e0, coef_o, hc);
+  }
+  RawRow<ALIGN> nd = load_row8<ALIGN>(row(2 * y0 + 1), cm, sw), ne = load_row8<ALIGN>(row(2 * y0 + 2), cm, sw);
+#pragma unroll
+  for (int r = 0; r < PR; r++) {
+    const int y = y0 + r;
+    const RawRow<ALIGN> cd = nd, ce = ne;
+    if (r + 1 < PR) {   // the next step's rows are in flight while this step is summed
+      nd = load_row8<ALIGN>(row(2 * y + 3), cm, sw);
+      ne = load_row8<ALIGN>(row(2 * y + 4), cm, sw);
+    }
+    hsum8<ALIGN>(cd, coef_e0, coef_o, hd);
+    hsum8<ALIGN>(ce, coef_e0, coef_o, he);
+    uint32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = ha[j] + he[j] + 0x00800080u + 4u * (hb[j] + hd[j]) + 6u * hc[j];
+    uint2 out;
+    out.x = __byte_perm(v[0], v[1], 0x7531);           // bits 8..15 of every 16-bit lane
+    out.y = __byte_perm(v[2], v[3], 0x7531);
+    if (y < dh) store8(dst + size_t(y) * dw, x0, dw, out, words_ok);
+#pragma unroll
+    for (int j = 0; j < 4; j++) { ha[j] = hc[j]; hb[j] = hd[j]; hc[j] = he[j]; }
   }
 }
 
@@ -385,7 +486,27 @@ cudaError_t sdvlb_launch_pyramid(const FrameBatch& B, const PyrGeom& g, cudaStre
   size_t smem = 0;
   const int tail_src = tail_source_level(g, &smem);
   const int direct_to = tail_src > 0 ? tail_src : g.levels - 1;   // levels 1..direct_to by pyr_down_kernel
+  static const bool direct = getenv("SDVLB_PYR_DIRECT") != nullptr;   // comparison knob: the round-1 direct-form kernel
+  static const int rows_per_thread = getenv("SDVLB_PYR_ROWS") ? atoi(getenv("SDVLB_PYR_ROWS")) : SDVLB_PYR_ROWS_DEFAULT;
   for (int l = 1; l <= direct_to; l++) {
+    const int sw = g.w[l - 1];
+    if ((sw & 3) == 0 && !direct) {   // word-aligned rows (level offsets are 256-byte aligned): rolling separable form
+#define SDVLB_ROLL(AL, R)                                                                                            \
+  do {                                                                                                               \
+    const int tasks = ((g.w[l] + 7) >> 3) * ((g.h[l] + R - 1) / R);                                                  \
+    dim3 grid((tasks + PD_THREADS - 1) / PD_THREADS, B.n);                                                           \
+    SDVLB_PREPARE((pyr_down_roll_kernel<AL, R>), 0);                                                                 \
+    pyr_down_roll_kernel<AL, R><<<grid, PD_THREADS, 0, stream>>>(B, g.off[l - 1], sw, g.h[l - 1], g.off[l], g.w[l], g.h[l]); \
+  } while (0)
+      // 8 rows per thread sum 19 source rows for 8 output rows, 4 rows 11 for 4 (+16 % work) but twice the threads: the
+      // small levels are latency-bound and take the latter (A/B on B200: 33.3 / 32.0 us per 64 frames with 8 / 4 everywhere)
+      const int rpt = rows_per_thread ? rows_per_thread : (g.h[l] >= 200 ? 8 : 4);
+      if ((sw & 15) == 0) { if (rpt == 8) SDVLB_ROLL(16, 8); else SDVLB_ROLL(16, 4); }
+      else if ((sw & 7) == 0) { if (rpt == 8) SDVLB_ROLL(8, 8); else SDVLB_ROLL(8, 4); }
+      else { if (rpt == 8) SDVLB_ROLL(4, 8); else SDVLB_ROLL(4, 4); }
+#undef SDVLB_ROLL
+      continue;
+    }
     const int tasks = ((g.w[l] + 7) >> 3) * g.h[l];
     dim3 grid((tasks + PD_THREADS - 1) / PD_THREADS, B.n);
     SDVLB_PREPARE(pyr_down_kernel, 0);
