@@ -253,22 +253,22 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_tail_kernel(const __grid_const
     const int dst_st = (dw + 3) & ~3;
     uint8_t* __restrict__ gdst = pyr + G.off[l];
     const bool last = (l + 1 == G.levels);
-    const int gpr = (dw + 7) >> 3;
-    for (int task = tid; task < gpr * dh; task += PT_THREADS) {
-      const int y = task / gpr, x0 = (task - y * gpr) * 8;
-      uint2 v;
-      if ((sw & 3) == 0) {
-        v = down8<false>(s_a, sst, sw, sh, y, x0);
-      } else {                                         // odd-sized source: byte taps
-        v.x = v.y = 0;
-        for (int k = 0; k < 8; k++)
-          if (x0 + k < dw) {
-            const uint32_t px = down1(s_a, sst, sw, sh, y, x0 + k);
-            if (k < 4) v.x |= px << (8 * k); else v.y |= px << (8 * (k - 4));
-          }
+    if ((sw & 3) == 0) {
+      const int gpr = (dw + 7) >> 3;
+      for (int task = tid; task < gpr * dh; task += PT_THREADS) {
+        const int y = task / gpr, x0 = (task - y * gpr) * 8;
+        const uint2 v = down8<false>(s_a, sst, sw, sh, y, x0);
+        store8(gdst + size_t(y) * dw, x0, dw, v, (dw & 3) == 0);
+        if (!last) store8(s_b + size_t(y) * dst_st, x0, dst_st, v, true);   // padding columns are never used as taps
       }
-      store8(gdst + size_t(y) * dw, x0, dw, v, (dw & 3) == 0);
-      if (!last) store8(s_b + size_t(y) * dst_st, x0, dst_st, v, true);   // padding columns are never used as taps
+    } else {   // odd-sized source (94 -> 47 of a 752-wide frame): byte taps, ONE output per thread -- these levels are
+               // tiny, so the step lasts as long as its longest thread (8 outputs per thread: 180 busy threads of 1024)
+      for (int i = tid; i < dw * dh; i += PT_THREADS) {
+        const int y = i / dw, x = i - y * dw;
+        const uint8_t px = down1(s_a, sst, sw, sh, y, x);
+        gdst[size_t(y) * dw + x] = px;
+        if (!last) s_b[size_t(y) * dst_st + x] = px;
+      }
     }
     __syncthreads();
     uint8_t* t = s_a; s_a = s_b; s_b = t;
