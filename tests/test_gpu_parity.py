@@ -37,7 +37,10 @@ def test_pyramid_random_and_odd_sizes(binding, abi, O):
     # whose tail levels run from shared memory and sizes too large for that
     for (w, h, levels) in [(101, 99, 3), (94, 60, 2), (47, 30, 2), (640, 480, 5), (333, 250, 4), (752, 480, 5),
                            (376, 240, 4), (188, 120, 3), (72, 40, 3), (20, 16, 2), (1920, 1080, 5), (1284, 724, 5),
-                           (2048, 2048, 4)]:
+                           (2048, 2048, 4),
+                           # rolling separable kernel: rows aligned to 8 / 4 bytes only, with 8 and 4 output rows per thread,
+                           # partial row blocks, partial column groups, destination rows that are not word-aligned
+                           (1000, 450, 3), (1096, 808, 3), (1284, 402, 2), (100, 36, 2), (136, 100, 2), (24, 410, 2)]:
         p = abi.default_params()
         p.pyramid_levels = levels
         p.max_align_level = levels - 1
