@@ -73,7 +73,7 @@ def ncu_summary_path():
 
 
 NCU_SUMMARY = ncu_summary_path()
-NCU_KERNELS = {"pyr_down_kernel": "pyramid", "pyr_tail_kernel": "pyramid", "fast_cells_kernel": "fast",
+NCU_KERNELS = {"pyr_down_kernel": "pyramid", "pyr_down_roll_kernel": "pyramid", "pyr_tail_kernel": "pyramid", "fast_cells_kernel": "fast",
                "fast_select_kernel": "select", "seq_align_kernel": "align", "image_align_kernel": "align",
                "search_seq_kernel": "search", "seq_post_kernel": "pose", "orb_frames_kernel": "orb"}
 NCU_SEQS_PER_LAUNCH = 64
@@ -91,7 +91,8 @@ def ncu_traffic_per_launch(kernel, seqs):
     with open(NCU_SUMMARY) as f:
         for line in f:
             if line.startswith("## "):
-                name, grid = line[3:].split()[0], line[line.index("grid"):].strip()
+                name, grid = line[3:line.index("grid")].strip(), line[line.index("grid"):].strip()
+                name = name.removeprefix("void ").split("<")[0]          # template kernels: "void name<args>"
                 cur = (name, grid) if NCU_KERNELS.get(name) == kernel else None
                 if cur:
                     per.setdefault(cur, []).append(0.0)

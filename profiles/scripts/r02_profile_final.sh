@@ -13,7 +13,7 @@ timeout 400 python bench.py --orb --steps 40 --warmup 5 --no-extras > gpurun_out
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_${TAG}_bench_reference.json 2> gpurun_out/r02_${TAG}_bench_reference.err; echo "reference rc=$?"
 B="python bench.py --steps 2 --warmup 3 --groups 1 --threads 1 --repeats 1 --no-extras"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_r02$TAG.csv $B > gpurun_out/ncu_launch_r02$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"upload|pyr_|fast_cells|fast_select|seq_align|search_seq|seq_post" -s 30 -c 18 -o gpurun_out/prof_r02$TAG $B > gpurun_out/ncu_full_r02$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"upload|pyr_|fast_cells|fast_select|seq_align|search_seq|seq_post" -s 30 -c 20 -o gpurun_out/prof_r02$TAG $B > gpurun_out/ncu_full_r02$TAG.log 2>&1
 ls -la gpurun_out/*.ncu-rep | tail -3
 for f in gpurun_out/r02_${TAG}_bench_*.json; do python - <<PY
 import json
