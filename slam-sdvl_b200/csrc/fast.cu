@@ -26,9 +26,12 @@ constexpr int SEL_PART_CELLS = 32;    // cells of one level per CTA of the selec
 constexpr int TSE = 40;               // score tile row stride in elements: one BYTE per pixel (a score is at most 254), so
                                       // that a CTA needs 36.6 instead of 41.7 KB and six instead of five share an SM
 constexpr int TSH = TSE / 2;          // ... in 16-bit halves (one half = one horizontally adjacent pixel pair)
-// Pixel tile row stride in words: 45 = 13 (mod 32), so the 13 + 13 + 6 pairs of three consecutive tile rows that one warp
-// pass of a full cell touches fall into 32 distinct banks (a stride of 20 makes 6 of them collide).
-constexpr int PSW = 45;
+// Pixel tile row stride in words.  A row holds 34 pixels = 18 words with the reach of the ring; 23 is the smallest odd
+// stride at which the quads of four consecutive tile rows that one warp pass of the quick test touches spread best
+// over the banks (1.67 wavefronts per load; 45, the stride of the pair-per-lane quick test, gives 2.0) -- and, what
+// matters more, a CTA then needs 25.3 instead of 36.6 KB, so eight instead of six share an SM: 68.2 -> 64.5 us per
+// 64 frames (stride 39, same banks, six CTAs: 68.0).
+constexpr int PSW = 23;
 constexpr int PSE = 2 * PSW;
 constexpr int LIST_CAP = 26 * 26 + 28;
 
