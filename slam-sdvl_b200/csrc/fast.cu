@@ -30,7 +30,8 @@ constexpr int TSH = TSE / 2;          // ... in 16-bit halves (one half = one ho
 // stride at which the quads of four consecutive tile rows that one warp pass of the quick test touches spread best
 // over the banks (1.67 wavefronts per load; 45, the stride of the pair-per-lane quick test, gives 2.0) -- and, what
 // matters more, a CTA then needs 25.3 instead of 36.6 KB, so eight instead of six share an SM: 68.2 -> 64.5 us per
-// 64 frames (stride 39, same banks, six CTAs: 68.0).
+// 64 frames (stride 39, same banks, six CTAs: 68.0).  Ten CTAs per SM (candidates aliased into the tail of the corner
+// list, score rows of 32 bytes, 48 registers) measured 64.2: not kept.
 constexpr int PSW = 23;
 constexpr int PSE = 2 * PSW;
 constexpr int LIST_CAP = 26 * 26 + 28;
