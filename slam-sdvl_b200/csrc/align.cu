@@ -189,8 +189,10 @@ __device__ __forceinline__ void align_carve(unsigned char* mem, int cap, AlignSm
   s.d = reinterpret_cast<double*>(mem);
   s.f = reinterpret_cast<float*>(s.d + size_t(ND) * cap);
   s.flag = reinterpret_cast<uint8_t*>(s.f + size_t(cap) * PF);
-  uintptr_t p = (reinterpret_cast<uintptr_t>(s.flag + cap) + 15) & ~uintptr_t(15);
-  s.wred = reinterpret_cast<double*>(p);
+  // (offset arithmetic on `mem`, which is 16-byte aligned -- a pointer -> integer -> pointer round trip would hide from
+  // the compiler that everything below lives in shared memory, and every access would become a generic LD / ST)
+  const size_t off = (size_t(cap) * (ND * 8 + PF * 4 + 1) + 15) & ~size_t(15);
+  s.wred = reinterpret_cast<double*>(mem + off);
   s.hred = s.wred + AL_WARPS * 8;
   s.hcor = s.hred + AL_WARPS * 21;
   s.Hall = s.hcor + AL_WARPS * 21;
