@@ -162,7 +162,7 @@ struct PoseShared {
 
 // FeatureAlign::ConvergePose (feature_align.cc:341-421) over the observations whose flag == sel, by the PO_MAIN main
 // threads.  The result is left in sh.T; returns false (uniformly) when no observation is selected.
-__device__ bool converge_pose_cta(const PoseProblem& P, int sel, const double* T_init, const DevParams& dp,
+__device__ __forceinline__ bool converge_pose_cta(const PoseProblem& P, int sel, const double* T_init, const DevParams& dp,
                                   PoseShared& sh, double (*part)[PO_MAIN]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   DSE3 T, last_T;
@@ -327,18 +327,25 @@ __device__ __forceinline__ bool converge_pose_small(const PoseProblem& P, int ba
 
 struct RansacShared {
   sdvlb_rand backup;         // the stream before the speculative draws
-  double (*hRt)[12];         // [R] pose of every hypothesis as rotation + translation   } carved from dynamic shared
-  int* hsup;                 // [R] supporters                                            } memory by ransac_carve()
-  int* hconv;                // [R] ConvergePose returned true
-  int* rnd;                  // [R] speculative draws
   int best, it, nits, best_supporters, more;
 };
+// The per-hypothesis arrays, carved from dynamic shared memory.  Every thread derives the pointers itself (registers):
+// read back from a structure in memory they would be opaque to the compiler and every access through them a generic
+// LD / ST instead of LDS / STS (the same holds for the observation arrays and the per-cell arrays below).
+struct RansacArrays {
+  double (*hRt)[12];         // [R] pose of every hypothesis as rotation + translation
+  int* hsup;                 // [R] supporters
+  int* hconv;                // [R] ConvergePose returned true
+  int* rnd;                  // [R] speculative draws
+};
 __host__ __device__ inline size_t ransac_bytes(int R) { return size_t(R) * (12 * sizeof(double) + 3 * sizeof(int)); }
-__device__ inline void ransac_carve(RansacShared& rs, unsigned char* mem, int R) {   // mem 8-byte aligned
-  rs.hRt = reinterpret_cast<double (*)[12]>(mem);
-  rs.hsup = reinterpret_cast<int*>(mem + size_t(R) * 12 * sizeof(double));
-  rs.hconv = rs.hsup + R;
-  rs.rnd = rs.hconv + R;
+__device__ __forceinline__ RansacArrays ransac_carve(unsigned char* mem, int R) {   // mem 8-byte aligned
+  RansacArrays ra;
+  ra.hRt = reinterpret_cast<double (*)[12]>(mem);
+  ra.hsup = reinterpret_cast<int*>(mem + size_t(R) * 12 * sizeof(double));
+  ra.hconv = ra.hsup + R;
+  ra.rnd = ra.hconv + R;
+  return ra;
 }
 
 // FeatureAlign::SelectInliers (feature_align.cc:152-216) over P (= fs_found): flags every observation INLIER/OUTLIER.
@@ -346,8 +353,9 @@ __device__ inline void ransac_carve(RansacShared& rs, unsigned char* mem, int R)
 //
 // Hypotheses h0..h1 of a batch are spread over the four warps (hypothesis h0 + k on warp k % 4): a warp waits for its
 // slowest Gauss-Newton loop, so the first, small batch -- the one that usually settles the loop -- has two per warp.
-__device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, const DevParams& dp, sdvlb_rand* rng,
-                                   RansacShared& rs, long long* stamps = nullptr) {
+__device__ __forceinline__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, const DevParams& dp,
+                                                   sdvlb_rand* rng, RansacShared& rs, const RansacArrays ra,
+                                                   long long* stamps = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int size = P.n;
   if (size == 0) return;
@@ -364,7 +372,7 @@ __device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, 
   while (h0 < R) {
     const int h1 = min(R, h0 == 0 ? 8 : (h0 == 8 ? 32 : R));
     if (tid == 0)   // speculative draws of the batch; the stream is rewound to the reference's count below
-      for (int h = h0; h < h1; h++) rs.rnd[h] = rand_next(rng);
+      for (int h = h0; h < h1; h++) ra.rnd[h] = rand_next(rng);
     main_sync();
     // consecutive hypotheses on different warps -- of the first four only, one per SM sub-partition: a hypothesis is a
     // serial fp64 chain, and two warps of them on one scheduler take turns (14.3 -> 17.7 us with six warps)
@@ -372,14 +380,14 @@ __device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, 
       const int h = h0 + k;
       {
         DSE3 T;
-        const bool ok = np == 5 ? converge_pose_small<5>(P, rs.rnd[h] % size, np, size, se3_load(T_frame), dp, &T)
-                                : converge_pose_small<0>(P, rs.rnd[h] % size, np, size, se3_load(T_frame), dp, &T);
-        rs.hconv[h] = ok ? 1 : 0;
-        rs.hsup[h] = 0;
+        const bool ok = np == 5 ? converge_pose_small<5>(P, ra.rnd[h] % size, np, size, se3_load(T_frame), dp, &T)
+                                : converge_pose_small<0>(P, ra.rnd[h] % size, np, size, se3_load(T_frame), dp, &T);
+        ra.hconv[h] = ok ? 1 : 0;
+        ra.hsup[h] = 0;
         double Rt[12];
         store_Rt(T, Rt);
 #pragma unroll
-        for (int q = 0; q < 12; q++) rs.hRt[h][q] = Rt[q];
+        for (int q = 0; q < 12; q++) ra.hRt[h][q] = Rt[q];
       }
     }
     main_sync();
@@ -389,9 +397,9 @@ __device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, 
     for (int i0 = 0; i0 < size; i0 += PO_MAIN) {
       const int i = i0 + tid;
       for (int h = h0; h < h1; h++) {
-        const bool in = i < size && within_threshold(rs.hRt[h], P, i, thr);
+        const bool in = i < size && within_threshold(ra.hRt[h], P, i, thr);
         const unsigned bal = __ballot_sync(0xffffffffu, in);
-        if (lane == 0 && bal) atomicAdd(&rs.hsup[h], __popc(bal));   // integer adds: order does not matter
+        if (lane == 0 && bal) atomicAdd(&ra.hsup[h], __popc(bal));   // integer adds: order does not matter
       }
     }
     main_sync();
@@ -399,9 +407,9 @@ __device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, 
       const double sprob = 0.99;
       int nits = rs.nits, it = rs.it, best_supporters = rs.best_supporters, best = rs.best;
       while (it < nits && it < h1) {
-        if (rs.hconv[it] && rs.hsup[it] > best_supporters) {
+        if (ra.hconv[it] && ra.hsup[it] > best_supporters) {
           best = it;
-          best_supporters = rs.hsup[it];
+          best_supporters = ra.hsup[it];
           const double epsilon = 1.0 - (double(best_supporters) / double(size));
           double tmp = 1.0 - epsilon;
           for (int k = 1; k < np; k++) tmp *= tmp;
@@ -427,7 +435,7 @@ __device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, 
   double Rt[12];
   if (rs.best >= 0) {
 #pragma unroll
-    for (int k = 0; k < 12; k++) Rt[k] = rs.hRt[rs.best][k];
+    for (int k = 0; k < 12; k++) Rt[k] = ra.hRt[rs.best][k];
   } else {
 #pragma unroll
     for (int k = 0; k < 12; k++) Rt[k] = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0;
@@ -443,7 +451,7 @@ __device__ void select_inliers_cta(const PoseProblem& P, const double* T_frame, 
 
 // Re-partition after a pose change: observations flagged `from` whose error at sh.Rt exceeds / is within thr.
 // Returns (uniformly) how many changed list.
-__device__ int recheck_cta(const PoseProblem& P, const double* Rt, int from, bool move_if_within, double thr, int to,
+__device__ __forceinline__ int recheck_cta(const PoseProblem& P, const double* Rt, int from, bool move_if_within, double thr, int to,
                            PoseShared& sh) {
   const int tid = threadIdx.x;
   if (tid == 0) sh.ctrl[2] = 0;
@@ -464,7 +472,7 @@ __device__ int recheck_cta(const PoseProblem& P, const double* Rt, int from, boo
 
 // FeatureAlign::OptimizePose(frame) without RemoveOutliers (feature_align.cc:73-82,218-243).  T_frame (shared, 7
 // doubles) holds frame->GetPose() on entry and the refined pose on return.
-__device__ void optimize_pose_cta(const PoseProblem& P, double* T_frame, const DevParams& dp, PoseShared& sh,
+__device__ __forceinline__ void optimize_pose_cta(const PoseProblem& P, double* T_frame, const DevParams& dp, PoseShared& sh,
                                   double (*part)[PO_MAIN]) {
   const int tid = threadIdx.x;
   const double thr = dp.p.inlier_error_threshold / dp.cam.fx;
@@ -509,7 +517,7 @@ __device__ __forceinline__ void signal_done(const SeqStepArgs& A) {
 // iteration of every RANSAC hypothesis re-reads them.
 constexpr int OBS_SMEM_MAX = 256;
 __host__ __device__ inline size_t obs_smem_bytes(int cap) { return size_t(cap) * (7 * sizeof(double) + sizeof(int32_t)); }
-__device__ inline void obs_carve(unsigned char* mem, int cap, PoseProblem& P) {   // mem 8-byte aligned
+__device__ __forceinline__ void obs_carve(unsigned char* mem, int cap, PoseProblem& P) {   // mem 8-byte aligned
   double* d = reinterpret_cast<double*>(mem);
   P.o_a = d; P.o_pos = d + 2 * size_t(cap); P.o_scale = d + 5 * size_t(cap); P.o_err = d + 6 * size_t(cap);
   P.o_flag = reinterpret_cast<int32_t*>(d + 7 * size_t(cap));
@@ -520,16 +528,15 @@ struct PostShared {
   RansacShared rs;
   double T_frame[7];
   sdvlb_rand rng;
-  int* win;                    // [n_cells] per cell: rank of its match (INT_MAX: none)          } dynamic shared
-  int* slot;                   // [n_cells] index of its match in fs_found, -1: not visited     } memory
-  int* order;                  // [n_cells] cell_order_
-  int* head;                   // [n_cells] first candidate of the cell's chain, -1: empty
   int scan[PO_MAIN];
   int attempts, n_found, n_inl, n_outl;
   int adopt;
   int kf_live[SDVLB_SEQ_KF_CAP];
 };
 
+// kObsSmem: max_matches <= OBS_SMEM_MAX, the observation arrays are carved from shared memory (a compile-time fact, so
+// that the accesses are LDS / STS; chosen at run time the pointers would be generic).
+template <bool kObsSmem>
 __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_constant__ SeqStepArgs A) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   const long long t_entry = clock64();
@@ -551,20 +558,19 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     }
     return;
   }
-  if (tid == 0) {             // small shared memory on purpose: this CTA must fit beside the build stream's kernels
-    unsigned char* mem = reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN;
-    ransac_carve(sh.rs, mem, A.dp.p.max_ransac_its);
-    mem += (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16;
-    sh.win = reinterpret_cast<int*>(mem);
-    sh.slot = sh.win + n_cells;
-    sh.order = sh.slot + n_cells;
-    sh.head = sh.order + n_cells;
-  }
-  __syncthreads();
+  // small shared memory on purpose: this CTA must fit beside the build stream's kernels.  Every thread derives the
+  // array pointers itself (see RansacArrays)
+  unsigned char* const mem0 = reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN;
+  const RansacArrays ra = ransac_carve(mem0, A.dp.p.max_ransac_its);
+  int* const p_win = reinterpret_cast<int*>(mem0 + (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16);
+  int* const p_slot = p_win + n_cells;     // [n_cells] index of its match in fs_found, -1: not visited
+  int* const p_order = p_slot + n_cells;   // [n_cells] cell_order_
+  int* const p_head = p_order + n_cells;   // [n_cells] first candidate of the cell's chain, -1: empty
+                                           // p_win: [n_cells] per cell: rank of its match (INT_MAX: none)
 
   // ---- load the persistent FeatureAlign state (all PO_THREADS threads)
   for (int i = tid; i < n_cells; i += PO_THREADS) {
-    sh.order[i] = S->cell_order[i]; sh.win[i] = INT_MAX; sh.slot[i] = -1; sh.head[i] = -1;
+    p_order[i] = S->cell_order[i]; p_win[i] = INT_MAX; p_slot[i] = -1; p_head[i] = -1;
   }
   if (tid < 34) sh.rng.r[tid] = S->rng.r[tid];
   if (tid == 0) {
@@ -585,7 +591,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
       // need values of earlier rounds through the lag-31 term, so a round is three interleaved prefix sums (stride 3)
       // of known terms -- four shuffle steps instead of 30 dependent updates.  seq[] = the last 34 values in
       // chronological order, then the new ones; it lives in win/slot, idle since SelectPoints.
-      uint32_t* seq = reinterpret_cast<uint32_t*>(sh.win);
+      uint32_t* seq = reinterpret_cast<uint32_t*>(p_win);
       const int nd = n_cells - 1, n0 = sh.rng.n;
       for (int k = lane; k < 34; k += 32) seq[k] = sh.rng.r[(n0 - 34 + k) % 34];
       __syncwarp();
@@ -610,24 +616,24 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
 #pragma unroll 4
         for (int i = 1; i < n_cells; ++i) {
           const int j = int(seq[34 + i - 1]);
-          const int a = sh.order[i], b = sh.order[j];
-          sh.order[i] = b; sh.order[j] = a;
+          const int a = p_order[i], b = p_order[j];
+          p_order[i] = b; p_order[j] = a;
         }
       }
       __syncwarp();
-      for (int i = lane; i < n_cells; i += 32) S->cell_order[i] = sh.order[i];
+      for (int i = lane; i < n_cells; i += 32) S->cell_order[i] = p_order[i];
       if (lane == 0) Rz->phase_cycles[7] = int(clock64() - t_entry);
       return;
     }
     if (tid == PO_MAIN) {
       for (int i = 1; i < n_cells; ++i) {
         const int j = rand_next(&sh.rng) % (i + 1);
-        const int a = sh.order[i], b = sh.order[j];
-        sh.order[i] = b; sh.order[j] = a;
+        const int a = p_order[i], b = p_order[j];
+        p_order[i] = b; p_order[j] = a;
       }
     }
     __syncwarp();
-    for (int i = lane; i < n_cells; i += 32) S->cell_order[i] = sh.order[i];
+    for (int i = lane; i < n_cells; i += 32) S->cell_order[i] = p_order[i];
     for (int i = lane; i < 34; i += 32) S->rng.r[i] = sh.rng.r[i];
     if (lane == 0) { S->rng.n = sh.rng.n; Rz->phase_cycles[7] = int(clock64() - t_entry); }
     return;
@@ -662,7 +668,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     }
     c_cell[i] = cell;
     c_score[i] = ft.n_successful;
-    if (cell >= 0) c_next[i] = atomicExch(&sh.head[cell], i);   // chain order is arbitrary; ranks do not depend on it
+    if (cell >= 0) c_next[i] = atomicExch(&p_head[cell], i);   // chain order is arbitrary; ranks do not depend on it
   }
   main_sync();
   // ---- rank inside the cell: Score() descending, stable (std::list::sort, feature_align.cc:111)
@@ -671,12 +677,12 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     if (cell < 0) { c_rank[i] = -1; continue; }
     const int sc = c_score[i];
     int rank = 0;
-    for (int j = sh.head[cell]; j >= 0; j = c_next[j]) {
+    for (int j = p_head[cell]; j >= 0; j = c_next[j]) {
       const int sj = c_score[j];
       rank += (sj > sc || (sj == sc && j < i)) ? 1 : 0;
     }
     c_rank[i] = rank;
-    if (M[i].status == SDVLB_MATCH_FOUND) atomicMin(&sh.win[cell], rank);
+    if (M[i].status == SDVLB_MATCH_FOUND) atomicMin(&p_win[cell], rank);
   }
   main_sync();
   t_phase[1] = clock64();
@@ -685,7 +691,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     const int per = (n_cells + PO_MAIN - 1) / PO_MAIN;
     const int q0 = tid * per, q1 = min(n_cells, q0 + per);
     int local = 0;
-    for (int q = q0; q < q1; q++) local += sh.win[sh.order[q]] != INT_MAX ? 1 : 0;
+    for (int q = q0; q < q1; q++) local += p_win[p_order[q]] != INT_MAX ? 1 : 0;
     // exclusive scan over the PO_MAIN per-thread counts: shuffles inside a warp, then the warp totals
     int incl = local;
 #pragma unroll
@@ -707,10 +713,10 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     main_sync();
     const int max_matches = A.dp.p.max_matches;
     for (int q = q0; q < q1; q++) {
-      const int c = sh.order[q];
-      const bool has = sh.win[c] != INT_MAX;
+      const int c = p_order[q];
+      const bool has = p_win[c] != INT_MAX;
       // the loop `for (i < size && matches_ < max_matches_)` visits this cell iff fewer than max_matches so far
-      if (pre < max_matches) sh.slot[c] = has ? pre : -2;   // -2: visited, no match
+      if (pre < max_matches) p_slot[c] = has ? pre : -2;   // -2: visited, no match
       pre += has ? 1 : 0;
     }
   }
@@ -718,9 +724,8 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   const int n_found = sh.n_found;
   PoseProblem P;
   const int obs_cap = min(OBS_SMEM_MAX, (A.dp.p.max_matches + 7) & ~7);
-  if (A.dp.p.max_matches <= OBS_SMEM_MAX) {
-    obs_carve(reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN +
-                  (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16 + ((size_t(4 * n_cells) * sizeof(int) + 15) / 16) * 16,
+  if constexpr (kObsSmem) {
+    obs_carve(mem0 + (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16 + ((size_t(4 * n_cells) * sizeof(int) + 15) / 16) * 16,
               obs_cap, P);
   } else {
     P.o_a = S->o_a; P.o_pos = S->o_pos; P.o_scale = S->o_scale; P.o_err = S->o_err; P.o_flag = S->o_flag;
@@ -732,9 +737,9 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     for (int i = tid; i < nc; i += PO_MAIN) {
       const int cell = c_cell[i];
       if (cell < 0) continue;
-      const int slot = sh.slot[cell];
+      const int slot = p_slot[cell];
       if (slot == -1) continue;                       // cell never visited
-      const int rank = c_rank[i], win = sh.win[cell];
+      const int rank = c_rank[i], win = p_win[cell];
       if (rank > win) continue;                       // the cell was left at its first match
       my_attempts++;
       if (rank == win && slot >= 0) {                 // found: Promote, new Feature(frame, px, level)
@@ -782,9 +787,9 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
     for (int i = tid; i < nc; i += PO_MAIN) {
       const int cell = c_cell[i];
       if (cell < 0) continue;
-      const int slot = sh.slot[cell];
+      const int slot = p_slot[cell];
       if (slot == -1) continue;
-      const int rank = c_rank[i], win = sh.win[cell];
+      const int rank = c_rank[i], win = p_win[cell];
       if (rank > win) continue;
       SeqFeat& f = L[i];
       if (rank == win && slot >= 0) { f.n_successful += 1; f.n_failed = 0; }
@@ -798,7 +803,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) seq_post_kernel(const __grid_co
   // ---- SelectInliers (RANSAC)
   t_phase[2] = clock64();
   t_phase[6] = t_phase[7] = t_phase[2];
-  select_inliers_cta(P, sh.T_frame, A.dp, &sh.rng, sh.rs, t_phase + 6);
+  select_inliers_cta(P, sh.T_frame, A.dp, &sh.rng, sh.rs, ra, t_phase + 6);
   t_phase[3] = clock64();
   asm volatile("bar.sync 2, %0;" ::"n"(PO_THREADS) : "memory");   // releases the shuffle warp: rand() is its from here on
 
@@ -905,8 +910,8 @@ __global__ void __launch_bounds__(PO_MAIN, 1) pose_call_kernel(const __grid_cons
   PoseCallShared& sh = *reinterpret_cast<PoseCallShared*>(s_raw);
   double (*part)[PO_MAIN] = reinterpret_cast<double (*)[PO_MAIN]>(s_raw + ((sizeof(PoseCallShared) + 15) / 16) * 16);
   const int tid = threadIdx.x;
-  if (tid == 0)
-    ransac_carve(sh.rs, reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN, A.dp.p.max_ransac_its);
+  const RansacArrays ra =
+      ransac_carve(reinterpret_cast<unsigned char*>(&part[0][0]) + sizeof(double) * NVP * PO_MAIN, A.dp.p.max_ransac_its);
   PoseProblem P;
   P.n = A.n;
   if (A.n <= OBS_SMEM_MAX) {
@@ -932,7 +937,7 @@ __global__ void __launch_bounds__(PO_MAIN, 1) pose_call_kernel(const __grid_cons
   }
   main_sync();
   if (A.mode == 0) {
-    select_inliers_cta(P, sh.T_frame, A.dp, &sh.rng, sh.rs);
+    select_inliers_cta(P, sh.T_frame, A.dp, &sh.rng, sh.rs, ra);
     if (tid < 34) A.rng->r[tid] = sh.rng.r[tid];
     if (tid == 0) A.rng->n = sh.rng.n;
   } else {
@@ -960,8 +965,12 @@ cudaError_t sdvlb_launch_seq_post(const SeqStepArgs& A, cudaStream_t stream) {
   const size_t dyn = ((sizeof(PostShared) + 15) / 16) * 16 + sizeof(double) * NVP * PO_MAIN +
                      (ransac_bytes(A.dp.p.max_ransac_its) + 15) / 16 * 16 + ((size_t(4 * n_cells) * sizeof(int) + 15) / 16) * 16 +
                      obs_smem_bytes(obs_cap);
-  SDVLB_PREPARE(seq_post_kernel, dyn);
-  return sdvlb_launch_dependent(seq_post_kernel, dim3(A.n), dim3(PO_THREADS), dyn, stream, A);
+  if (obs_cap > 0) {
+    SDVLB_PREPARE(seq_post_kernel<true>, dyn);
+    return sdvlb_launch_dependent(seq_post_kernel<true>, dim3(A.n), dim3(PO_THREADS), dyn, stream, A);
+  }
+  SDVLB_PREPARE(seq_post_kernel<false>, dyn);
+  return sdvlb_launch_dependent(seq_post_kernel<false>, dim3(A.n), dim3(PO_THREADS), dyn, stream, A);
 }
 
 cudaError_t sdvlb_launch_pose_call(const PoseCallArgs& A, cudaStream_t stream) {
