@@ -503,7 +503,9 @@ __global__ void __launch_bounds__(128) seq_apply_kernel(const SeqCmd* __restrict
 // the host; the last one publishes the submission's sequence number in the pinned completion word.
 __device__ __forceinline__ void signal_done(const SeqStepArgs& A) {
   if (!A.h_flag) return;
-  __threadfence_system();
+  // release at GPU scope; the last CTA's system fence below is cumulative over everything that happened before the
+  // arrivals it has observed, i.e. over the result writes of every CTA of the submission
+  __threadfence();
   const unsigned arrived = atomicAdd(A.d_done, 1u) + 1u;
   if (arrived == unsigned(A.n)) {
     *A.d_done = 0u;
