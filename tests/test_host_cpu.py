@@ -204,3 +204,19 @@ def test_bench_reference_arm_contract(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "4", "--warmup", "3"],
                        capture_output=True, text=True, timeout=600, env=env, cwd=str(tmp_path))
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_rolling_pyramid_model_matches_the_oracle(O):
+    """The separable rolling-window form of pyr_down_roll_kernel (its numpy model, profiles/scripts/pyr_roll_model.py:
+    horizontal sums as 16-bit pairs, borders folded into the dot-product coefficients, 4 / 8 output rows per thread)
+    against the oracle's cv::pyrDown restatement, for every row alignment the kernel is instantiated for."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pyr_roll_model", os.path.join(ROOT, "profiles", "scripts", "pyr_roll_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rng = np.random.default_rng(11)
+    for (w, h) in [(64, 24), (40, 26), (44, 18), (24, 50), (20, 10)]:   # rows aligned to 16 / 8 / 4 / 8 / 4 bytes
+        for img in (rng.integers(0, 256, (h, w), dtype=np.uint8), np.full((h, w), 255, np.uint8)):
+            ref = O.pyramid(img, 2)[1]
+            for rows_per_thread in (4, 8):
+                assert np.array_equal(m.rolling(img, rows_per_thread), ref), f"{w}x{h}, {rows_per_thread} rows per thread"
