@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(PD_THREADS) pyr_down_kernel(const __grid_const
 // s, dst(y, x) = (h(2y-2) + 4 h(2y-1) + 6 h(2y) + 4 h(2y+1) + h(2y+2) + 128) >> 8 <= 65408 >> 8.  A thread owns 8
 // adjacent output columns and walks down PR output rows: every step loads TWO new source rows (one 16-byte load plus
 // the word on either side), forms their 8 horizontal sums with IDP.4A (2 per sum) packed as 16-bit pairs, and combines
-// the five live rows with plain 32-bit adds on the pairs (a lane never exceeds 16 bits, so no carry crosses) -- ~10
+// the five live rows with plain 32-bit adds on the pairs (a lane never exceeds 16 bits, so no carry crosses) -- ~16
 // instead of ~70 instructions per output of the direct form, which recomputes every horizontal sum 2.5 times and
 // clamps the address of each of its 30 loads.
 // Borders cost nothing per row: a word outside the row is not loaded (it reads as 0) and the reflected taps are folded
