@@ -220,3 +220,21 @@ def test_rolling_pyramid_model_matches_the_oracle(O):
             ref = O.pyramid(img, 2)[1]
             for rows_per_thread in (4, 8):
                 assert np.array_equal(m.rolling(img, rows_per_thread), ref), f"{w}x{h}, {rows_per_thread} rows per thread"
+
+
+def test_bench_reads_dram_traffic_of_every_kernel_from_the_ncu_summary():
+    """roofline.traffic comes from the committed `ncu --set full` summary: every bench key must resolve, including the
+    kernels ncu prints as `void name<args>` (templates) and keys made of several launches (pyramid)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    assert os.path.exists(bench.NCU_SUMMARY), "no ncu summary under profiles/"
+    for key in ("pyramid", "fast", "select", "align", "search", "pose"):
+        t = bench.ncu_traffic_per_launch(key, 64)
+        assert t is not None and t > 0, key
+    assert bench.ncu_traffic_per_launch("pyramid", 32) == pytest.approx(bench.ncu_traffic_per_launch("pyramid", 64) / 2)
